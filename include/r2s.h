@@ -1,0 +1,103 @@
+/*
+ * r2s.h -- C ABI of libr2s.so, the B200 (sm_100a) implementation of the rho2sdf grid-sampling hot path.
+ *
+ * The reference (kopacja/rho2sdf.jl) has no FFI seam of its own: the drop-in boundary is the Julia
+ * function seam.  Each entry point below replaces the body of one reference function; the Julia wrapper
+ * (rho2sdf.jl_b200/julia/Rho2sdfB200.jl) keeps the reference signatures and `ccall`s these.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; r2s_last_error() gives the message
+ *     (the Julia wrapper turns it into error(msg), mirroring the reference's error(...) calls)
+ *   - arrays are Julia's: column-major, X = 3 x nnp (double), IEN = nen x nel (int64, 1-BASED node ids),
+ *     grid point linear id = k*(N1+1)*(N2+1) + j*(N1+1) + i with i fastest (src/MeshGrid/Grid.jl:84-90)
+ *   - all pointer arguments are HOST pointers unless the name ends in _dev; the caller owns every buffer,
+ *     the library never keeps a host pointer after the call returns; device memory belongs to the context
+ *   - calls are synchronous; a context is not re-entrant; one context drives one GPU (one process per GPU)
+ *   - there is no CPU fallback: without a CUDA device every call fails with an error
+ */
+#ifndef R2S_H
+#define R2S_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r2s_ctx r2s_ctx;
+
+/* hidden constants of the reference made explicit; r2s_default_params() fills the reference values */
+typedef struct r2s_params {
+  double rho_t;                 /* threshold density (RhoToSDF.jl:151-156)                               */
+  double delta_factor;          /* band half width in cells, 1.1 (sdfOnDensityField.jl:158)              */
+  int32_t remove_artifacts;     /* RhoToSDF.jl:174                                                        */
+  double artifact_threshold;    /* 0.0 (RhoToSDF.jl:195)                                                  */
+  double artifact_min_ratio;    /* 0.01 (RhoToSDF.jl:27)                                                  */
+  int32_t rbf_interp;           /* 1 = interpolation (CG solve), 0 = approximation (RhoToSDF.jl:25)       */
+  int32_t smooth;               /* 1 = :same, 2 = :fine (RhoToSDF.jl:222)                                 */
+  double rbf_cut;               /* 1e-3 (RBFs4Smoothing.jl:328)                                           */
+  double target_volume;         /* V_frac * V_domain (RBFs4Smoothing.jl:267)                              */
+  int32_t final_volume;         /* 1 = also evaluate calculate_volume_from_sdf on the fine grid (:373)    */
+} r2s_params;
+
+typedef struct r2s_report {
+  int64_t n_solid, n_crossing, n_active, n_pairs, n_not_converged, n_newton_iters;
+  int64_t n_flipped;            /* remove_sdf_artifacts! return value                                     */
+  int32_t cg_iters, bisections;
+  float th, volume;             /* LS_Threshold offset and final fine-grid volume                          */
+  float ms_bin, ms_project, ms_assemble, ms_sign, ms_cc, ms_rbf_prep, ms_cg, ms_lsf, ms_threshold, ms_fine, ms_volume, ms_total;
+  int64_t launches;             /* kernels launched by the last call                                       */
+} r2s_report;
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for a private stream */
+int r2s_create(r2s_ctx **ctx, int device, void *stream);
+void r2s_destroy(r2s_ctx *ctx);
+const char *r2s_last_error(r2s_ctx *ctx);
+void r2s_default_params(r2s_params *p);
+int r2s_last_report(r2s_ctx *ctx, r2s_report *rep);
+
+/* ---- Mesh{T} container: replaces MeshGrid.Mesh ctor data (src/MeshGrid/MeshInformations.jl:36-67) --------- */
+/* nen = 8 (HEX8) or 4 (TET4).  Builds INE (MeshInformations.jl:69-77) and the boundary-face table on the device. */
+int r2s_set_mesh(r2s_ctx *ctx, int nen, int64_t nnp, const double *X, int64_t nel, const int64_t *IEN);
+/* Grid fields exactly as Julia's Grid ctor computed them (src/MeshGrid/Grid.jl:10-34) */
+int r2s_set_grid(r2s_ctx *ctx, const double amin[3], const double amax[3], const int64_t N[3], double cell_size);
+
+/* calculate_mesh_volume (src/MeshGrid/MeshVolume.jl:4-42) */
+int r2s_mesh_volume(r2s_ctx *ctx, const double *rho_e, double *V_domain, double *V_frac);
+/* DenseInNodes (src/MeshGrid/NodalDensities.jl:89-109) */
+int r2s_nodal_densities(r2s_ctx *ctx, const double *rho_e, double *rho_n);
+/* calculate_isocontour_volume / find_threshold_for_volume (src/MeshGrid/Isocontour_volume.jl:1-154), HEX8 only */
+int r2s_isocontour_volume(r2s_ctx *ctx, const double *rho_n, double threshold, double *volume);
+int r2s_find_threshold(r2s_ctx *ctx, const double *rho_n, double target_volume, double rtol, int maxit, double *rho_t);
+
+/* evalDistances (src/SignedDistances/sdfOnDensityField.jl:139-486): dist[ngp]; xp[3*ngp] or NULL */
+int r2s_eval_distances(r2s_ctx *ctx, const double *rho_n, double rho_t, double delta_factor, double *dist, double *xp);
+/* Sign_Detection (src/SignedDistances/SignDetection.jl:275-283): signs[ngp] in {-1,+1} */
+int r2s_sign_detection(r2s_ctx *ctx, const double *rho_n, double rho_t, double *signs);
+/* remove_sdf_artifacts! (src/SignedDistances/SdfArtifactRemoval.jl:134-245): sdf[ngp] in/out */
+int r2s_remove_artifacts(r2s_ctx *ctx, double *sdf, double threshold, double min_component_ratio, int64_t *flipped);
+/* RBFs_smoothing (src/SdfSmoothing/RBFs4Smoothing.jl:321-377): fine_sdf[prod(N*smooth+1)], x fastest */
+int r2s_rbf_smoothing(r2s_ctx *ctx, const double *sdf, int is_interp, int smooth, double rbf_cut, double target_volume,
+                      float *fine_sdf, float *th, float *volume);
+/* calculate_volume_from_sdf (src/SdfSmoothing/CalcVolumeFromSDF.jl:26-125) on an nx x ny x nz Float32 grid */
+int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, int64_t nz, float edge, float iso, double *volume);
+
+/* ---- the timed region of rho2sdf() (src/RhoToSDF.jl:164-227) as one call ---------------------------------- */
+/* host buffers in/out (H2D of rho_n, D2H of sdf_dists and fine_sdf inside the call) */
+int r2s_pipeline(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_dists, float *fine_sdf, r2s_report *rep);
+/* device-resident variant: rho_n already uploaded, results stay on the device */
+int r2s_upload_nodal_densities(r2s_ctx *ctx, const double *rho_n);
+int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep);
+int r2s_download_sdf(r2s_ctx *ctx, double *sdf_dists);
+int r2s_download_fine_sdf(r2s_ctx *ctx, float *fine_sdf);
+/* device pointers of the results of the last pipeline (double[ngp], float[prod(N*smooth+1)]) */
+int r2s_result_ptrs_dev(r2s_ctx *ctx, void **sdf_dev, void **fine_sdf_dev);
+
+/* ---- z-slab sharding (one process per GPU) ------------------------------------------ */
+/* restrict this context to coarse planes k in [k0,k1) of the grid set by r2s_set_grid (halo planes are handled
+ * internally); k0 = 0, k1 = N3+1 restores the full grid */
+int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

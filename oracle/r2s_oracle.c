@@ -456,6 +456,8 @@ static void iso_tangent_step(const isoeval *E, const int fix[3], double lam, dou
   double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
   for (int i = 0; i < 3; i++) d[i] = y1 * z1[i] + y2 * z2[i];
 }
+static int r2so_debug = 0;
+API void r2so_set_debug(int v) { r2so_debug = v; }
 static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][8], const double re[8], double xi[3], int *niter) {
   isoprob P = {Xe, re, x, rho_t};
   double gs = fabs(rho_t); for (int k = 0; k < 8; k++) if (fabs(re[k]) > gs) gs = fabs(re[k]); if (gs < 1.0) gs = 1.0;
@@ -481,11 +483,12 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
     if (!(best < INFINITY)) { xi[0] = xi[1] = xi[2] = 0.0; if (niter) *niter = -1; return 0; }
   }
   /* ---- phase 2 ---- */
-  double lam = 0.0, dm = 0.0; int it, status = 0, stall = 0;
+  double lam = 0.0, dm = 0.0; int it, status = 0, stall = 0, force = 0;
   for (it = 0; it < 100 && status == 0; it++) {
     int bnd[3], tried[3] = {0, 0, 0};
     for (int i = 0; i < 3; i++) { bnd[i] = xi[i] >= 1.0 ? 1 : (xi[i] <= -1.0 ? -1 : 0); fix[i] = bnd[i]; }
     isoeval E; iso_full(&P, xi, &E);
+    if (r2so_debug) printf("O it=%d xi=(%.15g %.15g %.15g) f=%.15g g=%.3e fix=(%d %d %d) force=%d\n", it, xi[0], xi[1], xi[2], E.f, E.g, fix[0], fix[1], fix[2], force);
     double d[3] = {0, 0, 0}; int have_step = 0;
     for (int pass = 0; pass < 8; pass++) {
       double num = 0, den = 0; for (int i = 0; i < 3; i++) if (!fix[i]) { num += E.a[i] * E.c[i]; den += E.a[i] * E.a[i]; }
@@ -507,7 +510,7 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
       else {
         d[0] = d[1] = d[2] = 0.0;
         for (int i = 0; i < 3; i++) if (!fix[i]) {      /* diagonal Newton on the free variables (degenerate case) */
-          double h = E.Hf[i][i] + lam * E.Hg[i][i]; if (!(h > 1e-8 * E.Hgn[i][i])) h = E.Hgn[i][i];
+          double h = E.Hgn[i][i];                       /* Hess g has a zero diagonal */
           if (h > 0.0) d[i] = -E.c[i] / h;
         }
       }
@@ -515,7 +518,8 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
       for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { fix[i] = bnd[i]; refix = 1; }
       if (refix) continue;
       dm = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
-      if (dm > tolx) { have_step = 1; break; }
+      if (r2so_debug) printf("O   pass=%d lam=%.15g d=(%.6e %.6e %.6e) fix=(%d %d %d) den=%.3e\n", pass, lam, d[0], d[1], d[2], fix[0], fix[1], fix[2], den);
+      if (dm > tolx && !force) { have_step = 1; break; }
       /* converged on this face: release the bound with the most wrong-signed multiplier, if any */
       int worst = -1; double wv = 0.0;
       for (int i = 0; i < 3; i++) if (fix[i] && !tried[i]) {
@@ -523,7 +527,7 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
         if (gain > 1e-10 * (fabs(E.c[i]) + fabs(lam * E.a[i]) + 1e-300) && gain > wv) { wv = gain; worst = i; }
       }
       if (worst < 0) { status = 1; break; }
-      fix[worst] = 0; tried[worst] = 1;
+      fix[worst] = 0; tried[worst] = 1; force = 0;
     }
     if (status) break;
     if (!have_step) { status = 1; break; }
@@ -534,7 +538,7 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
       if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
     }
     double slope = E.c[0] * d[0] + E.c[1] * d[1] + E.c[2] * d[2];
-    if (!(slope < 0.0)) { status = 1; break; }
+    if (!(slope < 0.0)) { force = 1; continue; }        /* no descent left on this face: go to the multiplier test */
     double alpha = amax; int acc = 0;
     for (int ls = 0; ls < 40; ls++) {
       double xt[3]; int fx[3] = {fix[0], fix[1], fix[2]};
@@ -543,18 +547,20 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
       for (int i = 0; i < 3; i++) { if (xt[i] >= 1.0) { xt[i] = 1.0; fx[i] = 1; } if (xt[i] <= -1.0) { xt[i] = -1.0; fx[i] = -1; } }
       if (iso_restore(&P, xt, fx, tolg)) {
         double ft, gt; iso_fg(&P, xt, &ft, &gt, NULL);
-        if (ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
+        /* steps below 1e-7 are in the quadratic-convergence regime of Newton: accept them without the Armijo test
+         * (the decrease of f is below its evaluation noise there) */
+        if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
           if (E.f - ft <= 1e-15 * E.f) stall++; else stall = 0;
           xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = 1; break;
         }
       }
       alpha *= 0.5;
     }
-    if (!acc) { status = 2; break; }
-    if (stall >= 3) { status = 1; break; }
+    if (!acc) { if (dm < 1e-6) { force = 1; continue; } status = 2; break; }
+    if (stall >= 3) { force = 1; stall = 0; }
   }
   if (niter) *niter = it;
-  return status == 1 || (status == 2 && dm < 1e-6);
+  return status == 1;
 }
 API int r2so_project_iso_hex8(const double *x, double rho_t, const double *Xe_colmajor, const double *re, double *xi, int *niter) {
   double Xe[3][8]; for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) Xe[d][a] = Xe_colmajor[3 * a + d];
@@ -947,8 +953,8 @@ API int r2so_remove_artifacts(double *sdf, const i64 *N, double threshold, doubl
   /* min_component_size = max(1, round(Int, ratio*largest)) with round-half-to-even (:206) */
   double q = min_ratio * (double)largest; i64 ms = (i64)nearbyint(q); if (ms < 1) ms = 1;
   i64 nf = 0;
-  for (i64 v = 0; v < n; v++) if (sdf[v] >= threshold) { i64 r = uf_find(par, v); if (r != lroot && sz[r] < ms) { par[v] = -1 - r; } }
-  for (i64 v = 0; v < n; v++) if (par[v] < 0) { sdf[v] = -fabs(sdf[v]); nf++; }
+  for (i64 v = 0; v < n; v++) par[v] = (sdf[v] >= threshold) ? uf_find(par, v) : -1;      /* flatten first, then flip */
+  for (i64 v = 0; v < n; v++) if (par[v] >= 0 && par[v] != lroot && sz[par[v]] < ms) { sdf[v] = -fabs(sdf[v]); nf++; }
   *flipped = nf; free(par); free(sz); return 0;
 }
 

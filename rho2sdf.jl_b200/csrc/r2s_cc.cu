@@ -1,0 +1,99 @@
+// r2s_cc.cu -- remove_sdf_artifacts! (SignedDistances/SdfArtifactRemoval.jl:134-245) on the GPU
+//
+// 6-connected components of {sdf >= threshold} by a lock-free union-find (atomicCAS hooking of the larger root under
+// the smaller one, path halving), canonical label = smallest linear index of the component.  Labels are not an output
+// of the reference -- only the set of flipped points is -- so any canonical labelling is parity-safe; the largest
+// component is chosen by (size, then smallest root), which is deterministic.
+#include "r2s_common.cuh"
+
+__device__ __forceinline__ int uf_find(int *L, int x) {
+  while (true) {
+    int p = L[x];
+    if (p == x) return x;
+    int gp = L[p];
+    if (gp != p) L[x] = gp;     // path halving (benign race: only ever replaces a parent by an ancestor)
+    x = p;
+  }
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b) {
+  while (true) {
+    a = uf_find(L, a); b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }      // a > b: hook a under b
+    int old = atomicCAS(&L[a], a, b);
+    if (old == a) return;
+  }
+}
+__global__ void k_cc_init(i64 n, i64 v0, const double *__restrict__ sdf, double thr, int *__restrict__ L, int *__restrict__ sz) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  L[v] = (sdf[v0 + v] >= thr) ? (int)v : -1;
+  sz[v] = 0;
+}
+__global__ void k_cc_merge(int nx, int ny, int nz, int *__restrict__ L) {
+  i64 n = (i64)nx * ny * nz;
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= n || L[v] < 0) return;
+  int i = (int)(v % nx), j = (int)((v / nx) % ny), k = (int)(v / ((i64)nx * ny));
+  if (i + 1 < nx && L[v + 1] >= 0) uf_union(L, (int)v, (int)v + 1);
+  if (j + 1 < ny && L[v + nx] >= 0) uf_union(L, (int)v, (int)(v + nx));
+  if (k + 1 < nz && L[v + (i64)nx * ny] >= 0) uf_union(L, (int)v, (int)(v + (i64)nx * ny));
+}
+__global__ void k_cc_flatten(i64 n, int *__restrict__ L, int *__restrict__ sz) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= n || L[v] < 0) return;
+  // read-only walk to the root: a path-halving write here could land AFTER another thread stored its final root
+  // label and replace it by a non-root ancestor
+  int r = (int)v;
+  while (true) { int p = L[r]; if (p == r) break; r = p; }
+  L[v] = r;
+  atomicAdd(&sz[r], 1);
+}
+__global__ void k_cc_largest(i64 n, const int *__restrict__ L, const int *__restrict__ sz, u64 *__restrict__ best) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  u64 key = 0;
+  if (v < n && L[v] == (int)v) key = ((u64)(unsigned)sz[v] << 32) | (u64)(0xffffffffu - (unsigned)v);
+  for (int o = 16; o > 0; o >>= 1) { u64 other = __shfl_down_sync(0xffffffffu, key, o); if (other > key) key = other; }
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
+}
+__global__ void k_cc_flip(i64 n, i64 v0, const int *__restrict__ L, const int *__restrict__ sz, int lroot, int min_size, double *__restrict__ sdf, u64 *__restrict__ nflip) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  bool flip = false;
+  if (v < n) { int r = L[v]; flip = (r >= 0 && r != lroot && sz[r] < min_size); }
+  if (flip) sdf[v0 + v] = -fabs(sdf[v0 + v]);
+  unsigned m = __ballot_sync(0xffffffffu, flip);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nflip, (u64)__popc(m));
+}
+
+int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flipped) {
+  const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
+  int nx = g.np[0], ny = g.np[1], nz = (int)(ctx->k1 - ctx->k0);
+  i64 n = (i64)nx * ny * nz, v0 = (i64)ctx->k0 * nx * ny;
+  if (n >= (1ll << 31)) FAIL("remove_sdf_artifacts: slab too large for 32-bit labels");
+  CK(ctx->cc_label.reserve(sizeof(int) * (size_t)n));
+  CK(ctx->cc_size.reserve(sizeof(int) * (size_t)n));
+  CK(ctx->cc_scal.reserve(sizeof(u64) * 4));
+  CK(cudaMemsetAsync(ctx->cc_scal.p, 0, sizeof(u64) * 4, st));
+  int *L = ctx->cc_label.as<int>(), *sz = ctx->cc_size.as<int>(); u64 *sc = ctx->cc_scal.as<u64>();
+  double *sdf = ctx->sdf.as<double>();
+  int nb = cdiv(n, 256);
+  k_cc_init<<<nb, 256, 0, st>>>(n, v0, sdf, thr, L, sz); LAUNCH_CHECK();
+  k_cc_merge<<<nb, 256, 0, st>>>(nx, ny, nz, L); LAUNCH_CHECK();
+  k_cc_flatten<<<nb, 256, 0, st>>>(n, L, sz); LAUNCH_CHECK();
+  k_cc_largest<<<nb, 256, 0, st>>>(n, L, sz, sc); LAUNCH_CHECK();
+  u64 best = 0;
+  CK(cudaMemcpyAsync(&best, sc, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *flipped = 0;
+  if (best == 0) return 0;                                          // no interior nodes (:149-152)
+  i64 largest = (i64)(best >> 32); int lroot = (int)(0xffffffffu - (unsigned)(best & 0xffffffffu));
+  // min_component_size = max(1, round(Int, ratio * largest)), round-half-to-even (:206)
+  double q = ratio * (double)largest; i64 ms = (i64)nearbyint(q); if (ms < 1) ms = 1;
+  if (ms > 0x7fffffff) ms = 0x7fffffff;
+  k_cc_flip<<<nb, 256, 0, st>>>(n, v0, L, sz, lroot, (int)ms, sdf, sc + 1); LAUNCH_CHECK();
+  u64 nf = 0;
+  CK(cudaMemcpyAsync(&nf, sc + 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *flipped = (i64)nf;
+  return 0;
+}

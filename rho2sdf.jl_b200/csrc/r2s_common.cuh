@@ -1,0 +1,137 @@
+// r2s_common.cuh -- context, device buffers, launch bookkeeping shared by the kernels of libr2s.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/r2s.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define R2S_BIG 1.0e10
+
+// tile of grid points handled by one CTA of the per-voxel (gather) kernels
+#define TILE_X 8
+#define TILE_Y 8
+#define TILE_Z 4
+#define TILE_VOX (TILE_X * TILE_Y * TILE_Z)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  // grow-only; contents are NOT preserved
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return (T *)p; }
+};
+
+// per-active-element record produced by the binning step (elements that can change the distance field)
+struct ActRec {
+  int ps[3];      // first grid-point index per axis inside the element's (AABB +- delta) cell range
+  int pe[3];      // one past the last
+  int el;         // element id (0-based)
+  int cls;        // 1 solid (only boundary faces), 2 crossing
+  int fmask;      // bit sg set <=> face sg is a boundary face
+  int pad;
+  i64 pair_off;   // offset of this element's (element, point) block in the pair buffer (crossing only)
+};
+
+struct GridDev {
+  double amin[3], amax[3], cell;
+  int N[3];        // cells per axis
+  int np[3];       // points per axis = N+1
+  i64 ngp;
+  int nt[3];       // tiles per axis
+  i64 ntiles;
+  // device tables, concatenated per axis: offsets ax_off[d]
+  const double *pc;      // point coordinate
+  const int *cellof;     // cell of point
+  const int *cstart;     // first point of cell c (length N+3 per axis)
+  int pc_off[3], cs_off[3];
+};
+
+struct r2s_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  r2s_report rep;
+  i64 launches = 0;
+  cudaEvent_t ev[16];
+
+  // mesh
+  int nen = 0, nes = 0, nsn = 0;
+  i64 nnp = 0, nel = 0;
+  DevBuf X, IEN32, ine_ptr, ine_el, fbnd;   // X double[3*nnp]; IEN32 int[nen*nel] 0-based; INE CSR; fbnd uint8[nel]
+  DevBuf rho_e, rho_n;
+
+  // grid
+  bool has_grid = false;
+  GridDev g;
+  i64 k0 = 0, k1 = 0;                       // slab of coarse planes handled by this context
+  DevBuf gtab_d, gtab_i;
+  std::vector<double> h_pc[3];
+
+  // distance / sign work buffers
+  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, pairbuf, pairxp, cubtmp, counters;
+  DevBuf dist, xp, sdf, signs;
+  DevBuf s_rng, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
+  // connected components
+  DevBuf cc_label, cc_size, cc_scal;
+  // smoothing
+  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist;
+  int smooth_last = 1;
+
+  // volumes
+  DevBuf v_part;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      ctx->err = _b;                                                                               \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+#define FAIL(msg)           \
+  do {                      \
+    ctx->err = (msg);       \
+    return 1;               \
+  } while (0)
+
+#define LAUNCH_CHECK()                      \
+  do {                                      \
+    ctx->launches++;                        \
+    CK(cudaGetLastError());                 \
+  } while (0)
+
+static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// ---- implemented in the individual translation units --------------------------------------------------
+int r2s_mesh_upload_ien(r2s_ctx *ctx, const int64_t *IEN);                 // r2s_mesh.cu: int64 1-based -> int32 0-based on device
+int r2s_mesh_build_tables(r2s_ctx *ctx);                                   // r2s_mesh.cu: INE + boundary faces
+int r2s_dev_mesh_volume(r2s_ctx *ctx, double *vd, double *vf);             // r2s_mesh.cu
+int r2s_dev_nodal_densities(r2s_ctx *ctx);                                 // r2s_mesh.cu (rho_e -> rho_n, device)
+int r2s_dev_isocontour_volume(r2s_ctx *ctx, double thr, double *vol);      // r2s_mesh.cu
+int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool want_xp);   // r2s_dist.cu -> ctx->dist (,xp)
+int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf);              // r2s_sign.cu -> ctx->signs / ctx->sdf
+int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flipped);          // r2s_cc.cu on ctx->sdf
+int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double target, bool final_volume, float *th, float *vol);   // r2s_rbf.cu: ctx->sdf -> ctx->f_fine
+int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, double *vol);        // r2s_rbf.cu
+int r2s_scan_exclusive_i64(r2s_ctx *ctx, const i64 *in, i64 *out, i64 n);  // r2s_util.cu (cub)
+int r2s_scan_exclusive_i32(r2s_ctx *ctx, const int *in, int *out, i64 n);
+int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64 **sorted);

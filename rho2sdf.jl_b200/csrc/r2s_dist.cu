@@ -1,0 +1,392 @@
+// r2s_dist.cu -- evalDistances (SignedDistances/sdfOnDensityField.jl:139-486) on the GPU
+//
+//  1. binning   : classify elements (solid / crossing / void, :199-201,:312), give every active element the grid-point
+//                 range of its AABB +- delta cell range (MeshGrid/Grid.jl:122-154) and bin it into the voxel tiles it
+//                 overlaps: (tile, element) keys -> radix sort -> per-tile element lists in ascending element order.
+//  2. project   : element-centric, one warp per 32 grid points of a crossing element: closest point on the in-element
+//                 iso-surface (r2s_iso.cuh), distance written to a per-(element, point) pair buffer.  FP64-bound.
+//  3. assemble  : voxel-centric, one thread per grid point: walks its tile's element list IN ELEMENT ORDER and replays
+//                 the reference's running-min logic exactly (boundary-face triangles with their state-dependent
+//                 early-outs, then the element's iso distance from the pair buffer).  Bit-exact decisions (r2s_exact.cuh).
+//                 No atomics: every voxel is owned by one thread, the result is deterministic.
+#include "r2s_common.cuh"
+#include "r2s_tables.cuh"
+#include "r2s_exact.cuh"
+#include "r2s_iso.cuh"
+
+// ------------------------------------------------------------------------------------------------ binning
+__global__ void k_classify(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ rn, const unsigned char *__restrict__ fb,
+                           double rho_t, unsigned char *__restrict__ cls, int *__restrict__ flag, i64 *__restrict__ counts) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  int c = 0;
+  if (e < nel) {
+    double mn = 1e300, mx = -1e300;
+    for (int a = 0; a < nen; a++) { double r = rn[IEN[nen * e + a]]; mn = fmin(mn, r); mx = fmax(mx, r); }
+    if (mn >= rho_t) c = 1; else if (mx > rho_t) c = 2;
+    cls[e] = (unsigned char)c;
+    flag[e] = (c == 2 || (c == 1 && fb[e] != 0)) ? 1 : 0;
+  }
+  // class counters (report only)
+  unsigned m1 = __ballot_sync(0xffffffffu, c == 1), m2 = __ballot_sync(0xffffffffu, c == 2);
+  if ((threadIdx.x & 31) == 0) { if (m1) atomicAdd((u64 *)&counts[0], (u64)__popc(m1)); if (m2) atomicAdd((u64 *)&counts[1], (u64)__popc(m2)); }
+}
+// compacted active list: record with point ranges, tile count, pair count
+__global__ void k_act_records(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, const unsigned char *__restrict__ cls,
+                              const unsigned char *__restrict__ fb, const int *__restrict__ flag, const int *__restrict__ idx, GridDev g, double delta,
+                              int kz0, int kz1, ActRec *__restrict__ rec, i64 *__restrict__ ntile, i64 *__restrict__ npair, i64 *__restrict__ nchunk) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel || !flag[e]) return;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+  ActRec r; r.el = (int)e; r.cls = cls[e]; r.fmask = fb[e]; r.pad = 0; r.pair_off = 0;
+  bool ok = true;
+  for (int d = 0; d < 3; d++) {
+    int I0 = 0, I1 = -1;
+    ok = ok && ex::cell_range_axis(lo[d], hi[d], delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
+    if (ok) { r.ps[d] = g.cstart[g.cs_off[d] + I0]; r.pe[d] = g.cstart[g.cs_off[d] + I1 + 1]; } else { r.ps[d] = 0; r.pe[d] = 0; }
+  }
+  // z-slab restriction (multi-GPU): only planes [kz0,kz1)
+  if (r.ps[2] < kz0) r.ps[2] = kz0;
+  if (r.pe[2] > kz1) r.pe[2] = kz1;
+  i64 vol = 0, nt = 0;
+  if (ok && r.pe[0] > r.ps[0] && r.pe[1] > r.ps[1] && r.pe[2] > r.ps[2]) {
+    vol = (i64)(r.pe[0] - r.ps[0]) * (r.pe[1] - r.ps[1]) * (r.pe[2] - r.ps[2]);
+    nt = (i64)((r.pe[0] - 1) / TILE_X - r.ps[0] / TILE_X + 1) * ((r.pe[1] - 1) / TILE_Y - r.ps[1] / TILE_Y + 1) * ((r.pe[2] - 1) / TILE_Z - r.ps[2] / TILE_Z + 1);
+  } else { r.pe[0] = r.ps[0]; r.pe[1] = r.ps[1]; r.pe[2] = r.ps[2]; }
+  int a = idx[e];
+  rec[a] = r; ntile[a] = nt;
+  i64 np = (r.cls == 2) ? vol : 0;
+  npair[a] = np; nchunk[a] = (np + 31) / 32;
+}
+__global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__restrict__ toff, const i64 *__restrict__ poff, GridDev g,
+                            u64 *__restrict__ keys, int *__restrict__ tile_cnt) {
+  i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  ActRec r = rec[a];
+  rec[a].pair_off = poff[a];
+  if (r.pe[0] <= r.ps[0]) return;
+  i64 o = toff[a];
+  for (int tz = r.ps[2] / TILE_Z; tz <= (r.pe[2] - 1) / TILE_Z; tz++)
+    for (int ty = r.ps[1] / TILE_Y; ty <= (r.pe[1] - 1) / TILE_Y; ty++)
+      for (int tx = r.ps[0] / TILE_X; tx <= (r.pe[0] - 1) / TILE_X; tx++) {
+        u64 t = ((u64)tz * g.nt[1] + ty) * g.nt[0] + tx;
+        keys[o++] = (t << 32) | (u64)a;
+        atomicAdd(&tile_cnt[t], 1);
+      }
+}
+
+// ------------------------------------------------------------------------------------------------ project (hot, FP64)
+// one warp per 32-point chunk of a crossing element
+template <bool WANT_XP>
+__global__ void __launch_bounds__(128) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
+                                                      const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
+                                                      double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters) {
+  i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  if (item >= nitems) return;
+  // binary search: last a with choff[a] <= item
+  i64 lo = 0, hi = nact - 1;
+  while (lo < hi) { i64 mid = (lo + hi + 1) >> 1; if (choff[mid] <= item) lo = mid; else hi = mid - 1; }
+  const ActRec r = rec[lo];
+  int chunk = (int)(item - choff[lo]);
+  // element data: lane l < 8 loads node l; monomial coefficients assembled through shuffles
+  double v[4] = {0, 0, 0, 0};
+  if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
+  double A[4][8], re[8];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    double nv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nv[k] = __shfl_sync(0xffffffffu, v[c], k);
+    iso::monomial8(nv, A[c]);
+    if (c == 3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) re[k] = nv[k];
+    }
+  }
+  double gs = fabs(rho_t);
+#pragma unroll
+  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
+  gs = fmax(gs, 1.0);
+  int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
+  i64 vol = (i64)nx * ny * nz, li = (i64)chunk * 32 + lane;
+  int nit = 0; bool okc = true;
+  if (li < vol) {
+    int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
+    double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]};
+    double xi[3];
+    okc = iso::project_hex8(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+    double p[3]; iso::eval_pos(A, xi, p);
+    double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
+    pairbuf[r.pair_off + li] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+    if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
+  }
+  // statistics: iterations and failures (one atomic per warp)
+  int its = nit > 0 ? nit : 0;
+  for (int o = 16; o > 0; o >>= 1) its += __shfl_down_sync(0xffffffffu, its, o);
+  unsigned bad = __ballot_sync(0xffffffffu, !okc);
+  if (lane == 0) { atomicAdd(&counters[2], (u64)its); if (bad) atomicAdd(&counters[3], (u64)__popc(bad)); }
+}
+template <bool WANT_XP>
+__global__ void __launch_bounds__(128) k_project_tet4(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
+                                                      const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
+                                                      double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters) {
+  i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  if (item >= nitems) return;
+  i64 lo = 0, hi = nact - 1;
+  while (lo < hi) { i64 mid = (lo + hi + 1) >> 1; if (choff[mid] <= item) lo = mid; else hi = mid - 1; }
+  const ActRec r = rec[lo];
+  int chunk = (int)(item - choff[lo]);
+  double Xe[3][4], re[4];
+  for (int a = 0; a < 4; a++) { i64 n = IEN[4 * (i64)r.el + a]; re[a] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * n + d]; }
+  int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
+  i64 vol = (i64)nx * ny * nz, li = (i64)chunk * 32 + lane;
+  if (li < vol) {
+    int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
+    double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]}, p[3];
+    bool ok = iso::project_tet4(Xe, re, c_tet_isn, x, rho_t, p);
+    double dist = -1.0;     // negative = "no projection" (the reference would keep the running value)
+    if (ok) { double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2]; dist = sqrt((d0 * d0 + d1 * d1) + d2 * d2); }
+    else atomicAdd(&counters[3], 1ull);
+    pairbuf[r.pair_off + li] = dist;
+    if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ assemble (exact)
+struct VoxState { double c; double xp[3]; };
+template <bool WANT_XP>
+__device__ __forceinline__ void write_value(VoxState &s, double dt, const double xp[3]) {   // WriteValue :44-57
+  if (fabs(dt) < fabs(s.c)) { s.c = dt; if (WANT_XP) { s.xp[0] = xp[0]; s.xp[1] = xp[1]; s.xp[2] = xp[2]; } }
+}
+// IsProjectedOnFullSegment (:78-119)
+template <bool WANT_XP, int NEN>
+__device__ inline bool projected_on_full_segment(const double Xe[3][NEN], const double re[NEN], double rho_t, const double xp[3], const double x[3], VoxState &s) {
+  double rho;
+  if (NEN == 8) {
+    double xi[3], N[8];
+    ex::inverse_map_hex8((const double(*)[8])Xe, xp, xi);
+    if (!(ex::max3abs(xi[0], xi[1], xi[2]) < 1.001)) return false;
+    ex::hex8_shape(xi, N);
+    rho = ex::dot8(N, re);
+  } else {
+    double lc[3];
+    if (!ex::inverse_map_tet4((const double(*)[4])Xe, xp, lc)) return false;
+    if (!(lc[0] >= 0 && lc[1] >= 0 && lc[2] >= 0 && ex::add(ex::add(lc[0], lc[1]), lc[2]) <= 1.0)) return false;
+    double l4 = ex::sub(1.0, ex::add(ex::add(lc[0], lc[1]), lc[2]));
+    rho = ex::add(ex::add(ex::add(ex::mul(lc[0], re[0]), ex::mul(lc[1], re[1])), ex::mul(lc[2], re[2])), ex::mul(l4, re[3]));
+  }
+  if (rho >= rho_t) { write_value<WANT_XP>(s, ex::norm3(ex::sub(x[0], xp[0]), ex::sub(x[1], xp[1]), ex::sub(x[2], xp[2])), xp); return true; }
+  return false;
+}
+// process_triangle_projection! (:628-815) for one grid point
+template <bool WANT_XP, int NEN>
+__device__ inline void triangle_point(const double Xe[3][NEN], const double re[NEN], double rho_t, bool solid, const double Xt[3][3], const double Et[3][3],
+                                      const double n[3], const double x[3], VoxState &s) {
+  double lam[3]; ex::barycentric(Xt[0], Xt[1], Xt[2], n, x, lam);
+  double xp[3]; bool ok = false;
+  double lmin = lam[0]; if (lam[1] < lmin) lmin = lam[1]; if (lam[2] < lmin) lmin = lam[2];
+  if (lmin >= 0.0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) xp[d] = ex::add(ex::add(ex::mul(lam[0], Xt[0][d]), ex::mul(lam[1], Xt[1][d])), ex::mul(lam[2], Xt[2][d]));
+    double dt = ex::norm3(ex::sub(x[0], xp[0]), ex::sub(x[1], xp[1]), ex::sub(x[2], xp[2]));
+    if (solid) { if (fabs(dt) < fabs(s.c)) { write_value<WANT_XP>(s, dt, xp); ok = true; } }
+    else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (ok) continue;      // "break" on the first successful edge
+      double L = ex::norm3(Et[j][0], Et[j][1], Et[j][2]);
+      double u[3] = {ex::dvd(Et[j][0], L), ex::dvd(Et[j][1], L), ex::dvd(Et[j][2], L)};
+      double P = ex::add(ex::add(ex::mul(ex::sub(x[0], Xt[j][0]), u[0]), ex::mul(ex::sub(x[1], Xt[j][1]), u[1])), ex::mul(ex::sub(x[2], Xt[j][2]), u[2]));
+      if (P >= 0 && P <= L) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) xp[d] = ex::add(Xt[j][d], ex::mul(u[d], P));
+        double dt = ex::norm3(ex::sub(x[0], xp[0]), ex::sub(x[1], xp[1]), ex::sub(x[2], xp[2]));
+        if (solid) { if (fabs(dt) < fabs(s.c)) { write_value<WANT_XP>(s, dt, xp); ok = true; } }
+        else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+      }
+    }
+  }
+  if (!ok) {
+    double dd[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) dd[j] = ex::norm3(ex::sub(x[0], Xt[j][0]), ex::sub(x[1], Xt[j][1]), ex::sub(x[2], Xt[j][2]));
+    int idx = 0; if (dd[1] < dd[idx]) idx = 1; if (dd[2] < dd[idx]) idx = 2;
+    double dmin = idx == 0 ? dd[0] : (idx == 1 ? dd[1] : dd[2]);
+#pragma unroll
+    for (int d = 0; d < 3; d++) xp[d] = idx == 0 ? Xt[0][d] : (idx == 1 ? Xt[1][d] : Xt[2][d]);
+    if (solid) write_value<WANT_XP>(s, dmin, xp);
+    else projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+  }
+}
+// process_boundary_faces! (:489-558) for one grid point (point index pi[3], coordinate x)
+template <bool WANT_XP, int NEN>
+__device__ inline void boundary_faces_point(const ActRec &r, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn,
+                                            const GridDev &g, double rho_t, double delta, const int pi[3], const double x[3], VoxState &s) {
+  constexpr int NSN = NEN == 8 ? 4 : 3, NES = NEN == 8 ? 6 : 4;
+  double Xe[3][NEN], re[NEN];
+  for (int a = 0; a < NEN; a++) { i64 n = IEN[NEN * (i64)r.el + a]; re[a] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * n + d]; }
+  for (int sg = 0; sg < NES; sg++) {
+    if (!((r.fmask >> sg) & 1)) continue;
+    double Xs[NSN][3], Xc[3];
+    for (int a = 0; a < NSN; a++) { int ln = NEN == 8 ? c_hex_isn[sg][a] : c_tet_isn[sg][a]; for (int d = 0; d < 3; d++) Xs[a][d] = Xe[d][ln]; }
+    for (int d = 0; d < 3; d++) { double t = Xs[0][d]; for (int a = 1; a < NSN; a++) t = ex::add(t, Xs[a][d]); Xc[d] = ex::dvd(t, (double)NSN); }
+    for (int a = 0; a < NSN; a++) {
+      int a2 = (a + 1) % NSN; double Xt[3][3], Et[3][3], n[3];
+      for (int d = 0; d < 3; d++) { Xt[0][d] = Xs[a][d]; Xt[1][d] = Xs[a2][d]; Xt[2][d] = Xc[d]; }
+      // cell range of the triangle (Grid.jl:122-154) -> is this grid point's cell inside?
+      bool in = true;
+      for (int d = 0; d < 3 && in; d++) {
+        double lo = fmin(Xt[0][d], fmin(Xt[1][d], Xt[2][d])), hi = fmax(Xt[0][d], fmax(Xt[1][d], Xt[2][d])); int I0, I1;
+        in = ex::cell_range_axis(lo, hi, delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
+        if (in) { int c = g.cellof[g.pc_off[d] + pi[d]]; in = (c >= I0 && c <= I1); }
+      }
+      if (!in) continue;
+      for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+      n[0] = ex::sub(ex::mul(Et[0][1], Et[1][2]), ex::mul(Et[0][2], Et[1][1]));
+      n[1] = ex::sub(ex::mul(Et[0][2], Et[1][0]), ex::mul(Et[0][0], Et[1][2]));
+      n[2] = ex::sub(ex::mul(Et[0][0], Et[1][1]), ex::mul(Et[0][1], Et[1][0]));
+      double nn = ex::norm3(n[0], n[1], n[2]);
+      n[0] = ex::dvd(n[0], nn); n[1] = ex::dvd(n[1], nn); n[2] = ex::dvd(n[2], nn);
+      triangle_point<WANT_XP, NEN>(Xe, re, rho_t, r.cls == 1, Xt, Et, n, x, s);
+    }
+  }
+}
+
+template <bool WANT_XP, int NEN>
+__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
+                                                       const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
+                                                       const double *__restrict__ rn, double rho_t, double delta, const double *__restrict__ pairbuf,
+                                                       const double *__restrict__ pairxp, double *__restrict__ dist, double *__restrict__ xpo) {
+  __shared__ ActRec srec[64];
+  int t = blockIdx.x;
+  int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
+  int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
+  int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
+  bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  double x[3] = {0, 0, 0};
+  if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
+  VoxState s; s.c = -R2S_BIG; s.xp[0] = s.xp[1] = s.xp[2] = 0.0;
+  int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
+  for (int base = p0; base < p1; base += 64) {
+    int nb = min(64, p1 - base);
+    __syncthreads();
+    if (threadIdx.x < nb) srec[threadIdx.x] = rec[(int)(keys[base + threadIdx.x] & 0xffffffffull)];
+    __syncthreads();
+    if (!valid) continue;
+    for (int q = 0; q < nb; q++) {
+      const ActRec &r = srec[q];
+      if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
+      if (r.fmask) boundary_faces_point<WANT_XP, NEN>(r, IEN, X, rn, g, rho_t, delta, pi, x, s);
+      if (r.cls == 2) {
+        i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
+        double dt = pairbuf[idx];
+        if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
+          s.c = dt;
+          if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+        }
+      }
+    }
+  }
+  if (valid) {
+    i64 v = ((i64)pi[2] * g.np[1] + pi[1]) * g.np[0] + pi[0];
+    dist[v] = fabs(s.c);
+    if (WANT_XP) { xpo[3 * v] = s.xp[0]; xpo[3 * v + 1] = s.xp[1]; xpo[3 * v + 2] = s.xp[2]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host driver
+int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool want_xp) {
+  if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
+  if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
+  const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
+  i64 nel = ctx->nel; int nen = ctx->nen;
+  double delta = delta_factor * g.cell;
+  int kz0 = (int)ctx->k0, kz1 = (int)ctx->k1;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  CK(ctx->cls.reserve((size_t)nel));
+  CK(ctx->act_flag.reserve(sizeof(int) * (size_t)(nel + 1)));
+  CK(ctx->act_idx.reserve(sizeof(int) * (size_t)(nel + 1)));
+  CK(ctx->counters.reserve(sizeof(u64) * 8));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * 8, st));
+  CK(cudaMemsetAsync(ctx->act_flag.as<int>() + nel, 0, sizeof(int), st));
+  k_classify<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), ctx->fbnd.as<unsigned char>(), rho_t,
+                                             ctx->cls.as<unsigned char>(), ctx->act_flag.as<int>(), ctx->counters.as<i64>()); LAUNCH_CHECK();
+  if (r2s_scan_exclusive_i32(ctx, ctx->act_flag.as<int>(), ctx->act_idx.as<int>(), nel + 1)) return 1;
+  int nact_i = 0;
+  CK(cudaMemcpyAsync(&nact_i, ctx->act_idx.as<int>() + nel, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  i64 nact = nact_i;
+  CK(ctx->dist.reserve(sizeof(double) * (size_t)g.ngp));
+  if (want_xp) CK(ctx->xp.reserve(sizeof(double) * 3 * (size_t)g.ngp));
+  CK(ctx->tile_ptr.reserve(sizeof(int) * (size_t)(g.ntiles + 2)));
+  CK(cudaMemsetAsync(ctx->tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
+  i64 npairs = 0, nkeys = 0, nitems = 0;
+  u64 *sorted = nullptr;
+  if (nact > 0) {
+    CK(ctx->act_rec.reserve(sizeof(ActRec) * (size_t)nact));
+    CK(ctx->cnt_a.reserve(sizeof(i64) * 3 * (size_t)(nact + 1)));
+    CK(ctx->cnt_b.reserve(sizeof(i64) * 3 * (size_t)(nact + 1)));
+    i64 *ntile = ctx->cnt_a.as<i64>(), *npair = ntile + (nact + 1), *nchunk = npair + (nact + 1);
+    i64 *toff = ctx->cnt_b.as<i64>(), *poff = toff + (nact + 1), *choff = poff + (nact + 1);
+    CK(cudaMemsetAsync(ctx->cnt_a.p, 0, sizeof(i64) * 3 * (size_t)(nact + 1), st));
+    k_act_records<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->cls.as<unsigned char>(), ctx->fbnd.as<unsigned char>(),
+                                                  ctx->act_flag.as<int>(), ctx->act_idx.as<int>(), g, delta, kz0, kz1, ctx->act_rec.as<ActRec>(), ntile, npair, nchunk);
+    LAUNCH_CHECK();
+    if (r2s_scan_exclusive_i64(ctx, ntile, toff, nact + 1)) return 1;
+    if (r2s_scan_exclusive_i64(ctx, npair, poff, nact + 1)) return 1;
+    if (r2s_scan_exclusive_i64(ctx, nchunk, choff, nact + 1)) return 1;
+    i64 h3[3];
+    CK(cudaMemcpyAsync(&h3[0], toff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h3[1], poff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h3[2], choff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nkeys = h3[0]; npairs = h3[1]; nitems = h3[2];
+    if (nkeys >= (1ll << 31) || npairs >= (1ll << 40)) FAIL("distance binning: problem too large for one slab (key/pair count overflow)");
+    CK(ctx->keys.reserve(sizeof(u64) * (size_t)(nkeys + 1)));
+    CK(ctx->keys_alt.reserve(sizeof(u64) * (size_t)(nkeys + 1)));
+    CK(ctx->pairbuf.reserve(sizeof(double) * (size_t)(npairs + 1)));
+    if (want_xp) CK(ctx->pairxp.reserve(sizeof(double) * 3 * (size_t)(npairs + 1)));
+    k_emit_keys<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff, poff, g, ctx->keys.as<u64>(), ctx->tile_ptr.as<int>() + 1); LAUNCH_CHECK();
+    int tbits = 1; while ((1ll << tbits) < g.ntiles) tbits++;
+    if (nkeys > 0) { if (r2s_sort_keys_u64(ctx, ctx->keys.as<u64>(), ctx->keys_alt.as<u64>(), nkeys, 32 + tbits, &sorted)) return 1; }
+  }
+  // tile_ptr[t+1] currently holds the count of tile t (tile_ptr[0] = 0): inclusive scan in place == exclusive offsets
+  {
+    DevBuf &tmp = ctx->s_cnt;   // reuse as scratch
+    CK(tmp.reserve(sizeof(int) * (size_t)(g.ntiles + 2)));
+    if (r2s_scan_exclusive_i32(ctx, ctx->tile_ptr.as<int>() + 1, tmp.as<int>(), g.ntiles + 1)) return 1;
+    CK(cudaMemcpyAsync(ctx->tile_ptr.as<int>(), tmp.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaEventRecord(ctx->ev[1], st));
+  if (nitems > 0) {
+    i64 *choff = ctx->cnt_b.as<i64>() + 2 * (nact + 1);
+    int nb = cdiv(nitems * 32, 128);
+#define PROJ(KERN, XP) KERN<XP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
+                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
+    if (nen == 8) { if (want_xp) PROJ(k_project_hex8, true); else PROJ(k_project_hex8, false); }
+    else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
+    LAUNCH_CHECK();
+#undef PROJ
+  }
+  CK(cudaEventRecord(ctx->ev[2], st));
+  {
+#define ASM(XP, NEN) k_assemble<XP, NEN><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_ptr.as<int>(), sorted, ctx->act_rec.as<ActRec>(), \
+        ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
+        ctx->dist.as<double>(), ctx->xp.as<double>())
+    if (nen == 8) { if (want_xp) ASM(true, 8); else ASM(false, 8); }
+    else { if (want_xp) ASM(true, 4); else ASM(false, 4); }
+    LAUNCH_CHECK();
+#undef ASM
+  }
+  CK(cudaEventRecord(ctx->ev[3], st));
+  u64 hc[8];
+  CK(cudaMemcpyAsync(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
+  ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
+  CK(cudaEventElapsedTime(&ctx->rep.ms_bin, ctx->ev[0], ctx->ev[1]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_project, ctx->ev[1], ctx->ev[2]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_assemble, ctx->ev[2], ctx->ev[3]));
+  return 0;
+}

@@ -1,0 +1,340 @@
+// r2s_iso.cuh -- closest point on the in-element iso-surface of a HEX8 / TET4 (device functions)
+//
+//   min ||x - X(xi)||^2   s.t.   rho(xi) = rho_t,   -1 <= xi <= 1          (SignedDistances/ComputeCoordsOnIso.jl:16-87)
+//
+// The reference hands this to NLopt :LD_SLSQP from xi = 0.  Here: a feasible-path SQP from the same start
+//   phase 1  Newton-project xi = 0 onto {g = 0} inside the box (fallback: iso-crossing of an element edge closest to x)
+//   phase 2  Newton steps in the tangent space of g on the current face of the box (exact Hessian of the Lagrangian,
+//            Gauss-Newton fallback), ratio test against the bounds, restoration onto g = 0, Armijo on f;
+//            bounds are released by multiplier sign once the face problem has converged.
+// The trilinear fields are held in monomial form  v = A0 + A1 x + A2 e + A3 z + A4 xe + A5 ez + A6 zx + A7 xez  so that a
+// value costs 7 FMAs and a gradient 9; FMA contraction is allowed here (this is the FP64-bound hot loop) -- the result is
+// converged to |step| <= 1e-11 in xi, far below the 1e-9 h parity tolerance.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace iso {
+
+struct Eval {
+  double f, g, F[3], c[3], a[3];
+  double Hgn[3][3];   // 2 J^T J
+  double m[3];        // extra off-diagonal terms of Hess f: pairs (0,1),(1,2),(2,0)
+  double hg[3];       // off-diagonal terms of Hess g, same pair order (its diagonal is zero)
+};
+
+__device__ __forceinline__ double tri_val(const double A[8], double X, double E, double Z, double xe, double ez, double zx, double xez) {
+  return fma(A[7], xez, fma(A[6], zx, fma(A[5], ez, fma(A[4], xe, fma(A[3], Z, fma(A[2], E, fma(A[1], X, A[0])))))));
+}
+// g and grad g only
+__device__ __forceinline__ void eval_g(const double A[4][8], double rho_t, const double xi[3], double &g, double a[3]) {
+  double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
+  g = tri_val(A[3], X, E, Z, xe, ez, zx, xez) - rho_t;
+  a[0] = fma(A[3][7], ez, fma(A[3][6], Z, fma(A[3][4], E, A[3][1])));
+  a[1] = fma(A[3][7], zx, fma(A[3][5], Z, fma(A[3][4], X, A[3][2])));
+  a[2] = fma(A[3][7], xe, fma(A[3][6], X, fma(A[3][5], E, A[3][3])));
+}
+__device__ __forceinline__ void eval_pos(const double A[4][8], const double xi[3], double p[3]) {
+  double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
+#pragma unroll
+  for (int d = 0; d < 3; d++) p[d] = tri_val(A[d], X, E, Z, xe, ez, zx, xez);
+}
+__device__ __forceinline__ double eval_f(const double A[4][8], const double x[3], const double xi[3]) {
+  double p[3]; eval_pos(A, xi, p);
+  double F0 = p[0] - x[0], F1 = p[1] - x[1], F2 = p[2] - x[2];
+  return fma(F2, F2, fma(F1, F1, F0 * F0));
+}
+__device__ __forceinline__ void eval_full(const double A[4][8], const double x[3], double rho_t, const double xi[3], Eval &E_) {
+  double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
+  double J[3][3], mx[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    E_.F[d] = tri_val(A[d], X, E, Z, xe, ez, zx, xez) - x[d];
+    J[d][0] = fma(A[d][7], ez, fma(A[d][6], Z, fma(A[d][4], E, A[d][1])));
+    J[d][1] = fma(A[d][7], zx, fma(A[d][5], Z, fma(A[d][4], X, A[d][2])));
+    J[d][2] = fma(A[d][7], xe, fma(A[d][6], X, fma(A[d][5], E, A[d][3])));
+    mx[d][0] = fma(A[d][7], Z, A[d][4]);   // d2/dxi deta
+    mx[d][1] = fma(A[d][7], X, A[d][5]);   // d2/deta dzeta
+    mx[d][2] = fma(A[d][7], E, A[d][6]);   // d2/dzeta dxi
+  }
+  E_.f = fma(E_.F[2], E_.F[2], fma(E_.F[1], E_.F[1], E_.F[0] * E_.F[0]));
+  eval_g(A, rho_t, xi, E_.g, E_.a);
+  E_.hg[0] = fma(A[3][7], Z, A[3][4]); E_.hg[1] = fma(A[3][7], X, A[3][5]); E_.hg[2] = fma(A[3][7], E, A[3][6]);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    E_.c[j] = 2.0 * fma(J[2][j], E_.F[2], fma(J[1][j], E_.F[1], J[0][j] * E_.F[0]));
+    E_.m[j] = 2.0 * fma(E_.F[2], mx[2][j], fma(E_.F[1], mx[1][j], E_.F[0] * mx[0][j]));
+#pragma unroll
+    for (int i = 0; i < 3; i++) E_.Hgn[i][j] = 2.0 * fma(J[2][i], J[2][j], fma(J[1][i], J[1][j], J[0][i] * J[0][j]));
+  }
+}
+// full Hessian entry of the Lagrangian
+__device__ __forceinline__ double Hl(const Eval &E, double lam, int i, int j) {
+  if (i == j) return E.Hgn[i][i];
+  int p = (i + j == 1) ? 0 : ((i + j == 3) ? 1 : 2);
+  return E.Hgn[i][j] + fma(lam, E.hg[p], E.m[p]);
+}
+
+// Newton restoration onto g = 0 moving only variables with fix[i] == 0; variables leaving the box are clamped and fixed
+__device__ __forceinline__ bool restore(const double A[4][8], double rho_t, double xi[3], int fix[3], double tolg) {
+  for (int it = 0; it < 40; it++) {
+    double g, a[3]; eval_g(A, rho_t, xi, g, a);
+    if (fabs(g) <= tolg) return true;
+    double den = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) if (!fix[i]) den = fma(a[i], a[i], den);
+    if (!(den > 0.0)) return false;
+    double s = g / den;
+#pragma unroll
+    for (int i = 0; i < 3; i++) if (!fix[i]) {
+      xi[i] = fma(-s, a[i], xi[i]);
+      if (xi[i] >= 1.0) { xi[i] = 1.0; fix[i] = 1; } else if (xi[i] <= -1.0) { xi[i] = -1.0; fix[i] = -1; }
+    }
+  }
+  return false;
+}
+
+// tangent step, two free variables (I,J), K fixed
+template <int I, int J>
+__device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3]) {
+  double zi = -E.a[J], zj = E.a[I];
+  double zz = fma(zi, zi, zj * zj);
+  if (!(zz > 0.0)) return;
+  double hii = Hl(E, lam, I, I), hij = Hl(E, lam, I, J), hjj = Hl(E, lam, J, J);
+  double kap = zi * fma(hii, zi, hij * zj) + zj * fma(hij, zi, hjj * zj);
+  double kgn = zi * fma(E.Hgn[I][I], zi, E.Hgn[I][J] * zj) + zj * fma(E.Hgn[I][J], zi, E.Hgn[J][J] * zj);
+  if (!(kap > 1e-8 * kgn)) kap = kgn;
+  if (!(kap > 0.0)) return;
+  double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
+  d[I] = t * zi; d[J] = t * zj;
+}
+// tangent step, all three free; null-space basis built around component K (largest |a_K|), U=(K+1)%3, V=(K+2)%3
+template <int K>
+__device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3]) {
+  constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
+  double z1[3] = {0, 0, 0}, z2[3] = {0, 0, 0};
+  z1[U] = E.a[K]; z1[K] = -E.a[U]; z2[V] = E.a[K]; z2[K] = -E.a[V];
+  double Hz1[3], Hz2[3], Gz1[3], Gz2[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Hz1[i] = fma(Hl(E, lam, i, 2), z1[2], fma(Hl(E, lam, i, 1), z1[1], Hl(E, lam, i, 0) * z1[0]));
+    Hz2[i] = fma(Hl(E, lam, i, 2), z2[2], fma(Hl(E, lam, i, 1), z2[1], Hl(E, lam, i, 0) * z2[0]));
+    Gz1[i] = fma(E.Hgn[i][2], z1[2], fma(E.Hgn[i][1], z1[1], E.Hgn[i][0] * z1[0]));
+    Gz2[i] = fma(E.Hgn[i][2], z2[2], fma(E.Hgn[i][1], z2[1], E.Hgn[i][0] * z2[0]));
+  }
+  double m11 = fma(z1[2], Hz1[2], fma(z1[1], Hz1[1], z1[0] * Hz1[0])), m12 = fma(z1[2], Hz2[2], fma(z1[1], Hz2[1], z1[0] * Hz2[0])),
+         m22 = fma(z2[2], Hz2[2], fma(z2[1], Hz2[1], z2[0] * Hz2[0]));
+  double g11 = fma(z1[2], Gz1[2], fma(z1[1], Gz1[1], z1[0] * Gz1[0])), g12 = fma(z1[2], Gz2[2], fma(z1[1], Gz2[1], z1[0] * Gz2[0])),
+         g22 = fma(z2[2], Gz2[2], fma(z2[1], Gz2[1], z2[0] * Gz2[0]));
+  double r1 = -fma(z1[2], E.c[2], fma(z1[1], E.c[1], z1[0] * E.c[0])), r2 = -fma(z2[2], E.c[2], fma(z2[1], E.c[1], z2[0] * E.c[0]));
+  double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
+  if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
+  if (!(det > 0.0 && m11 > 0.0)) return;
+  double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
+#pragma unroll
+  for (int i = 0; i < 3; i++) d[i] = fma(y1, z1[i], y2 * z2[i]);
+}
+__device__ __forceinline__ void tangent_step(const Eval &E, const int fix[3], double lam, double d[3]) {
+  d[0] = d[1] = d[2] = 0.0;
+  int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
+  if (nf < 2) return;
+  if (nf == 2) {
+    if (fix[0]) tangent2<1, 2>(E, lam, d);
+    else if (fix[1]) tangent2<0, 2>(E, lam, d);
+    else tangent2<0, 1>(E, lam, d);
+    return;
+  }
+  int k = 0;
+  if (fabs(E.a[1]) > fabs(E.a[k])) k = 1;
+  if (fabs(E.a[2]) > fabs(k == 0 ? E.a[0] : E.a[1])) k = 2;
+  if (k == 0) { if (fabs(E.a[0]) > 0.0) tangent3<0>(E, lam, d); }
+  else if (k == 1) { if (fabs(E.a[1]) > 0.0) tangent3<1>(E, lam, d); }
+  else { if (fabs(E.a[2]) > 0.0) tangent3<2>(E, lam, d); }
+}
+
+// HEX8 projection.  A: monomial coefficients [x,y,z,rho][8]; re: nodal densities (for the edge fallback).
+// Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
+__device__ __forceinline__ bool project_hex8(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
+                                             const double x[3], double rho_t, double gs, double xi[3], int &nit) {
+  const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
+  int fix[3] = {0, 0, 0};
+  xi[0] = xi[1] = xi[2] = 0.0;
+  bool ok = restore(A, rho_t, xi, fix, tolg);
+  if (!ok) {
+    double best = INFINITY;
+    for (int e = 0; e < 12; e++) {
+      int a = edges[e][0], b = edges[e][1]; double ra = re[a] - rho_t, rb = re[b] - rho_t;
+      if ((ra <= 0 && rb >= 0) || (ra >= 0 && rb <= 0)) {
+        double t = (ra == rb) ? 0.5 : ra / (ra - rb), cand[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) cand[d] = sg[a][d] + t * (sg[b][d] - sg[a][d]);
+        double dd = eval_f(A, x, cand);
+        if (dd < best) { best = dd; xi[0] = cand[0]; xi[1] = cand[1]; xi[2] = cand[2]; }
+      }
+    }
+    if (!(best < INFINITY)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  }
+  double lam = 0.0, dm = 0.0; int it, status = 0, stall = 0; bool force = false;
+  for (it = 0; it < 100 && status == 0; it++) {
+    int bnd[3], tried[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 3; i++) { bnd[i] = xi[i] >= 1.0 ? 1 : (xi[i] <= -1.0 ? -1 : 0); fix[i] = bnd[i]; }
+    Eval E; eval_full(A, x, rho_t, xi, E);
+    double d[3] = {0, 0, 0}; bool have_step = false;
+    for (int pass = 0; pass < 8; pass++) {
+      double num = 0, den = 0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (!fix[i]) { num = fma(E.a[i], E.c[i], num); den = fma(E.a[i], E.a[i], den); }
+      if (den > atol2) { lam = -num / den; tangent_step(E, fix, lam, d); }
+      else {
+        double llo = -INFINITY, lhi = INFINITY, akk = 0.0, ckk = 0.0; bool anyk = false;
+#pragma unroll
+        for (int i = 0; i < 3; i++) if (fix[i]) {
+          double as = E.a[i] * fix[i], cs = E.c[i] * fix[i];
+          if (as > 0) { double b = -cs / as; if (b < lhi) lhi = b; } else if (as < 0) { double b = -cs / as; if (b > llo) llo = b; }
+          if (!anyk || fabs(E.a[i]) > fabs(akk)) { akk = E.a[i]; ckk = E.c[i]; anyk = true; }
+        }
+        if (llo <= lhi) lam = (llo > -INFINITY && lhi < INFINITY) ? 0.5 * (llo + lhi) : (llo > -INFINITY ? llo : (lhi < INFINITY ? lhi : 0.0));
+        else if (anyk && akk != 0.0) lam = -ckk / akk;
+        d[0] = d[1] = d[2] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) if (!fix[i]) {
+          double h = E.Hgn[i][i]; if (h > 0.0) d[i] = -E.c[i] / h;    // Hess g has a zero diagonal
+        }
+      }
+      bool refix = false;
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { fix[i] = bnd[i]; refix = true; }
+      if (refix) continue;
+      dm = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
+      if (dm > tolx && !force) { have_step = true; break; }
+      int worst = -1; double wv = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (fix[i] && !tried[i]) {
+        double gain = fma(lam, E.a[i], E.c[i]) * (double)fix[i];
+        if (gain > 1e-10 * (fabs(E.c[i]) + fabs(lam * E.a[i]) + 1e-300) && gain > wv) { wv = gain; worst = i; }
+      }
+      if (worst < 0) { status = 1; break; }
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (i == worst) { fix[i] = 0; tried[i] = 1; }
+      force = false;
+    }
+    if (status) break;
+    if (!have_step) { status = 1; break; }
+    double amax = 1.0; int blk = -1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) if (!fix[i]) {
+      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
+      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
+    }
+    double slope = fma(E.c[2], d[2], fma(E.c[1], d[1], E.c[0] * d[0]));
+    if (!(slope < 0.0)) { force = true; continue; }      // no descent left on this face: go to the multiplier test
+    double alpha = amax; bool acc = false;
+    for (int ls = 0; ls < 40; ls++) {
+      double xt[3]; int fx[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        fx[i] = fix[i]; xt[i] = fma(alpha, d[i], xi[i]);
+        if (i == blk && alpha == amax) { xt[i] = d[i] > 0 ? 1.0 : -1.0; fx[i] = d[i] > 0 ? 1 : -1; }
+        if (xt[i] >= 1.0) { xt[i] = 1.0; fx[i] = 1; }
+        if (xt[i] <= -1.0) { xt[i] = -1.0; fx[i] = -1; }
+      }
+      if (restore(A, rho_t, xt, fx, tolg)) {
+        double ft = eval_f(A, x, xt);
+        // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
+        if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
+          if (E.f - ft <= 1e-15 * E.f) stall++; else stall = 0;
+          xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true; break;
+        }
+      }
+      alpha *= 0.5;
+    }
+    if (!acc) { if (dm < 1e-6) { force = true; continue; } status = 2; break; }
+    if (stall >= 3) { force = true; stall = 0; }
+  }
+  nit = it;
+  return status == 1;
+}
+
+// monomial coefficients of a trilinear field from its 8 nodal values (node order of hex8_shape.jl:27-34)
+__device__ __forceinline__ void monomial8(const double v[8], double A[8]) {
+  double s01 = v[0] + v[1], d01 = v[1] - v[0], s32 = v[3] + v[2], d32 = v[2] - v[3];
+  double s45 = v[4] + v[5], d45 = v[5] - v[4], s76 = v[7] + v[6], d76 = v[6] - v[7];
+  // bottom (z=-1) and top (z=+1) bilinear coefficients
+  double b0 = s01 + s32, b1 = d01 + d32, b2 = s32 - s01, b3 = d32 - d01;     // 4*(c, x, e, xe) on bottom
+  double t0 = s45 + s76, t1 = d45 + d76, t2 = s76 - s45, t3 = d76 - d45;     // on top
+  A[0] = 0.125 * (b0 + t0); A[1] = 0.125 * (b1 + t1); A[2] = 0.125 * (b2 + t2); A[4] = 0.125 * (b3 + t3);
+  A[3] = 0.125 * (t0 - b0); A[6] = 0.125 * (t1 - b1); A[5] = 0.125 * (t2 - b2); A[7] = 0.125 * (t3 - b3);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// TET4 (ComputeCoordsOnIso.jl:90-181): rho is affine on the tet -> projection of x onto the convex polygon {rho=rho_t}
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double det3(const double M[3][3]) {
+  return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+__device__ __forceinline__ void closest_on_segment(const double a[3], const double b[3], const double x[3], double q[3]) {
+  double e[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ee = (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2];
+  double t = ee > 0 ? (((x[0] - a[0]) * e[0] + (x[1] - a[1]) * e[1]) + (x[2] - a[2]) * e[2]) / ee : 0.0;
+  t = fmin(fmax(t, 0.0), 1.0);
+#pragma unroll
+  for (int d = 0; d < 3; d++) q[d] = a[d] + t * e[d];
+}
+__device__ inline bool project_tet4(const double Xe[3][4], const double re[4], const int isn[4][3], const double x[3], double rho_t, double xp[3]) {
+  double M[3][3], r[3] = {re[1] - re[0], re[2] - re[0], re[3] - re[0]}, G[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) { M[0][d] = Xe[d][1] - Xe[d][0]; M[1][d] = Xe[d][2] - Xe[d][0]; M[2][d] = Xe[d][3] - Xe[d][0]; }
+  double det = det3(M);
+  if (!(fabs(det) > 0.0)) return false;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double B[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) B[k][l] = (l == c) ? r[k] : M[k][l];
+    G[c] = det3(B) / det;
+  }
+  double gg = (G[0] * G[0] + G[1] * G[1]) + G[2] * G[2];
+  if (!(gg > 0.0)) return false;
+  double rx = re[0] + ((G[0] * (x[0] - Xe[0][0]) + G[1] * (x[1] - Xe[1][0])) + G[2] * (x[2] - Xe[2][0]));
+  double s = (rx - rho_t) / gg, q[3] = {x[0] - s * G[0], x[1] - s * G[1], x[2] - s * G[2]};
+  {  // barycentrics of q (columns of M^T are the edge vectors)
+    double A[3][3], b[3], l[4];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { A[d][0] = M[0][d]; A[d][1] = M[1][d]; A[d][2] = M[2][d]; b[d] = q[d] - Xe[d][0]; }
+    double dA = det3(A);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double B[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int m = 0; m < 3; m++) B[k][m] = (m == c) ? b[k] : A[k][m];
+      l[c + 1] = det3(B) / dA;
+    }
+    l[0] = 1.0 - ((l[1] + l[2]) + l[3]);
+    if (l[0] >= 0.0 && l[1] >= 0.0 && l[2] >= 0.0 && l[3] >= 0.0) { xp[0] = q[0]; xp[1] = q[1]; xp[2] = q[2]; return true; }
+  }
+  double best = INFINITY;
+  for (int f = 0; f < 4; f++) {
+    double P[3][3]; int np = 0;
+    for (int e = 0; e < 3 && np < 3; e++) {
+      int a = isn[f][e], b = isn[f][(e + 1) % 3]; double ra = re[a] - rho_t, rb = re[b] - rho_t;
+      if ((ra <= 0 && rb > 0) || (ra > 0 && rb <= 0) || (ra < 0 && rb >= 0) || (ra >= 0 && rb < 0)) {
+        double t = ra / (ra - rb);
+        for (int d = 0; d < 3; d++) P[np][d] = Xe[d][a] + t * (Xe[d][b] - Xe[d][a]);
+        np++;
+      }
+    }
+    if (np < 2) continue;
+    for (int i = 0; i < np; i++) {
+      if (np == 2 && i == 1) break;
+      int j = (i + 1) % np; double c[3]; closest_on_segment(P[i], P[j], x, c);
+      double dd = ((x[0] - c[0]) * (x[0] - c[0]) + (x[1] - c[1]) * (x[1] - c[1])) + (x[2] - c[2]) * (x[2] - c[2]);
+      if (dd < best) { best = dd; xp[0] = c[0]; xp[1] = c[1]; xp[2] = c[2]; }
+    }
+  }
+  return best < INFINITY;
+}
+}  // namespace iso

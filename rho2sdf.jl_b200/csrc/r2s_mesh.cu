@@ -1,0 +1,288 @@
+// r2s_mesh.cu -- mesh tables and the pre-timer stages of rho2sdf(): node->element connectivity, boundary faces,
+// calculate_mesh_volume, DenseInNodes, calculate_isocontour_volume.   Compiled with -fmad=false: these values feed
+// threshold comparisons downstream, so they are evaluated in the reference's operation order without contraction.
+#include "r2s_common.cuh"
+#include "r2s_tables.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// INE: node -> elements (MeshGrid/MeshInformations.jl:69-77), lists sorted ascending like the reference's push! order
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_ine_count(const int *__restrict__ IEN, i64 n, int *__restrict__ cnt) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) atomicAdd(&cnt[IEN[t]], 1);
+}
+__global__ void k_ine_fill(const int *__restrict__ IEN, i64 n, int nen, const int *__restrict__ ptr, int *__restrict__ cur, int *__restrict__ out) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) { int nd = IEN[t]; int s = atomicAdd(&cur[nd], 1); out[ptr[nd] + s] = (int)(t / nen); }
+}
+__global__ void k_ine_sort(i64 nnp, const int *__restrict__ ptr, int *__restrict__ lst) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n >= nnp) return;
+  int a = ptr[n], b = ptr[n + 1];
+  for (int i = a + 1; i < b; i++) { int v = lst[i], j = i - 1; while (j >= a && lst[j] > v) { lst[j + 1] = lst[j]; j--; } lst[j + 1] = v; }
+}
+__global__ void k_ien_convert(const i64 *__restrict__ in, i64 n, int *__restrict__ out) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (int)(in[t] - 1);
+}
+// boundary faces (SignedDistances/sdfOnDensityField.jl:511-519): the INE lists of the face's nodes share exactly one element
+__global__ void k_face_boundary(i64 nel, int nen, int nes, int nsn, const int *__restrict__ IEN, const int *__restrict__ ptr, const int *__restrict__ lst,
+                                unsigned char *__restrict__ fb) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  int mask = 0;
+  for (int sg = 0; sg < nes; sg++) {
+    const int *fn = nen == 8 ? c_hex_isn[sg] : c_tet_isn[sg];
+    int n0 = IEN[nen * e + fn[0]], count = 0;
+    for (int p = ptr[n0]; p < ptr[n0 + 1]; p++) {
+      int e2 = lst[p]; bool all = true;
+      for (int a = 1; a < nsn && all; a++) {
+        int na = IEN[nen * e + fn[a]]; bool found = false;
+        for (int b = 0; b < nen; b++) found |= (IEN[nen * (i64)e2 + b] == na);
+        all = found;
+      }
+      if (all) count++;
+    }
+    if (count == 1) mask |= 1 << sg;
+  }
+  fb[e] = (unsigned char)mask;
+}
+
+int r2s_mesh_upload_ien(r2s_ctx *ctx, const int64_t *IEN) {
+  i64 n = ctx->nel * ctx->nen;
+  DevBuf tmp;
+  CK(tmp.reserve(sizeof(i64) * (size_t)n));
+  CK(cudaMemcpyAsync(tmp.p, IEN, sizeof(i64) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  k_ien_convert<<<cdiv(n, 256), 256, 0, ctx->stream>>>(tmp.as<i64>(), n, ctx->IEN32.as<int>()); LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  tmp.release();
+  return 0;
+}
+int r2s_mesh_build_tables(r2s_ctx *ctx) {
+  i64 n = ctx->nel * ctx->nen;
+  CK(ctx->ine_ptr.reserve(sizeof(int) * (size_t)(ctx->nnp + 1)));
+  CK(ctx->ine_el.reserve(sizeof(int) * (size_t)n));
+  CK(ctx->fbnd.reserve((size_t)ctx->nel));
+  DevBuf cnt, cur;
+  CK(cnt.reserve(sizeof(int) * (size_t)(ctx->nnp + 1)));
+  CK(cur.reserve(sizeof(int) * (size_t)(ctx->nnp + 1)));
+  CK(cudaMemsetAsync(cnt.p, 0, sizeof(int) * (size_t)(ctx->nnp + 1), ctx->stream));
+  CK(cudaMemsetAsync(cur.p, 0, sizeof(int) * (size_t)(ctx->nnp + 1), ctx->stream));
+  k_ine_count<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->IEN32.as<int>(), n, cnt.as<int>()); LAUNCH_CHECK();
+  if (r2s_scan_exclusive_i32(ctx, cnt.as<int>(), ctx->ine_ptr.as<int>(), ctx->nnp + 1)) return 1;
+  k_ine_fill<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->IEN32.as<int>(), n, ctx->nen, ctx->ine_ptr.as<int>(), cur.as<int>(), ctx->ine_el.as<int>()); LAUNCH_CHECK();
+  k_ine_sort<<<cdiv(ctx->nnp, 256), 256, 0, ctx->stream>>>(ctx->nnp, ctx->ine_ptr.as<int>(), ctx->ine_el.as<int>()); LAUNCH_CHECK();
+  k_face_boundary<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->nes, ctx->nsn, ctx->IEN32.as<int>(), ctx->ine_ptr.as<int>(),
+                                                                ctx->ine_el.as<int>(), ctx->fbnd.as<unsigned char>()); LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  cnt.release(); cur.release();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shape functions in the reference's form (ShapeFunctions/hex8_shape.jl:2-70); this TU is built with -fmad=false
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline void hex8_shape_d(const double xi[3], double N[8], double dN[8][3]) {
+  double m1 = xi[0] - 1, p1 = xi[0] + 1, m2 = xi[1] - 1, p2 = xi[1] + 1, m3 = xi[2] - 1, p3 = xi[2] + 1;
+  double t1 = m1 * m2, t2 = p1 * m2, t3 = p1 * p2, t4 = m1 * p2, c = 0.125;
+  N[0] = -c * t1 * m3; N[1] = c * t2 * m3; N[2] = -c * t3 * m3; N[3] = c * t4 * m3;
+  N[4] = c * t1 * p3;  N[5] = -c * t2 * p3; N[6] = c * t3 * p3; N[7] = -c * t4 * p3;
+  double d = c * m3, dp = c * p3;
+  dN[0][0] = -d * m2; dN[1][0] = d * m2; dN[2][0] = -d * p2; dN[3][0] = d * p2;
+  dN[4][0] = dp * m2; dN[5][0] = -dp * m2; dN[6][0] = dp * p2; dN[7][0] = -dp * p2;
+  dN[0][1] = -d * m1; dN[1][1] = d * p1; dN[2][1] = -d * p1; dN[3][1] = d * m1;
+  dN[4][1] = dp * m1; dN[5][1] = -dp * p1; dN[6][1] = dp * p1; dN[7][1] = -dp * m1;
+  dN[0][2] = -c * t1; dN[1][2] = c * t2; dN[2][2] = -c * t3; dN[3][2] = c * t4;
+  dN[4][2] = c * t1;  dN[5][2] = -c * t2; dN[6][2] = c * t3;  dN[7][2] = -c * t4;
+}
+__device__ inline double det3(const double J[3][3]) {
+  return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+         J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+}
+
+// deterministic sum: per-block partials in a fixed slot, summed in slot order by one thread
+__global__ void k_sum_partials(const double *__restrict__ part, int n, int stride, double *__restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (int s = 0; s < stride; s++) { double acc = 0; for (int i = 0; i < n; i++) acc += part[(size_t)i * stride + s]; out[s] = acc; }
+}
+template <int NV>
+__device__ inline void block_sum_store(double v[NV], double *part) {
+  __shared__ double sh[NV][32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double x = v[q];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[q][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int q = 0; q < NV; q++) { double acc = 0; for (int i = 0; i < nw; i++) acc += sh[q][i]; part[(size_t)blockIdx.x * NV + q] = acc; }
+}
+
+// calculate_mesh_volume (MeshGrid/MeshVolume.jl:4-117), 3x3x3 Gauss
+__global__ void k_mesh_volume(i64 nel, int nen, const double *__restrict__ X, const int *__restrict__ IEN, const double *__restrict__ rho,
+                              GaussTab G3, double *__restrict__ part) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  double v2[2] = {0.0, 0.0};
+  if (e < nel) {
+    double vol = 0.0;
+    if (nen == 8) {
+      double xe[3][8];
+      for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) xe[d][a] = X[3 * (i64)IEN[8 * e + a] + d];
+      double N[8], dN[8][3];
+      for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) {
+        double xi[3] = {G3.x[i], G3.x[j], G3.x[k]}; hex8_shape_d(xi, N, dN);
+        double J[3][3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double s = 0; for (int a = 0; a < 8; a++) s += xe[r][a] * dN[a][c]; J[r][c] = s; }
+        vol += G3.w[i] * G3.w[j] * G3.w[k] * fabs(det3(J));
+      }
+    } else {
+      double xe[3][4];
+      for (int a = 0; a < 4; a++) for (int d = 0; d < 3; d++) xe[d][a] = X[3 * (i64)IEN[4 * e + a] + d];
+      double J[3][3];
+      for (int r = 0; r < 3; r++) { J[r][0] = xe[r][0] - xe[r][3]; J[r][1] = xe[r][1] - xe[r][3]; J[r][2] = xe[r][2] - xe[r][3]; }
+      double adet = fabs(det3(J));
+      for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) {
+        double xi = (G3.x[i] + 1.0) / 2.0, eta = (G3.x[j] + 1.0) / 2.0 * (1.0 - xi), zeta = (G3.x[k] + 1.0) / 2.0 * (1.0 - xi - eta);
+        if (xi < 0 || eta < 0 || zeta < 0 || xi + eta + zeta > 1.0) continue;
+        double jt = (1.0 - xi) * (1.0 - xi) * (1.0 - xi - eta) / 8.0;
+        vol += G3.w[i] * G3.w[j] * G3.w[k] * adet * jt;
+      }
+    }
+    v2[0] = vol; v2[1] = vol * rho[e];
+  }
+  block_sum_store<2>(v2, part);
+}
+int r2s_dev_mesh_volume(r2s_ctx *ctx, double *vd, double *vf) {
+  int nb = cdiv(ctx->nel, 128);
+  CK(ctx->v_part.reserve(sizeof(double) * (size_t)(2 * nb + 2)));
+  double *part = ctx->v_part.as<double>();
+  k_mesh_volume<<<nb, 128, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->X.as<double>(), ctx->IEN32.as<int>(), ctx->rho_e.as<double>(), gauss_legendre_host(3), part); LAUNCH_CHECK();
+  k_sum_partials<<<1, 32, 0, ctx->stream>>>(part, nb, 2, part + 2 * (size_t)nb); LAUNCH_CHECK();
+  double h[2];
+  CK(cudaMemcpyAsync(h, part + 2 * (size_t)nb, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *vd = h[0]; *vf = h[1] / h[0];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DenseInNodes (MeshGrid/NodalDensities.jl:89-218)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_centroids(i64 nel, int nen, const double *__restrict__ X, const int *__restrict__ IEN, double *__restrict__ C) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  for (int d = 0; d < 3; d++) { double s = 0; for (int a = 0; a < nen; a++) s += X[3 * (i64)IEN[nen * e + a] + d]; C[3 * e + d] = s / nen; }
+}
+__device__ inline void jacobi_eig4(double A[4][4], double lam[4], double V[4][4]) {
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) V[i][j] = (i == j);
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0; for (int p = 0; p < 4; p++) for (int q = p + 1; q < 4; q++) off += A[p][q] * A[p][q];
+    if (off == 0.0) break;
+    for (int p = 0; p < 4; p++) for (int q = p + 1; q < 4; q++) {
+      if (A[p][q] == 0.0) continue;
+      double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 4; k++) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+      for (int k = 0; k < 4; k++) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+      for (int k = 0; k < 4; k++) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+    }
+  }
+  for (int i = 0; i < 4; i++) lam[i] = A[i][i];
+  for (int i = 0; i < 4; i++) for (int j = i + 1; j < 4; j++) if (lam[j] < lam[i]) {
+    double t = lam[i]; lam[i] = lam[j]; lam[j] = t;
+    for (int k = 0; k < 4; k++) { double u = V[k][i]; V[k][i] = V[k][j]; V[k][j] = u; }
+  }
+}
+__global__ void k_nodal_densities(i64 nnp, const double *__restrict__ X, const double *__restrict__ C, const int *__restrict__ ptr, const int *__restrict__ lst,
+                                  const double *__restrict__ rho, double *__restrict__ out) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i >= nnp) return;
+  int a0 = ptr[i], n1 = ptr[i + 1] - a0; const int *els = lst + a0;
+  if (n1 == 0) { out[i] = 0.0; return; }
+  if (n1 == 1) { out[i] = rho[els[0]]; return; }
+  if (n1 < 4) {
+    double L[3], Lmax = 0;
+    for (int j = 0; j < n1; j++) {
+      double v0 = X[3 * i] - C[3 * (i64)els[j]], v1 = X[3 * i + 1] - C[3 * (i64)els[j] + 1], v2 = X[3 * i + 2] - C[3 * (i64)els[j] + 2];
+      L[j] = sqrt((v0 * v0 + v1 * v1) + v2 * v2); if (L[j] > Lmax) Lmax = L[j];
+    }
+    Lmax *= 1.2; double dm = 0, de = 0;
+    for (int j = 0; j < n1; j++) { dm += rho[els[j]] * (1 - L[j] / Lmax); de += (1 - L[j] / Lmax); }
+    out[i] = dm / de; return;
+  }
+  double AtA[4][4] = {{0}}, Atb[4] = {0, 0, 0, 0}, bsum = 0;
+  for (int j = 0; j < n1; j++) {
+    double row[4] = {1.0, C[3 * (i64)els[j]], C[3 * (i64)els[j] + 1], C[3 * (i64)els[j] + 2]}, b = rho[els[j]];
+    for (int r = 0; r < 4; r++) { for (int c = 0; c < 4; c++) AtA[r][c] += row[r] * row[c]; Atb[r] += row[r] * b; }
+    bsum += b;
+  }
+  double lam[4], V[4][4]; jacobi_eig4(AtA, lam, V);
+  double lmax = lam[0], lmin = lam[0];
+  for (int k = 1; k < 4; k++) { if (lam[k] > lmax) lmax = lam[k]; if (lam[k] < lmin) lmin = lam[k]; }
+  double e1 = fabs(lmax / lmin), e2 = fabs(lmax / lam[1]), e3 = fabs(lmax / lam[2]);
+  int poz = -1;
+  if (1e7 > e1 && 3e3 > e2) poz = 0;
+  else if (1e7 < e1 && 3e3 > e2) poz = 1;
+  else if (1e7 < e1 && 3e3 < e2) poz = (3e3 > e3) ? 2 : 3;
+  if (poz < 0) { out[i] = bsum / (double)n1; return; }
+  double b1[4], x2[4] = {0, 0, 0, 0}, xx[4];
+  for (int k = 0; k < 4; k++) { double s = 0; for (int r = 0; r < 4; r++) s += V[r][k] * Atb[r]; b1[k] = s; }
+  for (int k = poz; k < 4; k++) x2[k] = b1[k] / lam[k];
+  for (int r = 0; r < 4; r++) { double s = 0; for (int k = 0; k < 4; k++) s += V[r][k] * x2[k]; xx[r] = s; }
+  out[i] = 1.0 * xx[0] + X[3 * i] * xx[1] + X[3 * i + 1] * xx[2] + X[3 * i + 2] * xx[3];
+}
+int r2s_dev_nodal_densities(r2s_ctx *ctx) {
+  DevBuf C;
+  CK(C.reserve(sizeof(double) * 3 * (size_t)ctx->nel));
+  CK(ctx->rho_n.reserve(sizeof(double) * (size_t)ctx->nnp));
+  k_centroids<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->X.as<double>(), ctx->IEN32.as<int>(), C.as<double>()); LAUNCH_CHECK();
+  k_nodal_densities<<<cdiv(ctx->nnp, 128), 128, 0, ctx->stream>>>(ctx->nnp, ctx->X.as<double>(), C.as<double>(), ctx->ine_ptr.as<int>(), ctx->ine_el.as<int>(),
+                                                                   ctx->rho_e.as<double>(), ctx->rho_n.as<double>()); LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  C.release();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculate_isocontour_volume (MeshGrid/Isocontour_volume.jl:1-75): 15^3 Gauss in crossing elements, 3^3 in solid ones
+// one warp per element; lanes stride over the quadrature points, fixed-order warp reduction
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_iso_volume(i64 nel, const double *__restrict__ X, const int *__restrict__ IEN, const double *__restrict__ rn, double thr,
+                             GaussTab G3, GaussTab G15, double *__restrict__ part) {
+  i64 e = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  double v1[1] = {0.0};
+  if (e < nel) {
+    double ev[8], mn = 1e300, mx = -1e300, xe[3][8];
+    for (int a = 0; a < 8; a++) { int n = IEN[8 * e + a]; ev[a] = rn[n]; mn = fmin(mn, ev[a]); mx = fmax(mx, ev[a]); for (int d = 0; d < 3; d++) xe[d][a] = X[3 * (i64)n + d]; }
+    if (!(mx < thr)) {
+      bool chk = !(mn >= thr); int n = chk ? 15 : 3; const double *gp = chk ? G15.x : G3.x, *w = chk ? G15.w : G3.w;
+      double vol = 0.0, N[8], dN[8][3];
+      for (int q = lane; q < n * n * n; q += 32) {
+        int i = q % n, j = (q / n) % n, k = q / (n * n);
+        double xi[3] = {gp[i], gp[j], gp[k]}; hex8_shape_d(xi, N, dN);
+        if (chk) { double v = 0; for (int a = 0; a < 8; a++) v += N[a] * ev[a]; if (v < thr) continue; }
+        double J[3][3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double s = 0; for (int a = 0; a < 8; a++) s += xe[r][a] * dN[a][c]; J[r][c] = s; }
+        vol += w[i] * w[j] * w[k] * fabs(det3(J));
+      }
+      v1[0] = vol;
+    }
+  }
+  block_sum_store<1>(v1, part);
+}
+int r2s_dev_isocontour_volume(r2s_ctx *ctx, double thr, double *vol) {
+  if (ctx->nen != 8) FAIL("calculate_isocontour_volume is implemented for HEX8 only (as in the reference, Isocontour_volume.jl:27-38)");
+  int nb = cdiv(ctx->nel * 32, 256);
+  CK(ctx->v_part.reserve(sizeof(double) * (size_t)(nb + 2)));
+  double *part = ctx->v_part.as<double>();
+  k_iso_volume<<<nb, 256, 0, ctx->stream>>>(ctx->nel, ctx->X.as<double>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), thr, gauss_legendre_host(3), gauss_legendre_host(15), part); LAUNCH_CHECK();
+  k_sum_partials<<<1, 32, 0, ctx->stream>>>(part, nb, 1, part + nb); LAUNCH_CHECK();
+  double h;
+  CK(cudaMemcpyAsync(&h, part + nb, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *vol = h;
+  return 0;
+}

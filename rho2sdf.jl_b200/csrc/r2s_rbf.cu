@@ -1,0 +1,427 @@
+// r2s_rbf.cu -- RBFs_smoothing (SdfSmoothing/RBFs4Smoothing.jl:321-377) and calculate_volume_from_sdf
+// (SdfSmoothing/CalcVolumeFromSDF.jl:26-125) on the GPU, Float32 like the reference.
+//
+// On the regular SDF grid the truncated Gaussian kernel matrix K (:142-176, sigma = cell, cut 1e-3) is an 81-point
+// stencil (offsets with |d|^2 <= 6, weights exp(-|d|^2)); the KD-tree / sparse-matrix machinery of the reference becomes
+//   * a shared-memory tiled stencil mat-vec fused with the CG vector updates and dot products (HBM-bound),
+//   * an 8-phase polyphase stencil for the evaluation on the :fine grid (taps with |d|^2 <= ln(1000) in half cells),
+//   * a two-pass cut-cell quadrature for the volume-matching bisection (LS_Threshold, :265-300).
+// Sums are deterministic: block partials in fixed slots (double) or 64-bit fixed-point integer atomics.
+#include <float.h>
+#include "r2s_common.cuh"
+#include "r2s_tables.cuh"
+
+// ------------------------------------------------------------------------------------------------ process_vector (:15-22)
+__global__ void k_to_f32(i64 n, i64 v0, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  float a = -1.0f;
+  if (v < n) { float f = (float)sdf[v0 + v]; s[v] = f; float af = fabsf(f); if (af < 1.0e9f) a = af; }
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_down_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0 && a >= 0.0f) atomicMax(maxbits, __float_as_uint(a) + 1u);   // +1 so that "found 0.0" differs from "none"
+}
+__global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__restrict__ maxbits) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  float maxv = __uint_as_float(*maxbits - 1u);
+  float f = s[v], a = fabsf(f); const float big = 1.0e10f, rt = sqrtf(FLT_EPSILON);
+  if (fabsf(a - big) <= rt * fmaxf(a, big)) s[v] = (f > 0 ? 1.0f : (f < 0 ? -1.0f : 0.0f)) * maxv;    // isapprox(|v|, 1f10), default rtol
+}
+
+// ------------------------------------------------------------------------------------------------ 81-point stencil
+// weights by squared offset m = di^2+dj^2+dk^2 <= 6
+struct StencilW { float w[8]; };
+#define ST_X 32
+#define ST_Y 4
+#define ST_Z 16
+#define ST_ZB 4            // outputs per thread along z
+#define ST_H 2             // halo
+// out = K * in_eff with in_eff = (beta_mode ? r + beta*u : in).  When beta_mode, the interior in_eff is written back to u.
+// partial[block] (double) receives sum(in_eff * out) over the block's interior.
+template <bool BETA>
+__global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx, int ny, int nz, const float *__restrict__ in, const float *__restrict__ r,
+                                                                           const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
+                                                                           double *__restrict__ partial, StencilW W) {
+  __shared__ float sm[ST_Z + 2 * ST_H][ST_Y + 2 * ST_H][ST_X + 2 * ST_H];
+  __shared__ double red[ST_X * ST_Y * (ST_Z / ST_ZB) / 32];
+  const int bx = blockIdx.x * ST_X, by = blockIdx.y * ST_Y, bz = blockIdx.z * ST_Z;
+  const int tid = threadIdx.x;
+  float beta = 0.0f;
+  if (BETA) beta = scal[0];
+  // cooperative tile load with halo (zero outside the grid: K has no entries there)
+  const int TX = ST_X + 2 * ST_H, TY = ST_Y + 2 * ST_H, TZ = ST_Z + 2 * ST_H;
+  for (int t = tid; t < TX * TY * TZ; t += blockDim.x) {
+    int lx = t % TX, ly = (t / TX) % TY, lz = t / (TX * TY);
+    int gx = bx + lx - ST_H, gy = by + ly - ST_H, gz = bz + lz - ST_H;
+    float v = 0.0f;
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) {
+      i64 gi = ((i64)gz * ny + gy) * nx + gx;
+      if (BETA) {
+        v = r[gi] + beta * u[gi];       // the new u goes to a separate buffer: other blocks still read the old one for their halos
+      } else v = in[gi];
+    }
+    sm[lz][ly][lx] = v;
+  }
+  __syncthreads();
+  const int lx = tid % ST_X, ly = (tid / ST_X) % ST_Y, lzb = tid / (ST_X * ST_Y);
+  float acc[ST_ZB];
+#pragma unroll
+  for (int q = 0; q < ST_ZB; q++) acc[q] = 0.0f;
+#pragma unroll
+  for (int dj = -2; dj <= 2; dj++)
+#pragma unroll
+    for (int di = -2; di <= 2; di++) {
+      if (di * di + dj * dj > 6) continue;
+      float col[ST_ZB + 4];
+#pragma unroll
+      for (int z = 0; z < ST_ZB + 4; z++) col[z] = sm[lzb * ST_ZB + z][ly + ST_H + dj][lx + ST_H + di];
+#pragma unroll
+      for (int dk = -2; dk <= 2; dk++) {
+        if (di * di + dj * dj + dk * dk > 6) continue;
+        float w = W.w[di * di + dj * dj + dk * dk];
+#pragma unroll
+        for (int q = 0; q < ST_ZB; q++) acc[q] = fmaf(w, col[q + 2 + dk], acc[q]);
+      }
+    }
+  double dsum = 0.0;
+#pragma unroll
+  for (int q = 0; q < ST_ZB; q++) {
+    int gx = bx + lx, gy = by + ly, gz = bz + lzb * ST_ZB + q;
+    if (gx < nx && gy < ny && gz < nz) {
+      i64 gi = ((i64)gz * ny + gy) * nx + gx;
+      float ctr = sm[lzb * ST_ZB + q + ST_H][ly + ST_H][lx + ST_H];
+      out[gi] = acc[q];
+      if (BETA) unew[gi] = ctr;
+      dsum += (double)ctr * (double)acc[q];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+  if ((tid & 31) == 0) red[tid >> 5] = dsum;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i];
+    partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
+  }
+}
+// CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, uc, rr}
+__global__ void k_sum_to(const double *__restrict__ part, int n, double *__restrict__ dst) {
+  __shared__ double sh[256];
+  double a = 0; for (int i = threadIdx.x; i < n; i += 256) a += part[i];
+  sh[threadIdx.x] = a; __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int i = 0; i < 256; i++) s += sh[i]; *dst = s; }
+}
+__global__ void k_cg_alpha(float *scal, const double *uc) {     // alpha = residual^2 / dot(u, c)
+  float res = scal[2]; scal[1] = res * res / (float)(*uc);
+}
+__global__ void k_cg_update(i64 n, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c, float *__restrict__ x,
+                            float *__restrict__ r, double *__restrict__ partial) {
+  __shared__ double red[8];
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  float alpha = scal[1]; double rr = 0.0;
+  if (v < n) { x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv; rr = (double)rv * (double)rv; }
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
+  __syncthreads();
+  if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i]; partial[blockIdx.x] = a; }
+}
+__global__ void k_cg_residual(float *scal, const double *rr) {  // prev = residual; residual = norm(r); beta for the next iteration
+  float prev = scal[2], res = (float)sqrt(*rr);
+  scal[3] = prev; scal[2] = res; scal[0] = res * res / (prev * prev);
+}
+__global__ void k_cg_init(float *scal, const double *rr) {
+  float res = (float)sqrt(*rr);
+  scal[2] = res; scal[3] = 1.0f; scal[4] = sqrtf(FLT_EPSILON) * res; scal[0] = res * res / (1.0f * 1.0f); scal[1] = 0.0f;
+}
+__global__ void k_dot_self(i64 n, const float *__restrict__ a, double *__restrict__ partial) {
+  __shared__ double red[8];
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  double s = 0.0; if (v < n) s = (double)a[v] * (double)a[v];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i]; partial[blockIdx.x] = t; }
+}
+
+// ------------------------------------------------------------------------------------------------ min / max of a float field
+__global__ void k_minmax(i64 n, const float *__restrict__ a, unsigned *__restrict__ mm) {   // mm[0] = ordered-min, mm[1] = ordered-max
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  float lo = INFINITY, hi = -INFINITY;
+  if (v < n) { lo = a[v]; hi = a[v]; }
+  for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_down_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_down_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    // order-preserving map float -> uint
+    unsigned bl = __float_as_uint(lo), bh = __float_as_uint(hi);
+    bl = (bl & 0x80000000u) ? ~bl : (bl | 0x80000000u); bh = (bh & 0x80000000u) ? ~bh : (bh | 0x80000000u);
+    atomicMin(&mm[0], bl); atomicMax(&mm[1], bh);
+  }
+}
+static inline float ordered_to_float(unsigned b) { b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b; float f; memcpy(&f, &b, 4); return f; }
+
+// ------------------------------------------------------------------------------------------------ volume (CalcVolumeFromSDF.jl:26-125)
+// pass 1: classify cells of (sdf - th): full cells counted, cut cells appended to a list
+__global__ void k_vol_classify(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
+  i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
+  i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  bool full = false, cut = false;
+  if (c < ncell) {
+    int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
+    i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
+    float v0 = sdf[b] - th, v1 = sdf[b + 1] - th, v2 = sdf[b + nx] - th, v3 = sdf[b + nx + 1] - th;
+    float v4 = sdf[b + sxy] - th, v5 = sdf[b + sxy + 1] - th, v6 = sdf[b + sxy + nx] - th, v7 = sdf[b + sxy + nx + 1] - th;
+    float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
+    float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
+    if (!(mx < iso)) { if (mn >= iso) full = true; else cut = true; }
+  }
+  unsigned mf = __ballot_sync(0xffffffffu, full), mc = __ballot_sync(0xffffffffu, cut);
+  int lane = threadIdx.x & 31, base = 0;
+  if (lane == 0) { if (mf) atomicAdd(&acc[0], (u64)__popc(mf)); if (mc) base = (int)atomicAdd(&acc[1], (u64)__popc(mc)); }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (cut) { int slot = base + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = (int)c; }
+}
+// pass 2: one warp per cut cell, 9^3 Gauss points over the lanes; the cell's Float32 partial volume (in units of the
+// cell volume) is accumulated as a 2^-40 fixed-point integer (deterministic)
+struct GaussF { float x[9]; float w[9]; };
+__global__ void k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int ncut, GaussF G,
+                          u64 *__restrict__ acc) {
+  int wid = (int)((blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= ncut) return;
+  i64 c = cutlist[wid];
+  int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
+  i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
+  float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
+  float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+  float part = 0.0f;       // sum of w_i w_j w_k over inside points (the Jacobian h^3/8 is applied on the host)
+  for (int q = lane; q < 729; q += 32) {
+    int iq = q % 9, jq = (q / 9) % 9, kq = q / 81;
+    float xi = (G.x[iq] + 1) / 2, eta = (G.x[jq] + 1) / 2, zeta = (G.x[kq] + 1) / 2;
+    float c00 = c000 * (1.0f - xi) + c100 * xi, c01 = c001 * (1.0f - xi) + c101 * xi;
+    float c10 = c010 * (1.0f - xi) + c110 * xi, c11 = c011 * (1.0f - xi) + c111 * xi;
+    float c0 = c00 * (1.0f - eta) + c10 * eta, c1 = c01 * (1.0f - eta) + c11 * eta;
+    float ps = c0 * (1.0f - zeta) + c1 * zeta;
+    if (ps >= iso) part += G.w[iq] * G.w[jq] * G.w[kq];
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if (lane == 0) atomicAdd(&acc[2], (u64)llrint((double)part * 137438953472.0));      // part in [0,8]; 2^37 per unit, exact for a float
+}
+static GaussF gauss9f() { GaussTab t = gauss_legendre_host(9); GaussF g; for (int i = 0; i < 9; i++) { g.x[i] = (float)t.x[i]; g.w[i] = (float)t.w[i]; } return g; }
+
+// volume of {sdf - th >= iso}; edge = cell edge length (Float32 like the reference)
+static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, float th, float edge, float iso, double *vol) {
+  cudaStream_t st = ctx->stream;
+  i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
+  if (ncell >= (1ll << 31)) FAIL("calculate_volume_from_sdf: grid too large for 32-bit cell ids");
+  CK(ctx->f_scal.reserve(256));
+  int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
+  u64 *acc = (u64 *)((char *)ctx->f_scal.p + 128);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    CK(cudaMemsetAsync(acc, 0, sizeof(u64) * 4, st));
+    k_vol_classify<<<cdiv(ncell, 256), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
+    u64 h[2];
+    CK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((i64)h[1] > cutcap) {     // grow the cut list and redo the classification
+      CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 4 + 1024)));
+      cutcap = (int)(ctx->cutlist.cap / sizeof(int));
+      continue;
+    }
+    int ncut = (int)h[1];
+    u64 fixed = 0;
+    if (ncut > 0) {
+      k_vol_cut<<<cdiv((i64)ncut * 32, 256), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), ncut, gauss9f(), acc); LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(&fixed, acc + 2, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    float ev = edge * edge * edge, jac = ev / 8.0f;
+    *vol = (double)h[0] * (double)ev + ((double)fixed / 137438953472.0 /* 2^37 */) * (double)jac;
+    return 0;
+  }
+  FAIL("calculate_volume_from_sdf: cut-cell list overflow");
+}
+int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, double *vol) {
+  CK(ctx->cutlist.reserve(sizeof(int) * 1024));
+  return volume_dev(ctx, sdf_dev, (int)nx, (int)ny, (int)nz, 0.0f, edge, iso, vol);
+}
+
+// ------------------------------------------------------------------------------------------------ fine-grid evaluation (:363)
+// phase tables: for each of the smooth^3 sub-cell positions the taps (coarse offset, weight) with |d|^2 <= ln(1/cut)
+struct TapTable { int n[8]; int off[8][96]; };     // off packs (di+4) | (dj+4)<<4 | (dk+4)<<8
+__constant__ float c_tapw[8][96];
+__constant__ TapTable c_taps;
+#define FN_X 32
+#define FN_Y 4
+#define FN_Z 4
+template <int SM>
+__global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, int nz, int fx, int fy, int fz, const float *__restrict__ w, float th, float *__restrict__ out) {
+  // coarse tile covering this block's fine outputs, with halo 3 on each side (taps reach -2..+3)
+  constexpr int CX = FN_X / SM + 6, CY = FN_Y / SM + 6 + 1, CZ = FN_Z / SM + 6 + 1;
+  __shared__ float sm[CZ][CY][CX + 1];
+  const int fbx = blockIdx.x * FN_X, fby = blockIdx.y * FN_Y, fbz = blockIdx.z * FN_Z;
+  const int cbx = fbx / SM - 3, cby = fby / SM - 3, cbz = fbz / SM - 3;
+  for (int t = threadIdx.x; t < CX * CY * CZ; t += blockDim.x) {
+    int lx = t % CX, ly = (t / CX) % CY, lz = t / (CX * CY);
+    int gx = cbx + lx, gy = cby + ly, gz = cbz + lz;
+    float v = 0.0f;
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * nx + gx];
+    sm[lz][ly][lx] = v;
+  }
+  __syncthreads();
+  int i = fbx + threadIdx.x % FN_X, j = fby + (threadIdx.x / FN_X) % FN_Y, k = fbz + threadIdx.x / (FN_X * FN_Y);
+  if (i >= fx || j >= fy || k >= fz) return;
+  int ph = (i % SM) + SM * ((j % SM) + SM * (k % SM));
+  int lx = i / SM - cbx, ly = j / SM - cby, lz = k / SM - cbz;
+  float acc = 0.0f;
+  int nt = c_taps.n[ph];
+  for (int t = 0; t < nt; t++) {
+    int o = c_taps.off[ph][t];
+    acc = fmaf(c_tapw[ph][t], sm[lz + ((o >> 8) & 15) - 4][ly + ((o >> 4) & 15) - 4][lx + (o & 15) - 4], acc);
+  }
+  out[((i64)k * fy + j) * fx + i] = acc + th;
+}
+__global__ void k_add_scalar(i64 n, float *__restrict__ a, float s) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v < n) a[v] = a[v] + s;
+}
+
+static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
+  TapTable T; static float W[8][96];
+  memset(&T, 0, sizeof(T)); memset(W, 0, sizeof(W));
+  float maxd = (float)sqrt(-log(rbf_cut) * cell * cell);            // :221
+  for (int ph = 0; ph < sm * sm * sm; ph++) {
+    int px = ph % sm, py = (ph / sm) % sm, pz = ph / (sm * sm), n = 0;
+    for (int dk = -4; dk <= 4; dk++) for (int dj = -4; dj <= 4; dj++) for (int di = -4; di <= 4; di++) {
+      double ox = di - (double)px / sm, oy = dj - (double)py / sm, oz = dk - (double)pz / sm, m = ox * ox + oy * oy + oz * oz;
+      float dist = (float)(sqrt(m) * cell);
+      if (dist <= maxd) {
+        if (n >= 96) FAIL("rbf: tap table overflow (rbf_cut too small)");
+        if (di < -3 || di > 3 || dj < -3 || dj > 3 || dk < -3 || dk > 3) FAIL("rbf: kernel support too wide for the tile halo");
+        T.off[ph][n] = (di + 4) | ((dj + 4) << 4) | ((dk + 4) << 8); W[ph][n] = (float)exp(-m); n++;
+      }
+    }
+    T.n[ph] = n;
+  }
+  CK(cudaMemcpyToSymbolAsync(c_taps, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(c_tapw, W, sizeof(W), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double target, bool final_volume, float *th_out, float *vol_out) {
+  const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
+  if (ctx->k0 != 0 || ctx->k1 != g.np[2]) FAIL("rbf smoothing on a z-slab needs the halo exchange driver (not available through this entry point)");
+  const int nx = g.np[0], ny = g.np[1], nz = g.np[2]; const i64 n = (i64)nx * ny * nz;
+  const int fx = g.N[0] * smooth + 1, fy = g.N[1] * smooth + 1, fz = g.N[2] * smooth + 1; const i64 nf = (i64)fx * fy * fz;
+  // the stencil form needs the reference's cut to sit strictly between lattice shells (true for the default 1e-3)
+  StencilW W; { double L = -log(rbf_cut); if (!(L > 6.0 && L < 8.0)) FAIL("rbf: only kernel cut-offs with 6 < ln(1/cut) < 8 (81-point stencil) are supported"); for (int m = 0; m < 8; m++) W.w[m] = (float)exp(-(double)m); }
+  CK(cudaEventRecord(ctx->ev[4], st));
+  CK(ctx->f_s.reserve(sizeof(float) * (size_t)n)); CK(ctx->f_lsf.reserve(sizeof(float) * (size_t)n));
+  CK(ctx->f_fine.reserve(sizeof(float) * (size_t)nf));
+  CK(ctx->f_scal.reserve(256));
+  CK(ctx->cutlist.reserve(sizeof(int) * 4096));
+  float *scal = ctx->f_scal.as<float>(); unsigned *ubits = (unsigned *)((char *)ctx->f_scal.p + 64); double *dsc = (double *)((char *)ctx->f_scal.p + 96);
+  CK(cudaMemsetAsync(ctx->f_scal.p, 0, 256, st));
+  float *s = ctx->f_s.as<float>();
+  k_to_f32<<<cdiv(n, 256), 256, 0, st>>>(n, 0, ctx->sdf.as<double>(), s, ubits); LAUNCH_CHECK();
+  unsigned hb = 0;
+  CK(cudaMemcpyAsync(&hb, ubits, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hb == 0) FAIL("RBFs_smoothing: the SDF holds no finite value (maximum over an empty collection, RBFs4Smoothing.jl:17)");
+  k_replace_far<<<cdiv(n, 256), 256, 0, st>>>(n, s, ubits); LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[5], st));
+  dim3 sgrid(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(nz, ST_Z)); int sthreads = ST_X * ST_Y * (ST_Z / ST_ZB);
+  int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = cdiv(n, 256);
+  CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
+  double *part = ctx->f_part.as<double>();
+  const float *wgt = s; int iters = 0;
+  if (is_interp) {
+    // cg(K, s) with IterativeSolvers defaults (:199): x0 = 0, reltol = sqrt(eps(Float32)), maxiter = n
+    CK(ctx->f_w.reserve(sizeof(float) * (size_t)n)); CK(ctx->f_r.reserve(sizeof(float) * (size_t)n));
+    CK(ctx->f_u.reserve(sizeof(float) * 2 * (size_t)n)); CK(ctx->f_c.reserve(sizeof(float) * (size_t)n));
+    float *x = ctx->f_w.as<float>(), *r = ctx->f_r.as<float>(), *u = ctx->f_u.as<float>(), *c = ctx->f_c.as<float>();
+    CK(cudaMemsetAsync(x, 0, sizeof(float) * (size_t)n, st));
+    CK(cudaMemsetAsync(u, 0, sizeof(float) * 2 * (size_t)n, st));
+    CK(cudaMemcpyAsync(r, s, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    k_dot_self<<<nub, 256, 0, st>>>(n, r, part); LAUNCH_CHECK();
+    k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc); LAUNCH_CHECK();
+    k_cg_init<<<1, 1, 0, st>>>(scal, dsc); LAUNCH_CHECK();
+    float hs[8];
+    CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float residual = hs[2], tol = hs[4];
+    float *u_old = u, *u_new = u + n;      // ping-pong halves of the u buffer
+    while (iters < n && !(residual <= tol)) {
+      // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
+      k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, nullptr, r, u_old, u_new, scal, c, part, W); LAUNCH_CHECK();
+      k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
+      k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
+      k_cg_update<<<nub, 256, 0, st>>>(n, scal, u_new, c, x, r, part); LAUNCH_CHECK();
+      k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
+      k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      residual = hs[2]; iters++;
+      { float *t = u_old; u_old = u_new; u_new = t; }
+    }
+    wgt = x;
+  }
+  ctx->rep.cg_iters = iters;
+  CK(cudaEventRecord(ctx->ev[6], st));
+  // LSF on the coarse grid (:357) = K * weights
+  float *lsf = ctx->f_lsf.as<float>();
+  k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W); LAUNCH_CHECK();
+  // LS_Threshold (:265-300)
+  unsigned init_mm[2] = {0xffffffffu, 0u};
+  CK(cudaMemcpyAsync(ubits + 2, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
+  k_minmax<<<cdiv(n, 256), 256, 0, st>>>(n, lsf, ubits + 2); LAUNCH_CHECK();
+  unsigned hmm[2];
+  CK(cudaMemcpyAsync(hmm, ubits + 2, sizeof(hmm), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(ctx->ev[7], st));
+  float lo = ordered_to_float(hmm[0]), hi = ordered_to_float(hmm[1]);
+  // coarse cell edge as the reference measures it: norm(grid[2,1,1] - grid[1,1,1]) with Float32 range() coordinates (:41-43)
+  float edge;
+  {
+    float a = (float)g.amin[0], b = (float)g.amax[0];
+    float x0 = a, x1 = (nx > 1) ? (float)((double)a + 1.0 * (((double)b - (double)a) / (double)(nx - 1))) : a;
+    if (nx == 2) x1 = b;
+    float ex = x1 - x0; edge = sqrtf(ex * ex);
+  }
+  double eps = 1.0; int nb = 0; float th = 0.0f;
+  while (nb < 40 && eps > 1.0e-4) {
+    th = (lo + hi) / 2;
+    double v;
+    if (volume_dev(ctx, lsf, nx, ny, nz, th, edge, 0.0f, &v)) return 1;
+    float cur = (float)v;
+    eps = fabs(target - (double)cur);
+    if ((double)cur > target) lo = th; else hi = th;
+    nb++;
+  }
+  ctx->rep.bisections = nb;
+  float tho = -th;
+  CK(cudaEventRecord(ctx->ev[13], st));
+  // fine grid (:363-366)
+  if (upload_taps(ctx, smooth, rbf_cut, g.cell)) return 1;
+  dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(fz, FN_Z));
+  if (smooth == 1) k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, fz, wgt, tho, ctx->f_fine.as<float>());
+  else k_fine_eval<2><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, fz, wgt, tho, ctx->f_fine.as<float>());
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(ctx->ev[14], st));
+  float volf = 0.0f;
+  if (final_volume) {
+    float a = (float)g.amin[0], b = (float)g.amax[0];
+    float dxf = (b - a) / (float)(fx - 1); float x0 = a, x1 = a + 1.0f * dxf; float e = sqrtf((x1 - x0) * (x1 - x0));
+    double v;
+    if (volume_dev(ctx, ctx->f_fine.as<float>(), fx, fy, fz, 0.0f, e, 0.0f, &v)) return 1;
+    volf = (float)v;
+  }
+  CK(cudaEventRecord(ctx->ev[15], st));
+  CK(cudaStreamSynchronize(st));
+  ctx->smooth_last = smooth;
+  *th_out = tho; *vol_out = volf;
+  CK(cudaEventElapsedTime(&ctx->rep.ms_rbf_prep, ctx->ev[4], ctx->ev[5]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_cg, ctx->ev[5], ctx->ev[6]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_lsf, ctx->ev[6], ctx->ev[7]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_threshold, ctx->ev[7], ctx->ev[13]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_fine, ctx->ev[13], ctx->ev[14]));
+  CK(cudaEventElapsedTime(&ctx->rep.ms_volume, ctx->ev[14], ctx->ev[15]));
+  return 0;
+}

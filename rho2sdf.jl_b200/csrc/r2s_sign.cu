@@ -1,0 +1,194 @@
+// r2s_sign.cu -- Sign_Detection (SignedDistances/SignDetection.jl:6-81 HEX8, :88-268 TET4) on the GPU, fused with
+// sdf_dists = dists .* signs (RhoToSDF.jl:171).
+//
+// The reference scans all nel element AABBs per grid point (O(ngp*nel)).  Here every element is binned into the voxel
+// tiles its candidate point range overlaps ((tile, element) keys, radix sort); a CTA owns one tile, stages the tile's
+// element list (ascending element index = the reference's candidate order) through shared memory together with the
+// element's nodal coordinates/densities, and every thread replays the reference's per-point rule exactly.
+#include "r2s_common.cuh"
+#include "r2s_tables.cuh"
+#include "r2s_exact.cuh"
+
+struct SRange { int a[3], b[3]; };   // inclusive grid-point index range of the candidate points of one element
+
+__device__ __forceinline__ int tet_cell_index(double x, double amin, double cell, int n1) {   // point_to_grid_index :256-268 (1-based, clamped)
+  int idx = (int)floor(ex::dvd(ex::sub(x, amin), cell)) + 1;
+  return max(1, min(n1, idx));
+}
+__global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, GridDev g, int kz0, int kz1,
+                              SRange *__restrict__ rng, i64 *__restrict__ ntile) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+  SRange r; bool ok = true;
+  for (int d = 0; d < 3; d++) {
+    const double *pc = g.pc + g.pc_off[d]; int n1 = g.np[d], a, b;
+    if (nen == 8) {
+      // closed AABB test lo <= x <= hi (sdfOnDensityField.jl:60-69): first point >= lo, last point <= hi (pc is monotone)
+      int l = 0, h = n1;
+      while (l < h) { int m = (l + h) >> 1; if (pc[m] < lo[d]) l = m + 1; else h = m; }
+      a = l; l = 0; h = n1;
+      while (l < h) { int m = (l + h) >> 1; if (pc[m] <= hi[d]) l = m + 1; else h = m; }
+      b = l - 1;
+    } else {
+      // create_grid_tetrahedra_mapping_TET4 (:195-196): cells max(1, floor((lo-min)/cell)-1) .. min(dims, ceil((hi-min)/cell)+1)
+      int mi = (int)floor(ex::dvd(ex::sub(lo[d], g.amin[d]), g.cell)) - 1; if (mi < 1) mi = 1;
+      int ma = (int)ceil(ex::dvd(ex::sub(hi[d], g.amin[d]), g.cell)) + 1; if (ma > n1) ma = n1;
+      a = n1; b = -1;
+      int p0 = max(0, mi - 4), p1 = min(n1 - 1, ma + 3);
+      for (int p = p0; p <= p1; p++) { int idx = tet_cell_index(pc[p], g.amin[d], g.cell, n1); if (idx >= mi && idx <= ma) { if (p < a) a = p; if (p > b) b = p; } }
+    }
+    if (d == 2) { if (a < kz0) a = kz0; if (b > kz1 - 1) b = kz1 - 1; }
+    r.a[d] = a; r.b[d] = b; ok = ok && (a <= b);
+  }
+  if (!ok) { r.a[0] = 1; r.b[0] = 0; }
+  rng[e] = r;
+  ntile[e] = ok ? (i64)(r.b[0] / TILE_X - r.a[0] / TILE_X + 1) * (r.b[1] / TILE_Y - r.a[1] / TILE_Y + 1) * (r.b[2] / TILE_Z - r.a[2] / TILE_Z + 1) : 0;
+}
+__global__ void k_sign_emit(i64 nel, const SRange *__restrict__ rng, const i64 *__restrict__ toff, GridDev g, u64 *__restrict__ keys, int *__restrict__ tile_cnt) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  SRange r = rng[e];
+  if (r.a[0] > r.b[0]) return;
+  i64 o = toff[e];
+  for (int tz = r.a[2] / TILE_Z; tz <= r.b[2] / TILE_Z; tz++)
+    for (int ty = r.a[1] / TILE_Y; ty <= r.b[1] / TILE_Y; ty++)
+      for (int tx = r.a[0] / TILE_X; tx <= r.b[0] / TILE_X; tx++) {
+        u64 t = ((u64)tz * g.nt[1] + ty) * g.nt[0] + tx;
+        keys[o++] = (t << 32) | (u64)e;
+        atomicAdd(&tile_cnt[t], 1);
+      }
+}
+
+#define SB 32   // elements staged per batch
+template <int NEN>
+__global__ void __launch_bounds__(TILE_VOX) k_sign(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
+                                                   const SRange *__restrict__ rng, const int *__restrict__ IEN, const double *__restrict__ X,
+                                                   const double *__restrict__ rn, double rho_t, const double *__restrict__ dist,
+                                                   double *__restrict__ signs, double *__restrict__ sdf) {
+  __shared__ SRange srng[SB];
+  __shared__ double sX[SB][3][NEN];
+  __shared__ double sR[SB][NEN];
+  int t = blockIdx.x;
+  int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
+  int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
+  int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
+  bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  double x[3] = {0, 0, 0};
+  if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
+  double sign = -1.0, mx = -1e300, max_local = 10.0; bool done = false, any = false;
+  int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
+  for (int base = p0; base < p1; base += SB) {
+    int nb = min(SB, p1 - base);
+    __syncthreads();
+    for (int w = threadIdx.x; w < nb * NEN; w += TILE_VOX) {
+      int q = w / NEN, a = w % NEN; int e = (int)(keys[base + q] & 0xffffffffull);
+      i64 n = IEN[NEN * (i64)e + a];
+      sX[q][0][a] = X[3 * n]; sX[q][1][a] = X[3 * n + 1]; sX[q][2][a] = X[3 * n + 2]; sR[q][a] = rn[n];
+      if (a == 0) srng[q] = rng[e];
+    }
+    __syncthreads();
+    if (!valid) continue;
+    for (int q = 0; q < nb; q++) {
+      const SRange &r = srng[q];
+      if (pi[0] < r.a[0] || pi[0] > r.b[0] || pi[1] < r.a[1] || pi[1] > r.b[1] || pi[2] < r.a[2] || pi[2] > r.b[2]) continue;
+      if (NEN == 8) {
+        any = true;
+#pragma unroll
+        for (int a = 0; a < 8; a++) mx = fmax(mx, sR[q][a]);
+        if (done) continue;
+        double Xe[3][8], re[8], xi[3], N[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) { Xe[0][a] = sX[q][0][a]; Xe[1][a] = sX[q][1][a]; Xe[2][a] = sX[q][2][a]; re[a] = sR[q][a]; }
+        ex::inverse_map_hex8(Xe, x, xi);
+        double mn = ex::max3abs(xi[0], xi[1], xi[2]);
+        if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
+          ex::hex8_shape(xi, N);
+          double rho = ex::dot8(N, re);
+          if (rho >= rho_t) sign = 1.0;
+          if (mn < 0.95) done = true;                              // :51-59 break
+          max_local = mn;
+        }
+      } else {
+        if (done) continue;
+        double Xe[3][4], re[4], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+        for (int a = 0; a < 4; a++) { re[a] = sR[q][a];
+#pragma unroll
+          for (int d = 0; d < 3; d++) { double c = sX[q][d][a]; Xe[d][a] = c; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+        // is_point_in_tetrahedron (:220-242), tolerance 1e-10
+        const double tol = 1e-10; bool out = false;
+#pragma unroll
+        for (int d = 0; d < 3; d++) if (x[d] < ex::sub(lo[d], tol) || x[d] > ex::add(hi[d], tol)) out = true;
+        if (out) continue;
+        double A[3][3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { A[d][0] = ex::sub(Xe[d][1], Xe[d][0]); A[d][1] = ex::sub(Xe[d][2], Xe[d][0]); A[d][2] = ex::sub(Xe[d][3], Xe[d][0]); b[d] = ex::sub(x[d], Xe[d][0]); }
+        using namespace ex;
+        double c00 = sub(mul(A[1][1], A[2][2]), mul(A[1][2], A[2][1])), c01 = sub(mul(A[1][2], A[2][0]), mul(A[1][0], A[2][2])), c02 = sub(mul(A[1][0], A[2][1]), mul(A[1][1], A[2][0]));
+        double det = add(add(mul(A[0][0], c00), mul(A[0][1], c01)), mul(A[0][2], c02));
+        if (!(fabs(det) > 0.0)) continue;
+        double c10 = sub(mul(A[0][2], A[2][1]), mul(A[0][1], A[2][2])), c11 = sub(mul(A[0][0], A[2][2]), mul(A[0][2], A[2][0])), c12 = sub(mul(A[0][1], A[2][0]), mul(A[0][0], A[2][1]));
+        double c20 = sub(mul(A[0][1], A[1][2]), mul(A[0][2], A[1][1])), c21 = sub(mul(A[0][2], A[1][0]), mul(A[0][0], A[1][2])), c22 = sub(mul(A[0][0], A[1][1]), mul(A[0][1], A[1][0]));
+        double l2 = dvd(add(add(mul(c00, b[0]), mul(c10, b[1])), mul(c20, b[2])), det), l3 = dvd(add(add(mul(c01, b[0]), mul(c11, b[1])), mul(c21, b[2])), det),
+               l4 = dvd(add(add(mul(c02, b[0]), mul(c12, b[1])), mul(c22, b[2])), det);
+        double l1 = sub(1.0, add(add(l2, l3), l4));
+        if (!(l1 >= -tol && l2 >= -tol && l3 >= -tol && l4 >= -tol && l1 <= 1.0 + tol && l2 <= 1.0 + tol && l3 <= 1.0 + tol && l4 <= 1.0 + tol)) continue;
+        double lc[3];
+        if (!inverse_map_tet4(Xe, x, lc)) continue;               // found == false (:132)
+        double l4b = sub(1.0, add(add(lc[0], lc[1]), lc[2]));
+        double rho = add(add(add(mul(lc[0], re[0]), mul(lc[1], re[1])), mul(lc[2], re[2])), mul(l4b, re[3]));
+        if (rho >= rho_t) { sign = 1.0; done = true; }
+      }
+    }
+  }
+  if (valid) {
+    if (NEN == 8 && (!any || mx < rho_t)) sign = -1.0;            // :36 skip
+    i64 v = ((i64)pi[2] * g.np[1] + pi[1]) * g.np[0] + pi[0];
+    if (signs) signs[v] = sign;
+    if (sdf) sdf[v] = dist[v] * sign;
+  }
+}
+
+int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
+  if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
+  if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
+  const GridDev &g = ctx->g; cudaStream_t st = ctx->stream; i64 nel = ctx->nel; int nen = ctx->nen;
+  int kz0 = (int)ctx->k0, kz1 = (int)ctx->k1;
+  CK(ctx->s_rng.reserve(sizeof(SRange) * (size_t)nel));
+  CK(ctx->cnt_a.reserve(sizeof(i64) * (size_t)(nel + 1)));
+  CK(ctx->cnt_b.reserve(sizeof(i64) * (size_t)(nel + 1)));
+  CK(ctx->s_tile_ptr.reserve(sizeof(int) * (size_t)(g.ntiles + 2)));
+  CK(ctx->s_cnt.reserve(sizeof(int) * (size_t)(g.ntiles + 2)));
+  CK(cudaMemsetAsync(ctx->s_tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
+  CK(cudaMemsetAsync(ctx->cnt_a.as<i64>() + nel, 0, sizeof(i64), st));
+  i64 *ntile = ctx->cnt_a.as<i64>(), *toff = ctx->cnt_b.as<i64>();
+  k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, kz0, kz1, ctx->s_rng.as<SRange>(), ntile); LAUNCH_CHECK();
+  if (r2s_scan_exclusive_i64(ctx, ntile, toff, nel + 1)) return 1;
+  i64 nkeys = 0;
+  CK(cudaMemcpyAsync(&nkeys, toff + nel, sizeof(i64), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (nkeys >= (1ll << 31)) FAIL("sign binning: too many (tile, element) pairs for one slab");
+  u64 *sorted = nullptr;
+  if (nkeys > 0) {
+    CK(ctx->s_keys.reserve(sizeof(u64) * (size_t)nkeys));
+    CK(ctx->s_keys_alt.reserve(sizeof(u64) * (size_t)nkeys));
+    k_sign_emit<<<cdiv(nel, 128), 128, 0, st>>>(nel, ctx->s_rng.as<SRange>(), toff, g, ctx->s_keys.as<u64>(), ctx->s_tile_ptr.as<int>() + 1); LAUNCH_CHECK();
+    int tbits = 1; while ((1ll << tbits) < g.ntiles) tbits++;
+    if (r2s_sort_keys_u64(ctx, ctx->s_keys.as<u64>(), ctx->s_keys_alt.as<u64>(), nkeys, 32 + tbits, &sorted)) return 1;
+  }
+  if (r2s_scan_exclusive_i32(ctx, ctx->s_tile_ptr.as<int>() + 1, ctx->s_cnt.as<int>(), g.ntiles + 1)) return 1;
+  CK(cudaMemcpyAsync(ctx->s_tile_ptr.as<int>(), ctx->s_cnt.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
+  double *signs = nullptr, *sdf = nullptr;
+  if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
+  if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
+  if (nen == 8)
+    k_sign<8><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
+                                                       ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
+  else
+    k_sign<4><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
+                                                       ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
+  LAUNCH_CHECK();
+  return 0;
+}
