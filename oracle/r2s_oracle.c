@@ -308,15 +308,30 @@ static int cell_range(const ogrid *g, const double lo[3], const double hi[3], do
  * decision-critical: fixed operation order, mirrored bit-for-bit by the CUDA device function)
  * returns 1 and xi on success, 0 and xi=(10,10,10) on failure (FindLocalCoordinates.jl:106)
  * ---------------------------------------------------------------------------------------------- */
+/* monomial coefficients of a trilinear field v = A0 + A1 x + A2 e + A3 z + A4 xe + A5 ez + A6 zx + A7 xez from its nodal
+ * values (node order of hex8_shape.jl:27-34); fixed operation order */
+static void mono8(const double v[8], double A[8]) {
+  double s01 = v[0] + v[1], d01 = v[1] - v[0], s32 = v[3] + v[2], d32 = v[2] - v[3];
+  double s45 = v[4] + v[5], d45 = v[5] - v[4], s76 = v[7] + v[6], d76 = v[6] - v[7];
+  double b0 = s01 + s32, b1 = d01 + d32, b2 = s32 - s01, b3 = d32 - d01;
+  double t0 = s45 + s76, t1 = d45 + d76, t2 = s76 - s45, t3 = d76 - d45;
+  A[0] = 0.125 * (b0 + t0); A[1] = 0.125 * (b1 + t1); A[2] = 0.125 * (b2 + t2); A[4] = 0.125 * (b3 + t3);
+  A[3] = 0.125 * (t0 - b0); A[6] = 0.125 * (t1 - b1); A[5] = 0.125 * (t2 - b2); A[7] = 0.125 * (t3 - b3);
+}
 static int inverse_map_hex8(const double Xe[3][8], const double x[3], double xi[3]) {
+  double A[3][8]; int affine = 1;
+  for (int d = 0; d < 3; d++) { mono8(Xe[d], A[d]); if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = 0; }
   xi[0] = xi[1] = xi[2] = 0.0;
   for (int it = 0; it < 50; it++) {
-    double N[8], dN[8][3]; hex8_shape_d(xi, N, dN);
+    double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
     double r[3], J[3][3];
     for (int d = 0; d < 3; d++) {
-      double s = Xe[d][0] * N[0]; for (int a = 1; a < 8; a++) s = s + Xe[d][a] * N[a];
-      r[d] = s - x[d];
-      for (int c = 0; c < 3; c++) { double t = Xe[d][0] * dN[0][c]; for (int a = 1; a < 8; a++) t = t + Xe[d][a] * dN[a][c]; J[d][c] = t; }
+      const double *a = A[d];
+      double val = ((((((a[0] + a[1] * X) + a[2] * E) + a[3] * Z) + a[4] * xe) + a[5] * ez) + a[6] * zx) + a[7] * xez;
+      r[d] = val - x[d];
+      J[d][0] = ((a[1] + a[4] * E) + a[6] * Z) + a[7] * ez;
+      J[d][1] = ((a[2] + a[4] * X) + a[5] * Z) + a[7] * zx;
+      J[d][2] = ((a[3] + a[5] * E) + a[6] * X) + a[7] * xe;
     }
     /* solve J dx = r by the adjugate (cofactor) formula */
     double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
@@ -330,6 +345,7 @@ static int inverse_map_hex8(const double Xe[3][8], const double x[3], double xi[
     xi[0] = xi[0] - d0; xi[1] = xi[1] - d1; xi[2] = xi[2] - d2;
     double m = fmax(fabs(d0), fmax(fabs(d1), fabs(d2)));
     if (!(m < 1.0e3) || !(fmax(fabs(xi[0]), fmax(fabs(xi[1]), fabs(xi[2]))) < 1.0e3)) break;   /* diverged / NaN */
+    if (affine) return 1;                    /* parallelepiped: the map is affine, one Newton step is exact */
     if (m < 1.0e-13) return 1;
   }
   xi[0] = xi[1] = xi[2] = 10.0; return 0;

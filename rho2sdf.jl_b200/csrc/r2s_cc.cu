@@ -47,7 +47,10 @@ __global__ void k_cc_flatten(i64 n, int *__restrict__ L, int *__restrict__ sz) {
   int r = (int)v;
   while (true) { int p = L[r]; if (p == r) break; r = p; }
   L[v] = r;
-  atomicAdd(&sz[r], 1);
+  // one atomic per distinct root per warp (the largest component would otherwise serialise on a single address)
+  unsigned act = __activemask();
+  unsigned peers = __match_any_sync(act, r);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sz[r], __popc(peers));
 }
 __global__ void k_cc_largest(i64 n, const int *__restrict__ L, const int *__restrict__ sz, u64 *__restrict__ best) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;

@@ -59,7 +59,7 @@ __global__ void k_act_records(i64 nel, int nen, const int *__restrict__ IEN, con
   npair[a] = np; nchunk[a] = (np + 31) / 32;
 }
 __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__restrict__ toff, const i64 *__restrict__ poff, GridDev g,
-                            u64 *__restrict__ keys, int *__restrict__ tile_cnt) {
+                            u64 *__restrict__ keys, int *__restrict__ tile_cnt, unsigned char *__restrict__ tile_faces) {
   i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (a >= nact) return;
   ActRec r = rec[a];
@@ -72,6 +72,7 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
         u64 t = ((u64)tz * g.nt[1] + ty) * g.nt[0] + tx;
         keys[o++] = (t << 32) | (u64)a;
         atomicAdd(&tile_cnt[t], 1);
+        if (r.fmask) tile_faces[t] = 1;       // this tile needs the boundary-face path of the assemble kernel
       }
 }
 
@@ -253,40 +254,58 @@ __device__ inline void boundary_faces_point(const ActRec &r, const int *__restri
   }
 }
 
-template <bool WANT_XP, int NEN>
-__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
+// One CTA per tile, one thread per grid point; the tile's element list is culled per warp (footprint 8x4x1 points) into
+// shared memory in list order, then every lane replays ITS candidates in ascending element order.
+#define ACULL_CAP 96
+// FACES = false: tiles whose list holds no element with boundary faces (the vast majority) run a light variant with a
+// small register footprint; FACES = true handles the others.  Both walk all tiles and skip those of the other kind.
+template <bool WANT_XP, int NEN, bool FACES>
+__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
                                                        const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
                                                        const double *__restrict__ rn, double rho_t, double delta, const double *__restrict__ pairbuf,
                                                        const double *__restrict__ pairxp, double *__restrict__ dist, double *__restrict__ xpo) {
-  __shared__ ActRec srec[64];
-  int t = blockIdx.x;
-  int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
-  int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
-  int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
-  bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  __shared__ ActRec srec[TILE_VOX / 32][ACULL_CAP];
+  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((tile_faces[t] != 0) != FACES) return;
+  const int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
+  const int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
+  const int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
+  const bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  const int wx0 = tx * TILE_X, wx1 = wx0 + TILE_X - 1, wy0 = ty * TILE_Y + (warp % (TILE_Y / 4)) * 4, wy1 = wy0 + 3, wz = tz * TILE_Z + warp / (TILE_Y / 4);
   double x[3] = {0, 0, 0};
   if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
   VoxState s; s.c = -R2S_BIG; s.xp[0] = s.xp[1] = s.xp[2] = 0.0;
-  int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
-  for (int base = p0; base < p1; base += 64) {
-    int nb = min(64, p1 - base);
-    __syncthreads();
-    if (threadIdx.x < nb) srec[threadIdx.x] = rec[(int)(keys[base + threadIdx.x] & 0xffffffffull)];
-    __syncthreads();
-    if (!valid) continue;
-    for (int q = 0; q < nb; q++) {
-      const ActRec &r = srec[q];
-      if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
-      if (r.fmask) boundary_faces_point<WANT_XP, NEN>(r, IEN, X, rn, g, rho_t, delta, pi, x, s);
-      if (r.cls == 2) {
-        i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
-        double dt = pairbuf[idx];
-        if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
-          s.c = dt;
-          if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+  const int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
+  int p = p0;
+  while (p < p1) {
+    int n = 0;
+    while (p < p1 && n <= ACULL_CAP - 32) {
+      int idx = p + lane; bool ov = false; ActRec r;
+      if (idx < p1) {
+        r = rec[(int)(keys[idx] & 0xffffffffull)];
+        ov = r.ps[0] <= wx1 && r.pe[0] > wx0 && r.ps[1] <= wy1 && r.pe[1] > wy0 && r.ps[2] <= wz && r.pe[2] > wz;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, ov);
+      if (ov) srec[warp][n + __popc(m & ((1u << lane) - 1))] = r;
+      n += __popc(m); p += 32;
+    }
+    __syncwarp();
+    if (valid) {
+      for (int q = 0; q < n; q++) {
+        const ActRec &r = srec[warp][q];
+        if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
+        if (FACES && r.fmask) boundary_faces_point<WANT_XP, NEN>(r, IEN, X, rn, g, rho_t, delta, pi, x, s);
+        if (r.cls == 2) {
+          i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
+          double dt = pairbuf[idx];
+          if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
+            s.c = dt;
+            if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+          }
         }
       }
     }
+    __syncwarp();
   }
   if (valid) {
     i64 v = ((i64)pi[2] * g.np[1] + pi[1]) * g.np[0] + pi[0];
@@ -321,6 +340,8 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   if (want_xp) CK(ctx->xp.reserve(sizeof(double) * 3 * (size_t)g.ngp));
   CK(ctx->tile_ptr.reserve(sizeof(int) * (size_t)(g.ntiles + 2)));
   CK(cudaMemsetAsync(ctx->tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
+  CK(ctx->tile_faces.reserve((size_t)g.ntiles + 16));
+  CK(cudaMemsetAsync(ctx->tile_faces.p, 0, (size_t)g.ntiles, st));
   i64 npairs = 0, nkeys = 0, nitems = 0;
   u64 *sorted = nullptr;
   if (nact > 0) {
@@ -347,7 +368,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     CK(ctx->keys_alt.reserve(sizeof(u64) * (size_t)(nkeys + 1)));
     CK(ctx->pairbuf.reserve(sizeof(double) * (size_t)(npairs + 1)));
     if (want_xp) CK(ctx->pairxp.reserve(sizeof(double) * 3 * (size_t)(npairs + 1)));
-    k_emit_keys<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff, poff, g, ctx->keys.as<u64>(), ctx->tile_ptr.as<int>() + 1); LAUNCH_CHECK();
+    k_emit_keys<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff, poff, g, ctx->keys.as<u64>(), ctx->tile_ptr.as<int>() + 1, ctx->tile_faces.as<unsigned char>()); LAUNCH_CHECK();
     int tbits = 1; while ((1ll << tbits) < g.ntiles) tbits++;
     if (nkeys > 0) { if (r2s_sort_keys_u64(ctx, ctx->keys.as<u64>(), ctx->keys_alt.as<u64>(), nkeys, 32 + tbits, &sorted)) return 1; }
   }
@@ -371,12 +392,11 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   {
-#define ASM(XP, NEN) k_assemble<XP, NEN><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_ptr.as<int>(), sorted, ctx->act_rec.as<ActRec>(), \
-        ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
-        ctx->dist.as<double>(), ctx->xp.as<double>())
-    if (nen == 8) { if (want_xp) ASM(true, 8); else ASM(false, 8); }
-    else { if (want_xp) ASM(true, 4); else ASM(false, 4); }
-    LAUNCH_CHECK();
+#define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
+        ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
+        ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
+    if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
+    else { if (want_xp) { ASM(true, 4, false); ASM(true, 4, true); } else { ASM(false, 4, false); ASM(false, 4, true); } }
 #undef ASM
   }
   CK(cudaEventRecord(ctx->ev[3], st));

@@ -45,27 +45,31 @@ __device__ __forceinline__ double dot8(const double a[8], const double b[8]) {
   return s;
 }
 
-// Inverse isoparametric map of a HEX8 (restates SignedDistances/FindLocalCoordinates.jl:16-107 as a converged
-// Newton iteration from xi = 0).  Xe[d][a].  Returns true on success; (10,10,10) otherwise (:106).
-__device__ inline bool inverse_map_hex8(const double Xe[3][8], const double x[3], double xi[3]) {
+// monomial coefficients of a trilinear field v = A0 + A1 x + A2 e + A3 z + A4 xe + A5 ez + A6 zx + A7 xez from its nodal values
+__device__ __forceinline__ void mono8(const double v[8], double A[8]) {
+  double s01 = add(v[0], v[1]), d01 = sub(v[1], v[0]), s32 = add(v[3], v[2]), d32 = sub(v[2], v[3]);
+  double s45 = add(v[4], v[5]), d45 = sub(v[5], v[4]), s76 = add(v[7], v[6]), d76 = sub(v[6], v[7]);
+  double b0 = add(s01, s32), b1 = add(d01, d32), b2 = sub(s32, s01), b3 = sub(d32, d01);
+  double t0 = add(s45, s76), t1 = add(d45, d76), t2 = sub(s76, s45), t3 = sub(d76, d45);
+  A[0] = mul(0.125, add(b0, t0)); A[1] = mul(0.125, add(b1, t1)); A[2] = mul(0.125, add(b2, t2)); A[4] = mul(0.125, add(b3, t3));
+  A[3] = mul(0.125, sub(t0, b0)); A[6] = mul(0.125, sub(t1, b1)); A[5] = mul(0.125, sub(t2, b2)); A[7] = mul(0.125, sub(t3, b3));
+}
+// Inverse isoparametric map of a HEX8 (restates SignedDistances/FindLocalCoordinates.jl:16-107 as a converged Newton
+// iteration from xi = 0 on the monomial form).  A[d][8] from mono8 of the nodal coordinates, `affine` = all mixed
+// coefficients are exactly zero (parallelepiped: one step is exact).  Returns true on success; (10,10,10) otherwise (:106).
+__device__ inline bool inverse_map_hex8_mono(const double A[3][8], bool affine, const double x[3], double xi[3]) {
   xi[0] = xi[1] = xi[2] = 0.0;
   for (int it = 0; it < 50; it++) {
-    double N[8], dN[8][3];
-    hex8_shape_d(xi, N, dN);
+    double X = xi[0], E = xi[1], Z = xi[2], xe = mul(X, E), ez = mul(E, Z), zx = mul(Z, X), xez = mul(xe, Z);
     double r[3], J[3][3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      double s = mul(Xe[d][0], N[0]);
-#pragma unroll
-      for (int a = 1; a < 8; a++) s = add(s, mul(Xe[d][a], N[a]));
-      r[d] = sub(s, x[d]);
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        double t = mul(Xe[d][0], dN[0][c]);
-#pragma unroll
-        for (int a = 1; a < 8; a++) t = add(t, mul(Xe[d][a], dN[a][c]));
-        J[d][c] = t;
-      }
+      const double *a = A[d];
+      double val = add(add(add(add(add(add(add(a[0], mul(a[1], X)), mul(a[2], E)), mul(a[3], Z)), mul(a[4], xe)), mul(a[5], ez)), mul(a[6], zx)), mul(a[7], xez));
+      r[d] = sub(val, x[d]);
+      J[d][0] = add(add(add(a[1], mul(a[4], E)), mul(a[6], Z)), mul(a[7], ez));
+      J[d][1] = add(add(add(a[2], mul(a[4], X)), mul(a[5], Z)), mul(a[7], zx));
+      J[d][2] = add(add(add(a[3], mul(a[5], E)), mul(a[6], X)), mul(a[7], xe));
     }
     double c00 = sub(mul(J[1][1], J[2][2]), mul(J[1][2], J[2][1])), c01 = sub(mul(J[1][2], J[2][0]), mul(J[1][0], J[2][2])),
            c02 = sub(mul(J[1][0], J[2][1]), mul(J[1][1], J[2][0]));
@@ -81,10 +85,17 @@ __device__ inline bool inverse_map_hex8(const double Xe[3][8], const double x[3]
     xi[0] = sub(xi[0], d0); xi[1] = sub(xi[1], d1); xi[2] = sub(xi[2], d2);
     double m = max3abs(d0, d1, d2);
     if (!(m < 1.0e3) || !(max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) break;
+    if (affine) return true;
     if (m < 1.0e-13) return true;
   }
   xi[0] = xi[1] = xi[2] = 10.0;
   return false;
+}
+__device__ inline bool inverse_map_hex8(const double Xe[3][8], const double x[3], double xi[3]) {
+  double A[3][8]; bool affine = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { mono8(Xe[d], A[d]); if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false; }
+  return inverse_map_hex8_mono(A, affine, x, xi);
 }
 // TET4: FindLocalCoordinates.jl:110-149 (adjugate solve), returns validity per ElementTypes.jl:104-106
 __device__ inline bool inverse_map_tet4(const double Xe[3][4], const double x[3], double lc[3]) {

@@ -157,50 +157,83 @@ __global__ void k_minmax(i64 n, const float *__restrict__ a, unsigned *__restric
 static inline float ordered_to_float(unsigned b) { b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b; float f; memcpy(&f, &b, 4); return f; }
 
 // ------------------------------------------------------------------------------------------------ volume (CalcVolumeFromSDF.jl:26-125)
-// pass 1: classify cells of (sdf - th): full cells counted, cut cells appended to a list
-__global__ void k_vol_classify(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
-  i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
-  i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  bool full = false, cut = false;
-  if (c < ncell) {
+// pass 1: classify cells of (sdf - th): full cells counted, cut cells appended to a list.  Grid-stride; counts are
+// aggregated per block (one atomic per block for the full cells, one per block-iteration for the list slots).
+__global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, u64 *__restrict__ acc,
+                                                      int *__restrict__ cutlist, int cutcap) {
+  __shared__ int s_warp[8]; __shared__ int s_base;
+  const i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1), sxy = (i64)nx * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nfull = 0;
+  for (i64 c0 = (i64)blockIdx.x * 256; c0 < ncell; c0 += (i64)gridDim.x * 256) {
+    i64 c = c0 + threadIdx.x; bool cut = false;
+    if (c < ncell) {
+      int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
+      i64 b = ((i64)k * ny + j) * nx + i;
+      float v0 = sdf[b] - th, v1 = sdf[b + 1] - th, v2 = sdf[b + nx] - th, v3 = sdf[b + nx + 1] - th;
+      float v4 = sdf[b + sxy] - th, v5 = sdf[b + sxy + 1] - th, v6 = sdf[b + sxy + nx] - th, v7 = sdf[b + sxy + nx + 1] - th;
+      float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
+      float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
+      if (!(mx < iso)) { if (mn >= iso) nfull++; else cut = true; }
+    }
+    unsigned mc = __ballot_sync(0xffffffffu, cut);
+    if (__syncthreads_or(mc != 0)) {
+      if (lane == 0) s_warp[warp] = __popc(mc);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { int t = s_warp[w]; s_warp[w] = tot; tot += t; }
+        s_base = (int)atomicAdd(&acc[1], (u64)tot);
+      }
+      __syncthreads();
+      if (cut) { int slot = s_base + s_warp[warp] + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = (int)c; }
+      __syncthreads();
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) nfull += __shfl_down_sync(0xffffffffu, nfull, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = nfull;
+  __syncthreads();
+  if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += s_warp[w]; if (tot) atomicAdd(&acc[0], (u64)tot); }
+}
+// pass 2: one warp per cut cell (grid-stride over the list; the count is read from device memory so that no host
+// round trip separates the two passes).  Lanes own (iq, jq) Gauss-point pairs and run the kq loop; every point value is
+// evaluated with the reference's expression order (xi, then eta, then zeta lerps).  The cell's Float32 partial sum of
+// w_i w_j w_k over inside points is accumulated as a 2^-37 fixed-point integer (deterministic).
+struct GaussF { float x[9]; float w[9]; };
+__global__ void __launch_bounds__(256) k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
+                                                 GaussF G, u64 *__restrict__ acc) {
+  __shared__ float gx[9], gw[9];
+  if (threadIdx.x < 9) { gx[threadIdx.x] = (G.x[threadIdx.x] + 1) / 2; gw[threadIdx.x] = G.w[threadIdx.x]; }
+  __syncthreads();
+  int ncut = (int)min((u64)cutcap, acc[1]);
+  int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  u64 local = 0;
+  for (int wid = (int)((blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5); wid < ncut; wid += nwarps) {
+    i64 c = cutlist[wid];
     int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
     i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
-    float v0 = sdf[b] - th, v1 = sdf[b + 1] - th, v2 = sdf[b + nx] - th, v3 = sdf[b + nx + 1] - th;
-    float v4 = sdf[b + sxy] - th, v5 = sdf[b + sxy + 1] - th, v6 = sdf[b + sxy + nx] - th, v7 = sdf[b + sxy + nx + 1] - th;
-    float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
-    float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
-    if (!(mx < iso)) { if (mn >= iso) full = true; else cut = true; }
+    float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
+    float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+    float part = 0.0f;
+    for (int q = lane; q < 81; q += 32) {
+      int iq = q % 9, jq = q / 9;
+      float xi = gx[iq], eta = gx[jq];
+      float c00 = c000 * (1.0f - xi) + c100 * xi, c01 = c001 * (1.0f - xi) + c101 * xi;
+      float c10 = c010 * (1.0f - xi) + c110 * xi, c11 = c011 * (1.0f - xi) + c111 * xi;
+      float c0 = c00 * (1.0f - eta) + c10 * eta, c1 = c01 * (1.0f - eta) + c11 * eta;
+      float wij = gw[iq] * gw[jq];
+#pragma unroll
+      for (int kq = 0; kq < 9; kq++) {
+        float zeta = gx[kq];
+        float ps = c0 * (1.0f - zeta) + c1 * zeta;
+        if (ps >= iso) part += wij * gw[kq];
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0) local += (u64)llrint((double)part * 137438953472.0);      // part in [0,8]; 2^37 per unit, exact for a float
   }
-  unsigned mf = __ballot_sync(0xffffffffu, full), mc = __ballot_sync(0xffffffffu, cut);
-  int lane = threadIdx.x & 31, base = 0;
-  if (lane == 0) { if (mf) atomicAdd(&acc[0], (u64)__popc(mf)); if (mc) base = (int)atomicAdd(&acc[1], (u64)__popc(mc)); }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (cut) { int slot = base + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = (int)c; }
-}
-// pass 2: one warp per cut cell, 9^3 Gauss points over the lanes; the cell's Float32 partial volume (in units of the
-// cell volume) is accumulated as a 2^-40 fixed-point integer (deterministic)
-struct GaussF { float x[9]; float w[9]; };
-__global__ void k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int ncut, GaussF G,
-                          u64 *__restrict__ acc) {
-  int wid = (int)((blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (wid >= ncut) return;
-  i64 c = cutlist[wid];
-  int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
-  i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
-  float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
-  float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
-  float part = 0.0f;       // sum of w_i w_j w_k over inside points (the Jacobian h^3/8 is applied on the host)
-  for (int q = lane; q < 729; q += 32) {
-    int iq = q % 9, jq = (q / 9) % 9, kq = q / 81;
-    float xi = (G.x[iq] + 1) / 2, eta = (G.x[jq] + 1) / 2, zeta = (G.x[kq] + 1) / 2;
-    float c00 = c000 * (1.0f - xi) + c100 * xi, c01 = c001 * (1.0f - xi) + c101 * xi;
-    float c10 = c010 * (1.0f - xi) + c110 * xi, c11 = c011 * (1.0f - xi) + c111 * xi;
-    float c0 = c00 * (1.0f - eta) + c10 * eta, c1 = c01 * (1.0f - eta) + c11 * eta;
-    float ps = c0 * (1.0f - zeta) + c1 * zeta;
-    if (ps >= iso) part += G.w[iq] * G.w[jq] * G.w[kq];
-  }
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-  if (lane == 0) atomicAdd(&acc[2], (u64)llrint((double)part * 137438953472.0));      // part in [0,8]; 2^37 per unit, exact for a float
+  if (lane == 0 && local) atomicAdd(&acc[2], local);
 }
 static GaussF gauss9f() { GaussTab t = gauss_legendre_host(9); GaussF g; for (int i = 0; i < 9; i++) { g.x[i] = (float)t.x[i]; g.w[i] = (float)t.w[i]; } return g; }
 
@@ -210,28 +243,22 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("calculate_volume_from_sdf: grid too large for 32-bit cell ids");
   CK(ctx->f_scal.reserve(256));
-  int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
   u64 *acc = (u64 *)((char *)ctx->f_scal.p + 128);
+  static const GaussF G9 = gauss9f();
   for (int attempt = 0; attempt < 2; attempt++) {
+    int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(acc, 0, sizeof(u64) * 4, st));
-    k_vol_classify<<<cdiv(ncell, 256), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
-    u64 h[2];
+    k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
+    k_vol_cut<<<148 * 4, 256, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc); LAUNCH_CHECK();
+    u64 h[3];
     CK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if ((i64)h[1] > cutcap) {     // grow the cut list and redo the classification
-      CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 4 + 1024)));
-      cutcap = (int)(ctx->cutlist.cap / sizeof(int));
+    if ((i64)h[1] > cutcap) {     // the cut list was too small: grow it and redo both passes
+      CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
       continue;
     }
-    int ncut = (int)h[1];
-    u64 fixed = 0;
-    if (ncut > 0) {
-      k_vol_cut<<<cdiv((i64)ncut * 32, 256), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), ncut, gauss9f(), acc); LAUNCH_CHECK();
-      CK(cudaMemcpyAsync(&fixed, acc + 2, sizeof(u64), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
     float ev = edge * edge * edge, jac = ev / 8.0f;
-    *vol = (double)h[0] * (double)ev + ((double)fixed / 137438953472.0 /* 2^37 */) * (double)jac;
+    *vol = (double)h[0] * (double)ev + ((double)h[2] / 137438953472.0 /* 2^37 */) * (double)jac;
     return 0;
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
@@ -385,11 +412,12 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     if (nx == 2) x1 = b;
     float ex = x1 - x0; edge = sqrtf(ex * ex);
   }
-  double eps = 1.0; int nb = 0; float th = 0.0f;
+  double eps = 1.0; int nb = 0; float th = 0.0f; double v = 0.0; bool have_prev = false; float th_prev = 0.0f;
   while (nb < 40 && eps > 1.0e-4) {
     th = (lo + hi) / 2;
-    double v;
-    if (volume_dev(ctx, lsf, nx, ny, nz, th, edge, 0.0f, &v)) return 1;
+    // once lo and hi are adjacent floats the midpoint repeats: the volume of an identical threshold is not recomputed
+    if (!(have_prev && th == th_prev)) { if (volume_dev(ctx, lsf, nx, ny, nz, th, edge, 0.0f, &v)) return 1; }
+    have_prev = true; th_prev = th;
     float cur = (float)v;
     eps = fabs(target - (double)cur);
     if ((double)cur > target) lo = th; else hi = th;

@@ -61,87 +61,119 @@ __global__ void k_sign_emit(i64 nel, const SRange *__restrict__ rng, const i64 *
       }
 }
 
-#define SB 32   // elements staged per batch
+// One CTA per tile, one thread per grid point.  Each WARP walks the tile's element list 32 entries at a time, keeps the
+// entries whose candidate range overlaps the warp's 8x4x1 point footprint (ballot compaction into shared memory, order
+// preserved), then every lane advances through that culled list on its own: all lanes run the expensive inverse map at
+// the same time, each on its own next candidate, instead of serialising over elements.
+#define CULL_CAP 96
 template <int NEN>
-__global__ void __launch_bounds__(TILE_VOX) k_sign(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
+__global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
                                                    const SRange *__restrict__ rng, const int *__restrict__ IEN, const double *__restrict__ X,
                                                    const double *__restrict__ rn, double rho_t, const double *__restrict__ dist,
                                                    double *__restrict__ signs, double *__restrict__ sdf) {
-  __shared__ SRange srng[SB];
-  __shared__ double sX[SB][3][NEN];
-  __shared__ double sR[SB][NEN];
-  int t = blockIdx.x;
-  int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
-  int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
-  int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
-  bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  __shared__ int s_el[TILE_VOX / 32][CULL_CAP];
+  __shared__ SRange s_rg[TILE_VOX / 32][CULL_CAP];
+  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
+  const int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
+  const int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
+  const bool valid = pi[0] < g.np[0] && pi[1] < g.np[1] && pi[2] < g.np[2] && pi[2] >= kz0 && pi[2] < kz1;
+  // footprint of this warp (TILE_X = 8 points in x, 4 rows in y, one plane in z)
+  const int wx0 = tx * TILE_X, wx1 = wx0 + TILE_X - 1, wy0 = ty * TILE_Y + (warp % (TILE_Y / 4)) * 4, wy1 = wy0 + 3, wz = tz * TILE_Z + warp / (TILE_Y / 4);
   double x[3] = {0, 0, 0};
   if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
   double sign = -1.0, mx = -1e300, max_local = 10.0; bool done = false, any = false;
-  int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
-  for (int base = p0; base < p1; base += SB) {
-    int nb = min(SB, p1 - base);
-    __syncthreads();
-    for (int w = threadIdx.x; w < nb * NEN; w += TILE_VOX) {
-      int q = w / NEN, a = w % NEN; int e = (int)(keys[base + q] & 0xffffffffull);
-      i64 n = IEN[NEN * (i64)e + a];
-      sX[q][0][a] = X[3 * n]; sX[q][1][a] = X[3 * n + 1]; sX[q][2][a] = X[3 * n + 2]; sR[q][a] = rn[n];
-      if (a == 0) srng[q] = rng[e];
+  const int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
+  int p = p0;
+  while (p < p1) {
+    int n = 0;
+    while (p < p1 && n <= CULL_CAP - 32) {
+      int idx = p + lane; bool ov = false; int e = 0; SRange r;
+      if (idx < p1) {
+        e = (int)(keys[idx] & 0xffffffffull); r = rng[e];
+        ov = r.a[0] <= wx1 && r.b[0] >= wx0 && r.a[1] <= wy1 && r.b[1] >= wy0 && r.a[2] <= wz && r.b[2] >= wz;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, ov);
+      if (ov) { int slot = n + __popc(m & ((1u << lane) - 1)); s_el[warp][slot] = e; s_rg[warp][slot] = r; }
+      n += __popc(m); p += 32;
     }
-    __syncthreads();
-    if (!valid) continue;
-    for (int q = 0; q < nb; q++) {
-      const SRange &r = srng[q];
-      if (pi[0] < r.a[0] || pi[0] > r.b[0] || pi[1] < r.a[1] || pi[1] > r.b[1] || pi[2] < r.a[2] || pi[2] > r.b[2]) continue;
-      if (NEN == 8) {
-        any = true;
-#pragma unroll
-        for (int a = 0; a < 8; a++) mx = fmax(mx, sR[q][a]);
-        if (done) continue;
-        double Xe[3][8], re[8], xi[3], N[8];
-#pragma unroll
-        for (int a = 0; a < 8; a++) { Xe[0][a] = sX[q][0][a]; Xe[1][a] = sX[q][1][a]; Xe[2][a] = sX[q][2][a]; re[a] = sR[q][a]; }
-        ex::inverse_map_hex8(Xe, x, xi);
-        double mn = ex::max3abs(xi[0], xi[1], xi[2]);
-        if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
-          ex::hex8_shape(xi, N);
-          double rho = ex::dot8(N, re);
-          if (rho >= rho_t) sign = 1.0;
-          if (mn < 0.95) done = true;                              // :51-59 break
-          max_local = mn;
+    __syncwarp();
+    int pos = 0;
+    while (true) {
+      // advance to this lane's next candidate
+      if (valid) {
+        while (pos < n) {
+          const SRange &r = s_rg[warp][pos];
+          if (pi[0] >= r.a[0] && pi[0] <= r.b[0] && pi[1] >= r.a[1] && pi[1] <= r.b[1] && pi[2] >= r.a[2] && pi[2] <= r.b[2]) break;
+          pos++;
         }
-      } else {
-        if (done) continue;
-        double Xe[3][4], re[4], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      } else pos = n;
+      bool act = pos < n && !(NEN == 4 && done);
+      if (!__any_sync(0xffffffffu, act)) break;
+      if (act) {
+        const int e = s_el[warp][pos]; pos++;
+        if (NEN == 8) {
+          any = true;
+          int nd[8]; double re[8];
 #pragma unroll
-        for (int a = 0; a < 4; a++) { re[a] = sR[q][a];
+          for (int a = 0; a < 8; a++) { nd[a] = IEN[8 * (i64)e + a]; re[a] = rn[nd[a]]; mx = fmax(mx, re[a]); }
+          if (!done) {
+            double xi[3], N[8], A[3][8]; bool affine = true;
 #pragma unroll
-          for (int d = 0; d < 3; d++) { double c = sX[q][d][a]; Xe[d][a] = c; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
-        // is_point_in_tetrahedron (:220-242), tolerance 1e-10
-        const double tol = 1e-10; bool out = false;
+            for (int d = 0; d < 3; d++) {      // one coordinate at a time: only the monomial coefficients stay live
+              double v[8];
 #pragma unroll
-        for (int d = 0; d < 3; d++) if (x[d] < ex::sub(lo[d], tol) || x[d] > ex::add(hi[d], tol)) out = true;
-        if (out) continue;
-        double A[3][3], b[3];
+              for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)nd[a] + d];
+              ex::mono8(v, A[d]);
+              if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
+            }
+            ex::inverse_map_hex8_mono(A, affine, x, xi);
+            double mn = ex::max3abs(xi[0], xi[1], xi[2]);
+            if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
+              ex::hex8_shape(xi, N);
+              double rho = ex::dot8(N, re);
+              if (rho >= rho_t) sign = 1.0;
+              if (mn < 0.95) done = true;                              // :51-59 break
+              max_local = mn;
+            }
+          }
+        } else {
+          double Xe[3][4], re[4], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
 #pragma unroll
-        for (int d = 0; d < 3; d++) { A[d][0] = ex::sub(Xe[d][1], Xe[d][0]); A[d][1] = ex::sub(Xe[d][2], Xe[d][0]); A[d][2] = ex::sub(Xe[d][3], Xe[d][0]); b[d] = ex::sub(x[d], Xe[d][0]); }
-        using namespace ex;
-        double c00 = sub(mul(A[1][1], A[2][2]), mul(A[1][2], A[2][1])), c01 = sub(mul(A[1][2], A[2][0]), mul(A[1][0], A[2][2])), c02 = sub(mul(A[1][0], A[2][1]), mul(A[1][1], A[2][0]));
-        double det = add(add(mul(A[0][0], c00), mul(A[0][1], c01)), mul(A[0][2], c02));
-        if (!(fabs(det) > 0.0)) continue;
-        double c10 = sub(mul(A[0][2], A[2][1]), mul(A[0][1], A[2][2])), c11 = sub(mul(A[0][0], A[2][2]), mul(A[0][2], A[2][0])), c12 = sub(mul(A[0][1], A[2][0]), mul(A[0][0], A[2][1]));
-        double c20 = sub(mul(A[0][1], A[1][2]), mul(A[0][2], A[1][1])), c21 = sub(mul(A[0][2], A[1][0]), mul(A[0][0], A[1][2])), c22 = sub(mul(A[0][0], A[1][1]), mul(A[0][1], A[1][0]));
-        double l2 = dvd(add(add(mul(c00, b[0]), mul(c10, b[1])), mul(c20, b[2])), det), l3 = dvd(add(add(mul(c01, b[0]), mul(c11, b[1])), mul(c21, b[2])), det),
-               l4 = dvd(add(add(mul(c02, b[0]), mul(c12, b[1])), mul(c22, b[2])), det);
-        double l1 = sub(1.0, add(add(l2, l3), l4));
-        if (!(l1 >= -tol && l2 >= -tol && l3 >= -tol && l4 >= -tol && l1 <= 1.0 + tol && l2 <= 1.0 + tol && l3 <= 1.0 + tol && l4 <= 1.0 + tol)) continue;
-        double lc[3];
-        if (!inverse_map_tet4(Xe, x, lc)) continue;               // found == false (:132)
-        double l4b = sub(1.0, add(add(lc[0], lc[1]), lc[2]));
-        double rho = add(add(add(mul(lc[0], re[0]), mul(lc[1], re[1])), mul(lc[2], re[2])), mul(l4b, re[3]));
-        if (rho >= rho_t) { sign = 1.0; done = true; }
+          for (int a = 0; a < 4; a++) { i64 nd = IEN[4 * (i64)e + a]; re[a] = rn[nd];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { double c = X[3 * nd + d]; Xe[d][a] = c; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+          // is_point_in_tetrahedron (:220-242), tolerance 1e-10
+          const double tol = 1e-10; bool out = false;
+#pragma unroll
+          for (int d = 0; d < 3; d++) if (x[d] < ex::sub(lo[d], tol) || x[d] > ex::add(hi[d], tol)) out = true;
+          if (!out) {
+            using namespace ex;
+            double A[3][3], b[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { A[d][0] = sub(Xe[d][1], Xe[d][0]); A[d][1] = sub(Xe[d][2], Xe[d][0]); A[d][2] = sub(Xe[d][3], Xe[d][0]); b[d] = sub(x[d], Xe[d][0]); }
+            double c00 = sub(mul(A[1][1], A[2][2]), mul(A[1][2], A[2][1])), c01 = sub(mul(A[1][2], A[2][0]), mul(A[1][0], A[2][2])), c02 = sub(mul(A[1][0], A[2][1]), mul(A[1][1], A[2][0]));
+            double det = add(add(mul(A[0][0], c00), mul(A[0][1], c01)), mul(A[0][2], c02));
+            if (fabs(det) > 0.0) {
+              double c10 = sub(mul(A[0][2], A[2][1]), mul(A[0][1], A[2][2])), c11 = sub(mul(A[0][0], A[2][2]), mul(A[0][2], A[2][0])), c12 = sub(mul(A[0][1], A[2][0]), mul(A[0][0], A[2][1]));
+              double c20 = sub(mul(A[0][1], A[1][2]), mul(A[0][2], A[1][1])), c21 = sub(mul(A[0][2], A[1][0]), mul(A[0][0], A[1][2])), c22 = sub(mul(A[0][0], A[1][1]), mul(A[0][1], A[1][0]));
+              double l2 = dvd(add(add(mul(c00, b[0]), mul(c10, b[1])), mul(c20, b[2])), det), l3 = dvd(add(add(mul(c01, b[0]), mul(c11, b[1])), mul(c21, b[2])), det),
+                     l4 = dvd(add(add(mul(c02, b[0]), mul(c12, b[1])), mul(c22, b[2])), det);
+              double l1 = sub(1.0, add(add(l2, l3), l4));
+              if (l1 >= -tol && l2 >= -tol && l3 >= -tol && l4 >= -tol && l1 <= 1.0 + tol && l2 <= 1.0 + tol && l3 <= 1.0 + tol && l4 <= 1.0 + tol) {
+                double lc[3];
+                if (inverse_map_tet4(Xe, x, lc)) {               // found (:132)
+                  double l4b = sub(1.0, add(add(lc[0], lc[1]), lc[2]));
+                  double rho = add(add(add(mul(lc[0], re[0]), mul(lc[1], re[1])), mul(lc[2], re[2])), mul(l4b, re[3]));
+                  if (rho >= rho_t) { sign = 1.0; done = true; }
+                }
+              }
+            }
+          }
+        }
       }
     }
+    __syncwarp();
   }
   if (valid) {
     if (NEN == 8 && (!any || mx < rho_t)) sign = -1.0;            // :36 skip
