@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- SDF voxels/s of the rho2sdf grid-sampling hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libr2s.so through its C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores (CPU oracle port)
+
+Workload (BASELINE.json configs[4]): synthetic n^3 HEX8 SIMP density field (n = 256), grid step h_e/2,
+rho_t = 0.5, remove_artifacts, rbf_interp, rbf_grid = :fine  ->  (2(2n+6)+1)^3 = 1037^3 fine voxels.
+A "step" is one pass of the region the reference itself times (src/RhoToSDF.jl:164-227): grid points -> distances -> signs ->
+artifact removal -> RBF smoothing on the fine grid.  `value` = fine voxels / step time with the nodal densities resident
+in HBM; `e2e` = the same through r2s_pipeline() with pinned HOST buffers (H2D of rho_n, D2H of sdf_dists and fine_sdf).
+For N > 1 the coarse grid is cut into z-slabs, one rank (process) per GPU; scaling is strong (fixed problem).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "sdf_voxels_per_sec"
+UNIT = "voxels/s"
+# algorithmic work per unit (restated in DESIGN.md "Rooflines")
+FLOP_PER_PAIR = 2100.0          # FP64 flop per (element, grid point) projection
+B_PER_VOXEL_CG_ITER = 28.0      # Float32 CG: stencil read p + write Ap (8 B) + x, r, p updates (20 B)
+B_PER_FINE_VOXEL = 4.5          # fine evaluation: 4 B write + 1/8 * 4 B weight read
+FMA_PER_FINE_VOXEL = 79.75      # mean of the 8 polyphase tap counts (81 + 3*70 + 3*80 + 88) / 8
+B_PER_VOXEL_SIGN = 8.0
+B_PER_VOXEL_CC = 4 * 9.0 + 16.0  # 4 label passes x 9 B + the final sdf read-modify-write
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # samples under load = the upper half of the power readings (the sampler also sees the idle gaps between steps)
+        if sm:
+            order = np.argsort(pw)
+            load = [sm[i] for i in order[len(order) // 2:]]
+            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+def workload(n):
+    from fixtures import simp_hex8
+    return simp_hex8(n)
+
+
+def fine_voxels(grid, smooth):
+    return int(np.prod([int(v) * smooth + 1 for v in grid.N]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU oracle arm (also the cpu_baseline leg).  Julia is not installable in this image (no network, no toolchain), so the
+# "reference" here is the C/OpenMP restatement in oracle/ -- kind = "port".
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_pipeline(n):
+    import oracle
+    from fixtures import Grid
+    X, IEN, rho = workload(n)
+    g = Grid(X.min(0), X.max(0), 2 * n, 3)
+    vd, vf = oracle.mesh_volume(X, IEN, rho)
+    rn = oracle.nodal_densities(X, IEN, rho)
+    nt = oracle.max_threads()
+
+    def step():
+        t0 = time.perf_counter()
+        d, _, _ = oracle.eval_distances(X, IEN, g, rn, 0.5, 1.1, nthreads=nt, want_xp=False)
+        s = oracle.sign_detection(X, IEN, g, rn, 0.5, nthreads=nt)
+        sdf, _ = oracle.remove_artifacts(d * s, g)
+        fine, _ = oracle.rbf_smoothing(sdf, g, True, 2, vd * vf, mode=0, nthreads=nt)
+        return time.perf_counter() - t0, fine.size
+    return step, nt, g
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.cpu_n
+    step, nt, g = cpu_pipeline(n)
+    for _ in range(max(0, min(args.warmup, 1))):
+        step()
+    ts = []
+    for _ in range(args.steps):
+        t, nv = step()
+        ts.append(t)
+    t = float(np.mean(ts))
+    sample = "n=%d^3 HEX8 SIMP replica of the workload (%d coarse points, %d fine voxels), full timed region" % (n, g.ngp, nv)
+    line = {"impl": "reference", "metric": METRIC, "value": nv / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic %d^3 HEX8 SIMP density -> %d^3-class fine SDF grid (configs[4]); CPU arm runs the bounded %d^3 replica" % (args.n, 4 * args.n + 13, n),
+                       "rho_t": 0.5, "rbf_interp": True, "rbf_grid": "fine", "remove_artifacts": True},
+            "cpu_baseline": {"value": nv / t, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
+            "e2e": {"value": nv / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import rho2sdf_b200 as r2s
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d --master-addr 127.0.0.1 bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+    n = args.n
+    with torch.cuda.stream(stream):
+        X, IEN, rho = workload(n)
+        mesh = r2s.Mesh(X, IEN, rho, element_type=r2s.HEX8, device=local, stream=stream.cuda_stream)      # untimed: the reference builds Mesh before its timer
+        grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+        rho_n = r2s.DenseInNodes(mesh, rho)
+        mesh._use_grid(grid)
+        c = mesh.ctx
+        nz = int(grid.N[2]) + 1
+        k0, k1 = 0, nz
+        if world > 1:
+            k0, k1 = r2s.slab_partition(nz, world)[rank]
+            r2s.init_slab_comm(c, rank, world, k0, k1)
+        p = r2s.Params(); c.lib.r2s_default_params(C.byref(p))
+        p.rho_t, p.smooth, p.rbf_interp, p.remove_artifacts = 0.5, 2, 1, 1
+        p.target_volume, p.final_volume = mesh.V_frac * mesh.V_domain, 1
+        nfine = fine_voxels(grid, 2)
+        fdims = [int(v) * 2 + 1 for v in grid.N]
+        # slab-local output sizes (planes this rank returns to the host in the e2e leg)
+        kf0, kf1 = 2 * k0, (2 * k1 if k1 < nz else fdims[2])
+        n_sdf_local = (k1 - k0) * int(grid.N[0] + 1) * int(grid.N[1] + 1)
+        n_fine_local = (kf1 - kf0) * fdims[0] * fdims[1]
+        # pinned host buffers for the e2e leg
+        h_rho = torch.from_numpy(rho_n).pin_memory()
+        h_sdf = torch.empty(n_sdf_local, dtype=torch.float64).pin_memory()
+        h_fine = torch.empty(n_fine_local, dtype=torch.float32).pin_memory()
+        c.check(c.lib.r2s_upload_nodal_densities(c.h, C.c_void_p(h_rho.data_ptr())))
+
+        def barrier():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def step_resident():
+            rep = r2s.Report()
+            c.check(c.lib.r2s_pipeline_resident(c.h, C.byref(p), C.byref(rep)))
+            return rep
+
+        def step_e2e():
+            rep = r2s.Report()
+            c.check(c.lib.r2s_pipeline_slab(c.h, C.byref(p), C.c_void_p(h_rho.data_ptr()), C.c_void_p(h_sdf.data_ptr()), C.c_void_p(h_fine.data_ptr()), C.byref(rep)))
+            return rep
+
+        for _ in range(args.warmup):
+            step_resident()
+        # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + synchronize on both sides ----
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        reps = [step_resident() for _ in range(args.steps)]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # ---- e2e: the same K steps through the host-buffer entry point ----
+        step_e2e()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        f0.record(stream)
+        ereps = [step_e2e() for _ in range(args.steps)]
+        f1.record(stream)
+        barrier()
+        wall_e2e = (time.perf_counter() - w0) * 1e3
+        ms_e2e = max(f0.elapsed_time(f1), 0.0)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms, ms_e2e, wall_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_e2e, wall_e2e = (float(v) for v in t.tolist())
+        # ---- roofline denominators measured on this device ----
+        fp64, fp32 = C.c_double(), C.c_double()
+        c.check(c.lib.r2s_measure_fma_peak(c.h, 1, C.byref(fp64)))
+        c.check(c.lib.r2s_measure_fma_peak(c.h, 0, C.byref(fp32)))
+    hbm, hbm_src = load_peaks()
+    if rank == 0:
+        K = args.steps
+        step_ms = ms / K
+        e2e_ms = max(ms_e2e, wall_e2e) / K       # host-blocking copies: the wall clock is the honest figure
+        d = {k: float(np.mean([getattr(r, k) for r in reps])) for k in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_rbf_prep", "ms_cg", "ms_lsf",
+                                                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")}
+        rep = reps[-1]
+        ngp_local = n_sdf_local
+        stages = {
+            "project_hex8": {"bound": "fp64", "ms": d["ms_project"], "achieved": FLOP_PER_PAIR * rep.n_pairs / (d["ms_project"] * 1e-3) / 1e12 if d["ms_project"] > 0 else None,
+                             "peak": fp64.value, "unit": "TFLOP/s"},
+            "cg_stencil81": {"bound": "hbm", "ms": d["ms_cg"], "achieved": B_PER_VOXEL_CG_ITER * ngp_local * rep.cg_iters / (d["ms_cg"] * 1e-3) / 1e9 if d["ms_cg"] > 0 else None,
+                             "peak": hbm, "unit": "GB/s"},
+            "fine_eval": {"bound": "hbm", "ms": d["ms_fine"], "achieved": B_PER_FINE_VOXEL * n_fine_local / (d["ms_fine"] * 1e-3) / 1e9 if d["ms_fine"] > 0 else None,
+                          "peak": hbm, "unit": "GB/s", "fp32_tflops": 2 * FMA_PER_FINE_VOXEL * n_fine_local / (d["ms_fine"] * 1e-3) / 1e12 if d["ms_fine"] > 0 else None,
+                          "fp32_peak": fp32.value},
+            "sign": {"bound": "hbm", "ms": d["ms_sign"], "achieved": B_PER_VOXEL_SIGN * ngp_local / (d["ms_sign"] * 1e-3) / 1e9 if d["ms_sign"] > 0 else None, "peak": hbm, "unit": "GB/s"},
+            "cc": {"bound": "hbm", "ms": d["ms_cc"], "achieved": B_PER_VOXEL_CC * ngp_local / (d["ms_cc"] * 1e-3) / 1e9 if d["ms_cc"] > 0 else None, "peak": hbm, "unit": "GB/s"},
+        }
+        for s in stages.values():
+            s["frac"] = (s["achieved"] / s["peak"]) if s["achieved"] and s["peak"] else None
+        dom = stages["project_hex8"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "project_hex8_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": nfine / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic %d^3 HEX8 SIMP density (seed 20240517) -> %dx%dx%d fine SDF grid (BASELINE configs[4])" % (n, fdims[0], fdims[1], fdims[2]),
+                       "coarse_points": int(grid.ngp), "fine_voxels": nfine, "rho_t": 0.5, "delta_factor": 1.1, "rbf_interp": True, "rbf_grid": "fine",
+                       "remove_artifacts": True, "parallelism": "zslab%d" % world, "l2_policy": "inputs larger than L2 (working set %.1f GB per step)" % ((rep.n_pairs * 8 + grid.ngp * 40 + nfine * 4) / 1e9),
+                       "smoothing_dtype": "f32 (as the reference)"},
+            "e2e": {"value": nfine / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(rho_n.nbytes) * world,
+                    "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4), "api": "r2s_pipeline_slab (pinned host buffers)"},
+            "gpu_launches": int(sum(r.launches for r in reps)),
+            "roofline": {"kernel": "k_project_hex8", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic,
+                         "peak_source": "FP64 FMA chain micro-kernel measured in this run (r2s_measure_fma_peak); HBM peak %s" % hbm_src,
+                         "algorithmic": "%.0f FP64 flop per (element, point) pair x %d pairs per launch" % (FLOP_PER_PAIR, rep.n_pairs)},
+            "stages_ms": d, "kernels": stages,
+            "report": {"pairs": int(rep.n_pairs), "newton_iters": int(rep.n_newton_iters), "not_converged": int(rep.n_not_converged), "cg_iters": int(rep.cg_iters),
+                       "bisections": int(rep.bisections), "flipped": int(rep.n_flipped), "th": float(rep.th), "volume": float(rep.volume),
+                       "target_volume": float(p.target_volume), "solid": int(rep.n_solid), "crossing": int(rep.n_crossing)},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            step, nt, g = cpu_pipeline(args.cpu_n)
+            t, nv = step()
+            line["cpu_baseline"] = {"value": nv / t, "unit": UNIT, "cores": nt, "kind": "port",
+                                    "sample": "one pass of the timed region on the %d^3 replica of the workload (%d fine voxels) with the C/OpenMP oracle, %.1f s" % (args.cpu_n, nv, t)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="elements per axis of the synthetic HEX8 SIMP field")
+    ap.add_argument("--cpu-n", type=int, default=32, help="replica size for the CPU oracle leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -96,6 +96,12 @@ int r2s_result_ptrs_dev(r2s_ctx *ctx, void **sdf_dev, void **fine_sdf_dev);
 /* restrict this context to coarse planes k in [k0,k1) of the grid set by r2s_set_grid (halo planes are handled
  * internally); k0 = 0, k1 = N3+1 restores the full grid */
 int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1);
+/* r2s_pipeline for one slab with host buffers: returns only this rank's planes, sdf_slab[(k1-k0)*np0*np1] and
+ * fine_slab[(kf1-kf0)*f0*f1], kf0 = smooth*k0, kf1 = smooth*k1 (the last slab also owns the final fine plane) */
+int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep);
+
+/* ---- measurement helper (bench.py): FMA-pipe peak of the device in TFLOP/s, fp64 != 0 -> double, else float -------- */
+int r2s_measure_fma_peak(r2s_ctx *ctx, int fp64, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ import numpy as np
 __all__ = ["HEX8", "TET4", "Rho2sdfOptions", "Mesh", "Grid", "getMesh_AABB", "generateGridPoints", "noninteractive_sdf_grid_setup",
            "DenseInNodes", "find_threshold_for_volume", "calculate_isocontour_volume", "evalDistances", "Sign_Detection",
            "remove_sdf_artifacts", "RBFs_smoothing", "calculate_volume_from_sdf", "rho2sdf", "rho2sdf_hex8", "rho2sdf_tet4",
-           "FineGrid", "R2SError", "load_library", "library_path", "Params", "Report", "Context"]
+           "FineGrid", "R2SError", "slab_partition", "load_library", "library_path", "Params", "Report", "Context"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -100,6 +100,8 @@ def load_library():
     L.r2s_download_sdf.argtypes = [vp, vp]
     L.r2s_download_fine_sdf.argtypes = [vp, vp]
     L.r2s_result_ptrs_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.r2s_pipeline_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report)]
+    L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]
     _LIB = L
     return L
 
@@ -142,6 +144,19 @@ class Context:
         r = Report()
         self.lib.r2s_last_report(self.h, C.byref(r))
         return r
+
+
+def slab_partition(nz_points, world):
+    """Contiguous z-slabs of coarse planes, one per rank: [(k0, k1), ...] covering [0, nz_points)."""
+    if world < 1 or nz_points < world:
+        raise R2SError("cannot cut %d planes into %d slabs" % (nz_points, world))
+    base, rem = divmod(int(nz_points), int(world))
+    out, k = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -303,4 +303,20 @@ int r2s_pipeline(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double 
   if (fine_sdf && r2s_download_fine_sdf(ctx, fine_sdf)) return 1;
   return 0;
 }
+// Host-buffer entry point for one z-slab (== r2s_pipeline when the slab is the whole grid): uploads rho_n, runs the timed
+// region, returns ONLY this rank's planes: sdf_slab[(k1-k0) * np0 * np1] (coarse planes [k0,k1)) and
+// fine_slab[(kf1-kf0) * f0 * f1] with kf0 = smooth*k0, kf1 = smooth*k1 (the last slab also owns the final fine plane).
+int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep) {
+  if (!ctx || !p) return 1;
+  if (upload_rho_n(ctx, rho_n)) return 1;
+  if (r2s_pipeline_resident(ctx, p, rep)) return 1;
+  const GridDev &g = ctx->g; int s = p->smooth;
+  size_t pl = (size_t)g.np[0] * g.np[1];
+  i64 fx = g.N[0] * (i64)s + 1, fy = g.N[1] * (i64)s + 1, fz = g.N[2] * (i64)s + 1;
+  i64 kf0 = s * ctx->k0, kf1 = (ctx->k1 < g.np[2]) ? s * ctx->k1 : fz;
+  if (sdf_slab) CK(cudaMemcpyAsync(sdf_slab, ctx->sdf.as<double>() + pl * (size_t)ctx->k0, sizeof(double) * pl * (size_t)(ctx->k1 - ctx->k0), cudaMemcpyDeviceToHost, ctx->stream));
+  if (fine_slab) CK(cudaMemcpyAsync(fine_slab, ctx->f_fine.as<float>() + (size_t)fx * fy * (size_t)kf0, sizeof(float) * (size_t)fx * fy * (size_t)(kf1 - kf0), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 }  // extern "C"

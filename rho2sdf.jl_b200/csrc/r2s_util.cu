@@ -29,3 +29,42 @@ int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64
   *sorted = db.Current();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ roofline denominators
+// FMA-pipe peak measured on the device the context drives: 8 independent FMA chains per thread, enough CTAs to fill
+// every SM.  MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only; the iso-projection kernel is FP64-FMA bound
+// and the fine-grid RBF evaluation FP32-FMA bound, so bench.py measures those two denominators here.
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+  for (int i = 0; i < iters; i++) {
+    x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+    x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+  }
+  T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == (T)123456789) out[0] = s;          // never true; keeps the chains alive
+}
+template <typename T>
+static int fma_peak(r2s_ctx *ctx, double *tflops) {
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->cubtmp.reserve(256));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+  int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_fma_peak<T><<<blocks, 256, 0, ctx->stream>>>((T *)ctx->cubtmp.p, iters, (T)0.999999, (T)1e-7);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    double fl = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    if (rep > 0 && ms > 0) { double t = fl / (ms * 1e-3) / 1e12; if (t > best) best = t; }
+  }
+  *tflops = best;
+  return 0;
+}
+extern "C" int r2s_measure_fma_peak(r2s_ctx *ctx, int fp64, double *tflops) {
+  if (!ctx || !tflops) return 1;
+  return fp64 ? fma_peak<double>(ctx, tflops) : fma_peak<float>(ctx, tflops);
+}

@@ -87,3 +87,35 @@ def simp_hex8(n, seed=20240517, period_frac=0.25, t=-0.6, beta=8.0, noise=0.02):
     u = (h >> np.uint64(11)).astype(np.float64) / float(1 << 53) * 2.0 - 1.0
     rho = np.clip(1.0 / (1.0 + np.exp(-beta * (t - g))) + noise * u, 0.0, 1.0)
     return X, IEN, rho
+
+
+def lattice_hex8(n):
+    """n^3 unit HEX8 elements on the integer lattice [0,n]^3 (VTK node order); X (nnp,3), IEN (nel,8) 1-based."""
+    m = n + 1
+    k, j, i = np.meshgrid(np.arange(m), np.arange(m), np.arange(m), indexing="ij")
+    X = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1).astype(np.float64)
+    ke, je, ie = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ke, je, ie = ke.ravel(), je.ravel(), ie.ravel()
+    nid = lambda a, b, c: (c * m + b) * m + a + 1
+    IEN = np.stack([nid(ie, je, ke), nid(ie + 1, je, ke), nid(ie + 1, je + 1, ke), nid(ie, je + 1, ke),
+                    nid(ie, je, ke + 1), nid(ie + 1, je, ke + 1), nid(ie + 1, je + 1, ke + 1), nid(ie, je + 1, ke + 1)], axis=1).astype(np.int64)
+    return X, IEN
+
+
+SCHLAFLI = np.array([[1, 2, 3, 7], [1, 6, 2, 7], [1, 3, 4, 7], [1, 4, 8, 7], [1, 5, 6, 7], [1, 8, 5, 7]]) - 1   # SimpleCubeWithSchlafli.jl:22-29
+
+
+def schlafli_tet4(n, field="radial"):
+    """Schlaefli 6-tet split of the n^3 lattice cube (reference test/PrimitiveGeometriesTest/SimpleCubeWithSchlafli.jl:22-29)
+    with a nodal density: 'radial' = linear radial fall-off from the cube centre (the reference generators' field),
+    'simp' = the synthetic SIMP field of SURVEY.md 8(d) sampled at the nodes.  Returns X, IEN (6 n^3, 4) 1-based, rho_n."""
+    X, H = lattice_hex8(n)
+    T = np.ascontiguousarray(np.concatenate([H[:, s] for s in SCHLAFLI], axis=0))
+    if field == "radial":
+        r = np.linalg.norm(X - n / 2.0, axis=1)
+        rho_n = np.clip(1.0 - r / (0.75 * n), 0.0, 1.0)
+    else:
+        w = 2 * np.pi / (0.5 * n)
+        g = np.sin(w * X[:, 0]) * np.cos(w * X[:, 1]) + np.sin(w * X[:, 1]) * np.cos(w * X[:, 2]) + np.sin(w * X[:, 2]) * np.cos(w * X[:, 0])
+        rho_n = 1.0 / (1.0 + np.exp(-4.0 * (-0.6 - g)))
+    return X, T, rho_n
