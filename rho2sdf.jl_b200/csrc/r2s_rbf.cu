@@ -8,6 +8,7 @@
 //   * a two-pass cut-cell quadrature for the volume-matching bisection (LS_Threshold, :265-300).
 // Sums are deterministic: block partials in fixed slots (double) or 64-bit fixed-point integer atomics.
 #include <float.h>
+#include <algorithm>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
 
@@ -196,44 +197,111 @@ __global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, co
   __syncthreads();
   if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += s_warp[w]; if (tot) atomicAdd(&acc[0], (u64)tot); }
 }
-// pass 2: one warp per cut cell (grid-stride over the list; the count is read from device memory so that no host
-// round trip separates the two passes).  Lanes own (iq, jq) Gauss-point pairs and run the kq loop; every point value is
-// evaluated with the reference's expression order (xi, then eta, then zeta lerps).  The cell's Float32 partial sum of
-// w_i w_j w_k over inside points is accumulated as a 2^-37 fixed-point integer (deterministic).
+// pass 2: ONE THREAD per cut cell (grid-stride over the list; the count is read from device memory so that no host round
+// trip separates the two passes).  The three Gauss loops are fully unrolled with the abscissae / weights as kernel-parameter
+// (constant-bank) operands: 4 lerps per xi, 2 per (xi, eta), then per point one lerp, one compare and one predicated add --
+// about 4 instructions per Gauss point.  Every point value is evaluated with the reference's expression order (xi, then eta,
+// then zeta lerps; CalcVolumeFromSDF.jl:88-103).  The cell's Float32 sum of w_i w_j w_k over inside points (iq outer, kq
+// inner, a fixed order) is accumulated across cells as a 2^-37 fixed-point integer (deterministic).
 struct GaussF { float x[9]; float w[9]; };
-__global__ void __launch_bounds__(256) k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
+__global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
                                                  GaussF G, u64 *__restrict__ acc) {
-  __shared__ float gx[9], gw[9];
-  if (threadIdx.x < 9) { gx[threadIdx.x] = (G.x[threadIdx.x] + 1) / 2; gw[threadIdx.x] = G.w[threadIdx.x]; }
-  __syncthreads();
-  int ncut = (int)min((u64)cutcap, acc[1]);
-  int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ncut = (int)min((u64)cutcap, acc[1]);
+  const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
+  const i64 sxy = (i64)nx * ny;
   u64 local = 0;
-  for (int wid = (int)((blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5); wid < ncut; wid += nwarps) {
-    i64 c = cutlist[wid];
-    int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
-    i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
-    float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
-    float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
-    float part = 0.0f;
-    for (int q = lane; q < 81; q += 32) {
-      int iq = q % 9, jq = q / 9;
-      float xi = gx[iq], eta = gx[jq];
-      float c00 = c000 * (1.0f - xi) + c100 * xi, c01 = c001 * (1.0f - xi) + c101 * xi;
-      float c10 = c010 * (1.0f - xi) + c110 * xi, c11 = c011 * (1.0f - xi) + c111 * xi;
-      float c0 = c00 * (1.0f - eta) + c10 * eta, c1 = c01 * (1.0f - eta) + c11 * eta;
-      float wij = gw[iq] * gw[jq];
+  for (int base = blockIdx.x * blockDim.x; base < ncut; base += nthr) {      // warp-uniform trip count
+    const int idx = base + threadIdx.x;
+    if (idx < ncut) {
+      const i64 c = cutlist[idx];
+      const int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
+      const i64 b = ((i64)k * ny + j) * nx + i;
+      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
+      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+      float part = 0.0f;
 #pragma unroll
-      for (int kq = 0; kq < 9; kq++) {
-        float zeta = gx[kq];
-        float ps = c0 * (1.0f - zeta) + c1 * zeta;
-        if (ps >= iso) part += wij * gw[kq];
+      for (int iq = 0; iq < 9; iq++) {
+        const float xi = (G.x[iq] + 1) / 2, xm = 1.0f - xi;
+        const float c00 = c000 * xm + c100 * xi, c01 = c001 * xm + c101 * xi;
+        const float c10 = c010 * xm + c110 * xi, c11 = c011 * xm + c111 * xi;
+#pragma unroll
+        for (int jq = 0; jq < 9; jq++) {
+          const float eta = (G.x[jq] + 1) / 2, em = 1.0f - eta;
+          const float c0 = c00 * em + c10 * eta, c1 = c01 * em + c11 * eta;
+          const float wij = G.w[iq] * G.w[jq];
+#pragma unroll
+          for (int kq = 0; kq < 9; kq++) {
+            const float zeta = (G.x[kq] + 1) / 2;
+            const float ps = c0 * (1.0f - zeta) + c1 * zeta;
+            if (ps >= iso) part += wij * G.w[kq];
+          }
+        }
+      }
+      local += (u64)llrint((double)part * 137438953472.0);      // part in [0,8]; 2^37 per unit, exact for a float
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if (lane == 0 && local) atomicAdd(&acc[2], local);
+}
+// ---- LS_Threshold bisection (RBFs4Smoothing.jl:265-300): volume of {lsf - th >= 0} for a SEQUENCE of thresholds ----------
+// V(th) is a sum over cells; a cell's class depends only on (cmin, cmax) = (min, max) of its 8 corner values: full iff
+// cmin >= th, empty iff cmax < th (IEEE subtraction is sign-exact, so min_i(v_i - th) >= 0  <=>  cmin >= th).  Every later
+// threshold of the bisection lies inside the current bracket [lo, hi], so a cell with cmin >= hi stays full and a cell with
+// cmax < lo stays empty for the rest of the search: such cells are retired (full ones into a permanent counter) and only the
+// remaining "active" cells are carried to the next step in a compacted list.  The sum is accumulated in integers, so the
+// result is bit-identical to re-classifying every cell at every step, at ~3 full passes instead of 40.
+// acc: [0] full cells of this step  [1] cut count  [2] cut fixed-point sum  [3] permanently full  [4],[5] list sizes (ping-pong)
+template <bool IMPLICIT, bool EMIT>
+__global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th,
+                                                  const int *__restrict__ list_in, const u64 *__restrict__ n_in_ptr, int *__restrict__ list_out,
+                                                  u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
+  __shared__ int s_cut[8], s_keep[8]; __shared__ int s_base_cut, s_base_keep;
+  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)nx * ny;
+  const i64 n_in = IMPLICIT ? cpl * (i64)(kc1 - kc0) : (i64)*n_in_ptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nfull = 0, nperm = 0;
+  for (i64 t0 = (i64)blockIdx.x * 256; t0 < n_in; t0 += (i64)gridDim.x * 256) {
+    i64 t = t0 + threadIdx.x; bool cut = false, keep = false; int c = 0;
+    if (t < n_in) {
+      c = IMPLICIT ? (int)(t + cpl * kc0) : list_in[t];
+      int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = (int)(c / cpl);
+      i64 b = ((i64)k * ny + j) * nx + i;
+      float v0 = sdf[b], v1 = sdf[b + 1], v2 = sdf[b + nx], v3 = sdf[b + nx + 1];
+      float v4 = sdf[b + sxy], v5 = sdf[b + sxy + 1], v6 = sdf[b + sxy + nx], v7 = sdf[b + sxy + nx + 1];
+      float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
+      float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
+      if (EMIT && mn >= hi) nperm++;                         // full for every threshold still to come
+      else if (EMIT && mx < lo) {}                           // empty for every threshold still to come
+      else {
+        keep = EMIT;
+        if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
       }
     }
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-    if (lane == 0) local += (u64)llrint((double)part * 137438953472.0);      // part in [0,8]; 2^37 per unit, exact for a float
+    unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
+    if (__syncthreads_or((mc | mk) != 0)) {
+      if (lane == 0) { s_cut[warp] = __popc(mc); s_keep[warp] = __popc(mk); }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tc = 0, tk = 0;
+        for (int w = 0; w < 8; w++) { int a = s_cut[w]; s_cut[w] = tc; tc += a; int b2 = s_keep[w]; s_keep[w] = tk; tk += b2; }
+        s_base_cut = tc ? (int)atomicAdd(&acc[1], (u64)tc) : 0;
+        s_base_keep = tk ? (int)atomicAdd(n_out_ptr, (u64)tk) : 0;
+      }
+      __syncthreads();
+      if (cut) { int slot = s_base_cut + s_cut[warp] + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
+      if (keep) list_out[s_base_keep + s_keep[warp] + __popc(mk & ((1u << lane) - 1))] = c;
+      __syncthreads();
+    }
   }
-  if (lane == 0 && local) atomicAdd(&acc[2], local);
+  for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
+  __syncthreads();
+  if (lane == 0) { s_cut[warp] = nfull; s_keep[warp] = nperm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tf = 0, tp = 0; for (int w = 0; w < 8; w++) { tf += s_cut[w]; tp += s_keep[w]; }
+    if (tf) atomicAdd(&acc[0], (u64)tf);
+    if (tp) atomicAdd(&acc[3], (u64)tp);
+  }
 }
 static GaussF gauss9f() { GaussTab t = gauss_legendre_host(9); GaussF g; for (int i = 0; i < 9; i++) { g.x[i] = (float)t.x[i]; g.w[i] = (float)t.w[i]; } return g; }
 
@@ -249,7 +317,7 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
     int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(acc, 0, sizeof(u64) * 4, st));
     k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
-    k_vol_cut<<<148 * 4, 256, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc); LAUNCH_CHECK();
+    k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc); LAUNCH_CHECK();
     u64 h[3];
     CK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -262,6 +330,58 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
     return 0;
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
+}
+// state of one LS_Threshold search (see k_vol_step)
+struct VolBisect {
+  const float *sdf; int nx, ny, kc0, kc1; float edge; int step, cur; i64 n_cur; u64 *acc;
+};
+static int vol_bisect_begin(r2s_ctx *ctx, VolBisect &vb, const float *sdf, int nx, int ny, int nz, int kc0, int kc1, float edge) {
+  i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
+  if (ncell >= (1ll << 31)) FAIL("LS_Threshold: grid too large for 32-bit cell ids");
+  CK(ctx->f_scal.reserve(256));
+  vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0;
+  vb.n_cur = (i64)(nx - 1) * (ny - 1) * (i64)(kc1 - kc0);
+  vb.acc = (u64 *)((char *)ctx->f_scal.p + 128);
+  CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 8, ctx->stream));
+  return 0;
+}
+// volume of {sdf - th >= 0} over the cells of planes [kc0, kc1); [lo, hi] = the bracket th was taken from
+static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, float th, double *vol) {
+  cudaStream_t st = ctx->stream;
+  static const GaussF G9 = gauss9f();
+  const i64 n_all = (i64)(vb.nx - 1) * (vb.ny - 1) * (i64)(vb.kc1 - vb.kc0);
+  vb.step++;
+  const bool implicit = vb.step <= 3, emit = vb.step >= 3;
+  if (emit) { CK(ctx->vlist[0].reserve(sizeof(int) * (size_t)(n_all + 1))); if (vb.step > 3) CK(ctx->vlist[1].reserve(sizeof(int) * (size_t)(vb.n_cur + 1))); }
+  const int in = vb.cur, out = emit ? (vb.step == 3 ? 0 : 1 - vb.cur) : vb.cur;
+  u64 h[6];
+  for (int attempt = 0; attempt < 2; attempt++) {
+    int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
+    CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
+    i64 n_in = implicit ? n_all : vb.n_cur;
+    int grid = (int)std::min<i64>(std::max<i64>(cdiv(n_in, 256), 1), 148 * 16);
+    int *lin = ctx->vlist[in].as<int>(), *lout = ctx->vlist[out].as<int>(); u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
+    if (attempt == 0) {
+      if (emit) CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
+      if (implicit && !emit) k_vol_step<true, false><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else if (implicit) k_vol_step<true, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else k_vol_step<false, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lin, nin, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
+    } else {
+      // the cut list overflowed: it has been grown; re-classify (the retired cells are already accounted for)
+      if (!emit) k_vol_step<true, false><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+    }
+    LAUNCH_CHECK();
+    k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, 0, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h, vb.acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((i64)h[1] > cutcap) { CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024))); continue; }
+    if (emit) { vb.cur = out; vb.n_cur = (i64)h[4 + out]; }
+    float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
+    *vol = (double)(h[0] + h[3]) * (double)ev + ((double)h[2] / 137438953472.0 /* 2^37 */) * (double)jac;
+    return 0;
+  }
+  FAIL("LS_Threshold: cut-cell list overflow");
 }
 int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, double *vol) {
   CK(ctx->cutlist.reserve(sizeof(int) * 1024));
@@ -303,6 +423,94 @@ __global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, 
   }
   out[((i64)k * fy + j) * fx + i] = acc + th;
 }
+// :fine grid (smooth = 2): one thread per coarse cell (a, b, c) -> its 2x2x2 fine outputs.  The taps of fine point
+// (2a+px, 2b+py, 2c+pz) are the coarse points (a+di, b+dj, c+dk), di,dj,dk in -2..3, with weight
+// exp(-((di-px/2)^2 + (dj-py/2)^2 + (dk-pz/2)^2)) when inside the cut radius, else 0.  The weight table lives in constant
+// memory and is indexed with COMPILE-TIME offsets (the loops are fully unrolled), so every FMA takes its weight as a
+// constant-bank operand; taps that are outside the largest supported radius (|d|^2 > 8) are pruned at compile time.
+// Per 6-value x-row loaded from shared memory up to 48 FMAs are issued (FMA-bound, not LDS-bound).  Accumulation order per
+// output is dk, dj, di ascending -- the same as k_fine_eval<2> -- so both kernels give bit-identical results.
+__constant__ float c_w2[2][2][6][6][2][6];          // [pz][py][dk+2][dj+2][px][di+2]
+#define F2_X 32
+#define F2_Y 4
+#define F2_Z 8            // coarse cells per block along z (2 per thread)
+#define F2_ZT 4           // threads along z
+__device__ __forceinline__ constexpr bool f2_tap_possible(int px, int py, int pz, int di, int dj, int dk) {
+  // 4*|d|^2 <= 32  (|d|^2 <= 8)
+  return (2 * di - px) * (2 * di - px) + (2 * dj - py) * (2 * dj - py) + (2 * dk - pz) * (2 * dk - pz) <= 32;
+}
+template <int PZ, int PY, int DK, int DJ>
+__device__ __forceinline__ void f2_row(const float row[6], float &acc0, float &acc1) {
+#pragma unroll
+  for (int di = -2; di <= 3; di++) {
+    if (f2_tap_possible(0, PY, PZ, di, DJ, DK)) acc0 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][0][di + 2], row[di + 2], acc0);
+    if (f2_tap_possible(1, PY, PZ, di, DJ, DK)) acc1 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][1][di + 2], row[di + 2], acc1);
+  }
+}
+template <int DK, int DJ>
+__device__ __forceinline__ void f2_rows(const float row[6], float acc[8]) {
+  // acc index = px + 2*py + 4*pz
+  if (f2_tap_possible(0, 0, 0, 0, DJ, DK) || f2_tap_possible(1, 0, 0, 0, DJ, DK) || f2_tap_possible(1, 0, 0, 1, DJ, DK)) f2_row<0, 0, DK, DJ>(row, acc[0], acc[1]);
+  if (f2_tap_possible(0, 1, 0, 0, DJ, DK) || f2_tap_possible(1, 1, 0, 0, DJ, DK) || f2_tap_possible(1, 1, 0, 1, DJ, DK)) f2_row<0, 1, DK, DJ>(row, acc[2], acc[3]);
+  if (f2_tap_possible(0, 0, 1, 0, DJ, DK) || f2_tap_possible(1, 0, 1, 0, DJ, DK) || f2_tap_possible(1, 0, 1, 1, DJ, DK)) f2_row<1, 0, DK, DJ>(row, acc[4], acc[5]);
+  if (f2_tap_possible(0, 1, 1, 0, DJ, DK) || f2_tap_possible(1, 1, 1, 0, DJ, DK) || f2_tap_possible(1, 1, 1, 1, DJ, DK)) f2_row<1, 1, DK, DJ>(row, acc[6], acc[7]);
+}
+template <int DK>
+__device__ __forceinline__ void f2_plane(const float (*sm)[F2_Y + 5][F2_X + 5], int lz, int ly, int lx, float acc[8]) {
+#pragma unroll
+  for (int dj = -2; dj <= 3; dj++) {
+    float row[6];
+#pragma unroll
+    for (int di = 0; di < 6; di++) row[di] = sm[lz + DK + 2][ly + dj + 2][lx + di];
+    switch (dj) {     // dj is a compile-time constant after unrolling
+      case -2: f2_rows<DK, -2>(row, acc); break;
+      case -1: f2_rows<DK, -1>(row, acc); break;
+      case 0: f2_rows<DK, 0>(row, acc); break;
+      case 1: f2_rows<DK, 1>(row, acc); break;
+      case 2: f2_rows<DK, 2>(row, acc); break;
+      default: f2_rows<DK, 3>(row, acc); break;
+    }
+  }
+}
+// kc0/kc1: coarse planes whose fine outputs this launch produces (z-slab); fine planes 2c and 2c+1 (the latter if < fz)
+__global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny, int nz, int fx, int fy, int fz, int kc0, int kc1, const float *__restrict__ w, float th,
+                                                                  float *__restrict__ out) {
+  __shared__ float sm[F2_Z + 5][F2_Y + 5][F2_X + 5];
+  const int cbx = blockIdx.x * F2_X, cby = blockIdx.y * F2_Y, cbz = kc0 + blockIdx.z * F2_Z;
+  constexpr int TX = F2_X + 5, TY = F2_Y + 5, TZ = F2_Z + 5;
+  for (int t = threadIdx.x; t < TX * TY * TZ; t += blockDim.x) {
+    int lx = t % TX, ly = (t / TX) % TY, lz = t / (TX * TY);
+    int gx = cbx + lx - 2, gy = cby + ly - 2, gz = cbz + lz - 2;
+    float v = 0.0f;
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * nx + gx];
+    sm[lz][ly][lx] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % F2_X, ly = (threadIdx.x / F2_X) % F2_Y, lzt = threadIdx.x / (F2_X * F2_Y);
+  const int a = cbx + lx, b = cby + ly;
+  if (a >= nx || b >= ny) return;
+#pragma unroll 1
+  for (int q = 0; q < F2_Z / F2_ZT; q++) {
+    const int lz = lzt + q * F2_ZT, c = cbz + lz;
+    if (c >= kc1 || c >= nz) continue;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    f2_plane<-2>(sm, lz, ly, lx, acc); f2_plane<-1>(sm, lz, ly, lx, acc); f2_plane<0>(sm, lz, ly, lx, acc);
+    f2_plane<1>(sm, lz, ly, lx, acc); f2_plane<2>(sm, lz, ly, lx, acc); f2_plane<3>(sm, lz, ly, lx, acc);
+#pragma unroll
+    for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+      for (int py = 0; py < 2; py++) {
+        int i = 2 * a, j = 2 * b + py, k = 2 * c + pz;
+        if (j < fy && k < fz) {
+          i64 o = ((i64)k * fy + j) * fx + i;
+          out[o] = acc[2 * py + 4 * pz] + th;
+          if (i + 1 < fx) out[o + 1] = acc[1 + 2 * py + 4 * pz] + th;
+        }
+      }
+  }
+}
 __global__ void k_add_scalar(i64 n, float *__restrict__ a, float s) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (v < n) a[v] = a[v] + s;
@@ -324,6 +532,16 @@ static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
       }
     }
     T.n[ph] = n;
+  }
+  if (sm == 2) {      // dense per-phase weight table of k_fine_eval2 (same inclusion test, zero = excluded)
+    static float W2[2][2][6][6][2][6];
+    for (int pz = 0; pz < 2; pz++) for (int py = 0; py < 2; py++) for (int dk = -2; dk <= 3; dk++) for (int dj = -2; dj <= 3; dj++)
+      for (int px = 0; px < 2; px++) for (int di = -2; di <= 3; di++) {
+        double ox = di - 0.5 * px, oy = dj - 0.5 * py, oz = dk - 0.5 * pz, m = ox * ox + oy * oy + oz * oz;
+        float dist = (float)(sqrt(m) * cell);
+        W2[pz][py][dk + 2][dj + 2][px][di + 2] = (dist <= maxd) ? (float)exp(-m) : 0.0f;
+      }
+    CK(cudaMemcpyToSymbolAsync(c_w2, W2, sizeof(W2), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
   CK(cudaMemcpyToSymbolAsync(c_taps, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(c_tapw, W, sizeof(W), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -413,10 +631,12 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     float ex = x1 - x0; edge = sqrtf(ex * ex);
   }
   double eps = 1.0; int nb = 0; float th = 0.0f; double v = 0.0; bool have_prev = false; float th_prev = 0.0f;
+  VolBisect vb;
+  if (vol_bisect_begin(ctx, vb, lsf, nx, ny, nz, 0, nz - 1, edge)) return 1;
   while (nb < 40 && eps > 1.0e-4) {
     th = (lo + hi) / 2;
     // once lo and hi are adjacent floats the midpoint repeats: the volume of an identical threshold is not recomputed
-    if (!(have_prev && th == th_prev)) { if (volume_dev(ctx, lsf, nx, ny, nz, th, edge, 0.0f, &v)) return 1; }
+    if (!(have_prev && th == th_prev)) { if (vol_bisect_step(ctx, vb, lo, hi, th, &v)) return 1; }
     have_prev = true; th_prev = th;
     float cur = (float)v;
     eps = fabs(target - (double)cur);
@@ -430,7 +650,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   if (upload_taps(ctx, smooth, rbf_cut, g.cell)) return 1;
   dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(fz, FN_Z));
   if (smooth == 1) k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, fz, wgt, tho, ctx->f_fine.as<float>());
-  else k_fine_eval<2><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, fz, wgt, tho, ctx->f_fine.as<float>());
+  else {
+    dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(nz, F2_Z));
+    k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, 0, nz, wgt, tho, ctx->f_fine.as<float>());
+  }
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[14], st));
   float volf = 0.0f;

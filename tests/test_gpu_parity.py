@@ -146,7 +146,8 @@ def test_mat_fixtures_full_path(r2s, name):
     opts = r2s.Rho2sdfOptions(sdf_grid_setup="automatic", rbf_interp=True, rbf_grid="fine", remove_artifacts=True)
     fine, fg, g2, sdf, rep = r2s.rho2sdf(name, X, IEN, rho, options=opts, return_report=True)
     assert rep["rho_t"] == rt and list(g2.N) == list(grid.N)
-    assert np.array_equal(sdf, clean)
+    assert np.array_equal(np.sign(sdf), np.sign(clean)) and np.array_equal(np.abs(sdf) > 1e9, np.abs(clean) > 1e9)
+    assert np.max(np.abs(sdf - clean)) <= DIST_TOL * grid.cell_size
     ofine, oinfo = oracle.rbf_smoothing(clean, grid, True, 2, vd * vf, mode=0, nthreads=oracle.max_threads())
     assert np.max(np.abs(fine - ofine)) <= RBF_TOL * grid.cell_size
     assert fg.shape == tuple(int(n) * 2 + 1 for n in grid.N) and rep["launches"] > 0
