@@ -42,7 +42,7 @@ struct ActRec {
   int el;         // element id (0-based)
   int cls;        // 1 solid (only boundary faces), 2 crossing
   int fmask;      // bit sg set <=> face sg is a boundary face
-  int pad;
+  int tri_off;    // first record of this element's boundary-face triangles in the triangle table (fmask != 0)
   i64 pair_off;   // offset of this element's (element, point) block in the pair buffer (crossing only)
 };
 
@@ -83,7 +83,7 @@ struct r2s_ctx {
   std::vector<double> h_pc[3];
 
   // distance / sign work buffers
-  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, pairbuf, pairxp, cubtmp, counters;
+  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters;
   DevBuf dist, xp, sdf, signs;
   DevBuf s_rng, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
   // connected components

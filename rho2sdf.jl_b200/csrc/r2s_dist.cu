@@ -38,7 +38,7 @@ __global__ void k_act_records(i64 nel, int nen, const int *__restrict__ IEN, con
   if (e >= nel || !flag[e]) return;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
-  ActRec r; r.el = (int)e; r.cls = cls[e]; r.fmask = fb[e]; r.pad = 0; r.pair_off = 0;
+  ActRec r; r.el = (int)e; r.cls = cls[e]; r.fmask = fb[e]; r.tri_off = 0; r.pair_off = 0;
   bool ok = true;
   for (int d = 0; d < 3; d++) {
     int I0 = 0, I1 = -1;
@@ -220,37 +220,76 @@ __device__ inline void triangle_point(const double Xe[3][NEN], const double re[N
     else projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
   }
 }
-// process_boundary_faces! (:489-558) for one grid point (point index pi[3], coordinate x)
-template <bool WANT_XP, int NEN>
-__device__ inline void boundary_faces_point(const ActRec &r, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn,
-                                            const GridDev &g, double rho_t, double delta, const int pi[3], const double x[3], VoxState &s) {
+// Boundary-face triangles (process_boundary_faces! :489-558): every boundary face of an active element is split into nsn
+// triangles around its centroid (:520-529).  The triangles and the grid-point range of their (AABB +- delta) cell range
+// (Grid.jl:122-154) do not depend on the grid point, so they are built ONCE per call into a table (one thread per active
+// element) instead of once per (grid point, candidate element) inside the assemble kernel.
+struct TriRec {
+  int ps[3], pe[3];      // candidate grid-point range per axis [ps, pe)
+  double Xt[3][3];       // vertices (x1, x2, centroid)
+  double n[3];           // unit normal
+};
+__global__ void k_tri_count(i64 nact, const ActRec *__restrict__ rec, int nsn, int *__restrict__ cnt) {
+  i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  cnt[a] = __popc((unsigned)rec[a].fmask) * nsn;
+}
+template <int NEN>
+__global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__restrict__ toff, const int *__restrict__ IEN, const double *__restrict__ X, GridDev g,
+                              double delta, TriRec *__restrict__ tri) {
   constexpr int NSN = NEN == 8 ? 4 : 3, NES = NEN == 8 ? 6 : 4;
-  double Xe[3][NEN], re[NEN];
-  for (int a = 0; a < NEN; a++) { i64 n = IEN[NEN * (i64)r.el + a]; re[a] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * n + d]; }
+  i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  ActRec r = rec[a];
+  rec[a].tri_off = toff[a];
+  if (!r.fmask) return;
+  double Xe[3][NEN];
+  for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
+  int o = toff[a];
   for (int sg = 0; sg < NES; sg++) {
     if (!((r.fmask >> sg) & 1)) continue;
     double Xs[NSN][3], Xc[3];
-    for (int a = 0; a < NSN; a++) { int ln = NEN == 8 ? c_hex_isn[sg][a] : c_tet_isn[sg][a]; for (int d = 0; d < 3; d++) Xs[a][d] = Xe[d][ln]; }
-    for (int d = 0; d < 3; d++) { double t = Xs[0][d]; for (int a = 1; a < NSN; a++) t = ex::add(t, Xs[a][d]); Xc[d] = ex::dvd(t, (double)NSN); }
-    for (int a = 0; a < NSN; a++) {
-      int a2 = (a + 1) % NSN; double Xt[3][3], Et[3][3], n[3];
-      for (int d = 0; d < 3; d++) { Xt[0][d] = Xs[a][d]; Xt[1][d] = Xs[a2][d]; Xt[2][d] = Xc[d]; }
-      // cell range of the triangle (Grid.jl:122-154) -> is this grid point's cell inside?
-      bool in = true;
-      for (int d = 0; d < 3 && in; d++) {
-        double lo = fmin(Xt[0][d], fmin(Xt[1][d], Xt[2][d])), hi = fmax(Xt[0][d], fmax(Xt[1][d], Xt[2][d])); int I0, I1;
-        in = ex::cell_range_axis(lo, hi, delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
-        if (in) { int c = g.cellof[g.pc_off[d] + pi[d]]; in = (c >= I0 && c <= I1); }
+    for (int q = 0; q < NSN; q++) { int ln = NEN == 8 ? c_hex_isn[sg][q] : c_tet_isn[sg][q]; for (int d = 0; d < 3; d++) Xs[q][d] = Xe[d][ln]; }
+    for (int d = 0; d < 3; d++) { double t = Xs[0][d]; for (int q = 1; q < NSN; q++) t = ex::add(t, Xs[q][d]); Xc[d] = ex::dvd(t, (double)NSN); }
+    for (int q = 0; q < NSN; q++) {
+      int q2 = (q + 1) % NSN; TriRec T; double Et[2][3];
+      for (int d = 0; d < 3; d++) { T.Xt[0][d] = Xs[q][d]; T.Xt[1][d] = Xs[q2][d]; T.Xt[2][d] = Xc[d]; }
+      bool ok = true;
+      for (int d = 0; d < 3; d++) {
+        double lo = fmin(T.Xt[0][d], fmin(T.Xt[1][d], T.Xt[2][d])), hi = fmax(T.Xt[0][d], fmax(T.Xt[1][d], T.Xt[2][d])); int I0 = 0, I1 = -1;
+        ok = ok && ex::cell_range_axis(lo, hi, delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
+        if (ok) { T.ps[d] = g.cstart[g.cs_off[d] + I0]; T.pe[d] = g.cstart[g.cs_off[d] + I1 + 1]; } else { T.ps[d] = 0; T.pe[d] = 0; }
       }
-      if (!in) continue;
-      for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
-      n[0] = ex::sub(ex::mul(Et[0][1], Et[1][2]), ex::mul(Et[0][2], Et[1][1]));
-      n[1] = ex::sub(ex::mul(Et[0][2], Et[1][0]), ex::mul(Et[0][0], Et[1][2]));
-      n[2] = ex::sub(ex::mul(Et[0][0], Et[1][1]), ex::mul(Et[0][1], Et[1][0]));
-      double nn = ex::norm3(n[0], n[1], n[2]);
-      n[0] = ex::dvd(n[0], nn); n[1] = ex::dvd(n[1], nn); n[2] = ex::dvd(n[2], nn);
-      triangle_point<WANT_XP, NEN>(Xe, re, rho_t, r.cls == 1, Xt, Et, n, x, s);
+      if (!ok) { for (int d = 0; d < 3; d++) { T.ps[d] = 0; T.pe[d] = 0; } }
+      for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(T.Xt[1][d], T.Xt[0][d]); Et[1][d] = ex::sub(T.Xt[2][d], T.Xt[1][d]); }
+      T.n[0] = ex::sub(ex::mul(Et[0][1], Et[1][2]), ex::mul(Et[0][2], Et[1][1]));
+      T.n[1] = ex::sub(ex::mul(Et[0][2], Et[1][0]), ex::mul(Et[0][0], Et[1][2]));
+      T.n[2] = ex::sub(ex::mul(Et[0][0], Et[1][1]), ex::mul(Et[0][1], Et[1][0]));
+      double nn = ex::norm3(T.n[0], T.n[1], T.n[2]);
+      T.n[0] = ex::dvd(T.n[0], nn); T.n[1] = ex::dvd(T.n[1], nn); T.n[2] = ex::dvd(T.n[2], nn);
+      tri[o++] = T;
     }
+  }
+}
+// process_boundary_faces! for one grid point (point index pi[3], coordinate x): walks the element's triangle records
+template <bool WANT_XP, int NEN>
+__device__ inline void boundary_faces_point(const ActRec &r, const TriRec *__restrict__ tri, const int *__restrict__ IEN, const double *__restrict__ X,
+                                            const double *__restrict__ rn, double rho_t, const int pi[3], const double x[3], VoxState &s) {
+  constexpr int NSN = NEN == 8 ? 4 : 3;
+  const int ntri = __popc((unsigned)r.fmask) * NSN;
+  bool loaded = false;
+  double Xe[3][NEN], re[NEN];
+  for (int t = 0; t < ntri; t++) {
+    const TriRec &T = tri[r.tri_off + t];
+    if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
+    if (r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113)
+      for (int a = 0; a < NEN; a++) { i64 n = IEN[NEN * (i64)r.el + a]; re[a] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * n + d]; }
+      loaded = true;
+    }
+    double Xt[3][3], Et[3][3], n[3];
+    for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; n[d] = T.n[d]; }
+    for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+    triangle_point<WANT_XP, NEN>(Xe, re, rho_t, r.cls == 1, Xt, Et, n, x, s);
   }
 }
 
@@ -261,7 +300,7 @@ __device__ inline void boundary_faces_point(const ActRec &r, const int *__restri
 // small register footprint; FACES = true handles the others.  Both walk all tiles and skip those of the other kind.
 template <bool WANT_XP, int NEN, bool FACES>
 __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
-                                                       const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
+                                                       const ActRec *__restrict__ rec, const TriRec *__restrict__ tri, const int *__restrict__ IEN, const double *__restrict__ X,
                                                        const double *__restrict__ rn, double rho_t, double delta, const double *__restrict__ pairbuf,
                                                        const double *__restrict__ pairxp, double *__restrict__ dist, double *__restrict__ xpo) {
   __shared__ ActRec srec[TILE_VOX / 32][ACULL_CAP];
@@ -294,7 +333,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       for (int q = 0; q < n; q++) {
         const ActRec &r = srec[warp][q];
         if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
-        if (FACES && r.fmask) boundary_faces_point<WANT_XP, NEN>(r, IEN, X, rn, g, rho_t, delta, pi, x, s);
+        if (FACES && r.fmask) boundary_faces_point<WANT_XP, NEN>(r, tri, IEN, X, rn, rho_t, pi, x, s);
         if (r.cls == 2) {
           i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
           double dt = pairbuf[idx];
@@ -371,6 +410,19 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     k_emit_keys<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff, poff, g, ctx->keys.as<u64>(), ctx->tile_ptr.as<int>() + 1, ctx->tile_faces.as<unsigned char>()); LAUNCH_CHECK();
     int tbits = 1; while ((1ll << tbits) < g.ntiles) tbits++;
     if (nkeys > 0) { if (r2s_sort_keys_u64(ctx, ctx->keys.as<u64>(), ctx->keys_alt.as<u64>(), nkeys, 32 + tbits, &sorted)) return 1; }
+    // boundary-face triangle table
+    CK(ctx->tri_cnt.reserve(sizeof(int) * 2 * (size_t)(nact + 1)));
+    int *tcnt = ctx->tri_cnt.as<int>(), *toff32 = tcnt + (nact + 1);
+    CK(cudaMemsetAsync(tcnt + nact, 0, sizeof(int), st));
+    k_tri_count<<<cdiv(nact, 256), 256, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->nsn, tcnt); LAUNCH_CHECK();
+    if (r2s_scan_exclusive_i32(ctx, tcnt, toff32, nact + 1)) return 1;
+    int ntri = 0;
+    CK(cudaMemcpyAsync(&ntri, toff32 + nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(ctx->tri_rec.reserve(sizeof(TriRec) * (size_t)(ntri + 1)));
+    if (nen == 8) k_tri_records<8><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
+    else k_tri_records<4><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
+    LAUNCH_CHECK();
   }
   // tile_ptr[t+1] currently holds the count of tile t (tile_ptr[0] = 0): inclusive scan in place == exclusive offsets
   {
@@ -393,7 +445,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(cudaEventRecord(ctx->ev[2], st));
   {
 #define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
-        ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
+        ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
         ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
     if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
     else { if (want_xp) { ASM(true, 4, false); ASM(true, 4, true); } else { ASM(false, 4, false); ASM(false, 4, true); } }

@@ -9,19 +9,21 @@
 #include "r2s_tables.cuh"
 #include "r2s_exact.cuh"
 
-struct SRange { int a[3], b[3]; };   // inclusive grid-point index range of the candidate points of one element
+struct SRange { int a[3], b[3]; int hot, pad; };   // inclusive grid-point index range of the candidate points of one element;
+                                                   // hot = some nodal density >= rho_t (HEX8 skip rule, SignDetection.jl:36)
 
 __device__ __forceinline__ int tet_cell_index(double x, double amin, double cell, int n1) {   // point_to_grid_index :256-268 (1-based, clamped)
   int idx = (int)floor(ex::dvd(ex::sub(x, amin), cell)) + 1;
   return max(1, min(n1, idx));
 }
-__global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, GridDev g, int kz0, int kz1,
-                              SRange *__restrict__ rng, i64 *__restrict__ ntile) {
+__global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, double rho_t,
+                              GridDev g, int kz0, int kz1, SRange *__restrict__ rng, i64 *__restrict__ ntile) {
   i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (e >= nel) return;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
-  SRange r; bool ok = true;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rmax = -1e300;
+  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; rmax = fmax(rmax, rn[n]); for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+  SRange r; bool ok = true; r.pad = 0;
+  r.hot = (nen == 4 || !(rmax < rho_t)) ? 1 : 0;
   for (int d = 0; d < 3; d++) {
     const double *pc = g.pc + g.pc_off[d]; int n1 = g.np[d], a, b;
     if (nen == 8) {
@@ -82,9 +84,29 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
   const int wx0 = tx * TILE_X, wx1 = wx0 + TILE_X - 1, wy0 = ty * TILE_Y + (warp % (TILE_Y / 4)) * 4, wy1 = wy0 + 3, wz = tz * TILE_Z + warp / (TILE_Y / 4);
   double x[3] = {0, 0, 0};
   if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
-  double sign = -1.0, mx = -1e300, max_local = 10.0; bool done = false, any = false;
+  double sign = -1.0, max_local = 10.0; bool done = false;
   const int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
+  // pass A: does this point have a candidate at all whose nodal densities reach rho_t?  If not it is skipped with sign -1
+  // (SignDetection.jl:36; TET4 elements are all marked hot).  Costs only integer range tests; whole warps of the void
+  // region leave here without touching the mesh.
+  bool hotany = false;
+  for (int p = p0; p < p1; p += 32) {
+    int idx = p + lane; bool ov = false; SRange r;
+    if (idx < p1) {
+      r = rng[(int)(keys[idx] & 0xffffffffull)];
+      ov = r.hot && r.a[0] <= wx1 && r.b[0] >= wx0 && r.a[1] <= wy1 && r.b[1] >= wy0 && r.a[2] <= wz && r.b[2] >= wz;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ov);
+    while (m) {
+      int src = __ffs(m) - 1; m &= m - 1;
+      int a0 = __shfl_sync(0xffffffffu, r.a[0], src), b0 = __shfl_sync(0xffffffffu, r.b[0], src), a1 = __shfl_sync(0xffffffffu, r.a[1], src),
+          b1 = __shfl_sync(0xffffffffu, r.b[1], src), a2 = __shfl_sync(0xffffffffu, r.a[2], src), b2 = __shfl_sync(0xffffffffu, r.b[2], src);
+      if (pi[0] >= a0 && pi[0] <= b0 && pi[1] >= a1 && pi[1] <= b1 && pi[2] >= a2 && pi[2] <= b2) hotany = true;
+    }
+  }
+  const bool live = valid && hotany;
   int p = p0;
+  if (!__any_sync(0xffffffffu, live)) p = p1;
   while (p < p1) {
     int n = 0;
     while (p < p1 && n <= CULL_CAP - 32) {
@@ -101,41 +123,41 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
     int pos = 0;
     while (true) {
       // advance to this lane's next candidate
-      if (valid) {
+      if (live && !done) {
         while (pos < n) {
           const SRange &r = s_rg[warp][pos];
           if (pi[0] >= r.a[0] && pi[0] <= r.b[0] && pi[1] >= r.a[1] && pi[1] <= r.b[1] && pi[2] >= r.a[2] && pi[2] <= r.b[2]) break;
           pos++;
         }
       } else pos = n;
-      bool act = pos < n && !(NEN == 4 && done);
+      bool act = pos < n;
       if (!__any_sync(0xffffffffu, act)) break;
       if (act) {
         const int e = s_el[warp][pos]; pos++;
         if (NEN == 8) {
-          any = true;
-          int nd[8]; double re[8];
+          int nd[8];
 #pragma unroll
-          for (int a = 0; a < 8; a++) { nd[a] = IEN[8 * (i64)e + a]; re[a] = rn[nd[a]]; mx = fmax(mx, re[a]); }
-          if (!done) {
-            double xi[3], N[8], A[3][8]; bool affine = true;
+          for (int a = 0; a < 8; a++) nd[a] = IEN[8 * (i64)e + a];
+          double xi[3], A[3][8]; bool affine = true;
 #pragma unroll
-            for (int d = 0; d < 3; d++) {      // one coordinate at a time: only the monomial coefficients stay live
-              double v[8];
+          for (int d = 0; d < 3; d++) {      // one coordinate at a time: only the monomial coefficients stay live
+            double v[8];
 #pragma unroll
-              for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)nd[a] + d];
-              ex::mono8(v, A[d]);
-              if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
-            }
-            ex::inverse_map_hex8_mono(A, affine, x, xi);
-            double mn = ex::max3abs(xi[0], xi[1], xi[2]);
-            if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
-              ex::hex8_shape(xi, N);
-              double rho = ex::dot8(N, re);
-              if (rho >= rho_t) sign = 1.0;
-              if (mn < 0.95) done = true;                              // :51-59 break
-              max_local = mn;
-            }
+            for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)nd[a] + d];
+            ex::mono8(v, A[d]);
+            if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
+          }
+          ex::inverse_map_hex8_mono(A, affine, x, xi);
+          double mn = ex::max3abs(xi[0], xi[1], xi[2]);
+          if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
+            double N[8], re[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) re[a] = rn[nd[a]];
+            ex::hex8_shape(xi, N);
+            double rho = ex::dot8(N, re);
+            if (rho >= rho_t) sign = 1.0;
+            if (mn < 0.95) done = true;                              // :51-59 break
+            max_local = mn;
           }
         } else {
           double Xe[3][4], re[4], lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -176,7 +198,6 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
     __syncwarp();
   }
   if (valid) {
-    if (NEN == 8 && (!any || mx < rho_t)) sign = -1.0;            // :36 skip
     i64 v = ((i64)pi[2] * g.np[1] + pi[1]) * g.np[0] + pi[0];
     if (signs) signs[v] = sign;
     if (sdf) sdf[v] = dist[v] * sign;
@@ -196,7 +217,7 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   CK(cudaMemsetAsync(ctx->s_tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
   CK(cudaMemsetAsync(ctx->cnt_a.as<i64>() + nel, 0, sizeof(i64), st));
   i64 *ntile = ctx->cnt_a.as<i64>(), *toff = ctx->cnt_b.as<i64>();
-  k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, kz0, kz1, ctx->s_rng.as<SRange>(), ntile); LAUNCH_CHECK();
+  k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, g, kz0, kz1, ctx->s_rng.as<SRange>(), ntile); LAUNCH_CHECK();
   if (r2s_scan_exclusive_i64(ctx, ntile, toff, nel + 1)) return 1;
   i64 nkeys = 0;
   CK(cudaMemcpyAsync(&nkeys, toff + nel, sizeof(i64), cudaMemcpyDeviceToHost, st));
