@@ -45,6 +45,7 @@ typedef struct r2s_report {
   float th, volume;             /* LS_Threshold offset and final fine-grid volume                          */
   float ms_bin, ms_project, ms_assemble, ms_sign, ms_cc, ms_rbf_prep, ms_cg, ms_lsf, ms_threshold, ms_fine, ms_volume, ms_total;
   int64_t launches;             /* kernels launched by the last call                                       */
+  int64_t collectives;          /* NCCL collectives / grouped halo exchanges issued by the last call       */
 } r2s_report;
 
 /* ---- context -------------------------------------------------------------------------------------------- */
@@ -96,6 +97,15 @@ int r2s_result_ptrs_dev(r2s_ctx *ctx, void **sdf_dev, void **fine_sdf_dev);
 /* restrict this context to coarse planes k in [k0,k1) of the grid set by r2s_set_grid (halo planes are handled
  * internally); k0 = 0, k1 = N3+1 restores the full grid */
 int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1);
+/* Slab communicator (NCCL, bound with dlopen; see csrc/r2s_comm.cu).  Rank 0 makes a 128-byte id with r2s_comm_unique_id,
+ * the host program carries it to the other ranks (torch.distributed / MPI / a file), every rank calls r2s_comm_init and
+ * then r2s_set_slab (collective: the ranks exchange their plane ranges, which must tile [0, N3+1) in rank order with at
+ * least 3 planes each).  From then on r2s_pipeline_resident / r2s_pipeline_slab are collective calls: halo planes of the
+ * smoothing fields travel by ncclSend/ncclRecv between z-neighbours, dot products / extrema / volume sums by all-reduce,
+ * and the 1-bit interior mask of the artifact removal by one all-gather. */
+int r2s_comm_unique_id(void *id128);
+int r2s_comm_init(r2s_ctx *ctx, int rank, int nranks, const void *id128);
+int r2s_comm_destroy(r2s_ctx *ctx);
 /* r2s_pipeline for one slab with host buffers: returns only this rank's planes, sdf_slab[(k1-k0)*np0*np1] and
  * fine_slab[(kf1-kf0)*f0*f1], kf0 = smooth*k0, kf1 = smooth*k1 (the last slab also owns the final fine plane) */
 int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep);

@@ -24,7 +24,7 @@ import numpy as np
 __all__ = ["HEX8", "TET4", "Rho2sdfOptions", "Mesh", "Grid", "getMesh_AABB", "generateGridPoints", "noninteractive_sdf_grid_setup",
            "DenseInNodes", "find_threshold_for_volume", "calculate_isocontour_volume", "evalDistances", "Sign_Detection",
            "remove_sdf_artifacts", "RBFs_smoothing", "calculate_volume_from_sdf", "rho2sdf", "rho2sdf_hex8", "rho2sdf_tet4",
-           "FineGrid", "R2SError", "slab_partition", "load_library", "library_path", "Params", "Report", "Context"]
+           "FineGrid", "R2SError", "slab_partition", "init_slab_comm", "broadcast_unique_id", "load_library", "library_path", "Params", "Report", "Context"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -54,7 +54,7 @@ class Report(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_solid", "n_crossing", "n_active", "n_pairs", "n_not_converged", "n_newton_iters", "n_flipped")] + \
                [("cg_iters", C.c_int32), ("bisections", C.c_int32), ("th", C.c_float), ("volume", C.c_float)] + \
                [(n, C.c_float) for n in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_rbf_prep", "ms_cg", "ms_lsf",
-                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64)]
+                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64), ("collectives", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -101,6 +101,9 @@ def load_library():
     L.r2s_download_fine_sdf.argtypes = [vp, vp]
     L.r2s_result_ptrs_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.r2s_pipeline_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report)]
+    L.r2s_comm_unique_id.argtypes = [vp]
+    L.r2s_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.r2s_comm_destroy.argtypes = [vp]
     L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]
     _LIB = L
     return L
@@ -157,6 +160,37 @@ def slab_partition(nz_points, world):
         out.append((k, k + n))
         k += n
     return out
+
+
+def broadcast_unique_id(make_id, rank, world, group=None):
+    """Carry the 128-byte communicator id from rank 0 to every rank over torch.distributed (any backend: nccl or gloo).
+    `make_id()` is called on rank 0 only and must return 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        raw = make_id()
+        if len(raw) != 128:
+            raise R2SError("communicator id must be 128 bytes")
+        t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def init_slab_comm(ctx, rank, world, k0, k1, uid=None):
+    """Make `ctx` one rank of a z-slab decomposition: NCCL communicator (id from rank 0, carried by torch.distributed unless
+    `uid` is given) and the plane range [k0, k1) of this rank.  Collective: every rank must call it."""
+    lib = ctx.lib
+    if uid is None:
+        def make():
+            buf = C.create_string_buffer(128)
+            if lib.r2s_comm_unique_id(buf) != 0:
+                raise R2SError("r2s_comm_unique_id failed (is NCCL available?)")
+            return buf.raw
+        uid = broadcast_unique_id(make, rank, world)
+    ctx.check(lib.r2s_comm_init(ctx.h, int(rank), int(world), C.c_char_p(uid)))
+    ctx.check(lib.r2s_set_slab(ctx.h, int(k0), int(k1)))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

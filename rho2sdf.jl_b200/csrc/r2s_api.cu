@@ -27,10 +27,11 @@ void r2s_destroy(r2s_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  r2s_comm_destroy(ctx);
   DevBuf *all[] = {&ctx->X, &ctx->IEN32, &ctx->ine_ptr, &ctx->ine_el, &ctx->fbnd, &ctx->rho_e, &ctx->rho_n, &ctx->gtab_d, &ctx->gtab_i, &ctx->cls, &ctx->act_flag,
                    &ctx->act_idx, &ctx->act_rec, &ctx->cnt_a, &ctx->cnt_b, &ctx->keys, &ctx->keys_alt, &ctx->tile_ptr, &ctx->tile_faces, &ctx->tri_cnt, &ctx->tri_rec, &ctx->pairbuf, &ctx->pairxp, &ctx->cubtmp,
                    &ctx->counters, &ctx->dist, &ctx->xp, &ctx->sdf, &ctx->signs, &ctx->s_rng, &ctx->s_cnt, &ctx->s_keys, &ctx->s_keys_alt, &ctx->s_tile_ptr,
-                   &ctx->cc_label, &ctx->cc_size, &ctx->cc_scal, &ctx->f_s, &ctx->f_w, &ctx->f_r, &ctx->f_u, &ctx->f_c, &ctx->f_lsf, &ctx->f_fine, &ctx->f_part,
+                   &ctx->cc_label, &ctx->cc_size, &ctx->cc_scal, &ctx->cc_bits, &ctx->cc_bits_all, &ctx->f_s, &ctx->f_w, &ctx->f_r, &ctx->f_u, &ctx->f_c, &ctx->f_lsf, &ctx->f_fine, &ctx->f_part,
                    &ctx->f_scal, &ctx->cutlist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1]};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
@@ -110,7 +111,28 @@ int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1) {
   if (!ctx) return 1;
   if (!ctx->has_grid) FAIL("r2s_set_slab: call r2s_set_grid first");
   if (k0 < 0 || k1 > ctx->g.np[2] || k0 >= k1) FAIL("r2s_set_slab: invalid plane range");
+  if (ctx->nranks > 1 && k1 - k0 < 3) FAIL("r2s_set_slab: a slab needs at least 3 planes (smoothing halo)");
   ctx->k0 = k0; ctx->k1 = k1;
+  ctx->slab_k0.clear();
+  if (ctx->nranks > 1) {
+    // every rank learns the whole partition (collective: all ranks call r2s_set_slab); slabs must tile [0, N3+1) in rank order
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->cc_scal.reserve(sizeof(unsigned) * 2 * 64 + 64));
+    if (ctx->nranks > 64) FAIL("r2s_set_slab: more than 64 slabs");
+    unsigned mine[2] = {(unsigned)k0, (unsigned)k1}, all[128];
+    unsigned *d = ctx->cc_scal.as<unsigned>();
+    CK(cudaMemcpyAsync(d + 2 * ctx->rank, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    if (r2s_allgather_u32(ctx, d + 2 * ctx->rank, d, 2)) return 1;
+    CK(cudaMemcpyAsync(all, d, sizeof(unsigned) * 2 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < ctx->nranks; r++) {
+      if ((r == 0 && all[0] != 0) || (r > 0 && all[2 * r] != all[2 * r - 1]) || all[2 * r + 1] - all[2 * r] < 3)
+        FAIL("r2s_set_slab: slabs must tile the planes contiguously in rank order, at least 3 planes each");
+      ctx->slab_k0.push_back((int)all[2 * r]);
+    }
+    if ((int)all[2 * ctx->nranks - 1] != ctx->g.np[2]) FAIL("r2s_set_slab: slabs do not cover the grid");
+    ctx->slab_k0.push_back(ctx->g.np[2]);
+  }
   return 0;
 }
 
@@ -254,7 +276,7 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
   if (p->smooth < 1 || p->smooth > 2) FAIL("r2s_pipeline: smooth must be 1 (:same) or 2 (:fine)");
   CK(cudaSetDevice(ctx->device));
-  ctx->launches = 0;
+  ctx->launches = 0; ctx->collectives = 0;
   memset(&ctx->rep, 0, sizeof(ctx->rep));
   CK(cudaEventRecord(ctx->ev[8], ctx->stream));
   if (r2s_dev_eval_distances(ctx, p->rho_t, p->delta_factor, false)) return 1;
@@ -271,7 +293,7 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   CK(cudaEventElapsedTime(&ctx->rep.ms_sign, ctx->ev[9], ctx->ev[10]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_cc, ctx->ev[10], ctx->ev[11]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_total, ctx->ev[8], ctx->ev[12]));
-  ctx->rep.launches = ctx->launches;
+  ctx->rep.launches = ctx->launches; ctx->rep.collectives = ctx->collectives;
   if (rep) *rep = ctx->rep;
   return 0;
 }

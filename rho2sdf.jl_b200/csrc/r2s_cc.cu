@@ -4,6 +4,7 @@
 // the smaller one, path halving), canonical label = smallest linear index of the component.  Labels are not an output
 // of the reference -- only the set of flipped points is -- so any canonical labelling is parity-safe; the largest
 // component is chosen by (size, then smallest root), which is deterministic.
+#include <algorithm>
 #include "r2s_common.cuh"
 
 __device__ __forceinline__ int uf_find(int *L, int x) {
@@ -68,7 +69,80 @@ __global__ void k_cc_flip(i64 n, i64 v0, const int *__restrict__ L, const int *_
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(nflip, (u64)__popc(m));
 }
 
+// ---- multi-rank (z-slab) variant ----------------------------------------------------------------------------------
+// Components cross slab boundaries, but the only input of the labelling is the 1-bit interior mask: every rank packs the
+// mask of its planes (1 bit per grid point), one all-gather replicates the whole mask (ngp / 8 bytes -- 17 MB at 519^3),
+// every rank labels the full grid redundantly and flips only its own planes.  No label merging across ranks, bit-identical
+// to the single-GPU result by construction.
+struct SlabMap { int nranks; int k0[65]; };
+__global__ void k_mask_pack(int nxy, int wpp, int kz0, int kz1, const double *__restrict__ sdf, double thr, unsigned *__restrict__ bits) {
+  // one warp per 32 consecutive points of a plane
+  i64 wid = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  i64 nw = (i64)wpp * (kz1 - kz0);
+  if (wid >= nw) return;
+  int pl = (int)(wid / wpp), w = (int)(wid % wpp), idx = w * 32 + lane;
+  bool in = idx < nxy && sdf[(i64)(kz0 + pl) * nxy + idx] >= thr;
+  unsigned m = __ballot_sync(0xffffffffu, in);
+  if (lane == 0) bits[wid] = m;
+}
+__global__ void k_cc_init_bits(int nxy, int nz, int wpp, i64 stride, SlabMap sm, const unsigned *__restrict__ bits, int *__restrict__ L, int *__restrict__ sz) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= (i64)nxy * nz) return;
+  int k = (int)(v / nxy), idx = (int)(v % nxy), r = 0;
+  while (r + 1 < sm.nranks && k >= sm.k0[r + 1]) r++;
+  unsigned word = bits[(i64)r * stride + (i64)(k - sm.k0[r]) * wpp + (idx >> 5)];
+  L[v] = ((word >> (idx & 31)) & 1u) ? (int)v : -1;
+  sz[v] = 0;
+}
+static int remove_artifacts_slabs(r2s_ctx *ctx, double thr, double ratio, i64 *flipped) {
+  const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
+  const int nx = g.np[0], ny = g.np[1], nz = g.np[2], nxy = nx * ny, wpp = (nxy + 31) / 32;
+  const i64 n = (i64)nxy * nz;
+  if (n >= (1ll << 31)) FAIL("remove_sdf_artifacts: grid too large for 32-bit labels");
+  if ((int)ctx->slab_k0.size() != ctx->nranks + 1) FAIL("remove_sdf_artifacts: slab table missing (call r2s_set_slab after r2s_comm_init)");
+  SlabMap sm; sm.nranks = ctx->nranks; int maxpl = 0;
+  if (ctx->nranks > 64) FAIL("remove_sdf_artifacts: more than 64 slabs");
+  for (int r = 0; r <= ctx->nranks; r++) sm.k0[r] = ctx->slab_k0[r];
+  for (int r = 0; r < ctx->nranks; r++) maxpl = std::max(maxpl, sm.k0[r + 1] - sm.k0[r]);
+  const i64 stride = (i64)maxpl * wpp;
+  CK(ctx->cc_bits_all.reserve(sizeof(unsigned) * (size_t)(stride * ctx->nranks)));
+  CK(ctx->cc_label.reserve(sizeof(int) * (size_t)n));
+  CK(ctx->cc_size.reserve(sizeof(int) * (size_t)n));
+  CK(ctx->cc_scal.reserve(sizeof(u64) * 4));
+  CK(cudaMemsetAsync(ctx->cc_scal.p, 0, sizeof(u64) * 4, st));
+  unsigned *all = ctx->cc_bits_all.as<unsigned>(), *mine = all + stride * ctx->rank;
+  int *L = ctx->cc_label.as<int>(), *sz = ctx->cc_size.as<int>(); u64 *sc = ctx->cc_scal.as<u64>();
+  double *sdf = ctx->sdf.as<double>();
+  const int kz0 = (int)ctx->k0, kz1 = (int)ctx->k1;
+  CK(cudaMemsetAsync(mine, 0, sizeof(unsigned) * (size_t)stride, st));
+  k_mask_pack<<<cdiv((i64)wpp * (kz1 - kz0) * 32, 256), 256, 0, st>>>(nxy, wpp, kz0, kz1, sdf, thr, mine); LAUNCH_CHECK();
+  if (r2s_allgather_u32(ctx, mine, all, (size_t)stride)) return 1;       // in place: my block already sits at its slot
+  int nb = cdiv(n, 256);
+  k_cc_init_bits<<<nb, 256, 0, st>>>(nxy, nz, wpp, stride, sm, all, L, sz); LAUNCH_CHECK();
+  k_cc_merge<<<nb, 256, 0, st>>>(nx, ny, nz, L); LAUNCH_CHECK();
+  k_cc_flatten<<<nb, 256, 0, st>>>(n, L, sz); LAUNCH_CHECK();
+  k_cc_largest<<<nb, 256, 0, st>>>(n, L, sz, sc); LAUNCH_CHECK();
+  u64 best = 0;
+  CK(cudaMemcpyAsync(&best, sc, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *flipped = 0;
+  if (best == 0) return 0;
+  i64 largest = (i64)(best >> 32); int lroot = (int)(0xffffffffu - (unsigned)(best & 0xffffffffu));
+  double q = ratio * (double)largest; i64 ms = (i64)nearbyint(q); if (ms < 1) ms = 1;
+  if (ms > 0x7fffffff) ms = 0x7fffffff;
+  // flip my planes only: labels are global indices, so offset both arrays to the slab
+  i64 v0 = (i64)kz0 * nxy, nloc = (i64)(kz1 - kz0) * nxy;
+  k_cc_flip<<<cdiv(nloc, 256), 256, 0, st>>>(nloc, v0, L + v0, sz, lroot, (int)ms, sdf, sc + 1); LAUNCH_CHECK();
+  if (r2s_allreduce(ctx, sc + 1, 1, 1)) return 1;
+  u64 nf = 0;
+  CK(cudaMemcpyAsync(&nf, sc + 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *flipped = (i64)nf;
+  return 0;
+}
+
 int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flipped) {
+  if (ctx->nranks > 1) return remove_artifacts_slabs(ctx, thr, ratio, flipped);
   const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
   int nx = g.np[0], ny = g.np[1], nz = (int)(ctx->k1 - ctx->k0);
   i64 n = (i64)nx * ny * nz, v0 = (i64)ctx->k0 * nx * ny;

@@ -79,6 +79,7 @@ struct r2s_ctx {
   bool has_grid = false;
   GridDev g;
   i64 k0 = 0, k1 = 0;                       // slab of coarse planes handled by this context
+  void *comm = nullptr; int rank = 0, nranks = 1; i64 collectives = 0; std::vector<int> slab_k0;    // NCCL communicator of the slab decomposition (r2s_comm.cu)
   DevBuf gtab_d, gtab_i;
   std::vector<double> h_pc[3];
 
@@ -87,7 +88,7 @@ struct r2s_ctx {
   DevBuf dist, xp, sdf, signs;
   DevBuf s_rng, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
   // connected components
-  DevBuf cc_label, cc_size, cc_scal;
+  DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all;
   // smoothing
   DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, vlist[2];
   int smooth_last = 1;
@@ -135,3 +136,8 @@ int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, 
 int r2s_scan_exclusive_i64(r2s_ctx *ctx, const i64 *in, i64 *out, i64 n);  // r2s_util.cu (cub)
 int r2s_scan_exclusive_i32(r2s_ctx *ctx, const int *in, int *out, i64 n);
 int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64 **sorted);
+// r2s_comm.cu: collectives over the slab communicator (no-ops for a single rank)
+int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
+int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count);
+int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k1, int nz, int below, int above);
+extern "C" int r2s_comm_destroy(r2s_ctx *ctx);

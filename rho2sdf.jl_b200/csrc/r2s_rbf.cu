@@ -39,12 +39,12 @@ struct StencilW { float w[8]; };
 // out = K * in_eff with in_eff = (beta_mode ? r + beta*u : in).  When beta_mode, the interior in_eff is written back to u.
 // partial[block] (double) receives sum(in_eff * out) over the block's interior.
 template <bool BETA>
-__global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx, int ny, int nz, const float *__restrict__ in, const float *__restrict__ r,
+__global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
                                                                            const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
                                                                            double *__restrict__ partial, StencilW W) {
   __shared__ float sm[ST_Z + 2 * ST_H][ST_Y + 2 * ST_H][ST_X + 2 * ST_H];
   __shared__ double red[ST_X * ST_Y * (ST_Z / ST_ZB) / 32];
-  const int bx = blockIdx.x * ST_X, by = blockIdx.y * ST_Y, bz = blockIdx.z * ST_Z;
+  const int bx = blockIdx.x * ST_X, by = blockIdx.y * ST_Y, bz = kz0 + blockIdx.z * ST_Z;      // outputs: planes [kz0, kz1) (z-slab)
   const int tid = threadIdx.x;
   float beta = 0.0f;
   if (BETA) beta = scal[0];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx
 #pragma unroll
   for (int q = 0; q < ST_ZB; q++) {
     int gx = bx + lx, gy = by + ly, gz = bz + lzb * ST_ZB + q;
-    if (gx < nx && gy < ny && gz < nz) {
+    if (gx < nx && gy < ny && gz < kz1) {
       i64 gi = ((i64)gz * ny + gy) * nx + gx;
       float ctr = sm[lzb * ST_ZB + q + ST_H][ly + ST_H][lx + ST_H];
       out[gi] = acc[q];
@@ -113,12 +113,13 @@ __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restr
 __global__ void k_cg_alpha(float *scal, const double *uc) {     // alpha = residual^2 / dot(u, c)
   float res = scal[2]; scal[1] = res * res / (float)(*uc);
 }
-__global__ void k_cg_update(i64 n, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c, float *__restrict__ x,
+// elementwise over [0, n) (owned planes plus halo); the residual norm is summed over the owned part [o_lo, o_hi) only
+__global__ void k_cg_update(i64 n, i64 o_lo, i64 o_hi, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c, float *__restrict__ x,
                             float *__restrict__ r, double *__restrict__ partial) {
   __shared__ double red[8];
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   float alpha = scal[1]; double rr = 0.0;
-  if (v < n) { x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv; rr = (double)rv * (double)rv; }
+  if (v < n) { x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv; if (v >= o_lo && v < o_hi) rr = (double)rv * (double)rv; }
   for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
   __syncthreads();
@@ -331,6 +332,10 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
 }
+// acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
+__global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red) {
+  red[0] = acc[0] + acc[3]; red[1] = acc[1] > (u64)cutcap ? 1 : 0; red[2] = acc[2]; red[3] = 0;
+}
 // state of one LS_Threshold search (see k_vol_step)
 struct VolBisect {
   const float *sdf; int nx, ny, kc0, kc1; float edge; int step, cur; i64 n_cur; u64 *acc;
@@ -338,11 +343,11 @@ struct VolBisect {
 static int vol_bisect_begin(r2s_ctx *ctx, VolBisect &vb, const float *sdf, int nx, int ny, int nz, int kc0, int kc1, float edge) {
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("LS_Threshold: grid too large for 32-bit cell ids");
-  CK(ctx->f_scal.reserve(256));
+  CK(ctx->f_scal.reserve(512));
   vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0;
   vb.n_cur = (i64)(nx - 1) * (ny - 1) * (i64)(kc1 - kc0);
-  vb.acc = (u64 *)((char *)ctx->f_scal.p + 128);
-  CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 8, ctx->stream));
+  vb.acc = (u64 *)((char *)ctx->f_scal.p + 128);       // acc[0..7], red[0..3] behind it
+  CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 12, ctx->stream));
   return 0;
 }
 // volume of {sdf - th >= 0} over the cells of planes [kc0, kc1); [lo, hi] = the bracket th was taken from
@@ -373,12 +378,20 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
     }
     LAUNCH_CHECK();
     k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, 0, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
+    // cross-rank sum of (full cells, overflow flag, cut sum); integers, so the total does not depend on the slab count
+    u64 *red = vb.acc + 8, hr[4];
+    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, cutcap, red); LAUNCH_CHECK();
+    if (r2s_allreduce(ctx, red, 4, 1)) return 1;
     CK(cudaMemcpyAsync(h, vb.acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hr, red, sizeof(hr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if ((i64)h[1] > cutcap) { CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024))); continue; }
+    if (hr[1] != 0) {      // some rank's cut list overflowed: every rank repeats the step (collectives stay matched)
+      if ((i64)h[1] > cutcap) CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
+      continue;
+    }
     if (emit) { vb.cur = out; vb.n_cur = (i64)h[4 + out]; }
     float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
-    *vol = (double)(h[0] + h[3]) * (double)ev + ((double)h[2] / 137438953472.0 /* 2^37 */) * (double)jac;
+    *vol = (double)hr[0] * (double)ev + ((double)hr[2] / 137438953472.0 /* 2^37 */) * (double)jac;
     return 0;
   }
   FAIL("LS_Threshold: cut-cell list overflow");
@@ -397,11 +410,11 @@ __constant__ TapTable c_taps;
 #define FN_Y 4
 #define FN_Z 4
 template <int SM>
-__global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, int nz, int fx, int fy, int fz, const float *__restrict__ w, float th, float *__restrict__ out) {
+__global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, int nz, int fx, int fy, int fz, int kf0, const float *__restrict__ w, float th, float *__restrict__ out) {
   // coarse tile covering this block's fine outputs, with halo 3 on each side (taps reach -2..+3)
   constexpr int CX = FN_X / SM + 6, CY = FN_Y / SM + 6 + 1, CZ = FN_Z / SM + 6 + 1;
   __shared__ float sm[CZ][CY][CX + 1];
-  const int fbx = blockIdx.x * FN_X, fby = blockIdx.y * FN_Y, fbz = blockIdx.z * FN_Z;
+  const int fbx = blockIdx.x * FN_X, fby = blockIdx.y * FN_Y, fbz = kf0 + blockIdx.z * FN_Z;        // fz = one past the last fine plane of this launch
   const int cbx = fbx / SM - 3, cby = fby / SM - 3, cbz = fbz / SM - 3;
   for (int t = threadIdx.x; t < CX * CY * CZ; t += blockDim.x) {
     int lx = t % CX, ly = (t / CX) % CY, lz = t / (CX * CY);
@@ -511,6 +524,13 @@ __global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny
       }
   }
 }
+// u_new = r + beta * u_old on the halo planes of a slab (the fused stencil kernel writes u_new on the owned planes only)
+__global__ void k_unew_halo(i64 n1, i64 off2, i64 n2, const float *__restrict__ scal, const float *__restrict__ r, const float *__restrict__ u, float *__restrict__ unew) {
+  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (v >= n1 + n2) return;
+  i64 i = v < n1 ? v : off2 + (v - n1);
+  unew[i] = r[i] + scal[0] * u[i];
+}
 __global__ void k_add_scalar(i64 n, float *__restrict__ a, float s) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (v < n) a[v] = a[v] + s;
@@ -550,56 +570,72 @@ static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
 }
 
 // ------------------------------------------------------------------------------------------------ driver
+// Slab layout: every field is indexed globally (plane k at offset k * nx * ny); a rank owns the coarse planes [k0, k1) and
+// keeps up to 3 halo planes on each side valid.  With one rank [k0, k1) is the whole grid and every exchange is a no-op.
 int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double target, bool final_volume, float *th_out, float *vol_out) {
   const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
-  if (ctx->k0 != 0 || ctx->k1 != g.np[2]) FAIL("rbf smoothing on a z-slab needs the halo exchange driver (not available through this entry point)");
-  const int nx = g.np[0], ny = g.np[1], nz = g.np[2]; const i64 n = (i64)nx * ny * nz;
-  const int fx = g.N[0] * smooth + 1, fy = g.N[1] * smooth + 1, fz = g.N[2] * smooth + 1; const i64 nf = (i64)fx * fy * fz;
+  const int nx = g.np[0], ny = g.np[1], nz = g.np[2]; const i64 n = (i64)nx * ny * nz, pl = (i64)nx * ny;
+  const int k0 = (int)ctx->k0, k1 = (int)ctx->k1;
+  if (ctx->nranks == 1 && (k0 != 0 || k1 != nz)) FAIL("rbf smoothing on a z-slab needs the slab communicator (r2s_comm_init on every rank)");
+  const int e0 = std::max(0, k0 - 2), e1 = std::min(nz, k1 + 2);        // owned planes + CG halo
+  const i64 o_lo = (i64)k0 * pl, nown = (i64)(k1 - k0) * pl, x_lo = (i64)e0 * pl, next = (i64)(e1 - e0) * pl;
+  const int fx = g.N[0] * smooth + 1, fy = g.N[1] * smooth + 1, fz = g.N[2] * smooth + 1; const i64 nf = (i64)fx * fy * fz, fpl = (i64)fx * fy;
+  const int kf0 = smooth * k0, kf1 = (k1 < nz) ? smooth * k1 : fz;       // fine planes of this slab
   // the stencil form needs the reference's cut to sit strictly between lattice shells (true for the default 1e-3)
   StencilW W; { double L = -log(rbf_cut); if (!(L > 6.0 && L < 8.0)) FAIL("rbf: only kernel cut-offs with 6 < ln(1/cut) < 8 (81-point stencil) are supported"); for (int m = 0; m < 8; m++) W.w[m] = (float)exp(-(double)m); }
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(ctx->f_s.reserve(sizeof(float) * (size_t)n)); CK(ctx->f_lsf.reserve(sizeof(float) * (size_t)n));
   CK(ctx->f_fine.reserve(sizeof(float) * (size_t)nf));
-  CK(ctx->f_scal.reserve(256));
+  CK(ctx->f_scal.reserve(512));
   CK(ctx->cutlist.reserve(sizeof(int) * 4096));
   float *scal = ctx->f_scal.as<float>(); unsigned *ubits = (unsigned *)((char *)ctx->f_scal.p + 64); double *dsc = (double *)((char *)ctx->f_scal.p + 96);
   CK(cudaMemsetAsync(ctx->f_scal.p, 0, 256, st));
   float *s = ctx->f_s.as<float>();
-  k_to_f32<<<cdiv(n, 256), 256, 0, st>>>(n, 0, ctx->sdf.as<double>(), s, ubits); LAUNCH_CHECK();
+  k_to_f32<<<cdiv(nown, 256), 256, 0, st>>>(nown, o_lo, ctx->sdf.as<double>(), s + o_lo, ubits); LAUNCH_CHECK();
+  if (r2s_allreduce(ctx, ubits, 1, 2)) return 1;                          // global max finite |v| (RBFs4Smoothing.jl:17)
   unsigned hb = 0;
   CK(cudaMemcpyAsync(&hb, ubits, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (hb == 0) FAIL("RBFs_smoothing: the SDF holds no finite value (maximum over an empty collection, RBFs4Smoothing.jl:17)");
-  k_replace_far<<<cdiv(n, 256), 256, 0, st>>>(n, s, ubits); LAUNCH_CHECK();
+  k_replace_far<<<cdiv(nown, 256), 256, 0, st>>>(nown, s + o_lo, ubits); LAUNCH_CHECK();
+  if (r2s_halo_exchange_f32(ctx, s, pl, k0, k1, nz, 2, 3)) return 1;
   CK(cudaEventRecord(ctx->ev[5], st));
-  dim3 sgrid(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(nz, ST_Z)); int sthreads = ST_X * ST_Y * (ST_Z / ST_ZB);
-  int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = cdiv(n, 256);
+  dim3 sgrid(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)); int sthreads = ST_X * ST_Y * (ST_Z / ST_ZB);
+  int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = cdiv(next, 256);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
-  const float *wgt = s; int iters = 0;
+  float *wgt = s; int iters = 0;
   if (is_interp) {
     // cg(K, s) with IterativeSolvers defaults (:199): x0 = 0, reltol = sqrt(eps(Float32)), maxiter = n
     CK(ctx->f_w.reserve(sizeof(float) * (size_t)n)); CK(ctx->f_r.reserve(sizeof(float) * (size_t)n));
     CK(ctx->f_u.reserve(sizeof(float) * 2 * (size_t)n)); CK(ctx->f_c.reserve(sizeof(float) * (size_t)n));
     float *x = ctx->f_w.as<float>(), *r = ctx->f_r.as<float>(), *u = ctx->f_u.as<float>(), *c = ctx->f_c.as<float>();
-    CK(cudaMemsetAsync(x, 0, sizeof(float) * (size_t)n, st));
-    CK(cudaMemsetAsync(u, 0, sizeof(float) * 2 * (size_t)n, st));
-    CK(cudaMemcpyAsync(r, s, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-    k_dot_self<<<nub, 256, 0, st>>>(n, r, part); LAUNCH_CHECK();
-    k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(x + x_lo, 0, sizeof(float) * (size_t)next, st));
+    CK(cudaMemsetAsync(u + x_lo, 0, sizeof(float) * (size_t)next, st));
+    CK(cudaMemsetAsync(u + n + x_lo, 0, sizeof(float) * (size_t)next, st));
+    CK(cudaMemcpyAsync(r + x_lo, s + x_lo, sizeof(float) * (size_t)next, cudaMemcpyDeviceToDevice, st));
+    int nob = cdiv(nown, 256);
+    k_dot_self<<<nob, 256, 0, st>>>(nown, r + o_lo, part); LAUNCH_CHECK();
+    k_sum_to<<<1, 256, 0, st>>>(part, nob, dsc); LAUNCH_CHECK();
+    if (r2s_allreduce(ctx, dsc, 1, 0)) return 1;
     k_cg_init<<<1, 1, 0, st>>>(scal, dsc); LAUNCH_CHECK();
     float hs[8];
     CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float residual = hs[2], tol = hs[4];
     float *u_old = u, *u_new = u + n;      // ping-pong halves of the u buffer
+    const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
     while (iters < n && !(residual <= tol)) {
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, nullptr, r, u_old, u_new, scal, c, part, W); LAUNCH_CHECK();
+      k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W); LAUNCH_CHECK();
+      if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
+      if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
+      if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
       k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
-      k_cg_update<<<nub, 256, 0, st>>>(n, scal, u_new, c, x, r, part); LAUNCH_CHECK();
+      k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part); LAUNCH_CHECK();
       k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
+      if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
       k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
       CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -607,16 +643,20 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       { float *t = u_old; u_old = u_new; u_new = t; }
     }
     wgt = x;
+    if (r2s_halo_exchange_f32(ctx, x, pl, k0, k1, nz, 2, 3)) return 1;      // the fine evaluation reaches 3 planes up
   }
   ctx->rep.cg_iters = iters;
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W); LAUNCH_CHECK();
+  k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W); LAUNCH_CHECK();
+  if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
   // LS_Threshold (:265-300)
   unsigned init_mm[2] = {0xffffffffu, 0u};
   CK(cudaMemcpyAsync(ubits + 2, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
-  k_minmax<<<cdiv(n, 256), 256, 0, st>>>(n, lsf, ubits + 2); LAUNCH_CHECK();
+  k_minmax<<<cdiv(nown, 256), 256, 0, st>>>(nown, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
+  if (r2s_allreduce(ctx, ubits + 2, 1, 3)) return 1;
+  if (r2s_allreduce(ctx, ubits + 3, 1, 2)) return 1;
   unsigned hmm[2];
   CK(cudaMemcpyAsync(hmm, ubits + 2, sizeof(hmm), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -632,7 +672,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   }
   double eps = 1.0; int nb = 0; float th = 0.0f; double v = 0.0; bool have_prev = false; float th_prev = 0.0f;
   VolBisect vb;
-  if (vol_bisect_begin(ctx, vb, lsf, nx, ny, nz, 0, nz - 1, edge)) return 1;
+  if (vol_bisect_begin(ctx, vb, lsf, nx, ny, nz, k0, std::min(k1, nz - 1), edge)) return 1;
   while (nb < 40 && eps > 1.0e-4) {
     th = (lo + hi) / 2;
     // once lo and hi are adjacent floats the midpoint repeats: the volume of an identical threshold is not recomputed
@@ -646,23 +686,26 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   ctx->rep.bisections = nb;
   float tho = -th;
   CK(cudaEventRecord(ctx->ev[13], st));
-  // fine grid (:363-366)
+  // fine grid (:363-366): the fine planes of my coarse planes
   if (upload_taps(ctx, smooth, rbf_cut, g.cell)) return 1;
-  dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(fz, FN_Z));
-  if (smooth == 1) k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, fz, wgt, tho, ctx->f_fine.as<float>());
-  else {
-    dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(nz, F2_Z));
-    k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, 0, nz, wgt, tho, ctx->f_fine.as<float>());
+  if (smooth == 1) {
+    dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(kf1 - kf0, FN_Z));
+    k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, kf1, kf0, wgt, tho, ctx->f_fine.as<float>());
+  } else {
+    dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(k1 - k0, F2_Z));
+    k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, k0, k1, wgt, tho, ctx->f_fine.as<float>());
   }
   LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[14], st));
   float volf = 0.0f;
-  if (final_volume) {
+  if (final_volume) {      // calculate_volume_from_sdf on the fine grid (:373), iso = 0
     float a = (float)g.amin[0], b = (float)g.amax[0];
     float dxf = (b - a) / (float)(fx - 1); float x0 = a, x1 = a + 1.0f * dxf; float e = sqrtf((x1 - x0) * (x1 - x0));
-    double v;
-    if (volume_dev(ctx, ctx->f_fine.as<float>(), fx, fy, fz, 0.0f, e, 0.0f, &v)) return 1;
-    volf = (float)v;
+    if (r2s_halo_exchange_f32(ctx, ctx->f_fine.as<float>(), fpl, kf0, kf1, fz, 0, 1)) return 1;
+    VolBisect vf; double vv;
+    if (vol_bisect_begin(ctx, vf, ctx->f_fine.as<float>(), fx, fy, fz, kf0, std::min(kf1, fz - 1), e)) return 1;
+    if (vol_bisect_step(ctx, vf, 0.0f, 0.0f, 0.0f, &vv)) return 1;
+    volf = (float)vv;
   }
   CK(cudaEventRecord(ctx->ev[15], st));
   CK(cudaStreamSynchronize(st));
