@@ -9,6 +9,7 @@
 //                 the reference's running-min logic exactly (boundary-face triangles with their state-dependent
 //                 early-outs, then the element's iso distance from the pair buffer).  Bit-exact decisions (r2s_exact.cuh).
 //                 No atomics: every voxel is owned by one thread, the result is deterministic.
+#include <stdlib.h>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
 #include "r2s_exact.cuh"
@@ -126,6 +127,100 @@ __global__ void __launch_bounds__(128) k_project_hex8(i64 nitems, i64 nact, cons
   for (int o = 16; o > 0; o >>= 1) its += __shfl_down_sync(0xffffffffu, its, o);
   unsigned bad = __ballot_sync(0xffffffffu, !okc);
   if (lane == 0) { atomicAdd(&counters[2], (u64)its); if (bad) atomicAdd(&counters[3], (u64)__popc(bad)); }
+}
+// Lane-refill variant (used when the closest points xp are not requested): ONE WARP PER CROSSING ELEMENT.  The warp keeps
+// the element's monomial coefficients in registers and its lanes work through the element's candidate points independently:
+// a lane that finishes its point immediately takes the next one, so the lanes of a warp sit at different iterations of
+// different points and nobody waits for the slowest projection of a 32-point chunk.  Points inside the element's AABB are
+// taken first; for the others the distance to the AABB is a lower bound of the result, and a pair whose bound already
+// exceeds the voxel's current minimum cannot lower it and is skipped (exact: the result of evalDistances is the minimum over
+// the pairs).  The running minimum per voxel is a 64-bit atomicMin on the bit pattern of the non-negative double.  Voxels of
+// tiles that hold boundary-face elements keep the pair-buffer path (their replay is order dependent, see k_assemble).
+__global__ void k_fill_f64(i64 n, double *__restrict__ a, double v) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
+                                                          const double *__restrict__ rn, GridDev g, double rho_t, const unsigned char *__restrict__ tile_faces,
+                                                          double *__restrict__ pairbuf, double *__restrict__ dist, u64 *__restrict__ counters) {
+  const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+  if (a >= nact) return;
+  const ActRec r = rec[a];
+  if (r.cls != 2) return;
+  double v[4] = {0, 0, 0, 0};
+  if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
+  double A[4][8], re[8], lo[3], hi[3];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    double nv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nv[k] = __shfl_sync(0xffffffffu, v[c], k);
+    iso::monomial8(nv, A[c]);
+    if (c == 3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) re[k] = nv[k];
+    } else {
+      double l = nv[0], h = nv[0];
+#pragma unroll
+      for (int k = 1; k < 8; k++) { l = fmin(l, nv[k]); h = fmax(h, nv[k]); }
+      lo[c] = l; hi[c] = h;
+    }
+  }
+  double gs = fabs(rho_t);
+#pragma unroll
+  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
+  gs = fmax(gs, 1.0);
+  const double margin0 = 1e-12 * fmax(fmax(fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1]))), fmax(fabs(lo[2]), fabs(hi[2])));
+  const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
+  const int vol = nx * ny * nz;
+  bool busy = false, to_buf = false; iso::ProjState S; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
+  int sweep = 0, next = 0, its = 0, nbad = 0, npruned = 0;
+  while (true) {
+    // ---- refill idle lanes with the next candidate points of the current sweep
+    while (sweep < 2) {
+      const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+      if (!idle) break;
+      const int cand = next + __popc(idle & ((1u << lane) - 1));
+      if (!busy && cand < vol) {
+        const int i = cand % nx, j = (cand / nx) % ny, k = cand / (nx * ny);
+        const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
+        x[0] = g.pc[g.pc_off[0] + pi0]; x[1] = g.pc[g.pc_off[1] + pi1]; x[2] = g.pc[g.pc_off[2] + pi2];
+        const double d0 = fmax(fmax(lo[0] - x[0], x[0] - hi[0]), 0.0), d1 = fmax(fmax(lo[1] - x[1], x[1] - hi[1]), 0.0), d2 = fmax(fmax(lo[2] - x[2], x[2] - hi[2]), 0.0);
+        const double lb = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+        if ((sweep == 0) == (lb == 0.0)) {
+          vox = ((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0;
+          const i64 t = ((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X;
+          to_buf = tile_faces[t] != 0;
+          bool prune = false;
+          if (!to_buf && sweep == 1) { const double cur = dist[vox]; prune = lb - (margin0 + 1e-12 * lb) > cur; }
+          if (prune) npruned++;
+          else {
+            li = cand; busy = true;
+            if (!iso::proj_init(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) S.it = 1000;      // no iso point found: finalised below with xi = 0
+          }
+        }
+      }
+      next += __popc(idle);
+      if (next >= vol) { sweep++; next = 0; }
+    }
+    if (!__any_sync(0xffffffffu, busy)) break;
+    if (busy) {
+      int status = 2;
+      if (S.it < 100) status = iso::proj_iter(A, x, rho_t, gs, S);
+      if (status != 0 || S.it >= 100) {
+        if (S.it >= 1000) nbad++; else { its += S.it; if (status != 1) nbad++; }
+        double p[3]; iso::eval_pos(A, S.xi, p);
+        const double e0 = x[0] - p[0], e1 = x[1] - p[1], e2 = x[2] - p[2];
+        const double dd = sqrt(fma(e2, e2, fma(e1, e1, e0 * e0)));
+        if (to_buf) pairbuf[r.pair_off + li] = dd;
+        else atomicMin((u64 *)&dist[vox], (u64)__double_as_longlong(dd));
+        busy = false;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { its += __shfl_down_sync(0xffffffffu, its, o); nbad += __shfl_down_sync(0xffffffffu, nbad, o); npruned += __shfl_down_sync(0xffffffffu, npruned, o); }
+  if (lane == 0) { atomicAdd(&counters[2], (u64)its); if (nbad) atomicAdd(&counters[3], (u64)nbad); if (npruned) atomicAdd(&counters[4], (u64)npruned); }
 }
 template <bool WANT_XP>
 __global__ void __launch_bounds__(128) k_project_tet4(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
@@ -432,7 +527,21 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     CK(cudaMemcpyAsync(ctx->tile_ptr.as<int>(), tmp.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (nitems > 0) {
+  // HEX8 without xp: lane-refill projection with per-voxel atomicMin (face-free tiles) + exact replay of the tiles with boundary faces
+  const bool minpath = (nen == 8 && !want_xp);
+  if (minpath) {
+    i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
+    k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
+    if (nact > 0 && npairs > 0) {
+      // occupancy variant (registers per thread 255 / 168 / 128): R2S_PROJ_MINB = 2, 3, 4 (tuning knob, default from measurements)
+      static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
+#define PMIN(MB) k_project_hex8_min<MB><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
+                                                              ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>())
+      if (minb <= 2) PMIN(2); else if (minb == 3) PMIN(3); else PMIN(4);
+#undef PMIN
+      LAUNCH_CHECK();
+    }
+  } else if (nitems > 0) {
     i64 *choff = ctx->cnt_b.as<i64>() + 2 * (nact + 1);
     int nb = cdiv(nitems * 32, 128);
 #define PROJ(KERN, XP) KERN<XP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
@@ -447,7 +556,8 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
         ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
         ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
-    if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
+    if (minpath) { ASM(false, 8, true); }
+    else if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
     else { if (want_xp) { ASM(true, 4, false); ASM(true, 4, true); } else { ASM(false, 4, false); ASM(false, 4, true); } }
 #undef ASM
   }

@@ -152,14 +152,18 @@ __device__ __forceinline__ void tangent_step(const Eval &E, const int fix[3], do
   else { if (fabs(E.a[2]) > 0.0) tangent3<2>(E, lam, d); }
 }
 
-// HEX8 projection.  A: monomial coefficients [x,y,z,rho][8]; re: nodal densities (for the edge fallback).
-// Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
-__device__ __forceinline__ bool project_hex8(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
-                                             const double x[3], double rho_t, double gs, double xi[3], int &nit) {
-  const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
+// HEX8 projection as a resumable state machine: proj_init (phase 1) + proj_iter (ONE phase-2 iteration).  A: monomial
+// coefficients [x,y,z,rho][8]; re: nodal densities (for the edge fallback).  project_hex8 below is init + iterate-to-the-end;
+// the lane-refill kernel drives the two pieces itself so that the lanes of a warp can be at different iterations of
+// different grid points.  The arithmetic and its order are the same in both drivers (bit-identical results).
+struct ProjState { double xi[3]; double lam; int it, stall; bool force; };
+
+__device__ __forceinline__ bool proj_init(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
+                                          const double x[3], double rho_t, double gs, ProjState &S) {
+  const double tolg = 1e-14 * gs;
   int fix[3] = {0, 0, 0};
-  xi[0] = xi[1] = xi[2] = 0.0;
-  bool ok = restore(A, rho_t, xi, fix, tolg);
+  S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.it = 0; S.stall = 0; S.force = false;
+  bool ok = restore(A, rho_t, S.xi, fix, tolg);
   if (!ok) {
     double best = INFINITY;
     for (int e = 0; e < 12; e++) {
@@ -169,18 +173,24 @@ __device__ __forceinline__ bool project_hex8(const double A[4][8], const double 
 #pragma unroll
         for (int d = 0; d < 3; d++) cand[d] = sg[a][d] + t * (sg[b][d] - sg[a][d]);
         double dd = eval_f(A, x, cand);
-        if (dd < best) { best = dd; xi[0] = cand[0]; xi[1] = cand[1]; xi[2] = cand[2]; }
+        if (dd < best) { best = dd; S.xi[0] = cand[0]; S.xi[1] = cand[1]; S.xi[2] = cand[2]; }
       }
     }
-    if (!(best < INFINITY)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+    if (!(best < INFINITY)) { S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.it = -1; return false; }
   }
-  double lam = 0.0, dm = 0.0; int it, status = 0, stall = 0; bool force = false;
-  for (it = 0; it < 100 && status == 0; it++) {
+  return true;
+}
+// one phase-2 iteration; returns 0 = continue, 1 = converged, 2 = failed (line search exhausted)
+__device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3], double rho_t, double gs, ProjState &S) {
+  const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
+  double *xi = S.xi; double lam = S.lam, dm = 0.0; bool force = S.force;
+  int fix[3];
+  {
     int bnd[3], tried[3] = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 3; i++) { bnd[i] = xi[i] >= 1.0 ? 1 : (xi[i] <= -1.0 ? -1 : 0); fix[i] = bnd[i]; }
     Eval E; eval_full(A, x, rho_t, xi, E);
-    double d[3] = {0, 0, 0}; bool have_step = false;
+    double d[3] = {0, 0, 0}; bool have_step = false; int status = 0;
     for (int pass = 0; pass < 8; pass++) {
       double num = 0, den = 0;
 #pragma unroll
@@ -219,8 +229,9 @@ __device__ __forceinline__ bool project_hex8(const double A[4][8], const double 
       for (int i = 0; i < 3; i++) if (i == worst) { fix[i] = 0; tried[i] = 1; }
       force = false;
     }
-    if (status) break;
-    if (!have_step) { status = 1; break; }
+    S.lam = lam; S.force = force;
+    if (status) return 1;
+    if (!have_step) return 1;
     double amax = 1.0; int blk = -1;
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) {
@@ -228,7 +239,7 @@ __device__ __forceinline__ bool project_hex8(const double A[4][8], const double 
       if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
     }
     double slope = fma(E.c[2], d[2], fma(E.c[1], d[1], E.c[0] * d[0]));
-    if (!(slope < 0.0)) { force = true; continue; }      // no descent left on this face: go to the multiplier test
+    if (!(slope < 0.0)) { S.force = true; S.it++; return 0; }      // no descent left on this face: go to the multiplier test
     double alpha = amax; bool acc = false;
     for (int ls = 0; ls < 40; ls++) {
       double xt[3]; int fx[3];
@@ -243,16 +254,27 @@ __device__ __forceinline__ bool project_hex8(const double A[4][8], const double 
         double ft = eval_f(A, x, xt);
         // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
         if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
-          if (E.f - ft <= 1e-15 * E.f) stall++; else stall = 0;
+          if (E.f - ft <= 1e-15 * E.f) S.stall++; else S.stall = 0;
           xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true; break;
         }
       }
       alpha *= 0.5;
     }
-    if (!acc) { if (dm < 1e-6) { force = true; continue; } status = 2; break; }
-    if (stall >= 3) { force = true; stall = 0; }
+    if (!acc) { if (dm < 1e-6) { S.force = true; S.it++; return 0; } return 2; }
+    if (S.stall >= 3) { S.force = true; S.stall = 0; }
   }
-  nit = it;
+  S.it++;
+  return 0;
+}
+// Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
+__device__ __forceinline__ bool project_hex8(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
+                                             const double x[3], double rho_t, double gs, double xi[3], int &nit) {
+  ProjState S;
+  if (!proj_init(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  int status = 0;
+  while (S.it < 100 && status == 0) status = proj_iter(A, x, rho_t, gs, S);
+  xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
+  nit = S.it;
   return status == 1;
 }
 
