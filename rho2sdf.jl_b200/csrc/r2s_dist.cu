@@ -388,6 +388,45 @@ __device__ inline void boundary_faces_point(const ActRec &r, const TriRec *__res
   }
 }
 
+// Boundary faces of CROSSING elements (process_boundary_faces!(..., false), :584).  For a crossing element every candidate of
+// process_triangle_projection! is accepted or rejected by the rho-test alone (IsProjectedOnFullSegment, :78-119) -- never by
+// the running minimum -- and accepted candidates only ever lower the minimum.  So the element's face contribution to a grid
+// point is ONE number, min over its boundary triangles, independent of the order of anything else, and it can be folded into
+// the element's entry of the pair buffer: pair = min(iso distance, face candidates).  One warp per crossing element with
+// boundary faces, lanes over the element's candidate points; the order-dependent replay (k_assemble) is then left with the
+// faces of SOLID elements only, which need no inverse map.
+template <int NEN>
+__global__ void __launch_bounds__(128) k_faces_crossing(i64 nact, const ActRec *__restrict__ rec, const TriRec *__restrict__ tri, const int *__restrict__ IEN,
+                                                        const double *__restrict__ X, const double *__restrict__ rn, GridDev g, double rho_t, double *__restrict__ pairbuf) {
+  constexpr int NSN = NEN == 8 ? 4 : 3;
+  const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+  if (a >= nact) return;
+  const ActRec r = rec[a];
+  if (r.cls != 2 || !r.fmask) return;
+  double Xe[3][NEN], re[NEN];
+  for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; re[q] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
+  const int ntri = __popc((unsigned)r.fmask) * NSN;
+  const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2], vol = nx * ny * nz;
+  for (int li = lane; li < vol; li += 32) {
+    const int pi[3] = {r.ps[0] + li % nx, r.ps[1] + (li / nx) % ny, r.ps[2] + li / (nx * ny)};
+    const double x[3] = {g.pc[g.pc_off[0] + pi[0]], g.pc[g.pc_off[1] + pi[1]], g.pc[g.pc_off[2] + pi[2]]};
+    VoxState s; s.c = -R2S_BIG; s.xp[0] = s.xp[1] = s.xp[2] = 0.0;
+    for (int t = 0; t < ntri; t++) {
+      const TriRec &T = tri[r.tri_off + t];
+      if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
+      double Xt[3][3], Et[3][3], n[3];
+      for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; n[d] = T.n[d]; }
+      for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+      triangle_point<false, NEN>(Xe, re, rho_t, false, Xt, Et, n, x, s);
+    }
+    if (s.c != -R2S_BIG) {
+      const i64 idx = r.pair_off + li;
+      const double cur = pairbuf[idx];
+      if (!(cur >= 0.0 && cur <= s.c)) pairbuf[idx] = s.c;
+    }
+  }
+}
+
 // One CTA per tile, one thread per grid point; the tile's element list is culled per warp (footprint 8x4x1 points) into
 // shared memory in list order, then every lane replays ITS candidates in ascending element order.
 #define ACULL_CAP 96
@@ -428,7 +467,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       for (int q = 0; q < n; q++) {
         const ActRec &r = srec[warp][q];
         if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
-        if (FACES && r.fmask) boundary_faces_point<WANT_XP, NEN>(r, tri, IEN, X, rn, rho_t, pi, x, s);
+        if (FACES && r.fmask && (WANT_XP || r.cls == 1)) boundary_faces_point<WANT_XP, NEN>(r, tri, IEN, X, rn, rho_t, pi, x, s);     // crossing faces are folded into the pair buffer unless xp is wanted
         if (r.cls == 2) {
           i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
           double dt = pairbuf[idx];
@@ -528,7 +567,8 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   }
   CK(cudaEventRecord(ctx->ev[1], st));
   // HEX8 without xp: lane-refill projection with per-voxel atomicMin (face-free tiles) + exact replay of the tiles with boundary faces
-  const bool minpath = (nen == 8 && !want_xp);
+  static const bool refill = getenv("R2S_PROJ") && atoi(getenv("R2S_PROJ")) == 1;       // experimental lane-refill projection (not faster yet)
+  const bool minpath = (refill && nen == 8 && !want_xp);
   if (minpath) {
     i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
@@ -550,6 +590,11 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
     LAUNCH_CHECK();
 #undef PROJ
+  }
+  if (!want_xp && nact > 0 && npairs > 0) {
+    if (nen == 8) k_faces_crossing<8><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
+    else k_faces_crossing<4><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
+    LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   {

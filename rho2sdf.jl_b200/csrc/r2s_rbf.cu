@@ -8,6 +8,7 @@
 //   * a two-pass cut-cell quadrature for the volume-matching bisection (LS_Threshold, :265-300).
 // Sums are deterministic: block partials in fixed slots (double) or 64-bit fixed-point integer atomics.
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
@@ -100,6 +101,93 @@ __global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx
   __syncthreads();
   if (tid == 0) {
     double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i];
+    partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
+  }
+}
+// ---- plane-marching variant (2.5-D blocking) ----------------------------------------------------------------------
+// A CTA owns a 32 x 8 column of the grid and marches along z over S2_ZC output planes.  Each input plane (with its x-y halo)
+// is staged once in shared memory; a thread reads its 21 (di, dj) neighbours and scatters them into the five outputs the plane
+// contributes to (dk = -2..2), held in a rotating register queue.  Per output: 21 shared-memory loads and 81 FMAs (the
+// tile-per-CTA kernel above needs 42 loads plus a div/mod tile fill), which makes the mat-vec HBM-bound instead of issue-bound.
+// Same operation as k_stencil81; the per-output summation order differs (dk-major per plane), results agree to Float32 round-off.
+#define S2_X 32
+#define S2_Y 8
+#define S2_ZC 64
+template <bool BETA>
+__global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
+                                                                const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
+                                                                float *__restrict__ out, double *__restrict__ partial, StencilW W) {
+  __shared__ float sm[2][S2_Y + 4][S2_X + 4];
+  __shared__ double red[S2_X * S2_Y / 32];
+  const int tid = threadIdx.x, lx = tid % S2_X, ly = tid / S2_X;
+  const int bx = blockIdx.x * S2_X, by = blockIdx.y * S2_Y;
+  const int zc0 = kz0 + blockIdx.z * S2_ZC, zc1 = min(zc0 + S2_ZC, kz1);       // output planes of this CTA
+  const int gx = bx + lx, gy = by + ly;
+  const bool inside = gx < nx && gy < ny;
+  float beta = 0.0f;
+  if (BETA) beta = scal[0];
+  // the (up to) two tile elements this thread stages per plane
+  constexpr int TX = S2_X + 4, TY = S2_Y + 4, NT = TX * TY;
+  int e_lx[2], e_ly[2]; bool e_ok[2], e_own[2]; i64 e_off[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    int t = tid + q * S2_X * S2_Y;
+    e_ly[q] = t / TX; e_lx[q] = t % TX;
+    int x = bx + e_lx[q] - 2, y = by + e_ly[q] - 2;
+    e_ok[q] = t < NT && x >= 0 && x < nx && y >= 0 && y < ny;
+    e_own[q] = e_ok[q] && e_lx[q] >= 2 && e_lx[q] < TX - 2 && e_ly[q] >= 2 && e_ly[q] < TY - 2;      // interior of the tile: this CTA writes u_new there
+    e_off[q] = (i64)y * nx + x;
+    if (t >= NT) { e_ly[q] = 0; e_lx[q] = 0; }
+  }
+  const i64 pl = (i64)nx * ny;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;       // outputs zin-2 .. zin+2
+  float c0 = 0.f, c1 = 0.f;                                        // centre values of planes zin-2, zin-1
+  double dsum = 0.0;
+  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
+    const int buf = (zin - zc0 + 2) & 1;
+    // stage plane zin (zeros outside the grid: K has no entries there)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (tid + q * S2_X * S2_Y < NT) {
+        float v = 0.0f;
+        if (e_ok[q] && zin >= 0 && zin < nz) {
+          i64 gi = (i64)zin * pl + e_off[q];
+          if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && zin >= zc0 && zin < zc1) unew[gi] = v; }
+          else v = in[gi];
+        }
+        sm[buf][e_ly[q]][e_lx[q]] = v;
+      }
+    }
+    __syncthreads();
+    float ctr = 0.f;
+#pragma unroll
+    for (int dj = -2; dj <= 2; dj++)
+#pragma unroll
+      for (int di = -2; di <= 2; di++) {
+        const int m2 = di * di + dj * dj;
+        if (m2 > 6) continue;
+        const float v = sm[buf][ly + 2 + dj][lx + 2 + di];
+        if (di == 0 && dj == 0) ctr = v;
+        a2 = fmaf(W.w[m2], v, a2);
+        if (m2 + 1 <= 6) { a1 = fmaf(W.w[m2 + 1], v, a1); a3 = fmaf(W.w[m2 + 1], v, a3); }
+        if (m2 + 4 <= 6) { a0 = fmaf(W.w[m2 + 4], v, a0); a4 = fmaf(W.w[m2 + 4], v, a4); }
+      }
+    // output plane zin - 2 is complete
+    const int zo = zin - 2;
+    if (zo >= zc0 && inside) {
+      i64 gi = (i64)zo * pl + (i64)gy * nx + gx;
+      out[gi] = a0;
+      dsum += (double)c0 * (double)a0;
+    }
+    a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f;
+    c0 = c1; c1 = ctr;
+    // the other buffer is overwritten next iteration: everybody must be done reading it (it was read one iteration ago) -> one barrier per plane suffices
+  }
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+  if ((tid & 31) == 0) red[tid >> 5] = dsum;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0; for (int i = 0; i < S2_X * S2_Y / 32; i++) a += red[i];
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
 }
@@ -600,7 +688,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   k_replace_far<<<cdiv(nown, 256), 256, 0, st>>>(nown, s + o_lo, ubits); LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, s, pl, k0, k1, nz, 2, 3)) return 1;
   CK(cudaEventRecord(ctx->ev[5], st));
-  dim3 sgrid(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)); int sthreads = ST_X * ST_Y * (ST_Z / ST_ZB);
+  // mat-vec kernel: plane-marching (default) or tile-per-CTA (R2S_STENCIL=0, kept for comparison)
+  static const bool march = !(getenv("R2S_STENCIL") && atoi(getenv("R2S_STENCIL")) == 0);
+  dim3 sgrid = march ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z));
+  int sthreads = march ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB);
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = cdiv(next, 256);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
@@ -627,7 +718,9 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
     while (iters < n && !(residual <= tol)) {
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W); LAUNCH_CHECK();
+      if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      else k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
       if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
@@ -649,7 +742,9 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W); LAUNCH_CHECK();
+  if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  else k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
   // LS_Threshold (:265-300)
   unsigned init_mm[2] = {0xffffffffu, 0u};

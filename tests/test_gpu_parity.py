@@ -40,6 +40,9 @@ def check_distances(r2s, mesh, X, IEN, grid, rn, rt, delta):
     P = r2s.generateGridPoints(grid)
     near = ~far
     assert np.max(np.abs(np.linalg.norm(P[near] - xp[near], axis=1) - d[near])) <= 1e-9 * grid.cell_size
+    # the pipeline's path (no xp: crossing-element faces folded into the pair buffer) must give the very same distances
+    d2, _ = r2s.evalDistances(mesh, grid, None, rn, rt, delta_factor=delta, want_xp=False)
+    assert np.array_equal(d, d2)
     return d, od
 
 
