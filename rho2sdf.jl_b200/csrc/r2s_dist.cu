@@ -79,8 +79,8 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
 
 // ------------------------------------------------------------------------------------------------ project (hot, FP64)
 // one warp per 32-point chunk of a crossing element
-template <bool WANT_XP>
-__global__ void __launch_bounds__(128) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
+template <bool WANT_XP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
                                                       double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters) {
   i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
@@ -574,10 +574,10 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
     if (nact > 0 && npairs > 0) {
       // occupancy variant (registers per thread 255 / 168 / 128): R2S_PROJ_MINB = 2, 3, 4 (tuning knob, default from measurements)
-      static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
+      static const int minbr = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
 #define PMIN(MB) k_project_hex8_min<MB><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
                                                               ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>())
-      if (minb <= 2) PMIN(2); else if (minb == 3) PMIN(3); else PMIN(4);
+      if (minbr <= 2) PMIN(2); else if (minbr == 3) PMIN(3); else PMIN(4);
 #undef PMIN
       LAUNCH_CHECK();
     }
@@ -586,9 +586,16 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     int nb = cdiv(nitems * 32, 128);
 #define PROJ(KERN, XP) KERN<XP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
                                                    ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
-    if (nen == 8) { if (want_xp) PROJ(k_project_hex8, true); else PROJ(k_project_hex8, false); }
-    else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
+    // occupancy variant of the HEX8 kernel (255 / 168 / 128 registers per thread): R2S_PROJ_MINB = 2, 3, 4
+    static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 2;
+#define PROJH(XP, MB) k_project_hex8<XP, MB><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
+                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
+    if (nen == 8) {
+      if (want_xp) PROJH(true, 2);
+      else if (minb <= 2) PROJH(false, 2); else if (minb == 3) PROJH(false, 3); else PROJH(false, 4);
+    } else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
     LAUNCH_CHECK();
+#undef PROJH
 #undef PROJ
   }
   if (!want_xp && nact > 0 && npairs > 0) {

@@ -143,22 +143,28 @@ __global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, 
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;       // outputs zin-2 .. zin+2
   float c0 = 0.f, c1 = 0.f;                                        // centre values of planes zin-2, zin-1
   double dsum = 0.0;
-  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
-    const int buf = (zin - zc0 + 2) & 1;
-    // stage plane zin (zeros outside the grid: K has no entries there)
+  // software pipeline: the global loads of plane zin + 1 are issued before the FMAs of plane zin
+  float pv[2];
+  auto fetch = [&](int z) {
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      if (tid + q * S2_X * S2_Y < NT) {
-        float v = 0.0f;
-        if (e_ok[q] && zin >= 0 && zin < nz) {
-          i64 gi = (i64)zin * pl + e_off[q];
-          if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && zin >= zc0 && zin < zc1) unew[gi] = v; }
-          else v = in[gi];
-        }
-        sm[buf][e_ly[q]][e_lx[q]] = v;
+      float v = 0.0f;
+      if (e_ok[q] && z >= 0 && z < nz) {
+        i64 gi = (i64)z * pl + e_off[q];
+        if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && z >= zc0 && z < zc1) unew[gi] = v; }
+        else v = in[gi];
       }
+      pv[q] = v;      // zeros outside the grid: K has no entries there
     }
+  };
+  fetch(zc0 - 2);
+  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
+    const int buf = (zin - zc0 + 2) & 1;
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+      if (tid + q * S2_X * S2_Y < NT) sm[buf][e_ly[q]][e_lx[q]] = pv[q];
     __syncthreads();
+    if (zin + 1 < zc1 + 2) fetch(zin + 1);
     float ctr = 0.f;
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++)
