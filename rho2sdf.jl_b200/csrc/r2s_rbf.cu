@@ -207,13 +207,17 @@ __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restr
 __global__ void k_cg_alpha(float *scal, const double *uc) {     // alpha = residual^2 / dot(u, c)
   float res = scal[2]; scal[1] = res * res / (float)(*uc);
 }
-// elementwise over [0, n) (owned planes plus halo); the residual norm is summed over the owned part [o_lo, o_hi) only
-__global__ void k_cg_update(i64 n, i64 o_lo, i64 o_hi, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c, float *__restrict__ x,
-                            float *__restrict__ r, double *__restrict__ partial) {
+// elementwise over [0, n) (owned planes plus halo); the residual norm is summed over the owned part [o_lo, o_hi) only.
+// Grid-stride with a fixed grid (CG_BLOCKS CTAs): few, fat CTAs keep the loads in flight and leave only CG_BLOCKS partial sums.
+#define CG_BLOCKS (148 * 8)
+__global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c,
+                                                   float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial) {
   __shared__ double red[8];
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  float alpha = scal[1]; double rr = 0.0;
-  if (v < n) { x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv; if (v >= o_lo && v < o_hi) rr = (double)rv * (double)rv; }
+  const float alpha = scal[1]; double rr = 0.0;
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) {
+    x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv;
+    if (v >= o_lo && v < o_hi) rr += (double)rv * (double)rv;
+  }
   for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
   __syncthreads();
@@ -227,10 +231,10 @@ __global__ void k_cg_init(float *scal, const double *rr) {
   float res = (float)sqrt(*rr);
   scal[2] = res; scal[3] = 1.0f; scal[4] = sqrtf(FLT_EPSILON) * res; scal[0] = res * res / (1.0f * 1.0f); scal[1] = 0.0f;
 }
-__global__ void k_dot_self(i64 n, const float *__restrict__ a, double *__restrict__ partial) {
+__global__ void __launch_bounds__(256) k_dot_self(i64 n, const float *__restrict__ a, double *__restrict__ partial) {
   __shared__ double red[8];
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  double s = 0.0; if (v < n) s = (double)a[v] * (double)a[v];
+  double s = 0.0;
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) s += (double)a[v] * (double)a[v];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -698,7 +702,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   static const bool march = !(getenv("R2S_STENCIL") && atoi(getenv("R2S_STENCIL")) == 0);
   dim3 sgrid = march ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z));
   int sthreads = march ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB);
-  int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = cdiv(next, 256);
+  int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
   float *wgt = s; int iters = 0;
@@ -711,7 +715,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     CK(cudaMemsetAsync(u + x_lo, 0, sizeof(float) * (size_t)next, st));
     CK(cudaMemsetAsync(u + n + x_lo, 0, sizeof(float) * (size_t)next, st));
     CK(cudaMemcpyAsync(r + x_lo, s + x_lo, sizeof(float) * (size_t)next, cudaMemcpyDeviceToDevice, st));
-    int nob = cdiv(nown, 256);
+    int nob = (int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS);
     k_dot_self<<<nob, 256, 0, st>>>(nown, r + o_lo, part); LAUNCH_CHECK();
     k_sum_to<<<1, 256, 0, st>>>(part, nob, dsc); LAUNCH_CHECK();
     if (r2s_allreduce(ctx, dsc, 1, 0)) return 1;
