@@ -25,20 +25,37 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
     if (old == a) return;
   }
 }
-__global__ void k_cc_init(i64 n, i64 v0, const double *__restrict__ sdf, double thr, int *__restrict__ L, int *__restrict__ sz) {
+// Labels start as x-RUN STARTS: an interior voxel points at the first voxel of its contiguous interior run inside the warp's
+// 32 consecutive voxels of the same grid row (ballot + clz), so that whole runs are one tree from the start and the merge
+// kernel only has to link runs: across the warp boundary in x, and to the rows above (y) / planes above (z) once per pair of
+// overlapping runs instead of once per voxel pair.
+__device__ __forceinline__ int run_start_label(i64 v, int nx, bool interior) {
+  const int lane = threadIdx.x & 31;
+  const i64 row = v / nx;
+  const unsigned same = __match_any_sync(0xffffffffu, row);
+  const unsigned ones = __ballot_sync(0xffffffffu, interior) & same;
+  const unsigned z = ~ones & ((1u << lane) - 1u);
+  const int start = z ? 32 - __clz(z) : 0;
+  return interior ? (int)(v - (lane - start)) : -1;
+}
+__global__ void k_cc_init(i64 n, i64 v0, int nx, const double *__restrict__ sdf, double thr, int *__restrict__ L, int *__restrict__ sz) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  bool interior = v < n && sdf[v0 + v] >= thr;
+  int lab = run_start_label(v < n ? v : n, nx, interior);      // out-of-range lanes form their own "row"
   if (v >= n) return;
-  L[v] = (sdf[v0 + v] >= thr) ? (int)v : -1;
-  sz[v] = 0;
+  L[v] = lab; sz[v] = 0;
 }
 __global__ void k_cc_merge(int nx, int ny, int nz, int *__restrict__ L) {
-  i64 n = (i64)nx * ny * nz;
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  const i64 n = (i64)nx * ny * nz, pl = (i64)nx * ny;
+  const i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (v >= n || L[v] < 0) return;
-  int i = (int)(v % nx), j = (int)((v / nx) % ny), k = (int)(v / ((i64)nx * ny));
-  if (i + 1 < nx && L[v + 1] >= 0) uf_union(L, (int)v, (int)v + 1);
-  if (j + 1 < ny && L[v + nx] >= 0) uf_union(L, (int)v, (int)(v + nx));
-  if (k + 1 < nz && L[v + (i64)nx * ny] >= 0) uf_union(L, (int)v, (int)(v + (i64)nx * ny));
+  const int i = (int)(v % nx), j = (int)((v / nx) % ny), k = (int)(v / pl);
+  const bool left_in = i > 0 && L[v - 1] >= 0;
+  // x: runs were cut at warp boundaries
+  if (left_in && (threadIdx.x & 31) == 0) uf_union(L, (int)v, (int)v - 1);
+  // y / z: one link per pair of overlapping runs -- at the first overlapping x either this voxel or the neighbour starts its run
+  if (j + 1 < ny && L[v + nx] >= 0 && (!left_in || !(L[v + nx - 1] >= 0))) uf_union(L, (int)v, (int)(v + nx));
+  if (k + 1 < nz && L[v + pl] >= 0 && (!left_in || !(L[v + pl - 1] >= 0))) uf_union(L, (int)v, (int)(v + pl));
 }
 __global__ void k_cc_flatten(i64 n, int *__restrict__ L, int *__restrict__ sz) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -85,14 +102,19 @@ __global__ void k_mask_pack(int nxy, int wpp, int kz0, int kz1, const double *__
   unsigned m = __ballot_sync(0xffffffffu, in);
   if (lane == 0) bits[wid] = m;
 }
-__global__ void k_cc_init_bits(int nxy, int nz, int wpp, i64 stride, SlabMap sm, const unsigned *__restrict__ bits, int *__restrict__ L, int *__restrict__ sz) {
+__global__ void k_cc_init_bits(int nxy, int nx, int nz, int wpp, i64 stride, SlabMap sm, const unsigned *__restrict__ bits, int *__restrict__ L, int *__restrict__ sz) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (v >= (i64)nxy * nz) return;
-  int k = (int)(v / nxy), idx = (int)(v % nxy), r = 0;
-  while (r + 1 < sm.nranks && k >= sm.k0[r + 1]) r++;
-  unsigned word = bits[(i64)r * stride + (i64)(k - sm.k0[r]) * wpp + (idx >> 5)];
-  L[v] = ((word >> (idx & 31)) & 1u) ? (int)v : -1;
-  sz[v] = 0;
+  const i64 n = (i64)nxy * nz;
+  bool interior = false;
+  if (v < n) {
+    int k = (int)(v / nxy), idx = (int)(v % nxy), r = 0;
+    while (r + 1 < sm.nranks && k >= sm.k0[r + 1]) r++;
+    unsigned word = bits[(i64)r * stride + (i64)(k - sm.k0[r]) * wpp + (idx >> 5)];
+    interior = (word >> (idx & 31)) & 1u;
+  }
+  int lab = run_start_label(v < n ? v : n, nx, interior);
+  if (v >= n) return;
+  L[v] = lab; sz[v] = 0;
 }
 static int remove_artifacts_slabs(r2s_ctx *ctx, double thr, double ratio, i64 *flipped) {
   const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
@@ -118,7 +140,7 @@ static int remove_artifacts_slabs(r2s_ctx *ctx, double thr, double ratio, i64 *f
   k_mask_pack<<<cdiv((i64)wpp * (kz1 - kz0) * 32, 256), 256, 0, st>>>(nxy, wpp, kz0, kz1, sdf, thr, mine); LAUNCH_CHECK();
   if (r2s_allgather_u32(ctx, mine, all, (size_t)stride)) return 1;       // in place: my block already sits at its slot
   int nb = cdiv(n, 256);
-  k_cc_init_bits<<<nb, 256, 0, st>>>(nxy, nz, wpp, stride, sm, all, L, sz); LAUNCH_CHECK();
+  k_cc_init_bits<<<nb, 256, 0, st>>>(nxy, nx, nz, wpp, stride, sm, all, L, sz); LAUNCH_CHECK();
   k_cc_merge<<<nb, 256, 0, st>>>(nx, ny, nz, L); LAUNCH_CHECK();
   k_cc_flatten<<<nb, 256, 0, st>>>(n, L, sz); LAUNCH_CHECK();
   k_cc_largest<<<nb, 256, 0, st>>>(n, L, sz, sc); LAUNCH_CHECK();
@@ -154,7 +176,7 @@ int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flippe
   int *L = ctx->cc_label.as<int>(), *sz = ctx->cc_size.as<int>(); u64 *sc = ctx->cc_scal.as<u64>();
   double *sdf = ctx->sdf.as<double>();
   int nb = cdiv(n, 256);
-  k_cc_init<<<nb, 256, 0, st>>>(n, v0, sdf, thr, L, sz); LAUNCH_CHECK();
+  k_cc_init<<<nb, 256, 0, st>>>(n, v0, nx, sdf, thr, L, sz); LAUNCH_CHECK();
   k_cc_merge<<<nb, 256, 0, st>>>(nx, ny, nz, L); LAUNCH_CHECK();
   k_cc_flatten<<<nb, 256, 0, st>>>(n, L, sz); LAUNCH_CHECK();
   k_cc_largest<<<nb, 256, 0, st>>>(n, L, sz, sc); LAUNCH_CHECK();

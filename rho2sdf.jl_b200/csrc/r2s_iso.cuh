@@ -255,7 +255,12 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
         // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
         if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
           if (E.f - ft <= 1e-15 * E.f) S.stall++; else S.stall = 0;
-          xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true; break;
+          xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true;
+          // A full Newton step of size dm <= 1e-6 that ends strictly inside the box leaves an error of O(dm^2) <= 1e-12: the
+          // next iteration would only confirm |step| <= tolx, so it is skipped (saves one evaluation of ~3.5 per pair; the CPU
+          // oracle keeps the confirming iteration -- the two agree to ~1e-12 in xi, far inside the 1e-9 h tolerance).
+          if (dm <= 1e-6 && alpha == 1.0 && fx[0] == 0 && fx[1] == 0 && fx[2] == 0) { S.it++; return 1; }
+          break;
         }
       }
       alpha *= 0.5;

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, co
   if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += s_warp[w]; if (tot) atomicAdd(&acc[0], (u64)tot); }
 }
 // pass 2: ONE THREAD per cut cell (grid-stride over the list; the count is read from device memory so that no host round
-// trip separates the two passes).  The three Gauss loops are fully unrolled with the abscissae / weights as kernel-parameter
+// trip separates the two passes).  The two inner Gauss loops are fully unrolled with the abscissae / weights as kernel-parameter
 // (constant-bank) operands: 4 lerps per xi, 2 per (xi, eta), then per point one lerp, one compare and one predicated add --
 // about 4 instructions per Gauss point.  Every point value is evaluated with the reference's expression order (xi, then eta,
 // then zeta lerps; CalcVolumeFromSDF.jl:88-103).  The cell's Float32 sum of w_i w_j w_k over inside points (iq outer, kq
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const f
       const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
       const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
       float part = 0.0f;
-#pragma unroll
+#pragma unroll 1      // the 81-point inner body stays unrolled; unrolling all 729 points (60 KB of code) thrashed the instruction cache
       for (int iq = 0; iq < 9; iq++) {
         const float xi = (G.x[iq] + 1) / 2, xm = 1.0f - xi;
         const float c00 = c000 * xm + c100 * xi, c01 = c001 * xm + c101 * xi;
