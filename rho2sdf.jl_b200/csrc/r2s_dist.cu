@@ -174,10 +174,12 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
   const double margin0 = 1e-12 * fmax(fmax(fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1]))), fmax(fabs(lo[2]), fabs(hi[2])));
   const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
   const int vol = nx * ny * nz;
-  bool busy = false, to_buf = false; iso::ProjState S; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
+  // phase 1 once per element (it does not depend on the grid point)
+  iso::ProjState S0; const bool ok0 = iso::proj_init_element(A, rho_t, gs, S0);
+  bool busy = false, to_buf = false; iso::ProjState S = S0; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
   int sweep = 0, next = 0, its = 0, nbad = 0, npruned = 0;
   while (true) {
-    // ---- refill idle lanes with the next candidate points of the current sweep
+    // ---- refill idle lanes with the next candidate points of the current sweep (sweep 0: points inside the AABB, 1: the rest)
     while (sweep < 2) {
       const unsigned idle = __ballot_sync(0xffffffffu, !busy);
       if (!idle) break;
@@ -185,19 +187,19 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
       if (!busy && cand < vol) {
         const int i = cand % nx, j = (cand / nx) % ny, k = cand / (nx * ny);
         const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
-        x[0] = g.pc[g.pc_off[0] + pi0]; x[1] = g.pc[g.pc_off[1] + pi1]; x[2] = g.pc[g.pc_off[2] + pi2];
-        const double d0 = fmax(fmax(lo[0] - x[0], x[0] - hi[0]), 0.0), d1 = fmax(fmax(lo[1] - x[1], x[1] - hi[1]), 0.0), d2 = fmax(fmax(lo[2] - x[2], x[2] - hi[2]), 0.0);
-        const double lb = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
-        if ((sweep == 0) == (lb == 0.0)) {
-          vox = ((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0;
+        const double x0 = g.pc[g.pc_off[0] + pi0], x1 = g.pc[g.pc_off[1] + pi1], x2 = g.pc[g.pc_off[2] + pi2];
+        const double d0 = fmax(fmax(lo[0] - x0, x0 - hi[0]), 0.0), d1 = fmax(fmax(lo[1] - x1, x1 - hi[1]), 0.0), d2 = fmax(fmax(lo[2] - x2, x2 - hi[2]), 0.0);
+        const double lb2 = fma(d2, d2, fma(d1, d1, d0 * d0));
+        if ((sweep == 0) == (lb2 == 0.0)) {
+          const i64 vx = ((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0;
           const i64 t = ((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X;
-          to_buf = tile_faces[t] != 0;
+          const bool tb = tile_faces[t] != 0;
           bool prune = false;
-          if (!to_buf && sweep == 1) { const double cur = dist[vox]; prune = lb - (margin0 + 1e-12 * lb) > cur; }
+          if (!tb && sweep == 1) { const double cur = dist[vx] * (1.0 + 1e-12) + margin0; prune = lb2 > cur * cur; }      // lower bound already above the voxel's minimum
           if (prune) npruned++;
           else {
-            li = cand; busy = true;
-            if (!iso::proj_init(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) S.it = 1000;      // no iso point found: finalised below with xi = 0
+            li = cand; busy = true; vox = vx; to_buf = tb; x[0] = x0; x[1] = x1; x[2] = x2; S = S0;
+            if (!ok0 && !iso::proj_init(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(A, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
           }
         }
       }
@@ -210,9 +212,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
       if (S.it < 100) status = iso::proj_iter(A, x, rho_t, gs, S);
       if (status != 0 || S.it >= 100) {
         if (S.it >= 1000) nbad++; else { its += S.it; if (status != 1) nbad++; }
-        double p[3]; iso::eval_pos(A, S.xi, p);
-        const double e0 = x[0] - p[0], e1 = x[1] - p[1], e2 = x[2] - p[2];
-        const double dd = sqrt(fma(e2, e2, fma(e1, e1, e0 * e0)));
+        const double dd = sqrt(S.f);
         if (to_buf) pairbuf[r.pair_off + li] = dd;
         else atomicMin((u64 *)&dist[vox], (u64)__double_as_longlong(dd));
         busy = false;

@@ -156,13 +156,13 @@ __device__ __forceinline__ void tangent_step(const Eval &E, const int fix[3], do
 // coefficients [x,y,z,rho][8]; re: nodal densities (for the edge fallback).  project_hex8 below is init + iterate-to-the-end;
 // the lane-refill kernel drives the two pieces itself so that the lanes of a warp can be at different iterations of
 // different grid points.  The arithmetic and its order are the same in both drivers (bit-identical results).
-struct ProjState { double xi[3]; double lam; int it, stall; bool force; };
+struct ProjState { double xi[3]; double lam; double f; int it, stall; bool force; };      // f = |X(xi) - x|^2 at the current xi (valid once proj_iter has run)
 
 __device__ __forceinline__ bool proj_init(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
                                           const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs;
   int fix[3] = {0, 0, 0};
-  S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.it = 0; S.stall = 0; S.force = false;
+  S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
   bool ok = restore(A, rho_t, S.xi, fix, tolg);
   if (!ok) {
     double best = INFINITY;
@@ -180,6 +180,13 @@ __device__ __forceinline__ bool proj_init(const double A[4][8], const double re[
   }
   return true;
 }
+// Phase 1 without the edge fallback: the Newton projection of xi = 0 onto {g = 0} does not depend on the grid point, so a
+// warp that works on one element computes it once and hands the state to every point (same arithmetic as proj_init).
+__device__ __forceinline__ bool proj_init_element(const double A[4][8], double rho_t, double gs, ProjState &S) {
+  int fix[3] = {0, 0, 0};
+  S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
+  return restore(A, rho_t, S.xi, fix, 1e-14 * gs);
+}
 // one phase-2 iteration; returns 0 = continue, 1 = converged, 2 = failed (line search exhausted)
 __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
@@ -190,6 +197,7 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
 #pragma unroll
     for (int i = 0; i < 3; i++) { bnd[i] = xi[i] >= 1.0 ? 1 : (xi[i] <= -1.0 ? -1 : 0); fix[i] = bnd[i]; }
     Eval E; eval_full(A, x, rho_t, xi, E);
+    S.f = E.f;
     double d[3] = {0, 0, 0}; bool have_step = false; int status = 0;
     for (int pass = 0; pass < 8; pass++) {
       double num = 0, den = 0;
@@ -255,7 +263,7 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
         // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
         if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
           if (E.f - ft <= 1e-15 * E.f) S.stall++; else S.stall = 0;
-          xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true;
+          xi[0] = xt[0]; xi[1] = xt[1]; xi[2] = xt[2]; acc = true; S.f = ft;
           // A full Newton step of size dm <= 1e-6 that ends strictly inside the box leaves an error of O(dm^2) <= 1e-12: the
           // next iteration would only confirm |step| <= tolx, so it is skipped (saves one evaluation of ~3.5 per pair; the CPU
           // oracle keeps the confirming iteration -- the two agree to ~1e-12 in xi, far inside the 1e-9 h tolerance).
