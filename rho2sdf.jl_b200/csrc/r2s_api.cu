@@ -20,6 +20,8 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; } ctx->own_stream = true; }
   for (int i = 0; i < 16; i++) cudaEventCreate(&ctx->ev[i]);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 64; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
   *out = ctx;
   return 0;
 }
@@ -35,6 +37,8 @@ void r2s_destroy(r2s_ctx *ctx) {
                    &ctx->f_scal, &ctx->cutlist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1]};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 64; i++) cudaEventDestroy(ctx->ev_copy[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -285,6 +289,13 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   CK(cudaEventRecord(ctx->ev[10], ctx->stream));
   if (p->remove_artifacts) { i64 fl = 0; if (r2s_dev_remove_artifacts(ctx, p->artifact_threshold, p->artifact_min_ratio, &fl)) return 1; ctx->rep.n_flipped = fl; }
   CK(cudaEventRecord(ctx->ev[11], ctx->stream));
+  if (ctx->async_sdf_host) {      // sdf_dists is final here: its download overlaps the smoothing stage
+    const size_t pl = (size_t)ctx->g.np[0] * ctx->g.np[1];
+    cudaEvent_t e = ctx->ev_copy[ctx->n_ev_copy++ % 64];
+    CK(cudaEventRecord(e, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, e, 0));
+    CK(cudaMemcpyAsync(ctx->async_sdf_host, ctx->sdf.as<double>() + pl * (size_t)ctx->k0, sizeof(double) * pl * (size_t)(ctx->k1 - ctx->k0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
   float th = 0, vol = 0;
   if (r2s_dev_rbf(ctx, p->rbf_interp, p->smooth, p->rbf_cut, p->target_volume, p->final_volume != 0, &th, &vol)) return 1;
   CK(cudaEventRecord(ctx->ev[12], ctx->stream));
@@ -317,13 +328,11 @@ int r2s_result_ptrs_dev(r2s_ctx *ctx, void **sdf_dev, void **fine_dev) {
   if (fine_dev) *fine_dev = ctx->f_fine.p;
   return 0;
 }
+int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep);
 int r2s_pipeline(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_dists, float *fine_sdf, r2s_report *rep) {
   if (!ctx || !p) return 1;
-  if (upload_rho_n(ctx, rho_n)) return 1;
-  if (r2s_pipeline_resident(ctx, p, rep)) return 1;
-  if (sdf_dists && r2s_download_sdf(ctx, sdf_dists)) return 1;
-  if (fine_sdf && r2s_download_fine_sdf(ctx, fine_sdf)) return 1;
-  return 0;
+  if (ctx->has_grid && (ctx->k0 != 0 || ctx->k1 != ctx->g.np[2])) FAIL("r2s_pipeline: a z-slab is set; use r2s_pipeline_slab");
+  return r2s_pipeline_slab(ctx, p, rho_n, sdf_dists, fine_sdf, rep);      // whole grid = one slab; downloads overlap the compute
 }
 // Host-buffer entry point for one z-slab (== r2s_pipeline when the slab is the whole grid): uploads rho_n, runs the timed
 // region, returns ONLY this rank's planes: sdf_slab[(k1-k0) * np0 * np1] (coarse planes [k0,k1)) and
@@ -331,13 +340,14 @@ int r2s_pipeline(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double 
 int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep) {
   if (!ctx || !p) return 1;
   if (upload_rho_n(ctx, rho_n)) return 1;
-  if (r2s_pipeline_resident(ctx, p, rep)) return 1;
-  const GridDev &g = ctx->g; int s = p->smooth;
-  size_t pl = (size_t)g.np[0] * g.np[1];
-  i64 fx = g.N[0] * (i64)s + 1, fy = g.N[1] * (i64)s + 1, fz = g.N[2] * (i64)s + 1;
-  i64 kf0 = s * ctx->k0, kf1 = (ctx->k1 < g.np[2]) ? s * ctx->k1 : fz;
-  if (sdf_slab) CK(cudaMemcpyAsync(sdf_slab, ctx->sdf.as<double>() + pl * (size_t)ctx->k0, sizeof(double) * pl * (size_t)(ctx->k1 - ctx->k0), cudaMemcpyDeviceToHost, ctx->stream));
-  if (fine_slab) CK(cudaMemcpyAsync(fine_slab, ctx->f_fine.as<float>() + (size_t)fx * fy * (size_t)kf0, sizeof(float) * (size_t)fx * fy * (size_t)(kf1 - kf0), cudaMemcpyDeviceToHost, ctx->stream));
+  // the downloads are enqueued by the stages themselves as soon as a result is final (sdf_dists after the artifact removal,
+  // fine_sdf chunk by chunk behind the fine-grid evaluation) and run on a second stream while the remaining kernels execute
+  ctx->async_sdf_host = sdf_slab; ctx->async_fine_host = fine_slab; ctx->n_ev_copy = 0;
+  int rc = r2s_pipeline_resident(ctx, p, rep);
+  ctx->async_sdf_host = nullptr; ctx->async_fine_host = nullptr;
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  if (rc) return 1;
+  CK(e);
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -793,14 +793,30 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[13], st));
   // fine grid (:363-366): the fine planes of my coarse planes
   if (upload_taps(ctx, smooth, rbf_cut, g.cell)) return 1;
-  if (smooth == 1) {
-    dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(kf1 - kf0, FN_Z));
-    k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, kf1, kf0, wgt, tho, ctx->f_fine.as<float>());
-  } else {
-    dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(k1 - k0, F2_Z));
-    k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, k0, k1, wgt, tho, ctx->f_fine.as<float>());
+  {
+    // evaluated in chunks of coarse planes; when a host buffer is attached (r2s_pipeline_slab) each finished chunk is
+    // downloaded on the copy stream while the next chunks and the final volume are computed
+    const int chunk = ctx->async_fine_host ? 32 : (k1 - k0);
+    for (int c0 = k0; c0 < k1; c0 += chunk) {
+      const int c1 = std::min(c0 + chunk, k1);
+      const int f0 = smooth * c0, f1 = (c1 < nz) ? smooth * c1 : fz;
+      if (smooth == 1) {
+        dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(f1 - f0, FN_Z));
+        k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, f1, f0, wgt, tho, ctx->f_fine.as<float>());
+      } else {
+        dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(c1 - c0, F2_Z));
+        k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, c0, c1, wgt, tho, ctx->f_fine.as<float>());
+      }
+      LAUNCH_CHECK();
+      if (ctx->async_fine_host) {
+        cudaEvent_t e = ctx->ev_copy[ctx->n_ev_copy++ % 64];
+        CK(cudaEventRecord(e, st));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, e, 0));
+        CK(cudaMemcpyAsync(ctx->async_fine_host + (size_t)(f0 - kf0) * fpl, ctx->f_fine.as<float>() + (size_t)f0 * fpl, sizeof(float) * (size_t)(f1 - f0) * fpl, cudaMemcpyDeviceToHost,
+                           ctx->copy_stream));
+      }
+    }
   }
-  LAUNCH_CHECK();
   CK(cudaEventRecord(ctx->ev[14], st));
   float volf = 0.0f;
   if (final_volume) {      // calculate_volume_from_sdf on the fine grid (:373), iso = 0

@@ -112,54 +112,68 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
   if (valid) { x[0] = g.pc[g.pc_off[0] + pi[0]]; x[1] = g.pc[g.pc_off[1] + pi[1]]; x[2] = g.pc[g.pc_off[2] + pi[2]]; }
   double sign = -1.0, max_local = 10.0; bool done = false;
   const int p0 = tile_ptr[t], p1 = tile_ptr[t + 1];
-  // pass A: does this point have a candidate at all whose nodal densities reach rho_t?  If not it is skipped with sign -1
-  // (SignDetection.jl:36; TET4 elements are all marked hot).  Costs only integer range tests; whole warps of the void
-  // region leave here without touching the mesh.
-  bool hotany = false;
-  for (int p = p0; p < p1; p += 32) {
-    int idx = p + lane; bool ov = false; SRange r;
-    if (idx < p1) {
-      r = rng[(int)(keys[idx] & 0xffffffffull)];
-      ov = r.hot && r.a[0] <= wx1 && r.b[0] >= wx0 && r.a[1] <= wy1 && r.b[1] >= wy0 && r.a[2] <= wz && r.b[2] >= wz;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, ov);
-    while (m) {
-      int src = __ffs(m) - 1; m &= m - 1;
-      int a0 = __shfl_sync(0xffffffffu, r.a[0], src), b0 = __shfl_sync(0xffffffffu, r.b[0], src), a1 = __shfl_sync(0xffffffffu, r.a[1], src),
-          b1 = __shfl_sync(0xffffffffu, r.b[1], src), a2 = __shfl_sync(0xffffffffu, r.a[2], src), b2 = __shfl_sync(0xffffffffu, r.b[2], src);
-      if (pi[0] >= a0 && pi[0] <= b0 && pi[1] >= a1 && pi[1] <= b1 && pi[2] >= a2 && pi[2] <= b2) hotany = true;
-    }
-  }
-  const bool live = valid && hotany;
+  // Skip rule (SignDetection.jl:36): a point none of whose candidates has a nodal density >= rho_t keeps sign -1 (TET4 elements
+  // are all marked hot).  The tile's list is culled to the warp's footprint into shared memory; when it fits one round (the
+  // normal case) the hot test comes from that same round, otherwise a separate pass over the list computes it first.
+  bool hotany = false, hot_known = false, first = true;
   int p = p0;
-  if (!__any_sync(0xffffffffu, live)) p = p1;
   while (p < p1) {
-    int n = 0;
+    int n = 0; bool warp_hot = false;
     while (p < p1 && n <= CULL_CAP - 32) {
-      int idx = p + lane; bool ov = false; int e = 0; SRange r;
+      int idx = p + lane; bool ov = false; int e = 0; SRange r; r.hot = 0;
       if (idx < p1) {
         e = (int)(keys[idx] & 0xffffffffull); r = rng[e];
         ov = r.a[0] <= wx1 && r.b[0] >= wx0 && r.a[1] <= wy1 && r.b[1] >= wy0 && r.a[2] <= wz && r.b[2] >= wz;
       }
       unsigned m = __ballot_sync(0xffffffffu, ov);
+      warp_hot = warp_hot || __any_sync(0xffffffffu, ov && r.hot != 0);
       if (ov) { int slot = n + __popc(m & ((1u << lane) - 1)); s_el[warp][slot] = e; s_rg[warp][slot] = r; }
       n += __popc(m); p += 32;
     }
     __syncwarp();
-    int pos = 0;
-    while (true) {
-      // advance to this lane's next candidate
-      if (live && !done) {
-        while (pos < n) {
-          const SRange &r = s_rg[warp][pos];
-          if (pi[0] >= r.a[0] && pi[0] <= r.b[0] && pi[1] >= r.a[1] && pi[1] <= r.b[1] && pi[2] >= r.a[2] && pi[2] <= r.b[2]) break;
-          pos++;
+    if (first && p >= p1 && !warp_hot) break;      // void region: no element near this warp reaches rho_t -> every lane keeps -1
+    if (first && p < p1) {      // long list: the hot test needs all of it before the first candidate is processed
+      for (int pp = p0; pp < p1; pp += 32) {
+        int idx = pp + lane; bool ov = false; SRange r;
+        if (idx < p1) {
+          r = rng[(int)(keys[idx] & 0xffffffffull)];
+          ov = r.hot && r.a[0] <= wx1 && r.b[0] >= wx0 && r.a[1] <= wy1 && r.b[1] >= wy0 && r.a[2] <= wz && r.b[2] >= wz;
         }
-      } else pos = n;
-      bool act = pos < n;
+        unsigned m = __ballot_sync(0xffffffffu, ov);
+        while (m) {
+          int src = __ffs(m) - 1; m &= m - 1;
+          int a0 = __shfl_sync(0xffffffffu, r.a[0], src), b0 = __shfl_sync(0xffffffffu, r.b[0], src), a1 = __shfl_sync(0xffffffffu, r.a[1], src),
+              b1 = __shfl_sync(0xffffffffu, r.b[1], src), a2 = __shfl_sync(0xffffffffu, r.a[2], src), b2 = __shfl_sync(0xffffffffu, r.b[2], src);
+          if (pi[0] >= a0 && pi[0] <= b0 && pi[1] >= a1 && pi[1] <= b1 && pi[2] >= a2 && pi[2] <= b2) hotany = true;
+        }
+      }
+      hot_known = true;
+    }
+    // which entries of the culled list are candidates of THIS lane: one uniform sweep (broadcast reads, no bank conflicts)
+    unsigned mk0 = 0, mk1 = 0, mk2 = 0; bool hotloc = false;
+    for (int q = 0; q < n; q++) {
+      const SRange &r = s_rg[warp][q];
+      if (valid && pi[0] >= r.a[0] && pi[0] <= r.b[0] && pi[1] >= r.a[1] && pi[1] <= r.b[1] && pi[2] >= r.a[2] && pi[2] <= r.b[2]) {
+        if (q < 32) mk0 |= 1u << q; else if (q < 64) mk1 |= 1u << (q - 32); else mk2 |= 1u << (q - 64);
+        hotloc = hotloc || r.hot != 0;
+      }
+    }
+    if (!hot_known) { hotany = hotloc; hot_known = true; }
+    first = false;
+    const bool live = valid && hotany;
+    if (!__any_sync(0xffffffffu, live)) break;
+    int w = 0; unsigned cur = mk0;
+    while (true) {
+      // this lane's next candidate (ascending list position = ascending element index)
+      int pos = -1;
+      if (live && !done) {
+        while (w < 3 && cur == 0) { w++; cur = (w == 1) ? mk1 : (w == 2 ? mk2 : 0u); }
+        if (w < 3) { int bq = __ffs(cur) - 1; cur &= cur - 1; pos = w * 32 + bq; }
+      }
+      bool act = pos >= 0;
       if (!__any_sync(0xffffffffu, act)) break;
       if (act) {
-        const int e = s_el[warp][pos]; pos++;
+        const int e = s_el[warp][pos];
         if (NEN == 8) {
           double xi[3];
           const SignEl &S = sel[e];
