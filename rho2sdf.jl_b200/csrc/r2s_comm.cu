@@ -81,6 +81,9 @@ extern "C" int r2s_comm_destroy(r2s_ctx *ctx) {
   return 0;
 }
 
+// fuse the collectives issued between the two calls into one NCCL launch (nested groups are allowed)
+int r2s_group_start(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupStart()); return 0; }
+int r2s_group_end(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupEnd()); return 0; }
 // ---- collectives used by the pipeline; all are no-ops for a single rank ----------------------------------------------
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/) {
   if (ctx->nranks <= 1) return 0;

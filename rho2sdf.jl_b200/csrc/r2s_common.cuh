@@ -91,7 +91,7 @@ struct r2s_ctx {
   DevBuf dist, xp, sdf, signs;
   DevBuf s_rng, s_el, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
   // connected components
-  DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all;
+  DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all, cc_gsz, cc_seen;
   // smoothing
   DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, vlist[2];
   int smooth_last = 1;
@@ -141,6 +141,8 @@ int r2s_scan_exclusive_i32(r2s_ctx *ctx, const int *in, int *out, i64 n);
 int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64 **sorted);
 // r2s_comm.cu: collectives over the slab communicator (no-ops for a single rank)
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
+int r2s_group_start(r2s_ctx *ctx);
+int r2s_group_end(r2s_ctx *ctx);
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count);
 int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k1, int nz, int below, int above);
 extern "C" int r2s_comm_destroy(r2s_ctx *ctx);

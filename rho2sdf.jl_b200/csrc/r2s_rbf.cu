@@ -733,8 +733,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
+      if (r2s_group_start(ctx)) return 1;            // one NCCL launch: scalar all-reduce + halo planes of c
       if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
       if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
+      if (r2s_group_end(ctx)) return 1;
       k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
       k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part); LAUNCH_CHECK();
       k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
@@ -760,8 +762,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   unsigned init_mm[2] = {0xffffffffu, 0u};
   CK(cudaMemcpyAsync(ubits + 2, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
   k_minmax<<<cdiv(nown, 256), 256, 0, st>>>(nown, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
+  if (r2s_group_start(ctx)) return 1;
   if (r2s_allreduce(ctx, ubits + 2, 1, 3)) return 1;
   if (r2s_allreduce(ctx, ubits + 3, 1, 2)) return 1;
+  if (r2s_group_end(ctx)) return 1;
   unsigned hmm[2];
   CK(cudaMemcpyAsync(hmm, ubits + 2, sizeof(hmm), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -27,25 +27,7 @@ __global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, con
                               GridDev g, int kz0, int kz1, SRange *__restrict__ rng, i64 *__restrict__ ntile, SignEl *__restrict__ sel) {
   i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (e >= nel) return;
-  if (nen == 8) {
-    using namespace ex;
-    double A[3][8]; bool affine = true;
-    for (int d = 0; d < 3; d++) {
-      double v[8];
-      for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)IEN[8 * e + a] + d];
-      mono8(v, A[d]);
-      if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
-    }
-    SignEl S; S.affine = affine ? 1 : 0; S.pad = 0;
-    // first Newton step at xi = 0: val = a0, J[d][c] = A[d][1 + c] (the products with xi = 0 vanish)
-    double J[3][3];
-    for (int d = 0; d < 3; d++) { S.a0[d] = A[d][0]; J[d][0] = A[d][1]; J[d][1] = A[d][2]; J[d][2] = A[d][3]; }
-    S.c[0] = sub(mul(J[1][1], J[2][2]), mul(J[1][2], J[2][1])); S.c[1] = sub(mul(J[1][2], J[2][0]), mul(J[1][0], J[2][2])); S.c[2] = sub(mul(J[1][0], J[2][1]), mul(J[1][1], J[2][0]));
-    S.det = add(add(mul(J[0][0], S.c[0]), mul(J[0][1], S.c[1])), mul(J[0][2], S.c[2]));
-    S.c[3] = sub(mul(J[0][2], J[2][1]), mul(J[0][1], J[2][2])); S.c[4] = sub(mul(J[0][0], J[2][2]), mul(J[0][2], J[2][0])); S.c[5] = sub(mul(J[0][1], J[2][0]), mul(J[0][0], J[2][1]));
-    S.c[6] = sub(mul(J[0][1], J[1][2]), mul(J[0][2], J[1][1])); S.c[7] = sub(mul(J[0][2], J[1][0]), mul(J[0][0], J[1][2])); S.c[8] = sub(mul(J[0][0], J[1][1]), mul(J[0][1], J[1][0]));
-    sel[e] = S;
-  }
+
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rmax = -1e300;
   for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; rmax = fmax(rmax, rn[n]); for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
   SRange r; bool ok = true; r.pad = 0;
@@ -72,6 +54,25 @@ __global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, con
   }
   if (!ok) { r.a[0] = 1; r.b[0] = 0; }
   rng[e] = r;
+  if (nen == 8 && ok) {      // only elements with candidate points in this slab
+    using namespace ex;
+    double A[3][8]; bool affine = true;
+    for (int d = 0; d < 3; d++) {
+      double v[8];
+      for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)IEN[8 * e + a] + d];
+      mono8(v, A[d]);
+      if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
+    }
+    SignEl S; S.affine = affine ? 1 : 0; S.pad = 0;
+    // first Newton step at xi = 0: val = a0, J[d][c] = A[d][1 + c] (the products with xi = 0 vanish)
+    double J[3][3];
+    for (int d = 0; d < 3; d++) { S.a0[d] = A[d][0]; J[d][0] = A[d][1]; J[d][1] = A[d][2]; J[d][2] = A[d][3]; }
+    S.c[0] = sub(mul(J[1][1], J[2][2]), mul(J[1][2], J[2][1])); S.c[1] = sub(mul(J[1][2], J[2][0]), mul(J[1][0], J[2][2])); S.c[2] = sub(mul(J[1][0], J[2][1]), mul(J[1][1], J[2][0]));
+    S.det = add(add(mul(J[0][0], S.c[0]), mul(J[0][1], S.c[1])), mul(J[0][2], S.c[2]));
+    S.c[3] = sub(mul(J[0][2], J[2][1]), mul(J[0][1], J[2][2])); S.c[4] = sub(mul(J[0][0], J[2][2]), mul(J[0][2], J[2][0])); S.c[5] = sub(mul(J[0][1], J[2][0]), mul(J[0][0], J[2][1]));
+    S.c[6] = sub(mul(J[0][1], J[1][2]), mul(J[0][2], J[1][1])); S.c[7] = sub(mul(J[0][2], J[1][0]), mul(J[0][0], J[1][2])); S.c[8] = sub(mul(J[0][0], J[1][1]), mul(J[0][1], J[1][0]));
+    sel[e] = S;
+  }
   ntile[e] = ok ? (i64)(r.b[0] / TILE_X - r.a[0] / TILE_X + 1) * (r.b[1] / TILE_Y - r.a[1] / TILE_Y + 1) * (r.b[2] / TILE_Z - r.a[2] / TILE_Z + 1) : 0;
 }
 __global__ void k_sign_emit(i64 nel, const SRange *__restrict__ rng, const i64 *__restrict__ toff, GridDev g, u64 *__restrict__ keys, int *__restrict__ tile_cnt) {

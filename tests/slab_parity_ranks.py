@@ -41,10 +41,13 @@ def main():
         fine = np.empty(fd[0] * fd[1] * fd[2], dtype=np.float32); c.check(c.lib.r2s_download_fine_sdf(c.h, fine.ctypes.data_as(C.c_void_p)))
         return sdf.reshape(nz, ny, nx), fine.reshape(fd[2], fd[1], fd[0]), rep
 
-    sdf1, fine1, rep1 = run()                                   # single rank, whole grid
+    cases = [(0.5, 0.3), (0.93, 0.5), (0.08, 0.5)]                # (rho_t, artifact ratio): the extreme thresholds fragment the interior mask
+    single = []
+    for rt, ratio in cases:                                      # single rank, whole grid
+        p.rho_t, p.artifact_min_ratio = rt, ratio
+        single.append(run())
     k0, k1 = r2s.slab_partition(nz, world)[rank]
     r2s.init_slab_comm(c, rank, world, k0, k1)
-    sdfN, fineN, repN = run()                                   # this rank's slab of the N-rank run
     kf0, kf1 = 2 * k0, (2 * k1 if k1 < nz else fd[2])
     ok = True
     def check(name, cond):
@@ -52,16 +55,25 @@ def main():
         if not cond:
             ok = False
             print("[rank %d] FAIL %s" % (rank, name), flush=True)
-    check("sdf bit-identical on owned planes", np.array_equal(sdf1[k0:k1], sdfN[k0:k1]))
-    check("flipped equal", rep1.n_flipped == repN.n_flipped)
-    check("cg iterations equal", rep1.cg_iters == repN.cg_iters)
-    check("bisections equal", rep1.bisections == repN.bisections)
-    scale = max(1.0, float(np.abs(fine1).max()))
-    err = float(np.abs(fine1[kf0:kf1] - fineN[kf0:kf1]).max())
-    check("fine field within 1e-5 (err %.3e, scale %.3g)" % (err, scale), err <= 1e-5 * scale)
-    check("threshold offset", abs(rep1.th - repN.th) <= 1e-5 * scale)
-    check("final volume", abs(rep1.volume - repN.volume) <= 1e-5 * abs(rep1.volume))
-    check("collectives issued", repN.collectives > 0 and rep1.collectives == 0)
+    summary = []
+    for (rt, ratio), (sdf1, fine1, rep1) in zip(cases, single):
+        p.rho_t, p.artifact_min_ratio = rt, ratio
+        sdfN, fineN, repN = run()                               # this rank's slab of the N-rank run
+        tag = "[rho_t=%g] " % rt
+        check(tag + "sdf bit-identical on owned planes", np.array_equal(sdf1[k0:k1], sdfN[k0:k1]))
+        check(tag + "flipped equal (%d vs %d)" % (rep1.n_flipped, repN.n_flipped), rep1.n_flipped == repN.n_flipped)
+        check(tag + "cg iterations equal", rep1.cg_iters == repN.cg_iters)
+        check(tag + "bisections equal", rep1.bisections == repN.bisections)
+        scale = max(1.0, float(np.abs(fine1).max()))
+        err = float(np.abs(fine1[kf0:kf1] - fineN[kf0:kf1]).max())
+        check(tag + "fine field within 1e-5 (err %.3e, scale %.3g)" % (err, scale), err <= 1e-5 * scale)
+        check(tag + "threshold offset", abs(rep1.th - repN.th) <= 1e-5 * scale)
+        check(tag + "final volume", abs(rep1.volume - repN.volume) <= 1e-5 * abs(rep1.volume))
+        check(tag + "collectives issued", repN.collectives > 0 and rep1.collectives == 0)
+        summary.append("rho_t=%g flipped=%d cg=%d bis=%d th=%.7f/%.7f fine err=%.3e coll=%d ms1=%.2f msN=%.2f" %
+                       (rt, repN.n_flipped, repN.cg_iters, repN.bisections, rep1.th, repN.th, err, repN.collectives, rep1.ms_total, repN.ms_total))
+    p.rho_t, p.artifact_min_ratio = cases[0]
+    sdfN, fineN, repN = run()
     # host-buffer slab entry point returns exactly the owned planes
     h_sdf = np.empty((k1 - k0) * ny * nx); h_fine = np.empty((kf1 - kf0) * fd[1] * fd[0], dtype=np.float32); rep = r2s.Report()
     c.check(c.lib.r2s_pipeline_slab(c.h, C.byref(p), rn.ctypes.data_as(C.c_void_p), h_sdf.ctypes.data_as(C.c_void_p), h_fine.ctypes.data_as(C.c_void_p), C.byref(rep)))
@@ -70,8 +82,8 @@ def main():
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("flipped=%d cg=%d bis=%d th=%.7f/%.7f vol=%.3f/%.3f fine err=%.3e collectives=%d ms1=%.2f msN=%.2f" %
-              (repN.n_flipped, repN.cg_iters, repN.bisections, rep1.th, repN.th, rep1.volume, repN.volume, err, repN.collectives, rep1.ms_total, repN.ms_total), flush=True)
+        for ln in summary:
+            print(ln, flush=True)
         print("SLAB PARITY OK" if int(t.item()) == 1 else "SLAB PARITY FAILED", flush=True)
     dist.barrier()
     mesh.ctx.close()

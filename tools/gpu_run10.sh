@@ -1,9 +1,10 @@
 #!/bin/bash
-# strong-scaling sweep on one box: N = 1, 2, 4, 8 (as the driver does), plus the slab parity check on NG ranks
 mkdir -p gpurun_out
-NG=${1:-8}
+NG=${1:-4}
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29741 tests/slab_parity_ranks.py 48 > gpurun_out/slab_parity_$NG.log 2>&1; echo "slab parity ($NG ranks) rc=$?"
 grep -E "FAIL|OK|flipped|Error" gpurun_out/slab_parity_$NG.log | head -16
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/pytest_gpu.log
 show() { python - "$1" <<'PY'
 import json, sys
 f = sys.argv[1]
@@ -15,12 +16,5 @@ except Exception as e:
     print(f, "ERR", e)
 PY
 }
-for n in 1 2 4 8; do
-  if [ $n -gt $NG ]; then break; fi
-  if [ $n -eq 1 ]; then
-    timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
-  else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2975$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
-  fi
-  echo "N=$n rc=$?"; show gpurun_out/scale_$n.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\*\|^$" gpurun_out/scale_$n.err | tail -3
-done
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_1.json 2> gpurun_out/scale_1.err; echo "N=1 rc=$?"; show gpurun_out/scale_1.json; tail -2 gpurun_out/scale_1.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29754 bench.py --gpus $NG --steps 3 --warmup 3 > gpurun_out/scale_$NG.json 2> gpurun_out/scale_$NG.err; echo "N=$NG rc=$?"; show gpurun_out/scale_$NG.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\*\|^$" gpurun_out/scale_$NG.err | tail -3
