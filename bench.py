@@ -239,10 +239,17 @@ def run_gpu(args):
         wall_e2e = (time.perf_counter() - w0) * 1e3
         ms_e2e = max(f0.elapsed_time(f1), 0.0)
         clocks = sampler.stop() if sampler else None
+        per_rank = None
         if world > 1:
             t = torch.tensor([ms, ms_e2e, wall_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, ms_e2e, wall_e2e = (float(v) for v in t.tolist())
+            # per-rank stage times of the last timed step (load-balance evidence)
+            keys = ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_cg", "ms_threshold", "ms_total")
+            mine = torch.tensor([getattr(reps[-1], k) for k in keys] + [float(k1 - k0)], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = [dict(zip(keys + ("planes",), [round(float(v), 2) for v in a.tolist()])) for a in allr]
         # ---- roofline denominators measured on this device ----
         fp64, fp32 = C.c_double(), C.c_double()
         c.check(c.lib.r2s_measure_fma_peak(c.h, 1, C.byref(fp64)))
@@ -296,6 +303,8 @@ def run_gpu(args):
                        "target_volume": float(p.target_volume), "solid": int(rep.n_solid), "crossing": int(rep.n_crossing)},
             "clocks": clocks,
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:
             step, nt, g = cpu_pipeline(args.cpu_n)
             t, nv = step()

@@ -148,17 +148,24 @@ __global__ void k_ccg_scatter(int nxy, int nranks, i64 own_lo, i64 own_hi, const
 }
 __global__ void k_ccg_union(int nxy, int nranks, const int *__restrict__ all, int *__restrict__ L) {
   i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (t >= (i64)(nranks - 1) * nxy) return;
-  int r = (int)(t / nxy), p = (int)(t % nxy);
-  int a = all[(i64)r * 4 * nxy + nxy + p], b = all[(i64)(r + 1) * 4 * nxy + p];      // top of r, bottom of r + 1
-  if (a >= 0 && b >= 0) uf_union(L, a, b);
+  int a = -1, b = -1;
+  if (t < (i64)(nranks - 1) * nxy) {
+    int r = (int)(t / nxy), p = (int)(t % nxy);
+    a = all[(i64)r * 4 * nxy + nxy + p]; b = all[(i64)(r + 1) * 4 * nxy + p];      // top of r, bottom of r + 1
+  }
+  // the big components face each other along thousands of voxels: one union per distinct (a, b) pair per warp
+  const bool on = a >= 0 && b >= 0;
+  const u64 key = on ? (((u64)(unsigned)a << 32) | (unsigned)b) : ~0ull;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (on && (threadIdx.x & 31) == __ffs(peers) - 1) uf_union(L, a, b);
 }
 __global__ void k_ccg_sizes(int nxy, int nranks, const int *__restrict__ all, const int *__restrict__ L, const int *__restrict__ sz, int *__restrict__ gsz, int *__restrict__ seen) {
   i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (t >= (i64)nranks * 2 * nxy) return;
   int r = (int)(t / (2 * nxy)), q = (int)(t % (2 * nxy));
   int a = all[(i64)r * 4 * nxy + q];
-  if (a < 0) return;
+  const unsigned peers = __match_any_sync(__activemask(), a);
+  if (a < 0 || (threadIdx.x & 31) != __ffs(peers) - 1) return;      // one lane per distinct root per warp
   if (atomicExch(&seen[a], 1) == 0) atomicAdd(&gsz[find_ro(L, a)], sz[a]);
 }
 __global__ void k_ccg_largest(int nxy, int nranks, i64 nloc, i64 v0, const int *__restrict__ all, const int *__restrict__ L, const int *__restrict__ sz, const int *__restrict__ gsz,
