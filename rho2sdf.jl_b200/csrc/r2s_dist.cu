@@ -79,7 +79,7 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
 
 // ------------------------------------------------------------------------------------------------ project (hot, FP64)
 // one warp per 32-point chunk of a crossing element
-template <bool WANT_XP, int MINB>
+template <bool WANT_XP, int MINB, bool SMEM_A>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
                                                       double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters) {
@@ -93,18 +93,27 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   // element data: lane l < 8 loads node l; monomial coefficients assembled through shuffles
   double v[4] = {0, 0, 0, 0};
   if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
-  double A[4][8], re[8];
+  // SMEM_A: the warp-uniform monomial coefficients live in shared memory (broadcast reads) instead of 64 registers per thread
+  __shared__ double sA[SMEM_A ? 4 : 1][4][8];
+  double Ar[SMEM_A ? 1 : 4][8], re[8];
 #pragma unroll
   for (int c = 0; c < 4; c++) {
-    double nv[8];
+    double nv[8], Ac[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) nv[k] = __shfl_sync(0xffffffffu, v[c], k);
-    iso::monomial8(nv, A[c]);
+    iso::monomial8(nv, Ac);
+    if (SMEM_A) { if (lane < 8) sA[threadIdx.x >> 5][c][lane] = Ac[lane & 7]; }
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) Ar[SMEM_A ? 0 : c][k] = Ac[k];
+    }
     if (c == 3) {
 #pragma unroll
       for (int k = 0; k < 8; k++) re[k] = nv[k];
     }
   }
+  if (SMEM_A) __syncwarp();
+  const double (*A)[8] = SMEM_A ? (const double (*)[8])sA[threadIdx.x >> 5] : (const double (*)[8])Ar;
   double gs = fabs(rho_t);
 #pragma unroll
   for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
@@ -586,13 +595,17 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     int nb = cdiv(nitems * 32, 128);
 #define PROJ(KERN, XP) KERN<XP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
                                                    ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
-    // occupancy variant of the HEX8 kernel (255 / 168 / 128 registers per thread): R2S_PROJ_MINB = 2, 3, 4
-    static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 blocks/SM (128 regs, small spills) is 22% faster than 2 (255 regs)
-#define PROJH(XP, MB) k_project_hex8<XP, MB><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
+    // variants of the HEX8 kernel: R2S_PROJ_MINB = 2..6 CTAs/SM (255 / 168 / 128 / 102 / 85 registers), R2S_PROJ_SMEMA = 1 keeps the
+    // element's monomial coefficients in shared memory
+    static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
+    static const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
+#define PROJH(XP, MB, SA) k_project_hex8<XP, MB, SA><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
                                                    ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
     if (nen == 8) {
-      if (want_xp) PROJH(true, 2);
-      else if (minb <= 2) PROJH(false, 2); else if (minb == 3) PROJH(false, 3); else PROJH(false, 4);
+      if (want_xp) PROJH(true, 2, false);
+      else if (smema) { if (minb <= 4) PROJH(false, 4, true); else if (minb == 5) PROJH(false, 5, true); else PROJH(false, 6, true); }
+      else if (minb <= 2) PROJH(false, 2, false); else if (minb == 3) PROJH(false, 3, false); else if (minb == 4) PROJH(false, 4, false);
+      else if (minb == 5) PROJH(false, 5, false); else PROJH(false, 6, false);
     } else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
     LAUNCH_CHECK();
 #undef PROJH
