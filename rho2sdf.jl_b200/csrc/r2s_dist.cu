@@ -27,9 +27,14 @@ __global__ void k_classify(i64 nel, int nen, const int *__restrict__ IEN, const 
     cls[e] = (unsigned char)c;
     flag[e] = (c == 2 || (c == 1 && fb[e] != 0)) ? 1 : 0;
   }
-  // class counters (report only)
+  // class counters (report only): one pair of atomics per CTA
+  __shared__ int s1, s2;
+  if (threadIdx.x == 0) { s1 = 0; s2 = 0; }
+  __syncthreads();
   unsigned m1 = __ballot_sync(0xffffffffu, c == 1), m2 = __ballot_sync(0xffffffffu, c == 2);
-  if ((threadIdx.x & 31) == 0) { if (m1) atomicAdd((u64 *)&counts[0], (u64)__popc(m1)); if (m2) atomicAdd((u64 *)&counts[1], (u64)__popc(m2)); }
+  if ((threadIdx.x & 31) == 0) { if (m1) atomicAdd(&s1, __popc(m1)); if (m2) atomicAdd(&s2, __popc(m2)); }
+  __syncthreads();
+  if (threadIdx.x == 0) { if (s1) atomicAdd((u64 *)&counts[0], (u64)s1); if (s2) atomicAdd((u64 *)&counts[1], (u64)s2); }
 }
 // compacted active list: record with point ranges, tile count, pair count
 __global__ void k_act_records(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, const unsigned char *__restrict__ cls,
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   int its = nit > 0 ? nit : 0;
   for (int o = 16; o > 0; o >>= 1) its += __shfl_down_sync(0xffffffffu, its, o);
   unsigned bad = __ballot_sync(0xffffffffu, !okc);
-  if (lane == 0) { atomicAdd(&counters[2], (u64)its); if (bad) atomicAdd(&counters[3], (u64)__popc(bad)); }
+  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 1023)); atomicAdd(&cs[2], (u64)its); if (bad) atomicAdd(&cs[3], (u64)__popc(bad)); }      // statistics spread over 1024 slots
 }
 // Lane-refill variant (used when the closest points xp are not requested): ONE WARP PER CROSSING ELEMENT.  The warp keeps
 // the element's monomial coefficients in registers and its lanes work through the element's candidate points independently:
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
     }
   }
   for (int o = 16; o > 0; o >>= 1) { its += __shfl_down_sync(0xffffffffu, its, o); nbad += __shfl_down_sync(0xffffffffu, nbad, o); npruned += __shfl_down_sync(0xffffffffu, npruned, o); }
-  if (lane == 0) { atomicAdd(&counters[2], (u64)its); if (nbad) atomicAdd(&counters[3], (u64)nbad); if (npruned) atomicAdd(&counters[4], (u64)npruned); }
+  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 1023)); atomicAdd(&cs[2], (u64)its); if (nbad) atomicAdd(&cs[3], (u64)nbad); if (npruned) atomicAdd(&cs[4], (u64)npruned); }
 }
 template <bool WANT_XP>
 __global__ void __launch_bounds__(128) k_project_tet4(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
@@ -508,8 +513,8 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(ctx->cls.reserve((size_t)nel));
   CK(ctx->act_flag.reserve(sizeof(int) * (size_t)(nel + 1)));
   CK(ctx->act_idx.reserve(sizeof(int) * (size_t)(nel + 1)));
-  CK(ctx->counters.reserve(sizeof(u64) * 8));
-  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * 8, st));
+  CK(ctx->counters.reserve(sizeof(u64) * 8 * 1025));      // slot 0: element classes; slots 1..1024: projection statistics
+  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * 8 * 1025, st));
   CK(cudaMemsetAsync(ctx->act_flag.as<int>() + nel, 0, sizeof(int), st));
   k_classify<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), ctx->fbnd.as<unsigned char>(), rho_t,
                                              ctx->cls.as<unsigned char>(), ctx->act_flag.as<int>(), ctx->counters.as<i64>()); LAUNCH_CHECK();
@@ -627,9 +632,10 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #undef ASM
   }
   CK(cudaEventRecord(ctx->ev[3], st));
-  u64 hc[8];
-  CK(cudaMemcpyAsync(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+  static u64 hall[8 * 1025]; u64 hc[8];
+  CK(cudaMemcpyAsync(hall, ctx->counters.p, sizeof(hall), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  for (int q = 0; q < 8; q++) { hc[q] = hall[q]; for (int sl = 1; sl <= 1024; sl++) hc[q] += hall[8 * sl + q]; }
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
   ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
   CK(cudaEventElapsedTime(&ctx->rep.ms_bin, ctx->ev[0], ctx->ev[1]));

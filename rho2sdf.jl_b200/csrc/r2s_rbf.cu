@@ -14,12 +14,19 @@
 #include "r2s_tables.cuh"
 
 // ------------------------------------------------------------------------------------------------ process_vector (:15-22)
-__global__ void k_to_f32(i64 n, i64 v0, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_to_f32(i64 n, i64 v0, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
+  __shared__ float red[8];
   float a = -1.0f;
-  if (v < n) { float f = (float)sdf[v0 + v]; s[v] = f; float af = fabsf(f); if (af < 1.0e9f) a = af; }
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) {
+    float f = (float)sdf[v0 + v]; s[v] = f; float af = fabsf(f); if (af < 1.0e9f) a = fmaxf(a, af);
+  }
   for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_down_sync(0xffffffffu, a, o));
-  if ((threadIdx.x & 31) == 0 && a >= 0.0f) atomicMax(maxbits, __float_as_uint(a) + 1u);   // +1 so that "found 0.0" differs from "none"
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) a = fmaxf(a, red[i]);
+    if (a >= 0.0f) atomicMax(maxbits, __float_as_uint(a) + 1u);   // +1 so that "found 0.0" differs from "none"; one atomic per CTA
+  }
 }
 __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__restrict__ maxbits) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -197,6 +204,96 @@ __global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, 
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
 }
+// ---- plane-marching, two outputs per thread ---------------------------------------------------------------------
+// As k_stencil81_march, but a thread owns two x-adjacent columns: the six row values it needs come in as three 8-byte
+// shared-memory loads and serve both outputs (7.5 loads per output instead of 21), and the per-plane bookkeeping is shared.
+#define S3_X 32            // outputs per CTA in x (16 threads x 2)
+#define S3_Y 16
+template <bool BETA>
+__global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
+                                                          const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
+                                                          float *__restrict__ out, double *__restrict__ partial, StencilW W) {
+  constexpr int TX = S3_X + 4, TY = S3_Y + 4, NT = TX * TY;      // 36 x 20 tile, row pitch 36 floats (8-byte aligned pairs)
+  __shared__ __align__(8) float sm[2][TY][TX];
+  __shared__ double red[8];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int bx = blockIdx.x * S3_X, by = blockIdx.y * S3_Y;
+  const int zc0 = kz0 + blockIdx.z * S2_ZC, zc1 = min(zc0 + S2_ZC, kz1);
+  const int gx = bx + 2 * tx, gy = by + ty;
+  const bool in0 = gx < nx && gy < ny, in1 = gx + 1 < nx && gy < ny;
+  float beta = 0.0f;
+  if (BETA) beta = scal[0];
+  int e_lx[3], e_ly[3]; bool e_ok[3], e_own[3], e_use[3]; i64 e_off[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    int t = tid + q * 256;
+    e_use[q] = t < NT;
+    if (!e_use[q]) t = 0;
+    e_ly[q] = t / TX; e_lx[q] = t % TX;
+    int x = bx + e_lx[q] - 2, y = by + e_ly[q] - 2;
+    e_ok[q] = e_use[q] && x >= 0 && x < nx && y >= 0 && y < ny;
+    e_own[q] = e_ok[q] && e_lx[q] >= 2 && e_lx[q] < TX - 2 && e_ly[q] >= 2 && e_ly[q] < TY - 2;
+    e_off[q] = (i64)y * nx + x;
+  }
+  const i64 pl = (i64)nx * ny;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f;
+  float ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f;
+  double dsum = 0.0;
+  float pv[3];
+  auto fetch = [&](int z) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      float v = 0.0f;
+      if (e_ok[q] && z >= 0 && z < nz) {
+        i64 gi = (i64)z * pl + e_off[q];
+        if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && z >= zc0 && z < zc1) unew[gi] = v; }
+        else v = in[gi];
+      }
+      pv[q] = v;
+    }
+  };
+  fetch(zc0 - 2);
+  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
+    const int buf = (zin - zc0 + 2) & 1;
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      if (e_use[q]) sm[buf][e_ly[q]][e_lx[q]] = pv[q];
+    __syncthreads();
+    if (zin + 1 < zc1 + 2) fetch(zin + 1);
+    float ctra = 0.f, ctrb = 0.f;
+#pragma unroll
+    for (int dj = -2; dj <= 2; dj++) {
+      const float2 *row = reinterpret_cast<const float2 *>(&sm[buf][ty + 2 + dj][2 * tx]);
+      const float2 p0 = row[0], p1 = row[1], p2 = row[2];
+      const float v[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};       // x0-2 .. x0+3
+      if (dj == 0) { ctra = v[2]; ctrb = v[3]; }
+#pragma unroll
+      for (int di = -2; di <= 2; di++) {
+        const int m2 = di * di + dj * dj;
+        if (m2 > 6) continue;
+        const float va = v[di + 2], vb = v[di + 3];
+        a2 = fmaf(W.w[m2], va, a2); b2 = fmaf(W.w[m2], vb, b2);
+        if (m2 + 1 <= 6) { a1 = fmaf(W.w[m2 + 1], va, a1); a3 = fmaf(W.w[m2 + 1], va, a3); b1 = fmaf(W.w[m2 + 1], vb, b1); b3 = fmaf(W.w[m2 + 1], vb, b3); }
+        if (m2 + 4 <= 6) { a0 = fmaf(W.w[m2 + 4], va, a0); a4 = fmaf(W.w[m2 + 4], va, a4); b0 = fmaf(W.w[m2 + 4], vb, b0); b4 = fmaf(W.w[m2 + 4], vb, b4); }
+      }
+    }
+    const int zo = zin - 2;
+    if (zo >= zc0) {
+      const i64 gi = (i64)zo * pl + (i64)gy * nx + gx;
+      if (in0) { out[gi] = a0; dsum += (double)ca0 * (double)a0; }
+      if (in1) { out[gi + 1] = b0; dsum += (double)cb0 * (double)b0; }
+    }
+    a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f; b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0.f;
+    ca0 = ca1; ca1 = ctra; cb0 = cb1; cb1 = ctrb;
+  }
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+  if ((tid & 31) == 0) red[tid >> 5] = dsum;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0; for (int i = 0; i < 8; i++) a += red[i];
+    partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
+  }
+}
 // CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, uc, rr}
 __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restrict__ dst) {
   __shared__ double sh[256];
@@ -214,9 +311,16 @@ __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, co
                                                    float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial) {
   __shared__ double red[8];
   const float alpha = scal[1]; double rr = 0.0;
-  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) {
-    x[v] = x[v] + alpha * u[v]; float rv = r[v] - alpha * c[v]; r[v] = rv;
-    if (v >= o_lo && v < o_hi) rr += (double)rv * (double)rv;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += 4 * stride) {       // 4 independent elements per trip: 16 loads in flight
+    float xv[4], uv[4], rv[4], cv[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { i64 w = v + q * stride; if (w < n) { xv[q] = x[w]; uv[q] = u[w]; rv[q] = r[w]; cv[q] = c[w]; } }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      i64 w = v + q * stride;
+      if (w < n) { x[w] = xv[q] + alpha * uv[q]; float t = rv[q] - alpha * cv[q]; r[w] = t; if (w >= o_lo && w < o_hi) rr += (double)t * (double)t; }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
@@ -242,13 +346,16 @@ __global__ void __launch_bounds__(256) k_dot_self(i64 n, const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------ min / max of a float field
-__global__ void k_minmax(i64 n, const float *__restrict__ a, unsigned *__restrict__ mm) {   // mm[0] = ordered-min, mm[1] = ordered-max
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_minmax(i64 n, const float *__restrict__ a, unsigned *__restrict__ mm) {   // mm[0] = ordered-min, mm[1] = ordered-max
+  __shared__ float rlo[8], rhi[8];
   float lo = INFINITY, hi = -INFINITY;
-  if (v < n) { lo = a[v]; hi = a[v]; }
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) { float x = a[v]; lo = fminf(lo, x); hi = fmaxf(hi, x); }
   for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_down_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_down_sync(0xffffffffu, hi, o)); }
-  if ((threadIdx.x & 31) == 0) {
-    // order-preserving map float -> uint
+  if ((threadIdx.x & 31) == 0) { rlo[threadIdx.x >> 5] = lo; rhi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) { lo = fminf(lo, rlo[i]); hi = fmaxf(hi, rhi[i]); }
+    // order-preserving map float -> uint; one pair of atomics per CTA
     unsigned bl = __float_as_uint(lo), bh = __float_as_uint(hi);
     bl = (bl & 0x80000000u) ? ~bl : (bl | 0x80000000u); bh = (bh & 0x80000000u) ? ~bh : (bh | 0x80000000u);
     atomicMin(&mm[0], bl); atomicMax(&mm[1], bh);
@@ -689,7 +796,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   float *scal = ctx->f_scal.as<float>(); unsigned *ubits = (unsigned *)((char *)ctx->f_scal.p + 64); double *dsc = (double *)((char *)ctx->f_scal.p + 96);
   CK(cudaMemsetAsync(ctx->f_scal.p, 0, 256, st));
   float *s = ctx->f_s.as<float>();
-  k_to_f32<<<cdiv(nown, 256), 256, 0, st>>>(nown, o_lo, ctx->sdf.as<double>(), s + o_lo, ubits); LAUNCH_CHECK();
+  k_to_f32<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, o_lo, ctx->sdf.as<double>(), s + o_lo, ubits); LAUNCH_CHECK();
   if (r2s_allreduce(ctx, ubits, 1, 2)) return 1;                          // global max finite |v| (RBFs4Smoothing.jl:17)
   unsigned hb = 0;
   CK(cudaMemcpyAsync(&hb, ubits, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -699,9 +806,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   if (r2s_halo_exchange_f32(ctx, s, pl, k0, k1, nz, 2, 3)) return 1;
   CK(cudaEventRecord(ctx->ev[5], st));
   // mat-vec kernel: plane-marching (default) or tile-per-CTA (R2S_STENCIL=0, kept for comparison)
-  static const bool march = !(getenv("R2S_STENCIL") && atoi(getenv("R2S_STENCIL")) == 0);
-  dim3 sgrid = march ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z));
-  int sthreads = march ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB);
+  static const int svar = getenv("R2S_STENCIL") ? atoi(getenv("R2S_STENCIL")) : 2;      // 0 tile-per-CTA, 1 plane-marching, 2 plane-marching with 2 outputs/thread
+  const bool march = svar != 0;
+  dim3 sgrid = svar == 2 ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, S2_ZC)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
+  int sthreads = svar == 2 ? 256 : (svar == 1 ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB));
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
@@ -728,7 +836,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
     while (iters < n && !(residual <= tol)) {
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      if (svar == 2) k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      else if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       else k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
@@ -754,14 +863,15 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  if (svar == 2) k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  else if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   else k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
   // LS_Threshold (:265-300)
   unsigned init_mm[2] = {0xffffffffu, 0u};
   CK(cudaMemcpyAsync(ubits + 2, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
-  k_minmax<<<cdiv(nown, 256), 256, 0, st>>>(nown, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
+  k_minmax<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
   if (r2s_group_start(ctx)) return 1;
   if (r2s_allreduce(ctx, ubits + 2, 1, 3)) return 1;
   if (r2s_allreduce(ctx, ubits + 3, 1, 2)) return 1;
