@@ -149,17 +149,33 @@ class Context:
         return r
 
 
-def slab_partition(nz_points, world):
-    """Contiguous z-slabs of coarse planes, one per rank: [(k0, k1), ...] covering [0, nz_points)."""
-    if world < 1 or nz_points < world:
+def slab_partition(nz_points, world, plane_cost=None, min_planes=3):
+    """Contiguous z-slabs of coarse planes, one per rank: [(k0, k1), ...] covering [0, nz_points).
+    Without `plane_cost` the planes are split evenly; with a per-plane cost estimate (any positive array of length nz_points)
+    the cuts equalise the cumulative cost instead (load balancing: the mesh-boundary planes carry the boundary-face work)."""
+    nz_points, world = int(nz_points), int(world)
+    if world < 1 or nz_points < world * (min_planes if world > 1 else 1):
         raise R2SError("cannot cut %d planes into %d slabs" % (nz_points, world))
-    base, rem = divmod(int(nz_points), int(world))
-    out, k = [], 0
-    for r in range(world):
-        n = base + (1 if r < rem else 0)
-        out.append((k, k + n))
-        k += n
-    return out
+    if plane_cost is None:
+        base, rem = divmod(nz_points, world)
+        out, k = [], 0
+        for r in range(world):
+            n = base + (1 if r < rem else 0)
+            out.append((k, k + n))
+            k += n
+        return out
+    c = np.maximum(np.asarray(plane_cost, dtype=np.float64), 1e-12)
+    if c.shape != (nz_points,):
+        raise R2SError("plane_cost must have one entry per plane")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, cum[-1] * r / world))
+        k = max(k, cuts[-1] + min_planes)
+        k = min(k, nz_points - (world - r) * min_planes)
+        cuts.append(k)
+    cuts.append(nz_points)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
 def broadcast_unique_id(make_id, rank, world, group=None):

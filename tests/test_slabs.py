@@ -23,6 +23,19 @@ def test_slab_partition_tiles_the_planes(r2s):
         r2s.slab_partition(2, 4)
 
 
+def test_weighted_slab_partition_equalises_cost(r2s):
+    nz, world = 519, 8
+    cost = np.ones(nz); cost[:12] = 3.0; cost[-12:] = 3.0          # expensive end planes (mesh boundary faces)
+    parts = r2s.slab_partition(nz, world, plane_cost=cost)
+    assert parts[0][0] == 0 and parts[-1][1] == nz and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    loads = [cost[a:b].sum() for a, b in parts]
+    assert max(loads) / (cost.sum() / world) < 1.03
+    assert parts[0][1] - parts[0][0] < parts[3][1] - parts[3][0]  # the end slabs are thinner
+    assert min(b - a for a, b in parts) >= 3
+    uniform = r2s.slab_partition(nz, world, plane_cost=np.ones(nz))
+    assert max(b - a for a, b in uniform) - min(b - a for a, b in uniform) <= 1
+
+
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
