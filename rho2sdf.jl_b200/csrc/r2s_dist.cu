@@ -397,6 +397,20 @@ __device__ inline void boundary_faces_point(const ActRec &r, const TriRec *__res
     }
     double Xt[3][3], Et[3][3], n[3];
     for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; n[d] = T.n[d]; }
+    if (r.cls == 1) {
+      // Solid element: every candidate of this triangle (face, edge or vertex projection) only replaces the running value if it is
+      // strictly smaller, and each of them is at least the distance from x to the triangle's bounding box.  If that bound is not
+      // below the running value the triangle cannot change anything (exact; the margin covers the rounding of the candidates).
+      double lb2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const double lo = fmin(Xt[0][d], fmin(Xt[1][d], Xt[2][d])), hi = fmax(Xt[0][d], fmax(Xt[1][d], Xt[2][d]));
+        const double e = fmax(fmax(lo - x[d], x[d] - hi), 0.0);
+        lb2 = fma(e, e, lb2);
+      }
+      const double cur = fabs(s.c) * (1.0 + 1e-12);
+      if (lb2 * (1.0 - 1e-12) > cur * cur) continue;
+    }
     for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
     triangle_point<WANT_XP, NEN>(Xe, re, rho_t, r.cls == 1, Xt, Et, n, x, s);
   }
