@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="elements per axis of the synthetic HEX8 SIMP field")
-    ap.add_argument("--cpu-n", type=int, default=64, help="replica size for the CPU oracle leg")
+    ap.add_argument("--cpu-n", type=int, default=96, help="replica size for the CPU oracle leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="keep equal plane counts per slab (no cost-based re-cut during warm-up)")
     args = ap.parse_args()
