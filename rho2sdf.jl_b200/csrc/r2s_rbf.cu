@@ -537,6 +537,67 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
 }
+// Whole-grid variant of k_vol_step (bisection steps 1-3 and the final fine-grid volume): a warp owns 31 consecutive cells of
+// one cell row; every lane loads the 4 values of its x-column (coalesced) and takes the neighbouring column's min / max from
+// lane + 1, so a cell costs 4 loads instead of 8 and no div/mod.  Same classification, same integer accumulation.
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th, int *__restrict__ list_out,
+                                                  u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
+  __shared__ int s_cut[8], s_keep[8]; __shared__ int s_base_cut, s_base_keep;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nseg = (nx - 1 + 30) / 31, nrow = (ny - 1) * (kc1 - kc0);
+  const i64 ntask = (i64)nrow * nseg, sxy = (i64)nx * ny;
+  int nfull = 0, nperm = 0;
+  for (i64 base = (i64)blockIdx.x * 8; base < ntask; base += (i64)gridDim.x * 8) {
+    const i64 task = base + warp;
+    bool cut = false, keep = false; int c = 0;
+    float cmn = INFINITY, cmx = -INFINITY; int i = 0, j = 0, k = 0;
+    if (task < ntask) {
+      const int row = (int)(task / nseg), seg = (int)(task % nseg);
+      j = row % (ny - 1); k = kc0 + row / (ny - 1); i = seg * 31 + lane;
+      if (i < nx) {
+        const i64 b = ((i64)k * ny + j) * nx + i;
+        const float v0 = sdf[b], v1 = sdf[b + nx], v2 = sdf[b + sxy], v3 = sdf[b + sxy + nx];
+        cmn = fminf(fminf(v0, v1), fminf(v2, v3)); cmx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+      }
+    }
+    const float nmn = __shfl_down_sync(0xffffffffu, cmn, 1), nmx = __shfl_down_sync(0xffffffffu, cmx, 1);
+    if (task < ntask && lane < 31 && i < nx - 1) {
+      const float mn = fminf(cmn, nmn), mx = fmaxf(cmx, nmx);
+      c = (int)(((i64)k * (ny - 1) + j) * (nx - 1) + i);
+      if (EMIT && mn >= hi) nperm++;
+      else if (EMIT && mx < lo) {}
+      else {
+        keep = EMIT;
+        if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
+      }
+    }
+    unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
+    if (__syncthreads_or((mc | mk) != 0)) {
+      if (lane == 0) { s_cut[warp] = __popc(mc); s_keep[warp] = __popc(mk); }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tc = 0, tk = 0;
+        for (int w = 0; w < 8; w++) { int a = s_cut[w]; s_cut[w] = tc; tc += a; int b2 = s_keep[w]; s_keep[w] = tk; tk += b2; }
+        s_base_cut = tc ? (int)atomicAdd(&acc[1], (u64)tc) : 0;
+        s_base_keep = tk ? (int)atomicAdd(n_out_ptr, (u64)tk) : 0;
+      }
+      __syncthreads();
+      if (cut) { int slot = s_base_cut + s_cut[warp] + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
+      if (keep) list_out[s_base_keep + s_keep[warp] + __popc(mk & ((1u << lane) - 1))] = c;
+      __syncthreads();
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
+  __syncthreads();
+  if (lane == 0) { s_cut[warp] = nfull; s_keep[warp] = nperm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tf = 0, tp = 0; for (int w = 0; w < 8; w++) { tf += s_cut[w]; tp += s_keep[w]; }
+    if (tf) atomicAdd(&acc[0], (u64)tf);
+    if (tp) atomicAdd(&acc[3], (u64)tp);
+  }
+}
 // acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
 __global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red) {
   red[0] = acc[0] + acc[3]; red[1] = acc[1] > (u64)cutcap ? 1 : 0; red[2] = acc[2]; red[3] = 0;
@@ -573,12 +634,14 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
     int *lin = ctx->vlist[in].as<int>(), *lout = ctx->vlist[out].as<int>(); u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
     if (attempt == 0) {
       if (emit) CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
-      if (implicit && !emit) k_vol_step<true, false><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else if (implicit) k_vol_step<true, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      const i64 ntask = (i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31);
+      const int rgrid = (int)std::min<i64>(std::max<i64>(cdiv(ntask, 8), 1), 148 * 16);
+      if (implicit && !emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else if (implicit) k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
       else k_vol_step<false, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lin, nin, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
     } else {
       // the cut list overflowed: it has been grown; re-classify (the retired cells are already accounted for)
-      if (!emit) k_vol_step<true, false><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      if (!emit) k_vol_rows<false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31), 8), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
       else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
     }
     LAUNCH_CHECK();
