@@ -270,11 +270,13 @@ __device__ __forceinline__ void write_value(VoxState &s, double dt, const double
 }
 // IsProjectedOnFullSegment (:78-119)
 template <bool WANT_XP, int NEN>
-__device__ inline bool projected_on_full_segment(const double Xe[3][NEN], const double re[NEN], double rho_t, const double xp[3], const double x[3], VoxState &s) {
+__device__ inline bool projected_on_full_segment(const double Xe[3][NEN], const double re[NEN], double rho_t, const double xp[3], const double x[3], VoxState &s,
+                                                 const ex::AffineInv *pre = nullptr) {
   double rho;
   if (NEN == 8) {
     double xi[3], N[8];
-    ex::inverse_map_hex8((const double(*)[8])Xe, xp, xi);
+    if (pre && pre->affine) ex::affine_inverse_apply(*pre, xp, xi);      // same arithmetic as the general path on an affine element
+    else ex::inverse_map_hex8((const double(*)[8])Xe, xp, xi);
     if (!(ex::max3abs(xi[0], xi[1], xi[2]) < 1.001)) return false;
     ex::hex8_shape(xi, N);
     rho = ex::dot8(N, re);
@@ -291,7 +293,7 @@ __device__ inline bool projected_on_full_segment(const double Xe[3][NEN], const 
 // process_triangle_projection! (:628-815) for one grid point
 template <bool WANT_XP, int NEN>
 __device__ inline void triangle_point(const double Xe[3][NEN], const double re[NEN], double rho_t, bool solid, const double Xt[3][3], const double Et[3][3],
-                                      const double n[3], const double x[3], VoxState &s) {
+                                      const double n[3], const double x[3], VoxState &s, const ex::AffineInv *pre = nullptr) {
   double lam[3]; ex::barycentric(Xt[0], Xt[1], Xt[2], n, x, lam);
   double xp[3]; bool ok = false;
   double lmin = lam[0]; if (lam[1] < lmin) lmin = lam[1]; if (lam[2] < lmin) lmin = lam[2];
@@ -300,7 +302,7 @@ __device__ inline void triangle_point(const double Xe[3][NEN], const double re[N
     for (int d = 0; d < 3; d++) xp[d] = ex::add(ex::add(ex::mul(lam[0], Xt[0][d]), ex::mul(lam[1], Xt[1][d])), ex::mul(lam[2], Xt[2][d]));
     double dt = ex::norm3(ex::sub(x[0], xp[0]), ex::sub(x[1], xp[1]), ex::sub(x[2], xp[2]));
     if (solid) { if (fabs(dt) < fabs(s.c)) { write_value<WANT_XP>(s, dt, xp); ok = true; } }
-    else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+    else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s, pre);
   } else {
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -313,7 +315,7 @@ __device__ inline void triangle_point(const double Xe[3][NEN], const double re[N
         for (int d = 0; d < 3; d++) xp[d] = ex::add(Xt[j][d], ex::mul(u[d], P));
         double dt = ex::norm3(ex::sub(x[0], xp[0]), ex::sub(x[1], xp[1]), ex::sub(x[2], xp[2]));
         if (solid) { if (fabs(dt) < fabs(s.c)) { write_value<WANT_XP>(s, dt, xp); ok = true; } }
-        else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+        else ok = projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s, pre);
       }
     }
   }
@@ -326,7 +328,7 @@ __device__ inline void triangle_point(const double Xe[3][NEN], const double re[N
 #pragma unroll
     for (int d = 0; d < 3; d++) xp[d] = idx == 0 ? Xt[0][d] : (idx == 1 ? Xt[1][d] : Xt[2][d]);
     if (solid) write_value<WANT_XP>(s, dmin, xp);
-    else projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s);
+    else projected_on_full_segment<WANT_XP, NEN>(Xe, re, rho_t, xp, x, s, pre);
   }
 }
 // Boundary-face triangles (process_boundary_faces! :489-558): every boundary face of an active element is split into nsn
@@ -433,6 +435,13 @@ __global__ void __launch_bounds__(128) k_faces_crossing(i64 nact, const ActRec *
   if (r.cls != 2 || !r.fmask) return;
   double Xe[3][NEN], re[NEN];
   for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; re[q] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
+  ex::AffineInv pre; pre.affine = 0;
+  if (NEN == 8) {      // element-only part of the inverse map, once per warp instead of once per candidate
+    double A[3][8];
+#pragma unroll
+    for (int d = 0; d < 3; d++) ex::mono8((const double *)Xe[d], A[d]);
+    ex::affine_inverse_prepare(A, pre);
+  }
   const int ntri = __popc((unsigned)r.fmask) * NSN;
   const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2], vol = nx * ny * nz;
   for (int li = lane; li < vol; li += 32) {
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(128) k_faces_crossing(i64 nact, const ActRec *
       double Xt[3][3], Et[3][3], n[3];
       for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; n[d] = T.n[d]; }
       for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
-      triangle_point<false, NEN>(Xe, re, rho_t, false, Xt, Et, n, x, s);
+      triangle_point<false, NEN>(Xe, re, rho_t, false, Xt, Et, n, x, s, &pre);
     }
     if (s.c != -R2S_BIG) {
       const i64 idx = r.pair_off + li;

@@ -97,6 +97,35 @@ __device__ inline bool inverse_map_hex8(const double Xe[3][8], const double x[3]
   for (int d = 0; d < 3; d++) { mono8(Xe[d], A[d]); if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false; }
   return inverse_map_hex8_mono(A, affine, x, xi);
 }
+// Per-element data of the inverse map for AFFINE hexes (parallelepipeds: all mixed monomial coefficients are exactly zero).
+// The Newton iteration of inverse_map_hex8_mono from xi = 0 is then exact after one step, and everything in that step except
+// the right-hand side depends on the element only: a0 (image of the element centre), the cofactors of J and det J.  prepare()
+// evaluates them with the very same operations as the general path, apply() finishes the step for one point: 3 subtractions,
+// 9 multiplications, 6 additions, 3 divisions -- bit-identical to inverse_map_hex8 on an affine element.
+struct AffineInv { double a0[3]; double c[9]; double det; int affine; int pad; };
+__device__ inline void affine_inverse_prepare(const double A[3][8], AffineInv &S) {
+  bool affine = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
+  S.affine = affine ? 1 : 0; S.pad = 0;
+  double J[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) { S.a0[d] = A[d][0]; J[d][0] = A[d][1]; J[d][1] = A[d][2]; J[d][2] = A[d][3]; }
+  S.c[0] = sub(mul(J[1][1], J[2][2]), mul(J[1][2], J[2][1])); S.c[1] = sub(mul(J[1][2], J[2][0]), mul(J[1][0], J[2][2])); S.c[2] = sub(mul(J[1][0], J[2][1]), mul(J[1][1], J[2][0]));
+  S.det = add(add(mul(J[0][0], S.c[0]), mul(J[0][1], S.c[1])), mul(J[0][2], S.c[2]));
+  S.c[3] = sub(mul(J[0][2], J[2][1]), mul(J[0][1], J[2][2])); S.c[4] = sub(mul(J[0][0], J[2][2]), mul(J[0][2], J[2][0])); S.c[5] = sub(mul(J[0][1], J[2][0]), mul(J[0][0], J[2][1]));
+  S.c[6] = sub(mul(J[0][1], J[1][2]), mul(J[0][2], J[1][1])); S.c[7] = sub(mul(J[0][2], J[1][0]), mul(J[0][0], J[1][2])); S.c[8] = sub(mul(J[0][0], J[1][1]), mul(J[0][1], J[1][0]));
+}
+__device__ __forceinline__ bool affine_inverse_apply(const AffineInv &S, const double x[3], double xi[3]) {
+  if (!(fabs(S.det) > 0.0)) { xi[0] = xi[1] = xi[2] = 10.0; return false; }
+  const double r0 = sub(S.a0[0], x[0]), r1 = sub(S.a0[1], x[1]), r2 = sub(S.a0[2], x[2]);
+  const double d0 = dvd(add(add(mul(S.c[0], r0), mul(S.c[3], r1)), mul(S.c[6], r2)), S.det);
+  const double d1 = dvd(add(add(mul(S.c[1], r0), mul(S.c[4], r1)), mul(S.c[7], r2)), S.det);
+  const double d2 = dvd(add(add(mul(S.c[2], r0), mul(S.c[5], r1)), mul(S.c[8], r2)), S.det);
+  xi[0] = sub(0.0, d0); xi[1] = sub(0.0, d1); xi[2] = sub(0.0, d2);
+  if (!(max3abs(d0, d1, d2) < 1.0e3) || !(max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) { xi[0] = xi[1] = xi[2] = 10.0; return false; }
+  return true;
+}
 // TET4: FindLocalCoordinates.jl:110-149 (adjugate solve), returns validity per ElementTypes.jl:104-106
 __device__ inline bool inverse_map_tet4(const double Xe[3][4], const double x[3], double lc[3]) {
   double A[3][3], b[3];

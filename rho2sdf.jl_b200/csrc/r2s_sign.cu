@@ -12,13 +12,7 @@
 struct SRange { int a[3], b[3]; int hot, pad; };   // inclusive grid-point index range of the candidate points of one element;
                                                    // hot = some nodal density >= rho_t (HEX8 skip rule, SignDetection.jl:36)
 
-// Per-element data of the inverse isoparametric map for AFFINE hexes (parallelepipeds: all mixed monomial coefficients are
-// exactly zero).  The Newton iteration from xi = 0 (r2s_exact.cuh: inverse_map_hex8_mono) is then exact after one step, and
-// everything in that step except the right-hand side depends on the element only: a0 (image of the element centre), the
-// cofactors of J and det J.  They are computed once per element with the very same operations, so a lane evaluates a
-// candidate with 3 subtractions, 9 multiplications, 6 additions and 3 divisions instead of 32 gathers and ~250 operations --
-// bit-identical to the general path.
-struct SignEl { double a0[3]; double c[9]; double det; int affine; int pad; };
+typedef ex::AffineInv SignEl;      // per-element affine inverse-map data (r2s_exact.cuh)
 __device__ __forceinline__ int tet_cell_index(double x, double amin, double cell, int n1) {   // point_to_grid_index :256-268 (1-based, clamped)
   int idx = (int)floor(ex::dvd(ex::sub(x, amin), cell)) + 1;
   return max(1, min(n1, idx));
@@ -55,22 +49,13 @@ __global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, con
   if (!ok) { r.a[0] = 1; r.b[0] = 0; }
   rng[e] = r;
   if (nen == 8 && ok) {      // only elements with candidate points in this slab
-    using namespace ex;
-    double A[3][8]; bool affine = true;
+    double A[3][8];
     for (int d = 0; d < 3; d++) {
       double v[8];
       for (int a = 0; a < 8; a++) v[a] = X[3 * (i64)IEN[8 * e + a] + d];
-      mono8(v, A[d]);
-      if (A[d][4] != 0.0 || A[d][5] != 0.0 || A[d][6] != 0.0 || A[d][7] != 0.0) affine = false;
+      ex::mono8(v, A[d]);
     }
-    SignEl S; S.affine = affine ? 1 : 0; S.pad = 0;
-    // first Newton step at xi = 0: val = a0, J[d][c] = A[d][1 + c] (the products with xi = 0 vanish)
-    double J[3][3];
-    for (int d = 0; d < 3; d++) { S.a0[d] = A[d][0]; J[d][0] = A[d][1]; J[d][1] = A[d][2]; J[d][2] = A[d][3]; }
-    S.c[0] = sub(mul(J[1][1], J[2][2]), mul(J[1][2], J[2][1])); S.c[1] = sub(mul(J[1][2], J[2][0]), mul(J[1][0], J[2][2])); S.c[2] = sub(mul(J[1][0], J[2][1]), mul(J[1][1], J[2][0]));
-    S.det = add(add(mul(J[0][0], S.c[0]), mul(J[0][1], S.c[1])), mul(J[0][2], S.c[2]));
-    S.c[3] = sub(mul(J[0][2], J[2][1]), mul(J[0][1], J[2][2])); S.c[4] = sub(mul(J[0][0], J[2][2]), mul(J[0][2], J[2][0])); S.c[5] = sub(mul(J[0][1], J[2][0]), mul(J[0][0], J[2][1]));
-    S.c[6] = sub(mul(J[0][1], J[1][2]), mul(J[0][2], J[1][1])); S.c[7] = sub(mul(J[0][2], J[1][0]), mul(J[0][0], J[1][2])); S.c[8] = sub(mul(J[0][0], J[1][1]), mul(J[0][1], J[1][0]));
+    SignEl S; ex::affine_inverse_prepare(A, S);
     sel[e] = S;
   }
   ntile[e] = ok ? (i64)(r.b[0] / TILE_X - r.a[0] / TILE_X + 1) * (r.b[1] / TILE_Y - r.a[1] / TILE_Y + 1) * (r.b[2] / TILE_Z - r.a[2] / TILE_Z + 1) : 0;
@@ -178,18 +163,8 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
         if (NEN == 8) {
           double xi[3];
           const SignEl &S = sel[e];
-          if (S.affine) {
-            using namespace ex;
-            if (!(fabs(S.det) > 0.0)) { xi[0] = xi[1] = xi[2] = 10.0; }
-            else {
-              const double r0 = sub(S.a0[0], x[0]), r1 = sub(S.a0[1], x[1]), r2 = sub(S.a0[2], x[2]);
-              const double d0 = dvd(add(add(mul(S.c[0], r0), mul(S.c[3], r1)), mul(S.c[6], r2)), S.det);
-              const double d1 = dvd(add(add(mul(S.c[1], r0), mul(S.c[4], r1)), mul(S.c[7], r2)), S.det);
-              const double d2 = dvd(add(add(mul(S.c[2], r0), mul(S.c[5], r1)), mul(S.c[8], r2)), S.det);
-              xi[0] = sub(0.0, d0); xi[1] = sub(0.0, d1); xi[2] = sub(0.0, d2);
-              if (!(max3abs(d0, d1, d2) < 1.0e3) || !(max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) { xi[0] = xi[1] = xi[2] = 10.0; }
-            }
-          } else {
+          if (S.affine) ex::affine_inverse_apply(S, x, xi);
+          else {
             double A[3][8];
 #pragma unroll
             for (int d = 0; d < 3; d++) {      // one coordinate at a time: only the monomial coefficients stay live
