@@ -110,6 +110,18 @@ int r2s_comm_destroy(r2s_ctx *ctx);
  * fine_slab[(kf1-kf0)*f0*f1], kf0 = smooth*k0, kf1 = smooth*k1 (the last slab also owns the final fine plane) */
 int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep);
 
+/* ---- grid set-up statistics: calculate_edge_distances + analyze_mesh (src/MeshGrid/Grid_setup.jl:28-92) ---------------------- */
+/* median / shortest / longest element edge; the median is the grid step of noninteractive_sdf_grid_setup (:94-109) */
+int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double *longest);
+
+/* ---- result export: exportSdfToVTI (src/DataExport/ExportToVTI.jl:22-67) ----------------------------------------------- */
+/* VTK ImageData (.vti), one PointData scalar `label` ("distance" in rho2sdf, RhoToSDF.jl:267-273), raw appended block.
+ * r2s_export_vti streams a device-resident result (which = 0: sdf_dists Float64 on the coarse grid, 1: fine_sdf Float32 on the
+ * grid N*smooth+1) chunk by chunk; r2s_write_vti_host writes a host array (x fastest) and needs no context or GPU. */
+int r2s_export_vti(r2s_ctx *ctx, const char *path, const char *label, int which);
+int r2s_write_vti_host(const char *path, const char *label, const void *values, int is_f64, int64_t nx, int64_t ny, int64_t nz, const double origin[3],
+                       const double spacing[3]);
+
 /* ---- measurement helper (bench.py): FMA-pipe peak of the device in TFLOP/s, fp64 != 0 -> double, else float -------- */
 int r2s_measure_fma_peak(r2s_ctx *ctx, int fp64, double *tflops);
 

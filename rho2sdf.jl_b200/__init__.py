@@ -24,7 +24,7 @@ import numpy as np
 __all__ = ["HEX8", "TET4", "Rho2sdfOptions", "Mesh", "Grid", "getMesh_AABB", "generateGridPoints", "noninteractive_sdf_grid_setup",
            "DenseInNodes", "find_threshold_for_volume", "calculate_isocontour_volume", "evalDistances", "Sign_Detection",
            "remove_sdf_artifacts", "RBFs_smoothing", "calculate_volume_from_sdf", "rho2sdf", "rho2sdf_hex8", "rho2sdf_tet4",
-           "FineGrid", "R2SError", "slab_partition", "init_slab_comm", "broadcast_unique_id", "load_library", "library_path", "Params", "Report", "Context"]
+           "exportSdfToVTI", "export_device_result_to_vti", "read_vti", "FineGrid", "R2SError", "slab_partition", "init_slab_comm", "broadcast_unique_id", "load_library", "library_path", "Params", "Report", "Context"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -104,6 +104,9 @@ def load_library():
     L.r2s_comm_unique_id.argtypes = [vp]
     L.r2s_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.r2s_comm_destroy.argtypes = [vp]
+    L.r2s_edge_length_stats.argtypes = [vp, dp, dp, dp]
+    L.r2s_export_vti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.r2s_write_vti_host.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, vp]
     L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]
     _LIB = L
     return L
@@ -283,12 +286,13 @@ class Mesh:
 
 
 def noninteractive_sdf_grid_setup(mesh):
-    """src/MeshGrid/Grid_setup.jl:94-109: grid step = median element edge length."""
+    """src/MeshGrid/Grid_setup.jl:94-109: grid step = median element edge length (edge lengths, sort and median on the device)."""
     Xmin, Xmax = getMesh_AABB(mesh.X)
-    P = mesh.X[mesh.IEN - 1]                                  # (nel, nen, 3)
-    d = np.stack([np.sqrt(((P[:, b] - P[:, a]) ** 2).sum(axis=1)) for a, b in mesh.edges], axis=0)   # (noe, nel) like `distances`
-    B = float(np.median(d.ravel()))
-    N_new = int(math.floor(np.max(Xmax - Xmin) / B))
+    c = mesh.ctx
+    med, lo, hi = C.c_double(), C.c_double(), C.c_double()
+    c.check(c.lib.r2s_edge_length_stats(c.h, C.byref(med), C.byref(lo), C.byref(hi)))
+    mesh.edge_stats = {"median": med.value, "shortest": lo.value, "longest": hi.value}
+    N_new = int(math.floor(np.max(Xmax - Xmin) / med.value))
     return Grid(Xmin, Xmax, N_new, 3)
 
 
@@ -422,6 +426,54 @@ def calculate_volume_from_sdf(fine_sdf, fine_grid, iso_threshold=0.0, detailed_q
     v = C.c_double()
     c.check(c.lib.r2s_volume_from_sdf(c.h, _ptr(a), nx, ny, nz, float(edge), float(iso_threshold), C.byref(v)))
     return np.float32(v.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DataExport
+# ---------------------------------------------------------------------------------------------------------------------
+def exportSdfToVTI(filename, grid, values, value_label, smooth=None):
+    """src/DataExport/ExportToVTI.jl:22-67: VTK ImageData with dims N*smooth+1, origin AABB_min, spacing cell_size/smooth and one
+    point scalar `value_label`.  `values` is a host array (float32 or float64, x fastest); ".vti" is appended if missing."""
+    sm = 1 if smooth is None else int(smooth)
+    dims = [int(v) * sm + 1 for v in grid.N]
+    a = np.ascontiguousarray(values)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    if a.size != dims[0] * dims[1] * dims[2]:
+        raise R2SError("Values vector length (%d) doesn't match grid dimensions (%d)." % (a.size, dims[0] * dims[1] * dims[2]))   # :44-46
+    path = filename if filename.endswith(".vti") else filename + ".vti"
+    origin = _f64(grid.AABB_min)
+    spacing = _f64([grid.cell_size / sm] * 3)
+    rc = load_library().r2s_write_vti_host(path.encode(), str(value_label).encode(), _ptr(a), int(a.dtype == np.float64), dims[0], dims[1], dims[2], _ptr(origin), _ptr(spacing))
+    if rc != 0:
+        raise R2SError("exportSdfToVTI: cannot write %s (code %d)" % (path, rc))
+    return path
+
+
+def export_device_result_to_vti(mesh, filename, value_label="distance", fine=True):
+    """Stream the device-resident result of the last pipeline call (fine_sdf, or sdf_dists with fine=False) to a .vti file."""
+    path = filename if filename.endswith(".vti") else filename + ".vti"
+    c = mesh.ctx
+    c.check(c.lib.r2s_export_vti(c.h, path.encode(), str(value_label).encode(), 1 if fine else 0))
+    return path
+
+
+def read_vti(path):
+    """Minimal reader of the files written above (tests / round trips): returns (dims, origin, spacing, label, array[k, j, i])."""
+    import re
+    raw = open(path, "rb").read()
+    cut = raw.index(b'<AppendedData encoding="raw">')
+    head = raw[:cut].decode()
+    ext = [int(v) for v in re.search(r'WholeExtent="([^"]+)"', head).group(1).split()]
+    dims = (ext[1] + 1, ext[3] + 1, ext[5] + 1)
+    origin = [float(v) for v in re.search(r'Origin="([^"]+)"', head).group(1).split()]
+    spacing = [float(v) for v in re.search(r'Spacing="([^"]+)"', head).group(1).split()]
+    typ, label = re.search(r'<DataArray type="(\w+)" Name="([^"]+)"', head).groups()
+    start = raw.index(b"_", cut) + 1
+    nbytes = int(np.frombuffer(raw[start:start + 8], dtype="<u8")[0])
+    dt = np.dtype("<f8" if typ == "Float64" else "<f4")
+    data = np.frombuffer(raw[start + 8:start + 8 + nbytes], dtype=dt)
+    return dims, origin, spacing, label, data.reshape(dims[2], dims[1], dims[0])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -286,3 +286,46 @@ int r2s_dev_isocontour_volume(r2s_ctx *ctx, double thr, double *vol) {
   *vol = h;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ grid set-up statistics
+// calculate_edge_distances + analyze_mesh (MeshGrid/Grid_setup.jl:28-92): the lengths of all element edges and their
+// median, which is the grid step of the :automatic set-up (noninteractive_sdf_grid_setup, :94-109).  Edge tables:
+// ElementTypes.jl:30-35 (HEX8) and :63-66 (TET4).  sqrt(dx^2 + dy^2 + dz^2) without contraction, like the Julia expression.
+__constant__ int c_edges_hex[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+__constant__ int c_edges_tet[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+__global__ void k_edge_lengths(i64 nel, int nen, int noe, const int *__restrict__ IEN, const double *__restrict__ X, double *__restrict__ out) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= nel * noe) return;
+  i64 e = t / noe; int q = (int)(t % noe);
+  int a = nen == 8 ? c_edges_hex[q][0] : c_edges_tet[q][0], b = nen == 8 ? c_edges_hex[q][1] : c_edges_tet[q][1];
+  i64 na = IEN[nen * e + a], nb = IEN[nen * e + b];
+  double dx = __dsub_rn(X[3 * nb], X[3 * na]), dy = __dsub_rn(X[3 * nb + 1], X[3 * na + 1]), dz = __dsub_rn(X[3 * nb + 2], X[3 * na + 2]);
+  out[t] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+extern "C" int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double *longest) {
+  if (!ctx) return 1;
+  if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
+  CK(cudaSetDevice(ctx->device));
+  const int noe = ctx->nen == 8 ? 12 : 6; const i64 n = ctx->nel * noe;
+  if (n >= (1ll << 31)) FAIL("r2s_edge_length_stats: too many edges for one sort");
+  DevBuf a, b;
+  CK(a.reserve(sizeof(double) * (size_t)n)); CK(b.reserve(sizeof(double) * (size_t)n));
+  k_edge_lengths<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, noe, ctx->IEN32.as<int>(), ctx->X.as<double>(), a.as<double>()); LAUNCH_CHECK();
+  double *sorted = nullptr;
+  int rc = r2s_sort_f64(ctx, a.as<double>(), b.as<double>(), n, &sorted);
+  double h[4] = {0, 0, 0, 0};
+  if (!rc) {
+    // Julia's median: middle element, or the mean of the two middle elements for an even count
+    cudaMemcpyAsync(&h[0], sorted, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&h[1], sorted + (n - 1), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&h[2], sorted + (n - 1) / 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&h[3], sorted + n / 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = 1;
+  }
+  a.release(); b.release();
+  if (rc) FAIL("r2s_edge_length_stats: sort failed");
+  if (shortest) *shortest = h[0];
+  if (longest) *longest = h[1];
+  if (median) *median = (n % 2) ? h[2] : (h[2] + h[3]) / 2;
+  return 0;
+}

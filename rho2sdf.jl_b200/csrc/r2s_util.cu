@@ -30,6 +30,18 @@ int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64
   return 0;
 }
 
+// sorts n doubles ascending (used by the edge-length median of the grid set-up)
+int r2s_sort_f64(r2s_ctx *ctx, double *keys, double *alt, i64 n, double **sorted) {
+  cub::DoubleBuffer<double> db(keys, alt);
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, db, (int)n, 0, 64, ctx->stream));
+  CK(ctx->cubtmp.reserve(tmp));
+  CK(cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, tmp, db, (int)n, 0, 64, ctx->stream));
+  ctx->launches += 9;
+  *sorted = db.Current();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ roofline denominators
 // FMA-pipe peak measured on the device the context drives: 8 independent FMA chains per thread, enough CTAs to fill
 // every SM.  MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only; the iso-projection kernel is FP64-FMA bound

@@ -136,6 +136,10 @@ def test_mat_fixtures_full_path(r2s, name):
     mesh = r2s.Mesh(X, IEN, rho)
     grid = r2s.noninteractive_sdf_grid_setup(mesh)
     assert list(grid.N) == ([66, 26, 10] if name.startswith("cant") else [25, 44, 64])
+    # calculate_edge_distances / analyze_mesh (Grid_setup.jl:28-92): device median == numpy median of the same expression, bit for bit
+    P = X[IEN - 1]
+    d = np.stack([np.sqrt((P[:, b, 0] - P[:, a, 0]) ** 2 + (P[:, b, 1] - P[:, a, 1]) ** 2 + (P[:, b, 2] - P[:, a, 2]) ** 2) for a, b in mesh.edges])
+    assert mesh.edge_stats["median"] == float(np.median(d)) and mesh.edge_stats["shortest"] == d.min() and mesh.edge_stats["longest"] == d.max()
     vd, vf = oracle.mesh_volume(X, IEN, rho)
     # the volumes are sums over elements: order of summation differs (the reference itself accumulates with atomics, MeshVolume.jl:24-40)
     assert isapprox(mesh.V_domain, vd, rtol=1e-12) and isapprox(mesh.V_frac, vf, rtol=1e-12)
