@@ -114,6 +114,21 @@ function RBFs_smoothing(mesh::Mesh, dist::Vector{Float64}, my_grid::Grid, Is_int
   return fine, fine_grid_of(my_grid, smooth)
 end
 
+# ---- src/DataExport/ExportToVTI.jl:22-67 (SURVEY 8f-1): host array -> .vti; `export_device_vti` streams the device-resident result ---
+function exportSdfToVTI(filename::String, grid::Grid, values::Vector{<:AbstractFloat}, value_label::String, smooth::Union{Int,Nothing}=nothing)
+  sm = isnothing(smooth) ? 1 : smooth
+  dims = Int.(grid.N .* sm .+ 1)
+  length(values) == prod(dims) || error("Values vector length ($(length(values))) doesn't match grid dimensions ($(prod(dims))).")
+  vals = eltype(values) == Float32 ? values : Float64.(values)
+  path = endswith(filename, ".vti") ? filename : filename * ".vti"
+  rc = ccall((:r2s_write_vti_host, LIB), Cint, (Cstring, Cstring, Ptr{Cvoid}, Cint, Int64, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+             path, value_label, vals, eltype(vals) == Float64, dims[1], dims[2], dims[3], Float64.(grid.AABB_min), fill(grid.cell_size / sm, 3))
+  rc == 0 || error("exportSdfToVTI: cannot write $path (code $rc)")
+  return path
+end
+export_device_vti(mesh::Mesh, filename::String; label::String="distance", fine::Bool=true) =
+  (c = context(mesh); check(c, ccall((:r2s_export_vti, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Cint), c.h, filename, label, fine ? 1 : 0)); filename)
+
 # ---- src/RhoToSDF.jl:116-242: same preamble as the reference, the timed region (:164-227) is ONE library call ---------------
 function rho2sdf(taskName::String, X::Vector{Vector{Float64}}, IEN::Vector{Vector{Int64}}, rho::Vector{Float64}; options::Rho2sdfOptions=Rho2sdfOptions())
   element_type = options.element_type
