@@ -300,6 +300,7 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   if (r2s_dev_rbf(ctx, p->rbf_interp, p->smooth, p->rbf_cut, p->target_volume, p->final_volume != 0, &th, &vol)) return 1;
   CK(cudaEventRecord(ctx->ev[12], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_p2p_check(ctx)) return 1;
   ctx->rep.th = th; ctx->rep.volume = vol;
   CK(cudaEventElapsedTime(&ctx->rep.ms_sign, ctx->ev[9], ctx->ev[10]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_cc, ctx->ev[10], ctx->ev[11]));

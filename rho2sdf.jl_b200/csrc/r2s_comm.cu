@@ -9,7 +9,10 @@
 // a process that already has NCCL loaded (torch) the same library instance is reused.  The host program only has to carry
 // the 128-byte ncclUniqueId from rank 0 to the other ranks (torch.distributed broadcast / MPI / a file).
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "r2s_common.cuh"
 
 typedef struct { char internal[128]; } nccl_uid;
@@ -31,6 +34,8 @@ struct NcclApi {
   const char *(*GetErrorString)(int);
 };
 static NcclApi g_nccl;
+static int p2p_setup(r2s_ctx *ctx);
+static void p2p_teardown(r2s_ctx *ctx);
 static const char *nccl_load() {
   if (g_nccl.lib) return nullptr;
   const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
@@ -72,11 +77,11 @@ extern "C" int r2s_comm_init(r2s_ctx *ctx, int rank, int nranks, const void *id1
   nccl_comm c = nullptr;
   NCK(g_nccl.CommInitRank(&c, nranks, id, rank));
   ctx->comm = c; ctx->rank = rank; ctx->nranks = nranks;
-  return 0;
+  return p2p_setup(ctx);
 }
 extern "C" int r2s_comm_destroy(r2s_ctx *ctx) {
   if (!ctx) return 1;
-  if (ctx->comm && g_nccl.lib) { cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy((nccl_comm)ctx->comm); }
+  if (ctx->comm && g_nccl.lib) { cudaStreamSynchronize(ctx->stream); p2p_teardown(ctx); g_nccl.CommDestroy((nccl_comm)ctx->comm); }
   ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1;
   return 0;
 }
@@ -85,8 +90,10 @@ extern "C" int r2s_comm_destroy(r2s_ctx *ctx) {
 int r2s_group_start(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupStart()); return 0; }
 int r2s_group_end(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupEnd()); return 0; }
 // ---- collectives used by the pipeline; all are no-ops for a single rank ----------------------------------------------
+static int p2p_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind);
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/) {
   if (ctx->nranks <= 1) return 0;
+  if (ctx->p2p && count <= 4) return p2p_allreduce(ctx, buf, count, kind);
   int dt = kind == 0 ? NC_F64 : (kind == 1 || kind == 4 ? NC_UINT64 : NC_UINT32);
   int op = (kind == 0 || kind == 1) ? NC_SUM : (kind == 3 ? NC_MIN : NC_MAX);
   NCK(g_nccl.AllReduce(buf, buf, count, dt, op, (nccl_comm)ctx->comm, ctx->stream));
@@ -118,5 +125,219 @@ int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k
   }
   NCK(g_nccl.GroupEnd());
   ctx->collectives++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ peer-memory fast path
+// NCCL costs 20-40 us per call even for 8 bytes; the CG needs two scalar all-reduces and one halo exchange per iteration and
+// the threshold search one all-reduce per bisection, so at 8 GPUs those latencies were ~25 % of the step.  Here every rank
+// owns a small MAILBOX in device memory that all peers map through CUDA IPC:
+//   slots[parity][rank][8]  (8-byte words: 4 values, 1 sequence number)   and   halo flags[parity][2]
+// All-reduce #s: one 64-thread kernel -- thread p stores this rank's values into slot[s&1][rank] of peer p's mailbox, fences
+// (system scope) and stores s; then thread p spins on the local slot[s&1][p] until it carries s; thread 0 combines the R
+// contributions IN RANK ORDER (deterministic, identical on every rank).  Two parities make it safe for a fast rank to start
+// call s+1 while a slow one still combines call s (call s+2 cannot start before everybody finished call s).  The CG halo
+// planes of c are written straight into the neighbours' c arrays (also IPC-mapped) followed by a flag; the consumer waits for
+// both neighbours' flags in a one-warp kernel before its update kernel starts.  Spins are bounded: a timeout raises an error
+// flag instead of hanging the GPU.  R2S_P2P=0 falls back to NCCL for everything.
+#define P2P_SLOT_WORDS 8
+#define P2P_MAX_SPIN (1u << 28)
+struct P2PBox {
+  unsigned long long slot[2][64][P2P_SLOT_WORDS];
+  unsigned long long halo_flag[2][2];      // [parity][0 = from lower neighbour, 1 = from upper neighbour]
+  unsigned long long error;
+  unsigned long long halo_count[2];        // CTA completion counters of the put kernel
+};
+__global__ void k_p2p_allreduce(P2PBox *mine, P2PBox *const *peers, int rank, int R, unsigned seq, unsigned long long *vals, int n, int kind) {
+  const int p = threadIdx.x, par = seq & 1;
+  if (p < R) {
+    volatile unsigned long long *dst = peers[p]->slot[par][rank];
+    for (int i = 0; i < n; i++) dst[i] = vals[i];
+    __threadfence_system();
+    dst[P2P_SLOT_WORDS - 1] = (unsigned long long)seq;
+  }
+  if (p < R) {
+    volatile unsigned long long *src = mine->slot[par][p];
+    unsigned spin = 0;
+    while (src[P2P_SLOT_WORDS - 1] != (unsigned long long)seq) { if (++spin > P2P_MAX_SPIN) { mine->error = 1; break; } }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (p == 0) {
+    for (int i = 0; i < n; i++) {
+      volatile unsigned long long *s0 = mine->slot[par][0];
+      unsigned long long acc = s0[i];
+      for (int q = 1; q < R; q++) {
+        unsigned long long v = ((volatile unsigned long long *)mine->slot[par][q])[i];
+        if (kind == 0) acc = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc) + __longlong_as_double((long long)v));
+        else if (kind == 1) acc += v;
+        else if (kind == 3) acc = v < acc ? v : acc;
+        else acc = v > acc ? v : acc;                      // kinds 2, 4: max
+      }
+      vals[i] = acc;
+    }
+  }
+}
+// 32-bit kinds (2, 3) travel as zero-extended 64-bit words
+__global__ void k_p2p_widen(const unsigned *in, unsigned long long *out, int n) { if ((int)threadIdx.x < n) out[threadIdx.x] = in[threadIdx.x]; }
+__global__ void k_p2p_narrow(const unsigned long long *in, unsigned *out, int n) { if ((int)threadIdx.x < n) out[threadIdx.x] = (unsigned)in[threadIdx.x]; }
+
+static int p2p_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind) {
+  P2PBox *mine = (P2PBox *)ctx->p2p_box;
+  unsigned long long *stage = (unsigned long long *)((char *)ctx->p2p_box + sizeof(P2PBox));      // 4 words behind the mailbox
+  const unsigned seq = ++ctx->p2p_seq;
+  if (kind == 2 || kind == 3) {
+    k_p2p_widen<<<1, 32, 0, ctx->stream>>>((const unsigned *)buf, stage, (int)count);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, stage, (int)count, kind);
+    k_p2p_narrow<<<1, 32, 0, ctx->stream>>>(stage, (unsigned *)buf, (int)count);
+  } else {
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, (unsigned long long *)buf, (int)count, kind);
+  }
+  CK(cudaGetLastError());
+  ctx->p2p_ops++;
+  return 0;
+}
+
+// exchange one IPC handle per rank through NCCL and open the peers' allocations
+static int p2p_open_all(r2s_ctx *ctx, void *local, void **peer_out /*[nranks]*/, const int *want /*ranks to open, -1 terminated*/) {
+  // the all-gather below is collective: a rank whose own step fails still takes part and reports the failure afterwards
+  cudaIpcMemHandle_t h; memset(&h, 0, sizeof(h));
+  bool bad = cudaIpcGetMemHandle(&h, local) != cudaSuccess;
+  const int R = ctx->nranks; const size_t W = sizeof(h) / 4;      // 64 bytes = 16 words
+  DevBuf tmp; CK(tmp.reserve(sizeof(h) * (size_t)R));
+  CK(cudaMemcpyAsync((char *)tmp.p + sizeof(h) * ctx->rank, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  NCK(g_nccl.AllGather((char *)tmp.p + sizeof(h) * ctx->rank, tmp.p, W, NC_UINT32, (nccl_comm)ctx->comm, ctx->stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)R);
+  CK(cudaMemcpyAsync(all.data(), tmp.p, sizeof(h) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  tmp.release();
+  for (int i = 0; want[i] >= 0 && !bad; i++) {
+    int r = want[i];
+    if (r == ctx->rank) { peer_out[r] = local; continue; }
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { bad = true; break; }
+    peer_out[r] = ptr;
+  }
+  if (bad) { cudaGetLastError(); FAIL("CUDA IPC mapping of a peer buffer failed"); }
+  return 0;
+}
+// called at the end of r2s_comm_init: returns 0 also when the fast path stays off (then ctx->p2p == false)
+static int p2p_setup(r2s_ctx *ctx) {
+  ctx->p2p = false;
+  const char *env = getenv("R2S_P2P");
+  if (env && atoi(env) == 0) return 0;
+  if (ctx->nranks < 2 || ctx->nranks > 64) return 0;
+  // every rank must be able to reach every peer; all ranks take the same decision through a NCCL max-reduce of "cannot"
+  int ndev = 0; cudaGetDeviceCount(&ndev);
+  CK(cudaMalloc(&ctx->p2p_box, sizeof(P2PBox) + 64));
+  CK(cudaMemsetAsync(ctx->p2p_box, 0, sizeof(P2PBox) + 64, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int want[65]; for (int r = 0; r < ctx->nranks; r++) want[r] = r; want[ctx->nranks] = -1;
+  std::string saved = ctx->err;
+  int rc = p2p_open_all(ctx, ctx->p2p_box, ctx->p2p_peer_box, want);
+  // agree on the outcome
+  unsigned *flag = (unsigned *)((char *)ctx->p2p_box + sizeof(P2PBox) + 32), hflag = rc ? 1u : 0u;
+  CK(cudaMemcpyAsync(flag, &hflag, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  NCK(g_nccl.AllReduce(flag, flag, 1, NC_UINT32, NC_MAX, (nccl_comm)ctx->comm, ctx->stream));
+  CK(cudaMemcpyAsync(&hflag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (hflag) { ctx->err = saved; return 0; }      // some rank could not map its peers: everybody stays on NCCL
+  CK(cudaMalloc((void **)&ctx->p2p_peer_box_dev, sizeof(void *) * 64));
+  CK(cudaMemcpyAsync(ctx->p2p_peer_box_dev, ctx->p2p_peer_box, sizeof(void *) * (size_t)ctx->nranks, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->p2p = true; ctx->p2p_seq = 0; ctx->p2p_halo_seq = 0;
+  return 0;
+}
+static void p2p_teardown(r2s_ctx *ctx) {
+  if (!ctx->p2p_box) return;
+  for (int s = 0; s < 2; s++) if (ctx->p2p_c_peer[s]) { cudaIpcCloseMemHandle(ctx->p2p_c_peer[s]); ctx->p2p_c_peer[s] = nullptr; }
+  if (ctx->p2p) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->p2p_peer_box[r]) cudaIpcCloseMemHandle(ctx->p2p_peer_box[r]);
+  if (ctx->p2p_peer_box_dev) cudaFree(ctx->p2p_peer_box_dev);
+  cudaFree(ctx->p2p_box);
+  ctx->p2p_box = nullptr; ctx->p2p_peer_box_dev = nullptr; ctx->p2p = false; ctx->p2p_c_local = nullptr;
+}
+
+// ---- CG halo planes of c over peer memory ------------------------------------------------------------------------------
+int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
+  if (!ctx->p2p) return 0;
+  // collective decision: remap if any rank's buffer moved
+  unsigned long long *w = (unsigned long long *)((char *)ctx->p2p_box + sizeof(P2PBox) + 40);
+  unsigned long long changed = (ctx->p2p_c_local != (void *)c) ? 1ull : 0ull;
+  CK(cudaMemcpyAsync(w, &changed, sizeof(changed), cudaMemcpyHostToDevice, ctx->stream));
+  if (p2p_allreduce(ctx, w, 1, 4)) return 1;
+  CK(cudaMemcpyAsync(&changed, w, sizeof(changed), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!changed) return 0;
+  for (int s = 0; s < 2; s++) if (ctx->p2p_c_peer[s]) { cudaIpcCloseMemHandle(ctx->p2p_c_peer[s]); ctx->p2p_c_peer[s] = nullptr; }
+  void *peers[64]; memset(peers, 0, sizeof(peers));
+  int want[3], nw = 0;
+  if (ctx->rank > 0) want[nw++] = ctx->rank - 1;
+  if (ctx->rank + 1 < ctx->nranks) want[nw++] = ctx->rank + 1;
+  want[nw] = -1;
+  if (p2p_open_all(ctx, c, peers, want)) return 1;
+  ctx->p2p_c_peer[0] = ctx->rank > 0 ? peers[ctx->rank - 1] : nullptr;
+  ctx->p2p_c_peer[1] = ctx->rank + 1 < ctx->nranks ? peers[ctx->rank + 1] : nullptr;
+  ctx->p2p_c_local = c;
+  (void)bytes;
+  return 0;
+}
+// copies [n floats at src_off] of my array into the same offsets of the neighbour's array, then the last CTA raises the flag
+__global__ void __launch_bounds__(256) k_p2p_halo_put(const float *__restrict__ mine, float *lower, float *upper, i64 off_lo, i64 n_lo, i64 off_hi, i64 n_hi,
+                                                      P2PBox *box_lower, P2PBox *box_upper, P2PBox *box_mine, unsigned seq) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n_lo + n_hi; i += stride) {
+    if (i < n_lo) { if (lower) lower[off_lo + i] = mine[off_lo + i]; }
+    else if (upper) upper[off_hi + (i - n_lo)] = mine[off_hi + (i - n_lo)];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int par = seq & 1;
+    unsigned long long done = atomicAdd(&box_mine->halo_count[par], 1ull) + 1;
+    if (done == gridDim.x) {      // all CTAs have fenced their stores
+      box_mine->halo_count[par] = 0;
+      __threadfence_system();
+      if (box_lower) ((volatile unsigned long long *)box_lower->halo_flag[par])[1] = seq;      // I am the lower neighbour's UPPER neighbour
+      if (box_upper) ((volatile unsigned long long *)box_upper->halo_flag[par])[0] = seq;
+    }
+  }
+}
+__global__ void k_p2p_halo_wait(P2PBox *mine, int has_lower, int has_upper, unsigned seq) {
+  const int par = seq & 1;
+  if (threadIdx.x < 2) {
+    const bool need = threadIdx.x == 0 ? has_lower : has_upper;
+    volatile unsigned long long *f = &mine->halo_flag[par][threadIdx.x];
+    unsigned spin = 0;
+    while (need && *f != (unsigned long long)seq) { if (++spin > P2P_MAX_SPIN) { mine->error = 1; break; } }
+  }
+  __threadfence_system();
+}
+int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, int nz, int H) {
+  const int r = ctx->rank;
+  const unsigned seq = ++ctx->p2p_halo_seq;
+  const bool lo = r > 0, hi = r + 1 < ctx->nranks;
+  const i64 n_lo = lo ? (i64)std::min(H, k1 - k0) * plane_elems : 0, n_hi = hi ? (i64)std::min(H, k1 - k0) * plane_elems : 0;
+  const i64 off_lo = (i64)k0 * plane_elems, off_hi = (i64)(k1 - std::min(H, k1 - k0)) * plane_elems;
+  (void)nz;
+  P2PBox *mine = (P2PBox *)ctx->p2p_box;
+  k_p2p_halo_put<<<148, 256, 0, ctx->stream>>>(c, lo ? (float *)ctx->p2p_c_peer[0] : nullptr, hi ? (float *)ctx->p2p_c_peer[1] : nullptr, off_lo, n_lo, off_hi, n_hi,
+                                               lo ? (P2PBox *)ctx->p2p_peer_box[r - 1] : nullptr, hi ? (P2PBox *)ctx->p2p_peer_box[r + 1] : nullptr, mine, seq);
+  CK(cudaGetLastError());
+  ctx->p2p_ops++;
+  return 0;
+}
+int r2s_p2p_halo_wait(r2s_ctx *ctx) {
+  const int r = ctx->rank;
+  k_p2p_halo_wait<<<1, 32, 0, ctx->stream>>>((P2PBox *)ctx->p2p_box, r > 0, r + 1 < ctx->nranks, ctx->p2p_halo_seq);
+  CK(cudaGetLastError());
+  return 0;
+}
+// error flag of the mailbox (bounded spins): checked by the pipeline after its final synchronisation
+int r2s_p2p_check(r2s_ctx *ctx) {
+  if (!ctx->p2p) return 0;
+  unsigned long long e = 0;
+  CK(cudaMemcpyAsync(&e, &((P2PBox *)ctx->p2p_box)->error, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (e) FAIL("peer-memory exchange timed out (a rank did not arrive); set R2S_P2P=0 to use NCCL only");
   return 0;
 }

@@ -82,7 +82,11 @@ struct r2s_ctx {
   bool has_grid = false;
   GridDev g;
   i64 k0 = 0, k1 = 0;                       // slab of coarse planes handled by this context
-  void *comm = nullptr; int rank = 0, nranks = 1; i64 collectives = 0; std::vector<int> slab_k0;    // NCCL communicator of the slab decomposition (r2s_comm.cu)
+  void *comm = nullptr; int rank = 0, nranks = 1; i64 collectives = 0; std::vector<int> slab_k0;
+  // peer-memory fast path for the latency-critical exchanges (scalar all-reduces, CG halo planes): every rank maps every
+  // peer's mailbox (and the CG vector c) through CUDA IPC and writes into it directly over NVLink (r2s_comm.cu)
+  bool p2p = false; void *p2p_box = nullptr; void *p2p_peer_box[64]; void **p2p_peer_box_dev = nullptr; unsigned p2p_seq = 0;
+  void *p2p_c_local = nullptr; void *p2p_c_peer[2] = {nullptr, nullptr}; unsigned p2p_halo_seq = 0; i64 p2p_ops = 0;    // NCCL communicator of the slab decomposition (r2s_comm.cu)
   DevBuf gtab_d, gtab_i;
   std::vector<double> h_pc[3];
 
@@ -142,6 +146,10 @@ int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64
 int r2s_sort_f64(r2s_ctx *ctx, double *keys, double *alt, i64 n, double **sorted);
 // r2s_comm.cu: collectives over the slab communicator (no-ops for a single rank)
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
+int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes);                                     // (re)map the neighbours' CG vector c
+int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, int nz, int H);   // my boundary planes -> neighbours' halos
+int r2s_p2p_halo_wait(r2s_ctx *ctx);
+int r2s_p2p_check(r2s_ctx *ctx);
 int r2s_group_start(r2s_ctx *ctx);
 int r2s_group_end(r2s_ctx *ctx);
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count);

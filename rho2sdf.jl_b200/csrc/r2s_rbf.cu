@@ -898,6 +898,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     CK(cudaStreamSynchronize(st));
     float residual = hs[2], tol = hs[4];
     float *u_old = u, *u_new = u + n;      // ping-pong halves of the u buffer
+    if (r2s_p2p_map_c(ctx, c, sizeof(float) * (size_t)n)) return 1;
     const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
     while (iters < n && !(residual <= tol)) {
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
@@ -907,10 +908,16 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
-      if (r2s_group_start(ctx)) return 1;            // one NCCL launch: scalar all-reduce + halo planes of c
-      if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
-      if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
-      if (r2s_group_end(ctx)) return 1;
+      if (ctx->p2p) {                                // peer memory: my boundary planes of c go straight into the neighbours' halos
+        if (r2s_p2p_halo_put_c(ctx, c, pl, k0, k1, nz, 2)) return 1;
+        if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
+        if (r2s_p2p_halo_wait(ctx)) return 1;
+      } else {
+        if (r2s_group_start(ctx)) return 1;          // one NCCL launch: scalar all-reduce + halo planes of c
+        if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
+        if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
+        if (r2s_group_end(ctx)) return 1;
+      }
       k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
       k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part); LAUNCH_CHECK();
       k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
