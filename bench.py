@@ -267,10 +267,10 @@ def run_gpu(args):
             ms, ms_e2e, wall_e2e = (float(v) for v in t.tolist())
             # per-rank stage times of the last timed step (load-balance evidence)
             keys = ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_cg", "ms_threshold", "ms_total")
-            mine = torch.tensor([getattr(reps[-1], k) for k in keys] + [float(k1 - k0)], dtype=torch.float64, device="cuda")
+            mine = torch.tensor([getattr(reps[-1], k) for k in keys] + [float(k1 - k0)] + [float(v) for v in reps[-1].cg_probe], dtype=torch.float64, device="cuda")
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
-            per_rank = [dict(zip(keys + ("planes",), [round(float(v), 2) for v in a.tolist()])) for a in allr]
+            per_rank = [dict(zip(keys + ("planes", "cg_matvec", "cg_xchg1", "cg_update", "cg_xchg2"), [round(float(v), 3) for v in a.tolist()])) for a in allr]
         # ---- roofline denominators measured on this device ----
         fp64, fp32 = C.c_double(), C.c_double()
         c.check(c.lib.r2s_measure_fma_peak(c.h, 1, C.byref(fp64)))
@@ -318,7 +318,7 @@ def run_gpu(args):
             "roofline": {"kernel": "k_project_hex8", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic,
                          "peak_source": "FP64 FMA chain micro-kernel measured in this run (r2s_measure_fma_peak); HBM peak %s" % hbm_src,
                          "algorithmic": "%.0f FP64 flop per (element, point) pair x %d pairs per launch" % (FLOP_PER_PAIR, rep.n_pairs)},
-            "stages_ms": d, "kernels": stages,
+            "stages_ms": d, "kernels": stages, "cg_iteration_ms": dict(zip(("matvec", "exchange1", "update", "exchange2"), [round(float(v), 4) for v in rep.cg_probe])),
             "report": {"pairs": int(rep.n_pairs), "newton_iters": int(rep.n_newton_iters), "not_converged": int(rep.n_not_converged), "cg_iters": int(rep.cg_iters),
                        "bisections": int(rep.bisections), "flipped": int(rep.n_flipped), "th": float(rep.th), "volume": float(rep.volume),
                        "target_volume": float(p.target_volume), "solid": int(rep.n_solid), "crossing": int(rep.n_crossing)},

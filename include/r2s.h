@@ -46,6 +46,7 @@ typedef struct r2s_report {
   float ms_bin, ms_project, ms_assemble, ms_sign, ms_cc, ms_rbf_prep, ms_cg, ms_lsf, ms_threshold, ms_fine, ms_volume, ms_total;
   int64_t launches;             /* kernels launched by the last call                                       */
   int64_t collectives;          /* NCCL collectives / grouped halo exchanges issued by the last call       */
+  float cg_probe[4];            /* one CG iteration split: mat-vec, exchange 1 (dot + halo), update, exchange 2 (ms) */
 } r2s_report;
 
 /* ---- context -------------------------------------------------------------------------------------------- */

@@ -20,6 +20,7 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; } ctx->own_stream = true; }
   for (int i = 0; i < 16; i++) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 5; i++) cudaEventCreate(&ctx->ev_probe[i]);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 64; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
   *out = ctx;
@@ -37,6 +38,7 @@ void r2s_destroy(r2s_ctx *ctx) {
                    &ctx->f_scal, &ctx->cutlist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1]};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_probe[i]);
   for (int i = 0; i < 64; i++) cudaEventDestroy(ctx->ev_copy[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

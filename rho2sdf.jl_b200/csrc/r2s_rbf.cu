@@ -901,6 +901,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     if (r2s_p2p_map_c(ctx, c, sizeof(float) * (size_t)n)) return 1;
     const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
     while (iters < n && !(residual <= tol)) {
+      const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
+      if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
       if (svar == 2) k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       else if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
@@ -908,6 +910,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
+      if (probe) CK(cudaEventRecord(ctx->ev_probe[1], st));
       if (ctx->p2p) {                                // peer memory: my boundary planes of c go straight into the neighbours' halos
         if (r2s_p2p_halo_put_c(ctx, c, pl, k0, k1, nz, 2)) return 1;
         if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
@@ -918,14 +921,18 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
         if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
         if (r2s_group_end(ctx)) return 1;
       }
+      if (probe) CK(cudaEventRecord(ctx->ev_probe[2], st));
       k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
       k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part); LAUNCH_CHECK();
       k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
+      if (probe) CK(cudaEventRecord(ctx->ev_probe[3], st));
       if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
+      if (probe) CK(cudaEventRecord(ctx->ev_probe[4], st));
       k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
       CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       residual = hs[2]; iters++;
+      if (probe) for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1]));
       { float *t = u_old; u_old = u_new; u_new = t; }
     }
     wgt = x;
