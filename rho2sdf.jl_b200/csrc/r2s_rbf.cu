@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, 
 #define S3_X 32            // outputs per CTA in x (16 threads x 2)
 #define S3_Y 16
 template <bool BETA>
-__global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
+__global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, int zc, const float *__restrict__ in, const float *__restrict__ r,
                                                           const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
                                                           float *__restrict__ out, double *__restrict__ partial, StencilW W) {
   constexpr int TX = S3_X + 4, TY = S3_Y + 4, NT = TX * TY;      // 36 x 20 tile, row pitch 36 floats (8-byte aligned pairs)
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
   __shared__ double red[8];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int bx = blockIdx.x * S3_X, by = blockIdx.y * S3_Y;
-  const int zc0 = kz0 + blockIdx.z * S2_ZC, zc1 = min(zc0 + S2_ZC, kz1);
+  const int zc0 = kz0 + blockIdx.z * zc, zc1 = min(zc0 + zc, kz1);      // zc output planes per CTA (chosen by the host so that the chunks are even)
   const int gx = bx + 2 * tx, gy = by + ty;
   const bool in0 = gx < nx && gy < ny, in1 = gx + 1 < nx && gy < ny;
   float beta = 0.0f;
@@ -873,7 +873,9 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   // mat-vec kernel: plane-marching (default) or tile-per-CTA (R2S_STENCIL=0, kept for comparison)
   static const int svar = getenv("R2S_STENCIL") ? atoi(getenv("R2S_STENCIL")) : 2;      // 0 tile-per-CTA, 1 plane-marching, 2 plane-marching with 2 outputs/thread
   const bool march = svar != 0;
-  dim3 sgrid = svar == 2 ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, S2_ZC)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
+  // even z-chunks of about 64 planes: a 65-plane slab is one chunk, not 64 + 1
+  const int nchunk = std::max(1, (k1 - k0 + 32) / 64), zc = cdiv(k1 - k0, nchunk);
+  dim3 sgrid = svar == 2 ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
   int sthreads = svar == 2 ? 256 : (svar == 1 ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB));
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
@@ -904,7 +906,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
       if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      if (svar == 2) k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      if (svar == 2) k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
       else if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       else k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       LAUNCH_CHECK();
@@ -942,7 +944,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  if (svar == 2) k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  if (svar == 2) k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   else if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   else k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   LAUNCH_CHECK();

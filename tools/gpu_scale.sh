@@ -11,6 +11,8 @@ try:
     d = json.loads(open(f).read().strip().splitlines()[-1])
     print(f, "gpus", d["n_gpus"], "ms/step %.2f" % d["ms_per_step"], "value %.3e" % d["value"], "e2e %.3e (%.1f ms)" % (d["e2e"]["value"], d["e2e"]["ms_per_step"]))
     print("   ", {k: round(v, 2) for k, v in d["stages_ms"].items()})
+    print("    planes", d["config"].get("slab_planes"), "cg iteration", d.get("cg_iteration_ms"))
+    for r in d.get("per_rank", [])[:8]: print("      ", {k: r[k] for k in ("ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_cg", "cg_matvec", "cg_xchg1", "cg_update", "cg_xchg2", "planes")})
 except Exception as e:
     print(f, "ERR", e)
 PY
