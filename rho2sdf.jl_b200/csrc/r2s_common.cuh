@@ -75,7 +75,7 @@ struct r2s_ctx {
   // mesh
   int nen = 0, nes = 0, nsn = 0;
   i64 nnp = 0, nel = 0;
-  DevBuf X, IEN32, ine_ptr, ine_el, fbnd;   // X double[3*nnp]; IEN32 int[nen*nel] 0-based; INE CSR; fbnd uint8[nel]
+  DevBuf X, IEN32, ine_ptr, ine_el, fbnd, ezr;   // X double[3*nnp]; IEN32 int[nen*nel] 0-based; INE CSR; fbnd uint8[nel]
   DevBuf rho_e, rho_n;
 
   // grid

@@ -16,10 +16,15 @@
 #include "r2s_iso.cuh"
 
 // ------------------------------------------------------------------------------------------------ binning
+// [zlo, zhi]: z-extent of the slab's planes grown by a safe margin; elements entirely outside cannot reach a plane of this rank
+// and are left inactive without touching their nodes (single rank: the interval is infinite).  The class counters then
+// count the elements near the slab only.
 __global__ void k_classify(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ rn, const unsigned char *__restrict__ fb,
+                           const double2 *__restrict__ ezr, double zlo, double zhi,
                            double rho_t, unsigned char *__restrict__ cls, int *__restrict__ flag, i64 *__restrict__ counts) {
   i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   int c = 0;
+  if (e < nel) { const double2 z = ezr[e]; if (z.y < zlo || z.x > zhi) { cls[e] = 0; flag[e] = 0; e = nel; } }
   if (e < nel) {
     double mn = 1e300, mx = -1e300;
     for (int a = 0; a < nen; a++) { double r = rn[IEN[nen * e + a]]; mn = fmin(mn, r); mx = fmax(mx, r); }
@@ -539,7 +544,10 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(ctx->counters.reserve(sizeof(u64) * 8 * 1025));      // slot 0: element classes; slots 1..1024: projection statistics
   CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * 8 * 1025, st));
   CK(cudaMemsetAsync(ctx->act_flag.as<int>() + nel, 0, sizeof(int), st));
-  k_classify<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), ctx->fbnd.as<unsigned char>(), rho_t,
+  // z-interval of this rank's planes with a margin of (delta + 2 cells): only elements that can reach them are classified
+  double zlo = -1e300, zhi = 1e300;
+  if (kz0 > 0 || kz1 < g.np[2]) { const double m = delta + 2.0 * g.cell; zlo = ctx->h_pc[2][(size_t)kz0] - m; zhi = ctx->h_pc[2][(size_t)kz1 - 1] + m; }
+  k_classify<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), ctx->fbnd.as<unsigned char>(), ctx->ezr.as<double2>(), zlo, zhi, rho_t,
                                              ctx->cls.as<unsigned char>(), ctx->act_flag.as<int>(), ctx->counters.as<i64>()); LAUNCH_CHECK();
   if (r2s_scan_exclusive_i32(ctx, ctx->act_flag.as<int>(), ctx->act_idx.as<int>(), nel + 1)) return 1;
   int nact_i = 0;

@@ -58,6 +58,15 @@ int r2s_mesh_upload_ien(r2s_ctx *ctx, const int64_t *IEN) {
   tmp.release();
   return 0;
 }
+// z-extent of every element (geometry only, built with the mesh): lets a z-slab rank discard the elements far from its planes
+// with one 16-byte read instead of gathering their nodes
+__global__ void k_elem_zrange(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, double2 *__restrict__ ezr) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  double lo = 1e300, hi = -1e300;
+  for (int a = 0; a < nen; a++) { double z = X[3 * (i64)IEN[nen * e + a] + 2]; lo = fmin(lo, z); hi = fmax(hi, z); }
+  ezr[e] = make_double2(lo, hi);
+}
 int r2s_mesh_build_tables(r2s_ctx *ctx) {
   i64 n = ctx->nel * ctx->nen;
   CK(ctx->ine_ptr.reserve(sizeof(int) * (size_t)(ctx->nnp + 1)));
@@ -74,6 +83,8 @@ int r2s_mesh_build_tables(r2s_ctx *ctx) {
   k_ine_sort<<<cdiv(ctx->nnp, 256), 256, 0, ctx->stream>>>(ctx->nnp, ctx->ine_ptr.as<int>(), ctx->ine_el.as<int>()); LAUNCH_CHECK();
   k_face_boundary<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->nes, ctx->nsn, ctx->IEN32.as<int>(), ctx->ine_ptr.as<int>(),
                                                                 ctx->ine_el.as<int>(), ctx->fbnd.as<unsigned char>()); LAUNCH_CHECK();
+  CK(ctx->ezr.reserve(sizeof(double2) * (size_t)ctx->nel));
+  k_elem_zrange<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->ezr.as<double2>()); LAUNCH_CHECK();
   CK(cudaStreamSynchronize(ctx->stream));
   cnt.release(); cur.release();
   return 0;

@@ -18,9 +18,12 @@ __device__ __forceinline__ int tet_cell_index(double x, double amin, double cell
   return max(1, min(n1, idx));
 }
 __global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, double rho_t,
-                              GridDev g, int kz0, int kz1, SRange *__restrict__ rng, i64 *__restrict__ ntile, SignEl *__restrict__ sel) {
+                              GridDev g, int kz0, int kz1, const double2 *__restrict__ ezr, double zlo, double zhi, SRange *__restrict__ rng, i64 *__restrict__ ntile,
+                              SignEl *__restrict__ sel) {
   i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (e >= nel) return;
+  { const double2 z = ezr[e];      // z-slab: elements that cannot reach this rank's planes get an empty range without touching their nodes
+    if (z.y < zlo || z.x > zhi) { SRange r; r.a[0] = 1; r.b[0] = 0; r.a[1] = r.a[2] = 1; r.b[1] = r.b[2] = 0; r.hot = 0; r.pad = 0; rng[e] = r; ntile[e] = 0; return; } }
 
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rmax = -1e300;
   for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; rmax = fmax(rmax, rn[n]); for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
@@ -245,7 +248,9 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   CK(cudaMemsetAsync(ctx->s_tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
   CK(cudaMemsetAsync(ctx->cnt_a.as<i64>() + nel, 0, sizeof(i64), st));
   i64 *ntile = ctx->cnt_a.as<i64>(), *toff = ctx->cnt_b.as<i64>();
-  k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, g, kz0, kz1, ctx->s_rng.as<SRange>(), ntile, ctx->s_el.as<SignEl>()); LAUNCH_CHECK();
+  double zlo = -1e300, zhi = 1e300;
+  if (kz0 > 0 || kz1 < g.np[2]) { const double m = 3.0 * g.cell; zlo = ctx->h_pc[2][(size_t)kz0] - m; zhi = ctx->h_pc[2][(size_t)kz1 - 1] + m; }
+  k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, g, kz0, kz1, ctx->ezr.as<double2>(), zlo, zhi, ctx->s_rng.as<SRange>(), ntile, ctx->s_el.as<SignEl>()); LAUNCH_CHECK();
   if (r2s_scan_exclusive_i64(ctx, ntile, toff, nel + 1)) return 1;
   i64 nkeys = 0;
   CK(cudaMemcpyAsync(&nkeys, toff + nel, sizeof(i64), cudaMemcpyDeviceToHost, st));
