@@ -100,6 +100,14 @@ def workload(n):
     return simp_hex8(n)
 
 
+def base_config(n):
+    """The workload both arms are quoted on (BASELINE configs[4]); grid dims follow Grid(): N = 2n + 6 cells per axis."""
+    f = 4 * n + 13
+    return {"workload": "synthetic %d^3 HEX8 SIMP density (seed 20240517) -> %dx%dx%d fine SDF grid (BASELINE configs[4])" % (n, f, f, f),
+            "coarse_points": (2 * n + 7) ** 3, "fine_voxels": f ** 3, "rho_t": 0.5, "delta_factor": 1.1, "rbf_interp": True, "rbf_grid": "fine",
+            "remove_artifacts": True, "smoothing_dtype": "f32 (as the reference)"}
+
+
 def fine_voxels(grid, smooth):
     return int(np.prod([int(v) * smooth + 1 for v in grid.N]))
 
@@ -143,8 +151,7 @@ def run_reference(args):
     sample = "n=%d^3 HEX8 SIMP replica of the workload (%d coarse points, %d fine voxels), full timed region" % (n, g.ngp, nv)
     line = {"impl": "reference", "metric": METRIC, "value": nv / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
             "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic %d^3 HEX8 SIMP density -> %d^3-class fine SDF grid (configs[4]); CPU arm runs the bounded %d^3 replica" % (args.n, 4 * args.n + 13, n),
-                       "rho_t": 0.5, "rbf_interp": True, "rbf_grid": "fine", "remove_artifacts": True},
+            "config": dict(base_config(args.n), parallelism="host threads", sample="each step = the bounded %d^3 replica of the workload" % n),
             "cpu_baseline": {"value": nv / t, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": nv / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -308,10 +315,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": nfine / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic %d^3 HEX8 SIMP density (seed 20240517) -> %dx%dx%d fine SDF grid (BASELINE configs[4])" % (n, fdims[0], fdims[1], fdims[2]),
-                       "coarse_points": int(grid.ngp), "fine_voxels": nfine, "rho_t": 0.5, "delta_factor": 1.1, "rbf_interp": True, "rbf_grid": "fine",
-                       "remove_artifacts": True, "parallelism": "zslab%d" % world, "slab_planes": [int(b - a) for a, b in parts] if world > 1 else [nz], "l2_policy": "inputs larger than L2 (working set %.1f GB per step)" % ((rep.n_pairs * 8 + grid.ngp * 40 + nfine * 4) / 1e9),
-                       "smoothing_dtype": "f32 (as the reference)"},
+            "config": dict(base_config(n), parallelism="zslab%d" % world, slab_planes=[int(b - a) for a, b in parts] if world > 1 else [nz], l2_policy="inputs larger than L2 (working set %.1f GB per step)" % ((rep.n_pairs * 8 + grid.ngp * 40 + nfine * 4) / 1e9)),
             "e2e": {"value": nfine / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(rho_n.nbytes) * world,
                     "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4), "api": "r2s_pipeline_slab (pinned host buffers)"},
             "gpu_launches": int(sum(r.launches for r in reps)),

@@ -663,8 +663,8 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #undef ASM
   }
   CK(cudaEventRecord(ctx->ev[3], st));
-  static u64 hall[8 * 1025]; u64 hc[8];
-  CK(cudaMemcpyAsync(hall, ctx->counters.p, sizeof(hall), cudaMemcpyDeviceToHost, st));
+  ctx->h_counters.resize(8 * 1025); u64 *hall = ctx->h_counters.data(); u64 hc[8];
+  CK(cudaMemcpyAsync(hall, ctx->counters.p, sizeof(u64) * 8 * 1025, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int q = 0; q < 8; q++) { hc[q] = hall[q]; for (int sl = 1; sl <= 1024; sl++) hc[q] += hall[8 * sl + q]; }
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
