@@ -45,6 +45,7 @@ def lib():
         L.r2so_rbf_smoothing.argtypes = [_dp, _dp, _dp, _ip, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                          _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
         L.r2so_project_iso_hex8.argtypes = [_dp, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_int)]
+        L.r2so_inverse_map_hex8.argtypes = [_dp, _dp, _dp]
         L.r2so_max_threads.restype = C.c_int
     return _LIB
 
@@ -151,3 +152,10 @@ def project_iso_hex8(x, rho_t, Xe, re):
     ok = lib().r2so_project_iso_hex8(np.ascontiguousarray(x, dtype=np.float64), float(rho_t), np.ascontiguousarray(Xe, dtype=np.float64),
                                      np.ascontiguousarray(re, dtype=np.float64), xi, C.byref(it))
     return bool(ok), xi, it.value
+
+
+def inverse_map_hex8(x, Xe):
+    """Xe: (8,3). Returns (ok, xi)."""
+    xi = np.zeros(3)
+    ok = lib().r2so_inverse_map_hex8(np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(Xe, dtype=np.float64), xi)
+    return bool(ok), xi

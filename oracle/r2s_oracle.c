@@ -578,6 +578,11 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
   if (niter) *niter = it;
   return status == 1;
 }
+/* inverse isoparametric map of one HEX8 (test hook): Xe_colmajor = 3 x 8 column-major; returns 1 on success */
+API int r2so_inverse_map_hex8(const double *x, const double *Xe_colmajor, double *xi) {
+  double Xe[3][8]; for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) Xe[d][a] = Xe_colmajor[3 * a + d];
+  return inverse_map_hex8((const double(*)[8])Xe, x, xi);
+}
 API int r2so_project_iso_hex8(const double *x, double rho_t, const double *Xe_colmajor, const double *re, double *xi, int *niter) {
   double Xe[3][8]; for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) Xe[d][a] = Xe_colmajor[3 * a + d];
   return project_iso_hex8(x, rho_t, (const double(*)[8])Xe, re, xi, niter);

@@ -222,3 +222,128 @@ def test_tet4_oracle_agrees_with_hex8_on_linear_field():
     assert np.abs(dh[interior] - plane[interior]).max() < 1e-9 and np.abs(dt[interior] - plane[interior]).max() < 1e-9
     inside = (P.min(1) > 0.01) & (P.max(1) < n - 0.01) & (np.abs(P @ nrm + 0.1 - 0.5) > 1e-6)
     assert np.array_equal(sh[inside], st[inside])
+
+
+def test_inverse_map_matches_published_lbfgs():
+    """The reference finds local coordinates with NLopt :LD_LBFGS, bounds +-1.1, 9 starting points, best objective
+    (FindLocalCoordinates.jl:27-37,71-104).  scipy's L-BFGS-B is the same published algorithm (Byrd-Lu-Nocedal-Zhu); from the same
+    starts, converged tightly, its best point must coincide with the oracle's Newton inverse map wherever the point lies inside
+    the bounds -- and where it does not, both must say 'outside' (max|xi| >= 1.01, SignDetection.jl:48)."""
+    from scipy.optimize import minimize
+    X, IEN, rho = load_mesh("chapadlo")                      # unstructured, non-affine hexes
+    SG = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
+    shape = lambda xi: 0.125 * np.prod(1 + SG * xi, axis=1)
+
+    def dshape(xi):
+        t = 1 + SG * xi
+        return 0.125 * np.stack([SG[:, 0] * t[:, 1] * t[:, 2], SG[:, 1] * t[:, 0] * t[:, 2], SG[:, 2] * t[:, 0] * t[:, 1]], axis=1)
+
+    starts = [(0, 0, 0)] + [tuple(0.5 * s for s in c) for c in SG]
+    rng = np.random.default_rng(7)
+    inside = outside = 0
+    for _ in range(120):
+        e = int(rng.integers(IEN.shape[0]))
+        Xe = X[IEN[e] - 1]
+        size = np.ptp(Xe, axis=0)
+        x = Xe.mean(0) + rng.uniform(-0.6, 0.6, 3) * size
+        ok, xi = oracle.inverse_map_hex8(x, Xe)
+        best = None
+        for s0 in starts:
+            r = minimize(lambda q: np.sum((Xe.T @ shape(q) - x) ** 2), np.array(s0, float), jac=lambda q: 2 * (dshape(q).T @ Xe) @ (Xe.T @ shape(q) - x),
+                         method="L-BFGS-B", bounds=[(-1.1, 1.1)] * 3, options={"ftol": 1e-16, "gtol": 1e-14, "maxiter": 500})
+            if best is None or r.fun < best.fun:
+                best = r
+        m_ref = np.abs(best.x).max()
+        if best.fun < 1e-16 * float(size @ size) and m_ref < 1.0999:      # the bounded minimiser is an exact root strictly inside the bounds
+            assert ok and np.abs(xi - best.x).max() < 1e-6
+            inside += 1
+        else:                                                          # clamped at the bounds: the point is outside the element for both
+            assert (not ok) or np.abs(xi).max() >= 1.01
+            assert m_ref >= 1.01
+            outside += 1
+    assert inside >= 25 and outside >= 5, (inside, outside)
+
+
+def _rbf_reference_literal(sdf, g, is_interp, smooth, rbf_cut=1e-3):
+    """Line-by-line numpy/scipy restatement of RBFs_smoothing up to the fine-grid evaluation (src/SdfSmoothing/RBFs4Smoothing.jl:
+    process_vector :15-22, create_grid :36-46, create_smooth_grid :60-74, kernel :103-107, compute_sparse_kernel_matrix :142-176 with a
+    KD-tree `inrange`, IterativeSolvers.cg defaults :199, rbf_interpolation_kdtree :219-248 with a 124-nearest-neighbour query).
+    Third-party pieces as in the reference: a KD-tree (scipy.spatial.cKDTree for NearestNeighbors.jl) and a sparse Float32 matrix."""
+    from scipy.spatial import cKDTree
+    from scipy.sparse import coo_matrix
+    f32 = np.float32
+    v = sdf.astype(f32)
+    fin = np.abs(v) < f32(1e9)
+    maxv = np.abs(v[fin]).max()
+    far = np.abs(np.abs(v) - f32(1e10)) <= np.sqrt(np.finfo(f32).eps) * np.maximum(np.abs(v), f32(1e10))     # isapprox, default rtol
+    v = np.where(far, np.sign(v) * maxv, v).astype(f32)
+    n = [int(t) + 1 for t in g.N]
+    lo, hi = g.AABB_min.astype(f32), g.AABB_max.astype(f32)
+    ax = [np.linspace(np.float64(lo[d]), np.float64(hi[d]), n[d]).astype(f32) for d in range(3)]            # range(Float32, Float32, length)
+    kk, jj, ii = np.meshgrid(np.arange(n[2]), np.arange(n[1]), np.arange(n[0]), indexing="ij")
+    P = np.stack([ax[0][ii.ravel()], ax[1][jj.ravel()], ax[2][kk.ravel()]], axis=1)                         # x fastest, Float32
+    sigma = np.float64(g.cell_size)
+
+    def kern(a, b):                                                                                           # :103-107
+        d = a - b                                                                                             # Float32
+        r = np.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]).astype(f32)).astype(f32)
+        val = np.exp(-(r.astype(np.float64) / sigma) ** 2)
+        return np.where(val > rbf_cut, val, 0.0)
+
+    tree = cKDTree(P.astype(np.float64))
+    w = v.copy()
+    iters = 0
+    if is_interp:
+        radius = sigma * np.sqrt(-np.log(rbf_cut))
+        pairs = tree.query_ball_point(P.astype(np.float64), radius)
+        I = np.concatenate([np.full(len(p), i) for i, p in enumerate(pairs)]); J = np.concatenate([np.asarray(p, dtype=np.int64) for p in pairs])
+        V = kern(P[I], P[J]).astype(f32)
+        keep = V > f32(rbf_cut)
+        K = coo_matrix((V[keep], (I[keep], J[keep])), shape=(len(P), len(P))).tocsr().astype(f32)
+        # IterativeSolvers.cg(K, b): x0 = 0, reltol = sqrt(eps(Float32)), maxiter = n  (CGIterable)
+        x = np.zeros(len(P), f32); r = v.copy(); u = np.zeros(len(P), f32)
+        res = f32(np.linalg.norm(r)); prev = f32(1.0); tol = f32(np.sqrt(np.finfo(f32).eps)) * res
+        while iters < len(P) and not (res <= tol):
+            beta = f32(res * res / (prev * prev))
+            u = (r + beta * u).astype(f32)
+            c = (K @ u).astype(f32)
+            alpha = f32(res * res / f32(np.dot(u, c)))
+            x = (x + alpha * u).astype(f32); r = (r - alpha * c).astype(f32)
+            prev = res; res = f32(np.linalg.norm(r)); iters += 1
+        w = x
+
+    def evaluate(Q):                                                                                          # :219-248
+        maxd = f32(np.sqrt(-np.log(rbf_cut) * sigma ** 2))
+        dist, idx = tree.query(Q.astype(np.float64), k=min(124, len(P)))
+        out = np.zeros(len(Q), f32)
+        for t in range(dist.shape[1]):                                                                         # neighbours in ascending distance
+            dt = dist[:, t].astype(f32)
+            term = w[idx[:, t]].astype(np.float64) * np.exp(-(dt.astype(np.float64) / sigma) ** 2)
+            out = np.where(dt <= maxd, (out.astype(np.float64) + term).astype(f32), out)
+        return out
+
+    lsf = evaluate(P)
+    nf = [int(t) * smooth + 1 for t in g.N]
+    dx = f32((hi[0] - lo[0]) / f32(nf[0] - 1))
+    fax = [(lo[d] + np.arange(nf[d], dtype=f32) * dx).astype(f32) for d in range(3)]                         # xmin + (i-1)*dx in Float32
+    kk, jj, ii = np.meshgrid(np.arange(nf[2]), np.arange(nf[1]), np.arange(nf[0]), indexing="ij")
+    Q = np.stack([fax[0][ii.ravel()], fax[1][jj.ravel()], fax[2][kk.ravel()]], axis=1)
+    return w, lsf, evaluate(Q).reshape(nf[2], nf[1], nf[0]), iters
+
+
+@pytest.mark.parametrize("interp", [True, False])
+def test_rbf_oracle_matches_literal_kdtree_restatement(interp):
+    """The oracle's smoothing (stencil form) against the literal KD-tree / sparse-matrix / CG formulation of the reference."""
+    X, IEN, rho = block_geometry([2, 1, 1])
+    g = Grid(X.min(0), X.max(0), 10, 3)
+    d, _, _ = oracle.eval_distances(X, IEN, g, BLOCK_RHO_N, 0.5, 1.1, want_xp=False)
+    sdf = d * oracle.sign_detection(X, IEN, g, BLOCK_RHO_N, 0.5)
+    vd, vf = oracle.mesh_volume(X, IEN, rho)
+    w, lsf, fine_lsf, iters = _rbf_reference_literal(sdf, g, interp, 2)
+    ofine, info = oracle.rbf_smoothing(sdf, g, interp, 2, vd * vf, mode=0, want_aux=True)
+    scale = float(np.abs(lsf).max())
+    if interp:
+        assert abs(iters - info["cg_iters"]) <= 1
+    assert np.abs(w - info["weights"]).max() <= 2e-4 * float(np.abs(w).max())
+    assert np.abs(lsf - info["lsf"]).max() <= 1e-4 * scale
+    assert np.abs((fine_lsf + np.float32(info["th"])) - ofine).max() <= 1e-4 * scale
