@@ -313,3 +313,25 @@ def test_large_pipeline_properties(r2s, n):
     assert np.array_equal(d_slab[k0 * pl:k1 * pl], d_full[k0 * pl:k1 * pl])
     assert np.array_equal(s_slab[k0 * pl:k1 * pl], s_full[k0 * pl:k1 * pl])
     mesh.ctx.close()
+
+
+def test_tet4_two_million_tets_public_api(r2s):
+    """BASELINE configs[3]: synthetic TET4 SIMP field, 70^3 hex cells Schlaefli-split = 2 058 000 tets, explicit threshold (the reference's
+    automatic threshold is HEX8-only), :automatic grid, through rho2sdf_tet4.  The oracle is too slow here: size-independent properties."""
+    n = 70
+    X, IEN, rn = schlafli_tet4(n, "simp")
+    assert IEN.shape == (6 * n ** 3, 4)
+    rho = rn[IEN - 1].mean(axis=1)
+    out1 = r2s.rho2sdf_tet4("tet", X, IEN, rho, threshold_density=0.5, sdf_grid_setup="automatic", rbf_grid="fine", return_report=True)
+    fine, fg, grid, sdf, rep = out1
+    # grid step = median edge of the split (unit edges, face diagonals sqrt2, one body diagonal sqrt3 per tet path)
+    assert abs(grid.cell_size - n / np.floor(n / np.median([1, 1, 1, np.sqrt(2), np.sqrt(2), np.sqrt(3)]))) < 1e-9
+    assert fine.shape == tuple(int(v) * 2 + 1 for v in grid.N[::-1]) and fine.dtype == np.float32 and np.isfinite(fine).all()
+    assert sdf.shape == (grid.ngp,) and np.isfinite(sdf).all() and rep["n_crossing"] > 0 and rep["cg_iters"] > 5
+    inside = sdf > 0
+    assert 0.05 < inside.mean() < 0.6                                   # the SIMP field fills a moderate fraction of the box
+    band = np.abs(sdf) < 1e9
+    assert np.abs(sdf[band]).max() <= np.sqrt(3) * (1 + 2 * 2.1 * grid.cell_size) + 1e-9
+    # determinism through the public entry point
+    fine2, _, _, sdf2, _ = r2s.rho2sdf_tet4("tet", X, IEN, rho, threshold_density=0.5, sdf_grid_setup="automatic", rbf_grid="fine", return_report=True)
+    assert np.array_equal(sdf, sdf2) and np.array_equal(fine, fine2)
