@@ -505,19 +505,70 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       n += __popc(m); p += 32;
     }
     __syncwarp();
-    if (valid) {
-      for (int q = 0; q < n; q++) {
-        const ActRec &r = srec[warp][q];
-        if (pi[0] < r.ps[0] || pi[0] >= r.pe[0] || pi[1] < r.ps[1] || pi[1] >= r.pe[1] || pi[2] < r.ps[2] || pi[2] >= r.pe[2]) continue;
-        if (FACES && r.fmask && (WANT_XP || r.cls == 1)) boundary_faces_point<WANT_XP, NEN>(r, tri, IEN, X, rn, rho_t, pi, x, s);     // crossing faces are folded into the pair buffer unless xp is wanted
-        if (r.cls == 2) {
-          i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
-          double dt = pairbuf[idx];
-          if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
-            s.c = dt;
-            if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+    // which culled records contain THIS lane's point: one uniform sweep (broadcast reads)
+    unsigned mk0 = 0, mk1 = 0, mk2 = 0;
+    for (int q = 0; q < n; q++) {
+      const ActRec &r = srec[warp][q];
+      if (valid && pi[0] >= r.ps[0] && pi[0] < r.pe[0] && pi[1] >= r.ps[1] && pi[1] < r.pe[1] && pi[2] >= r.ps[2] && pi[2] < r.pe[2]) {
+        if (q < 32) mk0 |= 1u << q; else if (q < 64) mk1 |= 1u << (q - 32); else mk2 |= 1u << (q - 64);
+      }
+    }
+    // Every lane walks ITS records in list order (= ascending element index) and, inside a record, its boundary triangles in
+    // order, then takes the record's pair-buffer entry -- exactly the reference's sequence for that grid point.  The lanes do
+    // not wait for each other's records: in each round every lane brings its own next triangle to triangle_point, so the
+    // expensive part runs with (nearly) full warps instead of only the lanes that happen to share the current element.
+    constexpr int NSN = NEN == 8 ? 4 : 3;
+    int w = 0, pos = -1, t = 0, ntri = 0; unsigned cur = mk0; bool more = valid;
+    ActRec r; r.cls = 0; r.tri_off = 0; r.pair_off = 0; r.fmask = 0; r.el = 0;
+    double Xe[3][NEN], re[NEN]; bool loaded = false;
+    while (true) {
+      int ti = -1;                                   // index of this lane's next triangle (work item of this round)
+      while (more && ti < 0) {
+        if (t < ntri) {
+          const TriRec &T = tri[r.tri_off + t]; const int tcur = t; t++;
+          if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
+          if (r.cls == 1) {
+            // solid element: no candidate of this triangle can be below the distance to its bounding box; if that is not
+            // below the running value the triangle changes nothing (exact; the margin covers the rounding of the candidates)
+            double lb2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+              const double lo = fmin(T.Xt[0][d], fmin(T.Xt[1][d], T.Xt[2][d])), hi = fmax(T.Xt[0][d], fmax(T.Xt[1][d], T.Xt[2][d]));
+              const double e = fmax(fmax(lo - x[d], x[d] - hi), 0.0);
+              lb2 = fma(e, e, lb2);
+            }
+            const double cv = fabs(s.c) * (1.0 + 1e-12);
+            if (lb2 * (1.0 - 1e-12) > cv * cv) continue;
           }
+          ti = tcur;
+        } else {
+          if (pos >= 0 && r.cls == 2) {              // the record's faces are done: now its iso distance (:617-621)
+            i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
+            double dt = pairbuf[idx];
+            if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
+              s.c = dt;
+              if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+            }
+          }
+          while (w < 3 && cur == 0) { w++; cur = (w == 1) ? mk1 : (w == 2 ? mk2 : 0u); }
+          if (w >= 3) { more = false; pos = -1; break; }
+          const int bq = __ffs(cur) - 1; cur &= cur - 1; pos = w * 32 + bq;
+          r = srec[warp][pos];
+          t = 0; loaded = false;
+          ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
         }
+      }
+      if (!__any_sync(0xffffffffu, ti >= 0)) break;
+      if (ti >= 0) {
+        const TriRec &T = tri[r.tri_off + ti];
+        if (WANT_XP && r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113), replayed here only when xp is wanted
+          for (int a = 0; a < NEN; a++) { i64 nd = IEN[NEN * (i64)r.el + a]; re[a] = rn[nd]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * nd + d]; }
+          loaded = true;
+        }
+        double Xt[3][3], Et[3][3], nn[3];
+        for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; nn[d] = T.n[d]; }
+        for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+        triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
       }
     }
     __syncwarp();
