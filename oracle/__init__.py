@@ -46,6 +46,7 @@ def lib():
                                          _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
         L.r2so_project_iso_hex8.argtypes = [_dp, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_int)]
         L.r2so_inverse_map_hex8.argtypes = [_dp, _dp, _dp]
+        L.r2so_project_iso_tet4.argtypes = [_dp, C.c_double, _dp, _dp, _dp]
         L.r2so_max_threads.restype = C.c_int
     return _LIB
 
@@ -159,3 +160,11 @@ def inverse_map_hex8(x, Xe):
     xi = np.zeros(3)
     ok = lib().r2so_inverse_map_hex8(np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(Xe, dtype=np.float64), xi)
     return bool(ok), xi
+
+
+def project_iso_tet4(x, rho_t, Xe, re):
+    """Xe: (4,3). Returns (ok, xp)."""
+    xp = np.zeros(3)
+    ok = lib().r2so_project_iso_tet4(np.ascontiguousarray(x, dtype=np.float64), float(rho_t), np.ascontiguousarray(Xe, dtype=np.float64),
+                                     np.ascontiguousarray(re, dtype=np.float64), xp)
+    return bool(ok), xp

@@ -578,6 +578,12 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
   if (niter) *niter = it;
   return status == 1;
 }
+static int project_iso_tet4(const double x[3], double rho_t, const double Xe[3][4], const double re[4], double xp[3]);
+/* closest point on the iso-cut of one TET4 (test hook): Xe_colmajor = 3 x 4 column-major; returns 1 when a projection exists */
+API int r2so_project_iso_tet4(const double *x, double rho_t, const double *Xe_colmajor, const double *re, double *xp) {
+  double Xe[3][4]; for (int a = 0; a < 4; a++) for (int d = 0; d < 3; d++) Xe[d][a] = Xe_colmajor[3 * a + d];
+  return project_iso_tet4(x, rho_t, (const double(*)[4])Xe, re, xp);
+}
 /* inverse isoparametric map of one HEX8 (test hook): Xe_colmajor = 3 x 8 column-major; returns 1 on success */
 API int r2so_inverse_map_hex8(const double *x, const double *Xe_colmajor, double *xi) {
   double Xe[3][8]; for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) Xe[d][a] = Xe_colmajor[3 * a + d];

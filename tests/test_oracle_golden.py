@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from fixtures import BLOCK_RHO_N, Grid, block_geometry, load_mesh, simp_hex8
+from fixtures import BLOCK_RHO_N, Grid, block_geometry, load_mesh, schlafli_tet4, simp_hex8
 
 
 def isapprox(a, b, rtol=0.0, atol=0.0):
@@ -347,3 +347,137 @@ def test_rbf_oracle_matches_literal_kdtree_restatement(interp):
     assert np.abs(w - info["weights"]).max() <= 2e-4 * float(np.abs(w).max())
     assert np.abs(lsf - info["lsf"]).max() <= 1e-4 * scale
     assert np.abs((fine_lsf + np.float32(info["th"])) - ofine).max() <= 1e-4 * scale
+
+
+def test_tet4_projection_matches_published_slsqp():
+    """TET4 branch of compute_coords_on_iso (ComputeCoordsOnIso.jl:90-181): min |x - X N(l)|^2 s.t. rho.N(l) = rho_t, 0 <= l <= 1,
+    sum l <= 1, NLopt :LD_SLSQP from the centroid.  The problem is a convex QP, so its minimiser is unique: scipy's SLSQP (the same
+    published algorithm) must land on the point the oracle gets in closed form (projection on the polygon where the plane rho = rho_t cuts the tet)."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(11)
+    Nf = lambda l: np.array([l[0], l[1], l[2], 1.0 - l[0] - l[1] - l[2]])          # ShapeFunctions.jl:39-73
+    dN = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, -1, -1]], float)
+    checked = 0
+    for _ in range(80):
+        Xe = rng.uniform(0, 1, (4, 3)) + np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])      # a well-shaped random tet
+        re = rng.uniform(0, 1, 4)
+        if not (re.min() < 0.5 < re.max()):
+            continue
+        x = Xe.mean(0) + rng.uniform(-1.5, 1.5, 3)
+        ok, xp = oracle.project_iso_tet4(x, 0.5, Xe, re)
+        assert ok
+        cons = [{"type": "eq", "fun": lambda l: re @ Nf(l) - 0.5, "jac": lambda l: dN.T @ re},
+                {"type": "ineq", "fun": lambda l: 1.0 - l.sum(), "jac": lambda l: -np.ones(3)}]
+        r = minimize(lambda l: np.sum((x - Xe.T @ Nf(l)) ** 2), np.full(3, 0.25), jac=lambda l: -2 * (dN.T @ Xe) @ (x - Xe.T @ Nf(l)),
+                     method="SLSQP", bounds=[(0, 1)] * 3, constraints=cons, options={"ftol": 1e-16, "maxiter": 500})
+        if r.success and abs(re @ Nf(r.x) - 0.5) < 1e-10:
+            assert np.linalg.norm(Xe.T @ Nf(r.x) - xp) < 1e-6
+            checked += 1
+    assert checked >= 40
+
+
+def test_tet4_sign_matches_literal_restatement():
+    """Sign_Detection_TET4 (SignDetection.jl:88-165) restated literally in numpy -- cell lists of create_grid_tetrahedra_mapping_TET4
+    (:168-217, single thread = ascending element order), is_point_in_tetrahedron (:220-242, 4x4 solve, tol 1e-10),
+    find_local_coordinates(TET4) (FindLocalCoordinates.jl:110-149, 3x3 solve + validate_local_coords: all >= 0, sum <= 1.0),
+    first containing tet with rho >= rho_t wins -- against the oracle on a Schlaefli-split cube."""
+    n = 4
+    X, IEN, rn = schlafli_tet4(n, "radial")
+    g = Grid(X.min(0), X.max(0), 2 * n, 3)
+    so = oracle.sign_detection(X, IEN, g, rn, 0.5).reshape([int(v) + 1 for v in g.N[::-1]])
+    dims = g.N + 1
+    tets = X[IEN - 1]                                                  # (nel, 4, 3)
+    lo_idx = np.maximum(1, np.floor((tets.min(1) - g.AABB_min) / g.cell_size).astype(int) - 1)
+    hi_idx = np.minimum(dims, np.ceil((tets.max(1) - g.AABB_min) / g.cell_size).astype(int) + 1)
+    mism = checked = 0
+    for k in range(int(dims[2])):
+        for j in range(int(dims[1])):
+            for i in range(int(dims[0])):
+                x = g.AABB_min + g.cell_size * np.array([i, j, k])
+                gi = np.clip(np.floor((x - g.AABB_min) / g.cell_size).astype(int) + 1, 1, dims)
+                cand = np.where(((lo_idx <= gi) & (gi <= hi_idx)).all(1))[0]
+                sign = -1.0
+                for e in cand:
+                    T = tets[e]
+                    if (x < T.min(0) - 1e-10).any() or (x > T.max(0) + 1e-10).any():
+                        continue
+                    lam = np.linalg.solve(np.vstack([T.T, np.ones(4)]), np.append(x, 1.0))
+                    if not ((lam >= -1e-10).all() and (lam <= 1 + 1e-10).all()):
+                        continue
+                    l234 = np.linalg.solve((T[1:] - T[0]).T, x - T[0])
+                    l1 = 1.0 - l234.sum()
+                    full = np.array([l1, *l234])
+                    if not ((full >= 0).all() and full.sum() <= 1.0):
+                        continue
+                    N = np.array([l1, l234[0], l234[1], 1.0 - l1 - l234[0] - l234[1]])
+                    if N @ rn[IEN[e] - 1] >= 0.5:
+                        sign = 1.0
+                        break
+                checked += 1
+                mism += int(sign != so[k, j, i])
+    # LAPACK's pivoted solves and the oracle's adjugate formulas differ in the last bit: a point exactly on a shared face can be
+    # accepted by one and rejected by the other (the reference's own sum(lambda) <= 1.0 test is that sharp) -- allow a handful
+    assert checked == int(np.prod(dims)) and (so > 0).sum() > 50
+    assert mism <= 0.01 * checked, (mism, checked)
+
+
+def test_volume_from_sdf_matches_literal_restatement():
+    """calculate_volume_from_sdf (CalcVolumeFromSDF.jl:26-125) restated literally in numpy (Float32 lerps in the reference's order, 9^3
+    Gauss points in cut cells, full cells counted whole) on a random smooth field; and LS_Threshold's bisection (RBFs4Smoothing.jl:265-300)
+    driven by it reaches the same offset as a bisection driven by the oracle's volume."""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    from scipy import ndimage
+    sdf = ndimage.gaussian_filter(rng.standard_normal((11, 13, 12)), 1.5).astype(f32) * f32(4)       # [k, j, i]
+    edge = f32(0.37)
+    gp, gw = np.polynomial.legendre.leggauss(9)
+    gp, gw = gp.astype(f32), gw.astype(f32)
+
+    def volume(field, iso=f32(0)):
+        c = {(a, b, d): field[d:field.shape[0] - 1 + d, b:field.shape[1] - 1 + b, a:field.shape[2] - 1 + a] for a in (0, 1) for b in (0, 1) for d in (0, 1)}   # c[(i,j,k) offsets]
+        allv = np.stack(list(c.values()))
+        mn, mx = allv.min(0), allv.max(0)
+        ev = edge * edge * edge
+        jac = ev / f32(8)
+        total = np.float64((mn >= iso).sum()) * np.float64(ev)
+        cut = (mx >= iso) & (mn < iso)
+        part = np.zeros(cut.sum(), f32)
+        cc = {k: v[cut] for k, v in c.items()}
+        for kq in range(9):
+            zeta = (gp[kq] + f32(1)) / f32(2)
+            for jq in range(9):
+                eta = (gp[jq] + f32(1)) / f32(2)
+                for iq in range(9):
+                    xi = (gp[iq] + f32(1)) / f32(2)
+                    c00 = cc[(0, 0, 0)] * (f32(1) - xi) + cc[(1, 0, 0)] * xi
+                    c01 = cc[(0, 0, 1)] * (f32(1) - xi) + cc[(1, 0, 1)] * xi
+                    c10 = cc[(0, 1, 0)] * (f32(1) - xi) + cc[(1, 1, 0)] * xi
+                    c11 = cc[(0, 1, 1)] * (f32(1) - xi) + cc[(1, 1, 1)] * xi
+                    c0 = c00 * (f32(1) - eta) + c10 * eta
+                    c1 = c01 * (f32(1) - eta) + c11 * eta
+                    ps = c0 * (f32(1) - zeta) + c1 * zeta
+                    part = np.where(ps >= iso, part + (gw[iq] * gw[jq] * gw[kq]) * jac, part).astype(f32)
+        return float(total + np.float64(part.sum(dtype=np.float64)))
+
+    v_lit = volume(sdf)
+    v_or = oracle.volume_from_sdf(sdf, edge)
+    assert abs(v_lit - v_or) <= 2e-6 * v_lit                       # Float32 summation order is the only freedom
+    # LS_Threshold: th in [min, max], 40 steps, stop when |V_target - V| <= 1e-4 (absolute), V > target -> th_low = th
+    target = 0.35 * float(np.prod(np.array(sdf.shape) - 1)) * float(edge) ** 3
+
+    def bisect(vol):
+        lo, hi, n, eps, th = f32(sdf.min()), f32(sdf.max()), 0, 1.0, f32(0)
+        while n < 40 and eps > 1e-4:
+            th = (lo + hi) / f32(2)
+            cur = vol((sdf - th).astype(f32))
+            eps = abs(target - cur)
+            if cur > target:
+                lo = th
+            else:
+                hi = th
+            n += 1
+        return float(th)
+
+    th_lit = bisect(volume)
+    th_or = bisect(lambda f: oracle.volume_from_sdf(f, edge))
+    assert abs(th_lit - th_or) <= 1e-5 * float(np.abs(sdf).max())
