@@ -98,7 +98,7 @@ struct r2s_ctx {
   // connected components
   DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all, cc_gsz, cc_seen;
   // smoothing
-  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, vlist[2];
+  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2];
   int smooth_last = 1;
 
   // volumes
