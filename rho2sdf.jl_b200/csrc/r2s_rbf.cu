@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const f
   for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
   if (lane == 0 && local) atomicAdd(&acc[2], local);
 }
-// ---- cut cells split into slabs (default path of the bisection and of the final volume) -----------------------------
+// ---- cut cells split into slabs (experimental variant, R2S_VOLCUT=1; slower than k_vol_cut as measured, see vol_bisect_step) ---
 // For a fixed first Gauss coordinate the 81 remaining points of a cut cell are a bilinear patch between four lerped corner
 // values: if all four are >= 0 every point of the slab is inside, if all four are < 0 none is (exact also in Float32: a lerp of
 // non-negative numbers with weights in (0, 1) is non-negative, and likewise for negative ones).  Pass 1 (one thread per cut
@@ -758,7 +758,10 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
       else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
     }
     LAUNCH_CHECK();
-    static const bool slabs = !(getenv("R2S_VOLCUT") && atoi(getenv("R2S_VOLCUT")) == 0);      // R2S_VOLCUT=0: evaluate all 729 points of every cut cell
+    // R2S_VOLCUT=1 selects the slab-split variant below.  Measured on B200 (256^3 case): threshold stage 67.6 ms vs 25.0 ms for the
+    // plain one-thread-per-cell kernel -- the second gather of the corner values and the queue traffic cost more than the skipped
+    // Gauss points save -- so it stays off; kept because it evaluates only ~1/3 of the points and is parity-tested.
+    static const bool slabs = getenv("R2S_VOLCUT") && atoi(getenv("R2S_VOLCUT")) == 1;
     if (slabs) {
       static const SlabConst KS = slab_const();
       CK(ctx->slablist.reserve(sizeof(u64) * 9 * (size_t)cutcap + 64));
