@@ -481,3 +481,90 @@ def test_volume_from_sdf_matches_literal_restatement():
     th_lit = bisect(volume)
     th_or = bisect(lambda f: oracle.volume_from_sdf(f, edge))
     assert abs(th_lit - th_or) <= 1e-5 * float(np.abs(sdf).max())
+
+
+def _dense_in_nodes_literal(X, IEN, rho):
+    """DenseInNodes with FilterForNodalDensity, NodalDensityLeastSquares and LamReduction (NodalDensities.jl:89-218) in numpy, with
+    LAPACK's symmetric eigen-solver standing where Julia calls eigen(A'A)."""
+    nnp, nel = X.shape[0], IEN.shape[0]
+    centre = X[IEN - 1].mean(axis=1)
+    ine = [[] for _ in range(nnp)]
+    for e in range(nel):
+        for nd in IEN[e]:
+            ine[nd - 1].append(e)
+    out = np.zeros(nnp)
+    for i in range(nnp):
+        els = ine[i]
+        if len(els) == 1:
+            out[i] = rho[els[0]]
+        elif len(els) < 4:
+            L = np.array([np.linalg.norm(X[i] - centre[e]) for e in els])
+            Lmax = L.max() * 1.2
+            wts = 1 - L / Lmax
+            out[i] = float((rho[els] * wts).sum() / wts.sum())
+        else:
+            A = np.column_stack([np.ones(len(els)), centre[els]])
+            b = rho[els]
+            lam, phi = np.linalg.eigh(A.T @ A)
+            e1, e2, e3 = abs(lam.max() / lam.min()), abs(lam.max() / lam[1]), abs(lam.max() / lam[2])
+            if 1e7 > e1 and 3e3 > e2:
+                keep = lam
+            elif 1e7 < e1 and 3e3 > e2:
+                keep = lam[1:]
+            elif 1e7 < e1 and 3e3 < e2:
+                keep = lam[2:] if 3e3 > e3 else lam[3:]
+            else:
+                keep = np.array([])
+            if keep.size == 0:
+                out[i] = b.mean()
+            else:
+                poz = lam.size - keep.size
+                b1 = phi.T @ (A.T @ b)
+                x2 = np.concatenate([np.zeros(poz), b1[poz:] / keep])
+                out[i] = float(np.concatenate([[1.0], X[i]]) @ (phi @ x2))
+    return out
+
+
+@pytest.mark.parametrize("name", ["sphere", "cantilever_beam_vfrac_03"])
+def test_nodal_densities_match_literal_restatement(name):
+    X, IEN, rho = load_mesh(name)
+    lit = _dense_in_nodes_literal(X, IEN, rho)
+    orc = oracle.nodal_densities(X, IEN, rho)
+    # LAPACK eigh vs the oracle's Jacobi sweeps: with A'A conditioned like 1e4..1e7 (coordinates up to 60 on the cantilever) the two
+    # eigen-decompositions differ by ~cond * eps in the fitted value -- a few 1e-12, the same level at which Julia's LAPACK would differ
+    assert np.abs(lit - orc).max() <= (1e-12 if name == "sphere" else 1e-11)
+    if name == "sphere":
+        assert abs(lit.mean() - 0.29490556408887564) <= 1e-12          # the reference's golden (HexSphereSdfTest.jl:27)
+
+
+def test_mesh_volume_matches_literal_restatement():
+    """calculate_mesh_volume (MeshVolume.jl:4-117): 3^3 Gauss points, |det J| weights; HEX8 on an unstructured mesh and the TET4
+    cube-to-tet mapping with the reference's (1-xi)^2 (1-xi-eta)/8 factor."""
+    gp, gw = np.polynomial.legendre.leggauss(3)
+    SG = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
+    X, IEN, rho = load_mesh("chapadlo")
+    sel = np.arange(0, IEN.shape[0], 37)                # every 37th element is plenty
+    vol = np.zeros(sel.size)
+    for k in range(3):
+        for j in range(3):
+            for i in range(3):
+                xi = np.array([gp[i], gp[j], gp[k]])
+                t = 1 + SG * xi
+                dN = 0.125 * np.stack([SG[:, 0] * t[:, 1] * t[:, 2], SG[:, 1] * t[:, 0] * t[:, 2], SG[:, 2] * t[:, 0] * t[:, 1]], axis=1)
+                J = np.einsum("eai,aj->eij", X[IEN[sel] - 1], dN)
+                vol += gw[i] * gw[j] * gw[k] * np.abs(np.linalg.det(J))
+    vd, vf = oracle.mesh_volume(X, IEN[sel], rho[sel])
+    assert abs(vd - vol.sum()) <= 1e-10 * vol.sum() and abs(vf - (vol * rho[sel]).sum() / vol.sum()) <= 1e-12
+    # TET4
+    Xt, T, rn = schlafli_tet4(3, "radial")
+    dNt = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, -1, -1]], float)
+    vt = 0.0
+    for e in range(T.shape[0]):
+        Jd = abs(np.linalg.det(Xt[T[e] - 1].T @ dNt))
+        for k in range(3):
+            for j in range(3):
+                for i in range(3):
+                    xi = (gp[i] + 1) / 2; eta = (gp[j] + 1) / 2 * (1 - xi)
+                    vt += gw[i] * gw[j] * gw[k] * Jd * (1 - xi) ** 2 * (1 - xi - eta) / 8.0
+    vdt, _ = oracle.mesh_volume(Xt, T, np.ones(T.shape[0]))
+    assert abs(vdt - vt) <= 1e-10 * vt and abs(vdt - 0.75 * 27) < 1e-9
