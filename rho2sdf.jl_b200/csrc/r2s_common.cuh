@@ -76,6 +76,7 @@ struct r2s_ctx {
   int nen = 0, nes = 0, nsn = 0;
   i64 nnp = 0, nel = 0;
   DevBuf X, IEN32, ine_ptr, ine_el, fbnd, ezr;   // X double[3*nnp]; IEN32 int[nen*nel] 0-based; INE CSR; fbnd uint8[nel]
+  DevBuf ebox; i64 n_box = 0;                    // HEX8: uint8[nel] 1 = axis-aligned box in canonical node order (iso::HexBox), and their count
   DevBuf rho_e, rho_n;
 
   // grid

@@ -10,6 +10,7 @@
 //                 early-outs, then the element's iso distance from the pair buffer).  Bit-exact decisions (r2s_exact.cuh).
 //                 No atomics: every voxel is owned by one thread, the result is deterministic.
 #include <stdlib.h>
+#include <type_traits>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
 #include "r2s_exact.cuh"
@@ -88,17 +89,21 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
 }
 
 // ------------------------------------------------------------------------------------------------ project (hot, FP64)
-// one warp per 32-point chunk of a crossing element
-template <bool WANT_XP, int MINB, bool SMEM_A>
+// one warp per 32-point chunk of a crossing element.  BOX: the variant for axis-aligned box elements (iso::HexBox: 17 element
+// constants instead of 32, about half the FP64 work per iteration); kind_check != 0: the mesh holds both kinds of elements and
+// each of the two launches leaves the chunks of the other kind alone (ebox[e] = 1 for boxes, built with the mesh).
+template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
-                                                      double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters) {
+                                                      double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters,
+                                                      const unsigned char *__restrict__ ebox, int kind_check) {
   i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
   if (item >= nitems) return;
   // binary search: last a with choff[a] <= item
   i64 lo = 0, hi = nact - 1;
   while (lo < hi) { i64 mid = (lo + hi + 1) >> 1; if (choff[mid] <= item) lo = mid; else hi = mid - 1; }
   const ActRec r = rec[lo];
+  if (kind_check && (ebox[r.el] != 0) != BOX) return;
   int chunk = (int)(item - choff[lo]);
   // element data: lane l < 8 loads node l; monomial coefficients assembled through shuffles
   double v[4] = {0, 0, 0, 0};
@@ -134,9 +139,16 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   if (li < vol) {
     int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
     double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]};
-    double xi[3];
-    okc = iso::project_hex8(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
-    double p[3]; iso::eval_pos(A, xi, p);
+    double xi[3], p[3];
+    if (BOX) {
+      iso::HexBox B; iso::make_box(A, B);
+      okc = iso::project_hex8(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+      iso::eval_pos(B, xi, p);
+    } else {
+      const iso::HexTri T{A};
+      okc = iso::project_hex8(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+      iso::eval_pos(T, xi, p);
+    }
     double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
     pairbuf[r.pair_off + li] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
     if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
@@ -159,14 +171,16 @@ __global__ void k_fill_f64(i64 n, double *__restrict__ a, double v) {
   i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
 }
-template <int MINB>
+template <int MINB, bool BOX>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
                                                           const double *__restrict__ rn, GridDev g, double rho_t, const unsigned char *__restrict__ tile_faces,
-                                                          double *__restrict__ pairbuf, double *__restrict__ dist, u64 *__restrict__ counters) {
+                                                          double *__restrict__ pairbuf, double *__restrict__ dist, u64 *__restrict__ counters,
+                                                          const unsigned char *__restrict__ ebox, int kind_check) {
   const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
   if (a >= nact) return;
   const ActRec r = rec[a];
   if (r.cls != 2) return;
+  if (kind_check && (ebox[r.el] != 0) != BOX) return;
   double v[4] = {0, 0, 0, 0};
   if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
   double A[4][8], re[8], lo[3], hi[3];
@@ -193,8 +207,12 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
   const double margin0 = 1e-12 * fmax(fmax(fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1]))), fmax(fabs(lo[2]), fabs(hi[2])));
   const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
   const int vol = nx * ny * nz;
+  // element in the solver's form: box elements keep 17 constants, the 32 monomial coefficients are dead after this point
+  typedef typename std::conditional<BOX, iso::HexBox, iso::HexTri>::type ElemT;
+  ElemT EL;
+  if constexpr (BOX) iso::make_box(A, EL); else EL.A = A;
   // phase 1 once per element (it does not depend on the grid point)
-  iso::ProjState S0; const bool ok0 = iso::proj_init_element(A, rho_t, gs, S0);
+  iso::ProjState S0; const bool ok0 = iso::proj_init_element(EL, rho_t, gs, S0);
   bool busy = false, to_buf = false; iso::ProjState S = S0; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
   int sweep = 0, next = 0, its = 0, nbad = 0, npruned = 0;
   while (true) {
@@ -218,7 +236,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
           if (prune) npruned++;
           else {
             li = cand; busy = true; vox = vx; to_buf = tb; x[0] = x0; x[1] = x1; x[2] = x2; S = S0;
-            if (!ok0 && !iso::proj_init(A, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(A, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
+            if (!ok0 && !iso::proj_init(EL, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(EL, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
           }
         }
       }
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
     if (!__any_sync(0xffffffffu, busy)) break;
     if (busy) {
       int status = 2;
-      if (S.it < 100) status = iso::proj_iter(A, x, rho_t, gs, S);
+      if (S.it < 100) status = iso::proj_iter(EL, x, rho_t, gs, S);
       if (status != 0 || S.it >= 100) {
         if (S.it >= 1000) nbad++; else { its += S.it; if (status != 1) nbad++; }
         const double dd = sqrt(S.f);
@@ -662,18 +680,23 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     CK(cudaMemcpyAsync(ctx->tile_ptr.as<int>(), tmp.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
-  // HEX8 without xp: lane-refill projection with per-voxel atomicMin (face-free tiles) + exact replay of the tiles with boundary faces
-  static const bool refill = getenv("R2S_PROJ") && atoi(getenv("R2S_PROJ")) == 1;       // experimental lane-refill projection (not faster yet)
+  // HEX8 without xp: lane-refill projection with per-voxel atomicMin (face-free tiles) + exact replay of the tiles with boundary faces.
+  // (The R2S_PROJ* tuning knobs are read on every call so that one process can time the variants side by side, tools/ab_project.py.)
+  const bool refill = getenv("R2S_PROJ") && atoi(getenv("R2S_PROJ")) == 1;       // experimental lane-refill projection (not faster yet)
   const bool minpath = (refill && nen == 8 && !want_xp);
   if (minpath) {
     i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
     if (nact > 0 && npairs > 0) {
       // occupancy variant (registers per thread 255 / 168 / 128): R2S_PROJ_MINB = 2, 3, 4 (tuning knob, default from measurements)
-      static const int minbr = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
-#define PMIN(MB) k_project_hex8_min<MB><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
-                                                              ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>())
-      if (minbr <= 2) PMIN(2); else if (minbr == 3) PMIN(3); else PMIN(4);
+      const int minbr = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
+      // box elements (n_box of them, flag built with the mesh) go through the HexBox variant; a mixed mesh takes both launches
+      const bool use_box_r = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
+      const i64 nbx = use_box_r ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
+#define PMIN(MB, BX) k_project_hex8_min<MB, BX><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
+                                                              ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc)
+      if (nbx < nel) { if (minbr <= 2) PMIN(2, false); else if (minbr == 3) PMIN(3, false); else PMIN(4, false); LAUNCH_CHECK(); }
+      if (nbx > 0) { if (minbr <= 2) PMIN(2, true); else if (minbr == 3) PMIN(3, true); else PMIN(4, true); }
 #undef PMIN
       LAUNCH_CHECK();
     }
@@ -684,15 +707,28 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
                                                    ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
     // variants of the HEX8 kernel: R2S_PROJ_MINB = 2..6 CTAs/SM (255 / 168 / 128 / 102 / 85 registers), R2S_PROJ_SMEMA = 1 keeps the
     // element's monomial coefficients in shared memory
-    static const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
-    static const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
-#define PROJH(XP, MB, SA) k_project_hex8<XP, MB, SA><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
-                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
+    const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
+    const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
+#define PROJH(XP, MB, SA, BX) k_project_hex8<XP, MB, SA, BX><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
+                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc)
+    // Axis-aligned box elements (flag + count built with the mesh) take the HexBox variant of the kernel, the others the general
+    // trilinear one; a mesh with both kinds takes both launches, each leaving the other kind's chunks alone.  R2S_PROJ_BOX=0
+    // sends everything through the general kernel; R2S_PROJ_BOX_MINB = CTAs/SM of the box variant (4 / 5 / 6).
+    const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
+    const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 4;
+    const i64 nbx = (use_box && nen == 8) ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
     if (nen == 8) {
-      if (want_xp) PROJH(true, 2, false);
-      else if (smema) { if (minb <= 4) PROJH(false, 4, true); else if (minb == 5) PROJH(false, 5, true); else PROJH(false, 6, true); }
-      else if (minb <= 2) PROJH(false, 2, false); else if (minb == 3) PROJH(false, 3, false); else if (minb == 4) PROJH(false, 4, false);
-      else if (minb == 5) PROJH(false, 5, false); else PROJH(false, 6, false);
+      if (nbx < nel) {
+        if (want_xp) PROJH(true, 2, false, false);
+        else if (smema) { if (minb <= 4) PROJH(false, 4, true, false); else if (minb == 5) PROJH(false, 5, true, false); else PROJH(false, 6, true, false); }
+        else if (minb <= 2) PROJH(false, 2, false, false); else if (minb == 3) PROJH(false, 3, false, false); else if (minb == 4) PROJH(false, 4, false, false);
+        else if (minb == 5) PROJH(false, 5, false, false); else PROJH(false, 6, false, false);
+        if (nbx > 0) LAUNCH_CHECK();
+      }
+      if (nbx > 0) {
+        if (want_xp) PROJH(true, 4, false, true);
+        else if (minb_box <= 4) PROJH(false, 4, false, true); else if (minb_box == 5) PROJH(false, 5, false, true); else PROJH(false, 6, false, true);
+      }
     } else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
     LAUNCH_CHECK();
 #undef PROJH

@@ -75,8 +75,82 @@ __device__ __forceinline__ double Hl(const Eval &E, double lam, int i, int j) {
   return E.Hgn[i][j] + fma(lam, E.hg[p], E.m[p]);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Element types of the solver.  HexTri: general trilinear geometry, monomial coefficients [x,y,z,rho][8].  HexBox: the
+// element is an axis-aligned box in canonical node order, X_d(xi) = c_d + h_d xi_d (every mixed coefficient of the three
+// geometry fields is EXACTLY zero -- true for every voxel-type SIMP mesh, since each nodal coordinate then takes one of two
+// values per axis and the differences in monomial8 cancel exactly).  Dropping the exact-zero terms changes no finite value:
+// F, c, f and the diagonal of 2 J^T J are what the general formulas give; m and the off-diagonal of 2 J^T J vanish.  The
+// iteration then needs 17 element constants instead of 32 (registers) and about half the FP64 work.
+struct HexTri {
+  const double (*A)[8];
+  typedef Eval EvalT;
+};
+struct HexBox {
+  double R[8];            // monomial coefficients of rho
+  double c[3], h[3];      // X_d = c_d + h_d xi_d
+  double hh[3];           // 2 h_d^2 = diagonal of 2 J^T J
+  struct EvalT {
+    double f, g, F[3], c[3], a[3];
+    double hh[3];         // diagonal of Hess f (constant)
+    double hg[3];         // off-diagonal terms of Hess g, pairs (0,1),(1,2),(2,0)
+  };
+};
+// true when the geometry coefficients A[0..2] describe a box in canonical orientation
+__device__ __forceinline__ bool is_box(const double A[4][8]) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int k = 1; k < 8; k++) if (k != d + 1 && A[d][k] != 0.0) ok = false;
+  return ok;
+}
+__device__ __forceinline__ void make_box(const double A[4][8], HexBox &B) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) B.R[k] = A[3][k];
+#pragma unroll
+  for (int d = 0; d < 3; d++) { B.c[d] = A[d][0]; B.h[d] = A[d][d + 1]; B.hh[d] = 2.0 * (A[d][d + 1] * A[d][d + 1]); }
+}
+// rho-field part shared by both element types (R = monomial coefficients of rho)
+__device__ __forceinline__ void eval_g_R(const double R[8], double rho_t, const double xi[3], double &g, double a[3]) {
+  double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
+  g = tri_val(R, X, E, Z, xe, ez, zx, xez) - rho_t;
+  a[0] = fma(R[7], ez, fma(R[6], Z, fma(R[4], E, R[1])));
+  a[1] = fma(R[7], zx, fma(R[5], Z, fma(R[4], X, R[2])));
+  a[2] = fma(R[7], xe, fma(R[6], X, fma(R[5], E, R[3])));
+}
+// HexTri overloads: the array forms above, unchanged
+__device__ __forceinline__ void eval_g(const HexTri &T, double rho_t, const double xi[3], double &g, double a[3]) { eval_g(T.A, rho_t, xi, g, a); }
+__device__ __forceinline__ void eval_pos(const HexTri &T, const double xi[3], double p[3]) { eval_pos(T.A, xi, p); }
+__device__ __forceinline__ double eval_f(const HexTri &T, const double x[3], const double xi[3]) { return eval_f(T.A, x, xi); }
+__device__ __forceinline__ void eval_full(const HexTri &T, const double x[3], double rho_t, const double xi[3], Eval &E) { eval_full(T.A, x, rho_t, xi, E); }
+__device__ __forceinline__ double hdiag(const Eval &E, int i) { return E.Hgn[i][i]; }
+// HexBox overloads
+__device__ __forceinline__ void eval_g(const HexBox &B, double rho_t, const double xi[3], double &g, double a[3]) { eval_g_R(B.R, rho_t, xi, g, a); }
+__device__ __forceinline__ void eval_pos(const HexBox &B, const double xi[3], double p[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; d++) p[d] = fma(B.h[d], xi[d], B.c[d]);
+}
+__device__ __forceinline__ double eval_f(const HexBox &B, const double x[3], const double xi[3]) {
+  double F0 = fma(B.h[0], xi[0], B.c[0]) - x[0], F1 = fma(B.h[1], xi[1], B.c[1]) - x[1], F2 = fma(B.h[2], xi[2], B.c[2]) - x[2];
+  return fma(F2, F2, fma(F1, F1, F0 * F0));
+}
+__device__ __forceinline__ void eval_full(const HexBox &B, const double x[3], double rho_t, const double xi[3], HexBox::EvalT &E_) {
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    E_.F[d] = fma(B.h[d], xi[d], B.c[d]) - x[d];
+    E_.c[d] = 2.0 * (B.h[d] * E_.F[d]);
+    E_.hh[d] = B.hh[d];
+  }
+  E_.f = fma(E_.F[2], E_.F[2], fma(E_.F[1], E_.F[1], E_.F[0] * E_.F[0]));
+  eval_g_R(B.R, rho_t, xi, E_.g, E_.a);
+  E_.hg[0] = fma(B.R[7], xi[2], B.R[4]); E_.hg[1] = fma(B.R[7], xi[0], B.R[5]); E_.hg[2] = fma(B.R[7], xi[1], B.R[6]);
+}
+__device__ __forceinline__ double hdiag(const HexBox::EvalT &E, int i) { return E.hh[i]; }
+
 // Newton restoration onto g = 0 moving only variables with fix[i] == 0; variables leaving the box are clamped and fixed
-__device__ __forceinline__ bool restore(const double A[4][8], double rho_t, double xi[3], int fix[3], double tolg) {
+template <class EL>
+__device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3], int fix[3], double tolg) {
   for (int it = 0; it < 40; it++) {
     double g, a[3]; eval_g(A, rho_t, xi, g, a);
     if (fabs(g) <= tolg) return true;
@@ -134,7 +208,41 @@ __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3])
 #pragma unroll
   for (int i = 0; i < 3; i++) d[i] = fma(y1, z1[i], y2 * z2[i]);
 }
-__device__ __forceinline__ void tangent_step(const Eval &E, const int fix[3], double lam, double d[3]) {
+// HexBox: Hess f = diag(hh), Hess of the Lagrangian = diag(hh) + lam * (off-diagonal hg); the null-space vectors
+// z1 = a_K e_U - a_U e_K, z2 = a_K e_V - a_V e_K have one zero component each, which is used explicitly
+__device__ __forceinline__ int pair_of(int i, int j) { return (i + j == 1) ? 0 : ((i + j == 3) ? 1 : 2); }
+template <int I, int J>
+__device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, double d[3]) {
+  double zi = -E.a[J], zj = E.a[I];
+  double zz = fma(zi, zi, zj * zj);
+  if (!(zz > 0.0)) return;
+  double hii = E.hh[I], hij = lam * E.hg[pair_of(I, J)], hjj = E.hh[J];
+  double kap = zi * fma(hii, zi, hij * zj) + zj * fma(hij, zi, hjj * zj);
+  double kgn = zi * (hii * zi) + zj * (hjj * zj);
+  if (!(kap > 1e-8 * kgn)) kap = kgn;
+  if (!(kap > 0.0)) return;
+  double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
+  d[I] = t * zi; d[J] = t * zj;
+}
+template <int K>
+__device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, double d[3]) {
+  constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
+  const double aK = E.a[K], aU = E.a[U], aV = E.a[V];
+  const double HUK = lam * E.hg[pair_of(U, K)], HUV = lam * E.hg[pair_of(U, V)], HKV = lam * E.hg[pair_of(K, V)];
+  const double Hz1U = fma(E.hh[U], aK, -(HUK * aU)), Hz1K = fma(HUK, aK, -(E.hh[K] * aU));
+  const double Hz2U = fma(HUV, aK, -(HUK * aV)), Hz2K = fma(HKV, aK, -(E.hh[K] * aV)), Hz2V = fma(E.hh[V], aK, -(HKV * aV));
+  double m11 = fma(aK, Hz1U, -(aU * Hz1K)), m12 = fma(aK, Hz2U, -(aU * Hz2K)), m22 = fma(aK, Hz2V, -(aV * Hz2K));
+  const double kK = E.hh[K] * aU;
+  double g11 = fma(E.hh[U] * aK, aK, kK * aU), g12 = kK * aV, g22 = fma(E.hh[V] * aK, aK, (E.hh[K] * aV) * aV);
+  const double r1 = -fma(aK, E.c[U], -(aU * E.c[K])), r2 = -fma(aK, E.c[V], -(aV * E.c[K]));
+  double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
+  if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
+  if (!(det > 0.0 && m11 > 0.0)) return;
+  const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
+  d[U] = y1 * aK; d[V] = y2 * aK; d[K] = -fma(y1, aU, y2 * aV);
+}
+template <class EV>
+__device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], double lam, double d[3]) {
   d[0] = d[1] = d[2] = 0.0;
   int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
   if (nf < 2) return;
@@ -158,7 +266,8 @@ __device__ __forceinline__ void tangent_step(const Eval &E, const int fix[3], do
 // different grid points.  The arithmetic and its order are the same in both drivers (bit-identical results).
 struct ProjState { double xi[3]; double lam; double f; int it, stall; bool force; };      // f = |X(xi) - x|^2 at the current xi (valid once proj_iter has run)
 
-__device__ __forceinline__ bool proj_init(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
+template <class EL>
+__device__ __forceinline__ bool proj_init(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                           const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs;
   int fix[3] = {0, 0, 0};
@@ -182,13 +291,15 @@ __device__ __forceinline__ bool proj_init(const double A[4][8], const double re[
 }
 // Phase 1 without the edge fallback: the Newton projection of xi = 0 onto {g = 0} does not depend on the grid point, so a
 // warp that works on one element computes it once and hands the state to every point (same arithmetic as proj_init).
-__device__ __forceinline__ bool proj_init_element(const double A[4][8], double rho_t, double gs, ProjState &S) {
+template <class EL>
+__device__ __forceinline__ bool proj_init_element(const EL &A, double rho_t, double gs, ProjState &S) {
   int fix[3] = {0, 0, 0};
   S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
   return restore(A, rho_t, S.xi, fix, 1e-14 * gs);
 }
 // one phase-2 iteration; returns 0 = continue, 1 = converged, 2 = failed (line search exhausted)
-__device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3], double rho_t, double gs, ProjState &S) {
+template <class EL>
+__device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
   double *xi = S.xi; double lam = S.lam, dm = 0.0; bool force = S.force;
   int fix[3];
@@ -196,7 +307,7 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
     int bnd[3], tried[3] = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 3; i++) { bnd[i] = xi[i] >= 1.0 ? 1 : (xi[i] <= -1.0 ? -1 : 0); fix[i] = bnd[i]; }
-    Eval E; eval_full(A, x, rho_t, xi, E);
+    typename EL::EvalT E; eval_full(A, x, rho_t, xi, E);
     S.f = E.f;
     double d[3] = {0, 0, 0}; bool have_step = false; int status = 0;
     for (int pass = 0; pass < 8; pass++) {
@@ -217,7 +328,7 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
         d[0] = d[1] = d[2] = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; i++) if (!fix[i]) {
-          double h = E.Hgn[i][i]; if (h > 0.0) d[i] = -E.c[i] / h;    // Hess g has a zero diagonal
+          double h = hdiag(E, i); if (h > 0.0) d[i] = -E.c[i] / h;    // Hess g has a zero diagonal
         }
       }
       bool refix = false;
@@ -280,7 +391,8 @@ __device__ __forceinline__ int proj_iter(const double A[4][8], const double x[3]
   return 0;
 }
 // Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
-__device__ __forceinline__ bool project_hex8(const double A[4][8], const double re[8], const double sg[8][3], const int edges[12][2],
+template <class EL>
+__device__ __forceinline__ bool project_hex8(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                              const double x[3], double rho_t, double gs, double xi[3], int &nit) {
   ProjState S;
   if (!proj_init(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }

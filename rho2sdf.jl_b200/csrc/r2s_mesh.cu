@@ -3,6 +3,7 @@
 // threshold comparisons downstream, so they are evaluated in the reference's operation order without contraction.
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
+#include "r2s_iso.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // INE: node -> elements (MeshGrid/MeshInformations.jl:69-77), lists sorted ascending like the reference's push! order
@@ -67,6 +68,24 @@ __global__ void k_elem_zrange(i64 nel, int nen, const int *__restrict__ IEN, con
   for (int a = 0; a < nen; a++) { double z = X[3 * (i64)IEN[nen * e + a] + 2]; lo = fmin(lo, z); hi = fmax(hi, z); }
   ezr[e] = make_double2(lo, hi);
 }
+// HEX8 elements that are axis-aligned boxes in canonical node order (every mixed monomial coefficient of the geometry exactly zero):
+// the projection kernel has a variant for them (iso::HexBox, r2s_iso.cuh).  Geometry only, so the flag is built with the mesh.
+__global__ void k_elem_box(i64 nel, const int *__restrict__ IEN, const double *__restrict__ X, unsigned char *__restrict__ ebox, unsigned long long *__restrict__ count) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  bool box = false;
+  if (e < nel) {
+    double A[4][8];
+    for (int d = 0; d < 3; d++) {
+      double nv[8];
+      for (int a = 0; a < 8; a++) nv[a] = X[3 * (i64)IEN[8 * e + a] + d];
+      iso::monomial8(nv, A[d]);
+    }
+    box = iso::is_box(A) && A[0][1] != 0.0 && A[1][2] != 0.0 && A[2][3] != 0.0;
+    ebox[e] = box ? 1 : 0;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, box);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
 int r2s_mesh_build_tables(r2s_ctx *ctx) {
   i64 n = ctx->nel * ctx->nen;
   CK(ctx->ine_ptr.reserve(sizeof(int) * (size_t)(ctx->nnp + 1)));
@@ -85,6 +104,17 @@ int r2s_mesh_build_tables(r2s_ctx *ctx) {
                                                                 ctx->ine_el.as<int>(), ctx->fbnd.as<unsigned char>()); LAUNCH_CHECK();
   CK(ctx->ezr.reserve(sizeof(double2) * (size_t)ctx->nel));
   k_elem_zrange<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->ezr.as<double2>()); LAUNCH_CHECK();
+  ctx->n_box = 0;
+  if (ctx->nen == 8) {
+    const size_t flag_bytes = ((size_t)ctx->nel + 7) & ~(size_t)7;      // the 8-byte counter sits behind the flags
+    CK(ctx->ebox.reserve(flag_bytes + 8));
+    unsigned long long *dcount = (unsigned long long *)(ctx->ebox.as<unsigned char>() + flag_bytes), hcount = 0;
+    CK(cudaMemsetAsync(dcount, 0, 8, ctx->stream));
+    k_elem_box<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->ebox.as<unsigned char>(), dcount); LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&hcount, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_box = (i64)hcount;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   cnt.release(); cur.release();
   return 0;

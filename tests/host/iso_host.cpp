@@ -1,0 +1,69 @@
+// iso_host.cpp -- the device functions of rho2sdf.jl_b200/csrc/r2s_iso.cuh compiled for the HOST (g++, no CUDA runtime needed)
+// so that the per-lane arithmetic of the projection kernels can be checked against the CPU oracle without a GPU, and so that
+// the lane divergence of the warp-level drivers can be simulated offline (tools/divergence_sim.py).  Test infrastructure only.
+#include <math.h>
+#include <string.h>
+#ifndef __device__
+#define __device__
+#endif
+#ifndef __forceinline__
+#define __forceinline__ inline __attribute__((always_inline))
+#endif
+#define R2S_ISO_HOST 1
+#include "../../rho2sdf.jl_b200/csrc/r2s_iso.cuh"
+
+static const double sg[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+static const int edges[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+
+static void coefficients(const double *Xe /*[8][3]*/, const double *re, double A[4][8]) {
+  for (int c = 0; c < 4; c++) {
+    double nv[8];
+    for (int k = 0; k < 8; k++) nv[k] = c < 3 ? Xe[3 * k + c] : re[k];
+    iso::monomial8(nv, A[c]);
+  }
+}
+static double gscale(const double *re, double rho_t) {
+  double gs = fabs(rho_t);
+  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
+  return fmax(gs, 1.0);
+}
+
+extern "C" {
+// variant 0: general trilinear path, 1: box path (returns -2 when the element is not a canonical axis-aligned box)
+// out: xi[3], dist; trace (optional, length >= 128): per phase-2 iteration the status code.  Returns 1 converged, 0 failed.
+int iso_host_project(const double *Xe, const double *re, const double *x, double rho_t, int variant, double *xi, double *dist, int *nit) {
+  double A[4][8]; coefficients(Xe, re, A);
+  const double gs = gscale(re, rho_t);
+  bool ok; double p[3];
+  if (variant == 0) {
+    iso::HexTri T{(const double(*)[8])A};
+    ok = iso::project_hex8(T, re, sg, edges, x, rho_t, gs, xi, *nit);
+    iso::eval_pos(T, xi, p);
+  } else {
+    if (!iso::is_box(A)) return -2;
+    iso::HexBox B; iso::make_box(A, B);
+    ok = iso::project_hex8(B, re, sg, edges, x, rho_t, gs, xi, *nit);
+    iso::eval_pos(B, xi, p);
+  }
+  const double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
+  *dist = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+  return ok ? 1 : 0;
+}
+int iso_host_is_box(const double *Xe, const double *re) { double A[4][8]; coefficients(Xe, re, A); return iso::is_box(A) ? 1 : 0; }
+// batch over n points of ONE element; its[n] receives the phase-2 iteration count (the quantity a warp waits on)
+int iso_host_project_many(const double *Xe, const double *re, long n, const double *x, double rho_t, int variant, double *dist, int *its) {
+  double A[4][8]; coefficients(Xe, re, A);
+  const double gs = gscale(re, rho_t);
+  iso::HexTri T{(const double(*)[8])A}; iso::HexBox B;
+  if (variant == 1) { if (!iso::is_box(A)) return -2; iso::make_box(A, B); }
+  int bad = 0;
+  for (long q = 0; q < n; q++) {
+    double xi[3], p[3]; int nit = 0; bool ok;
+    if (variant == 0) { ok = iso::project_hex8(T, re, sg, edges, x + 3 * q, rho_t, gs, xi, nit); iso::eval_pos(T, xi, p); }
+    else { ok = iso::project_hex8(B, re, sg, edges, x + 3 * q, rho_t, gs, xi, nit); iso::eval_pos(B, xi, p); }
+    const double d0 = x[3 * q] - p[0], d1 = x[3 * q + 1] - p[1], d2 = x[3 * q + 2] - p[2];
+    dist[q] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0))); its[q] = nit; bad += ok ? 0 : 1;
+  }
+  return bad;
+}
+}
