@@ -335,3 +335,45 @@ def test_tet4_two_million_tets_public_api(r2s):
     # determinism through the public entry point
     fine2, _, _, sdf2, _ = r2s.rho2sdf_tet4("tet", X, IEN, rho, threshold_density=0.5, sdf_grid_setup="automatic", rbf_grid="fine", return_report=True)
     assert np.array_equal(sdf, sdf2) and np.array_equal(fine, fine2)
+
+
+def _mixed_mesh(n=10):
+    """Half axis-aligned boxes, half distorted hexes (interior nodes of the x > mid half jittered by +-0.12 h)."""
+    X, IEN, rho = simp_hex8(n)
+    X = X.copy()
+    h = (X[:, 0].max() - X[:, 0].min()) / n
+    rng = np.random.default_rng(7)
+    lo, hi = X.min(0), X.max(0)
+    inner = np.all((X > lo + 0.5 * h) & (X < hi - 0.5 * h), axis=1) & (X[:, 0] > 0.5 * (lo[0] + hi[0]) + 0.25 * h)
+    X[inner] += rng.uniform(-0.12, 0.12, (int(inner.sum()), 3)) * h
+    return X, IEN, rho
+
+
+def test_mixed_box_and_distorted_hexes(r2s, monkeypatch):
+    """A mesh holding both kinds of HEX8 elements -- axis-aligned boxes (HexBox variant of the projection kernel) and
+    distorted hexes (general trilinear variant): both launches run, each leaving the other kind alone; sending everything
+    through the general kernel (R2S_PROJ_BOX=0) gives the same field."""
+    n = 10
+    X, IEN, rho = _mixed_mesh(n)
+    mesh = r2s.Mesh(X, IEN, rho)
+    grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+    rn = r2s.DenseInNodes(mesh, rho)
+    d, od = check_distances(r2s, mesh, X, IEN, grid, rn, 0.5, 1.1)
+    monkeypatch.setenv("R2S_PROJ_BOX", "0")
+    d0, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+    assert np.max(np.abs(d0 - od)) <= DIST_TOL * grid.cell_size and np.max(np.abs(d0 - d)) <= 1e-11 * grid.cell_size
+    mesh.ctx.close()
+
+
+def test_lane_refill_projection_variant(r2s, monkeypatch):
+    """The opt-in lane-refill projection (R2S_PROJ=1: per-voxel atomicMin, AABB lower-bound pruning) on the mixed mesh."""
+    n = 10
+    X, IEN, rho = _mixed_mesh(n)
+    mesh = r2s.Mesh(X, IEN, rho)
+    grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+    rn = r2s.DenseInNodes(mesh, rho)
+    od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.5, 1.1, want_xp=False)
+    monkeypatch.setenv("R2S_PROJ", "1")
+    d1, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+    assert np.max(np.abs(d1 - od)) <= DIST_TOL * grid.cell_size
+    mesh.ctx.close()
