@@ -108,6 +108,13 @@ def base_config(n):
             "remove_artifacts": True, "smoothing_dtype": "f32 (as the reference)"}
 
 
+def rep_box_elements(mesh):
+    """Number of axis-aligned box elements of the mesh (they take the HexBox variant of the projection kernel)."""
+    n = C.c_int64(0)
+    mesh.ctx.check(mesh.ctx.lib.r2s_mesh_box_elements(mesh.ctx.h, C.byref(n)))
+    return int(n.value)
+
+
 def fine_voxels(grid, smooth):
     return int(np.prod([int(v) * smooth + 1 for v in grid.N]))
 
@@ -305,11 +312,22 @@ def run_gpu(args):
         for s in stages.values():
             s["frac"] = (s["achieved"] / s["peak"]) if s["achieved"] and s["peak"] else None
         dom = stages["project_hex8"]
-        traffic = None
+        # DRAM bytes per launch from the committed ncu --set full capture -- only quoted when it was taken on the kernel variant that
+        # ran here (the capture of round 1 is the general trilinear variant; the HexBox variant has none yet)
+        traffic, traffic_note = None, None
+        try:
+            box_variant = rep_box_elements(mesh) > 0 and os.environ.get("R2S_PROJ_BOX", "1") != "0"
+        except Exception as exc:                                   # a statistic only: never let it take the bench line down
+            box_variant, traffic_note = False, "box-element count unavailable: %s" % exc
         tp = os.path.join(ROOT, "profiles", "project_hex8_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                prof = json.load(open(tp))
+                if prof.get("variant", "general") == ("box" if box_variant else "general"):
+                    traffic = prof.get("dram_bytes_per_launch")
+                else:
+                    traffic_note = "no ncu --set full capture of the %s variant yet (profiles/project_hex8_traffic.json is the %s one: %.3g B per launch)" % (
+                        "HexBox" if box_variant else "general", prof.get("variant", "general"), prof.get("dram_bytes_per_launch", float("nan")))
             except Exception:
                 traffic = None
         line = {
@@ -319,7 +337,8 @@ def run_gpu(args):
             "e2e": {"value": nfine / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(rho_n.nbytes) * world,
                     "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4), "api": "r2s_pipeline_slab (pinned host buffers)"},
             "gpu_launches": int(sum(r.launches for r in reps)),
-            "roofline": {"kernel": "k_project_hex8", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic,
+            "roofline": {"kernel": "k_project_hex8", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
+                         "variant": "HexBox (axis-aligned box elements)" if box_variant else "general trilinear",
                          "peak_source": "FP64 FMA chain micro-kernel measured in this run (r2s_measure_fma_peak); HBM peak %s" % hbm_src,
                          "algorithmic": "%.0f FP64 flop per (element, point) pair x %d pairs per launch" % (FLOP_PER_PAIR, rep.n_pairs)},
             "stages_ms": d, "kernels": stages, "cg_iteration_ms": dict(zip(("matvec", "exchange1", "update", "exchange2"), [round(float(v), 4) for v in rep.cg_probe])),

@@ -115,6 +115,10 @@ int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, do
 /* median / shortest / longest element edge; the median is the grid step of noninteractive_sdf_grid_setup (:94-109) */
 int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double *longest);
 
+/* number of HEX8 elements that are axis-aligned boxes in canonical node order (geometry statistic built by r2s_set_mesh; such
+ * elements take the box variant of the projection kernel that stands for compute_coords_on_iso, ComputeCoordsOnIso.jl:16-87) */
+int r2s_mesh_box_elements(r2s_ctx *ctx, int64_t *n_box);
+
 /* ---- result export: exportSdfToVTI (src/DataExport/ExportToVTI.jl:22-67) ----------------------------------------------- */
 /* VTK ImageData (.vti), one PointData scalar `label` ("distance" in rho2sdf, RhoToSDF.jl:267-273), raw appended block.
  * r2s_export_vti streams a device-resident result (which = 0: sdf_dists Float64 on the coarse grid, 1: fine_sdf Float32 on the

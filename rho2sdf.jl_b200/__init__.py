@@ -105,6 +105,7 @@ def load_library():
     L.r2s_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.r2s_comm_destroy.argtypes = [vp]
     L.r2s_edge_length_stats.argtypes = [vp, dp, dp, dp]
+    L.r2s_mesh_box_elements.argtypes = [vp, C.POINTER(C.c_int64)]
     L.r2s_export_vti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
     L.r2s_write_vti_host.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, vp]
     L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]

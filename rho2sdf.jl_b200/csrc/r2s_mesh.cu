@@ -343,6 +343,12 @@ __global__ void k_edge_lengths(i64 nel, int nen, int noe, const int *__restrict_
   double dx = __dsub_rn(X[3 * nb], X[3 * na]), dy = __dsub_rn(X[3 * nb + 1], X[3 * na + 1]), dz = __dsub_rn(X[3 * nb + 2], X[3 * na + 2]);
   out[t] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
 }
+extern "C" int r2s_mesh_box_elements(r2s_ctx *ctx, int64_t *n_box) {
+  if (!ctx || !n_box) return 1;
+  if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
+  *n_box = ctx->n_box;
+  return 0;
+}
 extern "C" int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double *longest) {
   if (!ctx) return 1;
   if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
