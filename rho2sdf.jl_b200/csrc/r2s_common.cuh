@@ -92,7 +92,7 @@ struct r2s_ctx {
   std::vector<double> h_pc[3];
 
   // distance / sign work buffers
-  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters;
+  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters, p1tab;
   DevBuf dist, xp, sdf, signs;
   std::vector<u64> h_counters;             // host copy of the statistics slots
   DevBuf s_rng, s_el, s_cnt, s_keys, s_keys_alt, s_tile_ptr;

@@ -14,6 +14,14 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// Host build (tests/host/iso_host.cpp) only: operation counters for the offline cost studies; nothing on the device.
+#ifdef R2S_ISO_HOST
+static long iso_counts[8];      // 0 eval_full, 1 eval_g, 2 eval_f, 3 tangent steps, 4 line-search trials, 5 active-set passes
+#define ISO_COUNT(k) (iso_counts[k]++)
+#else
+#define ISO_COUNT(k) ((void)0)
+#endif
+
 namespace iso {
 
 struct Eval {
@@ -28,6 +36,7 @@ __device__ __forceinline__ double tri_val(const double A[8], double X, double E,
 }
 // g and grad g only
 __device__ __forceinline__ void eval_g(const double A[4][8], double rho_t, const double xi[3], double &g, double a[3]) {
+  ISO_COUNT(1);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   g = tri_val(A[3], X, E, Z, xe, ez, zx, xez) - rho_t;
   a[0] = fma(A[3][7], ez, fma(A[3][6], Z, fma(A[3][4], E, A[3][1])));
@@ -40,11 +49,13 @@ __device__ __forceinline__ void eval_pos(const double A[4][8], const double xi[3
   for (int d = 0; d < 3; d++) p[d] = tri_val(A[d], X, E, Z, xe, ez, zx, xez);
 }
 __device__ __forceinline__ double eval_f(const double A[4][8], const double x[3], const double xi[3]) {
+  ISO_COUNT(2);
   double p[3]; eval_pos(A, xi, p);
   double F0 = p[0] - x[0], F1 = p[1] - x[1], F2 = p[2] - x[2];
   return fma(F2, F2, fma(F1, F1, F0 * F0));
 }
 __device__ __forceinline__ void eval_full(const double A[4][8], const double x[3], double rho_t, const double xi[3], Eval &E_) {
+  ISO_COUNT(0);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   double J[3][3], mx[3][3];
 #pragma unroll
@@ -113,6 +124,7 @@ __device__ __forceinline__ void make_box(const double A[4][8], HexBox &B) {
 }
 // rho-field part shared by both element types (R = monomial coefficients of rho)
 __device__ __forceinline__ void eval_g_R(const double R[8], double rho_t, const double xi[3], double &g, double a[3]) {
+  ISO_COUNT(1);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   g = tri_val(R, X, E, Z, xe, ez, zx, xez) - rho_t;
   a[0] = fma(R[7], ez, fma(R[6], Z, fma(R[4], E, R[1])));
@@ -132,10 +144,12 @@ __device__ __forceinline__ void eval_pos(const HexBox &B, const double xi[3], do
   for (int d = 0; d < 3; d++) p[d] = fma(B.h[d], xi[d], B.c[d]);
 }
 __device__ __forceinline__ double eval_f(const HexBox &B, const double x[3], const double xi[3]) {
+  ISO_COUNT(2);
   double F0 = fma(B.h[0], xi[0], B.c[0]) - x[0], F1 = fma(B.h[1], xi[1], B.c[1]) - x[1], F2 = fma(B.h[2], xi[2], B.c[2]) - x[2];
   return fma(F2, F2, fma(F1, F1, F0 * F0));
 }
 __device__ __forceinline__ void eval_full(const HexBox &B, const double x[3], double rho_t, const double xi[3], HexBox::EvalT &E_) {
+  ISO_COUNT(0);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     E_.F[d] = fma(B.h[d], xi[d], B.c[d]) - x[d];
@@ -148,9 +162,20 @@ __device__ __forceinline__ void eval_full(const HexBox &B, const double x[3], do
 }
 __device__ __forceinline__ double hdiag(const HexBox::EvalT &E, int i) { return E.hh[i]; }
 
+// FAST variant of the solver (template flag, off by default): restore() leaves without the confirming evaluation once the step
+// just taken is so short that the remainder of the trilinear field is below tolg:
+//   g(xi + D) - g(xi) - a.D = R4 D0 D1 + R5 D1 D2 + R6 D2 D0 + R7 (xi0 D1 D2 + xi1 D2 D0 + xi2 D0 D1 + D0 D1 D2),
+// so |g_new| <= (|R4| + |R5| + |R6| + 4 |R7|) |D|^2 for |xi|, |D| <= 1 when D is the full Newton step (no variable clamped).
+// (A reciprocal-based replacement of the divisions was tried and dropped: the fast path of the IEEE division is itself
+// MUFU.RCP64H + Newton, about 9 FP64 instructions, so there is little to gain.)
+__device__ __forceinline__ const double *rho_coeffs(const HexTri &T) { return T.A[3]; }
+__device__ __forceinline__ const double *rho_coeffs(const HexBox &B) { return B.R; }
+
 // Newton restoration onto g = 0 moving only variables with fix[i] == 0; variables leaving the box are clamped and fixed
-template <class EL>
+template <class EL, bool FAST = false>
 __device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3], int fix[3], double tolg) {
+  double cq = 0.0;
+  if (FAST) { const double *R = rho_coeffs(A); cq = (fabs(R[4]) + fabs(R[5])) + (fabs(R[6]) + 4.0 * fabs(R[7])); }
   for (int it = 0; it < 40; it++) {
     double g, a[3]; eval_g(A, rho_t, xi, g, a);
     if (fabs(g) <= tolg) return true;
@@ -159,17 +184,19 @@ __device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3],
     for (int i = 0; i < 3; i++) if (!fix[i]) den = fma(a[i], a[i], den);
     if (!(den > 0.0)) return false;
     double s = g / den;
+    bool hit = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) {
       xi[i] = fma(-s, a[i], xi[i]);
-      if (xi[i] >= 1.0) { xi[i] = 1.0; fix[i] = 1; } else if (xi[i] <= -1.0) { xi[i] = -1.0; fix[i] = -1; }
+      if (xi[i] >= 1.0) { xi[i] = 1.0; fix[i] = 1; hit = true; } else if (xi[i] <= -1.0) { xi[i] = -1.0; fix[i] = -1; hit = true; }
     }
+    if (FAST && !hit && cq * (s * s * den) <= 0.5 * tolg) return true;      // the remainder after this full Newton step is below tolg
   }
   return false;
 }
 
 // tangent step, two free variables (I,J), K fixed
-template <int I, int J>
+template <int I, int J, bool FAST = false>
 __device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3]) {
   double zi = -E.a[J], zj = E.a[I];
   double zz = fma(zi, zi, zj * zj);
@@ -183,7 +210,7 @@ __device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3])
   d[I] = t * zi; d[J] = t * zj;
 }
 // tangent step, all three free; null-space basis built around component K (largest |a_K|), U=(K+1)%3, V=(K+2)%3
-template <int K>
+template <int K, bool FAST = false>
 __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3]) {
   constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
   double z1[3] = {0, 0, 0}, z2[3] = {0, 0, 0};
@@ -211,7 +238,7 @@ __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3])
 // HexBox: Hess f = diag(hh), Hess of the Lagrangian = diag(hh) + lam * (off-diagonal hg); the null-space vectors
 // z1 = a_K e_U - a_U e_K, z2 = a_K e_V - a_V e_K have one zero component each, which is used explicitly
 __device__ __forceinline__ int pair_of(int i, int j) { return (i + j == 1) ? 0 : ((i + j == 3) ? 1 : 2); }
-template <int I, int J>
+template <int I, int J, bool FAST = false>
 __device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, double d[3]) {
   double zi = -E.a[J], zj = E.a[I];
   double zz = fma(zi, zi, zj * zj);
@@ -224,7 +251,7 @@ __device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, dou
   double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
   d[I] = t * zi; d[J] = t * zj;
 }
-template <int K>
+template <int K, bool FAST = false>
 __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, double d[3]) {
   constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
   const double aK = E.a[K], aU = E.a[U], aV = E.a[V];
@@ -241,23 +268,23 @@ __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, dou
   const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
   d[U] = y1 * aK; d[V] = y2 * aK; d[K] = -fma(y1, aU, y2 * aV);
 }
-template <class EV>
+template <class EV, bool FAST = false>
 __device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], double lam, double d[3]) {
   d[0] = d[1] = d[2] = 0.0;
   int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
   if (nf < 2) return;
   if (nf == 2) {
-    if (fix[0]) tangent2<1, 2>(E, lam, d);
-    else if (fix[1]) tangent2<0, 2>(E, lam, d);
-    else tangent2<0, 1>(E, lam, d);
+    if (fix[0]) tangent2<1, 2, FAST>(E, lam, d);
+    else if (fix[1]) tangent2<0, 2, FAST>(E, lam, d);
+    else tangent2<0, 1, FAST>(E, lam, d);
     return;
   }
   int k = 0;
   if (fabs(E.a[1]) > fabs(E.a[k])) k = 1;
   if (fabs(E.a[2]) > fabs(k == 0 ? E.a[0] : E.a[1])) k = 2;
-  if (k == 0) { if (fabs(E.a[0]) > 0.0) tangent3<0>(E, lam, d); }
-  else if (k == 1) { if (fabs(E.a[1]) > 0.0) tangent3<1>(E, lam, d); }
-  else { if (fabs(E.a[2]) > 0.0) tangent3<2>(E, lam, d); }
+  if (k == 0) { if (fabs(E.a[0]) > 0.0) tangent3<0, FAST>(E, lam, d); }
+  else if (k == 1) { if (fabs(E.a[1]) > 0.0) tangent3<1, FAST>(E, lam, d); }
+  else { if (fabs(E.a[2]) > 0.0) tangent3<2, FAST>(E, lam, d); }
 }
 
 // HEX8 projection as a resumable state machine: proj_init (phase 1) + proj_iter (ONE phase-2 iteration).  A: monomial
@@ -266,13 +293,13 @@ __device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], doub
 // different grid points.  The arithmetic and its order are the same in both drivers (bit-identical results).
 struct ProjState { double xi[3]; double lam; double f; int it, stall; bool force; };      // f = |X(xi) - x|^2 at the current xi (valid once proj_iter has run)
 
-template <class EL>
+template <class EL, bool FAST = false>
 __device__ __forceinline__ bool proj_init(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                           const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs;
   int fix[3] = {0, 0, 0};
   S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
-  bool ok = restore(A, rho_t, S.xi, fix, tolg);
+  bool ok = restore<EL, FAST>(A, rho_t, S.xi, fix, tolg);
   if (!ok) {
     double best = INFINITY;
     for (int e = 0; e < 12; e++) {
@@ -291,14 +318,14 @@ __device__ __forceinline__ bool proj_init(const EL &A, const double re[8], const
 }
 // Phase 1 without the edge fallback: the Newton projection of xi = 0 onto {g = 0} does not depend on the grid point, so a
 // warp that works on one element computes it once and hands the state to every point (same arithmetic as proj_init).
-template <class EL>
+template <class EL, bool FAST = false>
 __device__ __forceinline__ bool proj_init_element(const EL &A, double rho_t, double gs, ProjState &S) {
   int fix[3] = {0, 0, 0};
   S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
-  return restore(A, rho_t, S.xi, fix, 1e-14 * gs);
+  return restore<EL, FAST>(A, rho_t, S.xi, fix, 1e-14 * gs);
 }
 // one phase-2 iteration; returns 0 = continue, 1 = converged, 2 = failed (line search exhausted)
-template <class EL>
+template <class EL, bool FAST = false>
 __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
   double *xi = S.xi; double lam = S.lam, dm = 0.0; bool force = S.force;
@@ -314,7 +341,8 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
       double num = 0, den = 0;
 #pragma unroll
       for (int i = 0; i < 3; i++) if (!fix[i]) { num = fma(E.a[i], E.c[i], num); den = fma(E.a[i], E.a[i], den); }
-      if (den > atol2) { lam = -num / den; tangent_step(E, fix, lam, d); }
+      ISO_COUNT(5);
+      if (den > atol2) { lam = -num / den; ISO_COUNT(3); tangent_step<typename EL::EvalT, FAST>(E, fix, lam, d); }
       else {
         double llo = -INFINITY, lhi = INFINITY, akk = 0.0, ckk = 0.0; bool anyk = false;
 #pragma unroll
@@ -369,7 +397,8 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
         if (xt[i] >= 1.0) { xt[i] = 1.0; fx[i] = 1; }
         if (xt[i] <= -1.0) { xt[i] = -1.0; fx[i] = -1; }
       }
-      if (restore(A, rho_t, xt, fx, tolg)) {
+      ISO_COUNT(4);
+      if (restore<EL, FAST>(A, rho_t, xt, fx, tolg)) {
         double ft = eval_f(A, x, xt);
         // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
         if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
@@ -391,13 +420,27 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
   return 0;
 }
 // Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
-template <class EL>
+template <class EL, bool FAST = false>
 __device__ __forceinline__ bool project_hex8(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                              const double x[3], double rho_t, double gs, double xi[3], int &nit) {
   ProjState S;
-  if (!proj_init(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  if (!proj_init<EL, FAST>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
   int status = 0;
-  while (S.it < 100 && status == 0) status = proj_iter(A, x, rho_t, gs, S);
+  while (S.it < 100 && status == 0) status = proj_iter<EL, FAST>(A, x, rho_t, gs, S);
+  xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
+  nit = S.it;
+  return status == 1;
+}
+// The same with phase 1 taken from a per-element table (xi0 = Newton projection of xi = 0 onto {g = 0}, ok0 = it converged): phase 1
+// does not depend on the grid point, so one thread per element can compute it once instead of every (element, point) pair.
+template <class EL, bool FAST = false>
+__device__ __forceinline__ bool project_hex8_from(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
+                                                  const double x[3], double rho_t, double gs, const double xi0[3], bool ok0, double xi[3], int &nit) {
+  ProjState S;
+  S.xi[0] = xi0[0]; S.xi[1] = xi0[1]; S.xi[2] = xi0[2]; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
+  if (!ok0 && !proj_init<EL, FAST>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  int status = 0;
+  while (S.it < 100 && status == 0) status = proj_iter<EL, FAST>(A, x, rho_t, gs, S);
   xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
   nit = S.it;
   return status == 1;

@@ -1,0 +1,106 @@
+"""The projection solver's device functions (rho2sdf.jl_b200/csrc/r2s_iso.cuh) compiled for the HOST and checked against the CPU
+oracle: per-lane arithmetic of the CUDA kernels without a GPU.  Covers the general trilinear element (HexTri), the axis-aligned box
+element (HexBox), the FAST restoration and the per-element phase 1 (the opt-in kernel variants)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SG = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
+
+
+@pytest.fixture(scope="module")
+def host():
+    src = os.path.join(HERE, "host", "iso_host.cpp")
+    so = os.path.join(HERE, "host", "libiso_host.so")
+    hdr = os.path.join(ROOT, "rho2sdf.jl_b200", "csrc", "r2s_iso.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include", src, "-o", so])
+    L = C.CDLL(so)
+    dp = np.ctypeslib.ndpointer(np.float64, flags="C")
+    L.iso_host_project_many.argtypes = [dp, dp, C.c_long, dp, C.c_double, C.c_int, dp, np.ctypeslib.ndpointer(np.int32, flags="C")]
+    L.iso_host_is_box.argtypes = [dp, dp]
+    return L
+
+
+def many(L, Xe, re, P, rho_t, variant):
+    d = np.zeros(len(P)); it = np.zeros(len(P), dtype=np.int32)
+    rc = L.iso_host_project_many(np.ascontiguousarray(Xe), np.ascontiguousarray(re), len(P), np.ascontiguousarray(P), rho_t, variant, d, it)
+    return rc, d, it
+
+
+def random_cases(rng, n, box):
+    for t in range(n):
+        c = rng.uniform(-5, 5, 3); h = rng.uniform(0.1, 1.0, 3)
+        if t % 2 == 0:
+            h[:] = h[0]
+        Xe = c + SG * h
+        if not box:
+            Xe = Xe + rng.uniform(-0.15, 0.15, (8, 3)) * h
+        re = rng.uniform(0, 1, 8)
+        if t % 3 == 0:
+            re = np.clip(rng.normal(0.5, 0.4, 8), 0.001, 1)
+        if t % 7 == 0:
+            re = 0.5 + rng.uniform(-1, 1, 8) * 1e-3          # nearly flat field: tiny gradients
+        if re.min() < 0.5 < re.max():
+            yield Xe, re, c + rng.uniform(-2.2, 2.2, (32, 3)) * h, float(h.min())
+
+
+def oracle_distance(x, Xe, re, rho_t=0.5):
+    ok, xi, _ = oracle.project_iso_hex8(x, rho_t, Xe, re)
+    return ok, np.linalg.norm(x - (np.prod(1 + SG * xi, axis=1) / 8) @ Xe)
+
+
+def test_box_detection(host):
+    rng = np.random.default_rng(0)
+    Xe = np.array([1.0, -2.0, 0.5]) + SG * np.array([0.3, 0.7, 0.2])
+    assert host.iso_host_is_box(np.ascontiguousarray(Xe), np.zeros(8)) == 1
+    assert host.iso_host_is_box(np.ascontiguousarray(Xe[[1, 2, 3, 0, 5, 6, 7, 4]]), np.zeros(8)) == 0        # rotated node order: general path
+    assert host.iso_host_is_box(np.ascontiguousarray(Xe + rng.uniform(-1e-9, 1e-9, (8, 3))), np.zeros(8)) == 0
+    assert many(host, Xe[[1, 2, 3, 0, 5, 6, 7, 4]], rng.uniform(0, 1, 8), np.zeros((1, 3)), 0.5, 1)[0] == -2
+
+
+def test_general_and_box_variants_match_the_oracle(host):
+    rng = np.random.default_rng(11)
+    worst = {0: 0.0, 1: 0.0}; npairs = 0
+    for box in (True, False):
+        for Xe, re, P, h in random_cases(rng, 300, box):
+            for v in ((0, 1) if box else (0,)):
+                _, d, _ = many(host, Xe, re, P, 0.5, v)
+                for q in range(0, len(P), 4):
+                    ok, do = oracle_distance(P[q], Xe, re)
+                    if ok:
+                        worst[v] = max(worst[v], abs(d[q] - do) / h); npairs += 1
+    assert npairs > 2000
+    assert worst[0] <= 1e-10 and worst[1] <= 1e-10, worst          # parity tolerance of the GPU tests is 1e-9 h
+
+
+def test_box_variant_equals_general_variant(host):
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for Xe, re, P, h in random_cases(rng, 1500, True):
+        _, d0, it0 = many(host, Xe, re, P, 0.5, 0)
+        _, d1, it1 = many(host, Xe, re, P, 0.5, 1)
+        worst = max(worst, float(np.abs(d0 - d1).max()) / h)
+    assert worst <= 1e-12, worst
+
+
+def test_fast_restoration_and_element_phase1_change_nothing(host):
+    """FAST only skips an evaluation whose outcome is known (|g| <= tolg by the remainder bound); phase 1 from the element is the
+    same arithmetic done once: both must reproduce the exact variants bit for bit."""
+    rng = np.random.default_rng(9)
+    for Xe, re, P, h in random_cases(rng, 1500, True):
+        _, d1, it1 = many(host, Xe, re, P, 0.5, 1)
+        for v in (2, 3):
+            _, d, it = many(host, Xe, re, P, 0.5, v)
+            assert np.array_equal(d, d1) and np.array_equal(it, it1)
+    for Xe, re, P, h in random_cases(rng, 500, False):
+        _, d0, it0 = many(host, Xe, re, P, 0.5, 0)
+        _, d4, it4 = many(host, Xe, re, P, 0.5, 4)
+        assert np.array_equal(d0, d4) and np.array_equal(it0, it4)
