@@ -8,6 +8,8 @@ Tolerances (BASELINE.json north_star):
   * Float32 smoothing: |gpu - oracle| <= 1e-3 * h (the reference itself is only reproducible to Float32 round-off there:
     Float32 atomics and a reltol-3.45e-4 CG), CG iteration count equal, volume within the bisection's 1e-4
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -377,3 +379,29 @@ def test_lane_refill_projection_variant(r2s, monkeypatch):
     d1, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
     assert np.max(np.abs(d1 - od)) <= DIST_TOL * grid.cell_size
     mesh.ctx.close()
+
+
+OPTIN = pytest.mark.skipif(os.environ.get("R2S_TEST_OPTIN") != "1", reason="opt-in kernel variants that have not run on a GPU yet: set R2S_TEST_OPTIN=1")
+
+
+@OPTIN
+@pytest.mark.parametrize("knobs", [{"R2S_PROJ_FAST": "1"}, {"R2S_PROJ_P1": "1"}, {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1"},
+                                   {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "8"}, {"R2S_PROJ": "1", "R2S_PROJ_FAST": "1"}])
+def test_optin_projection_variants(r2s, monkeypatch, knobs):
+    """FAST restoration / per-element phase-1 table (r2s_iso.cuh): on the host build they reproduce the exact variants bit for bit
+    (tests/test_iso_host.py); here the kernels that carry them, on the mixed mesh and on a replica of the bench workload."""
+    for X, IEN, rho, n in (_mixed_mesh(10) + (10,), simp_hex8(16) + (16,)):
+        mesh = r2s.Mesh(X, IEN, rho)
+        grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+        rn = r2s.DenseInNodes(mesh, rho)
+        d_ref, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+        od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.5, 1.1, want_xp=False)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        d, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+        for k in knobs:
+            monkeypatch.delenv(k)
+        assert np.max(np.abs(d - od)) <= DIST_TOL * grid.cell_size
+        if "R2S_PROJ" not in knobs:
+            assert np.array_equal(d, d_ref)                 # same arithmetic as the default kernels
+        mesh.ctx.close()

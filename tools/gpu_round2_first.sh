@@ -1,0 +1,6 @@
+#!/bin/bash
+# First GPU call of the next round: the opt-in projection variants (FAST restoration, phase-1 table) that were written after the
+# round-1 GPU budget ended.  Parity tests with the opt-in tests enabled, then the variants side by side on the bench workload.
+mkdir -p gpurun_out
+R2S_TEST_OPTIN=1 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_optin.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_optin.log
+timeout 200 python tools/ab_project.py --steps 3 > gpurun_out/ab_project_r2.jsonl 2> gpurun_out/ab_project_r2.err; echo "ab rc=$?"; cut -c1-330 gpurun_out/ab_project_r2.jsonl; tail -2 gpurun_out/ab_project_r2.err
