@@ -92,7 +92,7 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
 // Phase 1 of the iso-surface projection once per crossing element: xi0 = Newton projection of xi = 0 onto {rho = rho_t} inside the
 // element (it involves the density field only, so one table serves both element kinds); w = 1 when it converged, else the points of
 // the element take the edge fallback of proj_init.  Same arithmetic as the per-lane phase 1 (iso::proj_init_element).
-template <bool FAST>
+template <int MODE>
 __global__ void k_phase1(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ rn, double rho_t, double4 *__restrict__ p1) {
   const i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (a >= nact) return;
@@ -110,16 +110,17 @@ __global__ void k_phase1(i64 nact, const ActRec *__restrict__ rec, const int *__
   for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
   gs = fmax(gs, 1.0);
   iso::ProjState S;
-  const bool ok = iso::proj_init_element<iso::HexBox, FAST>(B, rho_t, gs, S);
+  const bool ok = iso::proj_init_element<iso::HexBox, MODE>(B, rho_t, gs, S);
   p1[a] = make_double4(S.xi[0], S.xi[1], S.xi[2], ok ? 1.0 : 0.0);
 }
 // one warp per 32-point chunk of a crossing element.  BOX: the variant for axis-aligned box elements (iso::HexBox: 17 element
 // constants instead of 32, about half the FP64 work per iteration); kind_check != 0: the mesh holds both kinds of elements and
 // each of the two launches leaves the chunks of the other kind alone (ebox[e] = 1 for boxes, built with the mesh).
-// FAST: the solver's FAST variant (r2s_iso.cuh: reciprocal-based Newton steps, restoration without the confirming evaluation).
+// MODE: solver variant (r2s_iso.cuh) -- bit 0 FAST restoration (no confirming evaluation, same results), bit 1 one code path for all
+// tangent-step cases (HexBox only, results equal to rounding).
 // P1: phase 1 of the solver (Newton projection of xi = 0 onto the iso-surface, the same for every point of an element)
 // comes from the per-element table built by k_phase1 instead of being recomputed by every lane of every chunk.
-template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX, bool FAST, bool P1>
+template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX, int MODE, bool P1>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
                                                       double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters,
@@ -171,13 +172,13 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
     if (P1) { const double4 q = p1[lo]; xi0[0] = q.x; xi0[1] = q.y; xi0[2] = q.z; ok0 = q.w != 0.0; }
     if (BOX) {
       iso::HexBox B; iso::make_box(A, B);
-      if (P1) okc = iso::project_hex8_from<iso::HexBox, FAST>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
-      else okc = iso::project_hex8<iso::HexBox, FAST>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+      if (P1) okc = iso::project_hex8_from<iso::HexBox, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
+      else okc = iso::project_hex8<iso::HexBox, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
       iso::eval_pos(B, xi, p);
     } else {
       const iso::HexTri T{A};
-      if (P1) okc = iso::project_hex8_from<iso::HexTri, FAST>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
-      else okc = iso::project_hex8<iso::HexTri, FAST>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+      if (P1) okc = iso::project_hex8_from<iso::HexTri, MODE>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
+      else okc = iso::project_hex8<iso::HexTri, MODE>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
       iso::eval_pos(T, xi, p);
     }
     double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
@@ -202,7 +203,7 @@ __global__ void k_fill_f64(i64 n, double *__restrict__ a, double v) {
   i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
 }
-template <int MINB, bool BOX, bool FAST>
+template <int MINB, bool BOX, int MODE>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
                                                           const double *__restrict__ rn, GridDev g, double rho_t, const unsigned char *__restrict__ tile_faces,
                                                           double *__restrict__ pairbuf, double *__restrict__ dist, u64 *__restrict__ counters,
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
   ElemT EL;
   if constexpr (BOX) iso::make_box(A, EL); else EL.A = A;
   // phase 1 once per element (it does not depend on the grid point)
-  iso::ProjState S0; const bool ok0 = iso::proj_init_element<ElemT, FAST>(EL, rho_t, gs, S0);
+  iso::ProjState S0; const bool ok0 = iso::proj_init_element<ElemT, MODE>(EL, rho_t, gs, S0);
   bool busy = false, to_buf = false; iso::ProjState S = S0; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
   int sweep = 0, next = 0, its = 0, nbad = 0, npruned = 0;
   while (true) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
           if (prune) npruned++;
           else {
             li = cand; busy = true; vox = vx; to_buf = tb; x[0] = x0; x[1] = x1; x[2] = x2; S = S0;
-            if (!ok0 && !iso::proj_init<ElemT, FAST>(EL, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(EL, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
+            if (!ok0 && !iso::proj_init<ElemT, MODE>(EL, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(EL, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
           }
         }
       }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
     if (!__any_sync(0xffffffffu, busy)) break;
     if (busy) {
       int status = 2;
-      if (S.it < 100) status = iso::proj_iter<ElemT, FAST>(EL, x, rho_t, gs, S);
+      if (S.it < 100) status = iso::proj_iter<ElemT, MODE>(EL, x, rho_t, gs, S);
       if (status != 0 || S.it >= 100) {
         if (S.it >= 1000) nbad++; else { its += S.it; if (status != 1) nbad++; }
         const double dd = sqrt(S.f);
@@ -724,10 +725,11 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
       // box elements (n_box of them, flag built with the mesh) go through the HexBox variant; a mixed mesh takes both launches
       const bool use_box_r = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
       const i64 nbx = use_box_r ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
-      const bool fast_r = getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1;
-#define PMIN(MB, BX, FS) k_project_hex8_min<MB, BX, FS><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
+      const bool uni_r = getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1;
+      const bool fast_r = uni_r || (getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
+#define PMIN(MB, BX, MD) k_project_hex8_min<MB, BX, MD><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
                                                               ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc)
-#define PMINF(MB, BX) do { if (fast_r) PMIN(MB, BX, true); else PMIN(MB, BX, false); } while (0)
+#define PMINF(MB, BX) do { if (uni_r && BX) PMIN(MB, BX, 3); else if (fast_r) PMIN(MB, BX, 1); else PMIN(MB, BX, 0); } while (0)
       if (nbx < nel) { if (minbr <= 2) PMINF(2, false); else if (minbr == 3) PMINF(3, false); else PMINF(4, false); LAUNCH_CHECK(); }
       if (nbx > 0) { if (minbr <= 2) PMINF(2, true); else if (minbr == 3) PMINF(3, true); else PMINF(4, true); }
 #undef PMINF
@@ -743,25 +745,30 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     // element's monomial coefficients in shared memory
     const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
     const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
-#define PROJH6(XP, MB, SA, BX, FS, PP) k_project_hex8<XP, MB, SA, BX, FS, PP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
+#define PROJH6(XP, MB, SA, BX, MD, PP) k_project_hex8<XP, MB, SA, BX, MD, PP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
                                                    ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc, p1tab)
-#define PROJH(XP, MB, SA, BX, FS) PROJH6(XP, MB, SA, BX, FS, false)
+#define PROJH(XP, MB, SA, BX, FS) PROJH6(XP, MB, SA, BX, 0, false)
     // the opt-in variants (FAST solver and / or phase 1 from the table), instantiated for the occupancies worth measuring
-#define PROJO(MB, BX) do { if (fast && use_p1) PROJH6(false, MB, false, BX, true, true); else if (fast) PROJH6(false, MB, false, BX, true, false); else PROJH6(false, MB, false, BX, false, true); } while (0)
+#define PROJO(MB, BX) do { \
+      if (uni && BX) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
+      else if (fast) { if (use_p1) PROJH6(false, MB, false, BX, 1, true); else PROJH6(false, MB, false, BX, 1, false); } \
+      else PROJH6(false, MB, false, BX, 0, true); } while (0)
     // Axis-aligned box elements (flag + count built with the mesh) take the HexBox variant of the kernel, the others the general
     // trilinear one; a mesh with both kinds takes both launches, each leaving the other kind's chunks alone.  R2S_PROJ_BOX=0
     // sends everything through the general kernel; R2S_PROJ_BOX_MINB = CTAs/SM of the box variant (4 / 5 / 6).
-    // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST variant of the solver), R2S_PROJ_P1=1 (phase 1 from a per-element table).
+    // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path, box
+    // elements), R2S_PROJ_P1=1 (phase 1 from a per-element table).
     const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
     const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 5;      // measured at n = 256: 92.6 / 86.5 / 89.5 ms for 4 / 5 / 6 CTAs per SM (profiles/r1f_ab_project_variants_n256.jsonl)
-    const bool fast = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1;
+    const bool uni = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1;
+    const bool fast = uni || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
     const bool use_p1 = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_P1") && atoi(getenv("R2S_PROJ_P1")) == 1;
     const i64 nbx = (use_box && nen == 8) ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
     const double4 *p1tab = nullptr;
     if (use_p1) {
       CK(ctx->p1tab.reserve(sizeof(double4) * (size_t)(nact + 1)));
-      if (fast) k_phase1<true><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
-      else k_phase1<false><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
+      if (fast) k_phase1<1><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
+      else k_phase1<0><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
       LAUNCH_CHECK();
       p1tab = ctx->p1tab.as<double4>();
     }

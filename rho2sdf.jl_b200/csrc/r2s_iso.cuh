@@ -13,13 +13,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 
 // Host build (tests/host/iso_host.cpp) only: operation counters for the offline cost studies; nothing on the device.
 #ifdef R2S_ISO_HOST
 static long iso_counts[8];      // 0 eval_full, 1 eval_g, 2 eval_f, 3 tangent steps, 4 line-search trials, 5 active-set passes
 #define ISO_COUNT(k) (iso_counts[k]++)
+// optional event trace of one projection (tools/divergence_model.py): codes 1 eval_g inside restore, 2 line-search trial, 3 eval_full
+// (= start of a phase-2 iteration), 10..12 tangent3<K>, 13..15 tangent2 (fixed variable 0,1,2), 16 fewer than two free variables,
+// 17 Gauss-Newton fallback of the multiplier branch
+static int *iso_trace = nullptr; static long iso_trace_n = 0, iso_trace_cap = 0;
+#define ISO_TRACE(c) do { if (iso_trace && iso_trace_n < iso_trace_cap) iso_trace[iso_trace_n++] = (c); } while (0)
 #else
 #define ISO_COUNT(k) ((void)0)
+#define ISO_TRACE(c) ((void)0)
 #endif
 
 namespace iso {
@@ -36,7 +43,7 @@ __device__ __forceinline__ double tri_val(const double A[8], double X, double E,
 }
 // g and grad g only
 __device__ __forceinline__ void eval_g(const double A[4][8], double rho_t, const double xi[3], double &g, double a[3]) {
-  ISO_COUNT(1);
+  ISO_COUNT(1); ISO_TRACE(1);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   g = tri_val(A[3], X, E, Z, xe, ez, zx, xez) - rho_t;
   a[0] = fma(A[3][7], ez, fma(A[3][6], Z, fma(A[3][4], E, A[3][1])));
@@ -55,7 +62,7 @@ __device__ __forceinline__ double eval_f(const double A[4][8], const double x[3]
   return fma(F2, F2, fma(F1, F1, F0 * F0));
 }
 __device__ __forceinline__ void eval_full(const double A[4][8], const double x[3], double rho_t, const double xi[3], Eval &E_) {
-  ISO_COUNT(0);
+  ISO_COUNT(0); ISO_TRACE(3);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   double J[3][3], mx[3][3];
 #pragma unroll
@@ -124,7 +131,7 @@ __device__ __forceinline__ void make_box(const double A[4][8], HexBox &B) {
 }
 // rho-field part shared by both element types (R = monomial coefficients of rho)
 __device__ __forceinline__ void eval_g_R(const double R[8], double rho_t, const double xi[3], double &g, double a[3]) {
-  ISO_COUNT(1);
+  ISO_COUNT(1); ISO_TRACE(1);
   double X = xi[0], E = xi[1], Z = xi[2], xe = X * E, ez = E * Z, zx = Z * X, xez = xe * Z;
   g = tri_val(R, X, E, Z, xe, ez, zx, xez) - rho_t;
   a[0] = fma(R[7], ez, fma(R[6], Z, fma(R[4], E, R[1])));
@@ -149,7 +156,7 @@ __device__ __forceinline__ double eval_f(const HexBox &B, const double x[3], con
   return fma(F2, F2, fma(F1, F1, F0 * F0));
 }
 __device__ __forceinline__ void eval_full(const HexBox &B, const double x[3], double rho_t, const double xi[3], HexBox::EvalT &E_) {
-  ISO_COUNT(0);
+  ISO_COUNT(0); ISO_TRACE(3);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     E_.F[d] = fma(B.h[d], xi[d], B.c[d]) - x[d];
@@ -172,8 +179,9 @@ __device__ __forceinline__ const double *rho_coeffs(const HexTri &T) { return T.
 __device__ __forceinline__ const double *rho_coeffs(const HexBox &B) { return B.R; }
 
 // Newton restoration onto g = 0 moving only variables with fix[i] == 0; variables leaving the box are clamped and fixed
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3], int fix[3], double tolg) {
+  constexpr bool FAST = (MODE & 1) != 0;
   double cq = 0.0;
   if (FAST) { const double *R = rho_coeffs(A); cq = (fabs(R[4]) + fabs(R[5])) + (fabs(R[6]) + 4.0 * fabs(R[7])); }
   for (int it = 0; it < 40; it++) {
@@ -196,7 +204,7 @@ __device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3],
 }
 
 // tangent step, two free variables (I,J), K fixed
-template <int I, int J, bool FAST = false>
+template <int I, int J>
 __device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3]) {
   double zi = -E.a[J], zj = E.a[I];
   double zz = fma(zi, zi, zj * zj);
@@ -210,7 +218,7 @@ __device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3])
   d[I] = t * zi; d[J] = t * zj;
 }
 // tangent step, all three free; null-space basis built around component K (largest |a_K|), U=(K+1)%3, V=(K+2)%3
-template <int K, bool FAST = false>
+template <int K>
 __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3]) {
   constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
   double z1[3] = {0, 0, 0}, z2[3] = {0, 0, 0};
@@ -238,7 +246,7 @@ __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3])
 // HexBox: Hess f = diag(hh), Hess of the Lagrangian = diag(hh) + lam * (off-diagonal hg); the null-space vectors
 // z1 = a_K e_U - a_U e_K, z2 = a_K e_V - a_V e_K have one zero component each, which is used explicitly
 __device__ __forceinline__ int pair_of(int i, int j) { return (i + j == 1) ? 0 : ((i + j == 3) ? 1 : 2); }
-template <int I, int J, bool FAST = false>
+template <int I, int J>
 __device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, double d[3]) {
   double zi = -E.a[J], zj = E.a[I];
   double zz = fma(zi, zi, zj * zj);
@@ -251,7 +259,7 @@ __device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, dou
   double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
   d[I] = t * zi; d[J] = t * zj;
 }
-template <int K, bool FAST = false>
+template <int K>
 __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, double d[3]) {
   constexpr int U = (K + 1) % 3, V = (K + 2) % 3;
   const double aK = E.a[K], aU = E.a[U], aV = E.a[V];
@@ -268,23 +276,68 @@ __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, dou
   const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
   d[U] = y1 * aK; d[V] = y2 * aK; d[K] = -fma(y1, aU, y2 * aV);
 }
-template <class EV, bool FAST = false>
+// MODE bit 1 (HexBox only): ONE code path for every tangent-step case.  The three tangent3<K> and the three tangent2<I,J> variants
+// differ only by a cyclic rotation of the indices: (K,U,V) = (K,K+1,K+2) with K = argmax |a_k| when all three variables are free,
+// K = L+1 when variable L is fixed (then V = L, the second null-space vector is dropped: m12 = r2 = 0, m22 = 1 turns the 2x2 solve
+// into tangent2's scalar step).  Lanes of a warp sit on different faces of the box; with the template variants every distinct
+// case is issued separately (the offline SIMT model, tools/divergence_model.py, attributes half of the issued work of the
+// projection kernel to that), here the rotation is a handful of selects.  Same mathematics, rounding differs in the last bits.
+__device__ __forceinline__ double rot3(int k, double x0, double x1, double x2) { return k == 0 ? x0 : (k == 1 ? x1 : x2); }
+__device__ __forceinline__ void tangent_step_rot(const HexBox::EvalT &E, const int fix[3], double lam, double d[3]) {
+  d[0] = d[1] = d[2] = 0.0;
+  const int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
+  if (nf < 2) { ISO_TRACE(16); return; }
+  int K;
+  if (nf == 2) K = fix[0] ? 1 : (fix[1] ? 2 : 0);
+  else { K = 0; if (fabs(E.a[1]) > fabs(E.a[K])) K = 1; if (fabs(E.a[2]) > fabs(K == 0 ? E.a[0] : E.a[1])) K = 2; }
+  ISO_TRACE(18);
+  const int U = K == 2 ? 0 : K + 1, V = K == 0 ? 2 : K - 1;
+  const double aK = rot3(K, E.a[0], E.a[1], E.a[2]), aU = rot3(U, E.a[0], E.a[1], E.a[2]), aV = rot3(V, E.a[0], E.a[1], E.a[2]);
+  const double cK = rot3(K, E.c[0], E.c[1], E.c[2]), cU = rot3(U, E.c[0], E.c[1], E.c[2]), cV = rot3(V, E.c[0], E.c[1], E.c[2]);
+  const double hK = rot3(K, E.hh[0], E.hh[1], E.hh[2]), hU = rot3(U, E.hh[0], E.hh[1], E.hh[2]), hV = rot3(V, E.hh[0], E.hh[1], E.hh[2]);
+  // pair (U,K) is hg[K], pair (U,V) is hg[U], pair (K,V) is hg[V] in the cyclic numbering (0,1),(1,2),(2,0)
+  const double HUK = lam * rot3(K, E.hg[0], E.hg[1], E.hg[2]), HUV = lam * rot3(U, E.hg[0], E.hg[1], E.hg[2]), HKV = lam * rot3(V, E.hg[0], E.hg[1], E.hg[2]);
+  const double Hz1U = fma(hU, aK, -(HUK * aU)), Hz1K = fma(HUK, aK, -(hK * aU));
+  double m11 = fma(aK, Hz1U, -(aU * Hz1K));
+  const double kK = hK * aU;
+  double g11 = fma(hU * aK, aK, kK * aU);
+  const double r1 = -fma(aK, cU, -(aU * cK));
+  double m12 = 0.0, m22 = 1.0, g12 = 0.0, g22 = 1.0, r2 = 0.0;
+  if (nf == 3) {
+    const double Hz2U = fma(HUV, aK, -(HUK * aV)), Hz2K = fma(HKV, aK, -(hK * aV)), Hz2V = fma(hV, aK, -(HKV * aV));
+    m12 = fma(aK, Hz2U, -(aU * Hz2K)); m22 = fma(aK, Hz2V, -(aV * Hz2K));
+    g12 = kK * aV; g22 = fma(hV * aK, aK, (hK * aV) * aV);
+    r2 = -fma(aK, cV, -(aV * cK));
+  }
+  double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
+  if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
+  if (!(det > 0.0 && m11 > 0.0)) return;
+  const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
+  const double dU = y1 * aK, dV = y2 * aK, dK = -fma(y1, aU, y2 * aV);
+  // rotate back: component i receives dK / dU / dV according to its role
+#pragma unroll
+  for (int i = 0; i < 3; i++) d[i] = (i == K) ? dK : ((i == U) ? dU : dV);
+}
+template <class EV, int MODE = 0>
 __device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], double lam, double d[3]) {
+  if constexpr ((MODE & 2) != 0 && std::is_same<EV, HexBox::EvalT>::value) { tangent_step_rot(E, fix, lam, d); return; }
   d[0] = d[1] = d[2] = 0.0;
   int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
-  if (nf < 2) return;
+  if (nf < 2) { ISO_TRACE(16); return; }
   if (nf == 2) {
-    if (fix[0]) tangent2<1, 2, FAST>(E, lam, d);
-    else if (fix[1]) tangent2<0, 2, FAST>(E, lam, d);
-    else tangent2<0, 1, FAST>(E, lam, d);
+    ISO_TRACE(fix[0] ? 13 : (fix[1] ? 14 : 15));
+    if (fix[0]) tangent2<1, 2>(E, lam, d);
+    else if (fix[1]) tangent2<0, 2>(E, lam, d);
+    else tangent2<0, 1>(E, lam, d);
     return;
   }
   int k = 0;
   if (fabs(E.a[1]) > fabs(E.a[k])) k = 1;
   if (fabs(E.a[2]) > fabs(k == 0 ? E.a[0] : E.a[1])) k = 2;
-  if (k == 0) { if (fabs(E.a[0]) > 0.0) tangent3<0, FAST>(E, lam, d); }
-  else if (k == 1) { if (fabs(E.a[1]) > 0.0) tangent3<1, FAST>(E, lam, d); }
-  else { if (fabs(E.a[2]) > 0.0) tangent3<2, FAST>(E, lam, d); }
+  ISO_TRACE(10 + k);
+  if (k == 0) { if (fabs(E.a[0]) > 0.0) tangent3<0>(E, lam, d); }
+  else if (k == 1) { if (fabs(E.a[1]) > 0.0) tangent3<1>(E, lam, d); }
+  else { if (fabs(E.a[2]) > 0.0) tangent3<2>(E, lam, d); }
 }
 
 // HEX8 projection as a resumable state machine: proj_init (phase 1) + proj_iter (ONE phase-2 iteration).  A: monomial
@@ -293,13 +346,13 @@ __device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], doub
 // different grid points.  The arithmetic and its order are the same in both drivers (bit-identical results).
 struct ProjState { double xi[3]; double lam; double f; int it, stall; bool force; };      // f = |X(xi) - x|^2 at the current xi (valid once proj_iter has run)
 
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ bool proj_init(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                           const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs;
   int fix[3] = {0, 0, 0};
   S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
-  bool ok = restore<EL, FAST>(A, rho_t, S.xi, fix, tolg);
+  bool ok = restore<EL, MODE>(A, rho_t, S.xi, fix, tolg);
   if (!ok) {
     double best = INFINITY;
     for (int e = 0; e < 12; e++) {
@@ -318,14 +371,14 @@ __device__ __forceinline__ bool proj_init(const EL &A, const double re[8], const
 }
 // Phase 1 without the edge fallback: the Newton projection of xi = 0 onto {g = 0} does not depend on the grid point, so a
 // warp that works on one element computes it once and hands the state to every point (same arithmetic as proj_init).
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ bool proj_init_element(const EL &A, double rho_t, double gs, ProjState &S) {
   int fix[3] = {0, 0, 0};
   S.xi[0] = S.xi[1] = S.xi[2] = 0.0; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
-  return restore<EL, FAST>(A, rho_t, S.xi, fix, 1e-14 * gs);
+  return restore<EL, MODE>(A, rho_t, S.xi, fix, 1e-14 * gs);
 }
 // one phase-2 iteration; returns 0 = continue, 1 = converged, 2 = failed (line search exhausted)
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double rho_t, double gs, ProjState &S) {
   const double tolg = 1e-14 * gs, tolx = 1e-11, atol2 = 1e-24 * gs * gs;
   double *xi = S.xi; double lam = S.lam, dm = 0.0; bool force = S.force;
@@ -342,8 +395,9 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
 #pragma unroll
       for (int i = 0; i < 3; i++) if (!fix[i]) { num = fma(E.a[i], E.c[i], num); den = fma(E.a[i], E.a[i], den); }
       ISO_COUNT(5);
-      if (den > atol2) { lam = -num / den; ISO_COUNT(3); tangent_step<typename EL::EvalT, FAST>(E, fix, lam, d); }
+      if (den > atol2) { lam = -num / den; ISO_COUNT(3); tangent_step<typename EL::EvalT, MODE>(E, fix, lam, d); }
       else {
+        ISO_TRACE(17);
         double llo = -INFINITY, lhi = INFINITY, akk = 0.0, ckk = 0.0; bool anyk = false;
 #pragma unroll
         for (int i = 0; i < 3; i++) if (fix[i]) {
@@ -397,8 +451,8 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
         if (xt[i] >= 1.0) { xt[i] = 1.0; fx[i] = 1; }
         if (xt[i] <= -1.0) { xt[i] = -1.0; fx[i] = -1; }
       }
-      ISO_COUNT(4);
-      if (restore<EL, FAST>(A, rho_t, xt, fx, tolg)) {
+      ISO_COUNT(4); ISO_TRACE(2);
+      if (restore<EL, MODE>(A, rho_t, xt, fx, tolg)) {
         double ft = eval_f(A, x, xt);
         // steps below 1e-7 are in Newton's quadratic regime: accepted without the Armijo test (decrease below noise)
         if (dm <= 1e-7 || ft <= E.f + 1e-4 * alpha * slope + 1e-15 * E.f) {
@@ -420,27 +474,27 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
   return 0;
 }
 // Returns true when converged; xi receives the local coordinates; nit the phase-2 iteration count.
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ bool project_hex8(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                              const double x[3], double rho_t, double gs, double xi[3], int &nit) {
   ProjState S;
-  if (!proj_init<EL, FAST>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  if (!proj_init<EL, MODE>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
   int status = 0;
-  while (S.it < 100 && status == 0) status = proj_iter<EL, FAST>(A, x, rho_t, gs, S);
+  while (S.it < 100 && status == 0) status = proj_iter<EL, MODE>(A, x, rho_t, gs, S);
   xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
   nit = S.it;
   return status == 1;
 }
 // The same with phase 1 taken from a per-element table (xi0 = Newton projection of xi = 0 onto {g = 0}, ok0 = it converged): phase 1
 // does not depend on the grid point, so one thread per element can compute it once instead of every (element, point) pair.
-template <class EL, bool FAST = false>
+template <class EL, int MODE = 0>
 __device__ __forceinline__ bool project_hex8_from(const EL &A, const double re[8], const double sg[8][3], const int edges[12][2],
                                                   const double x[3], double rho_t, double gs, const double xi0[3], bool ok0, double xi[3], int &nit) {
   ProjState S;
   S.xi[0] = xi0[0]; S.xi[1] = xi0[1]; S.xi[2] = xi0[2]; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
-  if (!ok0 && !proj_init<EL, FAST>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
+  if (!ok0 && !proj_init<EL, MODE>(A, re, sg, edges, x, rho_t, gs, S)) { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; return false; }
   int status = 0;
-  while (S.it < 100 && status == 0) status = proj_iter<EL, FAST>(A, x, rho_t, gs, S);
+  while (S.it < 100 && status == 0) status = proj_iter<EL, MODE>(A, x, rho_t, gs, S);
   xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
   nit = S.it;
   return status == 1;

@@ -50,29 +50,34 @@ int iso_host_project(const double *Xe, const double *re, const double *x, double
   return ok ? 1 : 0;
 }
 void iso_host_counts(long *out, int reset) { for (int k = 0; k < 8; k++) { out[k] = iso_counts[k]; if (reset) iso_counts[k] = 0; } }
+// event trace (see ISO_TRACE in r2s_iso.cuh): the caller provides the buffer; a 0 is appended by iso_host_project_many after every pair
+void iso_host_trace(int *buf, long cap) { iso_trace = buf; iso_trace_cap = cap; iso_trace_n = 0; }
+long iso_host_trace_len() { return iso_trace_n; }
 int iso_host_is_box(const double *Xe, const double *re) { double A[4][8]; coefficients(Xe, re, A); return iso::is_box(A) ? 1 : 0; }
 // batch over n points of ONE element; its[n] receives the phase-2 iteration count (the quantity a warp waits on).
 // variant 0: general trilinear, 1: HexBox, 2: HexBox FAST, 3: HexBox FAST with phase 1 computed once for the element (the table
-// path of the kernels), 4: general trilinear with phase 1 once per element
+// path of the kernels), 4: general trilinear with phase 1 once per element, 5: as 3 with the single-path tangent step (MODE 3)
 int iso_host_project_many(const double *Xe, const double *re, long n, const double *x, double rho_t, int variant, double *dist, int *its) {
   double A[4][8]; coefficients(Xe, re, A);
   const double gs = gscale(re, rho_t);
   iso::HexTri T{(const double(*)[8])A}; iso::HexBox B;
-  if (variant >= 1 && variant <= 3) { if (!iso::is_box(A)) return -2; iso::make_box(A, B); }
+  if ((variant >= 1 && variant <= 3) || variant == 5) { if (!iso::is_box(A)) return -2; iso::make_box(A, B); }
   iso::ProjState S0; bool ok0 = false;
-  if (variant == 3) ok0 = iso::proj_init_element<iso::HexBox, true>(B, rho_t, gs, S0);
-  if (variant == 4) ok0 = iso::proj_init_element<iso::HexTri, false>(T, rho_t, gs, S0);
+  if (variant == 3 || variant == 5) ok0 = iso::proj_init_element<iso::HexBox, 1>(B, rho_t, gs, S0);
+  if (variant == 4) ok0 = iso::proj_init_element<iso::HexTri, 0>(T, rho_t, gs, S0);
   int bad = 0;
   for (long q = 0; q < n; q++) {
     double xi[3], p[3]; int nit = 0; bool ok;
     const double *xq = x + 3 * q;
     if (variant == 0) { ok = iso::project_hex8(T, re, sg, edges, xq, rho_t, gs, xi, nit); iso::eval_pos(T, xi, p); }
     else if (variant == 1) { ok = iso::project_hex8(B, re, sg, edges, xq, rho_t, gs, xi, nit); iso::eval_pos(B, xi, p); }
-    else if (variant == 2) { ok = iso::project_hex8<iso::HexBox, true>(B, re, sg, edges, xq, rho_t, gs, xi, nit); iso::eval_pos(B, xi, p); }
-    else if (variant == 3) { ok = iso::project_hex8_from<iso::HexBox, true>(B, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(B, xi, p); }
-    else { ok = iso::project_hex8_from<iso::HexTri, false>(T, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(T, xi, p); }
+    else if (variant == 2) { ok = iso::project_hex8<iso::HexBox, 1>(B, re, sg, edges, xq, rho_t, gs, xi, nit); iso::eval_pos(B, xi, p); }
+    else if (variant == 3) { ok = iso::project_hex8_from<iso::HexBox, 1>(B, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(B, xi, p); }
+    else if (variant == 5) { ok = iso::project_hex8_from<iso::HexBox, 3>(B, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(B, xi, p); }
+    else { ok = iso::project_hex8_from<iso::HexTri, 0>(T, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(T, xi, p); }
     const double d0 = xq[0] - p[0], d1 = xq[1] - p[1], d2 = xq[2] - p[2];
     dist[q] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0))); its[q] = nit; bad += ok ? 0 : 1;
+    ISO_TRACE(0);
   }
   return bad;
 }

@@ -104,3 +104,18 @@ def test_fast_restoration_and_element_phase1_change_nothing(host):
         _, d0, it0 = many(host, Xe, re, P, 0.5, 0)
         _, d4, it4 = many(host, Xe, re, P, 0.5, 4)
         assert np.array_equal(d0, d4) and np.array_equal(it0, it4)
+
+
+def test_single_path_tangent_step_matches(host):
+    """MODE 3 (one code path for all tangent-step cases, HexBox): same mathematics, different rounding -- distances agree far inside
+    the 1e-9 h parity tolerance with the exact box variant and with the oracle."""
+    rng = np.random.default_rng(21)
+    worst = 0.0; worst_o = 0.0
+    for Xe, re, P, h in random_cases(rng, 1500, True):
+        _, d1, _ = many(host, Xe, re, P, 0.5, 1)
+        _, d5, _ = many(host, Xe, re, P, 0.5, 5)
+        worst = max(worst, float(np.abs(d5 - d1).max()) / h)
+        ok, do = oracle_distance(P[0], Xe, re)
+        if ok:
+            worst_o = max(worst_o, abs(d5[0] - do) / h)
+    assert worst <= 1e-11 and worst_o <= 1e-10, (worst, worst_o)

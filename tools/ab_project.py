@@ -12,9 +12,10 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 
 DEFAULT = ("general:R2S_PROJ_BOX=0;box5:;box5_fast:R2S_PROJ_FAST=1;box5_p1:R2S_PROJ_P1=1;box5_fast_p1:R2S_PROJ_FAST=1,R2S_PROJ_P1=1;"
-           "box6_fast_p1:R2S_PROJ_FAST=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=6;box8_fast_p1:R2S_PROJ_FAST=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;"
-           "refill3_box:R2S_PROJ=1;refill3_box_fast:R2S_PROJ=1,R2S_PROJ_FAST=1;general_fast_p1:R2S_PROJ_BOX=0,R2S_PROJ_FAST=1,R2S_PROJ_P1=1")
-KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_P1")
+           "box5_uni:R2S_PROJ_UNI=1;box5_uni_p1:R2S_PROJ_UNI=1,R2S_PROJ_P1=1;box6_uni_p1:R2S_PROJ_UNI=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=6;"
+           "box8_uni_p1:R2S_PROJ_UNI=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;refill3_box:R2S_PROJ=1;refill3_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1;"
+           "refill4_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1,R2S_PROJ_MINB=4;general_fast_p1:R2S_PROJ_BOX=0,R2S_PROJ_FAST=1,R2S_PROJ_P1=1")
+KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_UNI", "R2S_PROJ_P1")
 
 
 def main():
