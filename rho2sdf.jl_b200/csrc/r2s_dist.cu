@@ -167,9 +167,15 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   if (li < vol) {
     int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
     double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]};
-    double xi[3], p[3];
+    double xi[3], p[3] = {0, 0, 0};
     double xi0[3] = {0, 0, 0}; bool ok0 = false;
     if (P1) { const double4 q = p1[lo]; xi0[0] = q.x; xi0[1] = q.y; xi0[2] = q.z; ok0 = q.w != 0.0; }
+    if constexpr (BOX && (MODE & 4) != 0) {      // scaled box form (no closest point: the driver never combines it with WANT_XP)
+      iso::HexBoxS B; iso::make_box_scaled(A, x, B);
+      if (P1) okc = iso::project_hex8_from<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
+      else okc = iso::project_hex8<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
+      pairbuf[r.pair_off + li] = sqrt(iso::eval_f(B, x, xi));
+    } else {
     if (BOX) {
       iso::HexBox B; iso::make_box(A, B);
       if (P1) okc = iso::project_hex8_from<iso::HexBox, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
     double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
     pairbuf[r.pair_off + li] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
     if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
+    }
   }
   // statistics: iterations and failures (one atomic per warp)
   int its = nit > 0 ? nit : 0;
@@ -750,17 +757,19 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #define PROJH(XP, MB, SA, BX, FS) PROJH6(XP, MB, SA, BX, 0, false)
     // the opt-in variants (FAST solver and / or phase 1 from the table), instantiated for the occupancies worth measuring
 #define PROJO(MB, BX) do { \
-      if (uni && BX) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
+      if (scaled && BX) { if (use_p1) PROJH6(false, MB, false, BX, 7, true); else PROJH6(false, MB, false, BX, 7, false); } \
+      else if (uni && BX) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
       else if (fast) { if (use_p1) PROJH6(false, MB, false, BX, 1, true); else PROJH6(false, MB, false, BX, 1, false); } \
       else PROJH6(false, MB, false, BX, 0, true); } while (0)
     // Axis-aligned box elements (flag + count built with the mesh) take the HexBox variant of the kernel, the others the general
     // trilinear one; a mesh with both kinds takes both launches, each leaving the other kind's chunks alone.  R2S_PROJ_BOX=0
     // sends everything through the general kernel; R2S_PROJ_BOX_MINB = CTAs/SM of the box variant (4 / 5 / 6).
     // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path, box
-    // elements), R2S_PROJ_P1=1 (phase 1 from a per-element table).
+    // elements), R2S_PROJ_SCALED=1 (UNI + the scaled box form HexBoxS), R2S_PROJ_P1=1 (phase 1 from a per-element table).
     const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
     const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 5;      // measured at n = 256: 92.6 / 86.5 / 89.5 ms for 4 / 5 / 6 CTAs per SM (profiles/r1f_ab_project_variants_n256.jsonl)
-    const bool uni = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1;
+    const bool scaled = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_SCALED") && atoi(getenv("R2S_PROJ_SCALED")) == 1;
+    const bool uni = scaled || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1);
     const bool fast = uni || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
     const bool use_p1 = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_P1") && atoi(getenv("R2S_PROJ_P1")) == 1;
     const i64 nbx = (use_box && nen == 8) ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;

@@ -387,7 +387,8 @@ OPTIN = pytest.mark.skipif(os.environ.get("R2S_TEST_OPTIN") != "1", reason="opt-
 @OPTIN
 @pytest.mark.parametrize("knobs", [{"R2S_PROJ_FAST": "1"}, {"R2S_PROJ_P1": "1"}, {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1"},
                                    {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "8"}, {"R2S_PROJ": "1", "R2S_PROJ_FAST": "1"},
-                                   {"R2S_PROJ_UNI": "1"}, {"R2S_PROJ_UNI": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}, {"R2S_PROJ": "1", "R2S_PROJ_UNI": "1"}])
+                                   {"R2S_PROJ_UNI": "1"}, {"R2S_PROJ_UNI": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}, {"R2S_PROJ": "1", "R2S_PROJ_UNI": "1"},
+                                   {"R2S_PROJ_SCALED": "1"}, {"R2S_PROJ_SCALED": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}])
 def test_optin_projection_variants(r2s, monkeypatch, knobs):
     """FAST restoration / per-element phase-1 table (r2s_iso.cuh): on the host build they reproduce the exact variants bit for bit
     (tests/test_iso_host.py); here the kernels that carry them, on the mixed mesh and on a replica of the bench workload."""
@@ -403,6 +404,6 @@ def test_optin_projection_variants(r2s, monkeypatch, knobs):
         for k in knobs:
             monkeypatch.delenv(k)
         assert np.max(np.abs(d - od)) <= DIST_TOL * grid.cell_size
-        if "R2S_PROJ" not in knobs and "R2S_PROJ_UNI" not in knobs:
+        if not ({"R2S_PROJ", "R2S_PROJ_UNI", "R2S_PROJ_SCALED"} & set(knobs)):
             assert np.array_equal(d, d_ref)                 # same arithmetic as the default kernels
         mesh.ctx.close()
