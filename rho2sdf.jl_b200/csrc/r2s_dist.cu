@@ -117,7 +117,7 @@ __global__ void k_phase1(i64 nact, const ActRec *__restrict__ rec, const int *__
 // constants instead of 32, about half the FP64 work per iteration); kind_check != 0: the mesh holds both kinds of elements and
 // each of the two launches leaves the chunks of the other kind alone (ebox[e] = 1 for boxes, built with the mesh).
 // MODE: solver variant (r2s_iso.cuh) -- bit 0 FAST restoration (no confirming evaluation, same results), bit 1 one code path for all
-// tangent-step cases (HexBox only, results equal to rounding).
+// tangent-step cases (results equal to rounding), bit 2 scaled box form (HexBox only).
 // P1: phase 1 of the solver (Newton projection of xi = 0 onto the iso-surface, the same for every point of an element)
 // comes from the per-element table built by k_phase1 instead of being recomputed by every lane of every chunk.
 template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX, int MODE, bool P1>
@@ -736,7 +736,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
       const bool fast_r = uni_r || (getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
 #define PMIN(MB, BX, MD) k_project_hex8_min<MB, BX, MD><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
                                                               ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc)
-#define PMINF(MB, BX) do { if (uni_r && BX) PMIN(MB, BX, 3); else if (fast_r) PMIN(MB, BX, 1); else PMIN(MB, BX, 0); } while (0)
+#define PMINF(MB, BX) do { if (uni_r) PMIN(MB, BX, 3); else if (fast_r) PMIN(MB, BX, 1); else PMIN(MB, BX, 0); } while (0)
       if (nbx < nel) { if (minbr <= 2) PMINF(2, false); else if (minbr == 3) PMINF(3, false); else PMINF(4, false); LAUNCH_CHECK(); }
       if (nbx > 0) { if (minbr <= 2) PMINF(2, true); else if (minbr == 3) PMINF(3, true); else PMINF(4, true); }
 #undef PMINF
@@ -758,14 +758,13 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     // the opt-in variants (FAST solver and / or phase 1 from the table), instantiated for the occupancies worth measuring
 #define PROJO(MB, BX) do { \
       if (scaled && BX) { if (use_p1) PROJH6(false, MB, false, BX, 7, true); else PROJH6(false, MB, false, BX, 7, false); } \
-      else if (uni && BX) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
+      else if (uni) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
       else if (fast) { if (use_p1) PROJH6(false, MB, false, BX, 1, true); else PROJH6(false, MB, false, BX, 1, false); } \
       else PROJH6(false, MB, false, BX, 0, true); } while (0)
     // Axis-aligned box elements (flag + count built with the mesh) take the HexBox variant of the kernel, the others the general
     // trilinear one; a mesh with both kinds takes both launches, each leaving the other kind's chunks alone.  R2S_PROJ_BOX=0
     // sends everything through the general kernel; R2S_PROJ_BOX_MINB = CTAs/SM of the box variant (4 / 5 / 6).
-    // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path, box
-    // elements), R2S_PROJ_SCALED=1 (UNI + the scaled box form HexBoxS), R2S_PROJ_P1=1 (phase 1 from a per-element table).
+    // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path), R2S_PROJ_SCALED=1 (UNI + the scaled box form HexBoxS), R2S_PROJ_P1=1 (phase 1 from a per-element table).
     const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
     const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 5;      // measured at n = 256: 92.6 / 86.5 / 89.5 ms for 4 / 5 / 6 CTAs per SM (profiles/r1f_ab_project_variants_n256.jsonl)
     const bool scaled = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_SCALED") && atoi(getenv("R2S_PROJ_SCALED")) == 1;

@@ -308,14 +308,28 @@ __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, dou
   const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
   d[U] = y1 * aK; d[V] = y2 * aK; d[K] = -fma(y1, aU, y2 * aV);
 }
-// MODE bit 1 (HexBox only): ONE code path for every tangent-step case.  The three tangent3<K> and the three tangent2<I,J> variants
+// MODE bit 1: ONE code path for every tangent-step case.  The three tangent3<K> and the three tangent2<I,J> variants
 // differ only by a cyclic rotation of the indices: (K,U,V) = (K,K+1,K+2) with K = argmax |a_k| when all three variables are free,
 // K = L+1 when variable L is fixed (then V = L, the second null-space vector is dropped: m12 = r2 = 0, m22 = 1 turns the 2x2 solve
 // into tangent2's scalar step).  Lanes of a warp sit on different faces of the box; with the template variants every distinct
 // case is issued separately (the offline SIMT model, tools/divergence_model.py, attributes half of the issued work of the
 // projection kernel to that), here the rotation is a handful of selects.  Same mathematics, rounding differs in the last bits.
 __device__ __forceinline__ double rot3(int k, double x0, double x1, double x2) { return k == 0 ? x0 : (k == 1 ? x1 : x2); }
-__device__ __forceinline__ void tangent_step_rot(const HexBox::EvalT &E, const int fix[3], double lam, double d[3]) {
+// quadratic forms z1'S z1, z1'S z2, z2'S z2 of a symmetric S (diagonal SK, SU, SV; off-diagonal SUK, SUV, SKV in rotated indices) with
+// z1 = aK e_U - aU e_K, z2 = aK e_V - aV e_K; with3 = false leaves the z2 forms at (0, 1) (two free variables)
+__device__ __forceinline__ void null_forms(double SK, double SU, double SV, double SUK, double SUV, double SKV, double aK, double aU, double aV, bool with3,
+                                           double &s11, double &s12, double &s22) {
+  const double z1U = fma(SU, aK, -(SUK * aU)), z1K = fma(SUK, aK, -(SK * aU));
+  s11 = fma(aK, z1U, -(aU * z1K));
+  s12 = 0.0; s22 = 1.0;
+  if (with3) {
+    const double z2U = fma(SUV, aK, -(SUK * aV)), z2K = fma(SKV, aK, -(SK * aV)), z2V = fma(SV, aK, -(SKV * aV));
+    s12 = fma(aK, z2U, -(aU * z2K)); s22 = fma(aK, z2V, -(aV * z2K));
+  }
+}
+template <class EV>
+__device__ __forceinline__ void tangent_step_rot(const EV &E, const int fix[3], double lam, double d[3]) {
+  constexpr bool BOXE = std::is_same<EV, HexBox::EvalT>::value;
   d[0] = d[1] = d[2] = 0.0;
   const int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
   if (nf < 2) { ISO_TRACE(16); return; }
@@ -324,23 +338,26 @@ __device__ __forceinline__ void tangent_step_rot(const HexBox::EvalT &E, const i
   else { K = 0; if (fabs(E.a[1]) > fabs(E.a[K])) K = 1; if (fabs(E.a[2]) > fabs(K == 0 ? E.a[0] : E.a[1])) K = 2; }
   ISO_TRACE(18);
   const int U = K == 2 ? 0 : K + 1, V = K == 0 ? 2 : K - 1;
+  const bool with3 = nf == 3;
   const double aK = rot3(K, E.a[0], E.a[1], E.a[2]), aU = rot3(U, E.a[0], E.a[1], E.a[2]), aV = rot3(V, E.a[0], E.a[1], E.a[2]);
   const double cK = rot3(K, E.c[0], E.c[1], E.c[2]), cU = rot3(U, E.c[0], E.c[1], E.c[2]), cV = rot3(V, E.c[0], E.c[1], E.c[2]);
-  const double hK = rot3(K, E.hh[0], E.hh[1], E.hh[2]), hU = rot3(U, E.hh[0], E.hh[1], E.hh[2]), hV = rot3(V, E.hh[0], E.hh[1], E.hh[2]);
-  // pair (U,K) is hg[K], pair (U,V) is hg[U], pair (K,V) is hg[V] in the cyclic numbering (0,1),(1,2),(2,0)
-  const double HUK = lam * rot3(K, E.hg[0], E.hg[1], E.hg[2]), HUV = lam * rot3(U, E.hg[0], E.hg[1], E.hg[2]), HKV = lam * rot3(V, E.hg[0], E.hg[1], E.hg[2]);
-  const double Hz1U = fma(hU, aK, -(HUK * aU)), Hz1K = fma(HUK, aK, -(hK * aU));
-  double m11 = fma(aK, Hz1U, -(aU * Hz1K));
-  const double kK = hK * aU;
-  double g11 = fma(hU * aK, aK, kK * aU);
-  const double r1 = -fma(aK, cU, -(aU * cK));
-  double m12 = 0.0, m22 = 1.0, g12 = 0.0, g22 = 1.0, r2 = 0.0;
-  if (nf == 3) {
-    const double Hz2U = fma(HUV, aK, -(HUK * aV)), Hz2K = fma(HKV, aK, -(hK * aV)), Hz2V = fma(hV, aK, -(HKV * aV));
-    m12 = fma(aK, Hz2U, -(aU * Hz2K)); m22 = fma(aK, Hz2V, -(aV * Hz2K));
-    g12 = kK * aV; g22 = fma(hV * aK, aK, (hK * aV) * aV);
-    r2 = -fma(aK, cV, -(aV * cK));
+  double m11, m12, m22, g11, g12, g22;
+  // pair (U,K) is entry K, pair (U,V) entry U, pair (K,V) entry V of the cyclic pair numbering (0,1),(1,2),(2,0)
+  if constexpr (BOXE) {
+    const double hK = rot3(K, E.hh[0], E.hh[1], E.hh[2]), hU = rot3(U, E.hh[0], E.hh[1], E.hh[2]), hV = rot3(V, E.hh[0], E.hh[1], E.hh[2]);
+    const double HUK = lam * rot3(K, E.hg[0], E.hg[1], E.hg[2]), HUV = lam * rot3(U, E.hg[0], E.hg[1], E.hg[2]), HKV = lam * rot3(V, E.hg[0], E.hg[1], E.hg[2]);
+    null_forms(hK, hU, hV, HUK, HUV, HKV, aK, aU, aV, with3, m11, m12, m22);
+    const double kK = hK * aU;      // Gauss-Newton part: diagonal only
+    g11 = fma(hU * aK, aK, kK * aU); g12 = 0.0; g22 = 1.0;
+    if (with3) { g12 = kK * aV; g22 = fma(hV * aK, aK, (hK * aV) * aV); }
+  } else {
+    const double hK = rot3(K, E.Hgn[0][0], E.Hgn[1][1], E.Hgn[2][2]), hU = rot3(U, E.Hgn[0][0], E.Hgn[1][1], E.Hgn[2][2]), hV = rot3(V, E.Hgn[0][0], E.Hgn[1][1], E.Hgn[2][2]);
+    const double G0 = E.Hgn[0][1], G1 = E.Hgn[1][2], G2 = E.Hgn[2][0];
+    const double M0 = G0 + fma(lam, E.hg[0], E.m[0]), M1 = G1 + fma(lam, E.hg[1], E.m[1]), M2 = G2 + fma(lam, E.hg[2], E.m[2]);
+    null_forms(hK, hU, hV, rot3(K, M0, M1, M2), rot3(U, M0, M1, M2), rot3(V, M0, M1, M2), aK, aU, aV, with3, m11, m12, m22);
+    null_forms(hK, hU, hV, rot3(K, G0, G1, G2), rot3(U, G0, G1, G2), rot3(V, G0, G1, G2), aK, aU, aV, with3, g11, g12, g22);
   }
+  const double r1 = -fma(aK, cU, -(aU * cK)), r2 = with3 ? -fma(aK, cV, -(aV * cK)) : 0.0;
   double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
   if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
   if (!(det > 0.0 && m11 > 0.0)) return;
@@ -352,7 +369,7 @@ __device__ __forceinline__ void tangent_step_rot(const HexBox::EvalT &E, const i
 }
 template <class EV, int MODE = 0>
 __device__ __forceinline__ void tangent_step(const EV &E, const int fix[3], double lam, double d[3]) {
-  if constexpr ((MODE & 2) != 0 && std::is_same<EV, HexBox::EvalT>::value) { tangent_step_rot(E, fix, lam, d); return; }
+  if constexpr ((MODE & 2) != 0) { tangent_step_rot(E, fix, lam, d); return; }
   d[0] = d[1] = d[2] = 0.0;
   int nf = (fix[0] == 0) + (fix[1] == 0) + (fix[2] == 0);
   if (nf < 2) { ISO_TRACE(16); return; }

@@ -120,3 +120,9 @@ def test_single_path_tangent_step_matches(host):
             if ok:
                 worst_o = max(worst_o, abs(d[0] - do) / h)
     assert worst <= 5e-11 and worst_o <= 1e-10, (worst, worst_o)
+    worst = 0.0
+    for Xe, re, P, h in random_cases(rng, 800, False):      # general trilinear element: variant 8 = MODE 3 with element phase 1
+        _, d0, _ = many(host, Xe, re, P, 0.5, 0)
+        _, d8, _ = many(host, Xe, re, P, 0.5, 8)
+        worst = max(worst, float(np.abs(d8 - d0).max()) / h)
+    assert worst <= 5e-11, worst
