@@ -273,12 +273,37 @@ def run_gpu(args):
         barrier()
         wall_e2e = (time.perf_counter() - w0) * 1e3
         ms_e2e = max(f0.elapsed_time(f1), 0.0)
+        # ---- optional: the same K steps through the pipelined host-buffer calls (two buffer sets; the downloads of step k drain
+        # while step k+1 computes).  Opt-in until it has been validated on a GPU (tests: R2S_TEST_OPTIN=1).
+        ms_pipe = None
+        if args.pipelined_e2e:
+            h_sdf2 = torch.empty(n_sdf_local, dtype=torch.float64).pin_memory()
+            h_fine2 = torch.empty(n_fine_local, dtype=torch.float32).pin_memory()
+            bufs = [(h_sdf, h_fine), (h_sdf2, h_fine2)]
+
+            def begin(k):
+                rep = r2s.Report(); t = C.c_int(-1)
+                c.check(c.lib.r2s_pipeline_slab_begin(c.h, C.byref(p), C.c_void_p(h_rho.data_ptr()), C.c_void_p(bufs[k % 2][0].data_ptr()), C.c_void_p(bufs[k % 2][1].data_ptr()),
+                                                      C.byref(rep), C.byref(t)))
+                return t.value
+            c.check(c.lib.r2s_pipeline_slab_wait(c.h, begin(0)))
+            barrier()
+            w1 = time.perf_counter()
+            tk = begin(0)
+            for k in range(1, args.steps):
+                tn = begin(k)
+                c.check(c.lib.r2s_pipeline_slab_wait(c.h, tk))
+                tk = tn
+            c.check(c.lib.r2s_pipeline_slab_wait(c.h, tk))
+            barrier()
+            ms_pipe = (time.perf_counter() - w1) * 1e3
         clocks = sampler.stop() if sampler else None
         per_rank = None
         if world > 1:
-            t = torch.tensor([ms, ms_e2e, wall_e2e], dtype=torch.float64, device="cuda")
+            t = torch.tensor([ms, ms_e2e, wall_e2e, ms_pipe if ms_pipe is not None else 0.0], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, ms_e2e, wall_e2e = (float(v) for v in t.tolist())
+            ms, ms_e2e, wall_e2e, mp = (float(v) for v in t.tolist())
+            ms_pipe = mp if ms_pipe is not None else None
             # per-rank stage times of the last timed step (load-balance evidence)
             keys = ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_cg", "ms_threshold", "ms_total")
             mine = torch.tensor([getattr(reps[-1], k) for k in keys] + [float(k1 - k0)] + [float(v) for v in reps[-1].cg_probe], dtype=torch.float64, device="cuda")
@@ -347,6 +372,9 @@ def run_gpu(args):
                        "target_volume": float(p.target_volume), "solid": int(rep.n_solid), "crossing": int(rep.n_crossing)},
             "clocks": clocks,
         }
+        if ms_pipe is not None:
+            line["e2e_pipelined"] = {"value": nfine / (ms_pipe / K * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / K, "api": "r2s_pipeline_slab_begin / _wait, two pinned buffer sets",
+                                     "h2d_bytes_per_step": int(rho_n.nbytes) * world, "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4)}
         if per_rank is not None:
             line["per_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:
@@ -370,6 +398,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="elements per axis of the synthetic HEX8 SIMP field")
     ap.add_argument("--cpu-n", type=int, default=96, help="replica size for the CPU oracle leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipelined-e2e", action="store_true", help="also time the pipelined host-buffer calls (r2s_pipeline_slab_begin/_wait); opt-in")
     ap.add_argument("--no-balance", action="store_true", help="keep equal plane counts per slab (no cost-based re-cut during warm-up)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -111,6 +111,12 @@ int r2s_comm_destroy(r2s_ctx *ctx);
  * fine_slab[(kf1-kf0)*f0*f1], kf0 = smooth*k0, kf1 = smooth*k1 (the last slab also owns the final fine plane) */
 int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep);
 
+/* Pipelined form for a sequence of density fields on one mesh/grid (batch use of rho2sdf): _begin returns when the device work is
+ * done and the result downloads are enqueued; they drain while the next _begin computes.  The host buffers of a call belong to
+ * the library until _wait(ticket) returns -- alternate between two sets of buffers. */
+int r2s_pipeline_slab_begin(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep, int *ticket);
+int r2s_pipeline_slab_wait(r2s_ctx *ctx, int ticket);
+
 /* ---- grid set-up statistics: calculate_edge_distances + analyze_mesh (src/MeshGrid/Grid_setup.jl:28-92) ---------------------- */
 /* median / shortest / longest element edge; the median is the grid step of noninteractive_sdf_grid_setup (:94-109) */
 int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double *longest);

@@ -101,6 +101,8 @@ def load_library():
     L.r2s_download_fine_sdf.argtypes = [vp, vp]
     L.r2s_result_ptrs_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.r2s_pipeline_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report)]
+    L.r2s_pipeline_slab_begin.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report), C.POINTER(C.c_int)]
+    L.r2s_pipeline_slab_wait.argtypes = [vp, C.c_int]
     L.r2s_comm_unique_id.argtypes = [vp]
     L.r2s_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.r2s_comm_destroy.argtypes = [vp]

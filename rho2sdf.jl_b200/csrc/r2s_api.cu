@@ -23,6 +23,7 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   for (int i = 0; i < 5; i++) cudaEventCreate(&ctx->ev_probe[i]);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 64; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
   *out = ctx;
   return 0;
 }
@@ -40,6 +41,7 @@ void r2s_destroy(r2s_ctx *ctx) {
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_probe[i]);
   for (int i = 0; i < 64; i++) cudaEventDestroy(ctx->ev_copy[i]);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_done[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -287,6 +289,8 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   CK(cudaEventRecord(ctx->ev[8], ctx->stream));
   if (r2s_dev_eval_distances(ctx, p->rho_t, p->delta_factor, false)) return 1;
   CK(cudaEventRecord(ctx->ev[9], ctx->stream));
+  // pipelined calls: the previous call's downloads read ctx->sdf / ctx->f_fine, which are first overwritten from here on
+  if (ctx->done_pending >= 0) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[ctx->done_pending], 0)); ctx->done_pending = -1; }
   if (r2s_dev_sign(ctx, p->rho_t, false, true)) return 1;                 // sdf = dist .* signs (RhoToSDF.jl:171)
   CK(cudaEventRecord(ctx->ev[10], ctx->stream));
   if (p->remove_artifacts) { i64 fl = 0; if (r2s_dev_remove_artifacts(ctx, p->artifact_threshold, p->artifact_min_ratio, &fl)) return 1; ctx->rep.n_flipped = fl; }
@@ -352,6 +356,27 @@ int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, do
   if (rc) return 1;
   CK(e);
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// Pipelined form of r2s_pipeline_slab for a sequence of density fields on the same mesh and grid: _begin returns when the device
+// work of this call is finished and its result downloads are ENQUEUED (copy stream); they drain while the next _begin computes.
+// The host buffers of a call belong to the library until r2s_pipeline_slab_wait(ticket) returns; alternate between two sets.
+int r2s_pipeline_slab_begin(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep, int *ticket) {
+  if (!ctx || !p || !ticket) return 1;
+  if (upload_rho_n(ctx, rho_n)) return 1;
+  ctx->async_sdf_host = sdf_slab; ctx->async_fine_host = fine_slab; ctx->n_ev_copy = 0;
+  int rc = r2s_pipeline_resident(ctx, p, rep);
+  ctx->async_sdf_host = nullptr; ctx->async_fine_host = nullptr;
+  if (rc) { cudaStreamSynchronize(ctx->copy_stream); ctx->done_pending = -1; return 1; }
+  const int t = ctx->done_next; ctx->done_next ^= 1;
+  CK(cudaEventRecord(ctx->ev_done[t], ctx->copy_stream));
+  ctx->done_pending = t;
+  *ticket = t;
+  return 0;
+}
+int r2s_pipeline_slab_wait(r2s_ctx *ctx, int ticket) {
+  if (!ctx || ticket < 0 || ticket > 1) return 1;
+  CK(cudaEventSynchronize(ctx->ev_done[ticket]));
   return 0;
 }
 }  // extern "C"

@@ -71,6 +71,8 @@ struct r2s_ctx {
   // overlap of the result download with compute (r2s_pipeline_slab): copies run on copy_stream behind events of the main stream
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[64]; int n_ev_copy = 0;
   double *async_sdf_host = nullptr; float *async_fine_host = nullptr;
+  // pipelined host-buffer calls (r2s_pipeline_slab_begin / _wait): the downloads of call k drain while call k+1 computes
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}; int done_next = 0; int done_pending = -1;
 
   // mesh
   int nen = 0, nes = 0, nsn = 0;

@@ -407,3 +407,37 @@ def test_optin_projection_variants(r2s, monkeypatch, knobs):
         if not ({"R2S_PROJ", "R2S_PROJ_UNI", "R2S_PROJ_SCALED"} & set(knobs)):
             assert np.array_equal(d, d_ref)                 # same arithmetic as the default kernels
         mesh.ctx.close()
+
+
+
+@OPTIN
+def test_pipelined_host_buffer_calls(r2s):
+    """r2s_pipeline_slab_begin / _wait: three consecutive calls on alternating buffer sets return what the synchronous call returns."""
+    import ctypes as C
+    n = 24
+    X, IEN, rho = simp_hex8(n)
+    mesh = r2s.Mesh(X, IEN, rho)
+    grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+    rn = r2s.DenseInNodes(mesh, rho)
+    sdf_ref, fine_ref, _ = _run_pipeline(r2s, mesh, grid, rn)
+    c = mesh.ctx
+    p = r2s.Params(); c.lib.r2s_default_params(C.byref(p))
+    p.rho_t, p.smooth, p.rbf_interp, p.remove_artifacts = 0.5, 2, 1, 1
+    p.target_volume, p.final_volume = mesh.V_frac * mesh.V_domain, 1
+    bufs = [(np.full(sdf_ref.size, np.nan), np.full(fine_ref.size, np.nan, dtype=np.float32)) for _ in range(2)]
+    rn2 = np.ascontiguousarray(rn)
+    tickets = []
+    for k in range(3):
+        rep = r2s.Report(); t = C.c_int(-1)
+        c.check(c.lib.r2s_pipeline_slab_begin(c.h, C.byref(p), rn2.ctypes.data_as(C.c_void_p), bufs[k % 2][0].ctypes.data_as(C.c_void_p),
+                                              bufs[k % 2][1].ctypes.data_as(C.c_void_p), C.byref(rep), C.byref(t)))
+        if tickets:
+            kk, tt = tickets.pop()
+            c.check(c.lib.r2s_pipeline_slab_wait(c.h, tt))
+            assert np.array_equal(bufs[kk % 2][0], sdf_ref.ravel()) and np.array_equal(bufs[kk % 2][1], fine_ref.ravel())
+            bufs[kk % 2][0][:] = np.nan; bufs[kk % 2][1][:] = np.nan
+        tickets.append((k, t.value))
+    kk, tt = tickets.pop()
+    c.check(c.lib.r2s_pipeline_slab_wait(c.h, tt))
+    assert np.array_equal(bufs[kk % 2][0], sdf_ref.ravel()) and np.array_equal(bufs[kk % 2][1], fine_ref.ravel())
+    mesh.ctx.close()
