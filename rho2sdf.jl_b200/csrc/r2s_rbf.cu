@@ -209,7 +209,12 @@ __global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, 
 // shared-memory loads and serve both outputs (7.5 loads per output instead of 21), and the per-plane bookkeeping is shared.
 #define S3_X 32            // outputs per CTA in x (16 threads x 2)
 #define S3_Y 16
-template <bool BETA>
+// FACT (opt-in, R2S_STENCIL=3): the tap weight depends on the squared distance only and w[m] = exp(-m), so w[m2 + dz^2] = w[m2] * w[dz^2]:
+// the in-plane sums S9 (taps with m2 <= 2) and S21 = S9 + S12 (all 21 in-plane taps) are formed once per input plane and enter the five
+// output planes as a2 += S21, a1/a3 += w[1] S21, a0/a4 += w[4] S9 -- 27 FMA-pipe operations per column and plane instead of 81.  The
+// products w[m2] * w[dz^2] differ from the tabulated float(exp(-(m2 + dz^2))) by Float32 round-off (mat-vec 4e-7 relative, CG
+// iteration counts and weights checked against the oracle in numpy).
+template <bool BETA, bool FACT>
 __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, int zc, const float *__restrict__ in, const float *__restrict__ r,
                                                           const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
                                                           float *__restrict__ out, double *__restrict__ partial, StencilW W) {
@@ -261,6 +266,7 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
     __syncthreads();
     if (zin + 1 < zc1 + 2) fetch(zin + 1);
     float ctra = 0.f, ctrb = 0.f;
+    float s9a = 0.f, s9b = 0.f, s12a = 0.f, s12b = 0.f;
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++) {
       const float2 *row = reinterpret_cast<const float2 *>(&sm[buf][ty + 2 + dj][2 * tx]);
@@ -272,10 +278,20 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
         const int m2 = di * di + dj * dj;
         if (m2 > 6) continue;
         const float va = v[di + 2], vb = v[di + 3];
+        if (FACT) {
+          if (m2 <= 2) { s9a = fmaf(W.w[m2], va, s9a); s9b = fmaf(W.w[m2], vb, s9b); }
+          else { s12a = fmaf(W.w[m2], va, s12a); s12b = fmaf(W.w[m2], vb, s12b); }
+          continue;
+        }
         a2 = fmaf(W.w[m2], va, a2); b2 = fmaf(W.w[m2], vb, b2);
         if (m2 + 1 <= 6) { a1 = fmaf(W.w[m2 + 1], va, a1); a3 = fmaf(W.w[m2 + 1], va, a3); b1 = fmaf(W.w[m2 + 1], vb, b1); b3 = fmaf(W.w[m2 + 1], vb, b3); }
         if (m2 + 4 <= 6) { a0 = fmaf(W.w[m2 + 4], va, a0); a4 = fmaf(W.w[m2 + 4], va, a4); b0 = fmaf(W.w[m2 + 4], vb, b0); b4 = fmaf(W.w[m2 + 4], vb, b4); }
       }
+    }
+    if (FACT) {
+      const float e1 = W.w[1], e4 = W.w[4], s21a = s9a + s12a, s21b = s9b + s12b;
+      a2 += s21a; a1 = fmaf(e1, s21a, a1); a3 = fmaf(e1, s21a, a3); a0 = fmaf(e4, s9a, a0); a4 = fmaf(e4, s9a, a4);
+      b2 += s21b; b1 = fmaf(e1, s21b, b1); b3 = fmaf(e1, s21b, b3); b0 = fmaf(e4, s9b, b0); b4 = fmaf(e4, s9b, b4);
     }
     const int zo = zin - 2;
     if (zo >= zc0) {
@@ -994,12 +1010,14 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   if (r2s_halo_exchange_f32(ctx, s, pl, k0, k1, nz, 2, 3)) return 1;
   CK(cudaEventRecord(ctx->ev[5], st));
   // mat-vec kernel: plane-marching (default) or tile-per-CTA (R2S_STENCIL=0, kept for comparison)
-  static const int svar = getenv("R2S_STENCIL") ? atoi(getenv("R2S_STENCIL")) : 2;      // 0 tile-per-CTA, 1 plane-marching, 2 plane-marching with 2 outputs/thread
-  const bool march = svar != 0;
+  // 0 tile-per-CTA, 1 plane-marching, 2 plane-marching with 2 outputs/thread (default), 3 = 2 with the factorised weights (opt-in, not yet
+  // measured on a GPU); read on every call so that one process can time the variants side by side
+  const int svar = getenv("R2S_STENCIL") ? atoi(getenv("R2S_STENCIL")) : 2;
+  const bool march = svar != 0, m2v = svar == 2 || svar == 3;
   // even z-chunks of about 64 planes: a 65-plane slab is one chunk, not 64 + 1
   const int nchunk = std::max(1, (k1 - k0 + 32) / 64), zc = cdiv(k1 - k0, nchunk);
-  dim3 sgrid = svar == 2 ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
-  int sthreads = svar == 2 ? 256 : (svar == 1 ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB));
+  dim3 sgrid = m2v ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
+  int sthreads = m2v ? 256 : (svar == 1 ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB));
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
@@ -1029,7 +1047,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
       if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      if (svar == 2) k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
+      if (svar == 3) k_stencil81_march2<true, true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
+      else if (svar == 2) k_stencil81_march2<true, false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
       else if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       else k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
       LAUNCH_CHECK();
@@ -1067,7 +1086,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  if (svar == 2) k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  if (svar == 3) k_stencil81_march2<false, true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  else if (svar == 2) k_stencil81_march2<false, false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   else if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   else k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   LAUNCH_CHECK();

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Side-by-side timing of the projection-kernel variants in ONE process (the R2S_PROJ* knobs are read on every call).
+"""Side-by-side timing of the kernel variants in ONE process (the R2S_PROJ* / R2S_STENCIL knobs are read on every call).
 
     python tools/ab_project.py [--n 256] [--steps 2] [--variants "name:K=V,K=V;name2:..."]
 
@@ -16,8 +16,8 @@ DEFAULT = ("general:R2S_PROJ_BOX=0;box5:;box5_fast:R2S_PROJ_FAST=1;box5_p1:R2S_P
            "box8_uni_p1:R2S_PROJ_UNI=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;refill3_box:R2S_PROJ=1;refill3_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1;"
            "refill4_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1,R2S_PROJ_MINB=4;general_fast_p1:R2S_PROJ_BOX=0,R2S_PROJ_FAST=1,R2S_PROJ_P1=1;general_uni_p1:R2S_PROJ_BOX=0,R2S_PROJ_UNI=1,R2S_PROJ_P1=1;"
            "box5_scaled:R2S_PROJ_SCALED=1;box5_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1;box6_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=6;"
-           "box8_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8")
-KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_P1")
+           "box8_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;stencil_fact:R2S_STENCIL=3")
+KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_P1", "R2S_STENCIL")
 
 
 def main():
@@ -62,9 +62,9 @@ def main():
         else:
             diff = float(np.max(np.abs(sdf - ref))) / grid.cell_size; sign_diff = int(np.count_nonzero(np.signbit(sdf) != np.signbit(ref)))
         out = {"variant": name, "knobs": kv, "n": n}
-        for k in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_total"):
+        for k in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cg", "ms_lsf", "ms_total"):
             out[k] = round(float(np.mean([getattr(r, k) for r in reps])), 3)
-        out.update(pairs=int(reps[-1].n_pairs), newton_iters=int(reps[-1].n_newton_iters), not_converged=int(reps[-1].n_not_converged),
+        out.update(pairs=int(reps[-1].n_pairs), newton_iters=int(reps[-1].n_newton_iters), not_converged=int(reps[-1].n_not_converged), cg_iters=int(reps[-1].cg_iters), th=float(reps[-1].th),
                    max_diff_over_h=diff, sign_diff=sign_diff)
         print(json.dumps(out), flush=True)
 
