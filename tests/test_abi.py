@@ -101,3 +101,22 @@ def test_grid_ctor_matches_reference_formula(r2s):
     assert list(g.N) == [16, 16, 16] and g.ngp == 4913 and abs(g.cell_size - 0.2) < 1e-15
     P = r2s.generateGridPoints(g)
     assert P.shape == (4913, 3) and np.allclose(P[1] - P[0], [g.cell_size, 0, 0])
+
+
+def test_tuning_knobs_named_by_the_tools_exist_in_the_sources():
+    """tools/ab_project.py and the opt-in GPU tests select kernel variants through environment knobs; a misspelt knob would silently
+    time / test the default kernels.  Every knob they name must be read somewhere in csrc/."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ab_project", os.path.join(root, "tools", "ab_project.py"))
+    ab = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ab)
+    src = "".join(open(os.path.join(root, "rho2sdf.jl_b200", "csrc", f)).read() for f in os.listdir(os.path.join(root, "rho2sdf.jl_b200", "csrc")) if f.endswith((".cu", ".cuh")))
+    read = set(re.findall(r'getenv\("(R2S_[A-Z0-9_]+)"\)', src))
+    named = set(ab.KNOBS)
+    for spec_ in ab.DEFAULT.split(";"):
+        _, _, kv = spec_.partition(":")
+        named |= {item.partition("=")[0] for item in kv.split(",") if item}
+    named |= set(re.findall(r'"(R2S_(?:PROJ|STENCIL|VOLCUT)[A-Z0-9_]*)"', open(os.path.join(root, "tests", "test_gpu_parity.py")).read()))
+    assert named <= read, sorted(named - read)
