@@ -117,14 +117,17 @@ __global__ void k_phase1(i64 nact, const ActRec *__restrict__ rec, const int *__
 // constants instead of 32, about half the FP64 work per iteration); kind_check != 0: the mesh holds both kinds of elements and
 // each of the two launches leaves the chunks of the other kind alone (ebox[e] = 1 for boxes, built with the mesh).
 // MODE: solver variant (r2s_iso.cuh) -- bit 0 FAST restoration (no confirming evaluation, same results), bit 1 one code path for all
-// tangent-step cases (results equal to rounding), bit 2 scaled box form (HexBox only).
+// tangent-step cases (results equal to rounding), bit 2 scaled box form (HexBox only), bit 3 the distance of a point in a tile without
+// boundary-face elements goes straight into dist[] by a 64-bit atomicMin (the minimum over the pairs is order independent there; the
+// pair buffer and the replay of k_assemble are then needed for the tiles with boundary faces only -- as in the lane-refill kernel).
 // P1: phase 1 of the solver (Newton projection of xi = 0 onto the iso-surface, the same for every point of an element)
 // comes from the per-element table built by k_phase1 instead of being recomputed by every lane of every chunk.
 template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX, int MODE, bool P1>
 __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
                                                       double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters,
-                                                      const unsigned char *__restrict__ ebox, int kind_check, const double4 *__restrict__ p1) {
+                                                      const unsigned char *__restrict__ ebox, int kind_check, const double4 *__restrict__ p1,
+                                                      const unsigned char *__restrict__ tile_faces, double *__restrict__ dist) {
   i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
   if (item >= nitems) return;
   // binary search: last a with choff[a] <= item
@@ -174,7 +177,14 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
       iso::HexBoxS B; iso::make_box_scaled(A, x, B);
       if (P1) okc = iso::project_hex8_from<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
       else okc = iso::project_hex8<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
-      pairbuf[r.pair_off + li] = sqrt(iso::eval_f(B, x, xi));
+      const double dd = sqrt(iso::eval_f(B, x, xi));
+      bool direct = false;
+      if constexpr ((MODE & 8) != 0) {
+        const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
+        direct = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] == 0;
+        if (direct) atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
+      }
+      if (!direct) pairbuf[r.pair_off + li] = dd;
     } else {
     if (BOX) {
       iso::HexBox B; iso::make_box(A, B);
@@ -188,7 +198,14 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
       iso::eval_pos(T, xi, p);
     }
     double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
-    pairbuf[r.pair_off + li] = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+    const double dd = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+    bool direct = false;
+    if constexpr ((MODE & 8) != 0 && !WANT_XP) {
+      const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
+      direct = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] == 0;
+      if (direct) atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
+    }
+    if (!direct) pairbuf[r.pair_off + li] = dd;
     if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
     }
   }
@@ -723,6 +740,12 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   // (The R2S_PROJ* tuning knobs are read on every call so that one process can time the variants side by side, tools/ab_project.py.)
   const bool refill = getenv("R2S_PROJ") && atoi(getenv("R2S_PROJ")) == 1;       // experimental lane-refill projection (not faster yet)
   const bool minpath = (refill && nen == 8 && !want_xp);
+  // chunk kernel with direct atomicMin output (opt-in, MODE bit 3): dist[] starts at BIG, k_assemble replays the tiles with boundary faces only
+  const bool atom = !minpath && nen == 8 && !want_xp && getenv("R2S_PROJ_ATOM") && atoi(getenv("R2S_PROJ_ATOM")) == 1 && !(getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1);
+  if (atom) {
+    i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
+    k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
+  }
   if (minpath) {
     i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
@@ -753,11 +776,13 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
     const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
 #define PROJH6(XP, MB, SA, BX, MD, PP) k_project_hex8<XP, MB, SA, BX, MD, PP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
-                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc, p1tab)
+                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc, p1tab, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>())
 #define PROJH(XP, MB, SA, BX, FS) PROJH6(XP, MB, SA, BX, 0, false)
     // the opt-in variants (FAST solver and / or phase 1 from the table), instantiated for the occupancies worth measuring
 #define PROJO(MB, BX) do { \
-      if (scaled && BX) { if (use_p1) PROJH6(false, MB, false, BX, 7, true); else PROJH6(false, MB, false, BX, 7, false); } \
+      if (atom && scaled && BX) PROJH6(false, MB, false, BX, 15, true); \
+      else if (atom) PROJH6(false, MB, false, BX, 11, true); \
+      else if (scaled && BX) { if (use_p1) PROJH6(false, MB, false, BX, 7, true); else PROJH6(false, MB, false, BX, 7, false); } \
       else if (uni) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
       else if (fast) { if (use_p1) PROJH6(false, MB, false, BX, 1, true); else PROJH6(false, MB, false, BX, 1, false); } \
       else PROJH6(false, MB, false, BX, 0, true); } while (0)
@@ -767,10 +792,11 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path), R2S_PROJ_SCALED=1 (UNI + the scaled box form HexBoxS), R2S_PROJ_P1=1 (phase 1 from a per-element table).
     const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
     const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 5;      // measured at n = 256: 92.6 / 86.5 / 89.5 ms for 4 / 5 / 6 CTAs per SM (profiles/r1f_ab_project_variants_n256.jsonl)
+    // R2S_PROJ_ATOM=1: UNI + P1 + direct atomicMin output for tiles without boundary-face elements (decided above: `atom`)
     const bool scaled = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_SCALED") && atoi(getenv("R2S_PROJ_SCALED")) == 1;
-    const bool uni = scaled || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1);
+    const bool uni = scaled || atom || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1);
     const bool fast = uni || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
-    const bool use_p1 = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_P1") && atoi(getenv("R2S_PROJ_P1")) == 1;
+    const bool use_p1 = atom || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_P1") && atoi(getenv("R2S_PROJ_P1")) == 1);
     const i64 nbx = (use_box && nen == 8) ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
     const double4 *p1tab = nullptr;
     if (use_p1) {
@@ -812,7 +838,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
         ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
         ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
-    if (minpath) { ASM(false, 8, true); }
+    if (minpath || atom) { ASM(false, 8, true); }
     else if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
     else { if (want_xp) { ASM(true, 4, false); ASM(true, 4, true); } else { ASM(false, 4, false); ASM(false, 4, true); } }
 #undef ASM

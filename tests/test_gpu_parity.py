@@ -388,7 +388,8 @@ OPTIN = pytest.mark.skipif(os.environ.get("R2S_TEST_OPTIN") != "1", reason="opt-
 @pytest.mark.parametrize("knobs", [{"R2S_PROJ_FAST": "1"}, {"R2S_PROJ_P1": "1"}, {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1"},
                                    {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "8"}, {"R2S_PROJ": "1", "R2S_PROJ_FAST": "1"},
                                    {"R2S_PROJ_UNI": "1"}, {"R2S_PROJ_UNI": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}, {"R2S_PROJ": "1", "R2S_PROJ_UNI": "1"},
-                                   {"R2S_PROJ_SCALED": "1"}, {"R2S_PROJ_SCALED": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}])
+                                   {"R2S_PROJ_SCALED": "1"}, {"R2S_PROJ_SCALED": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"},
+                                   {"R2S_PROJ_ATOM": "1"}, {"R2S_PROJ_ATOM": "1", "R2S_PROJ_SCALED": "1"}])
 def test_optin_projection_variants(r2s, monkeypatch, knobs):
     """FAST restoration / per-element phase-1 table (r2s_iso.cuh): on the host build they reproduce the exact variants bit for bit
     (tests/test_iso_host.py); here the kernels that carry them, on the mixed mesh and on a replica of the bench workload."""
@@ -404,7 +405,7 @@ def test_optin_projection_variants(r2s, monkeypatch, knobs):
         for k in knobs:
             monkeypatch.delenv(k)
         assert np.max(np.abs(d - od)) <= DIST_TOL * grid.cell_size
-        if not ({"R2S_PROJ", "R2S_PROJ_UNI", "R2S_PROJ_SCALED"} & set(knobs)):
+        if not ({"R2S_PROJ", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_ATOM"} & set(knobs)):
             assert np.array_equal(d, d_ref)                 # same arithmetic as the default kernels
         mesh.ctx.close()
 

@@ -128,6 +128,26 @@ def main():
                     lanes[l].pop(0)
                     if not lanes[l]: lanes[l] = None
         print("lane-refill kernel%s: lane utilisation %.1f%%; %.0f warp instructions issued per 32 pairs" % (" with ONE tangent code path" if unified else "", 100 * useful / issued, issued / npairs))
+    # ---- (d) persistent warps: a warp walks through many elements and refills idle lanes across element boundaries (no drain per element)
+    for unified in (False, True):
+        useful = issued = 0.0
+        nwarps = 16
+        for w in range(nwarps):
+            stream = [p[1] for pairs in elems[w::nwarps] for p in pairs]
+            lanes = [None] * 32; q = 0
+            while True:
+                for l in range(32):
+                    while lanes[l] is None and q < len(stream):
+                        lanes[l] = list(stream[q]) or None; q += 1
+                act = [l for l in range(32) if lanes[l]]
+                if not act: break
+                c, _ = iter_cost_warp([lanes[l][0] for l in act], unified)
+                issued += 32 * (c + 30.0)                                # refill bookkeeping + per-lane element constants
+                useful += sum(iter_cost_lane(lanes[l][0]) for l in act)
+                for l in act:
+                    lanes[l].pop(0)
+                    if not lanes[l]: lanes[l] = None
+        print("persistent lane-refill%s: lane utilisation %.1f%%; %.0f warp instructions issued per 32 pairs" % (" with ONE tangent code path" if unified else "", 100 * useful / issued, issued / npairs))
 
 
 if __name__ == "__main__":
