@@ -5,11 +5,12 @@
 // tiles its candidate point range overlaps ((tile, element) keys, radix sort); a CTA owns one tile, stages the tile's
 // element list (ascending element index = the reference's candidate order) through shared memory together with the
 // element's nodal coordinates/densities, and every thread replays the reference's per-point rule exactly.
+#include <stdlib.h>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
 #include "r2s_exact.cuh"
 
-struct SRange { int a[3], b[3]; int hot, pad; };   // inclusive grid-point index range of the candidate points of one element;
+struct SRange { int a[3], b[3]; int hot, pad; };   // inclusive grid-point index range of the candidate points of one element; pad = density class (below);
                                                    // hot = some nodal density >= rho_t (HEX8 skip rule, SignDetection.jl:36)
 
 typedef ex::AffineInv SignEl;      // per-element affine inverse-map data (r2s_exact.cuh)
@@ -25,9 +26,17 @@ __global__ void k_sign_ranges(i64 nel, int nen, const int *__restrict__ IEN, con
   { const double2 z = ezr[e];      // z-slab: elements that cannot reach this rank's planes get an empty range without touching their nodes
     if (z.y < zlo || z.x > zhi) { SRange r; r.a[0] = 1; r.b[0] = 0; r.a[1] = r.a[2] = 1; r.b[1] = r.b[2] = 0; r.hot = 0; r.pad = 0; rng[e] = r; ntile[e] = 0; return; } }
 
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rmax = -1e300;
-  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; rmax = fmax(rmax, rn[n]); for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
-  SRange r; bool ok = true; r.pad = 0;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rmax = -1e300, rmin = 1e300;
+  for (int a = 0; a < nen; a++) { i64 n = IEN[nen * e + a]; rmax = fmax(rmax, rn[n]); rmin = fmin(rmin, rn[n]); for (int d = 0; d < 3; d++) { double c = X[3 * n + d]; lo[d] = fmin(lo[d], c); hi[d] = fmax(hi[d], c); } }
+  SRange r; bool ok = true;
+  // Density class of a HEX8 element for the opt-in shortcut of k_sign<8, true>: for max|xi| < 1.01 every shape function is above
+  // -0.01 * 2.01^2 / 8 and they sum to one, so the interpolated density stays within [rmin - 0.05 range, rmax + 0.05 range].
+  // 1: it is >= rho_t for every admissible xi (the test "rho >= rho_t" is known to hold), 2: it is < rho_t, 0: undecided.
+  r.pad = 0;
+  if (nen == 8) {
+    const double range = rmax - rmin, tolc = 1e-9 * fmax(1.0, fabs(rho_t));
+    if (rmin - 0.05 * range >= rho_t + tolc) r.pad = 1; else if (rmax + 0.05 * range < rho_t - tolc) r.pad = 2;
+  }
   r.hot = (nen == 4 || !(rmax < rho_t)) ? 1 : 0;
   for (int d = 0; d < 3; d++) {
     const double *pc = g.pc + g.pc_off[d]; int n1 = g.np[d], a, b;
@@ -83,7 +92,9 @@ __global__ void k_sign_emit(i64 nel, const SRange *__restrict__ rng, const i64 *
 // preserved), then every lane advances through that culled list on its own: all lanes run the expensive inverse map at
 // the same time, each on its own next candidate, instead of serialising over elements.
 #define CULL_CAP 96
-template <int NEN>
+// CLS (opt-in, R2S_SIGN_CLASS=1): candidates whose element is of density class 1 / 2 (k_sign_ranges) skip the gather of the eight
+// nodal densities and the shape functions -- the outcome of "rho >= rho_t" is known; the state updates (max_local, break) are the same.
+template <int NEN, bool CLS>
 __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
                                                    const SRange *__restrict__ rng, const SignEl *__restrict__ sel, const int *__restrict__ IEN, const double *__restrict__ X,
                                                    const double *__restrict__ rn, double rho_t, const double *__restrict__ dist,
@@ -180,12 +191,16 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
           }
           double mn = ex::max3abs(xi[0], xi[1], xi[2]);
           if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
-            double N[8], re[8];
+            const int dcls = CLS ? s_rg[warp][pos].pad : 0;
+            if (dcls == 1) sign = 1.0;
+            else if (dcls == 0) {
+              double N[8], re[8];
 #pragma unroll
-            for (int a = 0; a < 8; a++) re[a] = rn[IEN[8 * (i64)e + a]];
-            ex::hex8_shape(xi, N);
-            double rho = ex::dot8(N, re);
-            if (rho >= rho_t) sign = 1.0;
+              for (int a = 0; a < 8; a++) re[a] = rn[IEN[8 * (i64)e + a]];
+              ex::hex8_shape(xi, N);
+              double rho = ex::dot8(N, re);
+              if (rho >= rho_t) sign = 1.0;
+            }
             if (mn < 0.95) done = true;                              // :51-59 break
             max_local = mn;
           }
@@ -269,11 +284,15 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   double *signs = nullptr, *sdf = nullptr;
   if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
   if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
-  if (nen == 8)
-    k_sign<8><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
+  const bool cls_shortcut = nen == 8 && getenv("R2S_SIGN_CLASS") && atoi(getenv("R2S_SIGN_CLASS")) == 1;      // opt-in, not yet measured on a GPU
+  if (cls_shortcut)
+    k_sign<8, true><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
+                                                             ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
+  else if (nen == 8)
+    k_sign<8, false><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
                                                        ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
   else
-    k_sign<4><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
+    k_sign<4, false><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
                                                        ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
   LAUNCH_CHECK();
   return 0;

@@ -458,3 +458,22 @@ def test_factorised_stencil_variant(r2s, monkeypatch):
     r2s.remove_sdf_artifacts(sdf, grid, mesh=mesh)
     check_rbf(r2s, mesh, grid, sdf, mesh.V_domain * mesh.V_frac)
     mesh.ctx.close()
+
+
+@OPTIN
+def test_sign_density_class_shortcut(r2s, monkeypatch):
+    """R2S_SIGN_CLASS=1: elements whose interpolated density cannot cross rho_t skip the shape-function evaluation; the sign field must be
+    bit-identical to the default kernel's (and the oracle's) on structured and unstructured meshes."""
+    cases = [simp_hex8(16) + (32,), _mixed_mesh(10) + (20,)] + [load_mesh(nm) + (40,) for nm in ("sphere", "chapadlo")]
+    for X, IEN, rho, nmax in cases:
+        mesh = r2s.Mesh(X, IEN, rho)
+        grid = r2s.Grid(*r2s.getMesh_AABB(X), nmax, 3)
+        rn = r2s.DenseInNodes(mesh, rho)
+        for rt in (0.5, 0.3):
+            monkeypatch.delenv("R2S_SIGN_CLASS", raising=False)
+            s0 = r2s.Sign_Detection(mesh, grid, None, rn, rt)
+            monkeypatch.setenv("R2S_SIGN_CLASS", "1")
+            s1 = r2s.Sign_Detection(mesh, grid, None, rn, rt)
+            assert np.array_equal(s0, s1)
+        monkeypatch.delenv("R2S_SIGN_CLASS", raising=False)
+        mesh.ctx.close()

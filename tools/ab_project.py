@@ -16,8 +16,8 @@ DEFAULT = ("general:R2S_PROJ_BOX=0;box5:;box5_fast:R2S_PROJ_FAST=1;box5_p1:R2S_P
            "box8_uni_p1:R2S_PROJ_UNI=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;refill3_box:R2S_PROJ=1;refill3_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1;"
            "refill4_box_uni:R2S_PROJ=1,R2S_PROJ_UNI=1,R2S_PROJ_MINB=4;general_fast_p1:R2S_PROJ_BOX=0,R2S_PROJ_FAST=1,R2S_PROJ_P1=1;general_uni_p1:R2S_PROJ_BOX=0,R2S_PROJ_UNI=1,R2S_PROJ_P1=1;"
            "box5_scaled:R2S_PROJ_SCALED=1;box5_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1;box6_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=6;"
-           "box8_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;box5_atom:R2S_PROJ_ATOM=1;box6_atom_scaled:R2S_PROJ_ATOM=1,R2S_PROJ_SCALED=1,R2S_PROJ_BOX_MINB=6;stencil_fact:R2S_STENCIL=3")
-KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_P1", "R2S_PROJ_ATOM", "R2S_STENCIL")
+           "box8_scaled_p1:R2S_PROJ_SCALED=1,R2S_PROJ_P1=1,R2S_PROJ_BOX_MINB=8;box5_atom:R2S_PROJ_ATOM=1;box6_atom_scaled:R2S_PROJ_ATOM=1,R2S_PROJ_SCALED=1,R2S_PROJ_BOX_MINB=6;stencil_fact:R2S_STENCIL=3;sign_class:R2S_SIGN_CLASS=1")
+KNOBS = ("R2S_PROJ", "R2S_PROJ_BOX", "R2S_PROJ_BOX_MINB", "R2S_PROJ_MINB", "R2S_PROJ_SMEMA", "R2S_PROJ_FAST", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_P1", "R2S_PROJ_ATOM", "R2S_STENCIL", "R2S_SIGN_CLASS")
 
 
 def main():
