@@ -11,7 +11,10 @@ out = None
 for r in rows[2:]:
     if len(r) < len(hdr) or not re.search(pat, r[col["Kernel Name"]]): continue
     rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]); wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-    out = {"kernel": r[col["Kernel Name"]].split("(")[0], "n": n, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+    kname = r[col["Kernel Name"]].split("(")[0]
+    targs = re.search(r"k_project_hex8<([^>]*)>", kname)       # <XP, MINB, SMEM_A, BOX, MODE, P1>: the 4th argument tells the element variant
+    variant = "box" if targs and len(targs.group(1).split(",")) >= 4 and targs.group(1).split(",")[3].strip() in ("1", "true") else "general"
+    out = {"kernel": kname, "variant": variant, "n": n, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
            "duration_ms_under_ncu": float(r[col["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[col["gpu__time_duration.sum"]]],
            "source": os.path.basename(rep)}
     break
