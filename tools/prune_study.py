@@ -135,6 +135,16 @@ def main():
             cur = min(cur, ds[q]); k += 1; iters_bf += int(its_s[q])
         done += k; per_vox.append(k)
     per_vox = np.array(per_vox)
+    # two global passes: A = every pair whose point lies inside the element's AABB (bound 0, never skippable); B = the others, skipped when
+    # their bound is not below the minimum pass A left for the point (points no pass-A pair reached keep +inf: nothing skipped for them)
+    bestA = np.full(int(g.ngp), np.inf)
+    inA = lb == 0.0
+    np.minimum.at(bestA, vox[inA], dist[inA])
+    for name, bound in (("element AABB", lb), ("tight box", lbt)):
+        keepB = (~inA) & (bound < bestA[vox])
+        kept = inA.sum() + keepB.sum()
+        print("two global passes with the %s: pass A %d pairs, pass B keeps %d of %d -> %.1f%% of all pairs, %.1f%% of the iterations" % (
+            name, inA.sum(), keepB.sum(), (~inA).sum(), 100 * kept / npairs, 100 * (its[inA].sum() + its[keepB].sum()) / its.sum()))
     print("pairs that can matter (bound < final minimum): element AABB %d (%.1f%%), tight box %d (%.1f%%)" % (
         need_a.sum(), 100 * need_a.mean(), need_t.sum(), 100 * need_t.mean()))
     print("best-first per grid point with the tight box: %d projections (%.1f%% of the pairs, %.2f per band point; p50 %d p90 %d max %d), %.1f%% of the iterations" % (
