@@ -3,7 +3,9 @@
 
 Runs the host build of the solver (tests/host/libiso_host.so) with its event trace on a replica of the bench workload and replays
 the traces of 32 lanes in lock step the way a warp executes them: a loop runs as long as its slowest lane, every distinct branch
-taken by some lane is issued once.  Costs are FP64-pipe instruction counts of the HexBox variant (read off the SASS).  Output:
+taken by some lane is issued once.  Costs are estimated FP64-pipe instruction counts per solver part of the HexBox variant (COST
+below: evaluation of g + Newton step 25, full evaluation 45, tangent3 95, tangent2 55, ...); the conclusions do not hinge on their exact
+values -- the model reproduces the measured lane utilisation (ncu: 16.9 of 32 lanes) and the measured ranking chunk > lane-refill.  Output:
 lane utilisation (useful lane-work / 32 x issued work) of (a) the chunk kernel (one warp = 32 consecutive points of an element,
 lanes synchronised at iteration granularity), (b) the same with one code path for all tangent-step variants, (c) the lane-refill
 kernel (lanes at different iterations of different points), and the share of the issued work per solver part."""
