@@ -126,3 +126,23 @@ def test_single_path_tangent_step_matches(host):
         _, d8, _ = many(host, Xe, re, P, 0.5, 8)
         worst = max(worst, float(np.abs(d8 - d0).max()) / h)
     assert worst <= 5e-11, worst
+
+
+def test_coordinate_offset_sensitivity(host):
+    """The solver works in global coordinates (like the reference): X(xi) - x cancels the mesh offset.  Up to offset / h = 1e4 the result
+    moves by < 1e-10 h; the scaled box form (HexBoxS, local coordinates) does not depend on the offset at all.  (Beyond ~1e5 the
+    line search of the global-coordinate variants -- and of the oracle -- hits the round-off floor)"""
+    rng = np.random.default_rng(5)
+    worst = {0: 0.0, 1: 0.0, 6: 0.0}
+    for _ in range(400):
+        c = np.round(rng.uniform(-5, 5, 3) * 2 ** 20) / 2 ** 20; h = np.round(rng.uniform(0.2, 1.0, 3) * 2 ** 20) / 2 ** 20
+        re = rng.uniform(0, 1, 8)
+        if not (re.min() < 0.5 < re.max()):
+            continue
+        U = np.round(rng.uniform(-2.2, 2.2, (16, 3)) * 2 ** 10) / 2 ** 10
+        Xe, P = c + SG * h, c + U * h
+        _, dref, _ = many(host, Xe, re, P, 0.5, 0)
+        for v, off in ((0, 1e4), (1, 1e4), (6, 1e6)):
+            _, d, _ = many(host, Xe + off, re, P + off, 0.5, v)
+            worst[v] = max(worst[v], float(np.abs(d - dref).max()) / float(h.min()))
+    assert worst[0] <= 1e-10 and worst[1] <= 1e-10 and worst[6] <= 1e-12, worst
