@@ -139,6 +139,14 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   // element data: lane l < 8 loads node l; monomial coefficients assembled through shuffles
   double v[4] = {0, 0, 0, 0};
   if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
+  // MODE bit 1 (the variants that are equal to the default only up to rounding anyway): element-local coordinates -- node 0 is subtracted
+  // from the nodes and from the grid point (exact in floating point for any reasonable mesh), so X(xi) - x no longer cancels the mesh
+  // offset (tests/test_iso_host.py::test_coordinate_offset_sensitivity)
+  double org[3] = {0, 0, 0};
+  if constexpr ((MODE & 2) != 0 && !WANT_XP) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { org[d] = __shfl_sync(0xffffffffu, v[d], 0); v[d] -= org[d]; }
+  }
   // SMEM_A: the warp-uniform monomial coefficients live in shared memory (broadcast reads) instead of 64 registers per thread
   __shared__ double sA[SMEM_A ? 4 : 1][4][8];
   double Ar[SMEM_A ? 1 : 4][8], re[8];
@@ -170,6 +178,7 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   if (li < vol) {
     int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
     double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]};
+    if constexpr ((MODE & 2) != 0 && !WANT_XP) { x[0] -= org[0]; x[1] -= org[1]; x[2] -= org[2]; }
     double xi[3], p[3] = {0, 0, 0};
     double xi0[3] = {0, 0, 0}; bool ok0 = false;
     if (P1) { const double4 q = p1[lo]; xi0[0] = q.x; xi0[1] = q.y; xi0[2] = q.z; ok0 = q.w != 0.0; }
