@@ -53,6 +53,13 @@ void iso_host_counts(long *out, int reset) { for (int k = 0; k < 8; k++) { out[k
 // event trace (see ISO_TRACE in r2s_iso.cuh): the caller provides the buffer; a 0 is appended by iso_host_project_many after every pair
 void iso_host_trace(int *buf, long cap) { iso_trace = buf; iso_trace_cap = cap; iso_trace_n = 0; }
 long iso_host_trace_len() { return iso_trace_n; }
+// TET4: closest point on the in-element iso-polygon (project_tet4); Xe [4][3] row-major nodes.  Returns 1 when a projection exists.
+int iso_host_project_tet4(const double *Xe, const double *re, const double *x, double rho_t, double *xp) {
+  static const int isn[4][3] = {{0, 2, 1}, {0, 1, 3}, {1, 2, 3}, {0, 3, 2}};
+  double T[3][4];
+  for (int a = 0; a < 4; a++) for (int d = 0; d < 3; d++) T[d][a] = Xe[3 * a + d];
+  return iso::project_tet4(T, re, isn, x, rho_t, xp) ? 1 : 0;
+}
 int iso_host_is_box(const double *Xe, const double *re) { double A[4][8]; coefficients(Xe, re, A); return iso::is_box(A) ? 1 : 0; }
 // batch over n points of ONE element; its[n] receives the phase-2 iteration count (the quantity a warp waits on).
 // variant 0: general trilinear, 1: HexBox, 2: HexBox FAST, 3: HexBox FAST with phase 1 computed once for the element (the table

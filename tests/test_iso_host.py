@@ -26,6 +26,7 @@ def host():
     dp = np.ctypeslib.ndpointer(np.float64, flags="C")
     L.iso_host_project_many.argtypes = [dp, dp, C.c_long, dp, C.c_double, C.c_int, dp, np.ctypeslib.ndpointer(np.int32, flags="C")]
     L.iso_host_is_box.argtypes = [dp, dp]
+    L.iso_host_project_tet4.argtypes = [dp, dp, dp, C.c_double, dp]
     return L
 
 
@@ -146,3 +147,26 @@ def test_coordinate_offset_sensitivity(host):
             _, d, _ = many(host, Xe + off, re, P + off, 0.5, v)
             worst[v] = max(worst[v], float(np.abs(d - dref).max()) / float(h.min()))
     assert worst[0] <= 1e-10 and worst[1] <= 1e-10 and worst[6] <= 1e-12, worst
+
+
+def test_tet4_projection_matches_the_oracle(host):
+    """project_tet4 (closest point on the in-element iso-polygon of a linear tetrahedron) on random tets, including nodes that sit exactly
+    on the iso value: same existence verdict, same distance."""
+    rng = np.random.default_rng(3)
+    n = 0
+    for t in range(6000):
+        Xe = np.ascontiguousarray(rng.uniform(-1, 1, (4, 3)) + rng.uniform(-5, 5, 3))
+        if abs(np.linalg.det(Xe[1:] - Xe[0])) < 1e-3:
+            continue
+        re = rng.uniform(0, 1, 4)
+        if t % 5 == 0:
+            re[rng.integers(4)] = 0.5
+        x = np.ascontiguousarray(Xe.mean(0) + rng.uniform(-2, 2, 3))
+        xp = np.zeros(3)
+        ok = host.iso_host_project_tet4(Xe, np.ascontiguousarray(re), x, 0.5, xp)
+        oko, xpo = oracle.project_iso_tet4(x, 0.5, Xe, re)
+        assert bool(ok) == oko
+        if ok:
+            assert abs(np.linalg.norm(x - xp) - np.linalg.norm(x - xpo)) <= 1e-12
+            n += 1
+    assert n > 3000
