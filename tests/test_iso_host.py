@@ -172,6 +172,38 @@ def test_tet4_projection_matches_the_oracle(host):
     assert n > 3000
 
 
+def test_bench_replica_pair_by_pair(host):
+    """A 24^3 replica of the bench workload (synthetic SIMP field, grid step h_e / 2, delta = 1.1 cells): the HexBox device code against the
+    oracle on every 5th (element, grid point) pair of every crossing element -- the per-pair version of the GPU parity test, which only
+    sees the minimum over the pairs of a grid point."""
+    from fixtures import Grid, simp_hex8
+    n = 24
+    X, IEN, rho = simp_hex8(n, period_frac=64.0 / n)
+    g = Grid(X.min(0), X.max(0), 2 * n, 3)
+    rn = oracle.nodal_densities(X, IEN, rho)
+    delta = 1.1 * g.cell_size
+    re_all = rn[IEN - 1]
+    crossing = np.nonzero((re_all.min(1) < 0.5) & (re_all.max(1) > 0.5))[0]
+    pc = [g.AABB_min[d] + g.cell_size * np.arange(g.N[d] + 1) for d in range(3)]
+    worst = 0.0; npairs = 0
+    for e in crossing:
+        Xe = np.ascontiguousarray(X[IEN[e] - 1]); re = np.ascontiguousarray(re_all[e]); lo, hi = Xe.min(0), Xe.max(0)
+        rng = []
+        for d in range(3):
+            I0 = int(np.floor(g.N[d] * ((lo[d] - delta) - g.AABB_min[d]) / (g.AABB_max[d] - g.AABB_min[d])))
+            I1 = int(np.floor(g.N[d] * ((hi[d] + delta) - g.AABB_min[d]) / (g.AABB_max[d] - g.AABB_min[d])))
+            rng.append(np.arange(max(I0, 0), min(I1, g.N[d]) + 1))
+        K, J, I = np.meshgrid(rng[2], rng[1], rng[0], indexing="ij")
+        P = np.ascontiguousarray(np.stack([pc[0][I.ravel()], pc[1][J.ravel()], pc[2][K.ravel()]], axis=1)[::5])
+        rc, d, _ = many(host, Xe, re, P, 0.5, 1)
+        assert rc == 0
+        for q in range(len(P)):
+            ok, do = oracle_distance(P[q], Xe, re)
+            assert ok
+            worst = max(worst, abs(d[q] - do) / g.cell_size); npairs += 1
+    assert npairs > 15000 and worst <= 1e-10, (npairs, worst)
+
+
 @pytest.mark.xfail(strict=True, reason="known: degenerate pairs where the device solver and the oracle part ways by round-off (DESIGN.md section 8)")
 def test_degenerate_pairs_found_by_fuzzing(host):
     """Two (element, point) pairs found by fuzzing the host build against the oracle (tests/golden/degenerate_pairs.npz):
