@@ -21,7 +21,7 @@ static long iso_counts[8];      // 0 eval_full, 1 eval_g, 2 eval_f, 3 tangent st
 #define ISO_COUNT(k) (iso_counts[k]++)
 // optional event trace of one projection (tools/divergence_model.py): codes 1 eval_g inside restore, 2 line-search trial, 3 eval_full
 // (= start of a phase-2 iteration), 10..12 tangent3<K>, 13..15 tangent2 (fixed variable 0,1,2), 16 fewer than two free variables,
-// 17 Gauss-Newton fallback of the multiplier branch
+// 17 Gauss-Newton fallback of the multiplier branch, 18 the single-path tangent step (MODE bit 1)
 static int *iso_trace = nullptr; static long iso_trace_n = 0, iso_trace_cap = 0;
 #define ISO_TRACE(c) do { if (iso_trace && iso_trace_n < iso_trace_cap) iso_trace[iso_trace_n++] = (c); } while (0)
 #else
