@@ -531,7 +531,7 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
         }
       }
       int refix = 0;
-      for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { fix[i] = bnd[i]; refix = 1; }
+      for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { if (fabs(d[i]) <= tolx) d[i] = 0.0; else { fix[i] = bnd[i]; refix = 1; } }      /* a numerically zero outward component is noise, not a reason to re-fix */
       if (refix) continue;
       dm = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
       if (r2so_debug) printf("O   pass=%d lam=%.15g d=(%.6e %.6e %.6e) fix=(%d %d %d) den=%.3e\n", pass, lam, d[0], d[1], d[2], fix[0], fix[1], fix[2], den);
@@ -550,8 +550,9 @@ static int project_iso_hex8(const double x[3], double rho_t, const double Xe[3][
     /* ratio test against the box */
     double amax = 1.0; int blk = -1;
     for (int i = 0; i < 3; i++) if (!fix[i]) {
-      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
-      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
+      /* ties between blocking bounds (within 1e-12) go to the lower index, so that round-off cannot choose the face */
+      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
+      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
     }
     double slope = E.c[0] * d[0] + E.c[1] * d[1] + E.c[2] * d[2];
     if (!(slope < 0.0)) { force = 1; continue; }        /* no descent left on this face: go to the multiplier test */

@@ -464,7 +464,7 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
       }
       bool refix = false;
 #pragma unroll
-      for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { fix[i] = bnd[i]; refix = true; }
+      for (int i = 0; i < 3; i++) if (!fix[i] && bnd[i] && d[i] * bnd[i] > 0.0) { if (fabs(d[i]) <= tolx) d[i] = 0.0; else { fix[i] = bnd[i]; refix = true; } }      // a numerically zero outward component is noise, not a reason to re-fix
       if (refix) continue;
       dm = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
       if (dm > tolx && !force) { have_step = true; break; }
@@ -485,8 +485,9 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
     double amax = 1.0; int blk = -1;
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) {
-      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
-      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax) { amax = t; blk = i; } }
+      // ties between blocking bounds (within 1e-12) go to the lower index, so that round-off cannot choose the face
+      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
+      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
     }
     double slope = fma(E.c[2], d[2], fma(E.c[1], d[1], E.c[0] * d[0]));
     if (!(slope < 0.0)) { S.force = true; S.it++; return 0; }      // no descent left on this face: go to the multiplier test

@@ -204,7 +204,6 @@ def test_bench_replica_pair_by_pair(host):
     assert npairs > 15000 and worst <= 1e-10, (npairs, worst)
 
 
-@pytest.mark.xfail(strict=True, reason="known: degenerate pairs where the device solver and the oracle part ways by round-off (DESIGN.md section 8)")
 def test_degenerate_pairs_found_by_fuzzing(host):
     """Two (element, point) pairs found by fuzzing the host build against the oracle (tests/golden/degenerate_pairs.npz):
     0: chapadlo element 1115, two nodal densities exactly at rho_t so that g vanishes along an element edge -- after the multiplier test
