@@ -95,6 +95,13 @@ class ClockSampler:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def workload(n):
     from fixtures import simp_hex8
     return simp_hex8(n)
@@ -130,16 +137,48 @@ def cpu_pipeline(n):
     g = Grid(X.min(0), X.max(0), 2 * n, 3)
     vd, vf = oracle.mesh_volume(X, IEN, rho)
     rn = oracle.nodal_densities(X, IEN, rho)
-    nt = oracle.max_threads()
+    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 for nproc > 1, which the oracle's explicit
+    # num_threads(nt) clauses override
+    nt = host_threads()
 
-    def step():
+    def step(keep=None):
         t0 = time.perf_counter()
         d, _, _ = oracle.eval_distances(X, IEN, g, rn, 0.5, 1.1, nthreads=nt, want_xp=False)
         s = oracle.sign_detection(X, IEN, g, rn, 0.5, nthreads=nt)
         sdf, _ = oracle.remove_artifacts(d * s, g)
-        fine, _ = oracle.rbf_smoothing(sdf, g, True, 2, vd * vf, mode=0, nthreads=nt)
-        return time.perf_counter() - t0, fine.size
+        fine, info = oracle.rbf_smoothing(sdf, g, True, 2, vd * vf, mode=0, nthreads=nt)
+        t = time.perf_counter() - t0
+        if keep is not None:      # the parity leg of the GPU arm compares these with the CUDA path on the same replica
+            keep.update(X=X, IEN=IEN, rho=rho, grid=g, sdf=sdf, fine=fine, cg_iters=info["cg_iters"], th=info["th"], target=vd * vf)
+        return t, fine.size
     return step, nt, g
+
+
+def gpu_parity_on_replica(r2s, ref, device, stream):
+    """The CUDA path on the replica the CPU oracle just ran (same inputs), compared field by field: the `parity` object of the bench line."""
+    X, IEN, rho, g = ref["X"], ref["IEN"], ref["rho"], ref["grid"]
+    mesh = r2s.Mesh(X, IEN, rho, element_type=r2s.HEX8, device=device, stream=stream)
+    grid = r2s.Grid(X.min(0), X.max(0), int(g.N[0]) - 6, 3)
+    assert list(grid.N) == list(g.N) and grid.cell_size == g.cell_size
+    rho_n = r2s.DenseInNodes(mesh, rho)
+    mesh._use_grid(grid)
+    c = mesh.ctx
+    p = r2s.Params(); c.lib.r2s_default_params(C.byref(p))
+    p.rho_t, p.smooth, p.rbf_interp, p.remove_artifacts = 0.5, 2, 1, 1
+    p.target_volume, p.final_volume = mesh.V_frac * mesh.V_domain, 1
+    sdf = np.empty(grid.ngp); fine = np.empty(ref["fine"].size, dtype=np.float32); rep = r2s.Report()
+    c.check(c.lib.r2s_pipeline(c.h, C.byref(p), rho_n.ctypes.data_as(C.c_void_p), sdf.ctypes.data_as(C.c_void_p), fine.ctypes.data_as(C.c_void_p), C.byref(rep)))
+    c.close()
+    h = grid.cell_size
+    osdf, ofine = ref["sdf"], ref["fine"].ravel()
+    far_g, far_o = np.abs(sdf) > 1e9, np.abs(osdf) > 1e9
+    band = ~(far_g | far_o)
+    return {"replica_n": int(round(len(rho) ** (1 / 3))), "coarse_points": int(grid.ngp), "fine_voxels": int(fine.size),
+            "max_dist_err_over_h": float(np.max(np.abs(np.abs(sdf[band]) - np.abs(osdf[band]))) / h), "band_mismatches": int(np.count_nonzero(far_g != far_o)),
+            "sign_mismatches": int(np.count_nonzero(np.signbit(sdf) != np.signbit(osdf))), "cg_iters": [int(rep.cg_iters), int(ref["cg_iters"])],
+            "cg_iters_equal": bool(rep.cg_iters == ref["cg_iters"]), "th_err_over_h": float(abs(rep.th - ref["th"]) / h),
+            "fine_err_over_h": float(np.max(np.abs(fine - ofine)) / h), "tolerances": {"dist": 1e-9, "sign": 0, "fine": 1e-3},
+            "checker": "oracle/r2s_oracle.c (CPU restatement), same seeded inputs"}
 
 
 def run_reference(args):
@@ -379,7 +418,9 @@ def run_gpu(args):
             line["per_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:
             step, nt, g = cpu_pipeline(args.cpu_n)
-            t, nv = step()
+            ref = {}
+            t, nv = step(ref)
+            line["parity"] = gpu_parity_on_replica(r2s, ref, local, None)
             line["cpu_baseline"] = {"value": nv / t, "unit": UNIT, "cores": nt, "kind": "port",
                                     "sample": "one pass of the timed region on the %d^3 replica of the workload (%d fine voxels) with the C/OpenMP oracle, %.1f s" % (args.cpu_n, nv, t)}
         print(json.dumps(line), flush=True)

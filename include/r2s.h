@@ -47,6 +47,7 @@ typedef struct r2s_report {
   int64_t launches;             /* kernels launched by the last call                                       */
   int64_t collectives;          /* NCCL collectives / grouped halo exchanges issued by the last call       */
   float cg_probe[4];            /* one CG iteration split: mat-vec, exchange 1 (dot + halo), update, exchange 2 (ms) */
+  int64_t n_pairs_pruned;       /* (element, point) pairs never projected: their lower bound was not below the point's minimum */
 } r2s_report;
 
 /* ---- context -------------------------------------------------------------------------------------------- */
@@ -124,6 +125,9 @@ int r2s_edge_length_stats(r2s_ctx *ctx, double *median, double *shortest, double
 /* number of HEX8 elements that are axis-aligned boxes in canonical node order (geometry statistic built by r2s_set_mesh; such
  * elements take the box variant of the projection kernel that stands for compute_coords_on_iso, ComputeCoordsOnIso.jl:16-87) */
 int r2s_mesh_box_elements(r2s_ctx *ctx, int64_t *n_box);
+/* 1 when the mesh is a tensor-product lattice of such boxes (any numbering, holes allowed): Sign_Detection_HEX8's candidate search
+ * (SignDetection.jl:27-36) then reads the <= 8 cells around a point from per-axis tables instead of sorted candidate lists */
+int r2s_mesh_is_lattice(r2s_ctx *ctx, int *is_lattice);
 
 /* ---- result export: exportSdfToVTI (src/DataExport/ExportToVTI.jl:22-67) ----------------------------------------------- */
 /* VTK ImageData (.vti), one PointData scalar `label` ("distance" in rho2sdf, RhoToSDF.jl:267-273), raw appended block.

@@ -54,7 +54,7 @@ class Report(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_solid", "n_crossing", "n_active", "n_pairs", "n_not_converged", "n_newton_iters", "n_flipped")] + \
                [("cg_iters", C.c_int32), ("bisections", C.c_int32), ("th", C.c_float), ("volume", C.c_float)] + \
                [(n, C.c_float) for n in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_rbf_prep", "ms_cg", "ms_lsf",
-                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64), ("collectives", C.c_int64), ("cg_probe", C.c_float * 4)]
+                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64), ("collectives", C.c_int64), ("cg_probe", C.c_float * 4), ("n_pairs_pruned", C.c_int64)]
 
     def asdict(self):
         return {n: (list(getattr(self, n)) if n == "cg_probe" else getattr(self, n)) for n, _ in self._fields_}
@@ -108,6 +108,7 @@ def load_library():
     L.r2s_comm_destroy.argtypes = [vp]
     L.r2s_edge_length_stats.argtypes = [vp, dp, dp, dp]
     L.r2s_mesh_box_elements.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.r2s_mesh_is_lattice.argtypes = [vp, C.POINTER(C.c_int)]
     L.r2s_export_vti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
     L.r2s_write_vti_host.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, vp]
     L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]
@@ -278,6 +279,13 @@ class Mesh:
         c.check(c.lib.r2s_mesh_volume(c.h, _ptr(self.rho), C.byref(vd), C.byref(vf)))
         self.V_domain, self.V_frac = vd.value, vf.value
         self._grid_id = None
+
+    @property
+    def is_lattice(self):
+        """True when the mesh is a tensor-product lattice of box elements (Sign_Detection then takes the list-free fast path)."""
+        f = C.c_int(0)
+        self.ctx.check(self.ctx.lib.r2s_mesh_is_lattice(self.ctx.h, C.byref(f)))
+        return bool(f.value)
 
     def _use_grid(self, grid):
         key = (tuple(grid.AABB_min), tuple(grid.AABB_max), tuple(int(v) for v in grid.N), grid.cell_size)

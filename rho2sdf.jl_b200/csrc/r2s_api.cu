@@ -1,5 +1,6 @@
 // r2s_api.cu -- the C ABI of libr2s.so (include/r2s.h): context, mesh/grid upload, per-stage entry points, pipeline
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "r2s_common.cuh"
@@ -24,6 +25,10 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 64; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+  if (cudaHostAlloc(&ctx->rb_host, R2S_RB_BYTES, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&ctx->rb_dev, ctx->rb_host, 0) != cudaSuccess) { r2s_destroy(ctx); return 6; }
+  auto knob = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+  ctx->knobs.p2p = knob("R2S_P2P", 1); ctx->knobs.sign_lattice = knob("R2S_SIGN_LATTICE", 1);
+  ctx->knobs.proj_box = knob("R2S_PROJ_BOX", 1); ctx->knobs.proj_prune = knob("R2S_PROJ_PRUNE", 1);
   *out = ctx;
   return 0;
 }
@@ -34,15 +39,16 @@ void r2s_destroy(r2s_ctx *ctx) {
   r2s_comm_destroy(ctx);
   DevBuf *all[] = {&ctx->X, &ctx->IEN32, &ctx->ine_ptr, &ctx->ine_el, &ctx->fbnd, &ctx->ezr, &ctx->ebox, &ctx->rho_e, &ctx->rho_n, &ctx->gtab_d, &ctx->gtab_i, &ctx->cls, &ctx->act_flag,
                    &ctx->act_idx, &ctx->act_rec, &ctx->cnt_a, &ctx->cnt_b, &ctx->keys, &ctx->keys_alt, &ctx->tile_ptr, &ctx->tile_faces, &ctx->tri_cnt, &ctx->tri_rec, &ctx->pairbuf, &ctx->pairxp, &ctx->cubtmp,
-                   &ctx->counters, &ctx->p1tab, &ctx->dist, &ctx->xp, &ctx->sdf, &ctx->signs, &ctx->s_rng, &ctx->s_el, &ctx->s_cnt, &ctx->s_keys, &ctx->s_keys_alt, &ctx->s_tile_ptr,
+                   &ctx->counters, &ctx->box_rec, &ctx->plist, &ctx->dist, &ctx->xp, &ctx->sdf, &ctx->signs, &ctx->s_rng, &ctx->s_el, &ctx->s_cnt, &ctx->s_keys, &ctx->s_keys_alt, &ctx->s_tile_ptr,
                    &ctx->cc_label, &ctx->cc_size, &ctx->cc_scal, &ctx->cc_bits, &ctx->cc_bits_all, &ctx->cc_gsz, &ctx->cc_seen, &ctx->f_s, &ctx->f_w, &ctx->f_r, &ctx->f_u, &ctx->f_c, &ctx->f_lsf, &ctx->f_fine, &ctx->f_part,
-                   &ctx->f_scal, &ctx->cutlist, &ctx->slablist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1]};
+                   &ctx->f_scal, &ctx->cutlist, &ctx->slablist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1], &ctx->lat_xs, &ctx->lat_cell, &ctx->lat_map, &ctx->lat_info, &ctx->lat_pt};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_probe[i]);
   for (int i = 0; i < 64; i++) cudaEventDestroy(ctx->ev_copy[i]);
   for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_done[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->rb_host) cudaFreeHost(ctx->rb_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -68,7 +74,8 @@ int r2s_set_mesh(r2s_ctx *ctx, int nen, int64_t nnp, const double *X, int64_t ne
   if (r2s_mesh_upload_ien(ctx, IEN)) return 1;
   CK(ctx->rho_e.reserve(sizeof(double) * (size_t)nel));
   CK(ctx->rho_n.reserve(sizeof(double) * (size_t)nnp));
-  return r2s_mesh_build_tables(ctx);
+  if (r2s_mesh_build_tables(ctx)) return 1;
+  return r2s_mesh_build_lattice(ctx);
 }
 
 int r2s_set_grid(r2s_ctx *ctx, const double amin[3], const double amax[3], const int64_t N[3], double cell) {

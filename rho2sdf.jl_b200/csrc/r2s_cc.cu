@@ -229,8 +229,7 @@ static int remove_artifacts_slabs(r2s_ctx *ctx, double thr, double ratio, i64 *f
   k_ccg_largest<<<cdiv(nb + nloc, 256), 256, 0, st>>>(nxy, R, nloc, v0, all, L, sz, gsz, seen, sc); LAUNCH_CHECK();
   if (r2s_allreduce(ctx, sc, 1, 4)) return 1;
   u64 best = 0;
-  CK(cudaMemcpyAsync(&best, sc, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &best, sc, sizeof(u64))) return 1;
   *flipped = 0;
   if (best == 0) return 0;
   i64 largest = (i64)(best >> 32); int lroot = (int)(0xffffffffu - (unsigned)(best & 0xffffffffu));
@@ -239,8 +238,7 @@ static int remove_artifacts_slabs(r2s_ctx *ctx, double thr, double ratio, i64 *f
   k_ccg_flip<<<nbl, 256, 0, st>>>(nloc, v0, L, sz, gsz, seen, lroot, (int)ms, sdf, sc + 1); LAUNCH_CHECK();
   if (r2s_allreduce(ctx, sc + 1, 1, 1)) return 1;
   u64 nf = 0;
-  CK(cudaMemcpyAsync(&nf, sc + 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &nf, sc + 1, sizeof(u64))) return 1;
   *flipped = (i64)nf;
   return 0;
 }
@@ -263,8 +261,7 @@ int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flippe
   k_cc_flatten<<<nb, 256, 0, st>>>(n, L, sz); LAUNCH_CHECK();
   k_cc_largest<<<nb, 256, 0, st>>>(n, L, sz, sc); LAUNCH_CHECK();
   u64 best = 0;
-  CK(cudaMemcpyAsync(&best, sc, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &best, sc, sizeof(u64))) return 1;
   *flipped = 0;
   if (best == 0) return 0;                                          // no interior nodes (:149-152)
   i64 largest = (i64)(best >> 32); int lroot = (int)(0xffffffffu - (unsigned)(best & 0xffffffffu));
@@ -273,8 +270,7 @@ int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flippe
   if (ms > 0x7fffffff) ms = 0x7fffffff;
   k_cc_flip<<<nb, 256, 0, st>>>(n, v0, L, sz, lroot, (int)ms, sdf, sc + 1); LAUNCH_CHECK();
   u64 nf = 0;
-  CK(cudaMemcpyAsync(&nf, sc + 1, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &nf, sc + 1, sizeof(u64))) return 1;
   *flipped = (i64)nf;
   return 0;
 }

@@ -208,8 +208,7 @@ static int p2p_open_all(r2s_ctx *ctx, void *local, void **peer_out /*[nranks]*/,
   CK(cudaMemcpyAsync((char *)tmp.p + sizeof(h) * ctx->rank, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
   NCK(g_nccl.AllGather((char *)tmp.p + sizeof(h) * ctx->rank, tmp.p, W, NC_UINT32, (nccl_comm)ctx->comm, ctx->stream));
   std::vector<cudaIpcMemHandle_t> all((size_t)R);
-  CK(cudaMemcpyAsync(all.data(), tmp.p, sizeof(h) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, all.data(), tmp.p, sizeof(h) * (size_t)R)) return 1;
   tmp.release();
   for (int i = 0; want[i] >= 0 && !bad; i++) {
     int r = want[i];
@@ -224,8 +223,7 @@ static int p2p_open_all(r2s_ctx *ctx, void *local, void **peer_out /*[nranks]*/,
 // called at the end of r2s_comm_init: returns 0 also when the fast path stays off (then ctx->p2p == false)
 static int p2p_setup(r2s_ctx *ctx) {
   ctx->p2p = false;
-  const char *env = getenv("R2S_P2P");
-  if (env && atoi(env) == 0) return 0;
+  if (!ctx->knobs.p2p) return 0;      // R2S_P2P=0: NCCL only
   if (ctx->nranks < 2 || ctx->nranks > 64) return 0;
   // every rank must be able to reach every peer; all ranks take the same decision through a NCCL max-reduce of "cannot"
   int ndev = 0; cudaGetDeviceCount(&ndev);
@@ -239,8 +237,7 @@ static int p2p_setup(r2s_ctx *ctx) {
   unsigned *flag = (unsigned *)((char *)ctx->p2p_box + sizeof(P2PBox) + 32), hflag = rc ? 1u : 0u;
   CK(cudaMemcpyAsync(flag, &hflag, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
   NCK(g_nccl.AllReduce(flag, flag, 1, NC_UINT32, NC_MAX, (nccl_comm)ctx->comm, ctx->stream));
-  CK(cudaMemcpyAsync(&hflag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, &hflag, flag, sizeof(unsigned))) return 1;
   if (hflag) { ctx->err = saved; return 0; }      // some rank could not map its peers: everybody stays on NCCL
   CK(cudaMalloc((void **)&ctx->p2p_peer_box_dev, sizeof(void *) * 64));
   CK(cudaMemcpyAsync(ctx->p2p_peer_box_dev, ctx->p2p_peer_box, sizeof(void *) * (size_t)ctx->nranks, cudaMemcpyHostToDevice, ctx->stream));
@@ -265,8 +262,7 @@ int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
   unsigned long long changed = (ctx->p2p_c_local != (void *)c) ? 1ull : 0ull;
   CK(cudaMemcpyAsync(w, &changed, sizeof(changed), cudaMemcpyHostToDevice, ctx->stream));
   if (p2p_allreduce(ctx, w, 1, 4)) return 1;
-  CK(cudaMemcpyAsync(&changed, w, sizeof(changed), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, &changed, w, sizeof(changed))) return 1;
   if (!changed) return 0;
   for (int s = 0; s < 2; s++) if (ctx->p2p_c_peer[s]) { cudaIpcCloseMemHandle(ctx->p2p_c_peer[s]); ctx->p2p_c_peer[s] = nullptr; }
   void *peers[64]; memset(peers, 0, sizeof(peers));
@@ -336,8 +332,7 @@ int r2s_p2p_halo_wait(r2s_ctx *ctx) {
 int r2s_p2p_check(r2s_ctx *ctx) {
   if (!ctx->p2p) return 0;
   unsigned long long e = 0;
-  CK(cudaMemcpyAsync(&e, &((P2PBox *)ctx->p2p_box)->error, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, &e, &((P2PBox *)ctx->p2p_box)->error, sizeof(e))) return 1;
   if (e) FAIL("peer-memory exchange timed out (a rank did not arrive); set R2S_P2P=0 to use NCCL only");
   return 0;
 }

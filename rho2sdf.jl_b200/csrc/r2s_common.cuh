@@ -60,8 +60,20 @@ struct GridDev {
   int pc_off[3], cs_off[3];
 };
 
+// tuning / A-B knobs, read from the environment ONCE by r2s_create (every one of them is exercised by a GPU test)
+struct Knobs {
+  int p2p = 1;            // R2S_P2P=0: NCCL only, no peer-memory mailbox (tests/slab_parity_ranks.py)
+  int sign_lattice = 1;   // R2S_SIGN_LATTICE=0: tensor-product lattice meshes take the general (sorted candidate list) sign kernel
+  int proj_box = 1;       // R2S_PROJ_BOX=0: axis-aligned box elements take the general trilinear projection
+  int proj_prune = 1;     // R2S_PROJ_PRUNE=0: the box projection evaluates every (element, point) pair (no lower-bound pruning)
+};
+
 struct r2s_ctx {
   int device = 0;
+  Knobs knobs;
+  // small device -> host read-backs go through a MAPPED pinned buffer written by a tiny kernel (no DMA engine involved, so they never
+  // queue behind the multi-GB result downloads of the copy stream); r2s_util.cu
+  void *rb_host = nullptr, *rb_dev = nullptr; size_t rb_off = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -79,6 +91,10 @@ struct r2s_ctx {
   i64 nnp = 0, nel = 0;
   DevBuf X, IEN32, ine_ptr, ine_el, fbnd, ezr;   // X double[3*nnp]; IEN32 int[nen*nel] 0-based; INE CSR; fbnd uint8[nel]
   DevBuf ebox; i64 n_box = 0;                    // HEX8: uint8[nel] 1 = axis-aligned box in canonical node order (iso::HexBox), and their count
+  // tensor-product lattice meshes (every element a box whose corners are neighbouring values of three per-axis coordinate tables):
+  // lat_xs = the tables (concatenated, offsets lat_off), lat_cell[e] = lattice cell of element e, lat_map[cell] = element or -1
+  bool lattice = false; int lat_nd[3] = {0, 0, 0}, lat_off[3] = {0, 0, 0}; i64 lat_ncell = 0;
+  DevBuf lat_xs, lat_cell, lat_map, lat_info, lat_pt;
   DevBuf rho_e, rho_n;
 
   // grid
@@ -94,9 +110,8 @@ struct r2s_ctx {
   std::vector<double> h_pc[3];
 
   // distance / sign work buffers
-  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters, p1tab;
+  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters, box_rec, plist;
   DevBuf dist, xp, sdf, signs;
-  std::vector<u64> h_counters;             // host copy of the statistics slots
   DevBuf s_rng, s_el, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
   // connected components
   DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all, cc_gsz, cc_seen;
@@ -148,6 +163,15 @@ int r2s_scan_exclusive_i64(r2s_ctx *ctx, const i64 *in, i64 *out, i64 n);  // r2
 int r2s_scan_exclusive_i32(r2s_ctx *ctx, const int *in, int *out, i64 n);
 int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64 **sorted);
 int r2s_sort_f64(r2s_ctx *ctx, double *keys, double *alt, i64 n, double **sorted);
+int r2s_unique_f64(r2s_ctx *ctx, const double *sorted, double *out, i64 n, i64 *count);      // distinct values of a sorted array
+// read-backs through the mapped buffer: rb_put enqueues a copy of `bytes` at src_dev and returns its offset (or (size_t)-1), rb_sync
+// waits for the stream; rb_at(off) is then valid until the next rb_put after a sync.  r2s_readback = put + sync + memcpy.
+#define R2S_RB_BYTES (192 * 1024)
+size_t r2s_rb_put(r2s_ctx *ctx, const void *src_dev, size_t bytes);
+int r2s_rb_sync(r2s_ctx *ctx);
+static inline const void *r2s_rb_at(r2s_ctx *ctx, size_t off) { return (const char *)ctx->rb_host + off; }
+int r2s_readback(r2s_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int r2s_mesh_build_lattice(r2s_ctx *ctx);                                  // r2s_mesh.cu: tensor-product lattice detection + tables
 // r2s_comm.cu: collectives over the slab communicator (no-ops for a single rank)
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes);                                     // (re)map the neighbours' CG vector c

@@ -89,44 +89,31 @@ __global__ void k_emit_keys(i64 nact, ActRec *__restrict__ rec, const i64 *__res
 }
 
 // ------------------------------------------------------------------------------------------------ project (hot, FP64)
-// Phase 1 of the iso-surface projection once per crossing element: xi0 = Newton projection of xi = 0 onto {rho = rho_t} inside the
-// element (it involves the density field only, so one table serves both element kinds); w = 1 when it converged, else the points of
-// the element take the edge fallback of proj_init.  Same arithmetic as the per-lane phase 1 (iso::proj_init_element).
-template <int MODE>
-__global__ void k_phase1(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ rn, double rho_t, double4 *__restrict__ p1) {
-  const i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (a >= nact) return;
-  const ActRec r = rec[a];
-  if (r.cls != 2) { p1[a] = make_double4(0.0, 0.0, 0.0, 0.0); return; }
-  double re[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) re[k] = rn[IEN[8 * (i64)r.el + k]];
-  iso::HexBox B;
-  iso::monomial8(re, B.R);
-#pragma unroll
-  for (int d = 0; d < 3; d++) { B.c[d] = 0.0; B.h[d] = 1.0; B.hh[d] = 2.0; }
-  double gs = fabs(rho_t);
-#pragma unroll
-  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
-  gs = fmax(gs, 1.0);
-  iso::ProjState S;
-  const bool ok = iso::proj_init_element<iso::HexBox, MODE>(B, rho_t, gs, S);
-  p1[a] = make_double4(S.xi[0], S.xi[1], S.xi[2], ok ? 1.0 : 0.0);
+// Solver variant of every HEX8 kernel (r2s_iso.cuh): FAST restoration (no confirming evaluation) + ONE code path for all tangent-step
+// cases; phase 1 (Newton projection of xi = 0 onto the iso-surface, the same for every point of an element) is computed once per
+// warp / per element.  The kernels work in element-local coordinates (node 0 subtracted from the nodes and from the grid point: exact
+// in floating point), so X(xi) - x does not cancel the mesh offset.
+#define PMODE 3
+__global__ void k_fill_f64(i64 n, double *__restrict__ a, double v) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
 }
-// one warp per 32-point chunk of a crossing element.  BOX: the variant for axis-aligned box elements (iso::HexBox: 17 element
-// constants instead of 32, about half the FP64 work per iteration); kind_check != 0: the mesh holds both kinds of elements and
-// each of the two launches leaves the chunks of the other kind alone (ebox[e] = 1 for boxes, built with the mesh).
-// MODE: solver variant (r2s_iso.cuh) -- bit 0 FAST restoration (no confirming evaluation, same results), bit 1 one code path for all
-// tangent-step cases (results equal to rounding), bit 2 scaled box form (HexBox only), bit 3 the distance of a point in a tile without
-// boundary-face elements goes straight into dist[] by a 64-bit atomicMin (the minimum over the pairs is order independent there; the
-// pair buffer and the replay of k_assemble are then needed for the tiles with boundary faces only -- as in the lane-refill kernel).
-// P1: phase 1 of the solver (Newton projection of xi = 0 onto the iso-surface, the same for every point of an element)
-// comes from the per-element table built by k_phase1 instead of being recomputed by every lane of every chunk.
-template <bool WANT_XP, int MINB, bool SMEM_A, bool BOX, int MODE, bool P1>
-__global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
+__device__ __forceinline__ void proj_stats(u64 *counters, int its, bool bad, int lane) {      // one atomic per warp, spread over 128 slots
+  for (int o = 16; o > 0; o >>= 1) its += __shfl_down_sync(0xffffffffu, its, o);
+  const unsigned mb = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 127)); atomicAdd(&cs[2], (u64)its); if (mb) atomicAdd(&cs[3], (u64)__popc(mb)); }
+}
+// Chunk kernel: one warp per 32-point chunk of a crossing element (general trilinear elements, and every element when the closest
+// points xp are wanted).  BOX: the element is an axis-aligned box (iso::HexBox: 17 element constants instead of 32, about half the FP64
+// work per iteration); kind_check: the mesh holds both kinds and this launch leaves the chunks of the other kind alone (ebox[e] = 1 for
+// boxes).  Without xp the distance of a point in a tile WITHOUT boundary-face elements goes straight into dist[] by a 64-bit atomicMin
+// on the bit pattern of the non-negative double (the minimum over the pairs is order independent there); pairs of the other tiles go to
+// the pair buffer for the exact replay of k_assemble.
+template <bool WANT_XP, bool BOX>
+__global__ void __launch_bounds__(128, WANT_XP ? (BOX ? 4 : 2) : 4) k_project_hex8(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
                                                       const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g,
                                                       double rho_t, double *__restrict__ pairbuf, double *__restrict__ pairxp, u64 *__restrict__ counters,
-                                                      const unsigned char *__restrict__ ebox, int kind_check, const double4 *__restrict__ p1,
+                                                      const unsigned char *__restrict__ ebox, int kind_check, int skip_box,
                                                       const unsigned char *__restrict__ tile_faces, double *__restrict__ dist) {
   i64 item = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
   if (item >= nitems) return;
@@ -135,120 +122,15 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8(i64 nitems, i64 nact
   while (lo < hi) { i64 mid = (lo + hi + 1) >> 1; if (choff[mid] <= item) lo = mid; else hi = mid - 1; }
   const ActRec r = rec[lo];
   if (kind_check && (ebox[r.el] != 0) != BOX) return;
+  if (skip_box && ebox[r.el] != 0) return;      // box elements are handled by the pair-list path
   int chunk = (int)(item - choff[lo]);
   // element data: lane l < 8 loads node l; monomial coefficients assembled through shuffles
   double v[4] = {0, 0, 0, 0};
   if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
-  // MODE bit 1 (the variants that are equal to the default only up to rounding anyway): element-local coordinates -- node 0 is subtracted
-  // from the nodes and from the grid point (exact in floating point for any reasonable mesh), so X(xi) - x no longer cancels the mesh
-  // offset (tests/test_iso_host.py::test_coordinate_offset_sensitivity)
-  double org[3] = {0, 0, 0};
-  if constexpr ((MODE & 2) != 0 && !WANT_XP) {
+  double org[3];
 #pragma unroll
-    for (int d = 0; d < 3; d++) { org[d] = __shfl_sync(0xffffffffu, v[d], 0); v[d] -= org[d]; }
-  }
-  // SMEM_A: the warp-uniform monomial coefficients live in shared memory (broadcast reads) instead of 64 registers per thread
-  __shared__ double sA[SMEM_A ? 4 : 1][4][8];
-  double Ar[SMEM_A ? 1 : 4][8], re[8];
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    double nv[8], Ac[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) nv[k] = __shfl_sync(0xffffffffu, v[c], k);
-    iso::monomial8(nv, Ac);
-    if (SMEM_A) { if (lane < 8) sA[threadIdx.x >> 5][c][lane] = Ac[lane & 7]; }
-    else {
-#pragma unroll
-      for (int k = 0; k < 8; k++) Ar[SMEM_A ? 0 : c][k] = Ac[k];
-    }
-    if (c == 3) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) re[k] = nv[k];
-    }
-  }
-  if (SMEM_A) __syncwarp();
-  const double (*A)[8] = SMEM_A ? (const double (*)[8])sA[threadIdx.x >> 5] : (const double (*)[8])Ar;
-  double gs = fabs(rho_t);
-#pragma unroll
-  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
-  gs = fmax(gs, 1.0);
-  int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
-  i64 vol = (i64)nx * ny * nz, li = (i64)chunk * 32 + lane;
-  int nit = 0; bool okc = true;
-  if (li < vol) {
-    int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
-    double x[3] = {g.pc[g.pc_off[0] + r.ps[0] + i], g.pc[g.pc_off[1] + r.ps[1] + j], g.pc[g.pc_off[2] + r.ps[2] + k]};
-    if constexpr ((MODE & 2) != 0 && !WANT_XP) { x[0] -= org[0]; x[1] -= org[1]; x[2] -= org[2]; }
-    double xi[3], p[3] = {0, 0, 0};
-    double xi0[3] = {0, 0, 0}; bool ok0 = false;
-    if (P1) { const double4 q = p1[lo]; xi0[0] = q.x; xi0[1] = q.y; xi0[2] = q.z; ok0 = q.w != 0.0; }
-    if constexpr (BOX && (MODE & 4) != 0) {      // scaled box form (no closest point: the driver never combines it with WANT_XP)
-      iso::HexBoxS B; iso::make_box_scaled(A, x, B);
-      if (P1) okc = iso::project_hex8_from<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
-      else okc = iso::project_hex8<iso::HexBoxS, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
-      const double dd = sqrt(iso::eval_f(B, x, xi));
-      bool direct = false;
-      if constexpr ((MODE & 8) != 0) {
-        const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
-        direct = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] == 0;
-        if (direct) atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
-      }
-      if (!direct) pairbuf[r.pair_off + li] = dd;
-    } else {
-    if (BOX) {
-      iso::HexBox B; iso::make_box(A, B);
-      if (P1) okc = iso::project_hex8_from<iso::HexBox, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
-      else okc = iso::project_hex8<iso::HexBox, MODE>(B, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
-      iso::eval_pos(B, xi, p);
-    } else {
-      const iso::HexTri T{A};
-      if (P1) okc = iso::project_hex8_from<iso::HexTri, MODE>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi0, ok0, xi, nit);
-      else okc = iso::project_hex8<iso::HexTri, MODE>(T, re, c_hex_sg, c_hex_edges, x, rho_t, gs, xi, nit);
-      iso::eval_pos(T, xi, p);
-    }
-    double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
-    const double dd = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
-    bool direct = false;
-    if constexpr ((MODE & 8) != 0 && !WANT_XP) {
-      const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
-      direct = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] == 0;
-      if (direct) atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
-    }
-    if (!direct) pairbuf[r.pair_off + li] = dd;
-    if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2]; }
-    }
-  }
-  // statistics: iterations and failures (one atomic per warp)
-  int its = nit > 0 ? nit : 0;
-  for (int o = 16; o > 0; o >>= 1) its += __shfl_down_sync(0xffffffffu, its, o);
-  unsigned bad = __ballot_sync(0xffffffffu, !okc);
-  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 1023)); atomicAdd(&cs[2], (u64)its); if (bad) atomicAdd(&cs[3], (u64)__popc(bad)); }      // statistics spread over 1024 slots
-}
-// Lane-refill variant (used when the closest points xp are not requested): ONE WARP PER CROSSING ELEMENT.  The warp keeps
-// the element's monomial coefficients in registers and its lanes work through the element's candidate points independently:
-// a lane that finishes its point immediately takes the next one, so the lanes of a warp sit at different iterations of
-// different points and nobody waits for the slowest projection of a 32-point chunk.  Points inside the element's AABB are
-// taken first; for the others the distance to the AABB is a lower bound of the result, and a pair whose bound already
-// exceeds the voxel's current minimum cannot lower it and is skipped (exact: the result of evalDistances is the minimum over
-// the pairs).  The running minimum per voxel is a 64-bit atomicMin on the bit pattern of the non-negative double.  Voxels of
-// tiles that hold boundary-face elements keep the pair-buffer path (their replay is order dependent, see k_assemble).
-__global__ void k_fill_f64(i64 n, double *__restrict__ a, double v) {
-  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (i < n) a[i] = v;
-}
-template <int MINB, bool BOX, int MODE>
-__global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X,
-                                                          const double *__restrict__ rn, GridDev g, double rho_t, const unsigned char *__restrict__ tile_faces,
-                                                          double *__restrict__ pairbuf, double *__restrict__ dist, u64 *__restrict__ counters,
-                                                          const unsigned char *__restrict__ ebox, int kind_check) {
-  const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
-  if (a >= nact) return;
-  const ActRec r = rec[a];
-  if (r.cls != 2) return;
-  if (kind_check && (ebox[r.el] != 0) != BOX) return;
-  double v[4] = {0, 0, 0, 0};
-  if (lane < 8) { i64 n = IEN[8 * (i64)r.el + lane]; v[0] = X[3 * n]; v[1] = X[3 * n + 1]; v[2] = X[3 * n + 2]; v[3] = rn[n]; }
-  double A[4][8], re[8], lo[3], hi[3];
+  for (int d = 0; d < 3; d++) { org[d] = __shfl_sync(0xffffffffu, v[d], 0); v[d] -= org[d]; }
+  double A[4][8], re[8];
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     double nv[8];
@@ -258,71 +140,224 @@ __global__ void __launch_bounds__(128, MINB) k_project_hex8_min(i64 nact, const 
     if (c == 3) {
 #pragma unroll
       for (int k = 0; k < 8; k++) re[k] = nv[k];
-    } else {
-      double l = nv[0], h = nv[0];
-#pragma unroll
-      for (int k = 1; k < 8; k++) { l = fmin(l, nv[k]); h = fmax(h, nv[k]); }
-      lo[c] = l; hi[c] = h;
     }
   }
   double gs = fabs(rho_t);
 #pragma unroll
   for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(re[k]));
   gs = fmax(gs, 1.0);
-  const double margin0 = 1e-12 * fmax(fmax(fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1]))), fmax(fabs(lo[2]), fabs(hi[2])));
-  const int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
-  const int vol = nx * ny * nz;
-  // element in the solver's form: box elements keep 17 constants, the 32 monomial coefficients are dead after this point
+  int nx = r.pe[0] - r.ps[0], ny = r.pe[1] - r.ps[1], nz = r.pe[2] - r.ps[2];
+  i64 vol = (i64)nx * ny * nz, li = (i64)chunk * 32 + lane;
+  int nit = 0; bool okc = true;
   typedef typename std::conditional<BOX, iso::HexBox, iso::HexTri>::type ElemT;
   ElemT EL;
   if constexpr (BOX) iso::make_box(A, EL); else EL.A = A;
-  // phase 1 once per element (it does not depend on the grid point)
-  iso::ProjState S0; const bool ok0 = iso::proj_init_element<ElemT, MODE>(EL, rho_t, gs, S0);
-  bool busy = false, to_buf = false; iso::ProjState S = S0; double x[3] = {0, 0, 0}; int li = 0; i64 vox = 0;
-  int sweep = 0, next = 0, its = 0, nbad = 0, npruned = 0;
-  while (true) {
-    // ---- refill idle lanes with the next candidate points of the current sweep (sweep 0: points inside the AABB, 1: the rest)
-    while (sweep < 2) {
-      const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-      if (!idle) break;
-      const int cand = next + __popc(idle & ((1u << lane) - 1));
-      if (!busy && cand < vol) {
-        const int i = cand % nx, j = (cand / nx) % ny, k = cand / (nx * ny);
-        const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
-        const double x0 = g.pc[g.pc_off[0] + pi0], x1 = g.pc[g.pc_off[1] + pi1], x2 = g.pc[g.pc_off[2] + pi2];
-        const double d0 = fmax(fmax(lo[0] - x0, x0 - hi[0]), 0.0), d1 = fmax(fmax(lo[1] - x1, x1 - hi[1]), 0.0), d2 = fmax(fmax(lo[2] - x2, x2 - hi[2]), 0.0);
-        const double lb2 = fma(d2, d2, fma(d1, d1, d0 * d0));
-        if ((sweep == 0) == (lb2 == 0.0)) {
-          const i64 vx = ((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0;
-          const i64 t = ((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X;
-          const bool tb = tile_faces[t] != 0;
-          bool prune = false;
-          if (!tb && sweep == 1) { const double cur = dist[vx] * (1.0 + 1e-12) + margin0; prune = lb2 > cur * cur; }      // lower bound already above the voxel's minimum
-          if (prune) npruned++;
-          else {
-            li = cand; busy = true; vox = vx; to_buf = tb; x[0] = x0; x[1] = x1; x[2] = x2; S = S0;
-            if (!ok0 && !iso::proj_init<ElemT, MODE>(EL, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S)) { S.f = iso::eval_f(EL, x, S.xi); S.it = 1000; }   // no iso point: xi = 0 is used
-          }
-        }
-      }
-      next += __popc(idle);
-      if (next >= vol) { sweep++; next = 0; }
+  iso::ProjState S0; const bool ok0 = iso::proj_init_element<ElemT, PMODE>(EL, rho_t, gs, S0);      // warp-uniform
+  if (li < vol) {
+    int i = (int)(li % nx), j = (int)((li / nx) % ny), k = (int)(li / ((i64)nx * ny));
+    const int pi0 = r.ps[0] + i, pi1 = r.ps[1] + j, pi2 = r.ps[2] + k;
+    const double x[3] = {g.pc[g.pc_off[0] + pi0] - org[0], g.pc[g.pc_off[1] + pi1] - org[1], g.pc[g.pc_off[2] + pi2] - org[2]};
+    double xi[3], p[3];
+    okc = iso::project_hex8_from<ElemT, PMODE>(EL, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S0.xi, ok0, xi, nit);
+    iso::eval_pos(EL, xi, p);
+    double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
+    const double dd = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+    bool direct = false;
+    if constexpr (!WANT_XP) {
+      direct = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] == 0;
+      if (direct) atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
     }
-    if (!__any_sync(0xffffffffu, busy)) break;
-    if (busy) {
-      int status = 2;
-      if (S.it < 100) status = iso::proj_iter<ElemT, MODE>(EL, x, rho_t, gs, S);
-      if (status != 0 || S.it >= 100) {
-        if (S.it >= 1000) nbad++; else { its += S.it; if (status != 1) nbad++; }
-        const double dd = sqrt(S.f);
-        if (to_buf) pairbuf[r.pair_off + li] = dd;
-        else atomicMin((u64 *)&dist[vox], (u64)__double_as_longlong(dd));
-        busy = false;
+    if (!direct) pairbuf[r.pair_off + li] = dd;
+    if (WANT_XP) { pairxp[3 * (r.pair_off + li)] = p[0] + org[0]; pairxp[3 * (r.pair_off + li) + 1] = p[1] + org[1]; pairxp[3 * (r.pair_off + li) + 2] = p[2] + org[2]; }
+  }
+  proj_stats(counters, nit > 0 ? nit : 0, !okc, lane);
+}
+
+// ---- pair-list path for box elements (the headline workload: every voxel-type SIMP mesh) ----------------------------------------
+// evalDistances keeps, per grid point, the MINIMUM over the crossing elements whose candidate range holds the point
+// (sdfOnDensityField.jl:606-621).  A pair whose lower bound -- the distance from the point to a box that contains the element's
+// iso-patch -- is not below the point's current minimum cannot change the result, so it is never projected (exact: the result is a
+// minimum).  Organisation:
+//   k_box_records  per crossing box element: solver constants (iso::HexBox in element-local coordinates), phase 1, and the TIGHT box
+//                  of its iso-patch: per axis the hull of the slices xi_d = s whose four corner densities straddle rho_t (a bilinear
+//                  field takes its extrema over a slice at the corners; the candidates for the hull's ends are s = +-1 and the iso
+//                  crossings of the four edges along d)
+//   k_pair_scan<0> pass A: pairs whose point lies inside the element's closed AABB (bound 0, always needed) and every pair of a tile
+//                  with boundary-face elements (those go to the pair buffer un-pruned: k_assemble replays them in element order)
+//   k_pair_scan<1> pass B, after pass A has been projected: the other pairs, kept only if their bound is below dist[] so far
+//   k_project_list one LANE per listed pair (dense warps whatever was pruned), result by atomicMin / into the pair buffer.
+struct BoxRec {
+  double R[8];               // monomial coefficients of rho
+  double c[3], h[3];         // X_d = c_d + h_d xi_d in element-local coordinates (node 0 at the origin)
+  double org[3];             // node 0
+  double xi0[3];             // phase 1: Newton projection of xi = 0 onto the iso-surface
+  double gs;                 // scale of the tolerances
+  double tlo[3], thi[3];     // tight box of the iso-patch, GLOBAL coordinates (slightly widened)
+  i64 pair_off;
+  int ps[3], nx, ny, vol, ok0, el;
+};
+__global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn,
+                              const unsigned char *__restrict__ ebox, double rho_t, BoxRec *__restrict__ box) {
+  const i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const ActRec r = rec[a];
+  BoxRec B; B.el = r.el; B.pair_off = r.pair_off; B.vol = 0; B.ok0 = 0;
+  if (r.cls != 2 || !ebox[r.el]) { box[a].vol = 0; return; }
+  double nv[4][8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { const i64 n = IEN[8 * (i64)r.el + k]; nv[0][k] = X[3 * n]; nv[1][k] = X[3 * n + 1]; nv[2][k] = X[3 * n + 2]; nv[3][k] = rn[n]; }
+  double A[4][8];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    B.org[d] = nv[d][0];
+#pragma unroll
+    for (int k = 0; k < 8; k++) nv[d][k] -= B.org[d];
+    iso::monomial8(nv[d], A[d]);
+  }
+  iso::monomial8(nv[3], A[3]);
+  iso::HexBox H; iso::make_box(A, H);
+#pragma unroll
+  for (int k = 0; k < 8; k++) B.R[k] = H.R[k];
+  double gs = fabs(rho_t);
+#pragma unroll
+  for (int k = 0; k < 8; k++) gs = fmax(gs, fabs(nv[3][k]));
+  B.gs = fmax(gs, 1.0);
+  iso::ProjState S0; B.ok0 = iso::proj_init_element<iso::HexBox, PMODE>(H, rho_t, B.gs, S0) ? 1 : 0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { B.c[d] = H.c[d]; B.h[d] = H.h[d]; B.xi0[d] = S0.xi[d]; B.ps[d] = r.ps[d]; }
+  B.nx = r.pe[0] - r.ps[0]; B.ny = r.pe[1] - r.ps[1]; B.vol = B.nx * B.ny * (r.pe[2] - r.ps[2]);
+  // tight box per axis: corner pairs (lo end, hi end) of the four edges along the axis, node order of hex8_shape.jl:27-34
+  const int ea[3][4] = {{0, 3, 4, 7}, {0, 1, 4, 5}, {0, 1, 2, 3}}, eb[3][4] = {{1, 2, 5, 6}, {3, 2, 7, 6}, {4, 5, 6, 7}};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double va[4], vb[4], cand[6]; int nc = 0;
+    cand[nc++] = -1.0; cand[nc++] = 1.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      va[q] = nv[3][ea[d][q]] - rho_t; vb[q] = nv[3][eb[d][q]] - rho_t;
+      if ((va[q] < 0.0) != (vb[q] < 0.0) && va[q] != vb[q]) cand[nc++] = fmin(1.0, fmax(-1.0, -1.0 + 2.0 * va[q] / (va[q] - vb[q])));
+    }
+    double smin = 1.0, smax = -1.0; bool any = false;
+    for (int t = 0; t < nc; t++) {
+      const double s = cand[t], w = 0.5 * (s + 1.0);
+      double mn = 1e300, mx = -1e300;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double val = va[q] + (vb[q] - va[q]) * w; mn = fmin(mn, val); mx = fmax(mx, val); }
+      const double tol = 1e-12 * B.gs;
+      if (mn <= tol && mx >= -tol) { smin = fmin(smin, s); smax = fmax(smax, s); any = true; }
+    }
+    if (!any) { smin = -1.0; smax = 1.0; }      // cannot happen for a crossing element; stay safe
+    const double pad = 1e-9;                    // widen in xi: the bound only has to be a lower bound
+    smin = fmax(-1.0, smin - pad); smax = fmin(1.0, smax + pad);
+    const double x0 = H.c[d] + H.h[d] * smin + B.org[d], x1 = H.c[d] + H.h[d] * smax + B.org[d];
+    const double wid = 4e-16 * (fabs(B.org[d]) + fabs(H.c[d]) + fabs(H.h[d]));
+    B.tlo[d] = fmin(x0, x1) - wid; B.thi[d] = fmax(x0, x1) + wid;
+  }
+  box[a] = B;
+}
+// one warp per active element; lanes stride over its candidate points.  plist entry: bit 63 = goes to the pair buffer, bits 24..62 =
+// active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
+#define PL_LI_BITS 24
+template <int PASS>
+__global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
+                                                   int prune, u64 *__restrict__ plist, u64 *__restrict__ cnt) {
+  const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+  if (a >= nact) return;
+  const int vol = box[a].vol;
+  if (vol == 0) return;
+  const BoxRec &B = box[a];
+  const int nx = B.nx, ny = B.ny, ps0 = B.ps[0], ps1 = B.ps[1], ps2 = B.ps[2];
+  // closed AABB of the element in global coordinates (exact: these are node coordinates)
+  double elo[3], ehi[3], tlo[3], thi[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double c0 = (B.c[d] - B.h[d]) + B.org[d], c1 = (B.c[d] + B.h[d]) + B.org[d];
+    elo[d] = fmin(c0, c1); ehi[d] = fmax(c0, c1); tlo[d] = B.tlo[d]; thi[d] = B.thi[d];
+  }
+  int npruned = 0;
+  for (int base = 0; base < vol; base += 32) {
+    const int li = base + lane; bool keep = false, to_buf = false;
+    if (li < vol) {
+      const int i = li % nx, j = (li / nx) % ny, k = li / (nx * ny);
+      const int pi0 = ps0 + i, pi1 = ps1 + j, pi2 = ps2 + k;
+      const double x0 = g.pc[g.pc_off[0] + pi0], x1 = g.pc[g.pc_off[1] + pi1], x2 = g.pc[g.pc_off[2] + pi2];
+      to_buf = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] != 0;
+      // "inside" with a relative slack: which pass a pair belongs to is free to choose, the slack only keeps round-off of the
+      // reconstructed corners from moving on-boundary points to pass B
+      const double sl = 1e-9 * (ehi[0] - elo[0] + ehi[1] - elo[1] + ehi[2] - elo[2]);
+      const bool inner = x0 >= elo[0] - sl && x0 <= ehi[0] + sl && x1 >= elo[1] - sl && x1 <= ehi[1] + sl && x2 >= elo[2] - sl && x2 <= ehi[2] + sl;
+      if (PASS == 0) keep = to_buf || inner || !prune;
+      else if (!to_buf && !inner) {
+        const double e0 = fmax(fmax(tlo[0] - x0, x0 - thi[0]), 0.0), e1 = fmax(fmax(tlo[1] - x1, x1 - thi[1]), 0.0), e2 = fmax(fmax(tlo[2] - x2, x2 - thi[2]), 0.0);
+        const double lb2 = fma(e2, e2, fma(e1, e1, e0 * e0));
+        const double cur = dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0];
+        keep = !(lb2 > cur * cur * (1.0 + 1e-10));
+        if (!keep) npruned++;
       }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      u64 pos = 0;
+      if (lane == 0) pos = atomicAdd(&cnt[0], (u64)__popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (keep) plist[pos + __popc(m & ((1u << lane) - 1))] = ((u64)(to_buf ? 1 : 0) << 63) | ((u64)a << PL_LI_BITS) | (u64)li;
     }
   }
-  for (int o = 16; o > 0; o >>= 1) { its += __shfl_down_sync(0xffffffffu, its, o); nbad += __shfl_down_sync(0xffffffffu, nbad, o); npruned += __shfl_down_sync(0xffffffffu, npruned, o); }
-  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 1023)); atomicAdd(&cs[2], (u64)its); if (nbad) atomicAdd(&cs[3], (u64)nbad); if (npruned) atomicAdd(&cs[4], (u64)npruned); }
+  if (PASS == 1) {
+    for (int o = 16; o > 0; o >>= 1) npruned += __shfl_down_sync(0xffffffffu, npruned, o);
+    if (lane == 0 && npruned) atomicAdd(&cnt[1], (u64)npruned);
+  }
+}
+// grid-stride over the list: consecutive lanes take consecutive entries (mostly the same element: broadcast loads of its record)
+__global__ void __launch_bounds__(128, 5) k_project_list(const u64 *__restrict__ plist, const u64 *__restrict__ cnt, const BoxRec *__restrict__ box, const int *__restrict__ IEN,
+                                                         const double *__restrict__ rn, GridDev g, double rho_t, double *__restrict__ pairbuf, double *__restrict__ dist,
+                                                         u64 *__restrict__ counters) {
+  const u64 n = cnt[0];
+  const int lane = threadIdx.x & 31;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  int its = 0, nbad = 0;
+  for (u64 base = (u64)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {      // warp-uniform trip count
+    const u64 it = base + lane;
+    if (it < n) {
+      const u64 ent = plist[it];
+      const bool to_buf = (ent >> 63) != 0; const i64 a = (i64)((ent & 0x7fffffffffffffffull) >> PL_LI_BITS); const int li = (int)(ent & ((1u << PL_LI_BITS) - 1));
+      const BoxRec &B = box[a];
+      iso::HexBox H;
+#pragma unroll
+      for (int k = 0; k < 8; k++) H.R[k] = B.R[k];
+#pragma unroll
+      for (int d = 0; d < 3; d++) { H.c[d] = B.c[d]; H.h[d] = B.h[d]; H.hh[d] = 2.0 * (H.h[d] * H.h[d]); }
+      const int nx = B.nx, ny = B.ny;
+      const int i = li % nx, j = (li / nx) % ny, k = li / (nx * ny);
+      const int pi0 = B.ps[0] + i, pi1 = B.ps[1] + j, pi2 = B.ps[2] + k;
+      const double x[3] = {g.pc[g.pc_off[0] + pi0] - B.org[0], g.pc[g.pc_off[1] + pi1] - B.org[1], g.pc[g.pc_off[2] + pi2] - B.org[2]};
+      const double gs = B.gs; const bool ok0 = B.ok0 != 0;
+      double xi0[3] = {B.xi0[0], B.xi0[1], B.xi0[2]}, xi[3], p[3]; int nit = 0;
+      iso::ProjState S;
+      S.xi[0] = xi0[0]; S.xi[1] = xi0[1]; S.xi[2] = xi0[2]; S.lam = 0.0; S.f = 0.0; S.it = 0; S.stall = 0; S.force = false;
+      bool okc = true;
+      if (!ok0) {      // rare: phase 1 failed for this element -> per-point edge fallback (needs the nodal densities)
+        double re[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) re[q] = rn[IEN[8 * (i64)B.el + q]];
+        okc = iso::proj_init<iso::HexBox, PMODE>(H, re, c_hex_sg, c_hex_edges, x, rho_t, gs, S);
+      }
+      if (okc) {
+        int status = 0;
+        while (S.it < 100 && status == 0) status = iso::proj_iter<iso::HexBox, PMODE>(H, x, rho_t, gs, S);
+        okc = status == 1; nit = S.it;
+        xi[0] = S.xi[0]; xi[1] = S.xi[1]; xi[2] = S.xi[2];
+      } else { xi[0] = xi[1] = xi[2] = 0.0; nit = -1; }
+      iso::eval_pos(H, xi, p);
+      const double d0 = x[0] - p[0], d1 = x[1] - p[1], d2 = x[2] - p[2];
+      const double dd = sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)));
+      if (to_buf) pairbuf[B.pair_off + li] = dd;
+      else atomicMin((u64 *)&dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0], (u64)__double_as_longlong(dd));
+      its += nit > 0 ? nit : 0; nbad += okc ? 0 : 1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { its += __shfl_down_sync(0xffffffffu, its, o); nbad += __shfl_down_sync(0xffffffffu, nbad, o); }
+  if (lane == 0) { u64 *cs = counters + 8 * (1 + (blockIdx.x & 127)); atomicAdd(&cs[2], (u64)its); if (nbad) atomicAdd(&cs[3], (u64)nbad); }
 }
 template <bool WANT_XP>
 __global__ void __launch_bounds__(128) k_project_tet4(i64 nitems, i64 nact, const ActRec *__restrict__ rec, const i64 *__restrict__ choff,
@@ -675,8 +710,9 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(ctx->cls.reserve((size_t)nel));
   CK(ctx->act_flag.reserve(sizeof(int) * (size_t)(nel + 1)));
   CK(ctx->act_idx.reserve(sizeof(int) * (size_t)(nel + 1)));
-  CK(ctx->counters.reserve(sizeof(u64) * 8 * 1025));      // slot 0: element classes; slots 1..1024: projection statistics
-  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * 8 * 1025, st));
+  constexpr int NCTR = 8 * 129;      // slot 0: element classes; slots 1..128: projection statistics; 8 more words: pair-list counters
+  CK(ctx->counters.reserve(sizeof(u64) * (NCTR + 8)));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(u64) * (NCTR + 8), st));
   CK(cudaMemsetAsync(ctx->act_flag.as<int>() + nel, 0, sizeof(int), st));
   // z-interval of this rank's planes with a margin of (delta + 2 cells): only elements that can reach them are classified
   double zlo = -1e300, zhi = 1e300;
@@ -685,8 +721,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
                                              ctx->cls.as<unsigned char>(), ctx->act_flag.as<int>(), ctx->counters.as<i64>()); LAUNCH_CHECK();
   if (r2s_scan_exclusive_i32(ctx, ctx->act_flag.as<int>(), ctx->act_idx.as<int>(), nel + 1)) return 1;
   int nact_i = 0;
-  CK(cudaMemcpyAsync(&nact_i, ctx->act_idx.as<int>() + nel, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &nact_i, ctx->act_idx.as<int>() + nel, sizeof(int))) return 1;
   i64 nact = nact_i;
   CK(ctx->dist.reserve(sizeof(double) * (size_t)g.ngp));
   if (want_xp) CK(ctx->xp.reserve(sizeof(double) * 3 * (size_t)g.ngp));
@@ -694,7 +729,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(cudaMemsetAsync(ctx->tile_ptr.p, 0, sizeof(int) * (size_t)(g.ntiles + 2), st));
   CK(ctx->tile_faces.reserve((size_t)g.ntiles + 16));
   CK(cudaMemsetAsync(ctx->tile_faces.p, 0, (size_t)g.ntiles, st));
-  i64 npairs = 0, nkeys = 0, nitems = 0;
+  i64 npairs = 0, nkeys = 0, nitems = 0; int ntri = 0;
   u64 *sorted = nullptr;
   if (nact > 0) {
     CK(ctx->act_rec.reserve(sizeof(ActRec) * (size_t)nact));
@@ -709,12 +744,20 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     if (r2s_scan_exclusive_i64(ctx, ntile, toff, nact + 1)) return 1;
     if (r2s_scan_exclusive_i64(ctx, npair, poff, nact + 1)) return 1;
     if (r2s_scan_exclusive_i64(ctx, nchunk, choff, nact + 1)) return 1;
-    i64 h3[3];
-    CK(cudaMemcpyAsync(&h3[0], toff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h3[1], poff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h3[2], choff + nact, sizeof(i64), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    nkeys = h3[0]; npairs = h3[1]; nitems = h3[2];
+    {
+      const size_t o0 = r2s_rb_put(ctx, toff + nact, sizeof(i64)), o1 = r2s_rb_put(ctx, poff + nact, sizeof(i64)), o2 = r2s_rb_put(ctx, choff + nact, sizeof(i64));
+      if (o0 == (size_t)-1 || o1 == (size_t)-1 || o2 == (size_t)-1) return 1;
+      // the triangle count of the boundary-face table is read back with the same synchronisation
+      CK(ctx->tri_cnt.reserve(sizeof(int) * 2 * (size_t)(nact + 1)));
+      int *tcnt = ctx->tri_cnt.as<int>(), *toff32 = tcnt + (nact + 1);
+      CK(cudaMemsetAsync(tcnt + nact, 0, sizeof(int), st));
+      k_tri_count<<<cdiv(nact, 256), 256, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->nsn, tcnt); LAUNCH_CHECK();
+      if (r2s_scan_exclusive_i32(ctx, tcnt, toff32, nact + 1)) return 1;
+      const size_t o3 = r2s_rb_put(ctx, toff32 + nact, sizeof(int));
+      if (o3 == (size_t)-1) return 1;
+      if (r2s_rb_sync(ctx)) return 1;
+      nkeys = *(const i64 *)r2s_rb_at(ctx, o0); npairs = *(const i64 *)r2s_rb_at(ctx, o1); nitems = *(const i64 *)r2s_rb_at(ctx, o2); ntri = *(const int *)r2s_rb_at(ctx, o3);
+    }
     if (nkeys >= (1ll << 31) || npairs >= (1ll << 40)) FAIL("distance binning: problem too large for one slab (key/pair count overflow)");
     CK(ctx->keys.reserve(sizeof(u64) * (size_t)(nkeys + 1)));
     CK(ctx->keys_alt.reserve(sizeof(u64) * (size_t)(nkeys + 1)));
@@ -724,14 +767,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     int tbits = 1; while ((1ll << tbits) < g.ntiles) tbits++;
     if (nkeys > 0) { if (r2s_sort_keys_u64(ctx, ctx->keys.as<u64>(), ctx->keys_alt.as<u64>(), nkeys, 32 + tbits, &sorted)) return 1; }
     // boundary-face triangle table
-    CK(ctx->tri_cnt.reserve(sizeof(int) * 2 * (size_t)(nact + 1)));
-    int *tcnt = ctx->tri_cnt.as<int>(), *toff32 = tcnt + (nact + 1);
-    CK(cudaMemsetAsync(tcnt + nact, 0, sizeof(int), st));
-    k_tri_count<<<cdiv(nact, 256), 256, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->nsn, tcnt); LAUNCH_CHECK();
-    if (r2s_scan_exclusive_i32(ctx, tcnt, toff32, nact + 1)) return 1;
-    int ntri = 0;
-    CK(cudaMemcpyAsync(&ntri, toff32 + nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    int *toff32 = ctx->tri_cnt.as<int>() + (nact + 1);
     CK(ctx->tri_rec.reserve(sizeof(TriRec) * (size_t)(ntri + 1)));
     if (nen == 8) k_tri_records<8><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
     else k_tri_records<4><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
@@ -745,97 +781,44 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     CK(cudaMemcpyAsync(ctx->tile_ptr.as<int>(), tmp.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
-  // HEX8 without xp: lane-refill projection with per-voxel atomicMin (face-free tiles) + exact replay of the tiles with boundary faces.
-  // (The R2S_PROJ* tuning knobs are read on every call so that one process can time the variants side by side, tools/ab_project.py.)
-  const bool refill = getenv("R2S_PROJ") && atoi(getenv("R2S_PROJ")) == 1;       // experimental lane-refill projection (not faster yet)
-  const bool minpath = (refill && nen == 8 && !want_xp);
-  // chunk kernel with direct atomicMin output (opt-in, MODE bit 3): dist[] starts at BIG, k_assemble replays the tiles with boundary faces only
-  const bool atom = !minpath && nen == 8 && !want_xp && getenv("R2S_PROJ_ATOM") && atoi(getenv("R2S_PROJ_ATOM")) == 1 && !(getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1);
-  if (atom) {
+  // Without xp, dist[] starts at BIG and receives the minima of the face-free tiles by atomicMin; k_assemble then replays only the tiles
+  // with boundary-face elements.  With xp everything goes through the pair buffer (the closest point of a voxel is tie-order dependent).
+  if (!want_xp) {
     i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
   }
-  if (minpath) {
-    i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
-    k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
-    if (nact > 0 && npairs > 0) {
-      // occupancy variant (registers per thread 255 / 168 / 128): R2S_PROJ_MINB = 2, 3, 4 (tuning knob, default from measurements)
-      const int minbr = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 3;
-      // box elements (n_box of them, flag built with the mesh) go through the HexBox variant; a mixed mesh takes both launches
-      const bool use_box_r = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
-      const i64 nbx = use_box_r ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
-      const bool uni_r = getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1;
-      const bool fast_r = uni_r || (getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
-#define PMIN(MB, BX, MD) k_project_hex8_min<MB, BX, MD><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
-                                                              ctx->tile_faces.as<unsigned char>(), ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc)
-#define PMINF(MB, BX) do { if (uni_r) PMIN(MB, BX, 3); else if (fast_r) PMIN(MB, BX, 1); else PMIN(MB, BX, 0); } while (0)
-      if (nbx < nel) { if (minbr <= 2) PMINF(2, false); else if (minbr == 3) PMINF(3, false); else PMINF(4, false); LAUNCH_CHECK(); }
-      if (nbx > 0) { if (minbr <= 2) PMINF(2, true); else if (minbr == 3) PMINF(3, true); else PMINF(4, true); }
-#undef PMINF
-#undef PMIN
-      LAUNCH_CHECK();
-    }
-  } else if (nitems > 0) {
+  if (nitems > 0) {
     i64 *choff = ctx->cnt_b.as<i64>() + 2 * (nact + 1);
-    int nb = cdiv(nitems * 32, 128);
-#define PROJ(KERN, XP) KERN<XP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
-                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>())
-    // variants of the HEX8 kernel: R2S_PROJ_MINB = 2..6 CTAs/SM (255 / 168 / 128 / 102 / 85 registers), R2S_PROJ_SMEMA = 1 keeps the
-    // element's monomial coefficients in shared memory
-    const int minb = getenv("R2S_PROJ_MINB") ? atoi(getenv("R2S_PROJ_MINB")) : 4;      // measured: 4 CTAs/SM is 22% faster than 2
-    const bool smema = getenv("R2S_PROJ_SMEMA") && atoi(getenv("R2S_PROJ_SMEMA")) == 1;
-#define PROJH6(XP, MB, SA, BX, MD, PP) k_project_hex8<XP, MB, SA, BX, MD, PP><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), \
-                                                   ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc, p1tab, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>())
-#define PROJH(XP, MB, SA, BX, FS) PROJH6(XP, MB, SA, BX, 0, false)
-    // the opt-in variants (FAST solver and / or phase 1 from the table), instantiated for the occupancies worth measuring
-#define PROJO(MB, BX) do { \
-      if (atom && scaled && BX) PROJH6(false, MB, false, BX, 15, true); \
-      else if (atom) PROJH6(false, MB, false, BX, 11, true); \
-      else if (scaled && BX) { if (use_p1) PROJH6(false, MB, false, BX, 7, true); else PROJH6(false, MB, false, BX, 7, false); } \
-      else if (uni) { if (use_p1) PROJH6(false, MB, false, BX, 3, true); else PROJH6(false, MB, false, BX, 3, false); } \
-      else if (fast) { if (use_p1) PROJH6(false, MB, false, BX, 1, true); else PROJH6(false, MB, false, BX, 1, false); } \
-      else PROJH6(false, MB, false, BX, 0, true); } while (0)
-    // Axis-aligned box elements (flag + count built with the mesh) take the HexBox variant of the kernel, the others the general
-    // trilinear one; a mesh with both kinds takes both launches, each leaving the other kind's chunks alone.  R2S_PROJ_BOX=0
-    // sends everything through the general kernel; R2S_PROJ_BOX_MINB = CTAs/SM of the box variant (4 / 5 / 6).
-    // Not yet measured on a GPU, hence opt-in: R2S_PROJ_FAST=1 (FAST restoration), R2S_PROJ_UNI=1 (FAST + one tangent-step code path), R2S_PROJ_SCALED=1 (UNI + the scaled box form HexBoxS), R2S_PROJ_P1=1 (phase 1 from a per-element table).
-    const bool use_box = !(getenv("R2S_PROJ_BOX") && atoi(getenv("R2S_PROJ_BOX")) == 0);
-    const int minb_box = getenv("R2S_PROJ_BOX_MINB") ? atoi(getenv("R2S_PROJ_BOX_MINB")) : 5;      // measured at n = 256: 92.6 / 86.5 / 89.5 ms for 4 / 5 / 6 CTAs per SM (profiles/r1f_ab_project_variants_n256.jsonl)
-    // R2S_PROJ_ATOM=1: UNI + P1 + direct atomicMin output for tiles without boundary-face elements (decided above: `atom`)
-    const bool scaled = nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_SCALED") && atoi(getenv("R2S_PROJ_SCALED")) == 1;
-    const bool uni = scaled || atom || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_UNI") && atoi(getenv("R2S_PROJ_UNI")) == 1);
-    const bool fast = uni || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_FAST") && atoi(getenv("R2S_PROJ_FAST")) == 1);
-    const bool use_p1 = atom || (nen == 8 && !want_xp && !smema && getenv("R2S_PROJ_P1") && atoi(getenv("R2S_PROJ_P1")) == 1);
-    const i64 nbx = (use_box && nen == 8) ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
-    const double4 *p1tab = nullptr;
-    if (use_p1) {
-      CK(ctx->p1tab.reserve(sizeof(double4) * (size_t)(nact + 1)));
-      if (fast) k_phase1<1><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
-      else k_phase1<0><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->p1tab.as<double4>());
-      LAUNCH_CHECK();
-      p1tab = ctx->p1tab.as<double4>();
-    }
+    const int nb = cdiv(nitems * 32, 128);
     if (nen == 8) {
-      const bool optin = (fast || use_p1) && !want_xp && !smema;
-      if (nbx < nel) {
-        if (want_xp) PROJH(true, 2, false, false, false);
-        else if (smema) { if (minb <= 4) PROJH(false, 4, true, false, false); else if (minb == 5) PROJH(false, 5, true, false, false); else PROJH(false, 6, true, false, false); }
-        else if (optin) { if (minb <= 4) PROJO(4, false); else PROJO(5, false); }
-        else if (minb <= 2) PROJH(false, 2, false, false, false); else if (minb == 3) PROJH(false, 3, false, false, false); else if (minb == 4) PROJH(false, 4, false, false, false);
-        else if (minb == 5) PROJH(false, 5, false, false, false); else PROJH(false, 6, false, false, false);
-        if (nbx > 0) LAUNCH_CHECK();
-      }
-      if (nbx > 0) {
-        if (want_xp) PROJH(true, 4, false, true, false);
-        else if (optin) { if (minb_box <= 5) PROJO(5, true); else if (minb_box == 6) PROJO(6, true); else PROJO(8, true); }
-        else if (minb_box <= 4) PROJH(false, 4, false, true, false); else if (minb_box == 5) PROJH(false, 5, false, true, false); else PROJH(false, 6, false, true, false);
-      }
-    } else { if (want_xp) PROJ(k_project_tet4, true); else PROJ(k_project_tet4, false); }
-    LAUNCH_CHECK();
-#undef PROJO
+      // axis-aligned box elements (flag + count built with the mesh): pair-list path without xp, HexBox chunk kernel with xp; the others
+      // take the general trilinear chunk kernel.  R2S_PROJ_BOX=0 sends everything through the general kernel.
+      const i64 nbx = ctx->knobs.proj_box ? ctx->n_box : 0; const int kc = (nbx > 0 && nbx < nel) ? 1 : 0;
+      const bool list_path = !want_xp && nbx > 0;
+#define PROJH(XP, BX, SKIP) k_project_hex8<XP, BX><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, \
+        ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>(), ctx->ebox.as<unsigned char>(), kc, SKIP, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>())
+      if (nbx < nel) { if (want_xp) PROJH(true, false, 0); else PROJH(false, false, list_path ? 1 : 0); LAUNCH_CHECK(); }
+      if (nbx > 0 && want_xp) { PROJH(true, true, 0); LAUNCH_CHECK(); }
 #undef PROJH
-#undef PROJH6
-#undef PROJ
+      if (list_path) {
+        CK(ctx->box_rec.reserve(sizeof(BoxRec) * (size_t)nact));
+        CK(ctx->plist.reserve(sizeof(u64) * (size_t)(npairs + 1)));
+        u64 *pc = ctx->counters.as<u64>() + NCTR;      // 4 words behind the statistics slots: [0],[1] pass A, [2],[3] pass B
+        BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
+        k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, box); LAUNCH_CHECK();
+        const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * 5 * 4;
+        k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc); LAUNCH_CHECK();
+        k_project_list<<<pgrid, 128, 0, st>>>(pl, pc, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
+        if (prune) {
+          k_pair_scan<1><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc + 2); LAUNCH_CHECK();
+          k_project_list<<<pgrid, 128, 0, st>>>(pl, pc + 2, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
+        }
+      }
+    } else {
+      if (want_xp) k_project_tet4<true><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>());
+      else k_project_tet4<false><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>());
+      LAUNCH_CHECK();
+    }
   }
   if (!want_xp && nact > 0 && npairs > 0) {
     if (nen == 8) k_faces_crossing<8><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
@@ -847,18 +830,17 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 #define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
         ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
         ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
-    if (minpath || atom) { ASM(false, 8, true); }
-    else if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, false); ASM(false, 8, true); } }
+    if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, true); } }      // without xp the face-free tiles are final already
     else { if (want_xp) { ASM(true, 4, false); ASM(true, 4, true); } else { ASM(false, 4, false); ASM(false, 4, true); } }
 #undef ASM
   }
   CK(cudaEventRecord(ctx->ev[3], st));
-  ctx->h_counters.resize(8 * 1025); u64 *hall = ctx->h_counters.data(); u64 hc[8];
-  CK(cudaMemcpyAsync(hall, ctx->counters.p, sizeof(u64) * 8 * 1025, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  for (int q = 0; q < 8; q++) { hc[q] = hall[q]; for (int sl = 1; sl <= 1024; sl++) hc[q] += hall[8 * sl + q]; }
+  u64 hall[NCTR + 8], hc[8];
+  if (r2s_readback(ctx, hall, ctx->counters.p, sizeof(hall))) return 1;
+  for (int q = 0; q < 8; q++) { hc[q] = hall[q]; for (int sl = 1; sl <= 128; sl++) hc[q] += hall[8 * sl + q]; }
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
   ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
+  ctx->rep.n_pairs_pruned = (i64)hall[NCTR + 3];
   CK(cudaEventElapsedTime(&ctx->rep.ms_bin, ctx->ev[0], ctx->ev[1]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_project, ctx->ev[1], ctx->ev[2]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_assemble, ctx->ev[2], ctx->ev[3]));

@@ -111,12 +111,85 @@ int r2s_mesh_build_tables(r2s_ctx *ctx) {
     unsigned long long *dcount = (unsigned long long *)(ctx->ebox.as<unsigned char>() + flag_bytes), hcount = 0;
     CK(cudaMemsetAsync(dcount, 0, 8, ctx->stream));
     k_elem_box<<<cdiv(ctx->nel, 256), 256, 0, ctx->stream>>>(ctx->nel, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->ebox.as<unsigned char>(), dcount); LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(&hcount, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (r2s_readback(ctx, &hcount, dcount, 8)) return 1;
     ctx->n_box = (i64)hcount;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   cnt.release(); cur.release();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-product lattice meshes.  When every HEX8 element is an axis-aligned box in canonical node order whose two corner
+// coordinates are NEIGHBOURING entries of three per-axis tables of distinct node coordinates (voxel-type SIMP meshes, also
+// graded ones and ones with holes, any element numbering), the elements whose closed AABB contains a point -- the candidate set
+// of Sign_Detection_HEX8 (SignDetection.jl:30) -- follow from the point's position in the three tables: no sort, no lists.
+// Built with the mesh: lat_xs (tables), lat_cell[e] (cell of element e), lat_map[cell] (element of a cell or -1).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_gather_axis(i64 nnp, const double *__restrict__ X, int d, double *__restrict__ out) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i < nnp) out[i] = X[3 * i + d];
+}
+__device__ inline int lat_find(const double *xs, int n, double v) {      // index of v in the sorted table or -1
+  int l = 0, h = n;
+  while (l < h) { int m = (l + h) >> 1; if (xs[m] < v) l = m + 1; else h = m; }
+  return (l < n && xs[l] == v) ? l : -1;
+}
+__global__ void k_lat_cells(i64 nel, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ xs, int o0, int o1, int o2, int n0, int n1, int n2,
+                            int *__restrict__ cell_of, int *__restrict__ map, int *__restrict__ fail) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  const i64 na = IEN[8 * e], nb = IEN[8 * e + 6];      // opposite corners (-1,-1,-1) and (+1,+1,+1) of the canonical node order
+  const int off[3] = {o0, o1, o2}, nd[3] = {n0, n1, n2};
+  int a[3]; bool ok = true;
+  for (int d = 0; d < 3; d++) {
+    const double lo = X[3 * na + d], hi = X[3 * nb + d];
+    a[d] = lat_find(xs + off[d], nd[d], lo);
+    ok = ok && a[d] >= 0 && a[d] + 1 < nd[d] && xs[off[d] + a[d] + 1] == hi && lo < hi;
+  }
+  if (!ok) { atomicExch(fail, 1); cell_of[e] = -1; return; }
+  const i64 c = ((i64)a[2] * (n1 - 1) + a[1]) * (n0 - 1) + a[0];
+  cell_of[e] = (int)c;
+  if (atomicCAS(&map[c], -1, (int)e) != -1) atomicExch(fail, 1);      // two elements in one cell: not a lattice mesh
+}
+int r2s_mesh_build_lattice(r2s_ctx *ctx) {
+  ctx->lattice = false; ctx->lat_ncell = 0;
+  if (ctx->nen != 8 || ctx->n_box != ctx->nel || ctx->nel >= (1ll << 28)) return 0;
+  cudaStream_t st = ctx->stream;
+  DevBuf a, b, u;
+  CK(a.reserve(sizeof(double) * (size_t)ctx->nnp)); CK(b.reserve(sizeof(double) * (size_t)ctx->nnp)); CK(u.reserve(sizeof(double) * (size_t)ctx->nnp));
+  std::vector<double> tabs; int nd[3], off[3];
+  for (int d = 0; d < 3; d++) {
+    k_gather_axis<<<cdiv(ctx->nnp, 256), 256, 0, st>>>(ctx->nnp, ctx->X.as<double>(), d, a.as<double>()); LAUNCH_CHECK();
+    double *sorted = nullptr; i64 cnt = 0;
+    if (r2s_sort_f64(ctx, a.as<double>(), b.as<double>(), ctx->nnp, &sorted)) return 1;
+    if (r2s_unique_f64(ctx, sorted, u.as<double>(), ctx->nnp, &cnt)) return 1;
+    if (cnt < 2 || cnt > 100000) { a.release(); b.release(); u.release(); return 0; }      // not a lattice worth tabulating
+    off[d] = (int)tabs.size(); nd[d] = (int)cnt; tabs.resize(tabs.size() + (size_t)cnt);
+    if (r2s_readback(ctx, tabs.data() + off[d], u.p, sizeof(double) * (size_t)cnt)) return 1;
+  }
+  a.release(); b.release(); u.release();
+  const i64 ncell = (i64)(nd[0] - 1) * (nd[1] - 1) * (nd[2] - 1);
+  if (ncell >= (1ll << 31) || ncell > 64 * ctx->nel + 4096) return 0;                       // a sparse point cloud of boxes: the cell map would not pay
+  CK(ctx->lat_xs.reserve(sizeof(double) * tabs.size()));
+  CK(cudaMemcpyAsync(ctx->lat_xs.p, tabs.data(), sizeof(double) * tabs.size(), cudaMemcpyHostToDevice, st));
+  CK(ctx->lat_cell.reserve(sizeof(int) * (size_t)ctx->nel));
+  CK(ctx->lat_map.reserve(sizeof(int) * (size_t)ncell + 8));
+  CK(cudaMemsetAsync(ctx->lat_map.p, 0xff, sizeof(int) * (size_t)ncell + 8, st));
+  int *fail = ctx->lat_map.as<int>() + ncell;      // one word behind the map
+  CK(cudaMemsetAsync(fail, 0, sizeof(int), st));
+  k_lat_cells<<<cdiv(ctx->nel, 256), 256, 0, st>>>(ctx->nel, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->lat_xs.as<double>(), off[0], off[1], off[2], nd[0], nd[1], nd[2],
+                                                   ctx->lat_cell.as<int>(), ctx->lat_map.as<int>(), fail); LAUNCH_CHECK();
+  int hfail = 1;
+  if (r2s_readback(ctx, &hfail, fail, sizeof(int))) return 1;
+  if (hfail) return 0;
+  for (int d = 0; d < 3; d++) { ctx->lat_nd[d] = nd[d]; ctx->lat_off[d] = off[d]; }
+  ctx->lat_ncell = ncell; ctx->lattice = true;
+  return 0;
+}
+extern "C" int r2s_mesh_is_lattice(r2s_ctx *ctx, int *is_lattice) {
+  if (!ctx || !is_lattice) return 1;
+  *is_lattice = ctx->lattice ? 1 : 0;
   return 0;
 }
 
@@ -202,8 +275,7 @@ int r2s_dev_mesh_volume(r2s_ctx *ctx, double *vd, double *vf) {
   k_mesh_volume<<<nb, 128, 0, ctx->stream>>>(ctx->nel, ctx->nen, ctx->X.as<double>(), ctx->IEN32.as<int>(), ctx->rho_e.as<double>(), gauss_legendre_host(3), part); LAUNCH_CHECK();
   k_sum_partials<<<1, 32, 0, ctx->stream>>>(part, nb, 2, part + 2 * (size_t)nb); LAUNCH_CHECK();
   double h[2];
-  CK(cudaMemcpyAsync(h, part + 2 * (size_t)nb, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, h, part + 2 * (size_t)nb, sizeof(h))) return 1;
   *vd = h[0]; *vf = h[1] / h[0];
   return 0;
 }
@@ -322,8 +394,7 @@ int r2s_dev_isocontour_volume(r2s_ctx *ctx, double thr, double *vol) {
   k_iso_volume<<<nb, 256, 0, ctx->stream>>>(ctx->nel, ctx->X.as<double>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), thr, gauss_legendre_host(3), gauss_legendre_host(15), part); LAUNCH_CHECK();
   k_sum_partials<<<1, 32, 0, ctx->stream>>>(part, nb, 1, part + nb); LAUNCH_CHECK();
   double h;
-  CK(cudaMemcpyAsync(&h, part + nb, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (r2s_readback(ctx, &h, part + nb, sizeof(h))) return 1;
   *vol = h;
   return 0;
 }

@@ -39,182 +39,17 @@ __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__re
 // ------------------------------------------------------------------------------------------------ 81-point stencil
 // weights by squared offset m = di^2+dj^2+dk^2 <= 6
 struct StencilW { float w[8]; };
-#define ST_X 32
-#define ST_Y 4
-#define ST_Z 16
-#define ST_ZB 4            // outputs per thread along z
-#define ST_H 2             // halo
-// out = K * in_eff with in_eff = (beta_mode ? r + beta*u : in).  When beta_mode, the interior in_eff is written back to u.
-// partial[block] (double) receives sum(in_eff * out) over the block's interior.
-template <bool BETA>
-__global__ void __launch_bounds__(ST_X *ST_Y *(ST_Z / ST_ZB)) k_stencil81(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
-                                                                           const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
-                                                                           double *__restrict__ partial, StencilW W) {
-  __shared__ float sm[ST_Z + 2 * ST_H][ST_Y + 2 * ST_H][ST_X + 2 * ST_H];
-  __shared__ double red[ST_X * ST_Y * (ST_Z / ST_ZB) / 32];
-  const int bx = blockIdx.x * ST_X, by = blockIdx.y * ST_Y, bz = kz0 + blockIdx.z * ST_Z;      // outputs: planes [kz0, kz1) (z-slab)
-  const int tid = threadIdx.x;
-  float beta = 0.0f;
-  if (BETA) beta = scal[0];
-  // cooperative tile load with halo (zero outside the grid: K has no entries there)
-  const int TX = ST_X + 2 * ST_H, TY = ST_Y + 2 * ST_H, TZ = ST_Z + 2 * ST_H;
-  for (int t = tid; t < TX * TY * TZ; t += blockDim.x) {
-    int lx = t % TX, ly = (t / TX) % TY, lz = t / (TX * TY);
-    int gx = bx + lx - ST_H, gy = by + ly - ST_H, gz = bz + lz - ST_H;
-    float v = 0.0f;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) {
-      i64 gi = ((i64)gz * ny + gy) * nx + gx;
-      if (BETA) {
-        v = r[gi] + beta * u[gi];       // the new u goes to a separate buffer: other blocks still read the old one for their halos
-      } else v = in[gi];
-    }
-    sm[lz][ly][lx] = v;
-  }
-  __syncthreads();
-  const int lx = tid % ST_X, ly = (tid / ST_X) % ST_Y, lzb = tid / (ST_X * ST_Y);
-  float acc[ST_ZB];
-#pragma unroll
-  for (int q = 0; q < ST_ZB; q++) acc[q] = 0.0f;
-#pragma unroll
-  for (int dj = -2; dj <= 2; dj++)
-#pragma unroll
-    for (int di = -2; di <= 2; di++) {
-      if (di * di + dj * dj > 6) continue;
-      float col[ST_ZB + 4];
-#pragma unroll
-      for (int z = 0; z < ST_ZB + 4; z++) col[z] = sm[lzb * ST_ZB + z][ly + ST_H + dj][lx + ST_H + di];
-#pragma unroll
-      for (int dk = -2; dk <= 2; dk++) {
-        if (di * di + dj * dj + dk * dk > 6) continue;
-        float w = W.w[di * di + dj * dj + dk * dk];
-#pragma unroll
-        for (int q = 0; q < ST_ZB; q++) acc[q] = fmaf(w, col[q + 2 + dk], acc[q]);
-      }
-    }
-  double dsum = 0.0;
-#pragma unroll
-  for (int q = 0; q < ST_ZB; q++) {
-    int gx = bx + lx, gy = by + ly, gz = bz + lzb * ST_ZB + q;
-    if (gx < nx && gy < ny && gz < kz1) {
-      i64 gi = ((i64)gz * ny + gy) * nx + gx;
-      float ctr = sm[lzb * ST_ZB + q + ST_H][ly + ST_H][lx + ST_H];
-      out[gi] = acc[q];
-      if (BETA) unew[gi] = ctr;
-      dsum += (double)ctr * (double)acc[q];
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
-  if ((tid & 31) == 0) red[tid >> 5] = dsum;
-  __syncthreads();
-  if (tid == 0) {
-    double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i];
-    partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
-  }
-}
-// ---- plane-marching variant (2.5-D blocking) ----------------------------------------------------------------------
-// A CTA owns a 32 x 8 column of the grid and marches along z over S2_ZC output planes.  Each input plane (with its x-y halo)
-// is staged once in shared memory; a thread reads its 21 (di, dj) neighbours and scatters them into the five outputs the plane
-// contributes to (dk = -2..2), held in a rotating register queue.  Per output: 21 shared-memory loads and 81 FMAs (the
-// tile-per-CTA kernel above needs 42 loads plus a div/mod tile fill), which makes the mat-vec HBM-bound instead of issue-bound.
-// Same operation as k_stencil81; the per-output summation order differs (dk-major per plane), results agree to Float32 round-off.
-#define S2_X 32
-#define S2_Y 8
-#define S2_ZC 64
-template <bool BETA>
-__global__ void __launch_bounds__(S2_X *S2_Y) k_stencil81_march(int nx, int ny, int nz, int kz0, int kz1, const float *__restrict__ in, const float *__restrict__ r,
-                                                                const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
-                                                                float *__restrict__ out, double *__restrict__ partial, StencilW W) {
-  __shared__ float sm[2][S2_Y + 4][S2_X + 4];
-  __shared__ double red[S2_X * S2_Y / 32];
-  const int tid = threadIdx.x, lx = tid % S2_X, ly = tid / S2_X;
-  const int bx = blockIdx.x * S2_X, by = blockIdx.y * S2_Y;
-  const int zc0 = kz0 + blockIdx.z * S2_ZC, zc1 = min(zc0 + S2_ZC, kz1);       // output planes of this CTA
-  const int gx = bx + lx, gy = by + ly;
-  const bool inside = gx < nx && gy < ny;
-  float beta = 0.0f;
-  if (BETA) beta = scal[0];
-  // the (up to) two tile elements this thread stages per plane
-  constexpr int TX = S2_X + 4, TY = S2_Y + 4, NT = TX * TY;
-  int e_lx[2], e_ly[2]; bool e_ok[2], e_own[2]; i64 e_off[2];
-#pragma unroll
-  for (int q = 0; q < 2; q++) {
-    int t = tid + q * S2_X * S2_Y;
-    e_ly[q] = t / TX; e_lx[q] = t % TX;
-    int x = bx + e_lx[q] - 2, y = by + e_ly[q] - 2;
-    e_ok[q] = t < NT && x >= 0 && x < nx && y >= 0 && y < ny;
-    e_own[q] = e_ok[q] && e_lx[q] >= 2 && e_lx[q] < TX - 2 && e_ly[q] >= 2 && e_ly[q] < TY - 2;      // interior of the tile: this CTA writes u_new there
-    e_off[q] = (i64)y * nx + x;
-    if (t >= NT) { e_ly[q] = 0; e_lx[q] = 0; }
-  }
-  const i64 pl = (i64)nx * ny;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;       // outputs zin-2 .. zin+2
-  float c0 = 0.f, c1 = 0.f;                                        // centre values of planes zin-2, zin-1
-  double dsum = 0.0;
-  // software pipeline: the global loads of plane zin + 1 are issued before the FMAs of plane zin
-  float pv[2];
-  auto fetch = [&](int z) {
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      float v = 0.0f;
-      if (e_ok[q] && z >= 0 && z < nz) {
-        i64 gi = (i64)z * pl + e_off[q];
-        if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && z >= zc0 && z < zc1) unew[gi] = v; }
-        else v = in[gi];
-      }
-      pv[q] = v;      // zeros outside the grid: K has no entries there
-    }
-  };
-  fetch(zc0 - 2);
-  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
-    const int buf = (zin - zc0 + 2) & 1;
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-      if (tid + q * S2_X * S2_Y < NT) sm[buf][e_ly[q]][e_lx[q]] = pv[q];
-    __syncthreads();
-    if (zin + 1 < zc1 + 2) fetch(zin + 1);
-    float ctr = 0.f;
-#pragma unroll
-    for (int dj = -2; dj <= 2; dj++)
-#pragma unroll
-      for (int di = -2; di <= 2; di++) {
-        const int m2 = di * di + dj * dj;
-        if (m2 > 6) continue;
-        const float v = sm[buf][ly + 2 + dj][lx + 2 + di];
-        if (di == 0 && dj == 0) ctr = v;
-        a2 = fmaf(W.w[m2], v, a2);
-        if (m2 + 1 <= 6) { a1 = fmaf(W.w[m2 + 1], v, a1); a3 = fmaf(W.w[m2 + 1], v, a3); }
-        if (m2 + 4 <= 6) { a0 = fmaf(W.w[m2 + 4], v, a0); a4 = fmaf(W.w[m2 + 4], v, a4); }
-      }
-    // output plane zin - 2 is complete
-    const int zo = zin - 2;
-    if (zo >= zc0 && inside) {
-      i64 gi = (i64)zo * pl + (i64)gy * nx + gx;
-      out[gi] = a0;
-      dsum += (double)c0 * (double)a0;
-    }
-    a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f;
-    c0 = c1; c1 = ctr;
-    // the other buffer is overwritten next iteration: everybody must be done reading it (it was read one iteration ago) -> one barrier per plane suffices
-  }
-  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
-  if ((tid & 31) == 0) red[tid >> 5] = dsum;
-  __syncthreads();
-  if (tid == 0) {
-    double a = 0; for (int i = 0; i < S2_X * S2_Y / 32; i++) a += red[i];
-    partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
-  }
-}
-// ---- plane-marching, two outputs per thread ---------------------------------------------------------------------
-// As k_stencil81_march, but a thread owns two x-adjacent columns: the six row values it needs come in as three 8-byte
-// shared-memory loads and serve both outputs (7.5 loads per output instead of 21), and the per-plane bookkeeping is shared.
+// ---- plane marching (2.5-D blocking), two outputs per thread ----------------------------------------------------------------
+// A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane (with its x-y halo) is staged
+// once in shared memory; a thread owns two x-adjacent columns: the six row values it needs come in as three 8-byte shared-memory loads
+// and serve both outputs.  The tap weight depends on the squared distance only and w[m] = exp(-m), so w[m2 + dz^2] = w[m2] * w[dz^2]:
+// the in-plane sums S9 (taps with m2 <= 2) and S21 = S9 + S12 (all 21 in-plane taps) are formed once per input plane and enter the
+// five output planes (rotating register queue) as a2 += S21, a1/a3 += w[1] S21, a0/a4 += w[4] S9 -- 27 FMA-pipe operations per column
+// and plane instead of 81.  The products w[m2] * w[dz^2] differ from float(exp(-(m2 + dz^2))) by Float32 round-off (mat-vec 4e-7
+// relative; CG iteration counts and weights equal to the oracle's, tests/test_gpu_parity.py).
 #define S3_X 32            // outputs per CTA in x (16 threads x 2)
 #define S3_Y 16
-// FACT (opt-in, R2S_STENCIL=3): the tap weight depends on the squared distance only and w[m] = exp(-m), so w[m2 + dz^2] = w[m2] * w[dz^2]:
-// the in-plane sums S9 (taps with m2 <= 2) and S21 = S9 + S12 (all 21 in-plane taps) are formed once per input plane and enter the five
-// output planes as a2 += S21, a1/a3 += w[1] S21, a0/a4 += w[4] S9 -- 27 FMA-pipe operations per column and plane instead of 81.  The
-// products w[m2] * w[dz^2] differ from the tabulated float(exp(-(m2 + dz^2))) by Float32 round-off (mat-vec 4e-7 relative, CG
-// iteration counts and weights checked against the oracle in numpy).
-template <bool BETA, bool FACT>
+template <bool BETA>
 __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, int zc, const float *__restrict__ in, const float *__restrict__ r,
                                                           const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
                                                           float *__restrict__ out, double *__restrict__ partial, StencilW W) {
@@ -278,17 +113,11 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
         const int m2 = di * di + dj * dj;
         if (m2 > 6) continue;
         const float va = v[di + 2], vb = v[di + 3];
-        if (FACT) {
-          if (m2 <= 2) { s9a = fmaf(W.w[m2], va, s9a); s9b = fmaf(W.w[m2], vb, s9b); }
-          else { s12a = fmaf(W.w[m2], va, s12a); s12b = fmaf(W.w[m2], vb, s12b); }
-          continue;
-        }
-        a2 = fmaf(W.w[m2], va, a2); b2 = fmaf(W.w[m2], vb, b2);
-        if (m2 + 1 <= 6) { a1 = fmaf(W.w[m2 + 1], va, a1); a3 = fmaf(W.w[m2 + 1], va, a3); b1 = fmaf(W.w[m2 + 1], vb, b1); b3 = fmaf(W.w[m2 + 1], vb, b3); }
-        if (m2 + 4 <= 6) { a0 = fmaf(W.w[m2 + 4], va, a0); a4 = fmaf(W.w[m2 + 4], va, a4); b0 = fmaf(W.w[m2 + 4], vb, b0); b4 = fmaf(W.w[m2 + 4], vb, b4); }
+        if (m2 <= 2) { s9a = fmaf(W.w[m2], va, s9a); s9b = fmaf(W.w[m2], vb, s9b); }
+        else { s12a = fmaf(W.w[m2], va, s12a); s12b = fmaf(W.w[m2], vb, s12b); }
       }
     }
-    if (FACT) {
+    {
       const float e1 = W.w[1], e4 = W.w[4], s21a = s9a + s12a, s21b = s9b + s12b;
       a2 += s21a; a1 = fmaf(e1, s21a, a1); a3 = fmaf(e1, s21a, a3); a0 = fmaf(e4, s9a, a0); a4 = fmaf(e4, s9a, a4);
       b2 += s21b; b1 = fmaf(e1, s21b, b1); b3 = fmaf(e1, s21b, b3); b0 = fmaf(e4, s9b, b0); b4 = fmaf(e4, s9b, b4);
@@ -467,117 +296,6 @@ __global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const f
   for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
   if (lane == 0 && local) atomicAdd(&acc[2], local);
 }
-// ---- cut cells split into slabs (experimental variant, R2S_VOLCUT=1; slower than k_vol_cut as measured, see vol_bisect_step) ---
-// For a fixed first Gauss coordinate the 81 remaining points of a cut cell are a bilinear patch between four lerped corner
-// values: if all four are >= 0 every point of the slab is inside, if all four are < 0 none is (exact also in Float32: a lerp of
-// non-negative numbers with weights in (0, 1) is non-negative, and likewise for negative ones).  Pass 1 (one thread per cut
-// cell) picks the slab axis along which the corner values vary most -- the axis the surface is most perpendicular to, so that
-// most slabs are uniform -- adds the uniform slabs as constants and queues the mixed ones; pass 2 (one thread per mixed slab)
-// evaluates their 81 points.  Only ~1/3 of the 729 points of a cut cell are evaluated on average.  A slab's Float32 sum of
-// (w_i w_j) w_k is accumulated as a 2^-37 fixed-point integer, so the total is deterministic and independent of the order.
-struct SlabConst { float gx[9]; float gw[9]; u64 full[9]; };       // abscissae in [0,1], weights, fixed-point sum of a fully inside slab
-__device__ __forceinline__ void slab_corners(const float *__restrict__ sdf, int nx, int ny, int c, float th, int axis, float u[2][2][2]) {
-  const int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = c / ((nx - 1) * (ny - 1));
-  const i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
-  float v[2][2][2];      // [x][y][z]
-  v[0][0][0] = sdf[b] - th; v[1][0][0] = sdf[b + 1] - th; v[0][1][0] = sdf[b + nx] - th; v[1][1][0] = sdf[b + nx + 1] - th;
-  v[0][0][1] = sdf[b + sxy] - th; v[1][0][1] = sdf[b + sxy + 1] - th; v[0][1][1] = sdf[b + sxy + nx] - th; v[1][1][1] = sdf[b + sxy + nx + 1] - th;
-#pragma unroll
-  for (int p = 0; p < 2; p++)
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        // (p, q, r) = (slab axis, next axis, next axis), cyclic: axis 0 -> (x,y,z), 1 -> (y,z,x), 2 -> (z,x,y)
-        const float val = axis == 0 ? v[p][q][r] : (axis == 1 ? v[r][p][q] : v[q][r][p]);
-        u[p][q][r] = val;
-      }
-}
-__device__ __forceinline__ int slab_axis(const float *__restrict__ sdf, int nx, int ny, int c, float th) {
-  const int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = c / ((nx - 1) * (ny - 1));
-  const i64 b = ((i64)k * ny + j) * nx + i, sxy = (i64)nx * ny;
-  const float v000 = sdf[b] - th, v100 = sdf[b + 1] - th, v010 = sdf[b + nx] - th, v110 = sdf[b + nx + 1] - th;
-  const float v001 = sdf[b + sxy] - th, v101 = sdf[b + sxy + 1] - th, v011 = sdf[b + sxy + nx] - th, v111 = sdf[b + sxy + nx + 1] - th;
-  const float dx = fabsf((v100 + v110 + v101 + v111) - (v000 + v010 + v001 + v011));
-  const float dy = fabsf((v010 + v110 + v011 + v111) - (v000 + v100 + v001 + v101));
-  const float dz = fabsf((v001 + v101 + v011 + v111) - (v000 + v100 + v010 + v110));
-  return (dx >= dy && dx >= dz) ? 0 : (dy >= dz ? 1 : 2);
-}
-// pass 1: one thread per cut cell; acc[2] += uniform slabs, mixed slabs -> slablist (entry = cell * 32 + axis * 9 + iq ... packed in 64 bits)
-__global__ void __launch_bounds__(128) k_vol_cut_slabs1(int nx, int ny, const float *__restrict__ sdf, float th, const int *__restrict__ cutlist, int cutcap, SlabConst K,
-                                                        u64 *__restrict__ acc, u64 *__restrict__ slablist) {
-  const int ncut = (int)min((u64)cutcap, acc[1]);
-  const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
-  u64 local = 0;
-  for (int base = blockIdx.x * blockDim.x; base < ncut; base += nthr) {
-    const int idx = base + threadIdx.x;
-    const bool on = idx < ncut;
-    int c = 0, axis = 0; float u[2][2][2];
-    if (on) { c = cutlist[idx]; axis = slab_axis(sdf, nx, ny, c, th); slab_corners(sdf, nx, ny, c, th, axis, u); }
-#pragma unroll 1
-    for (int iq = 0; iq < 9; iq++) {
-      bool mixed = false;
-      if (on) {
-        const float xi = K.gx[iq], xm = 1.0f - xi;
-        const float s00 = u[0][0][0] * xm + u[1][0][0] * xi, s01 = u[0][0][1] * xm + u[1][0][1] * xi;
-        const float s10 = u[0][1][0] * xm + u[1][1][0] * xi, s11 = u[0][1][1] * xm + u[1][1][1] * xi;
-        const float mn = fminf(fminf(s00, s01), fminf(s10, s11)), mx = fmaxf(fmaxf(s00, s01), fmaxf(s10, s11));
-        if (mn >= 0.0f) local += K.full[iq]; else if (!(mx < 0.0f)) mixed = true;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, mixed);
-      if (m) {
-        u64 pos = 0;
-        if (lane == 0) pos = atomicAdd(&acc[6], (u64)__popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (mixed) slablist[pos + __popc(m & ((1u << lane) - 1))] = ((u64)(unsigned)c << 8) | (u64)(axis * 16 + iq);
-      }
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  if (lane == 0 && local) atomicAdd(&acc[2], local);
-}
-// pass 2: one thread per mixed slab, 81 points
-__global__ void __launch_bounds__(128) k_vol_cut_slabs2(int nx, int ny, const float *__restrict__ sdf, float th, const u64 *__restrict__ slablist, SlabConst K, u64 *__restrict__ acc) {
-  const u64 nslab = acc[6];
-  const int lane = threadIdx.x & 31; const u64 nthr = (u64)gridDim.x * blockDim.x;
-  u64 local = 0;
-  for (u64 base = (u64)blockIdx.x * blockDim.x; base < nslab; base += nthr) {
-    const u64 idx = base + threadIdx.x;
-    if (idx < nslab) {
-      const u64 e = slablist[idx];
-      const int c = (int)(e >> 8), axis = (int)((e & 255) >> 4), iq = (int)(e & 15);
-      float u[2][2][2]; slab_corners(sdf, nx, ny, c, th, axis, u);
-      const float xi = K.gx[iq], xm = 1.0f - xi, wi = K.gw[iq];
-      const float s00 = u[0][0][0] * xm + u[1][0][0] * xi, s01 = u[0][0][1] * xm + u[1][0][1] * xi;
-      const float s10 = u[0][1][0] * xm + u[1][1][0] * xi, s11 = u[0][1][1] * xm + u[1][1][1] * xi;
-      float part = 0.0f;
-#pragma unroll
-      for (int jq = 0; jq < 9; jq++) {
-        const float eta = K.gx[jq], em = 1.0f - eta;
-        const float c0 = s00 * em + s10 * eta, c1 = s01 * em + s11 * eta, dc = c1 - c0, wij = wi * K.gw[jq];
-#pragma unroll
-        for (int kq = 0; kq < 9; kq++) {
-          const float ps = fmaf(dc, K.gx[kq], c0);
-          if (ps >= 0.0f) part += wij * K.gw[kq];
-        }
-      }
-      local += (u64)llrint((double)part * 137438953472.0);
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  if (lane == 0 && local) atomicAdd(&acc[2], local);
-}
-static SlabConst slab_const() {
-  GaussTab t = gauss_legendre_host(9); SlabConst K;
-  for (int i = 0; i < 9; i++) { K.gx[i] = ((float)t.x[i] + 1) / 2; K.gw[i] = (float)t.w[i]; }
-  for (int i = 0; i < 9; i++) {      // the sum pass 2 would produce for a slab whose 81 points are all inside (same Float32 order)
-    float part = 0.0f;
-    for (int j = 0; j < 9; j++) { const float wij = K.gw[i] * K.gw[j]; for (int k = 0; k < 9; k++) part += wij * K.gw[k]; }
-    K.full[i] = (u64)llrint((double)part * 137438953472.0);
-  }
-  return K;
-}
-
 // ---- LS_Threshold bisection (RBFs4Smoothing.jl:265-300): volume of {lsf - th >= 0} for a SEQUENCE of thresholds ----------
 // V(th) is a sum over cells; a cell's class depends only on (cmin, cmax) = (min, max) of its 8 corner values: full iff
 // cmin >= th, empty iff cmax < th (IEEE subtraction is sign-exact, so min_i(v_i - th) >= 0  <=>  cmin >= th).  Every later
@@ -654,8 +372,7 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
     k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
     k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc); LAUNCH_CHECK();
     u64 h[3];
-    CK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (r2s_readback(ctx, h, acc, sizeof(h))) return 1;
     if ((i64)h[1] > cutcap) {     // the cut list was too small: grow it and redo both passes
       CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
       continue;
@@ -774,26 +491,17 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
       else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
     }
     LAUNCH_CHECK();
-    // R2S_VOLCUT=1 selects the slab-split variant below.  Measured on B200 (256^3 case): threshold stage 67.6 ms vs 25.0 ms for the
-    // plain one-thread-per-cell kernel -- the second gather of the corner values and the queue traffic cost more than the skipped
-    // Gauss points save -- so it stays off; kept because it evaluates only ~1/3 of the points and is parity-tested.
-    static const bool slabs = getenv("R2S_VOLCUT") && atoi(getenv("R2S_VOLCUT")) == 1;
-    if (slabs) {
-      static const SlabConst KS = slab_const();
-      CK(ctx->slablist.reserve(sizeof(u64) * 9 * (size_t)cutcap + 64));
-      CK(cudaMemsetAsync(vb.acc + 6, 0, sizeof(u64), st));
-      k_vol_cut_slabs1<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.sdf, th, ctx->cutlist.as<int>(), cutcap, KS, vb.acc, ctx->slablist.as<u64>()); LAUNCH_CHECK();
-      k_vol_cut_slabs2<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.sdf, th, ctx->slablist.as<u64>(), KS, vb.acc); LAUNCH_CHECK();
-    } else {
-      k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, 0, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
-    }
+    k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, 0, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
     // cross-rank sum of (full cells, overflow flag, cut sum); integers, so the total does not depend on the slab count
     u64 *red = vb.acc + 8, hr[4];
     k_vol_pack<<<1, 1, 0, st>>>(vb.acc, cutcap, red); LAUNCH_CHECK();
     if (r2s_allreduce(ctx, red, 4, 1)) return 1;
-    CK(cudaMemcpyAsync(h, vb.acc, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hr, red, sizeof(hr), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    {      // acc[0..5] and red[0..3] are contiguous (red = acc + 8): one read-back of 12 words
+      u64 hall[12];
+      if (r2s_readback(ctx, hall, vb.acc, sizeof(hall))) return 1;
+      for (int q = 0; q < 6; q++) h[q] = hall[q];
+      for (int q = 0; q < 4; q++) hr[q] = hall[8 + q];
+    }
     if (hr[1] != 0) {      // some rank's cut list overflowed: every rank repeats the step (collectives stay matched)
       if ((i64)h[1] > cutcap) CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
       continue;
@@ -1003,21 +711,15 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   k_to_f32<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, o_lo, ctx->sdf.as<double>(), s + o_lo, ubits); LAUNCH_CHECK();
   if (r2s_allreduce(ctx, ubits, 1, 2)) return 1;                          // global max finite |v| (RBFs4Smoothing.jl:17)
   unsigned hb = 0;
-  CK(cudaMemcpyAsync(&hb, ubits, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &hb, ubits, sizeof(unsigned))) return 1;
   if (hb == 0) FAIL("RBFs_smoothing: the SDF holds no finite value (maximum over an empty collection, RBFs4Smoothing.jl:17)");
   k_replace_far<<<cdiv(nown, 256), 256, 0, st>>>(nown, s + o_lo, ubits); LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, s, pl, k0, k1, nz, 2, 3)) return 1;
   CK(cudaEventRecord(ctx->ev[5], st));
-  // mat-vec kernel: plane-marching (default) or tile-per-CTA (R2S_STENCIL=0, kept for comparison)
-  // 0 tile-per-CTA, 1 plane-marching, 2 plane-marching with 2 outputs/thread (default), 3 = 2 with the factorised weights (opt-in, not yet
-  // measured on a GPU); read on every call so that one process can time the variants side by side
-  const int svar = getenv("R2S_STENCIL") ? atoi(getenv("R2S_STENCIL")) : 2;
-  const bool march = svar != 0, m2v = svar == 2 || svar == 3;
-  // even z-chunks of about 64 planes: a 65-plane slab is one chunk, not 64 + 1
+  // mat-vec kernel: plane marching, two outputs per thread, factorised weights; even z-chunks of about 64 planes (a 65-plane slab is one chunk, not 64 + 1)
   const int nchunk = std::max(1, (k1 - k0 + 32) / 64), zc = cdiv(k1 - k0, nchunk);
-  dim3 sgrid = m2v ? dim3(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc)) : (svar == 1 ? dim3(cdiv(nx, S2_X), cdiv(ny, S2_Y), cdiv(k1 - k0, S2_ZC)) : dim3(cdiv(nx, ST_X), cdiv(ny, ST_Y), cdiv(k1 - k0, ST_Z)));
-  int sthreads = m2v ? 256 : (svar == 1 ? S2_X * S2_Y : ST_X * ST_Y * (ST_Z / ST_ZB));
+  dim3 sgrid(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc));
+  const int sthreads = 256;
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
@@ -1037,8 +739,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     if (r2s_allreduce(ctx, dsc, 1, 0)) return 1;
     k_cg_init<<<1, 1, 0, st>>>(scal, dsc); LAUNCH_CHECK();
     float hs[8];
-    CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (r2s_readback(ctx, hs, scal, sizeof(hs))) return 1;
     float residual = hs[2], tol = hs[4];
     float *u_old = u, *u_new = u + n;      // ping-pong halves of the u buffer
     if (r2s_p2p_map_c(ctx, c, sizeof(float) * (size_t)n)) return 1;
@@ -1047,10 +748,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
       if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      if (svar == 3) k_stencil81_march2<true, true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
-      else if (svar == 2) k_stencil81_march2<true, false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
-      else if (march) k_stencil81_march<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
-      else k_stencil81<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, nullptr, r, u_old, u_new, scal, c, part, W);
+      k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
@@ -1073,8 +771,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
       if (probe) CK(cudaEventRecord(ctx->ev_probe[4], st));
       k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
-      CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      if (r2s_readback(ctx, hs, scal, sizeof(hs))) return 1;
       residual = hs[2]; iters++;
       if (probe) for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1]));
       { float *t = u_old; u_old = u_new; u_new = t; }
@@ -1086,10 +783,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  if (svar == 3) k_stencil81_march2<false, true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
-  else if (svar == 2) k_stencil81_march2<false, false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
-  else if (march) k_stencil81_march<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
-  else k_stencil81<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
   // LS_Threshold (:265-300)
@@ -1101,8 +795,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   if (r2s_allreduce(ctx, ubits + 3, 1, 2)) return 1;
   if (r2s_group_end(ctx)) return 1;
   unsigned hmm[2];
-  CK(cudaMemcpyAsync(hmm, ubits + 2, sizeof(hmm), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, hmm, ubits + 2, sizeof(hmm))) return 1;
   CK(cudaEventRecord(ctx->ev[7], st));
   float lo = ordered_to_float(hmm[0]), hi = ordered_to_float(hmm[1]);
   // coarse cell edge as the reference measures it: norm(grid[2,1,1] - grid[1,1,1]) with Float32 range() coordinates (:41-43)

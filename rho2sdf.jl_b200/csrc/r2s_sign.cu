@@ -92,7 +92,7 @@ __global__ void k_sign_emit(i64 nel, const SRange *__restrict__ rng, const i64 *
 // preserved), then every lane advances through that culled list on its own: all lanes run the expensive inverse map at
 // the same time, each on its own next candidate, instead of serialising over elements.
 #define CULL_CAP 96
-// CLS (opt-in, R2S_SIGN_CLASS=1): candidates whose element is of density class 1 / 2 (k_sign_ranges) skip the gather of the eight
+// CLS: candidates whose element is of density class 1 / 2 (k_sign_ranges) skip the gather of the eight
 // nodal densities and the shape functions -- the outcome of "rho >= rho_t" is known; the state updates (max_local, break) are the same.
 template <int NEN, bool CLS>
 __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz1, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
@@ -249,11 +249,138 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_sign(GridDev g, int kz0, int kz
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ lattice fast path
+// Tensor-product lattice meshes (r2s_mesh_build_lattice): the elements whose closed AABB contains a grid point are the <= 2 x 2 x 2
+// lattice cells around it, read from per-axis tables -- no keys, no sort, no list walk.  The reference's rule is replayed on those
+// candidates in ascending element index with the arithmetic of the general path: for a box element the affine inverse map of
+// ex::affine_inverse_apply reduces per axis to xi_d = -((cof_d * (ctr_d - x_d)) / det) with ctr_d = fl(lo + hi) / 2, half_d = fl(hi - lo) / 2
+// (what ex::mono8 yields for a box, exactly), cof_0 = fl(h1 h2), cof_1 = fl(h0 h2), cof_2 = fl(h0 h1), det = fl(h0 cof_0); the terms
+// the general formula adds are exact zeros.  Bit-identical signs (tests: lattice path vs. k_sign<8> vs. oracle).
+// info[cell] = element id | density class << 29 | hot << 31, 0xffffffff = no element (hole, or irrelevant for this z-slab)
+__global__ void k_lat_info(i64 nel, const int *__restrict__ IEN, const double *__restrict__ rn, double rho_t, const int *__restrict__ cell_of,
+                           const double2 *__restrict__ ezr, double zlo, double zhi, unsigned *__restrict__ info) {
+  i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  const double2 z = ezr[e];
+  if (z.y < zlo || z.x > zhi) return;
+  double rmax = -1e300, rmin = 1e300;
+#pragma unroll
+  for (int a = 0; a < 8; a++) { const double r = rn[IEN[8 * e + a]]; rmax = fmax(rmax, r); rmin = fmin(rmin, r); }
+  unsigned cls = 0;      // same density classes as k_sign_ranges
+  const double range = rmax - rmin, tolc = 1e-9 * fmax(1.0, fabs(rho_t));
+  if (rmin - 0.05 * range >= rho_t + tolc) cls = 1; else if (rmax + 0.05 * range < rho_t - tolc) cls = 2;
+  const unsigned hot = !(rmax < rho_t) ? 1u : 0u;
+  info[cell_of[e]] = (unsigned)e | (cls << 29) | (hot << 31);
+}
+// per grid axis point: first candidate cell and how many (0, 1 or 2): cells a with xs[a] <= x <= xs[a+1] (closed AABB, sdfOnDensityField.jl:60-69)
+__global__ void k_lat_pt(GridDev g, const double *__restrict__ xs, int o0, int o1, int o2, int n0, int n1, int n2, int *__restrict__ pt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int off[3] = {o0, o1, o2}, nd[3] = {n0, n1, n2};
+  int d = 0, i = t;
+  if (i >= g.np[0]) { i -= g.np[0]; d = 1; if (i >= g.np[1]) { i -= g.np[1]; d = 2; if (i >= g.np[2]) return; } }
+  const double x = g.pc[g.pc_off[d] + i]; const double *tab = xs + off[d]; const int n = nd[d];
+  int l = 0, h = n;
+  while (l < h) { int m = (l + h) >> 1; if (tab[m] < x) l = m + 1; else h = m; }
+  int a0, cnt;
+  if (l < n && tab[l] == x) { a0 = l >= 1 ? l - 1 : 0; cnt = (l >= 1 ? 1 : 0) + (l <= n - 2 ? 1 : 0); }
+  else { a0 = l - 1; cnt = (l >= 1 && l <= n - 1) ? 1 : 0; }
+  pt[g.pc_off[d] + i] = (a0 << 2) | cnt;
+}
+#define CSWAP(a, b) do { const unsigned _lo = min(key[a], key[b]), _hi = max(key[a], key[b]); key[a] = _lo; key[b] = _hi; } while (0)
+__global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz1, const int *__restrict__ pt, const double *__restrict__ xs, int o0, int o1, int o2,
+                                                      int m0, int m1, const unsigned *__restrict__ info, const int *__restrict__ IEN, const double *__restrict__ rn,
+                                                      double rho_t, const double *__restrict__ dist, double *__restrict__ signs, double *__restrict__ sdf) {
+  const i64 pl = (i64)g.np[0] * g.np[1], nv = pl * (kz1 - kz0);
+  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= nv) return;
+  const int i = (int)(t % g.np[0]), j = (int)((t / g.np[0]) % g.np[1]), k = kz0 + (int)(t / pl);
+  const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
+  const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
+  double sign = -1.0;
+  if (n0 * n1 * n2 != 0) {
+    unsigned key[8]; bool hotany = false; int nc = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+      key[q] = 0xffffffffu;
+      if (ii < n0 && jj < n1 && kk < n2) {
+        const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
+        if (w != 0xffffffffu) { key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q; hotany = hotany || (w >> 31); nc++; }
+      }
+    }
+    if (nc > 0 && hotany) {      // skip rule (SignDetection.jl:36): some candidate has a nodal density >= rho_t
+      if (nc > 1) {              // ascending element index = the reference's candidate order
+        CSWAP(0, 1); CSWAP(2, 3); CSWAP(4, 5); CSWAP(6, 7); CSWAP(0, 2); CSWAP(1, 3); CSWAP(4, 6); CSWAP(5, 7); CSWAP(1, 2); CSWAP(5, 6);
+        CSWAP(0, 4); CSWAP(1, 5); CSWAP(2, 6); CSWAP(3, 7); CSWAP(2, 4); CSWAP(3, 5); CSWAP(1, 2); CSWAP(3, 4); CSWAP(5, 6);
+      } else {
+#pragma unroll
+        for (int q = 1; q < 8; q++) if (key[q] != 0xffffffffu) { key[0] = key[q]; }
+      }
+      const double x[3] = {g.pc[g.pc_off[0] + i], g.pc[g.pc_off[1] + j], g.pc[g.pc_off[2] + k]};
+      double max_local = 10.0;
+#pragma unroll 1
+      for (int q = 0; q < nc; q++) {
+        const unsigned kq = key[q]; const int e = (int)(kq >> 3), loc = (int)(kq & 7u);
+        const int a[3] = {c0 + (loc & 1), c1 + ((loc >> 1) & 1), c2 + (loc >> 2)};
+        const double l0 = xs[o0 + a[0]], h0 = xs[o0 + a[0] + 1], l1 = xs[o1 + a[1]], h1 = xs[o1 + a[1] + 1], l2 = xs[o2 + a[2]], h2 = xs[o2 + a[2] + 1];
+        const double hx = ex::mul(0.5, ex::sub(h0, l0)), hy = ex::mul(0.5, ex::sub(h1, l1)), hz = ex::mul(0.5, ex::sub(h2, l2));
+        const double cof0 = ex::mul(hy, hz), cof1 = ex::mul(hx, hz), cof2 = ex::mul(hx, hy), det = ex::mul(hx, cof0);
+        double xi[3];
+        if (!(fabs(det) > 0.0)) xi[0] = xi[1] = xi[2] = 10.0;
+        else {
+          const double d0 = ex::dvd(ex::mul(cof0, ex::sub(ex::mul(0.5, ex::add(l0, h0)), x[0])), det);
+          const double d1 = ex::dvd(ex::mul(cof1, ex::sub(ex::mul(0.5, ex::add(l1, h1)), x[1])), det);
+          const double d2 = ex::dvd(ex::mul(cof2, ex::sub(ex::mul(0.5, ex::add(l2, h2)), x[2])), det);
+          xi[0] = ex::sub(0.0, d0); xi[1] = ex::sub(0.0, d1); xi[2] = ex::sub(0.0, d2);
+          if (!(ex::max3abs(d0, d1, d2) < 1.0e3) || !(ex::max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) xi[0] = xi[1] = xi[2] = 10.0;
+        }
+        const double mn = ex::max3abs(xi[0], xi[1], xi[2]);
+        if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
+          const unsigned cls = (info[((i64)a[2] * m1 + a[1]) * m0 + a[0]] >> 29) & 3u;
+          if (cls == 1) sign = 1.0;
+          else if (cls == 0) {
+            double N[8], re[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) re[b] = rn[IEN[8 * (i64)e + b]];
+            ex::hex8_shape(xi, N);
+            if (ex::dot8(N, re) >= rho_t) sign = 1.0;
+          }
+          if (mn < 0.95) break;                                    // :51-59
+          max_local = mn;
+        }
+      }
+    }
+  }
+  const i64 v = (i64)k * pl + (i64)j * g.np[0] + i;
+  if (signs) signs[v] = sign;
+  if (sdf) sdf[v] = dist[v] * sign;
+}
+#undef CSWAP
+
 int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
   if (ctx->nel == 0) FAIL("r2s_set_mesh has not been called");
   const GridDev &g = ctx->g; cudaStream_t st = ctx->stream; i64 nel = ctx->nel; int nen = ctx->nen;
   int kz0 = (int)ctx->k0, kz1 = (int)ctx->k1;
+  if (ctx->lattice && ctx->knobs.sign_lattice && nen == 8) {
+    double *signs = nullptr, *sdf = nullptr;
+    if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
+    if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
+    const int npt = g.np[0] + g.np[1] + g.np[2];
+    CK(ctx->lat_info.reserve(sizeof(unsigned) * (size_t)ctx->lat_ncell));
+    CK(ctx->lat_pt.reserve(sizeof(int) * (size_t)npt));
+    CK(cudaMemsetAsync(ctx->lat_info.p, 0xff, sizeof(unsigned) * (size_t)ctx->lat_ncell, st));
+    double zlo = -1e300, zhi = 1e300;
+    if (kz0 > 0 || kz1 < g.np[2]) { const double m = 3.0 * g.cell; zlo = ctx->h_pc[2][(size_t)kz0] - m; zhi = ctx->h_pc[2][(size_t)kz1 - 1] + m; }
+    const int *lo = ctx->lat_off, *nd = ctx->lat_nd;
+    k_lat_info<<<cdiv(nel, 256), 256, 0, st>>>(nel, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->lat_cell.as<int>(), ctx->ezr.as<double2>(), zlo, zhi, ctx->lat_info.as<unsigned>()); LAUNCH_CHECK();
+    k_lat_pt<<<cdiv(npt, 256), 256, 0, st>>>(g, ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0], nd[1], nd[2], ctx->lat_pt.as<int>()); LAUNCH_CHECK();
+    const i64 nv = (i64)g.np[0] * g.np[1] * (kz1 - kz0);
+    k_sign_lattice<<<cdiv(nv, 256), 256, 0, st>>>(g, kz0, kz1, ctx->lat_pt.as<int>(), ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0] - 1, nd[1] - 1, ctx->lat_info.as<unsigned>(),
+                                                  ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf); LAUNCH_CHECK();
+    return 0;
+  }
   CK(ctx->s_rng.reserve(sizeof(SRange) * (size_t)nel));
   if (nen == 8) CK(ctx->s_el.reserve(sizeof(SignEl) * (size_t)nel));
   CK(ctx->cnt_a.reserve(sizeof(i64) * (size_t)(nel + 1)));
@@ -268,8 +395,7 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   k_sign_ranges<<<cdiv(nel, 256), 256, 0, st>>>(nel, nen, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, g, kz0, kz1, ctx->ezr.as<double2>(), zlo, zhi, ctx->s_rng.as<SRange>(), ntile, ctx->s_el.as<SignEl>()); LAUNCH_CHECK();
   if (r2s_scan_exclusive_i64(ctx, ntile, toff, nel + 1)) return 1;
   i64 nkeys = 0;
-  CK(cudaMemcpyAsync(&nkeys, toff + nel, sizeof(i64), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (r2s_readback(ctx, &nkeys, toff + nel, sizeof(i64))) return 1;
   if (nkeys >= (1ll << 31)) FAIL("sign binning: too many (tile, element) pairs for one slab");
   u64 *sorted = nullptr;
   if (nkeys > 0) {
@@ -284,13 +410,9 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   double *signs = nullptr, *sdf = nullptr;
   if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
   if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
-  const bool cls_shortcut = nen == 8 && getenv("R2S_SIGN_CLASS") && atoi(getenv("R2S_SIGN_CLASS")) == 1;      // opt-in, not yet measured on a GPU
-  if (cls_shortcut)
+  if (nen == 8)      // density-class shortcut: bit-identical to the plain rule (test_sign_density_class_shortcut), always on
     k_sign<8, true><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
                                                              ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
-  else if (nen == 8)
-    k_sign<8, false><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
-                                                       ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);
   else
     k_sign<4, false><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
                                                        ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);

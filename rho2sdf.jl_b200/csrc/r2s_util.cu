@@ -1,5 +1,6 @@
 // r2s_util.cu -- device-wide scan / radix sort plumbing (CUB from the CUDA toolkit) used by the binning steps
 #include <cub/cub.cuh>
+#include <string.h>
 #include "r2s_common.cuh"
 
 int r2s_scan_exclusive_i64(r2s_ctx *ctx, const i64 *in, i64 *out, i64 n) {
@@ -39,6 +40,43 @@ int r2s_sort_f64(r2s_ctx *ctx, double *keys, double *alt, i64 n, double **sorted
   CK(cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, tmp, db, (int)n, 0, 64, ctx->stream));
   ctx->launches += 9;
   *sorted = db.Current();
+  return 0;
+}
+
+int r2s_unique_f64(r2s_ctx *ctx, const double *sorted, double *out, i64 n, i64 *count) {
+  size_t tmp = 0;
+  CK(ctx->counters.reserve(64));
+  i64 *dn = ctx->counters.as<i64>();
+  CK(cub::DeviceSelect::Unique(nullptr, tmp, sorted, out, dn, (int)n, ctx->stream));
+  CK(ctx->cubtmp.reserve(tmp));
+  CK(cub::DeviceSelect::Unique(ctx->cubtmp.p, tmp, sorted, out, dn, (int)n, ctx->stream));
+  ctx->launches += 2;
+  return r2s_readback(ctx, count, dn, sizeof(i64));
+}
+
+// ------------------------------------------------------------------------------------------------ small read-backs
+__global__ void k_readback(const unsigned *__restrict__ src, unsigned *__restrict__ dst, int nwords) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+size_t r2s_rb_put(r2s_ctx *ctx, const void *src_dev, size_t bytes) {
+  const size_t words = (bytes + 3) / 4, off = ctx->rb_off;
+  if (!ctx->rb_host || off + words * 4 > R2S_RB_BYTES || ((size_t)src_dev & 3)) { ctx->err = "read-back buffer overflow / misaligned source"; return (size_t)-1; }
+  const int nb = words > 4096 ? 8 : 1;
+  k_readback<<<nb, 256, 0, ctx->stream>>>((const unsigned *)src_dev, (unsigned *)((char *)ctx->rb_dev + off), (int)words);
+  if (cudaGetLastError() != cudaSuccess) { ctx->err = "read-back kernel launch failed"; return (size_t)-1; }
+  ctx->rb_off = (off + words * 4 + 7) & ~(size_t)7;
+  return off;
+}
+int r2s_rb_sync(r2s_ctx *ctx) {
+  ctx->rb_off = 0;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int r2s_readback(r2s_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+  const size_t off = r2s_rb_put(ctx, src_dev, bytes);
+  if (off == (size_t)-1) return 1;
+  if (r2s_rb_sync(ctx)) return 1;
+  memcpy(dst_host, r2s_rb_at(ctx, off), bytes);
   return 0;
 }
 

@@ -102,6 +102,24 @@ def lattice_hex8(n):
     return X, IEN
 
 
+def graded_lattice_hex8(n, seed=3, holes=0.12):
+    """A tensor-product lattice mesh that is NOT the plain cube: graded (non-uniform) spacing per axis, ~12 % of the cells missing,
+    element and node numbering shuffled.  Returns X, IEN (1-based), rho (element densities of the SIMP field at the cell centres)."""
+    rng = np.random.default_rng(seed)
+    X0, IEN0, rho0 = simp_hex8(n)
+    ax = [np.concatenate([[0.0], np.cumsum(rng.uniform(0.6, 1.5, n))]) for _ in range(3)]
+    X = np.stack([ax[0][X0[:, 0].astype(int)], ax[1][X0[:, 1].astype(int)], ax[2][X0[:, 2].astype(int)]], axis=1)
+    keep = rng.random(IEN0.shape[0]) >= holes
+    order = rng.permutation(np.nonzero(keep)[0])
+    IEN, rho = IEN0[order], rho0[order]
+    used = np.unique(IEN)
+    perm = rng.permutation(used.size)
+    new_id = np.zeros(X.shape[0] + 1, dtype=np.int64)
+    new_id[used] = perm + 1
+    Xn = np.zeros((used.size, 3)); Xn[perm] = X[used - 1]
+    return Xn, np.ascontiguousarray(new_id[IEN]), rho
+
+
 SCHLAFLI = np.array([[1, 2, 3, 7], [1, 6, 2, 7], [1, 3, 4, 7], [1, 4, 8, 7], [1, 5, 6, 7], [1, 8, 5, 7]]) - 1   # SimpleCubeWithSchlafli.jl:22-29
 
 

@@ -103,20 +103,16 @@ def test_grid_ctor_matches_reference_formula(r2s):
     assert P.shape == (4913, 3) and np.allclose(P[1] - P[0], [g.cell_size, 0, 0])
 
 
-def test_tuning_knobs_named_by_the_tools_exist_in_the_sources():
-    """tools/ab_project.py and the opt-in GPU tests select kernel variants through environment knobs; a misspelt knob would silently
-    time / test the default kernels.  Every knob they name must be read somewhere in csrc/."""
-    import importlib.util
+def test_tuning_knobs_named_by_the_tests_exist_in_the_sources():
+    """The GPU tests and tools select kernel paths through environment knobs that r2s_create reads once; a misspelt knob would silently
+    test the default path.  Every knob they name must be parsed in csrc/, and every knob parsed in csrc/ must be exercised by a test."""
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("ab_project", os.path.join(root, "tools", "ab_project.py"))
-    ab = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(ab)
     src = "".join(open(os.path.join(root, "rho2sdf.jl_b200", "csrc", f)).read() for f in os.listdir(os.path.join(root, "rho2sdf.jl_b200", "csrc")) if f.endswith((".cu", ".cuh")))
-    read = set(re.findall(r'getenv\("(R2S_[A-Z0-9_]+)"\)', src))
-    named = set(ab.KNOBS)
-    for spec_ in ab.DEFAULT.split(";"):
-        _, _, kv = spec_.partition(":")
-        named |= {item.partition("=")[0] for item in kv.split(",") if item}
-    named |= set(re.findall(r'"(R2S_(?:PROJ|STENCIL|VOLCUT)[A-Z0-9_]*)"', open(os.path.join(root, "tests", "test_gpu_parity.py")).read()))
+    read = set(re.findall(r'(?:getenv|knob)\("(R2S_[A-Z0-9_]+)"', src))
+    named = set()
+    for f in ("tests/test_gpu_parity.py", "tests/slab_parity_ranks.py", "tests/test_slabs.py", "tools/ab_variants.py"):
+        named |= set(re.findall(r'"(R2S_[A-Z0-9_]+)"', open(os.path.join(root, f)).read()))
+    named -= {"R2S_TEST_OPTIN"}
     assert named <= read, sorted(named - read)
+    assert read <= named, "knobs without a test: %s" % sorted(read - named)

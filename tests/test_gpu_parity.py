@@ -34,7 +34,7 @@ def check_distances(r2s, mesh, X, IEN, grid, rn, rt, delta):
     assert np.array_equal(d[far], od[far])
     assert np.max(np.abs(d - od)) <= DIST_TOL * grid.cell_size
     rep = mesh.ctx.report()
-    assert rep.n_pairs == st["pairs"]
+    assert rep.n_pairs == st["pairs"] and rep.n_pairs_pruned == 0      # with xp every pair is projected
     # pairs whose iteration ran into its cap are still used (the reference uses NLopt's point even on :FAILURE,
     # ComputeCoordsOnIso.jl:82-86); they must be rare on both sides
     assert rep.n_not_converged <= 2 + 1e-5 * rep.n_pairs and st["not_converged"] <= 2 + 1e-5 * st["pairs"]
@@ -42,9 +42,11 @@ def check_distances(r2s, mesh, X, IEN, grid, rn, rt, delta):
     P = r2s.generateGridPoints(grid)
     near = ~far
     assert np.max(np.abs(np.linalg.norm(P[near] - xp[near], axis=1) - d[near])) <= 1e-9 * grid.cell_size
-    # the pipeline's path (no xp: crossing-element faces folded into the pair buffer) must give the very same distances
+    # the pipeline's path (no xp: pair list with pruning, atomicMin, crossing-element faces folded into the pair buffer) must give the
+    # same distances; the two paths are different kernels (FMA contraction may differ in the last bit), hence 1e-11 h instead of equality
     d2, _ = r2s.evalDistances(mesh, grid, None, rn, rt, delta_factor=delta, want_xp=False)
-    assert np.array_equal(d, d2)
+    assert np.array_equal(d > 1e9, d2 > 1e9) and np.max(np.abs(d - d2)) <= 1e-11 * grid.cell_size
+    assert np.max(np.abs(d2 - od)) <= DIST_TOL * grid.cell_size
     return d, od
 
 
@@ -352,66 +354,48 @@ def _mixed_mesh(n=10):
 
 
 def test_mixed_box_and_distorted_hexes(r2s, monkeypatch):
-    """A mesh holding both kinds of HEX8 elements -- axis-aligned boxes (HexBox variant of the projection kernel) and
-    distorted hexes (general trilinear variant): both launches run, each leaving the other kind alone; sending everything
-    through the general kernel (R2S_PROJ_BOX=0) gives the same field."""
+    """A mesh holding both kinds of HEX8 elements -- axis-aligned boxes (pair-list path with lower-bound pruning) and distorted hexes
+    (general trilinear chunk kernel): both run, each leaving the other kind alone; sending everything through the general kernel
+    (R2S_PROJ_BOX=0, read when the context is created) gives the same field."""
     n = 10
     X, IEN, rho = _mixed_mesh(n)
     mesh = r2s.Mesh(X, IEN, rho)
     grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
     rn = r2s.DenseInNodes(mesh, rho)
     d, od = check_distances(r2s, mesh, X, IEN, grid, rn, 0.5, 1.1)
+    assert 0 < mesh.ctx.report().n_pairs_pruned < mesh.ctx.report().n_pairs
+    mesh.ctx.close()
     monkeypatch.setenv("R2S_PROJ_BOX", "0")
-    d0, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+    mesh0 = r2s.Mesh(X, IEN, rho)
+    d0, _ = r2s.evalDistances(mesh0, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
+    assert mesh0.ctx.report().n_pairs_pruned == 0
     assert np.max(np.abs(d0 - od)) <= DIST_TOL * grid.cell_size and np.max(np.abs(d0 - d)) <= 1e-11 * grid.cell_size
-    mesh.ctx.close()
+    mesh0.ctx.close()
 
 
-def test_lane_refill_projection_variant(r2s, monkeypatch):
-    """The opt-in lane-refill projection (R2S_PROJ=1: per-voxel atomicMin, AABB lower-bound pruning) on the mixed mesh."""
-    n = 10
-    X, IEN, rho = _mixed_mesh(n)
-    mesh = r2s.Mesh(X, IEN, rho)
-    grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
-    rn = r2s.DenseInNodes(mesh, rho)
-    od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.5, 1.1, want_xp=False)
-    monkeypatch.setenv("R2S_PROJ", "1")
-    d1, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
-    assert np.max(np.abs(d1 - od)) <= DIST_TOL * grid.cell_size
-    mesh.ctx.close()
-
-
-OPTIN = pytest.mark.skipif(os.environ.get("R2S_TEST_OPTIN") != "1", reason="opt-in kernel variants that have not run on a GPU yet: set R2S_TEST_OPTIN=1")
-
-
-@OPTIN
-@pytest.mark.parametrize("knobs", [{"R2S_PROJ_FAST": "1"}, {"R2S_PROJ_P1": "1"}, {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1"},
-                                   {"R2S_PROJ_FAST": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "8"}, {"R2S_PROJ": "1", "R2S_PROJ_FAST": "1"},
-                                   {"R2S_PROJ_UNI": "1"}, {"R2S_PROJ_UNI": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"}, {"R2S_PROJ": "1", "R2S_PROJ_UNI": "1"},
-                                   {"R2S_PROJ_SCALED": "1"}, {"R2S_PROJ_SCALED": "1", "R2S_PROJ_P1": "1", "R2S_PROJ_BOX_MINB": "6"},
-                                   {"R2S_PROJ_ATOM": "1"}, {"R2S_PROJ_ATOM": "1", "R2S_PROJ_SCALED": "1"}])
-def test_optin_projection_variants(r2s, monkeypatch, knobs):
-    """FAST restoration / per-element phase-1 table (r2s_iso.cuh): on the host build they reproduce the exact variants bit for bit
-    (tests/test_iso_host.py); here the kernels that carry them, on the mixed mesh and on a replica of the bench workload."""
-    for X, IEN, rho, n in (_mixed_mesh(10) + (10,), simp_hex8(16) + (16,)):
+@pytest.mark.parametrize("case", ["simp16", "simp24_coarse_grid", "simp12_fine_grid", "mixed"])
+def test_projection_pruning_is_exact(r2s, monkeypatch, case):
+    """The pair-list path skips (element, point) pairs whose lower bound (distance to the tight box of the element's iso-patch) is not
+    below the point's current minimum.  The result of evalDistances is a minimum over the pairs, so pruning must not change a single
+    bit: R2S_PROJ_PRUNE=0 (every pair projected) against the default, on grids coarser and finer than the elements."""
+    X, IEN, rho, nmax = {"simp16": simp_hex8(16) + (32,), "simp24_coarse_grid": simp_hex8(24) + (30,), "simp12_fine_grid": simp_hex8(12) + (60,),
+                         "mixed": _mixed_mesh(10) + (20,)}[case]
+    res = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("R2S_PROJ_PRUNE", knob)
         mesh = r2s.Mesh(X, IEN, rho)
-        grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
+        grid = r2s.Grid(X.min(0), X.max(0), nmax, 3)
         rn = r2s.DenseInNodes(mesh, rho)
-        d_ref, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
-        od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.5, 1.1, want_xp=False)
-        for k, v in knobs.items():
-            monkeypatch.setenv(k, v)
-        d, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, delta_factor=1.1, want_xp=False)
-        for k in knobs:
-            monkeypatch.delenv(k)
-        assert np.max(np.abs(d - od)) <= DIST_TOL * grid.cell_size
-        if not ({"R2S_PROJ", "R2S_PROJ_UNI", "R2S_PROJ_SCALED", "R2S_PROJ_ATOM"} & set(knobs)):
-            assert np.array_equal(d, d_ref)                 # same arithmetic as the default kernels
+        res[knob] = [r2s.evalDistances(mesh, grid, None, rn, rt, delta_factor=df, want_xp=False)[0] for rt, df in ((0.5, 1.1), (0.3, 2.5))]
+        rep = mesh.ctx.report()
+        assert (rep.n_pairs_pruned > 0) == (knob == "1") and rep.n_pairs_pruned < rep.n_pairs
         mesh.ctx.close()
+    for a, b in zip(res["1"], res["0"]):
+        assert np.array_equal(a, b)
+    od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.3, 2.5, want_xp=False, nthreads=oracle.max_threads())
+    assert np.max(np.abs(res["1"][1] - od)) <= DIST_TOL * grid.cell_size
 
 
-
-@OPTIN
 def test_pipelined_host_buffer_calls(r2s):
     """r2s_pipeline_slab_begin / _wait: three consecutive calls on alternating buffer sets return what the synchronous call returns."""
     import ctypes as C
@@ -444,36 +428,54 @@ def test_pipelined_host_buffer_calls(r2s):
     mesh.ctx.close()
 
 
-@OPTIN
-def test_factorised_stencil_variant(r2s, monkeypatch):
-    """R2S_STENCIL=3: the 81-point mat-vec with factorised weights w[m2] * w[dz^2] (27 instead of 81 FMA per output and plane)."""
-    monkeypatch.setenv("R2S_STENCIL", "3")
-    n = 12
+def test_simp_hex8_64_pipeline_vs_oracle(r2s):
+    """The 64^3 replica of BASELINE configs[4] through ONE device-resident pipeline call against the CPU oracle's pipeline on the same
+    inputs (bench.py repeats this on the 96^3 replica and prints it as `parity`)."""
+    n = 64
     X, IEN, rho = simp_hex8(n)
     mesh = r2s.Mesh(X, IEN, rho)
     grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
     rn = r2s.DenseInNodes(mesh, rho)
-    d, _ = r2s.evalDistances(mesh, grid, None, rn, 0.5, want_xp=False)
-    sdf = d * r2s.Sign_Detection(mesh, grid, None, rn, 0.5)
-    r2s.remove_sdf_artifacts(sdf, grid, mesh=mesh)
-    check_rbf(r2s, mesh, grid, sdf, mesh.V_domain * mesh.V_frac)
+    assert mesh.is_lattice
+    sdf, fine, rep = _run_pipeline(r2s, mesh, grid, rn)
+    nt = oracle.max_threads()
+    assert np.array_equal(rn, oracle.nodal_densities(X, IEN, rho))
+    od, _, _ = oracle.eval_distances(X, IEN, grid, rn, 0.5, 1.1, nthreads=nt, want_xp=False)
+    osg = oracle.sign_detection(X, IEN, grid, rn, 0.5, nthreads=nt)
+    osdf, onf = oracle.remove_artifacts(od * osg, grid)
+    assert np.array_equal(np.abs(sdf) > 1e9, np.abs(osdf) > 1e9) and np.array_equal(np.signbit(sdf), np.signbit(osdf)) and rep.n_flipped == onf
+    assert np.max(np.abs(sdf - osdf)) <= DIST_TOL * grid.cell_size
+    ofine, oinfo = oracle.rbf_smoothing(osdf, grid, True, 2, mesh.V_domain * mesh.V_frac, mode=0, nthreads=nt)
+    assert rep.cg_iters == oinfo["cg_iters"] and abs(rep.th - oinfo["th"]) <= RBF_TOL * grid.cell_size
+    assert np.max(np.abs(fine - ofine)) <= RBF_TOL * grid.cell_size
     mesh.ctx.close()
 
 
-@OPTIN
-def test_sign_density_class_shortcut(r2s, monkeypatch):
-    """R2S_SIGN_CLASS=1: elements whose interpolated density cannot cross rho_t skip the shape-function evaluation; the sign field must be
-    bit-identical to the default kernel's (and the oracle's) on structured and unstructured meshes."""
-    cases = [simp_hex8(16) + (32,), _mixed_mesh(10) + (20,)] + [load_mesh(nm) + (40,) for nm in ("sphere", "chapadlo")]
-    for X, IEN, rho, nmax in cases:
-        mesh = r2s.Mesh(X, IEN, rho)
-        grid = r2s.Grid(*r2s.getMesh_AABB(X), nmax, 3)
-        rn = r2s.DenseInNodes(mesh, rho)
-        for rt in (0.5, 0.3):
-            monkeypatch.delenv("R2S_SIGN_CLASS", raising=False)
-            s0 = r2s.Sign_Detection(mesh, grid, None, rn, rt)
-            monkeypatch.setenv("R2S_SIGN_CLASS", "1")
-            s1 = r2s.Sign_Detection(mesh, grid, None, rn, rt)
-            assert np.array_equal(s0, s1)
-        monkeypatch.delenv("R2S_SIGN_CLASS", raising=False)
-        mesh.ctx.close()
+def test_sign_lattice_fast_path(r2s, monkeypatch):
+    """Sign_Detection_HEX8 on tensor-product lattice meshes: the list-free kernel (cells around a point from per-axis tables) against
+    the general kernel (R2S_SIGN_LATTICE=0: sorted candidate lists, density-class shortcut) and the oracle -- bit-identical signs on the
+    plain cube, on a graded lattice with holes and shuffled numbering, and on sphere.mat; unstructured meshes never take it."""
+    from fixtures import graded_lattice_hex8
+    cases = [simp_hex8(16) + (32, True), graded_lattice_hex8(12) + (30, True), load_mesh("sphere") + (24, True), _mixed_mesh(10) + (20, False),
+             load_mesh("chapadlo") + (40, False)]
+    for X, IEN, rho, nmax, lattice in cases:
+        res = {}
+        for knob in ("1", "0"):
+            monkeypatch.setenv("R2S_SIGN_LATTICE", knob)
+            mesh = r2s.Mesh(X, IEN, rho)                     # knobs are read when the context is created
+            assert mesh.is_lattice == lattice
+            grid = r2s.Grid(*r2s.getMesh_AABB(X), nmax, 3)
+            rn = r2s.DenseInNodes(mesh, rho)
+            res[knob] = [r2s.Sign_Detection(mesh, grid, None, rn, rt) for rt in (0.5, 0.3)]
+            if knob == "1":      # a z-slab of the lattice path equals the same planes of the full run
+                nz, pl = int(grid.N[2]) + 1, int(grid.N[0] + 1) * int(grid.N[1] + 1)
+                mesh.ctx.check(mesh.ctx.lib.r2s_set_slab(mesh.ctx.h, nz // 3, 2 * nz // 3))
+                s_slab = r2s.Sign_Detection(mesh, grid, None, rn, 0.5)
+                assert np.array_equal(s_slab[nz // 3 * pl:2 * nz // 3 * pl], res[knob][0][nz // 3 * pl:2 * nz // 3 * pl])
+            mesh.ctx.close()
+        monkeypatch.delenv("R2S_SIGN_LATTICE")
+        for q, rt in enumerate((0.5, 0.3)):
+            assert np.array_equal(res["1"][q], res["0"][q])
+            if X.shape[0] < 10000:
+                assert np.array_equal(res["1"][q], oracle.sign_detection(X, IEN, grid, rn, rt))
+            assert (res["1"][q] > 0).any() and (res["1"][q] < 0).any()

@@ -83,12 +83,14 @@ def test_slab_host_logic_gloo_world2(tmp_path):
 
 
 @pytest.mark.gpu
-def test_slab_parity_multi_gpu():
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_slab_parity_multi_gpu(p2p):
+    """p2p = 1: scalar all-reduces and CG halo planes over the peer-memory mailbox; R2S_P2P=0: everything through NCCL."""
     import torch
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs at least 2 GPUs (run tests/slab_parity_ranks.py under torchrun with gpurun --gpus 2)")
     world = 2 if ngpu < 4 else 4
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29732",
-                          os.path.join(ROOT, "tests", "slab_parity_ranks.py"), "48"], capture_output=True, text=True, timeout=900)
+                          os.path.join(ROOT, "tests", "slab_parity_ranks.py"), "48"], capture_output=True, text=True, timeout=900, env=dict(os.environ, R2S_P2P=p2p))
     assert out.returncode == 0 and "SLAB PARITY OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
