@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <vector>
 #include "r2s_common.cuh"
 
@@ -34,6 +36,28 @@ struct NcclApi {
   const char *(*GetErrorString)(int);
 };
 static NcclApi g_nccl;
+// ---- in-process slab group -------------------------------------------------------------------------------------------------
+// r2s_multi_* (r2s_multi.cu) runs one context per slab inside ONE process, each driven by its own host thread.  The ranks then
+// see each other's device memory directly (peer access between devices, plain pointers on one device), so nothing here needs NCCL
+// or CUDA IPC: scalar all-reduces and the CG halo planes use the same mailbox kernels as the multi-process path, bulk exchanges
+// (halo planes of the smoothing fields, the all-gather of the artifact removal) are cudaMemcpyPeerAsync pulls ordered by events,
+// with two host barriers per exchange ("source ready" / "everybody has read").  Several slabs may share one GPU (tests on a 1-GPU box).
+struct LocalGroup {
+  int n = 0; r2s_ctx *ctx[64];
+  std::mutex mu; std::condition_variable cv; int arrived = 0; unsigned long gen = 0; bool failed = false;
+  const void *src[64]; size_t cnt[64]; cudaEvent_t ev_ready[64], ev_done[64];
+  // returns false when some rank has failed (the caller must bail out instead of waiting for it)
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (failed) return false;
+    const unsigned long my = gen;
+    if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); return true; }
+    cv.wait(lk, [&] { return gen != my || failed; });
+    return !failed;
+  }
+};
+void r2s_local_group_abort(LocalGroup *g) { if (!g) return; std::lock_guard<std::mutex> lk(g->mu); g->failed = true; g->cv.notify_all(); }
+#define LBAR(lg) do { if (!(lg)->barrier()) FAIL("in-process slab group: another slab failed"); } while (0)
 static int p2p_setup(r2s_ctx *ctx);
 static void p2p_teardown(r2s_ctx *ctx);
 static const char *nccl_load() {
@@ -81,18 +105,21 @@ extern "C" int r2s_comm_init(r2s_ctx *ctx, int rank, int nranks, const void *id1
 }
 extern "C" int r2s_comm_destroy(r2s_ctx *ctx) {
   if (!ctx) return 1;
+  if (ctx->lg) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); if (ctx->p2p_peer_box_dev) cudaFree(ctx->p2p_peer_box_dev); if (ctx->p2p_box) cudaFree(ctx->p2p_box);
+                 ctx->p2p_box = nullptr; ctx->p2p_peer_box_dev = nullptr; ctx->p2p = false; ctx->p2p_c_local = nullptr; ctx->p2p_c_peer[0] = ctx->p2p_c_peer[1] = nullptr; ctx->lg = nullptr; }
   if (ctx->comm && g_nccl.lib) { cudaStreamSynchronize(ctx->stream); p2p_teardown(ctx); g_nccl.CommDestroy((nccl_comm)ctx->comm); }
   ctx->comm = nullptr; ctx->rank = 0; ctx->nranks = 1;
   return 0;
 }
 
 // fuse the collectives issued between the two calls into one NCCL launch (nested groups are allowed)
-int r2s_group_start(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupStart()); return 0; }
-int r2s_group_end(r2s_ctx *ctx) { if (ctx->nranks > 1) NCK(g_nccl.GroupEnd()); return 0; }
+int r2s_group_start(r2s_ctx *ctx) { if (ctx->nranks > 1 && !ctx->lg) NCK(g_nccl.GroupStart()); return 0; }
+int r2s_group_end(r2s_ctx *ctx) { if (ctx->nranks > 1 && !ctx->lg) NCK(g_nccl.GroupEnd()); return 0; }
 // ---- collectives used by the pipeline; all are no-ops for a single rank ----------------------------------------------
 static int p2p_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind);
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/) {
   if (ctx->nranks <= 1) return 0;
+  if (ctx->lg && count > 4) FAIL("in-process slab group: all-reduce of more than 4 words");
   if (ctx->p2p && count <= 4) return p2p_allreduce(ctx, buf, count, kind);
   int dt = kind == 0 ? NC_F64 : (kind == 1 || kind == 4 ? NC_UINT64 : NC_UINT32);
   int op = (kind == 0 || kind == 1) ? NC_SUM : (kind == 3 ? NC_MIN : NC_MAX);
@@ -100,8 +127,42 @@ int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1
   ctx->collectives++;
   return 0;
 }
+// local (in-process) bulk exchanges: pull from the peers' buffers between two host barriers
+static int local_pull_begin(r2s_ctx *ctx, const void *my_src, size_t my_bytes) {
+  LocalGroup *lg = ctx->lg;
+  lg->src[ctx->rank] = my_src; lg->cnt[ctx->rank] = my_bytes;
+  CK(cudaEventRecord(lg->ev_ready[ctx->rank], ctx->stream));      // everything this rank has enqueued so far (its source data) precedes the peers' pulls
+  LBAR(lg);
+  return 0;
+}
+static int local_pull(r2s_ctx *ctx, int peer, void *dst, const void *src, size_t bytes) {
+  LocalGroup *lg = ctx->lg;
+  CK(cudaStreamWaitEvent(ctx->stream, lg->ev_ready[peer], 0));
+  CK(cudaMemcpyPeerAsync(dst, ctx->device, src, lg->ctx[peer]->device, bytes, ctx->stream));
+  return 0;
+}
+static int local_pull_end(r2s_ctx *ctx, const int *readers, int nreaders) {
+  LocalGroup *lg = ctx->lg;
+  CK(cudaEventRecord(lg->ev_done[ctx->rank], ctx->stream));       // my pulls are enqueued behind this point ...
+  LBAR(lg);
+  for (int i = 0; i < nreaders; i++) CK(cudaStreamWaitEvent(ctx->stream, lg->ev_done[readers[i]], 0));      // ... and my later writes wait for the ranks that read from me
+  ctx->collectives++;
+  return 0;
+}
+static int local_allgather(r2s_ctx *ctx, const void *send, void *recv, size_t bytes) {
+  LocalGroup *lg = ctx->lg;
+  if (local_pull_begin(ctx, send, bytes)) return 1;
+  int readers[64], nr = 0;
+  for (int q = 0; q < lg->n; q++) {
+    char *dst = (char *)recv + (size_t)q * bytes;
+    if (q == ctx->rank) { if (dst != (const char *)send) CK(cudaMemcpyAsync(dst, send, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
+    else { if (local_pull(ctx, q, dst, lg->src[q], bytes)) return 1; readers[nr++] = q; }
+  }
+  return local_pull_end(ctx, readers, nr);
+}
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count) {
   if (ctx->nranks <= 1) { CK(cudaMemcpyAsync(recv, send, count * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream)); return 0; }
+  if (ctx->lg) return local_allgather(ctx, send, recv, count * sizeof(unsigned));
   NCK(g_nccl.AllGather(send, recv, count, NC_UINT32, (nccl_comm)ctx->comm, ctx->stream));
   ctx->collectives++;
   return 0;
@@ -111,6 +172,22 @@ int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t
 int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k1, int nz, int below, int above) {
   if (ctx->nranks <= 1) return 0;
   const int r = ctx->rank;
+  if (ctx->lg) {      // in-process: pull the neighbours' boundary planes of the same (globally indexed) field
+    LocalGroup *lg = ctx->lg;
+    if (local_pull_begin(ctx, a, 0)) return 1;
+    int readers[2], nrd = 0;
+    if (r + 1 < ctx->nranks) {
+      const int nr = above < nz - k1 ? above : nz - k1;      // planes [k1, k1 + nr) are the upper neighbour's first planes
+      if (nr > 0 && local_pull(ctx, r + 1, a + (i64)k1 * plane_elems, (const float *)lg->src[r + 1] + (i64)k1 * plane_elems, sizeof(float) * (size_t)nr * plane_elems)) return 1;
+      readers[nrd++] = r + 1;
+    }
+    if (r > 0) {
+      const int nr = below < k0 ? below : k0;
+      if (nr > 0 && local_pull(ctx, r - 1, a + (i64)(k0 - nr) * plane_elems, (const float *)lg->src[r - 1] + (i64)(k0 - nr) * plane_elems, sizeof(float) * (size_t)nr * plane_elems)) return 1;
+      readers[nrd++] = r - 1;
+    }
+    return local_pull_end(ctx, readers, nrd);
+  }
   NCK(g_nccl.GroupStart());
   if (r + 1 < ctx->nranks) {
     // the upper neighbour needs my top `below` planes; I need its bottom `above` planes
@@ -257,6 +334,16 @@ static void p2p_teardown(r2s_ctx *ctx) {
 // ---- CG halo planes of c over peer memory ------------------------------------------------------------------------------
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
   if (!ctx->p2p) return 0;
+  if (ctx->lg) {      // in-process: the neighbours' arrays are plain pointers, re-read on every call (they may have been re-allocated)
+    LocalGroup *lg = ctx->lg;
+    lg->src[ctx->rank] = c;
+    LBAR(lg);
+    ctx->p2p_c_peer[0] = ctx->rank > 0 ? (void *)lg->src[ctx->rank - 1] : nullptr;
+    ctx->p2p_c_peer[1] = ctx->rank + 1 < ctx->nranks ? (void *)lg->src[ctx->rank + 1] : nullptr;
+    ctx->p2p_c_local = c;
+    LBAR(lg);      // nobody overwrites src[] before everybody has read it
+    return 0;
+  }
   // collective decision: remap if any rank's buffer moved
   unsigned long long *w = (unsigned long long *)((char *)ctx->p2p_box + sizeof(P2PBox) + 40);
   unsigned long long changed = (ctx->p2p_c_local != (void *)c) ? 1ull : 0ull;

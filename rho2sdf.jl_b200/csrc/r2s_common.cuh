@@ -68,6 +68,8 @@ struct Knobs {
   int proj_prune = 1;     // R2S_PROJ_PRUNE=0: the box projection evaluates every (element, point) pair (no lower-bound pruning)
 };
 
+struct LocalGroup;      // in-process slab group (r2s_multi_*): r2s_comm.cu
+
 struct r2s_ctx {
   int device = 0;
   Knobs knobs;
@@ -101,6 +103,7 @@ struct r2s_ctx {
   bool has_grid = false;
   GridDev g;
   i64 k0 = 0, k1 = 0;                       // slab of coarse planes handled by this context
+  LocalGroup *lg = nullptr;                  // set when this context is one slab of an in-process group (threads instead of processes, no NCCL)
   void *comm = nullptr; int rank = 0, nranks = 1; i64 collectives = 0; std::vector<int> slab_k0;
   // peer-memory fast path for the latency-critical exchanges (scalar all-reduces, CG halo planes): every rank maps every
   // peer's mailbox (and the CG vector c) through CUDA IPC and writes into it directly over NVLink (r2s_comm.cu)
@@ -183,3 +186,7 @@ int r2s_group_end(r2s_ctx *ctx);
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count);
 int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k1, int nz, int below, int above);
 extern "C" int r2s_comm_destroy(r2s_ctx *ctx);
+// in-process groups (r2s_multi.cu drives them): one context per slab, one host thread per context
+LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err);
+void r2s_local_group_destroy(LocalGroup *g);
+void r2s_local_group_abort(LocalGroup *g);      // a rank failed: wake everybody waiting at a host barrier
