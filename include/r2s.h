@@ -12,11 +12,13 @@
  *     grid point linear id = k*(N1+1)*(N2+1) + j*(N1+1) + i with i fastest (src/MeshGrid/Grid.jl:84-90)
  *   - all pointer arguments are HOST pointers unless the name ends in _dev; the caller owns every buffer,
  *     the library never keeps a host pointer after the call returns; device memory belongs to the context
- *   - calls are synchronous; a context is not re-entrant; one context drives one GPU (one process per GPU)
+ *   - calls are synchronous; a context is not re-entrant; one r2s_ctx drives one GPU.  Several GPUs: either r2s_multi (ONE host call
+ *     drives all GPUs of the box from one process -- what the Julia drop-in uses), or one process per GPU with r2s_comm_init
  *   - there is no CPU fallback: without a CUDA device every call fails with an error
  */
 #ifndef R2S_H
 #define R2S_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -97,14 +99,16 @@ int r2s_result_ptrs_dev(r2s_ctx *ctx, void **sdf_dev, void **fine_sdf_dev);
 
 /* ---- z-slab sharding (one process per GPU) ------------------------------------------ */
 /* restrict this context to coarse planes k in [k0,k1) of the grid set by r2s_set_grid (halo planes are handled
- * internally); k0 = 0, k1 = N3+1 restores the full grid */
+ * internally); k0 = 0, k1 = N3+1 restores the full grid.  While a slab is set, r2s_eval_distances / r2s_sign_detection fill only the
+ * planes [k0,k1) of their whole-grid outputs, and the whole-grid stages r2s_remove_artifacts / r2s_rbf_smoothing refuse to run.
+ * r2s_set_grid resets the slab; on a multi-rank context r2s_set_slab must be called again before the next pipeline call. */
 int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1);
 /* Slab communicator (NCCL, bound with dlopen; see csrc/r2s_comm.cu).  Rank 0 makes a 128-byte id with r2s_comm_unique_id,
  * the host program carries it to the other ranks (torch.distributed / MPI / a file), every rank calls r2s_comm_init and
  * then r2s_set_slab (collective: the ranks exchange their plane ranges, which must tile [0, N3+1) in rank order with at
  * least 3 planes each).  From then on r2s_pipeline_resident / r2s_pipeline_slab are collective calls: halo planes of the
  * smoothing fields travel by ncclSend/ncclRecv between z-neighbours, dot products / extrema / volume sums by all-reduce,
- * and the 1-bit interior mask of the artifact removal by one all-gather. */
+ * and the boundary planes (labels, sizes) of the artifact removal by one all-gather. */
 int r2s_comm_unique_id(void *id128);
 int r2s_comm_init(r2s_ctx *ctx, int rank, int nranks, const void *id128);
 int r2s_comm_destroy(r2s_ctx *ctx);
@@ -117,6 +121,31 @@ int r2s_pipeline_slab(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, do
  * the library until _wait(ticket) returns -- alternate between two sets of buffers. */
 int r2s_pipeline_slab_begin(r2s_ctx *ctx, const r2s_params *p, const double *rho_n, double *sdf_slab, float *fine_slab, r2s_report *rep, int *ticket);
 int r2s_pipeline_slab_wait(r2s_ctx *ctx, int ticket);
+
+/* ---- all GPUs of the box from ONE host call (csrc/r2s_multi.cu) ------------------------------------------------------------ */
+/* The single-process counterpart of the slab communicator above, made for the Julia drop-in (rho2sdf() is one call in one process,
+ * RhoToSDF.jl:116-242): one context and one library-internal host thread per entry of device_ids, the planes cut into z-slabs
+ * (re-cut by measured cost after every call), exchanges over peer memory (NVLink) -- no NCCL, no mpiexec.  device_ids may repeat
+ * (several slabs on one GPU; used by the tests on one-GPU boxes).  Host arrays are WHOLE-GRID arrays; every slab writes its planes. */
+typedef struct r2s_multi r2s_multi;
+int r2s_multi_create(r2s_multi **m, const int *device_ids, int ndev);
+void r2s_multi_destroy(r2s_multi *m);
+const char *r2s_multi_last_error(r2s_multi *m);
+int r2s_multi_size(r2s_multi *m);
+/* context of one slab; slab 0 serves the pre-timer stages that work on the whole mesh (r2s_mesh_volume, r2s_nodal_densities,
+ * r2s_find_threshold, r2s_edge_length_stats) */
+r2s_ctx *r2s_multi_context(r2s_multi *m, int slab);
+int r2s_multi_set_mesh(r2s_multi *m, int nen, int64_t nnp, const double *X, int64_t nel, const int64_t *IEN);
+int r2s_multi_set_grid(r2s_multi *m, const double amin[3], const double amax[3], const int64_t N[3], double cell_size);
+int r2s_multi_slab_planes(r2s_multi *m, int64_t *cuts /* ndev + 1 plane boundaries */);
+int r2s_multi_set_rebalance(r2s_multi *m, int on);      /* 1 (default): re-cut the slabs by measured cost after every pipeline call */
+/* the timed region of rho2sdf() (RhoToSDF.jl:164-227): sdf_dists[ngp], fine_sdf[prod(N*smooth+1)]; rep: stage times = max over slabs */
+int r2s_multi_pipeline(r2s_multi *m, const r2s_params *p, const double *rho_n, double *sdf_dists, float *fine_sdf, r2s_report *rep);
+/* exportSdfToVTI for a result that lives on several GPUs: <base>_<slab>.vti pieces + <base>.pvti (one slab: <base>.vti) */
+int r2s_multi_export_vti(r2s_multi *m, const char *base, const char *label, int which);
+/* page-lock / release a caller-owned host array (cudaHostRegister): result arrays pinned once download asynchronously and faster */
+int r2s_pin_host(void *p, size_t bytes);
+int r2s_unpin_host(void *p);
 
 /* ---- grid set-up statistics: calculate_edge_distances + analyze_mesh (src/MeshGrid/Grid_setup.jl:28-92) ---------------------- */
 /* median / shortest / longest element edge; the median is the grid step of noninteractive_sdf_grid_setup (:94-109) */
@@ -132,8 +161,11 @@ int r2s_mesh_is_lattice(r2s_ctx *ctx, int *is_lattice);
 /* ---- result export: exportSdfToVTI (src/DataExport/ExportToVTI.jl:22-67) ----------------------------------------------- */
 /* VTK ImageData (.vti), one PointData scalar `label` ("distance" in rho2sdf, RhoToSDF.jl:267-273), raw appended block.
  * r2s_export_vti streams a device-resident result (which = 0: sdf_dists Float64 on the coarse grid, 1: fine_sdf Float32 on the
- * grid N*smooth+1) chunk by chunk; r2s_write_vti_host writes a host array (x fastest) and needs no context or GPU. */
+ * grid N*smooth+1) chunk by chunk; on a slab rank it is collective and writes that rank's piece (its planes + the shared boundary
+ * plane), r2s_export_pvti (any rank) writes the PImageData index naming the pieces "<piece_base>_<rank>.vti".
+ * r2s_write_vti_host writes a host array (x fastest) and needs no context or GPU. */
 int r2s_export_vti(r2s_ctx *ctx, const char *path, const char *label, int which);
+int r2s_export_pvti(r2s_ctx *ctx, const char *path, const char *label, int which, const char *piece_base);
 int r2s_write_vti_host(const char *path, const char *label, const void *values, int is_f64, int64_t nx, int64_t ny, int64_t nz, const double origin[3],
                        const double spacing[3]);
 

@@ -24,7 +24,7 @@ import numpy as np
 __all__ = ["HEX8", "TET4", "Rho2sdfOptions", "Mesh", "Grid", "getMesh_AABB", "generateGridPoints", "noninteractive_sdf_grid_setup",
            "DenseInNodes", "find_threshold_for_volume", "calculate_isocontour_volume", "evalDistances", "Sign_Detection",
            "remove_sdf_artifacts", "RBFs_smoothing", "calculate_volume_from_sdf", "rho2sdf", "rho2sdf_hex8", "rho2sdf_tet4",
-           "exportSdfToVTI", "export_device_result_to_vti", "read_vti", "FineGrid", "R2SError", "slab_partition", "init_slab_comm", "broadcast_unique_id", "load_library", "library_path", "Params", "Report", "Context"]
+           "exportSdfToVTI", "export_device_result_to_vti", "read_vti", "read_pvti", "MultiContext", "FineGrid", "R2SError", "slab_partition", "init_slab_comm", "broadcast_unique_id", "load_library", "library_path", "Params", "Report", "Context"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -110,6 +110,23 @@ def load_library():
     L.r2s_mesh_box_elements.argtypes = [vp, C.POINTER(C.c_int64)]
     L.r2s_mesh_is_lattice.argtypes = [vp, C.POINTER(C.c_int)]
     L.r2s_export_vti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.r2s_export_pvti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+    L.r2s_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.r2s_multi_destroy.argtypes = [vp]
+    L.r2s_multi_destroy.restype = None
+    L.r2s_multi_last_error.argtypes = [vp]
+    L.r2s_multi_last_error.restype = C.c_char_p
+    L.r2s_multi_size.argtypes = [vp]
+    L.r2s_multi_context.argtypes = [vp, C.c_int]
+    L.r2s_multi_context.restype = vp
+    L.r2s_multi_set_mesh.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int64, vp]
+    L.r2s_multi_set_grid.argtypes = [vp, vp, vp, vp, C.c_double]
+    L.r2s_multi_slab_planes.argtypes = [vp, vp]
+    L.r2s_multi_set_rebalance.argtypes = [vp, C.c_int]
+    L.r2s_multi_pipeline.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report)]
+    L.r2s_multi_export_vti.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.r2s_pin_host.argtypes = [vp, C.c_size_t]
+    L.r2s_unpin_host.argtypes = [vp]
     L.r2s_write_vti_host.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, vp]
     L.r2s_measure_fma_peak.argtypes = [vp, C.c_int, dp]
     _LIB = L
@@ -122,6 +139,62 @@ def _f64(a):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _BorrowedContext:
+    """A slab context owned by a MultiContext (never destroyed from here)."""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, C.c_void_p(h)
+
+    def check(self, rc):
+        if rc != 0:
+            raise R2SError(self.lib.r2s_last_error(self.h).decode())
+
+    def close(self):
+        pass
+
+    def report(self):
+        r = Report()
+        self.lib.r2s_last_report(self.h, C.byref(r))
+        return r
+
+
+class MultiContext:
+    """r2s_multi: ONE host call drives all listed GPUs (one z-slab and one library-internal thread per entry of `devices`; entries may
+    repeat -- several slabs on one GPU).  This is what the Julia drop-in's rho2sdf() uses on a multi-GPU box."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self.lib.r2s_multi_create(C.byref(self.h), ids, len(devices))
+        if rc != 0 or not self.h:
+            raise R2SError("r2s_multi_create failed (rc=%d): no usable CUDA device / no peer access -- this library has no CPU fallback" % rc)
+        self.n = len(devices)
+
+    def check(self, rc):
+        if rc != 0:
+            raise R2SError(self.lib.r2s_multi_last_error(self.h).decode())
+
+    def slab(self, r=0):
+        return _BorrowedContext(self.lib, self.lib.r2s_multi_context(self.h, int(r)))
+
+    def slab_planes(self):
+        cuts = np.zeros(self.n + 1, dtype=np.int64)
+        self.check(self.lib.r2s_multi_slab_planes(self.h, _ptr(cuts)))
+        return [int(v) for v in cuts]
+
+    def close(self):
+        if self.h:
+            self.lib.r2s_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -259,7 +332,9 @@ class Mesh:
     """MeshGrid.Mesh (src/MeshGrid/MeshInformations.jl:16-67).  Uploads the mesh to the GPU, builds INE and the
     boundary-face table there and computes V_domain / V_frac (calculate_mesh_volume)."""
 
-    def __init__(self, X, IEN, rho, sfce=None, element_type=HEX8, device=0, stream=None):
+    def __init__(self, X, IEN, rho, sfce=None, element_type=HEX8, device=0, stream=None, devices=None):
+        """`devices` (list of GPU ids, may repeat): the mesh goes to every listed device and the pipeline runs as z-slabs through the
+        single-call multi-GPU entry (r2s_multi_*); the per-stage functions (evalDistances, ...) then work on slab 0's whole-grid context."""
         self.element_type = element_type
         self.X = _f64(X)
         self.IEN = np.ascontiguousarray(IEN, dtype=np.int64)
@@ -272,9 +347,16 @@ class Mesh:
         self.nes, self.nsn = (6, 4) if self.nen == 8 else (4, 3)
         self.edges = _HEX_EDGES if self.nen == 8 else _TET_EDGES
         self.rho = _f64(rho)
-        self.ctx = Context(device, stream)
-        c = self.ctx
-        c.check(c.lib.r2s_set_mesh(c.h, self.nen, self.nnp, _ptr(self.X), self.nel, _ptr(self.IEN)))
+        self.multi = None
+        if devices is not None and len(devices) > 1:
+            self.multi = MultiContext(devices)
+            self.multi.check(self.multi.lib.r2s_multi_set_mesh(self.multi.h, self.nen, self.nnp, _ptr(self.X), self.nel, _ptr(self.IEN)))
+            self.ctx = self.multi.slab(0)
+            c = self.ctx
+        else:
+            self.ctx = Context(devices[0] if devices else device, stream)
+            c = self.ctx
+            c.check(c.lib.r2s_set_mesh(c.h, self.nen, self.nnp, _ptr(self.X), self.nel, _ptr(self.IEN)))
         vd, vf = C.c_double(), C.c_double()
         c.check(c.lib.r2s_mesh_volume(c.h, _ptr(self.rho), C.byref(vd), C.byref(vf)))
         self.V_domain, self.V_frac = vd.value, vf.value
@@ -292,8 +374,17 @@ class Mesh:
         if self._grid_id != key:
             c = self.ctx
             amin, amax, N = _f64(grid.AABB_min), _f64(grid.AABB_max), np.ascontiguousarray(grid.N, dtype=np.int64)
-            c.check(c.lib.r2s_set_grid(c.h, _ptr(amin), _ptr(amax), _ptr(N), float(grid.cell_size)))
+            if self.multi is not None:
+                self.multi.check(self.multi.lib.r2s_multi_set_grid(self.multi.h, _ptr(amin), _ptr(amax), _ptr(N), float(grid.cell_size)))
+            else:
+                c.check(c.lib.r2s_set_grid(c.h, _ptr(amin), _ptr(amax), _ptr(N), float(grid.cell_size)))
             self._grid_id = key
+
+    def close(self):
+        if self.multi is not None:
+            self.multi.close()
+        else:
+            self.ctx.close()
 
 
 def noninteractive_sdf_grid_setup(mesh):
@@ -476,7 +567,7 @@ def read_vti(path):
     cut = raw.index(b'<AppendedData encoding="raw">')
     head = raw[:cut].decode()
     ext = [int(v) for v in re.search(r'WholeExtent="([^"]+)"', head).group(1).split()]
-    dims = (ext[1] + 1, ext[3] + 1, ext[5] + 1)
+    dims = (ext[1] - ext[0] + 1, ext[3] - ext[2] + 1, ext[5] - ext[4] + 1)      # a piece of a slab decomposition starts at z = ext[4]
     origin = [float(v) for v in re.search(r'Origin="([^"]+)"', head).group(1).split()]
     spacing = [float(v) for v in re.search(r'Spacing="([^"]+)"', head).group(1).split()]
     typ, label = re.search(r'<DataArray type="(\w+)" Name="([^"]+)"', head).groups()
@@ -485,6 +576,27 @@ def read_vti(path):
     dt = np.dtype("<f8" if typ == "Float64" else "<f4")
     data = np.frombuffer(raw[start + 8:start + 8 + nbytes], dtype=dt)
     return dims, origin, spacing, label, data.reshape(dims[2], dims[1], dims[0])
+
+
+def read_pvti(path):
+    """Assemble the pieces named by a .pvti index (r2s_multi_export_vti / r2s_export_pvti): returns (dims, origin, spacing, label, array[k, j, i])."""
+    import re
+    head = open(path).read()
+    ext = [int(v) for v in re.search(r'WholeExtent="([^"]+)"', head).group(1).split()]
+    dims = (ext[1] + 1, ext[3] + 1, ext[5] + 1)
+    origin = [float(v) for v in re.search(r'Origin="([^"]+)"', head).group(1).split()]
+    spacing = [float(v) for v in re.search(r'Spacing="([^"]+)"', head).group(1).split()]
+    typ, label = re.search(r'<PDataArray type="(\w+)" Name="([^"]+)"', head).groups()
+    out = np.full((dims[2], dims[1], dims[0]), np.nan, dtype=np.float64 if typ == "Float64" else np.float32)
+    for pe, src in re.findall(r'<Piece Extent="([^"]+)" Source="([^"]+)"', head):
+        e = [int(v) for v in pe.split()]
+        _, _, _, _, arr = read_vti(os.path.join(os.path.dirname(os.path.abspath(path)), src))
+        assert arr.shape == (e[5] - e[4] + 1, dims[1], dims[0])
+        prev = out[e[4]:e[5] + 1]
+        both = ~np.isnan(prev)
+        assert np.array_equal(prev[both], arr[both])          # pieces agree on the boundary plane they share
+        out[e[4]:e[5] + 1] = arr
+    return dims, origin, spacing, label, out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -521,10 +633,12 @@ class Rho2sdfOptions:
         self.grid_step = grid_step      # stands in for the stdin prompt of interactive_sdf_grid_setup (:manual)
 
 
-def rho2sdf(taskName, X, IEN, rho, options=None, device=0, stream=None, return_report=False):
-    """src/RhoToSDF.jl:116-242 -> (fine_sdf, fine_grid, sdf_grid, sdf_dists).  Exports (VTI/VTU/JLD2) are out of scope."""
+def rho2sdf(taskName, X, IEN, rho, options=None, device=0, stream=None, return_report=False, devices=None, export_vti=None):
+    """src/RhoToSDF.jl:116-242 -> (fine_sdf, fine_grid, sdf_grid, sdf_dists).  `devices=[0, 1, ...]`: the timed region runs as z-slabs on
+    all listed GPUs from this one call (r2s_multi_pipeline).  `export_vti=base`: the fine SDF is streamed from the device(s) to
+    base.vti (one GPU) or base.pvti + pieces (RhoToSDF.jl:230-238, :267-273); VTU / JLD2 exports are out of scope."""
     options = options or Rho2sdfOptions()
-    mesh = Mesh(X, IEN, rho, None, element_type=options.element_type, device=device, stream=stream)
+    mesh = Mesh(X, IEN, rho, None, element_type=options.element_type, device=device, stream=stream, devices=devices)
     if options.sdf_grid_setup == "manual":
         if options.grid_step is None:
             raise R2SError(":manual grid set-up prompts on stdin in the reference (Grid_setup.jl:111-154); pass Rho2sdfOptions(grid_step=B) here")
@@ -546,7 +660,15 @@ def rho2sdf(taskName, X, IEN, rho, options=None, device=0, stream=None, return_r
     fine = np.empty(dims[0] * dims[1] * dims[2], dtype=np.float32)
     rep = Report()
     rn = _f64(rho_n)
-    c.check(c.lib.r2s_pipeline(c.h, C.byref(p), _ptr(rn), _ptr(sdf_dists), _ptr(fine), C.byref(rep)))
+    if mesh.multi is not None:
+        m = mesh.multi
+        m.check(m.lib.r2s_multi_pipeline(m.h, C.byref(p), _ptr(rn), _ptr(sdf_dists), _ptr(fine), C.byref(rep)))
+        if export_vti:
+            m.check(m.lib.r2s_multi_export_vti(m.h, str(export_vti).encode(), b"distance", 1))
+    else:
+        c.check(c.lib.r2s_pipeline(c.h, C.byref(p), _ptr(rn), _ptr(sdf_dists), _ptr(fine), C.byref(rep)))
+        if export_vti:
+            export_device_result_to_vti(mesh, str(export_vti), "distance", fine=True)
     out = (fine.reshape(dims[2], dims[1], dims[0]), FineGrid(sdf_grid, p.smooth), sdf_grid, sdf_dists)
     if return_report:
         return out + ({"rho_t": rho_t, "rho_n": rho_n, "V_domain": mesh.V_domain, "V_frac": mesh.V_frac, **rep.asdict()},)
@@ -555,11 +677,11 @@ def rho2sdf(taskName, X, IEN, rho, options=None, device=0, stream=None, return_r
 
 def rho2sdf_hex8(taskName, X, IEN, rho, **kwargs):
     """src/RhoToSDF.jl:284-293."""
-    extra = {k: kwargs.pop(k) for k in ("device", "stream", "return_report") if k in kwargs}
+    extra = {k: kwargs.pop(k) for k in ("device", "stream", "return_report", "devices", "export_vti") if k in kwargs}
     return rho2sdf(taskName, X, IEN, rho, options=Rho2sdfOptions(element_type=HEX8, **kwargs), **extra)
 
 
 def rho2sdf_tet4(taskName, X, IEN, rho, **kwargs):
     """src/RhoToSDF.jl:295-304."""
-    extra = {k: kwargs.pop(k) for k in ("device", "stream", "return_report") if k in kwargs}
+    extra = {k: kwargs.pop(k) for k in ("device", "stream", "return_report", "devices", "export_vti") if k in kwargs}
     return rho2sdf(taskName, X, IEN, rho, options=Rho2sdfOptions(element_type=TET4, **kwargs), **extra)

@@ -67,6 +67,7 @@ int r2s_set_mesh(r2s_ctx *ctx, int nen, int64_t nnp, const double *X, int64_t ne
   if (nel * nen >= (1ll << 31) || nnp >= (1ll << 31)) FAIL("r2s_set_mesh: mesh too large for 32-bit connectivity");
   CK(cudaSetDevice(ctx->device));
   for (i64 t = 0; t < nel * nen; t++) if (IEN[t] < 1 || IEN[t] > nnp) FAIL("r2s_set_mesh: IEN entry out of range (expected 1-based node ids)");
+  ctx->have_sdf = ctx->have_fine = false;
   ctx->nen = nen; ctx->nes = nen == 8 ? 6 : 4; ctx->nsn = nen == 8 ? 4 : 3; ctx->nnp = nnp; ctx->nel = nel;
   CK(ctx->X.reserve(sizeof(double) * 3 * (size_t)nnp));
   CK(ctx->IEN32.reserve(sizeof(int) * (size_t)(nel * nen)));
@@ -120,6 +121,7 @@ int r2s_set_grid(r2s_ctx *ctx, const double amin[3], const double amax[3], const
   CK(cudaStreamSynchronize(ctx->stream));
   g.pc = ctx->gtab_d.as<double>(); g.cellof = ctx->gtab_i.as<int>(); g.cstart = ctx->gtab_i.as<int>() + tot_p;
   ctx->has_grid = true; ctx->k0 = 0; ctx->k1 = g.np[2];
+  ctx->have_sdf = ctx->have_fine = false; ctx->slab_k0.clear();
   return 0;
 }
 int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1) {
@@ -128,7 +130,7 @@ int r2s_set_slab(r2s_ctx *ctx, int64_t k0, int64_t k1) {
   if (k0 < 0 || k1 > ctx->g.np[2] || k0 >= k1) FAIL("r2s_set_slab: invalid plane range");
   if (ctx->nranks > 1 && k1 - k0 < 3) FAIL("r2s_set_slab: a slab needs at least 3 planes (smoothing halo)");
   ctx->k0 = k0; ctx->k1 = k1;
-  ctx->slab_k0.clear();
+  ctx->slab_k0.clear(); ctx->have_sdf = ctx->have_fine = false;
   if (ctx->nranks > 1) {
     // every rank learns the whole partition (collective: all ranks call r2s_set_slab); slabs must tile [0, N3+1) in rank order
     CK(cudaSetDevice(ctx->device));
@@ -235,10 +237,12 @@ int r2s_sign_detection(r2s_ctx *ctx, const double *rho_n, double rho_t, double *
 int r2s_remove_artifacts(r2s_ctx *ctx, double *sdf, double threshold, double min_ratio, int64_t *flipped) {
   if (!ctx) return 1;
   if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
+  if (ctx->k0 != 0 || ctx->k1 != ctx->g.np[2]) FAIL("r2s_remove_artifacts works on the whole grid: a z-slab is set (use the pipeline calls on slab contexts)");
   ctx->launches = 0;
   CK(cudaSetDevice(ctx->device));
   CK(ctx->sdf.reserve(sizeof(double) * (size_t)ctx->g.ngp));
   CK(cudaMemcpyAsync(ctx->sdf.p, sdf, sizeof(double) * (size_t)ctx->g.ngp, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_sdf = true;
   i64 fl = 0;
   if (r2s_dev_remove_artifacts(ctx, threshold, min_ratio, &fl)) return 1;
   CK(cudaMemcpyAsync(sdf, ctx->sdf.p, sizeof(double) * (size_t)ctx->g.ngp, cudaMemcpyDeviceToHost, ctx->stream));
@@ -251,10 +255,12 @@ int r2s_rbf_smoothing(r2s_ctx *ctx, const double *sdf, int is_interp, int smooth
   if (!ctx) return 1;
   if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
   if (smooth < 1 || smooth > 2) FAIL("r2s_rbf_smoothing: smooth must be 1 (:same) or 2 (:fine)");
+  if (ctx->k0 != 0 || ctx->k1 != ctx->g.np[2]) FAIL("r2s_rbf_smoothing works on the whole grid: a z-slab is set (use the pipeline calls on slab contexts)");
   ctx->launches = 0;
   CK(cudaSetDevice(ctx->device));
   CK(ctx->sdf.reserve(sizeof(double) * (size_t)ctx->g.ngp));
   CK(cudaMemcpyAsync(ctx->sdf.p, sdf, sizeof(double) * (size_t)ctx->g.ngp, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_sdf = true;
   float t = 0, v = 0;
   if (r2s_dev_rbf(ctx, is_interp, smooth, rbf_cut, target_volume, volume != nullptr, &t, &v)) return 1;
   size_t nf = (size_t)(ctx->g.N[0] * (i64)smooth + 1) * (size_t)(ctx->g.N[1] * (i64)smooth + 1) * (size_t)(ctx->g.N[2] * (i64)smooth + 1);
@@ -290,6 +296,7 @@ int r2s_pipeline_resident(r2s_ctx *ctx, const r2s_params *p, r2s_report *rep) {
   if (!ctx || !p) return 1;
   if (!ctx->has_grid) FAIL("r2s_set_grid has not been called");
   if (p->smooth < 1 || p->smooth > 2) FAIL("r2s_pipeline: smooth must be 1 (:same) or 2 (:fine)");
+  if (ctx->nranks > 1 && (int)ctx->slab_k0.size() != ctx->nranks + 1) FAIL("r2s_pipeline: r2s_set_grid resets the slab of a multi-rank context: call r2s_set_slab (collective) before the pipeline");
   CK(cudaSetDevice(ctx->device));
   ctx->launches = 0; ctx->collectives = 0;
   memset(&ctx->rep, 0, sizeof(ctx->rep));

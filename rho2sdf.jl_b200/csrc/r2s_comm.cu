@@ -331,6 +331,47 @@ static void p2p_teardown(r2s_ctx *ctx) {
   ctx->p2p_box = nullptr; ctx->p2p_peer_box_dev = nullptr; ctx->p2p = false; ctx->p2p_c_local = nullptr;
 }
 
+// ---- in-process group set-up ---------------------------------------------------------------------------------------------
+LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err) {
+  auto fail = [&](const char *m) { if (err) *err = m; return (LocalGroup *)nullptr; };
+  if (n < 2 || n > 64) return fail("in-process slab group: 2..64 slabs");
+  LocalGroup *lg = new LocalGroup();
+  lg->n = n;
+  for (int r = 0; r < n; r++) { lg->ctx[r] = ctxs[r]; lg->ev_ready[r] = nullptr; lg->ev_done[r] = nullptr; }
+  // peer access between every pair of distinct devices (slabs that share a device need none)
+  for (int r = 0; r < n; r++) {
+    if (cudaSetDevice(ctxs[r]->device) != cudaSuccess) { delete lg; return fail("cudaSetDevice failed"); }
+    for (int q = 0; q < n; q++) {
+      if (ctxs[q]->device == ctxs[r]->device) continue;
+      int can = 0; cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
+      if (!can) { delete lg; return fail("in-process slab group: the devices cannot access each other's memory (no NVLink / PCIe peer access)"); }
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { delete lg; return fail("cudaDeviceEnablePeerAccess failed"); }
+      cudaGetLastError();
+    }
+    if (cudaEventCreateWithFlags(&lg->ev_ready[r], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&lg->ev_done[r], cudaEventDisableTiming) != cudaSuccess) { delete lg; return fail("cudaEventCreate failed"); }
+    if (cudaMalloc(&ctxs[r]->p2p_box, sizeof(P2PBox) + 64) != cudaSuccess || cudaMemset(ctxs[r]->p2p_box, 0, sizeof(P2PBox) + 64) != cudaSuccess) { delete lg; return fail("mailbox allocation failed"); }
+  }
+  for (int r = 0; r < n; r++) {
+    r2s_ctx *c = ctxs[r];
+    cudaSetDevice(c->device);
+    for (int q = 0; q < n; q++) c->p2p_peer_box[q] = ctxs[q]->p2p_box;
+    if (cudaMalloc((void **)&c->p2p_peer_box_dev, sizeof(void *) * 64) != cudaSuccess ||
+        cudaMemcpy(c->p2p_peer_box_dev, c->p2p_peer_box, sizeof(void *) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { delete lg; return fail("mailbox table allocation failed"); }
+    c->lg = lg; c->rank = r; c->nranks = n; c->comm = nullptr; c->p2p = true; c->p2p_seq = 0; c->p2p_halo_seq = 0; c->p2p_c_local = nullptr;
+  }
+  return lg;
+}
+void r2s_local_group_destroy(LocalGroup *lg) {
+  if (!lg) return;
+  for (int r = 0; r < lg->n; r++) {
+    if (lg->ctx[r]) { cudaSetDevice(lg->ctx[r]->device); r2s_comm_destroy(lg->ctx[r]); }
+    if (lg->ev_ready[r]) cudaEventDestroy(lg->ev_ready[r]);
+    if (lg->ev_done[r]) cudaEventDestroy(lg->ev_done[r]);
+  }
+  delete lg;
+}
+
 // ---- CG halo planes of c over peer memory ------------------------------------------------------------------------------
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
   if (!ctx->p2p) return 0;

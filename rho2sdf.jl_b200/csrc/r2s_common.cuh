@@ -121,6 +121,7 @@ struct r2s_ctx {
   // smoothing
   DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2];
   int smooth_last = 1;
+  bool have_sdf = false, have_fine = false;      // ctx->sdf / ctx->f_fine hold a result of the CURRENT grid (cleared by r2s_set_grid / r2s_set_mesh)
 
   // volumes
   DevBuf v_part;
@@ -186,6 +187,8 @@ int r2s_group_end(r2s_ctx *ctx);
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count);
 int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k1, int nz, int below, int above);
 extern "C" int r2s_comm_destroy(r2s_ctx *ctx);
+extern "C" int r2s_export_vti(r2s_ctx *ctx, const char *path, const char *label, int which);
+extern "C" int r2s_export_pvti(r2s_ctx *ctx, const char *path, const char *label, int which, const char *piece_base);
 // in-process groups (r2s_multi.cu drives them): one context per slab, one host thread per context
 LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err);
 void r2s_local_group_destroy(LocalGroup *g);

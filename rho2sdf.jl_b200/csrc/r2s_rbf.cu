@@ -861,7 +861,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   }
   CK(cudaEventRecord(ctx->ev[15], st));
   CK(cudaStreamSynchronize(st));
-  ctx->smooth_last = smooth;
+  ctx->smooth_last = smooth; ctx->have_fine = true;
   *th_out = tho; *vol_out = volf;
   CK(cudaEventElapsedTime(&ctx->rep.ms_rbf_prep, ctx->ev[4], ctx->ev[5]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_cg, ctx->ev[5], ctx->ev[6]));

@@ -366,7 +366,7 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   if (ctx->lattice && ctx->knobs.sign_lattice && nen == 8) {
     double *signs = nullptr, *sdf = nullptr;
     if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
-    if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
+    if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); ctx->have_sdf = true; }
     const int npt = g.np[0] + g.np[1] + g.np[2];
     CK(ctx->lat_info.reserve(sizeof(unsigned) * (size_t)ctx->lat_ncell));
     CK(ctx->lat_pt.reserve(sizeof(int) * (size_t)npt));
@@ -409,7 +409,7 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
   CK(cudaMemcpyAsync(ctx->s_tile_ptr.as<int>(), ctx->s_cnt.as<int>(), sizeof(int) * (size_t)(g.ntiles + 1), cudaMemcpyDeviceToDevice, st));
   double *signs = nullptr, *sdf = nullptr;
   if (write_signs) { CK(ctx->signs.reserve(sizeof(double) * (size_t)g.ngp)); signs = ctx->signs.as<double>(); }
-  if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); }
+  if (write_sdf) { CK(ctx->sdf.reserve(sizeof(double) * (size_t)g.ngp)); sdf = ctx->sdf.as<double>(); ctx->have_sdf = true; }
   if (nen == 8)      // density-class shortcut: bit-identical to the plain rule (test_sign_density_class_shortcut), always on
     k_sign<8, true><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->s_tile_ptr.as<int>(), sorted, ctx->s_rng.as<SRange>(), ctx->s_el.as<SignEl>(), ctx->IEN32.as<int>(), ctx->X.as<double>(),
                                                              ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf);

@@ -116,3 +116,33 @@ def test_tuning_knobs_named_by_the_tests_exist_in_the_sources():
     named -= {"R2S_TEST_OPTIN"}
     assert named <= read, sorted(named - read)
     assert read <= named, "knobs without a test: %s" % sorted(read - named)
+
+
+def _build_abi_smoke(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(root, "rho2sdf.jl_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "host", "abi_smoke.c"), "-o", exe,
+                           "-L", libdir, "-lr2s", "-Wl,-rpath," + libdir, "-lm"])
+    return exe
+
+
+def test_c_host_program_links_against_the_header(r2s, tmp_path):
+    """tests/host/abi_smoke.c: a plain C11 host compiles against include/r2s.h with -Werror and links libr2s.so (no Python, no torch)."""
+    import subprocess
+    exe = _build_abi_smoke(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr      # fails loudly without a device
+
+
+@pytest.mark.gpu
+def test_c_host_program_runs_the_pipeline(r2s, tmp_path):
+    """The same program on a GPU: single-context pipeline, then r2s_multi_pipeline on 3 slabs, compared with each other."""
+    import subprocess
+    exe = _build_abi_smoke(tmp_path)
+    out = subprocess.run([exe, "16", "3"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ABI SMOKE OK" in out.stdout, out.stdout + out.stderr
