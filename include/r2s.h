@@ -83,8 +83,9 @@ int r2s_remove_artifacts(r2s_ctx *ctx, double *sdf, double threshold, double min
 /* RBFs_smoothing (src/SdfSmoothing/RBFs4Smoothing.jl:321-377): fine_sdf[prod(N*smooth+1)], x fastest */
 int r2s_rbf_smoothing(r2s_ctx *ctx, const double *sdf, int is_interp, int smooth, double rbf_cut, double target_volume,
                       float *fine_sdf, float *th, float *volume);
-/* calculate_volume_from_sdf (src/SdfSmoothing/CalcVolumeFromSDF.jl:26-125) on an nx x ny x nz Float32 grid */
-int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, int64_t nz, float edge, float iso, double *volume);
+/* calculate_volume_from_sdf (src/SdfSmoothing/CalcVolumeFromSDF.jl:26-125) on an nx x ny x nz Float32 grid; quad_order =
+ * detailed_quad_order (:30, default 9; 1..32 -- test/ConvergenceTests/SphereConvergenceTest.jl:67 calls it with 20) */
+int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, int64_t nz, float edge, float iso, int quad_order, double *volume);
 
 /* ---- the timed region of rho2sdf() (src/RhoToSDF.jl:164-227) as one call ---------------------------------- */
 /* host buffers in/out (H2D of rho_n, D2H of sdf_dists and fine_sdf inside the call) */

@@ -93,7 +93,7 @@ def load_library():
     L.r2s_sign_detection.argtypes = [vp, vp, C.c_double, vp]
     L.r2s_remove_artifacts.argtypes = [vp, vp, C.c_double, C.c_double, ip]
     L.r2s_rbf_smoothing.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, fp, fp]
-    L.r2s_volume_from_sdf.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, dp]
+    L.r2s_volume_from_sdf.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int, dp]
     L.r2s_pipeline.argtypes = [vp, C.POINTER(Params), vp, vp, vp, C.POINTER(Report)]
     L.r2s_upload_nodal_densities.argtypes = [vp, vp]
     L.r2s_pipeline_resident.argtypes = [vp, C.POINTER(Params), C.POINTER(Report)]
@@ -515,8 +515,6 @@ def RBFs_smoothing(mesh, dist, my_grid, Is_interpolation, smooth, taskName="", t
 
 def calculate_volume_from_sdf(fine_sdf, fine_grid, iso_threshold=0.0, detailed_quad_order=9, ctx=None):
     """src/SdfSmoothing/CalcVolumeFromSDF.jl:26-125.  fine_sdf[k, j, i] float32; fine_grid: FineGrid or an edge length."""
-    if detailed_quad_order != 9:
-        raise R2SError("only the reference's default quadrature order 9 is implemented on the GPU")
     a = np.ascontiguousarray(fine_sdf, dtype=np.float32)
     nz, ny, nx = a.shape
     if isinstance(fine_grid, FineGrid):
@@ -526,7 +524,7 @@ def calculate_volume_from_sdf(fine_sdf, fine_grid, iso_threshold=0.0, detailed_q
         edge = np.float32(fine_grid)
     c = ctx or Context()
     v = C.c_double()
-    c.check(c.lib.r2s_volume_from_sdf(c.h, _ptr(a), nx, ny, nz, float(edge), float(iso_threshold), C.byref(v)))
+    c.check(c.lib.r2s_volume_from_sdf(c.h, _ptr(a), nx, ny, nz, float(edge), float(iso_threshold), int(detailed_quad_order), C.byref(v)))
     return np.float32(v.value)
 
 

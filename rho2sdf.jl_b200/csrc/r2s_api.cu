@@ -271,7 +271,7 @@ int r2s_rbf_smoothing(r2s_ctx *ctx, const double *sdf, int is_interp, int smooth
   ctx->rep.launches = ctx->launches;
   return 0;
 }
-int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, int64_t nz, float edge, float iso, double *volume) {
+int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, int64_t nz, float edge, float iso, int quad_order, double *volume) {
   if (!ctx) return 1;
   if (nx < 2 || ny < 2 || nz < 2) FAIL("r2s_volume_from_sdf: grid must have at least 2 points per axis");
   ctx->launches = 0;
@@ -279,7 +279,7 @@ int r2s_volume_from_sdf(r2s_ctx *ctx, const float *sdf, int64_t nx, int64_t ny, 
   DevBuf tmp;
   CK(tmp.reserve(sizeof(float) * (size_t)(nx * ny * nz)));
   CK(cudaMemcpyAsync(tmp.p, sdf, sizeof(float) * (size_t)(nx * ny * nz), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = r2s_dev_volume_from_sdf(ctx, tmp.as<float>(), nx, ny, nz, edge, iso, volume);
+  int rc = r2s_dev_volume_from_sdf(ctx, tmp.as<float>(), nx, ny, nz, edge, iso, quad_order, volume);
   cudaStreamSynchronize(ctx->stream);
   tmp.release();
   return rc;

@@ -373,6 +373,24 @@ void r2s_local_group_destroy(LocalGroup *lg) {
 }
 
 // ---- CG halo planes of c over peer memory ------------------------------------------------------------------------------
+// Collective, called BEFORE the CG vector c may be re-allocated (a larger grid on a live communicator): if any rank is going to grow
+// its buffer, every rank first closes its CUDA-IPC mappings of the neighbours' c (freeing memory that a peer still has mapped is
+// undefined behaviour, and a re-allocation that happens to return the old address would otherwise leave a dead mapping in use);
+// a second all-reduce makes sure everybody has closed before anybody frees.  r2s_p2p_map_c then maps the new buffers.
+int r2s_p2p_prepare_c(r2s_ctx *ctx, size_t have_bytes, size_t need_bytes) {
+  if (!ctx->p2p || ctx->lg) return 0;      // in-process groups use plain pointers, re-read on every call
+  unsigned long long *w = (unsigned long long *)((char *)ctx->p2p_box + sizeof(P2PBox) + 40);
+  unsigned long long grow = have_bytes < need_bytes ? 1ull : 0ull;
+  CK(cudaMemcpyAsync(w, &grow, sizeof(grow), cudaMemcpyHostToDevice, ctx->stream));
+  if (p2p_allreduce(ctx, w, 1, 4)) return 1;
+  if (r2s_readback(ctx, &grow, w, sizeof(grow))) return 1;
+  if (!grow) return 0;
+  for (int s = 0; s < 2; s++) if (ctx->p2p_c_peer[s]) { cudaIpcCloseMemHandle(ctx->p2p_c_peer[s]); ctx->p2p_c_peer[s] = nullptr; }
+  ctx->p2p_c_local = nullptr;      // forces the re-mapping in r2s_p2p_map_c on every rank
+  if (p2p_allreduce(ctx, w, 1, 4)) return 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
   if (!ctx->p2p) return 0;
   if (ctx->lg) {      // in-process: the neighbours' arrays are plain pointers, re-read on every call (they may have been re-allocated)

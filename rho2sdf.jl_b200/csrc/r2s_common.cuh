@@ -162,7 +162,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
 int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf);              // r2s_sign.cu -> ctx->signs / ctx->sdf
 int r2s_dev_remove_artifacts(r2s_ctx *ctx, double thr, double ratio, i64 *flipped);          // r2s_cc.cu on ctx->sdf
 int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double target, bool final_volume, float *th, float *vol);   // r2s_rbf.cu: ctx->sdf -> ctx->f_fine
-int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, double *vol);        // r2s_rbf.cu
+int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, int order, double *vol);        // r2s_rbf.cu
 int r2s_scan_exclusive_i64(r2s_ctx *ctx, const i64 *in, i64 *out, i64 n);  // r2s_util.cu (cub)
 int r2s_scan_exclusive_i32(r2s_ctx *ctx, const int *in, int *out, i64 n);
 int r2s_sort_keys_u64(r2s_ctx *ctx, u64 *keys, u64 *alt, i64 n, int end_bit, u64 **sorted);
@@ -178,6 +178,7 @@ int r2s_readback(r2s_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes
 int r2s_mesh_build_lattice(r2s_ctx *ctx);                                  // r2s_mesh.cu: tensor-product lattice detection + tables
 // r2s_comm.cu: collectives over the slab communicator (no-ops for a single rank)
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
+int r2s_p2p_prepare_c(r2s_ctx *ctx, size_t have_bytes, size_t need_bytes);                  // collective; before c may be re-allocated
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes);                                     // (re)map the neighbours' CG vector c
 int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, int nz, int H);   // my boundary planes -> neighbours' halos
 int r2s_p2p_halo_wait(r2s_ctx *ctx);

@@ -356,10 +356,48 @@ __global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int kc0, int k
     if (tp) atomicAdd(&acc[3], (u64)tp);
   }
 }
+// any quadrature order 1..32 (calculate_volume_from_sdf's detailed_quad_order; the convergence tests of the reference use 20): same
+// organisation as k_vol_cut, loops not unrolled, abscissae / weights read from the kernel-parameter bank with uniform indices
+struct GaussNF { float x[32]; float w[32]; int n; };
+__global__ void __launch_bounds__(128) k_vol_cut_n(int nx, int ny, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
+                                                   GaussNF G, u64 *__restrict__ acc) {
+  const int ncut = (int)min((u64)cutcap, acc[1]);
+  const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
+  const i64 sxy = (i64)nx * ny;
+  u64 local = 0;
+  for (int base = blockIdx.x * blockDim.x; base < ncut; base += nthr) {
+    const int idx = base + threadIdx.x;
+    if (idx < ncut) {
+      const i64 c = cutlist[idx];
+      const int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
+      const i64 b = ((i64)k * ny + j) * nx + i;
+      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
+      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+      float part = 0.0f;
+      for (int iq = 0; iq < G.n; iq++) {
+        const float xi = (G.x[iq] + 1) / 2, xm = 1.0f - xi;
+        const float c00 = c000 * xm + c100 * xi, c01 = c001 * xm + c101 * xi;
+        const float c10 = c010 * xm + c110 * xi, c11 = c011 * xm + c111 * xi;
+        for (int jq = 0; jq < G.n; jq++) {
+          const float eta = (G.x[jq] + 1) / 2, em = 1.0f - eta;
+          const float c0 = c00 * em + c10 * eta, c1 = c01 * em + c11 * eta;
+          const float wij = G.w[iq] * G.w[jq], dc = c1 - c0;
+          for (int kq = 0; kq < G.n; kq++) {
+            const float ps = fmaf(dc, (G.x[kq] + 1) / 2, c0);
+            if (ps >= iso) part += wij * G.w[kq];
+          }
+        }
+      }
+      local += (u64)llrint((double)part * 137438953472.0);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if (lane == 0 && local) atomicAdd(&acc[2], local);
+}
 static GaussF gauss9f() { GaussTab t = gauss_legendre_host(9); GaussF g; for (int i = 0; i < 9; i++) { g.x[i] = (float)t.x[i]; g.w[i] = (float)t.w[i]; } return g; }
 
 // volume of {sdf - th >= iso}; edge = cell edge length (Float32 like the reference)
-static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, float th, float edge, float iso, double *vol) {
+static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, float th, float edge, float iso, int order, double *vol) {
   cudaStream_t st = ctx->stream;
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("calculate_volume_from_sdf: grid too large for 32-bit cell ids");
@@ -370,7 +408,13 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
     int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(acc, 0, sizeof(u64) * 4, st));
     k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
-    k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc); LAUNCH_CHECK();
+    if (order == 9) k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc);
+    else {
+      GaussTab t = gauss_legendre_host(order); GaussNF G; G.n = order;
+      for (int q = 0; q < 32; q++) { G.x[q] = q < order ? (float)t.x[q] : 0.0f; G.w[q] = q < order ? (float)t.w[q] : 0.0f; }
+      k_vol_cut_n<<<148 * 16, 128, 0, st>>>(nx, ny, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G, acc);
+    }
+    LAUNCH_CHECK();
     u64 h[3];
     if (r2s_readback(ctx, h, acc, sizeof(h))) return 1;
     if ((i64)h[1] > cutcap) {     // the cut list was too small: grow it and redo both passes
@@ -513,9 +557,10 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
   }
   FAIL("LS_Threshold: cut-cell list overflow");
 }
-int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, double *vol) {
+int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, int order, double *vol) {
+  if (order < 1 || order > 32) FAIL("calculate_volume_from_sdf: detailed_quad_order must be between 1 and 32");
   CK(ctx->cutlist.reserve(sizeof(int) * 1024));
-  return volume_dev(ctx, sdf_dev, (int)nx, (int)ny, (int)nz, 0.0f, edge, iso, vol);
+  return volume_dev(ctx, sdf_dev, (int)nx, (int)ny, (int)nz, 0.0f, edge, iso, order, vol);
 }
 
 // ------------------------------------------------------------------------------------------------ fine-grid evaluation (:363)
@@ -727,7 +772,9 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   if (is_interp) {
     // cg(K, s) with IterativeSolvers defaults (:199): x0 = 0, reltol = sqrt(eps(Float32)), maxiter = n
     CK(ctx->f_w.reserve(sizeof(float) * (size_t)n)); CK(ctx->f_r.reserve(sizeof(float) * (size_t)n));
-    CK(ctx->f_u.reserve(sizeof(float) * 2 * (size_t)n)); CK(ctx->f_c.reserve(sizeof(float) * (size_t)n));
+    CK(ctx->f_u.reserve(sizeof(float) * 2 * (size_t)n));
+    if (r2s_p2p_prepare_c(ctx, ctx->f_c.cap, sizeof(float) * (size_t)n)) return 1;      // peers must drop their mappings of c before it is re-allocated
+    CK(ctx->f_c.reserve(sizeof(float) * (size_t)n));
     float *x = ctx->f_w.as<float>(), *r = ctx->f_r.as<float>(), *u = ctx->f_u.as<float>(), *c = ctx->f_c.as<float>();
     CK(cudaMemsetAsync(x + x_lo, 0, sizeof(float) * (size_t)next, st));
     CK(cudaMemsetAsync(u + x_lo, 0, sizeof(float) * (size_t)next, st));

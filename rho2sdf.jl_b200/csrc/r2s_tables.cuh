@@ -11,7 +11,7 @@ static __constant__ int c_hex_edges[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4
 
 // Gauss-Legendre rule of order n (what FastGaussQuadrature.gausslegendre(n) returns): Newton on P_n in long double,
 // nodes ascending, symmetrised.  Host side; the tables travel to kernels by value.
-struct GaussTab { double x[16]; double w[16]; int n; };
+struct GaussTab { double x[32]; double w[32]; int n; };      // orders up to 32 (the reference uses 3, 9, 15 and, in its convergence tests, 20)
 static inline GaussTab gauss_legendre_host(int n) {
   GaussTab t; t.n = n;
   for (int i = 0; i < n; i++) {

@@ -26,7 +26,7 @@ mutable struct R2SReport
   ms_bin::Cfloat; ms_project::Cfloat; ms_assemble::Cfloat; ms_sign::Cfloat; ms_cc::Cfloat; ms_rbf_prep::Cfloat; ms_cg::Cfloat; ms_lsf::Cfloat
   ms_threshold::Cfloat; ms_fine::Cfloat; ms_volume::Cfloat; ms_total::Cfloat
   launches::Int64; collectives::Int64; cg_probe::NTuple{4,Cfloat}; n_pairs_pruned::Int64
-  R2SReport() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0, (0f0, 0f0, 0f0, 0f0))
+  R2SReport() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0, (0f0, 0f0, 0f0, 0f0), 0)
 end
 
 mutable struct Context
@@ -42,7 +42,14 @@ mutable struct Context
 end
 check(c::Context, rc) = rc == 0 ? nothing : error(unsafe_string(ccall((:r2s_last_error, LIB), Cstring, (Ptr{Cvoid},), c.h)))   # mirrors the reference's error(...)
 
-const CONTEXTS = IdDict{Any,Context}()      # one device context per Mesh object
+# One device context per Mesh object, held WEAKLY: when the Mesh is garbage collected its entry disappears and the Context's finalizer
+# frees the device memory (an IdDict would pin every mesh ever used).  release!(mesh) frees it right away.
+const CONTEXTS = WeakKeyDict{Any,Context}()
+function release!(mesh::Mesh)
+  c = pop!(CONTEXTS, mesh, nothing)
+  c === nothing || finalize(c)
+  return nothing
+end
 
 function context(mesh::Mesh)
   get!(CONTEXTS, mesh) do
@@ -114,6 +121,34 @@ function RBFs_smoothing(mesh::Mesh, dist::Vector{Float64}, my_grid::Grid, Is_int
   return fine, fine_grid_of(my_grid, smooth)
 end
 
+# ---- src/SdfSmoothing/CalcVolumeFromSDF.jl:26-125 (stand-alone volume tool, test/ConvergenceTests/*) --------------------------------------
+function calculate_volume_from_sdf(fine_sdf::Array{Float32,3}, fine_grid::AbstractArray{Vector{Float32},3}; iso_threshold::Float32=0.0f0, detailed_quad_order::Int=9,
+                                   ctx::Context=Context())
+  nx, ny, nz = size(fine_sdf)
+  size(fine_grid) == (nx, ny, nz) || error("Dimensions of fine_sdf and fine_grid must match")
+  edge = Float32(sqrt(sum(abs2, fine_grid[2, 1, 1] .- fine_grid[1, 1, 1])))          # :37-38
+  v = Ref{Cdouble}(0.0)
+  check(ctx, ccall((:r2s_volume_from_sdf, LIB), Cint, (Ptr{Cvoid}, Ptr{Cfloat}, Int64, Int64, Int64, Cfloat, Cfloat, Cint, Ref{Cdouble}),
+                   ctx.h, fine_sdf, nx, ny, nz, edge, iso_threshold, detailed_quad_order, v))
+  return Float32(v[])
+end
+
+# ---- all GPUs of the box from this one process: r2s_multi (include/r2s.h) ----------------------------------------------------------
+mutable struct MultiContext
+  h::Ptr{Cvoid}; n::Int
+  function MultiContext(devices::Vector{<:Integer})
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:r2s_multi_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), ref, Cint.(devices), length(devices))
+    (rc != 0 || ref[] == C_NULL) && error("r2s_multi_create failed (rc=$rc): no usable CUDA devices / no peer access -- libr2s has no CPU fallback")
+    m = new(ref[], length(devices))
+    finalizer(x -> (x.h != C_NULL && ccall((:r2s_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), m)
+    return m
+  end
+end
+mcheck(m::MultiContext, rc) = rc == 0 ? nothing : error(unsafe_string(ccall((:r2s_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m.h)))
+"GPUs rho2sdf() uses: ENV[\"R2S_DEVICES\"] = \"0,1,2,3\" (default: device 0 only)"
+devices_from_env() = haskey(ENV, "R2S_DEVICES") ? parse.(Int, split(ENV["R2S_DEVICES"], ",")) : [0]
+
 # ---- src/DataExport/ExportToVTI.jl:22-67 (SURVEY 8f-1): host array -> .vti; `export_device_vti` streams the device-resident result ---
 function exportSdfToVTI(filename::String, grid::Grid, values::Vector{<:AbstractFloat}, value_label::String, smooth::Union{Int,Nothing}=nothing)
   sm = isnothing(smooth) ? 1 : smooth
@@ -130,20 +165,32 @@ export_device_vti(mesh::Mesh, filename::String; label::String="distance", fine::
   (c = context(mesh); check(c, ccall((:r2s_export_vti, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Cint), c.h, filename, label, fine ? 1 : 0)); filename)
 
 # ---- src/RhoToSDF.jl:116-242: same preamble as the reference, the timed region (:164-227) is ONE library call ---------------
-function rho2sdf(taskName::String, X::Vector{Vector{Float64}}, IEN::Vector{Vector{Int64}}, rho::Vector{Float64}; options::Rho2sdfOptions=Rho2sdfOptions())
+function rho2sdf(taskName::String, X::Vector{Vector{Float64}}, IEN::Vector{Vector{Int64}}, rho::Vector{Float64}; options::Rho2sdfOptions=Rho2sdfOptions(),
+                 devices::Vector{Int}=devices_from_env())
   element_type = options.element_type
   mesh = Mesh(X, IEN, rho, Rho2sdf.ShapeFunctions.shape_functions; element_type=element_type)                  # :128
   sdf_grid = options.sdf_grid_setup == :manual ? Rho2sdf.MeshGrid.interactive_sdf_grid_setup(mesh) : Rho2sdf.MeshGrid.noninteractive_sdf_grid_setup(mesh)   # :141-145
   ρₙ = DenseInNodes(mesh, rho)                                                                                  # :148
   ρₜ = options.threshold_density === nothing ? find_threshold_for_volume(mesh, ρₙ) : options.threshold_density   # :151-156
-  c = context(mesh); use_grid(c, sdf_grid)
   smooth = options.rbf_grid == :fine ? 2 : 1                                                                    # :222
   p = R2SParams(ρₜ, 1.1, options.remove_artifacts, 0.0, options.artifact_min_component_ratio, options.rbf_interp, smooth, 1e-3, mesh.V_frac * mesh.V_domain, 1)
   dims = Tuple(Int.(sdf_grid.N .* smooth .+ 1))
   sdf_dists = Vector{Float64}(undef, sdf_grid.ngp); fine_sdf = Array{Float32,3}(undef, dims); rep = R2SReport()
-  check(c, ccall((:r2s_pipeline, LIB), Cint, (Ptr{Cvoid}, Ref{R2SParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cfloat}, Ref{R2SReport}), c.h, p, ρₙ, sdf_dists, fine_sdf, rep))
+  if length(devices) > 1
+    # ONE call, all GPUs: the library cuts the coarse planes into z-slabs, one per device, and fills the whole-grid arrays
+    m = MultiContext(devices)
+    mcheck(m, ccall((:r2s_multi_set_mesh, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cdouble}, Int64, Ptr{Int64}), m.h, mesh.nen, mesh.nnp, mesh.X, mesh.nel, mesh.IEN))
+    mcheck(m, ccall((:r2s_multi_set_grid, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Cdouble),
+                    m.h, Vector{Float64}(sdf_grid.AABB_min), Vector{Float64}(sdf_grid.AABB_max), Vector{Int64}(sdf_grid.N), sdf_grid.cell_size))
+    mcheck(m, ccall((:r2s_multi_pipeline, LIB), Cint, (Ptr{Cvoid}, Ref{R2SParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cfloat}, Ref{R2SReport}), m.h, p, ρₙ, sdf_dists, fine_sdf, rep))
+    finalize(m)
+  else
+    c = context(mesh); use_grid(c, sdf_grid)
+    check(c, ccall((:r2s_pipeline, LIB), Cint, (Ptr{Cvoid}, Ref{R2SParams}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cfloat}, Ref{R2SReport}), c.h, p, ρₙ, sdf_dists, fine_sdf, rep))
+  end
   fine_grid = fine_grid_of(sdf_grid, smooth)
   Rho2sdf.export_sdf_results_with_element_type(fine_sdf, fine_grid, sdf_grid, taskName, smooth, options.rbf_interp, element_type)   # :230-238 (unchanged, Julia)
+  release!(mesh)                                                                                                # the Mesh is local to this call: free its device context now
   return fine_sdf, fine_grid, sdf_grid, sdf_dists                                                               # :241
 end
 rho2sdf_hex8(taskName, X, IEN, rho; kwargs...) = rho2sdf(taskName, X, IEN, rho; options=Rho2sdfOptions(; element_type=HEX8, kwargs...))    # :284-293

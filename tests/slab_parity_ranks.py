@@ -79,6 +79,34 @@ def main():
     c.check(c.lib.r2s_pipeline_slab(c.h, C.byref(p), rn.ctypes.data_as(C.c_void_p), h_sdf.ctypes.data_as(C.c_void_p), h_fine.ctypes.data_as(C.c_void_p), C.byref(rep)))
     check("pipeline_slab sdf", np.array_equal(h_sdf.reshape(k1 - k0, ny, nx), sdfN[k0:k1]))
     check("pipeline_slab fine", np.array_equal(h_fine.reshape(kf1 - kf0, fd[1], fd[0]), fineN[kf0:kf1]))
+    # a LARGER grid on the live communicator: every field is re-allocated, the peers' mappings of the CG vector must follow
+    grid2 = r2s.Grid(X.min(0), X.max(0), 3 * n, 3)
+    nx2, ny2, nz2 = (int(v) + 1 for v in grid2.N)
+    fd2 = [int(v) * 2 + 1 for v in grid2.N]
+    ref = r2s.Mesh(X, IEN, rho, device=local)                      # single-rank reference on its own context
+    ref._use_grid(grid2)
+    rc_ = ref.ctx
+    p.rho_t, p.artifact_min_ratio = 0.5, 0.3
+    rep1 = r2s.Report()
+    rc_.check(rc_.lib.r2s_upload_nodal_densities(rc_.h, rn.ctypes.data_as(C.c_void_p)))
+    rc_.check(rc_.lib.r2s_pipeline_resident(rc_.h, C.byref(p), C.byref(rep1)))
+    sdf1 = np.empty(grid2.ngp); rc_.check(rc_.lib.r2s_download_sdf(rc_.h, sdf1.ctypes.data_as(C.c_void_p)))
+    fine1 = np.empty(fd2[0] * fd2[1] * fd2[2], dtype=np.float32); rc_.check(rc_.lib.r2s_download_fine_sdf(rc_.h, fine1.ctypes.data_as(C.c_void_p)))
+    ref.ctx.close()
+    mesh._use_grid(grid2)                                           # r2s_set_grid resets the slab ...
+    k0, k1 = r2s.slab_partition(nz2, world)[rank]
+    c.check(c.lib.r2s_set_slab(c.h, k0, k1))                        # ... so it is set again (collective)
+    repN = r2s.Report()
+    c.check(c.lib.r2s_upload_nodal_densities(c.h, rn.ctypes.data_as(C.c_void_p)))
+    c.check(c.lib.r2s_pipeline_resident(c.h, C.byref(p), C.byref(repN)))
+    sdfN = np.empty(grid2.ngp); c.check(c.lib.r2s_download_sdf(c.h, sdfN.ctypes.data_as(C.c_void_p)))
+    fineN = np.empty(fd2[0] * fd2[1] * fd2[2], dtype=np.float32); c.check(c.lib.r2s_download_fine_sdf(c.h, fineN.ctypes.data_as(C.c_void_p)))
+    pl2, fpl2 = nx2 * ny2, fd2[0] * fd2[1]
+    kf0, kf1 = 2 * k0, (2 * k1 if k1 < nz2 else fd2[2])
+    check("[grown grid] sdf bit-identical", np.array_equal(sdf1[k0 * pl2:k1 * pl2], sdfN[k0 * pl2:k1 * pl2]))
+    check("[grown grid] cg iterations", rep1.cg_iters == repN.cg_iters)
+    scale = max(1.0, float(np.abs(fine1).max()))
+    check("[grown grid] fine field", float(np.abs(fine1[kf0 * fpl2:kf1 * fpl2] - fineN[kf0 * fpl2:kf1 * fpl2]).max()) <= 1e-5 * scale)
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

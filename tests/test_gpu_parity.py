@@ -229,6 +229,27 @@ def test_volume_from_sdf_convergence(r2s):
         vc = float(r2s.calculate_volume_from_sdf(cube, np.float32(ax[1] - ax[0]), ctx=ctx))
         assert abs(vc - 1.0) < (0.05 if N < 32 else 0.02)
     assert errs[0] > errs[1] > errs[2]           # monotone decrease (SphereConvergenceTest.jl:400-410)
+    # detailed_quad_order = 20, as the reference's acceptance suite calls it (SphereConvergenceTest.jl:67, CubeConvergenceTest.jl:67):
+    # the ladders of :364-398 (sphere: < 10 % for N >= 16, < 5 % for N >= 32, < 2 % for N >= 64) and the oracle's value at the same order
+    errs20 = []
+    for N, tol in ((8, 0.5), (16, 0.10), (32, 0.05), (64, 0.02)):
+        ax = np.linspace(-1, 1, N + 1, dtype=np.float32)
+        z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")
+        sph = (0.5 - np.sqrt(x * x + y * y + z * z)).astype(np.float32)
+        v = float(r2s.calculate_volume_from_sdf(sph, np.float32(ax[1] - ax[0]), detailed_quad_order=20, ctx=ctx))
+        errs20.append(abs(v - np.pi / 6) / (np.pi / 6))
+        assert errs20[-1] < tol
+        assert abs(v - oracle.volume_from_sdf(sph, np.float32(ax[1] - ax[0]), order=20)) <= 2e-6 * v
+        cube = (0.5 - np.maximum(np.maximum(np.abs(x), np.abs(y)), np.abs(z))).astype(np.float32)
+        vc = float(r2s.calculate_volume_from_sdf(cube, np.float32(ax[1] - ax[0]), detailed_quad_order=20, ctx=ctx))
+        assert abs(vc - oracle.volume_from_sdf(cube, np.float32(ax[1] - ax[0]), order=20)) <= 2e-6 * max(vc, 1e-3)
+    assert errs20[1] > errs20[2] > errs20[3]
+    for order in (1, 3, 15, 32):                 # every order the parameter admits; 0 and 33 are refused
+        v = float(r2s.calculate_volume_from_sdf(sph, np.float32(ax[1] - ax[0]), detailed_quad_order=order, ctx=ctx))
+        assert abs(v - oracle.volume_from_sdf(sph, np.float32(ax[1] - ax[0]), order=order)) <= 2e-6 * v
+    for order in (0, 33):
+        with pytest.raises(r2s.R2SError, match="detailed_quad_order"):
+            r2s.calculate_volume_from_sdf(sph, np.float32(ax[1] - ax[0]), detailed_quad_order=order, ctx=ctx)
     ctx.close()
 
 
