@@ -195,9 +195,10 @@ struct BoxRec {
   double tlo[3], thi[3];     // tight box of the iso-patch, GLOBAL coordinates (slightly widened)
   i64 pair_off;
   int ps[3], nx, ny, vol, ok0, el;
+  int ftile, pad_;           // 1 = some tile overlapped by the candidate range holds boundary-face elements (its pairs may go to the pair buffer)
 };
 __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn,
-                              const unsigned char *__restrict__ ebox, double rho_t, BoxRec *__restrict__ box) {
+                              const unsigned char *__restrict__ ebox, double rho_t, GridDev g, const unsigned char *__restrict__ tile_faces, BoxRec *__restrict__ box) {
   const i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (a >= nact) return;
   const ActRec r = rec[a];
@@ -226,6 +227,12 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 #pragma unroll
   for (int d = 0; d < 3; d++) { B.c[d] = H.c[d]; B.h[d] = H.h[d]; B.xi0[d] = S0.xi[d]; B.ps[d] = r.ps[d]; }
   B.nx = r.pe[0] - r.ps[0]; B.ny = r.pe[1] - r.ps[1]; B.vol = B.nx * B.ny * (r.pe[2] - r.ps[2]);
+  B.ftile = 0; B.pad_ = 0;
+  if (B.vol > 0)
+    for (int tz = r.ps[2] / TILE_Z; tz <= (r.pe[2] - 1) / TILE_Z; tz++)
+      for (int ty = r.ps[1] / TILE_Y; ty <= (r.pe[1] - 1) / TILE_Y; ty++)
+        for (int tx = r.ps[0] / TILE_X; tx <= (r.pe[0] - 1) / TILE_X; tx++)
+          if (tile_faces[((i64)tz * g.nt[1] + ty) * g.nt[0] + tx]) B.ftile = 1;
   // tight box per axis: corner pairs (lo end, hi end) of the four edges along the axis, node order of hex8_shape.jl:27-34
   const int ea[3][4] = {{0, 3, 4, 7}, {0, 1, 4, 5}, {0, 1, 2, 3}}, eb[3][4] = {{1, 2, 5, 6}, {3, 2, 7, 6}, {4, 5, 6, 7}};
 #pragma unroll
@@ -267,40 +274,51 @@ __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__res
   if (vol == 0) return;
   const BoxRec &B = box[a];
   const int nx = B.nx, ny = B.ny, ps0 = B.ps[0], ps1 = B.ps[1], ps2 = B.ps[2];
-  // closed AABB of the element in global coordinates (exact: these are node coordinates)
+  const bool ftile = B.ftile != 0;
+  // closed AABB of the element and tight box of its iso-patch, global coordinates.  The point coordinates are taken as amin + cell * i
+  // here (no table look-up; at most an ulp from the tabulated value): which pass a pair belongs to is free to choose, and the bound is
+  // compared with a relative margin of 1e-10.
   double elo[3], ehi[3], tlo[3], thi[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const double c0 = (B.c[d] - B.h[d]) + B.org[d], c1 = (B.c[d] + B.h[d]) + B.org[d];
     elo[d] = fmin(c0, c1); ehi[d] = fmax(c0, c1); tlo[d] = B.tlo[d]; thi[d] = B.thi[d];
   }
+  const double sl = 1e-9 * (ehi[0] - elo[0] + ehi[1] - elo[1] + ehi[2] - elo[2]);
+  constexpr int RB = 7;      // rounds handled as one batch: all loads of a batch are issued before the first decision (32 * 7 >= 6^3 points)
   int npruned = 0;
-  for (int base = 0; base < vol; base += 32) {
-    const int li = base + lane; bool keep = false, to_buf = false;
-    if (li < vol) {
-      const int i = li % nx, j = (li / nx) % ny, k = li / (nx * ny);
-      const int pi0 = ps0 + i, pi1 = ps1 + j, pi2 = ps2 + k;
-      const double x0 = g.pc[g.pc_off[0] + pi0], x1 = g.pc[g.pc_off[1] + pi1], x2 = g.pc[g.pc_off[2] + pi2];
-      to_buf = tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] != 0;
-      // "inside" with a relative slack: which pass a pair belongs to is free to choose, the slack only keeps round-off of the
-      // reconstructed corners from moving on-boundary points to pass B
-      const double sl = 1e-9 * (ehi[0] - elo[0] + ehi[1] - elo[1] + ehi[2] - elo[2]);
-      const bool inner = x0 >= elo[0] - sl && x0 <= ehi[0] + sl && x1 >= elo[1] - sl && x1 <= ehi[1] + sl && x2 >= elo[2] - sl && x2 <= ehi[2] + sl;
-      if (PASS == 0) keep = to_buf || inner || !prune;
-      else if (!to_buf && !inner) {
-        const double e0 = fmax(fmax(tlo[0] - x0, x0 - thi[0]), 0.0), e1 = fmax(fmax(tlo[1] - x1, x1 - thi[1]), 0.0), e2 = fmax(fmax(tlo[2] - x2, x2 - thi[2]), 0.0);
-        const double lb2 = fma(e2, e2, fma(e1, e1, e0 * e0));
-        const double cur = dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0];
-        keep = !(lb2 > cur * cur * (1.0 + 1e-10));
-        if (!keep) npruned++;
+  for (int base0 = 0; base0 < vol; base0 += 32 * RB) {
+    double lb2[RB], cur[RB]; int flags[RB];      // flags: bit 0 valid candidate of this pass, bit 1 to_buf, bit 2 needs the bound test
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      const int li = base0 + r * 32 + lane;
+      flags[r] = 0; lb2[r] = 0.0; cur[r] = R2S_BIG;
+      if (li < vol) {
+        const int i = li % nx, j = (li / nx) % ny, k = li / (nx * ny);
+        const int pi0 = ps0 + i, pi1 = ps1 + j, pi2 = ps2 + k;
+        const double x0 = fma(g.cell, (double)pi0, g.amin[0]), x1 = fma(g.cell, (double)pi1, g.amin[1]), x2 = fma(g.cell, (double)pi2, g.amin[2]);
+        const bool to_buf = ftile && tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] != 0;
+        const bool inner = x0 >= elo[0] - sl && x0 <= ehi[0] + sl && x1 >= elo[1] - sl && x1 <= ehi[1] + sl && x2 >= elo[2] - sl && x2 <= ehi[2] + sl;
+        if (PASS == 0) { if (to_buf || inner || !prune) flags[r] = 1 | (to_buf ? 2 : 0); }
+        else if (!to_buf && !inner) {
+          const double e0 = fmax(fmax(tlo[0] - x0, x0 - thi[0]), 0.0), e1 = fmax(fmax(tlo[1] - x1, x1 - thi[1]), 0.0), e2 = fmax(fmax(tlo[2] - x2, x2 - thi[2]), 0.0);
+          lb2[r] = fma(e2, e2, fma(e1, e1, e0 * e0));
+          cur[r] = dist[((i64)pi2 * g.np[1] + pi1) * g.np[0] + pi0];
+          flags[r] = 1 | 4;
+        }
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-      u64 pos = 0;
-      if (lane == 0) pos = atomicAdd(&cnt[0], (u64)__popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (keep) plist[pos + __popc(m & ((1u << lane) - 1))] = ((u64)(to_buf ? 1 : 0) << 63) | ((u64)a << PL_LI_BITS) | (u64)li;
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      bool keep = (flags[r] & 1) != 0;
+      if (PASS == 1 && keep && lb2[r] > cur[r] * cur[r] * (1.0 + 1e-10)) { keep = false; npruned++; }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        u64 pos = 0;
+        if (lane == 0) pos = atomicAdd(&cnt[0], (u64)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (keep) plist[pos + __popc(m & ((1u << lane) - 1))] = ((u64)((flags[r] >> 1) & 1) << 63) | ((u64)a << PL_LI_BITS) | (u64)(base0 + r * 32 + lane);
+      }
     }
   }
   if (PASS == 1) {
@@ -805,7 +823,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
         CK(ctx->plist.reserve(sizeof(u64) * (size_t)(npairs + 1)));
         u64 *pc = ctx->counters.as<u64>() + NCTR;      // 4 words behind the statistics slots: [0],[1] pass A, [2],[3] pass B
         BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
-        k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, box); LAUNCH_CHECK();
+        k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box); LAUNCH_CHECK();
         const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * 5 * 4;
         k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc); LAUNCH_CHECK();
         k_project_list<<<pgrid, 128, 0, st>>>(pl, pc, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();

@@ -10,15 +10,19 @@
 #include <float.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <cuda.h>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
 
 // ------------------------------------------------------------------------------------------------ process_vector (:15-22)
-__global__ void __launch_bounds__(256) k_to_f32(i64 n, i64 v0, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
+__global__ void __launch_bounds__(256) k_to_f32(i64 n, i64 v0, int nx, int px, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
+  // sdf: rows of nx doubles; s: rows of px >= nx floats (the pad stays zero).  n values starting at the unpadded offset v0 (a multiple of nx).
   __shared__ float red[8];
   float a = -1.0f;
+  const i64 row0 = v0 / nx;
   for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) {
-    float f = (float)sdf[v0 + v]; s[v] = f; float af = fabsf(f); if (af < 1.0e9f) a = fmaxf(a, af);
+    const i64 row = v / nx; const int i = (int)(v - row * nx);
+    float f = (float)sdf[v0 + v]; s[(row0 + row) * px + i] = f; float af = fabsf(f); if (af < 1.0e9f) a = fmaxf(a, af);
   }
   for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_down_sync(0xffffffffu, a, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
@@ -39,72 +43,114 @@ __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__re
 // ------------------------------------------------------------------------------------------------ 81-point stencil
 // weights by squared offset m = di^2+dj^2+dk^2 <= 6
 struct StencilW { float w[8]; };
-// ---- plane marching (2.5-D blocking), two outputs per thread ----------------------------------------------------------------
-// A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane (with its x-y halo) is staged
-// once in shared memory; a thread owns two x-adjacent columns: the six row values it needs come in as three 8-byte shared-memory loads
-// and serve both outputs.  The tap weight depends on the squared distance only and w[m] = exp(-m), so w[m2 + dz^2] = w[m2] * w[dz^2]:
-// the in-plane sums S9 (taps with m2 <= 2) and S21 = S9 + S12 (all 21 in-plane taps) are formed once per input plane and enter the
-// five output planes (rotating register queue) as a2 += S21, a1/a3 += w[1] S21, a0/a4 += w[4] S9 -- 27 FMA-pipe operations per column
-// and plane instead of 81.  The products w[m2] * w[dz^2] differ from float(exp(-(m2 + dz^2))) by Float32 round-off (mat-vec 4e-7
-// relative; CG iteration counts and weights equal to the oracle's, tests/test_gpu_parity.py).
+// ---- plane marching (2.5-D blocking) with TMA-staged planes, two outputs per thread ------------------------------------------------
+// A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane tile (36 x 20 floats with its
+// x-y halo) is brought into shared memory by ONE bulk tensor copy (cp.async.bulk.tensor.3d, TMA) issued by one thread NST - 1 planes
+// ahead and signalled through an mbarrier: no per-thread address arithmetic, no bounds tests (coordinates outside the grid are
+// zero-filled by the TMA unit -- K has no entries there), loads in flight for several planes.  The fields are stored with a row pitch
+// that is a multiple of 4 floats (TMA needs 16-byte global strides); the tensor map carries the logical extent nx.
+// CG form (BETA): the stencil input is u_new = r + beta * u_old; the r and u_old tiles arrive by TMA, the threads combine them into a
+// second shared buffer and write the interior back to u_new (separate array: other CTAs still read u_old for their halos).
+// A thread owns two x-adjacent columns: the six row values it needs come in as three 8-byte shared-memory loads and serve both
+// outputs.  The tap weight depends on the squared distance only and w[m] = exp(-m), so w[m2 + dz^2] = w[m2] * w[dz^2]: the in-plane
+// sums S9 (taps with m2 <= 2) and S21 = S9 + S12 (all 21 in-plane taps) are formed once per input plane and enter the five output
+// planes (rotating register queue) as a2 += S21, a1/a3 += w[1] S21, a0/a4 += w[4] S9 -- 27 FMA-pipe operations per column and plane
+// instead of 81.  The products w[m2] * w[dz^2] differ from float(exp(-(m2 + dz^2))) by Float32 round-off (mat-vec 4e-7 relative; CG
+// iteration counts and weights equal to the oracle's, tests/test_gpu_parity.py).
 #define S3_X 32            // outputs per CTA in x (16 threads x 2)
 #define S3_Y 16
+#define S3_TX (S3_X + 4)   // 36 x 20 tile; 36 floats = 144 B per row (a multiple of 16 B, as the TMA box requires)
+#define S3_TY (S3_Y + 4)
+#define S3_NST 4           // TMA stages: loads run 3 planes ahead of the compute
+#define S3_TILE_BYTES (S3_TX * S3_TY * 4)
+#define S3_SLOT 3072       // stage stride in shared memory (tile = 2880 B, destinations 128-byte aligned)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
 template <bool BETA>
-__global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz, int kz0, int kz1, int zc, const float *__restrict__ in, const float *__restrict__ r,
-                                                          const float *__restrict__ u, float *__restrict__ unew, const float *__restrict__ scal,
-                                                          float *__restrict__ out, double *__restrict__ partial, StencilW W) {
-  constexpr int TX = S3_X + 4, TY = S3_Y + 4, NT = TX * TY;      // 36 x 20 tile, row pitch 36 floats (8-byte aligned pairs)
-  __shared__ __align__(8) float sm[2][TY][TX];
+__global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nx, int ny, int nz, int px,
+                                                       int kz0, int kz1, int zc, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
+                                                       double *__restrict__ partial, StencilW W) {
+  constexpr int TX = S3_TX, TY = S3_TY, NT = TX * TY, NARR = BETA ? 2 : 1;
+  __shared__ __align__(128) unsigned char stage[S3_NST * NARR * S3_SLOT];
+  __shared__ __align__(16) float comb[BETA ? 2 : 1][BETA ? NT : 2];      // combined plane r + beta * u (double buffered), CG form only
+  __shared__ __align__(8) unsigned long long full[S3_NST];
   __shared__ double red[8];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int bx = blockIdx.x * S3_X, by = blockIdx.y * S3_Y;
   const int zc0 = kz0 + blockIdx.z * zc, zc1 = min(zc0 + zc, kz1);      // zc output planes per CTA (chosen by the host so that the chunks are even)
+  const int np = zc1 - zc0 + 4;                                           // input planes zc0 - 2 .. zc1 + 1
   const int gx = bx + 2 * tx, gy = by + ty;
   const bool in0 = gx < nx && gy < ny, in1 = gx + 1 < nx && gy < ny;
   float beta = 0.0f;
   if (BETA) beta = scal[0];
-  int e_lx[3], e_ly[3]; bool e_ok[3], e_own[3], e_use[3]; i64 e_off[3];
+  if (tid == 0) {
 #pragma unroll
-  for (int q = 0; q < 3; q++) {
-    int t = tid + q * 256;
-    e_use[q] = t < NT;
-    if (!e_use[q]) t = 0;
-    e_ly[q] = t / TX; e_lx[q] = t % TX;
-    int x = bx + e_lx[q] - 2, y = by + e_ly[q] - 2;
-    e_ok[q] = e_use[q] && x >= 0 && x < nx && y >= 0 && y < ny;
-    e_own[q] = e_ok[q] && e_lx[q] >= 2 && e_lx[q] < TX - 2 && e_ly[q] >= 2 && e_ly[q] < TY - 2;
-    e_off[q] = (i64)y * nx + x;
+    for (int q = 0; q < S3_NST; q++) mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const i64 pl = (i64)nx * ny;
+  __syncthreads();
+  auto issue = [&](int p) {      // thread 0: plane p of this CTA's march into stage p % NST
+    const int st = p % S3_NST;
+    mbar_expect_tx(&full[st], S3_TILE_BYTES * NARR);
+    tma_load_3d(stage + (st * NARR) * S3_SLOT, &mapA, bx - 2, by - 2, zc0 - 2 + p, &full[st]);
+    if (BETA) tma_load_3d(stage + (st * NARR + 1) * S3_SLOT, &mapB, bx - 2, by - 2, zc0 - 2 + p, &full[st]);
+  };
+  if (tid == 0) for (int p = 0; p < S3_NST - 1 && p < np; p++) issue(p);
+  // elements of the tile this thread combines per plane (CG form): interior ones are also written back to u_new
+  int e_ok[3]; i64 e_off[3];
+  if (BETA) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const int t = tid + q * 256, ly = t / TX, lx = t % TX, x = bx + lx - 2, y = by + ly - 2;
+      e_ok[q] = (t < NT ? 1 : 0) | ((t < NT && lx >= 2 && lx < TX - 2 && ly >= 2 && ly < TY - 2 && x < nx && y < ny) ? 2 : 0);
+      e_off[q] = (i64)y * px + x;
+    }
+  }
+  const i64 pl = (i64)px * ny;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f;
   float ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f;
   double dsum = 0.0;
-  float pv[3];
-  auto fetch = [&](int z) {
+  for (int p = 0; p < np; p++) {
+    const int st = p % S3_NST, zin = zc0 - 2 + p;
+    // the stage that plane p + NST - 1 goes into was read during iteration p - 1; everybody has passed that iteration's barrier
+    if (tid == 0 && p + S3_NST - 1 < np) issue(p + S3_NST - 1);
+    mbar_wait(&full[st], (unsigned)((p / S3_NST) & 1));
+    const float *tile;
+    if (BETA) {
+      const float *tr = reinterpret_cast<const float *>(stage + (st * NARR) * S3_SLOT), *tu = reinterpret_cast<const float *>(stage + (st * NARR + 1) * S3_SLOT);
+      float *cb = comb[p & 1];
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      float v = 0.0f;
-      if (e_ok[q] && z >= 0 && z < nz) {
-        i64 gi = (i64)z * pl + e_off[q];
-        if (BETA) { v = r[gi] + beta * u[gi]; if (e_own[q] && z >= zc0 && z < zc1) unew[gi] = v; }
-        else v = in[gi];
-      }
-      pv[q] = v;
+      for (int q = 0; q < 3; q++)
+        if (e_ok[q] & 1) {
+          const int t = tid + q * 256;
+          const float v = tr[t] + beta * tu[t];
+          cb[t] = v;
+          if ((e_ok[q] & 2) && zin >= zc0 && zin < zc1) unew[(i64)zin * pl + e_off[q]] = v;
+        }
+      __syncthreads();      // comb[p & 1] complete; also: every thread is done with the raw stage of plane p and with comb[(p + 1) & 1] of plane p - 1
+      tile = cb;
+    } else {
+      tile = reinterpret_cast<const float *>(stage + st * S3_SLOT);
     }
-  };
-  fetch(zc0 - 2);
-  for (int zin = zc0 - 2; zin < zc1 + 2; zin++) {
-    const int buf = (zin - zc0 + 2) & 1;
-#pragma unroll
-    for (int q = 0; q < 3; q++)
-      if (e_use[q]) sm[buf][e_ly[q]][e_lx[q]] = pv[q];
-    __syncthreads();
-    if (zin + 1 < zc1 + 2) fetch(zin + 1);
     float ctra = 0.f, ctrb = 0.f;
     float s9a = 0.f, s9b = 0.f, s12a = 0.f, s12b = 0.f;
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++) {
-      const float2 *row = reinterpret_cast<const float2 *>(&sm[buf][ty + 2 + dj][2 * tx]);
+      const float2 *row = reinterpret_cast<const float2 *>(tile + (ty + 2 + dj) * TX + 2 * tx);
       const float2 p0 = row[0], p1 = row[1], p2 = row[2];
       const float v[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};       // x0-2 .. x0+3
       if (dj == 0) { ctra = v[2]; ctrb = v[3]; }
@@ -124,12 +170,13 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
     }
     const int zo = zin - 2;
     if (zo >= zc0) {
-      const i64 gi = (i64)zo * pl + (i64)gy * nx + gx;
+      const i64 gi = (i64)zo * pl + (i64)gy * px + gx;
       if (in0) { out[gi] = a0; dsum += (double)ca0 * (double)a0; }
       if (in1) { out[gi + 1] = b0; dsum += (double)cb0 * (double)b0; }
     }
     a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f; b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0.f;
     ca0 = ca1; ca1 = ctra; cb0 = cb1; cb1 = ctrb;
+    if (!BETA) __syncthreads();      // the stage of plane p may be overwritten by the load issued at the top of the next iteration
   }
   for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
   if ((tid & 31) == 0) red[tid >> 5] = dsum;
@@ -138,6 +185,24 @@ __global__ void __launch_bounds__(256) k_stencil81_march2(int nx, int ny, int nz
     double a = 0; for (int i = 0; i < 8; i++) a += red[i];
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
+}
+// tensor map of a coarse Float32 field (nx x ny x nz values, row pitch px floats) with the 36 x 20 x 1 box of the stencil tiles
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int stencil_tensor_map(r2s_ctx *ctx, CUtensorMap *map, const float *base, int nx, int ny, int nz, int px) {
+  static tmap_encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      FAIL("cuTensorMapEncodeTiled is not available in this driver (TMA-staged stencil needs CUDA 12 on sm_90+)");
+    encode = (tmap_encode_fn)fn;
+  }
+  const cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz}, gstr[2] = {(cuuint64_t)px * 4, (cuuint64_t)px * ny * 4};
+  const cuuint32_t box[3] = {S3_TX, S3_TY, 1}, estr[3] = {1, 1, 1};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { char b[96]; snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc); FAIL(b); }
+  return 0;
 }
 // CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, uc, rr}
 __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restrict__ dst) {
@@ -191,10 +256,11 @@ __global__ void __launch_bounds__(256) k_dot_self(i64 n, const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------ min / max of a float field
-__global__ void __launch_bounds__(256) k_minmax(i64 n, const float *__restrict__ a, unsigned *__restrict__ mm) {   // mm[0] = ordered-min, mm[1] = ordered-max
+__global__ void __launch_bounds__(256) k_minmax(i64 n, int nx, int px, const float *__restrict__ a, unsigned *__restrict__ mm) {   // mm[0] = ordered-min, mm[1] = ordered-max
+  // a: rows of px floats of which the first nx count (n = padded length, a multiple of px)
   __shared__ float rlo[8], rhi[8];
   float lo = INFINITY, hi = -INFINITY;
-  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) { float x = a[v]; lo = fminf(lo, x); hi = fmaxf(hi, x); }
+  for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += (i64)gridDim.x * blockDim.x) { if ((int)(v % px) < nx) { float x = a[v]; lo = fminf(lo, x); hi = fmaxf(hi, x); } }
   for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_down_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_down_sync(0xffffffffu, hi, o)); }
   if ((threadIdx.x & 31) == 0) { rlo[threadIdx.x >> 5] = lo; rhi[threadIdx.x >> 5] = hi; }
   __syncthreads();
@@ -211,19 +277,19 @@ static inline float ordered_to_float(unsigned b) { b = (b & 0x80000000u) ? (b & 
 // ------------------------------------------------------------------------------------------------ volume (CalcVolumeFromSDF.jl:26-125)
 // pass 1: classify cells of (sdf - th): full cells counted, cut cells appended to a list.  Grid-stride; counts are
 // aggregated per block (one atomic per block for the full cells, one per block-iteration for the list slots).
-__global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, u64 *__restrict__ acc,
+__global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, int px, const float *__restrict__ sdf, float th, float iso, u64 *__restrict__ acc,
                                                       int *__restrict__ cutlist, int cutcap) {
   __shared__ int s_warp[8]; __shared__ int s_base;
-  const i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1), sxy = (i64)nx * ny;
+  const i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1), sxy = (i64)px * ny;      // px = row pitch of the field (>= nx)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nfull = 0;
   for (i64 c0 = (i64)blockIdx.x * 256; c0 < ncell; c0 += (i64)gridDim.x * 256) {
     i64 c = c0 + threadIdx.x; bool cut = false;
     if (c < ncell) {
       int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
-      i64 b = ((i64)k * ny + j) * nx + i;
-      float v0 = sdf[b] - th, v1 = sdf[b + 1] - th, v2 = sdf[b + nx] - th, v3 = sdf[b + nx + 1] - th;
-      float v4 = sdf[b + sxy] - th, v5 = sdf[b + sxy + 1] - th, v6 = sdf[b + sxy + nx] - th, v7 = sdf[b + sxy + nx + 1] - th;
+      i64 b = ((i64)k * ny + j) * px + i;
+      float v0 = sdf[b] - th, v1 = sdf[b + 1] - th, v2 = sdf[b + px] - th, v3 = sdf[b + px + 1] - th;
+      float v4 = sdf[b + sxy] - th, v5 = sdf[b + sxy + 1] - th, v6 = sdf[b + sxy + px] - th, v7 = sdf[b + sxy + px + 1] - th;
       float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
       float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
       if (!(mx < iso)) { if (mn >= iso) nfull++; else cut = true; }
@@ -255,20 +321,20 @@ __global__ void __launch_bounds__(256) k_vol_classify(int nx, int ny, int nz, co
 // CalcVolumeFromSDF.jl:88-103).  The cell's Float32 sum of w_i w_j w_k over inside points (iq outer, kq
 // inner, a fixed order) is accumulated across cells as a 2^-37 fixed-point integer (deterministic).
 struct GaussF { float x[9]; float w[9]; };
-__global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
+__global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int px, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
                                                  GaussF G, u64 *__restrict__ acc) {
   const int ncut = (int)min((u64)cutcap, acc[1]);
   const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
-  const i64 sxy = (i64)nx * ny;
+  const i64 sxy = (i64)px * ny;
   u64 local = 0;
   for (int base = blockIdx.x * blockDim.x; base < ncut; base += nthr) {      // warp-uniform trip count
     const int idx = base + threadIdx.x;
     if (idx < ncut) {
       const i64 c = cutlist[idx];
       const int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
-      const i64 b = ((i64)k * ny + j) * nx + i;
-      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
-      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+      const i64 b = ((i64)k * ny + j) * px + i;
+      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + px] - th, c110 = sdf[b + px + 1] - th;
+      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + px] - th, c111 = sdf[b + sxy + px + 1] - th;
       float part = 0.0f;
 #pragma unroll 1      // the 81-point inner body stays unrolled; unrolling all 729 points (60 KB of code) thrashed the instruction cache
       for (int iq = 0; iq < 9; iq++) {
@@ -305,11 +371,11 @@ __global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int nz, const f
 // result is bit-identical to re-classifying every cell at every step, at ~3 full passes instead of 40.
 // acc: [0] full cells of this step  [1] cut count  [2] cut fixed-point sum  [3] permanently full  [4],[5] list sizes (ping-pong)
 template <bool IMPLICIT, bool EMIT>
-__global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th,
+__global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int px, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th,
                                                   const int *__restrict__ list_in, const u64 *__restrict__ n_in_ptr, int *__restrict__ list_out,
                                                   u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
   __shared__ int s_cut[8], s_keep[8]; __shared__ int s_base_cut, s_base_keep;
-  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)nx * ny;
+  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)px * ny;
   const i64 n_in = IMPLICIT ? cpl * (i64)(kc1 - kc0) : (i64)*n_in_ptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nfull = 0, nperm = 0;
@@ -318,9 +384,9 @@ __global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int kc0, int k
     if (t < n_in) {
       c = IMPLICIT ? (int)(t + cpl * kc0) : list_in[t];
       int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = (int)(c / cpl);
-      i64 b = ((i64)k * ny + j) * nx + i;
-      float v0 = sdf[b], v1 = sdf[b + 1], v2 = sdf[b + nx], v3 = sdf[b + nx + 1];
-      float v4 = sdf[b + sxy], v5 = sdf[b + sxy + 1], v6 = sdf[b + sxy + nx], v7 = sdf[b + sxy + nx + 1];
+      i64 b = ((i64)k * ny + j) * px + i;
+      float v0 = sdf[b], v1 = sdf[b + 1], v2 = sdf[b + px], v3 = sdf[b + px + 1];
+      float v4 = sdf[b + sxy], v5 = sdf[b + sxy + 1], v6 = sdf[b + sxy + px], v7 = sdf[b + sxy + px + 1];
       float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
       float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
       if (EMIT && mn >= hi) nperm++;                         // full for every threshold still to come
@@ -359,20 +425,20 @@ __global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int kc0, int k
 // any quadrature order 1..32 (calculate_volume_from_sdf's detailed_quad_order; the convergence tests of the reference use 20): same
 // organisation as k_vol_cut, loops not unrolled, abscissae / weights read from the kernel-parameter bank with uniform indices
 struct GaussNF { float x[32]; float w[32]; int n; };
-__global__ void __launch_bounds__(128) k_vol_cut_n(int nx, int ny, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
+__global__ void __launch_bounds__(128) k_vol_cut_n(int nx, int ny, int px, const float *__restrict__ sdf, float th, float iso, const int *__restrict__ cutlist, int cutcap,
                                                    GaussNF G, u64 *__restrict__ acc) {
   const int ncut = (int)min((u64)cutcap, acc[1]);
   const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
-  const i64 sxy = (i64)nx * ny;
+  const i64 sxy = (i64)px * ny;
   u64 local = 0;
   for (int base = blockIdx.x * blockDim.x; base < ncut; base += nthr) {
     const int idx = base + threadIdx.x;
     if (idx < ncut) {
       const i64 c = cutlist[idx];
       const int i = (int)(c % (nx - 1)), j = (int)((c / (nx - 1)) % (ny - 1)), k = (int)(c / ((i64)(nx - 1) * (ny - 1)));
-      const i64 b = ((i64)k * ny + j) * nx + i;
-      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + nx] - th, c110 = sdf[b + nx + 1] - th;
-      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + nx] - th, c111 = sdf[b + sxy + nx + 1] - th;
+      const i64 b = ((i64)k * ny + j) * px + i;
+      const float c000 = sdf[b] - th, c100 = sdf[b + 1] - th, c010 = sdf[b + px] - th, c110 = sdf[b + px + 1] - th;
+      const float c001 = sdf[b + sxy] - th, c101 = sdf[b + sxy + 1] - th, c011 = sdf[b + sxy + px] - th, c111 = sdf[b + sxy + px + 1] - th;
       float part = 0.0f;
       for (int iq = 0; iq < G.n; iq++) {
         const float xi = (G.x[iq] + 1) / 2, xm = 1.0f - xi;
@@ -397,7 +463,7 @@ __global__ void __launch_bounds__(128) k_vol_cut_n(int nx, int ny, const float *
 static GaussF gauss9f() { GaussTab t = gauss_legendre_host(9); GaussF g; for (int i = 0; i < 9; i++) { g.x[i] = (float)t.x[i]; g.w[i] = (float)t.w[i]; } return g; }
 
 // volume of {sdf - th >= iso}; edge = cell edge length (Float32 like the reference)
-static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, float th, float edge, float iso, int order, double *vol) {
+static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, int px, float th, float edge, float iso, int order, double *vol) {
   cudaStream_t st = ctx->stream;
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("calculate_volume_from_sdf: grid too large for 32-bit cell ids");
@@ -407,12 +473,12 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
   for (int attempt = 0; attempt < 2; attempt++) {
     int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(acc, 0, sizeof(u64) * 4, st));
-    k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
-    if (order == 9) k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, nz, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc);
+    k_vol_classify<<<min(cdiv(ncell, 256), 148 * 16), 256, 0, st>>>(nx, ny, nz, px, sdf, th, iso, acc, ctx->cutlist.as<int>(), cutcap); LAUNCH_CHECK();
+    if (order == 9) k_vol_cut<<<148 * 16, 128, 0, st>>>(nx, ny, px, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G9, acc);
     else {
       GaussTab t = gauss_legendre_host(order); GaussNF G; G.n = order;
       for (int q = 0; q < 32; q++) { G.x[q] = q < order ? (float)t.x[q] : 0.0f; G.w[q] = q < order ? (float)t.w[q] : 0.0f; }
-      k_vol_cut_n<<<148 * 16, 128, 0, st>>>(nx, ny, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G, acc);
+      k_vol_cut_n<<<148 * 16, 128, 0, st>>>(nx, ny, px, sdf, th, iso, ctx->cutlist.as<int>(), cutcap, G, acc);
     }
     LAUNCH_CHECK();
     u64 h[3];
@@ -431,28 +497,26 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, fl
 // one cell row; every lane loads the 4 values of its x-column (coalesced) and takes the neighbouring column's min / max from
 // lane + 1, so a cell costs 4 loads instead of 8 and no div/mod.  Same classification, same integer accumulation.
 template <bool EMIT>
-__global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th, int *__restrict__ list_out,
+__global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int px, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th, int *__restrict__ list_out,
                                                   u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
-  __shared__ int s_cut[8], s_keep[8]; __shared__ int s_base_cut, s_base_keep;
+  // no block-level synchronisation: list slots are claimed per warp (one atomic per warp and list, only when the row segment holds such
+  // cells -- most segments hold none); the order of the lists does not matter, the volume is an exact integer sum
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nseg = (nx - 1 + 30) / 31, nrow = (ny - 1) * (kc1 - kc0);
-  const i64 ntask = (i64)nrow * nseg, sxy = (i64)nx * ny;
+  const i64 ntask = (i64)nrow * nseg, sxy = (i64)px * ny;
   int nfull = 0, nperm = 0;
-  for (i64 base = (i64)blockIdx.x * 8; base < ntask; base += (i64)gridDim.x * 8) {
-    const i64 task = base + warp;
+  for (i64 task = (i64)blockIdx.x * 8 + warp; task < ntask; task += (i64)gridDim.x * 8) {      // warp-uniform
     bool cut = false, keep = false; int c = 0;
-    float cmn = INFINITY, cmx = -INFINITY; int i = 0, j = 0, k = 0;
-    if (task < ntask) {
-      const int row = (int)(task / nseg), seg = (int)(task % nseg);
-      j = row % (ny - 1); k = kc0 + row / (ny - 1); i = seg * 31 + lane;
-      if (i < nx) {
-        const i64 b = ((i64)k * ny + j) * nx + i;
-        const float v0 = sdf[b], v1 = sdf[b + nx], v2 = sdf[b + sxy], v3 = sdf[b + sxy + nx];
-        cmn = fminf(fminf(v0, v1), fminf(v2, v3)); cmx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-      }
+    float cmn = INFINITY, cmx = -INFINITY;
+    const int row = (int)(task / nseg), seg = (int)(task % nseg);
+    const int j = row % (ny - 1), k = kc0 + row / (ny - 1), i = seg * 31 + lane;
+    if (i < nx) {
+      const i64 b = ((i64)k * ny + j) * px + i;
+      const float v0 = sdf[b], v1 = sdf[b + px], v2 = sdf[b + sxy], v3 = sdf[b + sxy + px];
+      cmn = fminf(fminf(v0, v1), fminf(v2, v3)); cmx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
     }
     const float nmn = __shfl_down_sync(0xffffffffu, cmn, 1), nmx = __shfl_down_sync(0xffffffffu, cmx, 1);
-    if (task < ntask && lane < 31 && i < nx - 1) {
+    if (lane < 31 && i < nx - 1) {
       const float mn = fminf(cmn, nmn), mx = fmaxf(cmx, nmx);
       c = (int)(((i64)k * (ny - 1) + j) * (nx - 1) + i);
       if (EMIT && mn >= hi) nperm++;
@@ -462,31 +526,22 @@ __global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int kc0, int k
         if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
       }
     }
-    unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
-    if (__syncthreads_or((mc | mk) != 0)) {
-      if (lane == 0) { s_cut[warp] = __popc(mc); s_keep[warp] = __popc(mk); }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int tc = 0, tk = 0;
-        for (int w = 0; w < 8; w++) { int a = s_cut[w]; s_cut[w] = tc; tc += a; int b2 = s_keep[w]; s_keep[w] = tk; tk += b2; }
-        s_base_cut = tc ? (int)atomicAdd(&acc[1], (u64)tc) : 0;
-        s_base_keep = tk ? (int)atomicAdd(n_out_ptr, (u64)tk) : 0;
-      }
-      __syncthreads();
-      if (cut) { int slot = s_base_cut + s_cut[warp] + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
-      if (keep) list_out[s_base_keep + s_keep[warp] + __popc(mk & ((1u << lane) - 1))] = c;
-      __syncthreads();
+    const unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
+    if (mc) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(&acc[1], (u64)__popc(mc));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (cut) { const int slot = base + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
+    }
+    if (EMIT && mk) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(n_out_ptr, (u64)__popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) list_out[base + __popc(mk & ((1u << lane) - 1))] = c;
     }
   }
   for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
-  __syncthreads();
-  if (lane == 0) { s_cut[warp] = nfull; s_keep[warp] = nperm; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tf = 0, tp = 0; for (int w = 0; w < 8; w++) { tf += s_cut[w]; tp += s_keep[w]; }
-    if (tf) atomicAdd(&acc[0], (u64)tf);
-    if (tp) atomicAdd(&acc[3], (u64)tp);
-  }
+  if (lane == 0) { if (nfull) atomicAdd(&acc[0], (u64)nfull); if (nperm) atomicAdd(&acc[3], (u64)nperm); }
 }
 // acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
 __global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red) {
@@ -494,13 +549,13 @@ __global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restr
 }
 // state of one LS_Threshold search (see k_vol_step)
 struct VolBisect {
-  const float *sdf; int nx, ny, kc0, kc1; float edge; int step, cur; i64 n_cur; u64 *acc;
+  const float *sdf; int nx, ny, px, kc0, kc1; float edge; int step, cur; i64 n_cur; u64 *acc;
 };
-static int vol_bisect_begin(r2s_ctx *ctx, VolBisect &vb, const float *sdf, int nx, int ny, int nz, int kc0, int kc1, float edge) {
+static int vol_bisect_begin(r2s_ctx *ctx, VolBisect &vb, const float *sdf, int nx, int ny, int nz, int px, int kc0, int kc1, float edge) {
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("LS_Threshold: grid too large for 32-bit cell ids");
   CK(ctx->f_scal.reserve(512));
-  vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0;
+  vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.px = px; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0;
   vb.n_cur = (i64)(nx - 1) * (ny - 1) * (i64)(kc1 - kc0);
   vb.acc = (u64 *)((char *)ctx->f_scal.p + 128);       // acc[0..7], red[0..3] behind it
   CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 12, ctx->stream));
@@ -526,16 +581,16 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
       if (emit) CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
       const i64 ntask = (i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31);
       const int rgrid = (int)std::min<i64>(std::max<i64>(cdiv(ntask, 8), 1), 148 * 16);
-      if (implicit && !emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else if (implicit) k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else k_vol_step<false, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lin, nin, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      if (implicit && !emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else if (implicit) k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else k_vol_step<false, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lin, nin, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
     } else {
       // the cut list overflowed: it has been grown; re-classify (the retired cells are already accounted for)
-      if (!emit) k_vol_rows<false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31), 8), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      if (!emit) k_vol_rows<false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31), 8), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
     }
     LAUNCH_CHECK();
-    k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, 0, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
+    k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.px, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
     // cross-rank sum of (full cells, overflow flag, cut sum); integers, so the total does not depend on the slab count
     u64 *red = vb.acc + 8, hr[4];
     k_vol_pack<<<1, 1, 0, st>>>(vb.acc, cutcap, red); LAUNCH_CHECK();
@@ -560,7 +615,7 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
 int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, int order, double *vol) {
   if (order < 1 || order > 32) FAIL("calculate_volume_from_sdf: detailed_quad_order must be between 1 and 32");
   CK(ctx->cutlist.reserve(sizeof(int) * 1024));
-  return volume_dev(ctx, sdf_dev, (int)nx, (int)ny, (int)nz, 0.0f, edge, iso, order, vol);
+  return volume_dev(ctx, sdf_dev, (int)nx, (int)ny, (int)nz, (int)nx, 0.0f, edge, iso, order, vol);
 }
 
 // ------------------------------------------------------------------------------------------------ fine-grid evaluation (:363)
@@ -572,7 +627,7 @@ __constant__ TapTable c_taps;
 #define FN_Y 4
 #define FN_Z 4
 template <int SM>
-__global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, int nz, int fx, int fy, int fz, int kf0, const float *__restrict__ w, float th, float *__restrict__ out) {
+__global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, int nz, int px, int fx, int fy, int fz, int kf0, const float *__restrict__ w, float th, float *__restrict__ out) {
   // coarse tile covering this block's fine outputs, with halo 3 on each side (taps reach -2..+3)
   constexpr int CX = FN_X / SM + 6, CY = FN_Y / SM + 6 + 1, CZ = FN_Z / SM + 6 + 1;
   __shared__ float sm[CZ][CY][CX + 1];
@@ -582,7 +637,7 @@ __global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, 
     int lx = t % CX, ly = (t / CX) % CY, lz = t / (CX * CY);
     int gx = cbx + lx, gy = cby + ly, gz = cbz + lz;
     float v = 0.0f;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * nx + gx];
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * px + gx];
     sm[lz][ly][lx] = v;
   }
   __syncthreads();
@@ -648,7 +703,7 @@ __device__ __forceinline__ void f2_plane(const float (*sm)[F2_Y + 5][F2_X + 5], 
   }
 }
 // kc0/kc1: coarse planes whose fine outputs this launch produces (z-slab); fine planes 2c and 2c+1 (the latter if < fz)
-__global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny, int nz, int fx, int fy, int fz, int kc0, int kc1, const float *__restrict__ w, float th,
+__global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny, int nz, int px, int fx, int fy, int fz, int kc0, int kc1, const float *__restrict__ w, float th,
                                                                   float *__restrict__ out) {
   __shared__ float sm[F2_Z + 5][F2_Y + 5][F2_X + 5];
   const int cbx = blockIdx.x * F2_X, cby = blockIdx.y * F2_Y, cbz = kc0 + blockIdx.z * F2_Z;
@@ -657,7 +712,7 @@ __global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny
     int lx = t % TX, ly = (t / TX) % TY, lz = t / (TX * TY);
     int gx = cbx + lx - 2, gy = cby + ly - 2, gz = cbz + lz - 2;
     float v = 0.0f;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * nx + gx];
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nz) v = w[((i64)gz * ny + gy) * px + gx];
     sm[lz][ly][lx] = v;
   }
   __syncthreads();
@@ -736,7 +791,9 @@ static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
 // keeps up to 3 halo planes on each side valid.  With one rank [k0, k1) is the whole grid and every exchange is a no-op.
 int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double target, bool final_volume, float *th_out, float *vol_out) {
   const GridDev &g = ctx->g; cudaStream_t st = ctx->stream;
-  const int nx = g.np[0], ny = g.np[1], nz = g.np[2]; const i64 n = (i64)nx * ny * nz, pl = (i64)nx * ny;
+  // every coarse Float32 field (s, weights, r, u, c, lsf) is stored with a row pitch px = nx rounded up to 4 floats: the TMA tensor maps
+  // of the stencil need 16-byte global strides.  The pad columns are kept at zero (they take part in the element-wise CG kernels).
+  const int nx = g.np[0], ny = g.np[1], nz = g.np[2], px = (nx + 3) & ~3; const i64 upl = (i64)nx * ny, pl = (i64)px * ny, n = pl * nz;
   const int k0 = (int)ctx->k0, k1 = (int)ctx->k1;
   if (ctx->nranks == 1 && (k0 != 0 || k1 != nz)) FAIL("rbf smoothing on a z-slab needs the slab communicator (r2s_comm_init on every rank)");
   const int e0 = std::max(0, k0 - 2), e1 = std::min(nz, k1 + 2);        // owned planes + CG halo
@@ -753,7 +810,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   float *scal = ctx->f_scal.as<float>(); unsigned *ubits = (unsigned *)((char *)ctx->f_scal.p + 64); double *dsc = (double *)((char *)ctx->f_scal.p + 96);
   CK(cudaMemsetAsync(ctx->f_scal.p, 0, 256, st));
   float *s = ctx->f_s.as<float>();
-  k_to_f32<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, o_lo, ctx->sdf.as<double>(), s + o_lo, ubits); LAUNCH_CHECK();
+  CK(cudaMemsetAsync(s + o_lo, 0, sizeof(float) * (size_t)nown, st));      // pad columns
+  k_to_f32<<<(int)std::min<i64>(cdiv((i64)(k1 - k0) * upl, 256), CG_BLOCKS), 256, 0, st>>>((i64)(k1 - k0) * upl, (i64)k0 * upl, nx, px, ctx->sdf.as<double>(), s, ubits); LAUNCH_CHECK();
   if (r2s_allreduce(ctx, ubits, 1, 2)) return 1;                          // global max finite |v| (RBFs4Smoothing.jl:17)
   unsigned hb = 0;
   if (r2s_readback(ctx, &hb, ubits, sizeof(unsigned))) return 1;
@@ -779,6 +837,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     CK(cudaMemsetAsync(x + x_lo, 0, sizeof(float) * (size_t)next, st));
     CK(cudaMemsetAsync(u + x_lo, 0, sizeof(float) * (size_t)next, st));
     CK(cudaMemsetAsync(u + n + x_lo, 0, sizeof(float) * (size_t)next, st));
+    CK(cudaMemsetAsync(c + x_lo, 0, sizeof(float) * (size_t)next, st));      // pad columns of c enter r through the element-wise update
+    CUtensorMap tm_r, tm_u[2];
+    if (stencil_tensor_map(ctx, &tm_r, r, nx, ny, nz, px) || stencil_tensor_map(ctx, &tm_u[0], u, nx, ny, nz, px) || stencil_tensor_map(ctx, &tm_u[1], u + n, nx, ny, nz, px)) return 1;
+    int upar = 0;      // which half of u holds u_old
     CK(cudaMemcpyAsync(r + x_lo, s + x_lo, sizeof(float) * (size_t)next, cudaMemcpyDeviceToDevice, st));
     int nob = (int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS);
     k_dot_self<<<nob, 256, 0, st>>>(nown, r + o_lo, part); LAUNCH_CHECK();
@@ -795,7 +857,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
       if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
       // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      k_stencil81_march2<true><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, nullptr, r, u_old, u_new, scal, c, part, W);
+      k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W);
       LAUNCH_CHECK();
       if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
       k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
@@ -821,7 +883,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       if (r2s_readback(ctx, hs, scal, sizeof(hs))) return 1;
       residual = hs[2]; iters++;
       if (probe) for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1]));
-      { float *t = u_old; u_old = u_new; u_new = t; }
+      { float *t = u_old; u_old = u_new; u_new = t; upar ^= 1; }
     }
     wgt = x;
     if (r2s_halo_exchange_f32(ctx, x, pl, k0, k1, nz, 2, 3)) return 1;      // the fine evaluation reaches 3 planes up
@@ -830,13 +892,17 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[6], st));
   // LSF on the coarse grid (:357) = K * weights
   float *lsf = ctx->f_lsf.as<float>();
-  k_stencil81_march2<false><<<sgrid, sthreads, 0, st>>>(nx, ny, nz, k0, k1, zc, wgt, nullptr, nullptr, nullptr, nullptr, lsf, part, W);
+  {
+    CUtensorMap tm_w;
+    if (stencil_tensor_map(ctx, &tm_w, wgt, nx, ny, nz, px)) return 1;
+    k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W);
+  }
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
   // LS_Threshold (:265-300)
   unsigned init_mm[2] = {0xffffffffu, 0u};
   CK(cudaMemcpyAsync(ubits + 2, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
-  k_minmax<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
+  k_minmax<<<(int)std::min<i64>(cdiv(nown, 256), CG_BLOCKS), 256, 0, st>>>(nown, nx, px, lsf + o_lo, ubits + 2); LAUNCH_CHECK();
   if (r2s_group_start(ctx)) return 1;
   if (r2s_allreduce(ctx, ubits + 2, 1, 3)) return 1;
   if (r2s_allreduce(ctx, ubits + 3, 1, 2)) return 1;
@@ -855,7 +921,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   }
   double eps = 1.0; int nb = 0; float th = 0.0f; double v = 0.0; bool have_prev = false; float th_prev = 0.0f;
   VolBisect vb;
-  if (vol_bisect_begin(ctx, vb, lsf, nx, ny, nz, k0, std::min(k1, nz - 1), edge)) return 1;
+  if (vol_bisect_begin(ctx, vb, lsf, nx, ny, nz, px, k0, std::min(k1, nz - 1), edge)) return 1;
   while (nb < 40 && eps > 1.0e-4) {
     th = (lo + hi) / 2;
     // once lo and hi are adjacent floats the midpoint repeats: the volume of an identical threshold is not recomputed
@@ -880,10 +946,10 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       const int f0 = smooth * c0, f1 = (c1 < nz) ? smooth * c1 : fz;
       if (smooth == 1) {
         dim3 fgrid(cdiv(fx, FN_X), cdiv(fy, FN_Y), cdiv(f1 - f0, FN_Z));
-        k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, fx, fy, f1, f0, wgt, tho, ctx->f_fine.as<float>());
+        k_fine_eval<1><<<fgrid, FN_X * FN_Y * FN_Z, 0, st>>>(nx, ny, nz, px, fx, fy, f1, f0, wgt, tho, ctx->f_fine.as<float>());
       } else {
         dim3 g2(cdiv(nx, F2_X), cdiv(ny, F2_Y), cdiv(c1 - c0, F2_Z));
-        k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, fx, fy, fz, c0, c1, wgt, tho, ctx->f_fine.as<float>());
+        k_fine_eval2<<<g2, F2_X * F2_Y * F2_ZT, 0, st>>>(nx, ny, nz, px, fx, fy, fz, c0, c1, wgt, tho, ctx->f_fine.as<float>());
       }
       LAUNCH_CHECK();
       if (ctx->async_fine_host) {
@@ -902,7 +968,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     float dxf = (b - a) / (float)(fx - 1); float x0 = a, x1 = a + 1.0f * dxf; float e = sqrtf((x1 - x0) * (x1 - x0));
     if (r2s_halo_exchange_f32(ctx, ctx->f_fine.as<float>(), fpl, kf0, kf1, fz, 0, 1)) return 1;
     VolBisect vf; double vv;
-    if (vol_bisect_begin(ctx, vf, ctx->f_fine.as<float>(), fx, fy, fz, kf0, std::min(kf1, fz - 1), e)) return 1;
+    if (vol_bisect_begin(ctx, vf, ctx->f_fine.as<float>(), fx, fy, fz, fx, kf0, std::min(kf1, fz - 1), e)) return 1;
     if (vol_bisect_step(ctx, vf, 0.0f, 0.0f, 0.0f, &vv)) return 1;
     volf = (float)vv;
   }

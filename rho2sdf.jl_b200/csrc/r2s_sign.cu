@@ -299,17 +299,26 @@ __global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz
   const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
   double sign = -1.0;
   if (n0 * n1 * n2 != 0) {
-    unsigned key[8]; bool hotany = false; int nc = 0;
+    unsigned key[8]; bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
       key[q] = 0xffffffffu;
       if (ii < n0 && jj < n1 && kk < n2) {
         const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
-        if (w != 0xffffffffu) { key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q; hotany = hotany || (w >> 31); nc++; }
+        if (w != 0xffffffffu) {
+          key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q; hotany = hotany || (w >> 31); nc++;
+          const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2;
+        }
       }
     }
-    if (nc > 0 && hotany) {      // skip rule (SignDetection.jl:36): some candidate has a nodal density >= rho_t
+    // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
+    // density class 2 (rho < rho_t wherever max|xi| < 1.01) no candidate can set the sign; if ALL are of class 1 (rho >= rho_t there)
+    // the first candidate -- accepted whatever its max|xi|, because max_local starts at 10 -- sets it.  Only points next to an element
+    // that may cross rho_t replay the rule (about 7 % of the elements of a SIMP field).
+    if (nc > 0 && nvoid == nc) sign = -1.0;
+    else if (nc > 0 && nsolid == nc) sign = 1.0;
+    else if (nc > 0 && hotany) {      // skip rule (SignDetection.jl:36): some candidate has a nodal density >= rho_t
       if (nc > 1) {              // ascending element index = the reference's candidate order
         CSWAP(0, 1); CSWAP(2, 3); CSWAP(4, 5); CSWAP(6, 7); CSWAP(0, 2); CSWAP(1, 3); CSWAP(4, 6); CSWAP(5, 7); CSWAP(1, 2); CSWAP(5, 6);
         CSWAP(0, 4); CSWAP(1, 5); CSWAP(2, 6); CSWAP(3, 7); CSWAP(2, 4); CSWAP(3, 5); CSWAP(1, 2); CSWAP(3, 4); CSWAP(5, 6);
