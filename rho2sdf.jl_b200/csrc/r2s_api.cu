@@ -28,7 +28,7 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   if (cudaHostAlloc(&ctx->rb_host, R2S_RB_BYTES, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&ctx->rb_dev, ctx->rb_host, 0) != cudaSuccess) { r2s_destroy(ctx); return 6; }
   auto knob = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
   ctx->knobs.p2p = knob("R2S_P2P", 1); ctx->knobs.sign_lattice = knob("R2S_SIGN_LATTICE", 1);
-  ctx->knobs.proj_box = knob("R2S_PROJ_BOX", 1); ctx->knobs.proj_prune = knob("R2S_PROJ_PRUNE", 1);
+  ctx->knobs.proj_box = knob("R2S_PROJ_BOX", 1); ctx->knobs.proj_prune = knob("R2S_PROJ_PRUNE", 1); ctx->knobs.vol_cache = knob("R2S_VOL_CACHE", 1); ctx->knobs.debug_sync = knob("R2S_DEBUG_SYNC", 0);
   *out = ctx;
   return 0;
 }
@@ -41,7 +41,7 @@ void r2s_destroy(r2s_ctx *ctx) {
                    &ctx->act_idx, &ctx->act_rec, &ctx->cnt_a, &ctx->cnt_b, &ctx->keys, &ctx->keys_alt, &ctx->tile_ptr, &ctx->tile_faces, &ctx->tri_cnt, &ctx->tri_rec, &ctx->pairbuf, &ctx->pairxp, &ctx->cubtmp,
                    &ctx->counters, &ctx->box_rec, &ctx->plist, &ctx->dist, &ctx->xp, &ctx->sdf, &ctx->signs, &ctx->s_rng, &ctx->s_el, &ctx->s_cnt, &ctx->s_keys, &ctx->s_keys_alt, &ctx->s_tile_ptr,
                    &ctx->cc_label, &ctx->cc_size, &ctx->cc_scal, &ctx->cc_bits, &ctx->cc_bits_all, &ctx->cc_gsz, &ctx->cc_seen, &ctx->f_s, &ctx->f_w, &ctx->f_r, &ctx->f_u, &ctx->f_c, &ctx->f_lsf, &ctx->f_fine, &ctx->f_part,
-                   &ctx->f_scal, &ctx->cutlist, &ctx->slablist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1], &ctx->lat_xs, &ctx->lat_cell, &ctx->lat_map, &ctx->lat_info, &ctx->lat_pt};
+                   &ctx->f_scal, &ctx->cutlist, &ctx->slablist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1], &ctx->vent[0], &ctx->vent[1], &ctx->lat_xs, &ctx->lat_cell, &ctx->lat_map, &ctx->lat_info, &ctx->lat_pt};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_probe[i]);

@@ -66,6 +66,8 @@ struct Knobs {
   int sign_lattice = 1;   // R2S_SIGN_LATTICE=0: tensor-product lattice meshes take the general (sorted candidate list) sign kernel
   int proj_box = 1;       // R2S_PROJ_BOX=0: axis-aligned box elements take the general trilinear projection
   int proj_prune = 1;     // R2S_PROJ_PRUNE=0: the box projection evaluates every (element, point) pair (no lower-bound pruning)
+  int debug_sync = 0;     // R2S_DEBUG_SYNC=1: synchronise after every kernel launch, so that a device fault is reported at the launch that caused it
+  int vol_cache = 1;      // R2S_VOL_CACHE=0: LS_Threshold re-evaluates every cut cell at every bisection (no cached quadratures)
 };
 
 struct LocalGroup;      // in-process slab group (r2s_multi_*): r2s_comm.cu
@@ -119,7 +121,7 @@ struct r2s_ctx {
   // connected components
   DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all, cc_gsz, cc_seen;
   // smoothing
-  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2];
+  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2], vent[2];
   int smooth_last = 1;
   bool have_sdf = false, have_fine = false;      // ctx->sdf / ctx->f_fine hold a result of the CURRENT grid (cleared by r2s_set_grid / r2s_set_mesh)
 
@@ -144,10 +146,11 @@ struct r2s_ctx {
     return 1;               \
   } while (0)
 
-#define LAUNCH_CHECK()                      \
-  do {                                      \
-    ctx->launches++;                        \
-    CK(cudaGetLastError());                 \
+#define LAUNCH_CHECK()                                                          \
+  do {                                                                          \
+    ctx->launches++;                                                            \
+    CK(cudaGetLastError());                                                     \
+    if (ctx->knobs.debug_sync) CK(cudaStreamSynchronize(ctx->stream));          \
   } while (0)
 
 static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }

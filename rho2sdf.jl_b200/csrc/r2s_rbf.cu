@@ -44,7 +44,7 @@ __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__re
 // weights by squared offset m = di^2+dj^2+dk^2 <= 6
 struct StencilW { float w[8]; };
 // ---- plane marching (2.5-D blocking) with TMA-staged planes, two outputs per thread ------------------------------------------------
-// A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane tile (36 x 20 floats with its
+// A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane tile (40 x 20 floats with its
 // x-y halo) is brought into shared memory by ONE bulk tensor copy (cp.async.bulk.tensor.3d, TMA) issued by one thread NST - 1 planes
 // ahead and signalled through an mbarrier: no per-thread address arithmetic, no bounds tests (coordinates outside the grid are
 // zero-filled by the TMA unit -- K has no entries there), loads in flight for several planes.  The fields are stored with a row pitch
@@ -59,11 +59,13 @@ struct StencilW { float w[8]; };
 // iteration counts and weights equal to the oracle's, tests/test_gpu_parity.py).
 #define S3_X 32            // outputs per CTA in x (16 threads x 2)
 #define S3_Y 16
-#define S3_TX (S3_X + 4)   // 36 x 20 tile; 36 floats = 144 B per row (a multiple of 16 B, as the TMA box requires)
+#define S3_HX 4            // x halo of the TILE: the stencil needs 2, but the innermost TMA coordinate must be a multiple of 16 bytes (4 floats):
+                           // a box starting at bx - 2 raises "illegal instruction" on B200 (tools/probes/tma_probe.cu), bx - 4 is fine
+#define S3_TX (S3_X + 2 * S3_HX)   // 40 x 20 tile; 40 floats = 160 B per row (a multiple of 16 B, as the TMA box requires)
 #define S3_TY (S3_Y + 4)
 #define S3_NST 4           // TMA stages: loads run 3 planes ahead of the compute
 #define S3_TILE_BYTES (S3_TX * S3_TY * 4)
-#define S3_SLOT 3072       // stage stride in shared memory (tile = 2880 B, destinations 128-byte aligned)
+#define S3_SLOT 3200       // stage stride in shared memory (= tile bytes, a multiple of 128: destinations are 128-byte aligned)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
@@ -106,17 +108,18 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
   auto issue = [&](int p) {      // thread 0: plane p of this CTA's march into stage p % NST
     const int st = p % S3_NST;
     mbar_expect_tx(&full[st], S3_TILE_BYTES * NARR);
-    tma_load_3d(stage + (st * NARR) * S3_SLOT, &mapA, bx - 2, by - 2, zc0 - 2 + p, &full[st]);
-    if (BETA) tma_load_3d(stage + (st * NARR + 1) * S3_SLOT, &mapB, bx - 2, by - 2, zc0 - 2 + p, &full[st]);
+    tma_load_3d(stage + (st * NARR) * S3_SLOT, &mapA, bx - S3_HX, by - 2, zc0 - 2 + p, &full[st]);
+    if (BETA) tma_load_3d(stage + (st * NARR + 1) * S3_SLOT, &mapB, bx - S3_HX, by - 2, zc0 - 2 + p, &full[st]);
   };
   if (tid == 0) for (int p = 0; p < S3_NST - 1 && p < np; p++) issue(p);
   // elements of the tile this thread combines per plane (CG form): interior ones are also written back to u_new
-  int e_ok[3]; i64 e_off[3];
+  constexpr int NE = (NT + 255) / 256;
+  int e_ok[NE]; i64 e_off[NE];
   if (BETA) {
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const int t = tid + q * 256, ly = t / TX, lx = t % TX, x = bx + lx - 2, y = by + ly - 2;
-      e_ok[q] = (t < NT ? 1 : 0) | ((t < NT && lx >= 2 && lx < TX - 2 && ly >= 2 && ly < TY - 2 && x < nx && y < ny) ? 2 : 0);
+    for (int q = 0; q < NE; q++) {
+      const int t = tid + q * 256, ly = t / TX, lx = t % TX, x = bx + lx - S3_HX, y = by + ly - 2;
+      e_ok[q] = (t < NT ? 1 : 0) | ((t < NT && lx >= S3_HX && lx < TX - S3_HX && ly >= 2 && ly < TY - 2 && x < nx && y < ny) ? 2 : 0);
       e_off[q] = (i64)y * px + x;
     }
   }
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
       const float *tr = reinterpret_cast<const float *>(stage + (st * NARR) * S3_SLOT), *tu = reinterpret_cast<const float *>(stage + (st * NARR + 1) * S3_SLOT);
       float *cb = comb[p & 1];
 #pragma unroll
-      for (int q = 0; q < 3; q++)
+      for (int q = 0; q < NE; q++)
         if (e_ok[q] & 1) {
           const int t = tid + q * 256;
           const float v = tr[t] + beta * tu[t];
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
     float s9a = 0.f, s9b = 0.f, s12a = 0.f, s12b = 0.f;
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++) {
-      const float2 *row = reinterpret_cast<const float2 *>(tile + (ty + 2 + dj) * TX + 2 * tx);
+      const float2 *row = reinterpret_cast<const float2 *>(tile + (ty + 2 + dj) * TX + 2 * tx + (S3_HX - 2));
       const float2 p0 = row[0], p1 = row[1], p2 = row[2];
       const float v[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};       // x0-2 .. x0+3
       if (dj == 0) { ctra = v[2]; ctrb = v[3]; }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
 }
-// tensor map of a coarse Float32 field (nx x ny x nz values, row pitch px floats) with the 36 x 20 x 1 box of the stencil tiles
+// tensor map of a coarse Float32 field (nx x ny x nz values, row pitch px floats) with the 40 x 20 x 1 box of the stencil tiles
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static int stencil_tensor_map(r2s_ctx *ctx, CUtensorMap *map, const float *base, int nx, int ny, int nz, int px) {
@@ -370,58 +373,6 @@ __global__ void __launch_bounds__(128) k_vol_cut(int nx, int ny, int px, const f
 // remaining "active" cells are carried to the next step in a compacted list.  The sum is accumulated in integers, so the
 // result is bit-identical to re-classifying every cell at every step, at ~3 full passes instead of 40.
 // acc: [0] full cells of this step  [1] cut count  [2] cut fixed-point sum  [3] permanently full  [4],[5] list sizes (ping-pong)
-template <bool IMPLICIT, bool EMIT>
-__global__ void __launch_bounds__(256) k_vol_step(int nx, int ny, int px, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th,
-                                                  const int *__restrict__ list_in, const u64 *__restrict__ n_in_ptr, int *__restrict__ list_out,
-                                                  u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
-  __shared__ int s_cut[8], s_keep[8]; __shared__ int s_base_cut, s_base_keep;
-  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)px * ny;
-  const i64 n_in = IMPLICIT ? cpl * (i64)(kc1 - kc0) : (i64)*n_in_ptr;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int nfull = 0, nperm = 0;
-  for (i64 t0 = (i64)blockIdx.x * 256; t0 < n_in; t0 += (i64)gridDim.x * 256) {
-    i64 t = t0 + threadIdx.x; bool cut = false, keep = false; int c = 0;
-    if (t < n_in) {
-      c = IMPLICIT ? (int)(t + cpl * kc0) : list_in[t];
-      int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = (int)(c / cpl);
-      i64 b = ((i64)k * ny + j) * px + i;
-      float v0 = sdf[b], v1 = sdf[b + 1], v2 = sdf[b + px], v3 = sdf[b + px + 1];
-      float v4 = sdf[b + sxy], v5 = sdf[b + sxy + 1], v6 = sdf[b + sxy + px], v7 = sdf[b + sxy + px + 1];
-      float mn = fminf(fminf(fminf(v0, v1), fminf(v2, v3)), fminf(fminf(v4, v5), fminf(v6, v7)));
-      float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
-      if (EMIT && mn >= hi) nperm++;                         // full for every threshold still to come
-      else if (EMIT && mx < lo) {}                           // empty for every threshold still to come
-      else {
-        keep = EMIT;
-        if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
-      }
-    }
-    unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
-    if (__syncthreads_or((mc | mk) != 0)) {
-      if (lane == 0) { s_cut[warp] = __popc(mc); s_keep[warp] = __popc(mk); }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int tc = 0, tk = 0;
-        for (int w = 0; w < 8; w++) { int a = s_cut[w]; s_cut[w] = tc; tc += a; int b2 = s_keep[w]; s_keep[w] = tk; tk += b2; }
-        s_base_cut = tc ? (int)atomicAdd(&acc[1], (u64)tc) : 0;
-        s_base_keep = tk ? (int)atomicAdd(n_out_ptr, (u64)tk) : 0;
-      }
-      __syncthreads();
-      if (cut) { int slot = s_base_cut + s_cut[warp] + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
-      if (keep) list_out[s_base_keep + s_keep[warp] + __popc(mk & ((1u << lane) - 1))] = c;
-      __syncthreads();
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
-  __syncthreads();
-  if (lane == 0) { s_cut[warp] = nfull; s_keep[warp] = nperm; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tf = 0, tp = 0; for (int w = 0; w < 8; w++) { tf += s_cut[w]; tp += s_keep[w]; }
-    if (tf) atomicAdd(&acc[0], (u64)tf);
-    if (tp) atomicAdd(&acc[3], (u64)tp);
-  }
-}
 // any quadrature order 1..32 (calculate_volume_from_sdf's detailed_quad_order; the convergence tests of the reference use 20): same
 // organisation as k_vol_cut, loops not unrolled, abscissae / weights read from the kernel-parameter bank with uniform indices
 struct GaussNF { float x[32]; float w[32]; int n; };
@@ -543,19 +494,124 @@ __global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int px, int kc
   for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
   if (lane == 0) { if (nfull) atomicAdd(&acc[0], (u64)nfull); if (nperm) atomicAdd(&acc[3], (u64)nperm); }
 }
+// ---- bisection steps >= 4: the ACTIVE list carries everything a cell needs ------------------------------------------------------
+// After three whole-grid steps only the cells that the remaining bracket [lo, hi] can still cut are active (a thin shell around the
+// level set).  From then on each active cell is a 48-byte record: its id, its eight corner values (one coalesced read instead of eight
+// scattered ones per step) and a CACHE of its last quadrature: part (the Float32 sum of w_i w_j w_k over the inside Gauss points),
+// the threshold it was computed at and a margin = the smallest |value| over the 729 Gauss points minus a bound on the Float32
+// round-off of those values.  While |th - th_cached| stays below the margin no Gauss value can change sign, the inside set -- and
+// with it the cell's Float32 sum, bit for bit -- is the same, and the cached sum is added without re-evaluating the cell.  As the
+// bracket halves, almost every cell freezes: the 40 bisections cost about a dozen full quadratures instead of 40.  The total is an
+// exact integer sum, so the result is bit-identical to re-evaluating every cut cell at every step (R2S_VOL_CACHE=0 does that).
+struct VEnt { int id; float c[8]; float part, th_e, margin; };
+__global__ void __launch_bounds__(256) k_vl_gather(i64 n, const int *__restrict__ ids, int nx, int ny, int px, const float *__restrict__ sdf, VEnt *__restrict__ out) {
+  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int c = ids[t];
+  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)px * ny;
+  const int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = (int)(c / cpl);
+  const i64 b = ((i64)k * ny + j) * px + i;
+  VEnt e; e.id = c;
+  e.c[0] = sdf[b]; e.c[1] = sdf[b + 1]; e.c[2] = sdf[b + px]; e.c[3] = sdf[b + px + 1];
+  e.c[4] = sdf[b + sxy]; e.c[5] = sdf[b + sxy + 1]; e.c[6] = sdf[b + sxy + px]; e.c[7] = sdf[b + sxy + px + 1];
+  e.part = 0.0f; e.th_e = NAN; e.margin = -1.0f;
+  out[t] = e;
+}
+// one thread per active record: retire / keep (compaction into `out`), classify at th, use the cache or queue the record for k_vl_eval
+__global__ void __launch_bounds__(256) k_vl_step(const VEnt *__restrict__ in, const u64 *__restrict__ n_in_ptr, VEnt *__restrict__ out, u64 *__restrict__ n_out_ptr, float lo, float hi,
+                                                 float th, int use_cache, u64 *__restrict__ acc, int *__restrict__ evlist) {
+  const i64 n_in = (i64)*n_in_ptr;
+  const int lane = threadIdx.x & 31;
+  int nfull = 0, nperm = 0; u64 local = 0;
+  for (i64 t0 = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); t0 < n_in; t0 += (i64)gridDim.x * blockDim.x) {      // warp-uniform
+    const i64 t = t0 + lane; bool keep = false, miss = false; VEnt e;
+    if (t < n_in) {
+      e = in[t];
+      const float mn = fminf(fminf(fminf(e.c[0], e.c[1]), fminf(e.c[2], e.c[3])), fminf(fminf(e.c[4], e.c[5]), fminf(e.c[6], e.c[7])));
+      const float mx = fmaxf(fmaxf(fmaxf(e.c[0], e.c[1]), fmaxf(e.c[2], e.c[3])), fmaxf(fmaxf(e.c[4], e.c[5]), fmaxf(e.c[6], e.c[7])));
+      if (mn >= hi) nperm++;                          // full for every threshold still to come
+      else if (mx < lo) {}                            // empty for every threshold still to come
+      else {
+        keep = true;
+        if (!(mx < th)) {
+          if (mn >= th) nfull++;
+          else if (use_cache && fabsf(th - e.th_e) * 1.00001f < e.margin) local += (u64)llrint((double)e.part * 137438953472.0);      // (NaN th_e compares false)
+          else miss = true;
+        }
+      }
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, keep), mm = __ballot_sync(0xffffffffu, miss);
+    int slot = 0;
+    if (mk) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(n_out_ptr, (u64)__popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      slot = base + __popc(mk & ((1u << lane) - 1));
+      if (keep) out[slot] = e;
+    }
+    if (mm) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(&acc[1], (u64)__popc(mm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (miss) evlist[base + __popc(mm & ((1u << lane) - 1))] = slot;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); local += __shfl_down_sync(0xffffffffu, local, o); }
+  if (lane == 0) { if (nfull) atomicAdd(&acc[0], (u64)nfull); if (nperm) atomicAdd(&acc[3], (u64)nperm); if (local) atomicAdd(&acc[2], local); }
+}
+// quadrature of the queued records at th (same point values, same order of the Float32 sum as k_vol_cut) + their new cache entries
+__global__ void __launch_bounds__(128) k_vl_eval(VEnt *__restrict__ ent, const int *__restrict__ evlist, float th, GaussF G, u64 *__restrict__ acc) {
+  const int nev = (int)acc[1];
+  const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
+  u64 local = 0;
+  for (int base = blockIdx.x * blockDim.x; base < nev; base += nthr) {      // warp-uniform trip count
+    const int idx = base + threadIdx.x;
+    if (idx < nev) {
+      VEnt &e = ent[evlist[idx]];
+      const float c000 = e.c[0] - th, c100 = e.c[1] - th, c010 = e.c[2] - th, c110 = e.c[3] - th;
+      const float c001 = e.c[4] - th, c101 = e.c[5] - th, c011 = e.c[6] - th, c111 = e.c[7] - th;
+      const float amax = fmaxf(fmaxf(fmaxf(fabsf(c000), fabsf(c100)), fmaxf(fabsf(c010), fabsf(c110))), fmaxf(fmaxf(fabsf(c001), fabsf(c101)), fmaxf(fabsf(c011), fabsf(c111))));
+      float part = 0.0f, m = INFINITY;
+#pragma unroll 1
+      for (int iq = 0; iq < 9; iq++) {
+        const float xi = (G.x[iq] + 1) / 2, xm = 1.0f - xi;
+        const float c00 = c000 * xm + c100 * xi, c01 = c001 * xm + c101 * xi;
+        const float c10 = c010 * xm + c110 * xi, c11 = c011 * xm + c111 * xi;
+#pragma unroll
+        for (int jq = 0; jq < 9; jq++) {
+          const float eta = (G.x[jq] + 1) / 2, em = 1.0f - eta;
+          const float c0 = c00 * em + c10 * eta, c1 = c01 * em + c11 * eta;
+          const float wij = G.w[iq] * G.w[jq], dc = c1 - c0;
+#pragma unroll
+          for (int kq = 0; kq < 9; kq++) {
+            const float ps = fmaf(dc, (G.x[kq] + 1) / 2, c0);
+            if (ps >= 0.0f) part += wij * G.w[kq];
+            m = fminf(m, fabsf(ps));
+          }
+        }
+      }
+      // a Gauss value moves by (th_cached - th) plus Float32 round-off of the corner subtractions and the three lerps: a few ulp of the
+      // corner magnitude, bounded generously by 1e-5 * amax (the step test applies the same factor to the threshold difference)
+      e.part = part; e.th_e = th; e.margin = m - 1.0e-5f * amax;
+      local += (u64)llrint((double)part * 137438953472.0);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if (lane == 0 && local) atomicAdd(&acc[2], local);
+}
 // acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
 __global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red) {
   red[0] = acc[0] + acc[3]; red[1] = acc[1] > (u64)cutcap ? 1 : 0; red[2] = acc[2]; red[3] = 0;
 }
 // state of one LS_Threshold search (see k_vol_step)
 struct VolBisect {
-  const float *sdf; int nx, ny, px, kc0, kc1; float edge; int step, cur; i64 n_cur; u64 *acc;
+  const float *sdf; int nx, ny, px, kc0, kc1; float edge; int step, cur; i64 n_cur, n_eval; u64 *acc;
 };
 static int vol_bisect_begin(r2s_ctx *ctx, VolBisect &vb, const float *sdf, int nx, int ny, int nz, int px, int kc0, int kc1, float edge) {
   i64 ncell = (i64)(nx - 1) * (ny - 1) * (nz - 1);
   if (ncell >= (1ll << 31)) FAIL("LS_Threshold: grid too large for 32-bit cell ids");
   CK(ctx->f_scal.reserve(512));
-  vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.px = px; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0;
+  vb.sdf = sdf; vb.nx = nx; vb.ny = ny; vb.px = px; vb.kc0 = kc0; vb.kc1 = kc1; vb.edge = edge; vb.step = 0; vb.cur = 0; vb.n_eval = 0;
   vb.n_cur = (i64)(nx - 1) * (ny - 1) * (i64)(kc1 - kc0);
   vb.acc = (u64 *)((char *)ctx->f_scal.p + 128);       // acc[0..7], red[0..3] behind it
   CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 12, ctx->stream));
@@ -567,27 +623,40 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
   static const GaussF G9 = gauss9f();
   const i64 n_all = (i64)(vb.nx - 1) * (vb.ny - 1) * (i64)(vb.kc1 - vb.kc0);
   vb.step++;
-  const bool implicit = vb.step <= 3, emit = vb.step >= 3;
-  if (emit) { CK(ctx->vlist[0].reserve(sizeof(int) * (size_t)(n_all + 1))); if (vb.step > 3) CK(ctx->vlist[1].reserve(sizeof(int) * (size_t)(vb.n_cur + 1))); }
-  const int in = vb.cur, out = emit ? (vb.step == 3 ? 0 : 1 - vb.cur) : vb.cur;
+  if (vb.step >= 4) {      // active-list steps: 48-byte records with cached quadratures (see k_vl_step)
+    const int in = vb.cur, out = 1 - vb.cur;
+    CK(ctx->vent[out].reserve(sizeof(VEnt) * (size_t)(vb.n_cur + 1)));
+    CK(ctx->vlist[1].reserve(sizeof(int) * (size_t)(vb.n_cur + 1)));      // queue of records to evaluate (slots of the output list)
+    u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
+    CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
+    CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
+    const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 16);
+    k_vl_step<<<grid, 256, 0, st>>>(ctx->vent[in].as<VEnt>(), nin, ctx->vent[out].as<VEnt>(), nout, lo, hi, th, ctx->knobs.vol_cache, vb.acc, ctx->vlist[1].as<int>()); LAUNCH_CHECK();
+    k_vl_eval<<<148 * 16, 128, 0, st>>>(ctx->vent[out].as<VEnt>(), ctx->vlist[1].as<int>(), th, G9, vb.acc); LAUNCH_CHECK();
+    u64 *red = vb.acc + 8, hall[12];
+    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, 0x7fffffff, red); LAUNCH_CHECK();
+    if (r2s_allreduce(ctx, red, 4, 1)) return 1;
+    if (r2s_readback(ctx, hall, vb.acc, sizeof(hall))) return 1;
+    vb.cur = out; vb.n_cur = (i64)hall[4 + out]; vb.n_eval += (i64)hall[1];
+    const float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
+    *vol = (double)hall[8] * (double)ev + ((double)hall[10] / 137438953472.0 /* 2^37 */) * (double)jac;
+    return 0;
+  }
+  const bool emit = vb.step == 3;      // steps 1-3 classify the whole grid (k_vol_rows); step 3 also emits the active list
+  if (emit) CK(ctx->vlist[0].reserve(sizeof(int) * (size_t)(n_all + 1)));
+  const int out = 0;
   u64 h[6];
   for (int attempt = 0; attempt < 2; attempt++) {
     int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
-    i64 n_in = implicit ? n_all : vb.n_cur;
-    int grid = (int)std::min<i64>(std::max<i64>(cdiv(n_in, 256), 1), 148 * 16);
-    int *lin = ctx->vlist[in].as<int>(), *lout = ctx->vlist[out].as<int>(); u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
-    if (attempt == 0) {
-      if (emit) CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
+    int *lout = ctx->vlist[out].as<int>(); u64 *nout = vb.acc + 4 + out;
+    {
+      // (a second attempt follows a cut-list overflow: the list has been grown, the step is repeated from scratch)
+      if (emit) { CK(cudaMemsetAsync(nout, 0, sizeof(u64), st)); CK(cudaMemsetAsync(vb.acc + 3, 0, sizeof(u64), st)); }      // step 3 is the first step that retires cells
       const i64 ntask = (i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31);
       const int rgrid = (int)std::min<i64>(std::max<i64>(cdiv(ntask, 8), 1), 148 * 16);
-      if (implicit && !emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else if (implicit) k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else k_vol_step<false, true><<<grid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lin, nin, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
-    } else {
-      // the cut list overflowed: it has been grown; re-classify (the retired cells are already accounted for)
-      if (!emit) k_vol_rows<false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31), 8), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else k_vol_step<false, false><<<(int)std::min<i64>(std::max<i64>(cdiv((i64)h[4 + out], 256), 1), 148 * 16), 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      if (!emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
+      else k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
     }
     LAUNCH_CHECK();
     k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.px, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
@@ -605,7 +674,13 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
       if ((i64)h[1] > cutcap) CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
       continue;
     }
-    if (emit) { vb.cur = out; vb.n_cur = (i64)h[4 + out]; }
+    if (emit) {      // step 3: the active cells become records (id + corner values + empty cache) for the list steps that follow
+      vb.cur = 0; vb.n_cur = (i64)h[4 + out];
+      CK(ctx->vent[0].reserve(sizeof(VEnt) * (size_t)(vb.n_cur + 1)));
+      if (vb.n_cur > 0) { k_vl_gather<<<cdiv(vb.n_cur, 256), 256, 0, st>>>(vb.n_cur, ctx->vlist[0].as<int>(), vb.nx, vb.ny, vb.px, vb.sdf, ctx->vent[0].as<VEnt>()); LAUNCH_CHECK(); }
+      // acc[4] must hold the size of list 0 for the next step: it does (out == 0 at step 3)
+    }
+    vb.n_eval += (i64)h[1];
     float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
     *vol = (double)hr[0] * (double)ev + ((double)hr[2] / 137438953472.0 /* 2^37 */) * (double)jac;
     return 0;

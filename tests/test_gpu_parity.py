@@ -500,3 +500,24 @@ def test_sign_lattice_fast_path(r2s, monkeypatch):
             if X.shape[0] < 10000:
                 assert np.array_equal(res["1"][q], oracle.sign_detection(X, IEN, grid, rn, rt))
             assert (res["1"][q] > 0).any() and (res["1"][q] < 0).any()
+
+
+def test_threshold_search_cache_is_exact(r2s, monkeypatch):
+    """LS_Threshold keeps, per active cut cell, the cell's last quadrature and a margin within which no Gauss value can change sign; the
+    volume is an exact integer sum, so the search must take bit-identical decisions with the cache (default) and without (R2S_VOL_CACHE=0).
+    R2S_DEBUG_SYNC=1 (a synchronisation after every launch, for fault localisation) must not change anything either."""
+    X, IEN, rho = simp_hex8(24)
+    res = {}
+    for name, env in (("cache", {}), ("nocache", {"R2S_VOL_CACHE": "0"}), ("debug", {"R2S_DEBUG_SYNC": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        mesh = r2s.Mesh(X, IEN, rho)
+        grid = r2s.Grid(X.min(0), X.max(0), 48, 3)
+        rn = r2s.DenseInNodes(mesh, rho)
+        res[name] = _run_pipeline(r2s, mesh, grid, rn)
+        mesh.ctx.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    for name in ("nocache", "debug"):
+        assert res[name][2].th == res["cache"][2].th and res[name][2].volume == res["cache"][2].volume and res[name][2].bisections == res["cache"][2].bisections
+        assert np.array_equal(res[name][0], res["cache"][0]) and np.array_equal(res[name][1], res["cache"][1])
