@@ -46,6 +46,10 @@ struct LocalGroup {
   int n = 0; r2s_ctx *ctx[64];
   std::mutex mu; std::condition_variable cv; int arrived = 0; unsigned long gen = 0; bool failed = false;
   const void *src[64]; size_t cnt[64]; cudaEvent_t ev_ready[64], ev_done[64];
+  bool spin_ok = false;      // every slab on its own device: the device-side mailbox (spin waits) is safe.  Slabs that SHARE a device must not wait for
+                             // each other inside kernels (an allocation or a full hardware queue on the shared device can hold back the kernel that is
+                             // waited for), so they use the event-ordered exchanges below for everything.
+  void *stage[64];           // per slab: 64 x 4 words of staging for the event-ordered all-reduce
   // returns false when some rank has failed (the caller must bail out instead of waiting for it)
   bool barrier() {
     std::unique_lock<std::mutex> lk(mu);
@@ -117,9 +121,11 @@ int r2s_group_start(r2s_ctx *ctx) { if (ctx->nranks > 1 && !ctx->lg) NCK(g_nccl.
 int r2s_group_end(r2s_ctx *ctx) { if (ctx->nranks > 1 && !ctx->lg) NCK(g_nccl.GroupEnd()); return 0; }
 // ---- collectives used by the pipeline; all are no-ops for a single rank ----------------------------------------------
 static int p2p_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind);
+static int local_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind);
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/) {
   if (ctx->nranks <= 1) return 0;
   if (ctx->lg && count > 4) FAIL("in-process slab group: all-reduce of more than 4 words");
+  if (ctx->lg && !ctx->p2p) return local_allreduce(ctx, buf, count, kind);
   if (ctx->p2p && count <= 4) return p2p_allreduce(ctx, buf, count, kind);
   int dt = kind == 0 ? NC_F64 : (kind == 1 || kind == 4 ? NC_UINT64 : NC_UINT32);
   int op = (kind == 0 || kind == 1) ? NC_SUM : (kind == 3 ? NC_MIN : NC_MAX);
@@ -159,6 +165,44 @@ static int local_allgather(r2s_ctx *ctx, const void *send, void *recv, size_t by
     else { if (local_pull(ctx, q, dst, lg->src[q], bytes)) return 1; readers[nr++] = q; }
   }
   return local_pull_end(ctx, readers, nr);
+}
+// combine R contributions of n words in rank order (deterministic, identical on every slab)
+__global__ void k_local_combine(const unsigned long long *__restrict__ stage, int R, int n, int kind, unsigned long long *__restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  unsigned long long acc = stage[i];
+  for (int q = 1; q < R; q++) {
+    const unsigned long long v = stage[q * 4 + i];
+    if (kind == 0) acc = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc) + __longlong_as_double((long long)v));
+    else if (kind == 1) acc += v;
+    else if (kind == 3) acc = v < acc ? v : acc;
+    else acc = v > acc ? v : acc;
+  }
+  out[i] = acc;
+}
+__global__ void k_local_combine32(const unsigned *__restrict__ stage, int R, int n, int kind, unsigned *__restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  unsigned acc = stage[i];
+  for (int q = 1; q < R; q++) { const unsigned v = stage[q * 8 + i]; acc = kind == 3 ? (v < acc ? v : acc) : (v > acc ? v : acc); }
+  out[i] = acc;
+}
+// event-ordered all-reduce of <= 4 words for slabs that share a device (no waiting inside kernels)
+static int local_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind) {
+  LocalGroup *lg = ctx->lg;
+  const bool w32 = kind == 2 || kind == 3; const size_t es = w32 ? 4 : 8, slot = 32;      // 32 bytes per contribution
+  if (local_pull_begin(ctx, buf, count * es)) return 1;
+  char *stage = (char *)lg->stage[ctx->rank];
+  int readers[64], nr = 0;
+  for (int q = 0; q < lg->n; q++) {
+    if (q == ctx->rank) CK(cudaMemcpyAsync(stage + (size_t)q * slot, buf, count * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    else { if (local_pull(ctx, q, stage + (size_t)q * slot, lg->src[q], count * es)) return 1; readers[nr++] = q; }
+  }
+  if (local_pull_end(ctx, readers, nr)) return 1;      // after this, nobody still reads my buf: it may be overwritten
+  if (w32) k_local_combine32<<<1, 32, 0, ctx->stream>>>((const unsigned *)stage, lg->n, (int)count, kind, (unsigned *)buf);
+  else k_local_combine<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)stage, lg->n, (int)count, kind, (unsigned long long *)buf);
+  CK(cudaGetLastError());
+  return 0;
 }
 int r2s_allgather_u32(r2s_ctx *ctx, const unsigned *send, unsigned *recv, size_t count) {
   if (ctx->nranks <= 1) { CK(cudaMemcpyAsync(recv, send, count * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream)); return 0; }
@@ -218,7 +262,7 @@ int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k
 // both neighbours' flags in a one-warp kernel before its update kernel starts.  Spins are bounded: a timeout raises an error
 // flag instead of hanging the GPU.  R2S_P2P=0 falls back to NCCL for everything.
 #define P2P_SLOT_WORDS 8
-#define P2P_MAX_SPIN (1u << 28)
+#define P2P_MAX_SPIN (1u << 26)      // bounded waits (tens of seconds): a dead peer raises the error flag instead of hanging the GPU
 struct P2PBox {
   unsigned long long slot[2][64][P2P_SLOT_WORDS];
   unsigned long long halo_flag[2][2];      // [parity][0 = from lower neighbour, 1 = from upper neighbour]
@@ -337,7 +381,9 @@ LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err) {
   if (n < 2 || n > 64) return fail("in-process slab group: 2..64 slabs");
   LocalGroup *lg = new LocalGroup();
   lg->n = n;
-  for (int r = 0; r < n; r++) { lg->ctx[r] = ctxs[r]; lg->ev_ready[r] = nullptr; lg->ev_done[r] = nullptr; }
+  for (int r = 0; r < n; r++) { lg->ctx[r] = ctxs[r]; lg->ev_ready[r] = nullptr; lg->ev_done[r] = nullptr; lg->stage[r] = nullptr; }
+  lg->spin_ok = true;
+  for (int r = 0; r < n; r++) for (int q = 0; q < r; q++) if (ctxs[q]->device == ctxs[r]->device) lg->spin_ok = false;
   // peer access between every pair of distinct devices (slabs that share a device need none)
   for (int r = 0; r < n; r++) {
     if (cudaSetDevice(ctxs[r]->device) != cudaSuccess) { delete lg; return fail("cudaSetDevice failed"); }
@@ -351,6 +397,7 @@ LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err) {
     }
     if (cudaEventCreateWithFlags(&lg->ev_ready[r], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&lg->ev_done[r], cudaEventDisableTiming) != cudaSuccess) { delete lg; return fail("cudaEventCreate failed"); }
     if (cudaMalloc(&ctxs[r]->p2p_box, sizeof(P2PBox) + 64) != cudaSuccess || cudaMemset(ctxs[r]->p2p_box, 0, sizeof(P2PBox) + 64) != cudaSuccess) { delete lg; return fail("mailbox allocation failed"); }
+    if (cudaMalloc(&lg->stage[r], 64 * 32) != cudaSuccess) { delete lg; return fail("staging allocation failed"); }
   }
   for (int r = 0; r < n; r++) {
     r2s_ctx *c = ctxs[r];
@@ -358,7 +405,7 @@ LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err) {
     for (int q = 0; q < n; q++) c->p2p_peer_box[q] = ctxs[q]->p2p_box;
     if (cudaMalloc((void **)&c->p2p_peer_box_dev, sizeof(void *) * 64) != cudaSuccess ||
         cudaMemcpy(c->p2p_peer_box_dev, c->p2p_peer_box, sizeof(void *) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { delete lg; return fail("mailbox table allocation failed"); }
-    c->lg = lg; c->rank = r; c->nranks = n; c->comm = nullptr; c->p2p = true; c->p2p_seq = 0; c->p2p_halo_seq = 0; c->p2p_c_local = nullptr;
+    c->lg = lg; c->rank = r; c->nranks = n; c->comm = nullptr; c->p2p = lg->spin_ok; c->p2p_seq = 0; c->p2p_halo_seq = 0; c->p2p_c_local = nullptr;
   }
   return lg;
 }
@@ -368,6 +415,7 @@ void r2s_local_group_destroy(LocalGroup *lg) {
     if (lg->ctx[r]) { cudaSetDevice(lg->ctx[r]->device); r2s_comm_destroy(lg->ctx[r]); }
     if (lg->ev_ready[r]) cudaEventDestroy(lg->ev_ready[r]);
     if (lg->ev_done[r]) cudaEventDestroy(lg->ev_done[r]);
+    if (lg->stage[r]) cudaFree(lg->stage[r]);
   }
   delete lg;
 }

@@ -267,7 +267,7 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 #define PL_LI_BITS 24
 template <int PASS>
 __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
-                                                   int prune, u64 *__restrict__ plist, u64 *__restrict__ cnt) {
+                                                   int prune, u64 *__restrict__ plist, u64 *__restrict__ cnt, u64 *__restrict__ stats) {
   const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
   if (a >= nact) return;
   const int vol = box[a].vol;
@@ -308,22 +308,30 @@ __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__res
         }
       }
     }
+    // ONE list-slot claim per warp and batch: a single global counter serves the whole grid, and same-address atomics retire at about one
+    // per clock -- a claim per 32-point round (7 per element) made this kernel atomic-bound (ncu: 3.4 + 7.2 ms)
+    unsigned keepm[RB]; int total = 0;
 #pragma unroll
     for (int r = 0; r < RB; r++) {
       bool keep = (flags[r] & 1) != 0;
       if (PASS == 1 && keep && lb2[r] > cur[r] * cur[r] * (1.0 + 1e-10)) { keep = false; npruned++; }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (m) {
-        u64 pos = 0;
-        if (lane == 0) pos = atomicAdd(&cnt[0], (u64)__popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (keep) plist[pos + __popc(m & ((1u << lane) - 1))] = ((u64)((flags[r] >> 1) & 1) << 63) | ((u64)a << PL_LI_BITS) | (u64)(base0 + r * 32 + lane);
+      keepm[r] = __ballot_sync(0xffffffffu, keep);
+      total += __popc(keepm[r]);
+    }
+    if (total) {
+      u64 pos = 0;
+      if (lane == 0) pos = atomicAdd(&cnt[0], (u64)total);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+      for (int r = 0; r < RB; r++) {
+        if ((keepm[r] >> lane) & 1u) plist[pos + __popc(keepm[r] & ((1u << lane) - 1))] = ((u64)((flags[r] >> 1) & 1) << 63) | ((u64)a << PL_LI_BITS) | (u64)(base0 + r * 32 + lane);
+        pos += __popc(keepm[r]);
       }
     }
   }
-  if (PASS == 1) {
+  if (PASS == 1) {      // statistics: spread over the 128 counter slots (summed on the host)
     for (int o = 16; o > 0; o >>= 1) npruned += __shfl_down_sync(0xffffffffu, npruned, o);
-    if (lane == 0 && npruned) atomicAdd(&cnt[1], (u64)npruned);
+    if (lane == 0 && npruned) atomicAdd(&stats[8 * (1 + (blockIdx.x & 127)) + 4], (u64)npruned);
   }
 }
 // grid-stride over the list: consecutive lanes take consecutive entries (mostly the same element: broadcast loads of its record)
@@ -825,10 +833,10 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
         BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
         k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box); LAUNCH_CHECK();
         const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * 5 * 4;
-        k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc); LAUNCH_CHECK();
+        k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc, ctx->counters.as<u64>()); LAUNCH_CHECK();
         k_project_list<<<pgrid, 128, 0, st>>>(pl, pc, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
         if (prune) {
-          k_pair_scan<1><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc + 2); LAUNCH_CHECK();
+          k_pair_scan<1><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc + 2, ctx->counters.as<u64>()); LAUNCH_CHECK();
           k_project_list<<<pgrid, 128, 0, st>>>(pl, pc + 2, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
         }
       }
@@ -858,7 +866,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   for (int q = 0; q < 8; q++) { hc[q] = hall[q]; for (int sl = 1; sl <= 128; sl++) hc[q] += hall[8 * sl + q]; }
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
   ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
-  ctx->rep.n_pairs_pruned = (i64)hall[NCTR + 3];
+  ctx->rep.n_pairs_pruned = (i64)hc[4];
   CK(cudaEventElapsedTime(&ctx->rep.ms_bin, ctx->ev[0], ctx->ev[1]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_project, ctx->ev[1], ctx->ev[2]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_assemble, ctx->ev[2], ctx->ev[3]));

@@ -21,9 +21,9 @@ struct r2s_multi {
   std::vector<int> dev;
   LocalGroup *lg = nullptr;
   std::string err;
-  std::vector<i64> cut;            // n + 1 plane boundaries
+  std::vector<i64> cut, next_cut;  // n + 1 plane boundaries in force / to be applied at the start of the next call
   std::vector<double> plane_cost;  // per coarse plane, from the last pipeline call (empty = even cut)
-  bool has_grid = false, rebalance = true;
+  bool has_grid = false, rebalance = true, recut_pending = false;      // a re-cut is applied at the START of the next pipeline call (the resident results stay valid for export)
   int nz = 0;
 };
 
@@ -110,7 +110,7 @@ int r2s_multi_set_grid(r2s_multi *m, const double amin[3], const double amax[3],
   if (N[2] + 1 < 3 * (int64_t)m->n) { m->err = "r2s_multi_set_grid: fewer than 3 coarse planes per slab"; return 1; }
   // r2s_set_grid resets a context to the whole grid; the slabs are set (collectively) right after
   for (int r = 0; r < m->n; r++) if (r2s_set_grid(m->ctx[(size_t)r], amin, amax, N, cell)) { m->err = m->ctx[(size_t)r]->err; return 1; }
-  m->nz = (int)N[2] + 1; m->plane_cost.clear(); m->has_grid = true;
+  m->nz = (int)N[2] + 1; m->plane_cost.clear(); m->has_grid = true; m->recut_pending = false;
   even_cut(m);
   return m->n > 1 ? apply_cut(m) : 0;
 }
@@ -126,6 +126,7 @@ int r2s_multi_pipeline(r2s_multi *m, const r2s_params *p, const double *rho_n, d
   if (!m || !p) return 1;
   if (!m->has_grid) { m->err = "r2s_multi_set_grid has not been called"; return 1; }
   if (m->n == 1) { int rc = r2s_pipeline(m->ctx[0], p, rho_n, sdf_dists, fine_sdf, rep); if (rc) m->err = m->ctx[0]->err; return rc; }
+  if (m->recut_pending) { m->recut_pending = false; m->cut = m->next_cut; if (apply_cut(m)) return 1; }
   const GridDev &g = m->ctx[0]->g;
   const size_t pl = (size_t)g.np[0] * g.np[1];
   const int s = p->smooth;
@@ -161,7 +162,10 @@ int r2s_multi_pipeline(r2s_multi *m, const r2s_params *p, const double *rho_n, d
     for (int r = 0; r < m->n; r++) for (i64 k = m->cut[(size_t)r]; k < m->cut[(size_t)r + 1]; k++) m->plane_cost[(size_t)k] = freec[(size_t)r] + cu;
     std::vector<i64> old = m->cut;
     cost_cut(m);
-    if (old != m->cut && apply_cut(m)) return 1;
+    if (old != m->cut) {
+      // the slabs in force (and the results resident on them) stay as they are until the next call; keep `cut` describing them
+      m->next_cut = m->cut; m->cut = old; m->recut_pending = true;
+    }
   }
   return 0;
 }

@@ -444,132 +444,158 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, in
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
 }
-// Whole-grid variant of k_vol_step (bisection steps 1-3 and the final fine-grid volume): a warp owns 31 consecutive cells of
-// one cell row; every lane loads the 4 values of its x-column (coalesced) and takes the neighbouring column's min / max from
-// lane + 1, so a cell costs 4 loads instead of 8 and no div/mod.  Same classification, same integer accumulation.
+// ---- warp-private staging of list entries in shared memory ------------------------------------------------------------------------
+// Every list of this file (cut cells, active cells, cells to evaluate) is appended to through ONE global counter.  Same-address atomics
+// retire at about one per clock, so a claim per 32-lane round makes a kernel atomic-bound (measured: k_vol_rows, k_vl_step, k_pair_scan).
+// Each warp therefore collects its entries in a shared-memory buffer and claims slots for ~100 entries at a time.  n is warp-uniform.
+#define WS_CAP 128
+template <typename T>
+__device__ __forceinline__ void ws_flush(T *buf, int &n, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
+  if (n == 0) return;
+  u64 base = 0;
+  if (lane == 0) base = atomicAdd(gcount, (u64)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < n; i += 32) if ((i64)(base + i) < cap) gout[base + i] = buf[i];
+  __syncwarp();
+  n = 0;
+}
+template <typename T>
+__device__ __forceinline__ void ws_push(T *buf, int &n, bool pred, const T &val, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (!m) return;
+  if (pred) buf[n + __popc(m & ((1u << lane) - 1))] = val;
+  n += __popc(m);
+  __syncwarp();
+  if (n > WS_CAP - 32) ws_flush(buf, n, gout, gcount, cap, lane);
+}
+// active cell of the threshold search: id, min / max of its corner values, index of its quadrature record (-1: none yet)
+struct VAct { int id; float mn, mx; int rec; };
+// Whole-grid classification (bisection steps 1-3 and the final fine-grid volume): a warp owns cell ROWS; per 31-cell segment every lane
+// loads the 4 values of its x-column (coalesced) and takes the neighbouring column's min / max from lane + 1, so a cell costs 4 loads
+// instead of 8; the row index arithmetic is done once per row.  Cut cells go to cutlist, (EMIT) cells the remaining bracket [lo, hi]
+// can still cut go to the active list; cells that are full for every threshold still to come are counted in acc[3].
 template <bool EMIT>
-__global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int px, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th, int *__restrict__ list_out,
-                                                  u64 *__restrict__ n_out_ptr, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
-  // no block-level synchronisation: list slots are claimed per warp (one atomic per warp and list, only when the row segment holds such
-  // cells -- most segments hold none); the order of the lists does not matter, the volume is an exact integer sum
+__global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int px, int kc0, int kc1, const float *__restrict__ sdf, float lo, float hi, float th, VAct *__restrict__ list_out,
+                                                  u64 *__restrict__ n_out_ptr, i64 list_cap, u64 *__restrict__ acc, int *__restrict__ cutlist, int cutcap) {
+  __shared__ int s_cut[8][WS_CAP];
+  __shared__ VAct s_keep[EMIT ? 8 : 1][EMIT ? WS_CAP : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nseg = (nx - 1 + 30) / 31, nrow = (ny - 1) * (kc1 - kc0);
-  const i64 ntask = (i64)nrow * nseg, sxy = (i64)px * ny;
-  int nfull = 0, nperm = 0;
-  for (i64 task = (i64)blockIdx.x * 8 + warp; task < ntask; task += (i64)gridDim.x * 8) {      // warp-uniform
-    bool cut = false, keep = false; int c = 0;
-    float cmn = INFINITY, cmx = -INFINITY;
-    const int row = (int)(task / nseg), seg = (int)(task % nseg);
-    const int j = row % (ny - 1), k = kc0 + row / (ny - 1), i = seg * 31 + lane;
-    if (i < nx) {
-      const i64 b = ((i64)k * ny + j) * px + i;
-      const float v0 = sdf[b], v1 = sdf[b + px], v2 = sdf[b + sxy], v3 = sdf[b + sxy + px];
-      cmn = fminf(fminf(v0, v1), fminf(v2, v3)); cmx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-    }
-    const float nmn = __shfl_down_sync(0xffffffffu, cmn, 1), nmx = __shfl_down_sync(0xffffffffu, cmx, 1);
-    if (lane < 31 && i < nx - 1) {
-      const float mn = fminf(cmn, nmn), mx = fmaxf(cmx, nmx);
-      c = (int)(((i64)k * (ny - 1) + j) * (nx - 1) + i);
-      if (EMIT && mn >= hi) nperm++;
-      else if (EMIT && mx < lo) {}
-      else {
-        keep = EMIT;
-        if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
+  const int nrow = (ny - 1) * (kc1 - kc0);
+  const i64 sxy = (i64)px * ny;
+  int nfull = 0, nperm = 0, ncq = 0, nkq = 0;
+  for (int row = blockIdx.x * 8 + warp; row < nrow; row += gridDim.x * 8) {      // warp-uniform
+    const int j = row % (ny - 1), k = kc0 + row / (ny - 1);
+    const i64 b0 = ((i64)k * ny + j) * px; const int c0 = (k * (ny - 1) + j) * (nx - 1);
+    for (int i0 = 0; i0 < nx - 1; i0 += 31) {
+      const int i = i0 + lane;
+      bool cut = false, keep = false;
+      float cmn = INFINITY, cmx = -INFINITY;
+      if (i < nx) {
+        const i64 b = b0 + i;
+        const float v0 = sdf[b], v1 = sdf[b + px], v2 = sdf[b + sxy], v3 = sdf[b + sxy + px];
+        cmn = fminf(fminf(v0, v1), fminf(v2, v3)); cmx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
       }
-    }
-    const unsigned mc = __ballot_sync(0xffffffffu, cut), mk = __ballot_sync(0xffffffffu, keep);
-    if (mc) {
-      int base = 0;
-      if (lane == 0) base = (int)atomicAdd(&acc[1], (u64)__popc(mc));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (cut) { const int slot = base + __popc(mc & ((1u << lane) - 1)); if (slot < cutcap) cutlist[slot] = c; }
-    }
-    if (EMIT && mk) {
-      int base = 0;
-      if (lane == 0) base = (int)atomicAdd(n_out_ptr, (u64)__popc(mk));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) list_out[base + __popc(mk & ((1u << lane) - 1))] = c;
+      const float nmn = __shfl_down_sync(0xffffffffu, cmn, 1), nmx = __shfl_down_sync(0xffffffffu, cmx, 1);
+      float mn = 0.f, mx = 0.f;
+      if (lane < 31 && i < nx - 1) {
+        mn = fminf(cmn, nmn); mx = fmaxf(cmx, nmx);
+        if (EMIT && mn >= hi) nperm++;
+        else if (EMIT && mx < lo) {}
+        else {
+          keep = EMIT;
+          if (!(mx < th)) { if (mn >= th) nfull++; else cut = true; }
+        }
+      }
+      ws_push<int>(s_cut[warp], ncq, cut, c0 + i, cutlist, &acc[1], (i64)cutcap, lane);
+      if (EMIT) { VAct e; e.id = c0 + i; e.mn = mn; e.mx = mx; e.rec = -1; ws_push<VAct>(s_keep[warp], nkq, keep, e, list_out, n_out_ptr, list_cap, lane); }
     }
   }
+  ws_flush<int>(s_cut[warp], ncq, cutlist, &acc[1], (i64)cutcap, lane);
+  if (EMIT) ws_flush<VAct>(s_keep[warp], nkq, list_out, n_out_ptr, list_cap, lane);
   for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); }
   if (lane == 0) { if (nfull) atomicAdd(&acc[0], (u64)nfull); if (nperm) atomicAdd(&acc[3], (u64)nperm); }
 }
 // ---- bisection steps >= 4: the ACTIVE list carries everything a cell needs ------------------------------------------------------
 // After three whole-grid steps only the cells that the remaining bracket [lo, hi] can still cut are active (a thin shell around the
-// level set).  From then on each active cell is a 48-byte record: its id, its eight corner values (one coalesced read instead of eight
-// scattered ones per step) and a CACHE of its last quadrature: part (the Float32 sum of w_i w_j w_k over the inside Gauss points),
+// level set).  The active list holds 16 bytes per cell (id, min / max of its corners, record index); a cell that is cut for the first time
+// gets a 48-byte RECORD: its eight corner values (gathered once) and a CACHE of its last quadrature: part (the Float32 sum of w_i w_j w_k over the inside Gauss points),
 // the threshold it was computed at and a margin = the smallest |value| over the 729 Gauss points minus a bound on the Float32
 // round-off of those values.  While |th - th_cached| stays below the margin no Gauss value can change sign, the inside set -- and
 // with it the cell's Float32 sum, bit for bit -- is the same, and the cached sum is added without re-evaluating the cell.  As the
 // bracket halves, almost every cell freezes: the 40 bisections cost about a dozen full quadratures instead of 40.  The total is an
 // exact integer sum, so the result is bit-identical to re-evaluating every cut cell at every step (R2S_VOL_CACHE=0 does that).
-struct VEnt { int id; float c[8]; float part, th_e, margin; };
-__global__ void __launch_bounds__(256) k_vl_gather(i64 n, const int *__restrict__ ids, int nx, int ny, int px, const float *__restrict__ sdf, VEnt *__restrict__ out) {
-  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int c = ids[t];
-  const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)px * ny;
-  const int i = c % (nx - 1), j = (c / (nx - 1)) % (ny - 1), k = (int)(c / cpl);
-  const i64 b = ((i64)k * ny + j) * px + i;
-  VEnt e; e.id = c;
-  e.c[0] = sdf[b]; e.c[1] = sdf[b + 1]; e.c[2] = sdf[b + px]; e.c[3] = sdf[b + px + 1];
-  e.c[4] = sdf[b + sxy]; e.c[5] = sdf[b + sxy + 1]; e.c[6] = sdf[b + sxy + px]; e.c[7] = sdf[b + sxy + px + 1];
-  e.part = 0.0f; e.th_e = NAN; e.margin = -1.0f;
-  out[t] = e;
-}
-// one thread per active record: retire / keep (compaction into `out`), classify at th, use the cache or queue the record for k_vl_eval
-__global__ void __launch_bounds__(256) k_vl_step(const VEnt *__restrict__ in, const u64 *__restrict__ n_in_ptr, VEnt *__restrict__ out, u64 *__restrict__ n_out_ptr, float lo, float hi,
-                                                 float th, int use_cache, u64 *__restrict__ acc, int *__restrict__ evlist) {
+struct VRec { float c[8]; float part, th_e, margin; int pad; };
+// one thread per active cell: retire / keep (compaction into `out`), classify at th from (mn, mx), use the cached quadrature of the cell's
+// record or queue the cell for k_vl_eval.  acc[6] = records handed out so far.
+__global__ void __launch_bounds__(256) k_vl_step(const VAct *__restrict__ in, const u64 *__restrict__ n_in_ptr, VAct *__restrict__ out, u64 *__restrict__ n_out_ptr, i64 out_cap, float lo,
+                                                 float hi, float th, int use_cache, u64 *__restrict__ acc, const VRec *__restrict__ recs, int2 *__restrict__ evlist, i64 ev_cap) {
+  __shared__ VAct s_keep[8][WS_CAP];
+  __shared__ int2 s_ev[8][WS_CAP];
   const i64 n_in = (i64)*n_in_ptr;
-  const int lane = threadIdx.x & 31;
-  int nfull = 0, nperm = 0; u64 local = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nfull = 0, nperm = 0, nkq = 0, neq = 0; u64 local = 0;
   for (i64 t0 = ((i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); t0 < n_in; t0 += (i64)gridDim.x * blockDim.x) {      // warp-uniform
-    const i64 t = t0 + lane; bool keep = false, miss = false; VEnt e;
+    const i64 t = t0 + lane; bool keep = false, miss = false, fresh = false; VAct e; e.id = 0; e.mn = e.mx = 0.f; e.rec = -1;
     if (t < n_in) {
       e = in[t];
-      const float mn = fminf(fminf(fminf(e.c[0], e.c[1]), fminf(e.c[2], e.c[3])), fminf(fminf(e.c[4], e.c[5]), fminf(e.c[6], e.c[7])));
-      const float mx = fmaxf(fmaxf(fmaxf(e.c[0], e.c[1]), fmaxf(e.c[2], e.c[3])), fmaxf(fmaxf(e.c[4], e.c[5]), fmaxf(e.c[6], e.c[7])));
-      if (mn >= hi) nperm++;                          // full for every threshold still to come
-      else if (mx < lo) {}                            // empty for every threshold still to come
+      if (e.mn >= hi) nperm++;                        // full for every threshold still to come
+      else if (e.mx < lo) {}                          // empty for every threshold still to come
       else {
         keep = true;
-        if (!(mx < th)) {
-          if (mn >= th) nfull++;
-          else if (use_cache && fabsf(th - e.th_e) * 1.00001f < e.margin) local += (u64)llrint((double)e.part * 137438953472.0);      // (NaN th_e compares false)
-          else miss = true;
+        if (!(e.mx < th)) {
+          if (e.mn >= th) nfull++;
+          else if (e.rec < 0) { miss = true; fresh = true; }
+          else {
+            const VRec &r = recs[e.rec];
+            if (use_cache && fabsf(th - r.th_e) * 1.00001f < r.margin) local += (u64)llrint((double)r.part * 137438953472.0);
+            else miss = true;
+          }
         }
       }
     }
-    const unsigned mk = __ballot_sync(0xffffffffu, keep), mm = __ballot_sync(0xffffffffu, miss);
-    int slot = 0;
-    if (mk) {
+    // new records: one claim per warp round (only cells that are cut for the first time)
+    const unsigned mf = __ballot_sync(0xffffffffu, fresh);
+    if (mf) {
       int base = 0;
-      if (lane == 0) base = (int)atomicAdd(n_out_ptr, (u64)__popc(mk));
+      if (lane == 0) base = (int)atomicAdd(&acc[6], (u64)__popc(mf));
       base = __shfl_sync(0xffffffffu, base, 0);
-      slot = base + __popc(mk & ((1u << lane) - 1));
-      if (keep) out[slot] = e;
+      if (fresh) e.rec = base + __popc(mf & ((1u << lane) - 1));
     }
-    if (mm) {
-      int base = 0;
-      if (lane == 0) base = (int)atomicAdd(&acc[1], (u64)__popc(mm));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (miss) evlist[base + __popc(mm & ((1u << lane) - 1))] = slot;
-    }
+    ws_push<VAct>(s_keep[warp], nkq, keep, e, out, n_out_ptr, out_cap, lane);
+    ws_push<int2>(s_ev[warp], neq, miss, make_int2(e.rec | (fresh ? (int)0x80000000 : 0), e.id), evlist, &acc[1], ev_cap, lane);
   }
+  ws_flush<VAct>(s_keep[warp], nkq, out, n_out_ptr, out_cap, lane);
+  ws_flush<int2>(s_ev[warp], neq, evlist, &acc[1], ev_cap, lane);
   for (int o = 16; o > 0; o >>= 1) { nfull += __shfl_down_sync(0xffffffffu, nfull, o); nperm += __shfl_down_sync(0xffffffffu, nperm, o); local += __shfl_down_sync(0xffffffffu, local, o); }
   if (lane == 0) { if (nfull) atomicAdd(&acc[0], (u64)nfull); if (nperm) atomicAdd(&acc[3], (u64)nperm); if (local) atomicAdd(&acc[2], local); }
 }
-// quadrature of the queued records at th (same point values, same order of the Float32 sum as k_vol_cut) + their new cache entries
-__global__ void __launch_bounds__(128) k_vl_eval(VEnt *__restrict__ ent, const int *__restrict__ evlist, float th, GaussF G, u64 *__restrict__ acc) {
+// quadrature of the queued cells at th (same point values, same order of the Float32 sum as k_vol_cut) + their new cache entries; a cell
+// that is cut for the first time gathers its corner values into its record
+__global__ void __launch_bounds__(128) k_vl_eval(VRec *__restrict__ recs, const int2 *__restrict__ evlist, int nx, int ny, int px, const float *__restrict__ sdf, float th, GaussF G,
+                                                 u64 *__restrict__ acc) {
   const int nev = (int)acc[1];
   const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
   u64 local = 0;
   for (int base = blockIdx.x * blockDim.x; base < nev; base += nthr) {      // warp-uniform trip count
     const int idx = base + threadIdx.x;
     if (idx < nev) {
-      VEnt &e = ent[evlist[idx]];
-      const float c000 = e.c[0] - th, c100 = e.c[1] - th, c010 = e.c[2] - th, c110 = e.c[3] - th;
-      const float c001 = e.c[4] - th, c101 = e.c[5] - th, c011 = e.c[6] - th, c111 = e.c[7] - th;
+      const int2 q = evlist[idx];
+      VRec &e = recs[q.x & 0x7fffffff];
+      float c[8];
+      if (q.x < 0) {
+        const i64 cpl = (i64)(nx - 1) * (ny - 1), sxy = (i64)px * ny;
+        const int i = q.y % (nx - 1), j = (q.y / (nx - 1)) % (ny - 1), k = (int)(q.y / cpl);
+        const i64 b = ((i64)k * ny + j) * px + i;
+        c[0] = sdf[b]; c[1] = sdf[b + 1]; c[2] = sdf[b + px]; c[3] = sdf[b + px + 1];
+        c[4] = sdf[b + sxy]; c[5] = sdf[b + sxy + 1]; c[6] = sdf[b + sxy + px]; c[7] = sdf[b + sxy + px + 1];
+#pragma unroll
+        for (int a = 0; a < 8; a++) e.c[a] = c[a];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 8; a++) c[a] = e.c[a];
+      }
+      const float c000 = c[0] - th, c100 = c[1] - th, c010 = c[2] - th, c110 = c[3] - th;
+      const float c001 = c[4] - th, c101 = c[5] - th, c011 = c[6] - th, c111 = c[7] - th;
       const float amax = fmaxf(fmaxf(fmaxf(fabsf(c000), fabsf(c100)), fmaxf(fabsf(c010), fabsf(c110))), fmaxf(fmaxf(fabsf(c001), fabsf(c101)), fmaxf(fabsf(c011), fabsf(c111))));
       float part = 0.0f, m = INFINITY;
 #pragma unroll 1
@@ -623,16 +649,17 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
   static const GaussF G9 = gauss9f();
   const i64 n_all = (i64)(vb.nx - 1) * (vb.ny - 1) * (i64)(vb.kc1 - vb.kc0);
   vb.step++;
-  if (vb.step >= 4) {      // active-list steps: 48-byte records with cached quadratures (see k_vl_step)
+  if (vb.step >= 4) {      // active-list steps: 16-byte entries, records with cached quadratures for the cells that get cut (see k_vl_step)
     const int in = vb.cur, out = 1 - vb.cur;
-    CK(ctx->vent[out].reserve(sizeof(VEnt) * (size_t)(vb.n_cur + 1)));
-    CK(ctx->vlist[1].reserve(sizeof(int) * (size_t)(vb.n_cur + 1)));      // queue of records to evaluate (slots of the output list)
+    CK(ctx->vent[out].reserve(sizeof(VAct) * (size_t)(vb.n_cur + 1)));
+    CK(ctx->vlist[1].reserve(sizeof(int2) * (size_t)(vb.n_cur + 1)));      // queue of cells to evaluate
     u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
     CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
     CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
-    const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 16);
-    k_vl_step<<<grid, 256, 0, st>>>(ctx->vent[in].as<VEnt>(), nin, ctx->vent[out].as<VEnt>(), nout, lo, hi, th, ctx->knobs.vol_cache, vb.acc, ctx->vlist[1].as<int>()); LAUNCH_CHECK();
-    k_vl_eval<<<148 * 16, 128, 0, st>>>(ctx->vent[out].as<VEnt>(), ctx->vlist[1].as<int>(), th, G9, vb.acc); LAUNCH_CHECK();
+    const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 8);
+    k_vl_step<<<grid, 256, 0, st>>>(ctx->vent[in].as<VAct>(), nin, ctx->vent[out].as<VAct>(), nout, vb.n_cur + 1, lo, hi, th, ctx->knobs.vol_cache, vb.acc, ctx->vrec.as<VRec>(),
+                                    ctx->vlist[1].as<int2>(), vb.n_cur + 1); LAUNCH_CHECK();
+    k_vl_eval<<<148 * 16, 128, 0, st>>>(ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.nx, vb.ny, vb.px, vb.sdf, th, G9, vb.acc); LAUNCH_CHECK();
     u64 *red = vb.acc + 8, hall[12];
     k_vol_pack<<<1, 1, 0, st>>>(vb.acc, 0x7fffffff, red); LAUNCH_CHECK();
     if (r2s_allreduce(ctx, red, 4, 1)) return 1;
@@ -642,22 +669,19 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
     *vol = (double)hall[8] * (double)ev + ((double)hall[10] / 137438953472.0 /* 2^37 */) * (double)jac;
     return 0;
   }
-  const bool emit = vb.step == 3;      // steps 1-3 classify the whole grid (k_vol_rows); step 3 also emits the active list
-  if (emit) CK(ctx->vlist[0].reserve(sizeof(int) * (size_t)(n_all + 1)));
-  const int out = 0;
+  const bool emit = vb.step == 3;      // steps 1-3 classify the whole grid (k_vol_rows); step 3 also emits the active list (into list 0)
+  if (emit) CK(ctx->vent[0].reserve(sizeof(VAct) * (size_t)(n_all + 1)));
   u64 h[6];
   for (int attempt = 0; attempt < 2; attempt++) {
     int cutcap = (int)(ctx->cutlist.cap / sizeof(int));
     CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
-    int *lout = ctx->vlist[out].as<int>(); u64 *nout = vb.acc + 4 + out;
-    {
-      // (a second attempt follows a cut-list overflow: the list has been grown, the step is repeated from scratch)
-      if (emit) { CK(cudaMemsetAsync(nout, 0, sizeof(u64), st)); CK(cudaMemsetAsync(vb.acc + 3, 0, sizeof(u64), st)); }      // step 3 is the first step that retires cells
-      const i64 ntask = (i64)(vb.ny - 1) * (vb.kc1 - vb.kc0) * ((vb.nx - 1 + 30) / 31);
-      const int rgrid = (int)std::min<i64>(std::max<i64>(cdiv(ntask, 8), 1), 148 * 16);
-      if (!emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, vb.acc, ctx->cutlist.as<int>(), cutcap);
-      else k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, lout, nout, vb.acc, ctx->cutlist.as<int>(), cutcap);
-    }
+    u64 *nout = vb.acc + 4;
+    // (a second attempt follows a cut-list overflow: the list has been grown, the step is repeated from scratch)
+    if (emit) { CK(cudaMemsetAsync(nout, 0, sizeof(u64), st)); CK(cudaMemsetAsync(vb.acc + 3, 0, sizeof(u64), st)); }      // step 3 is the first step that retires cells
+    const int nrow = (vb.ny - 1) * (vb.kc1 - vb.kc0);
+    const int rgrid = (int)std::min<i64>(std::max<i64>(cdiv(nrow, 8), 1), 148 * 8);
+    if (!emit) k_vol_rows<false><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, nullptr, nullptr, 0, vb.acc, ctx->cutlist.as<int>(), cutcap);
+    else k_vol_rows<true><<<rgrid, 256, 0, st>>>(vb.nx, vb.ny, vb.px, vb.kc0, vb.kc1, vb.sdf, lo, hi, th, ctx->vent[0].as<VAct>(), nout, n_all + 1, vb.acc, ctx->cutlist.as<int>(), cutcap);
     LAUNCH_CHECK();
     k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.px, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
     // cross-rank sum of (full cells, overflow flag, cut sum); integers, so the total does not depend on the slab count
@@ -674,11 +698,9 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
       if ((i64)h[1] > cutcap) CK(ctx->cutlist.reserve(sizeof(int) * (size_t)(h[1] + h[1] / 2 + 1024)));
       continue;
     }
-    if (emit) {      // step 3: the active cells become records (id + corner values + empty cache) for the list steps that follow
-      vb.cur = 0; vb.n_cur = (i64)h[4 + out];
-      CK(ctx->vent[0].reserve(sizeof(VEnt) * (size_t)(vb.n_cur + 1)));
-      if (vb.n_cur > 0) { k_vl_gather<<<cdiv(vb.n_cur, 256), 256, 0, st>>>(vb.n_cur, ctx->vlist[0].as<int>(), vb.nx, vb.ny, vb.px, vb.sdf, ctx->vent[0].as<VEnt>()); LAUNCH_CHECK(); }
-      // acc[4] must hold the size of list 0 for the next step: it does (out == 0 at step 3)
+    if (emit) {      // step 3: list 0 holds the active cells; room for one record per active cell (only cells that get cut use one)
+      vb.cur = 0; vb.n_cur = (i64)h[4];
+      CK(ctx->vrec.reserve(sizeof(VRec) * (size_t)(vb.n_cur + 1)));
     }
     vb.n_eval += (i64)h[1];
     float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
