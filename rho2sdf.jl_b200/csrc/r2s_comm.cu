@@ -269,7 +269,8 @@ struct P2PBox {
   unsigned long long error;
   unsigned long long halo_count[2];        // CTA completion counters of the put kernel
 };
-__global__ void k_p2p_allreduce(P2PBox *mine, P2PBox *const *peers, int rank, int R, unsigned seq, unsigned long long *vals, int n, int kind) {
+__global__ void k_p2p_allreduce(P2PBox *mine, P2PBox *const *peers, int rank, int R, unsigned seq, unsigned long long *vals, int n, int kind, const float *skip) {
+  if (skip && *skip != 0.0f) return;      // every rank sees the same flag (it is computed from all-reduced values): all skip or none
   const int p = threadIdx.x, par = seq & 1;
   if (p < R) {
     volatile unsigned long long *dst = peers[p]->slot[par][rank];
@@ -309,10 +310,10 @@ static int p2p_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind) {
   const unsigned seq = ++ctx->p2p_seq;
   if (kind == 2 || kind == 3) {
     k_p2p_widen<<<1, 32, 0, ctx->stream>>>((const unsigned *)buf, stage, (int)count);
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, stage, (int)count, kind);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, stage, (int)count, kind, ctx->skip_flag);
     k_p2p_narrow<<<1, 32, 0, ctx->stream>>>(stage, (unsigned *)buf, (int)count);
   } else {
-    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, (unsigned long long *)buf, (int)count, kind);
+    k_p2p_allreduce<<<1, 64, 0, ctx->stream>>>(mine, (P2PBox *const *)ctx->p2p_peer_box_dev, ctx->rank, ctx->nranks, seq, (unsigned long long *)buf, (int)count, kind, ctx->skip_flag);
   }
   CK(cudaGetLastError());
   ctx->p2p_ops++;
@@ -473,7 +474,8 @@ int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
 }
 // copies [n floats at src_off] of my array into the same offsets of the neighbour's array, then the last CTA raises the flag
 __global__ void __launch_bounds__(256) k_p2p_halo_put(const float *__restrict__ mine, float *lower, float *upper, i64 off_lo, i64 n_lo, i64 off_hi, i64 n_hi,
-                                                      P2PBox *box_lower, P2PBox *box_upper, P2PBox *box_mine, unsigned seq) {
+                                                      P2PBox *box_lower, P2PBox *box_upper, P2PBox *box_mine, unsigned seq, const float *skip) {
+  if (skip && *skip != 0.0f) return;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n_lo + n_hi; i += stride) {
     if (i < n_lo) { if (lower) lower[off_lo + i] = mine[off_lo + i]; }
@@ -492,7 +494,8 @@ __global__ void __launch_bounds__(256) k_p2p_halo_put(const float *__restrict__ 
     }
   }
 }
-__global__ void k_p2p_halo_wait(P2PBox *mine, int has_lower, int has_upper, unsigned seq) {
+__global__ void k_p2p_halo_wait(P2PBox *mine, int has_lower, int has_upper, unsigned seq, const float *skip) {
+  if (skip && *skip != 0.0f) return;
   const int par = seq & 1;
   if (threadIdx.x < 2) {
     const bool need = threadIdx.x == 0 ? has_lower : has_upper;
@@ -511,14 +514,14 @@ int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, 
   (void)nz;
   P2PBox *mine = (P2PBox *)ctx->p2p_box;
   k_p2p_halo_put<<<148, 256, 0, ctx->stream>>>(c, lo ? (float *)ctx->p2p_c_peer[0] : nullptr, hi ? (float *)ctx->p2p_c_peer[1] : nullptr, off_lo, n_lo, off_hi, n_hi,
-                                               lo ? (P2PBox *)ctx->p2p_peer_box[r - 1] : nullptr, hi ? (P2PBox *)ctx->p2p_peer_box[r + 1] : nullptr, mine, seq);
+                                               lo ? (P2PBox *)ctx->p2p_peer_box[r - 1] : nullptr, hi ? (P2PBox *)ctx->p2p_peer_box[r + 1] : nullptr, mine, seq, ctx->skip_flag);
   CK(cudaGetLastError());
   ctx->p2p_ops++;
   return 0;
 }
 int r2s_p2p_halo_wait(r2s_ctx *ctx) {
   const int r = ctx->rank;
-  k_p2p_halo_wait<<<1, 32, 0, ctx->stream>>>((P2PBox *)ctx->p2p_box, r > 0, r + 1 < ctx->nranks, ctx->p2p_halo_seq);
+  k_p2p_halo_wait<<<1, 32, 0, ctx->stream>>>((P2PBox *)ctx->p2p_box, r > 0, r + 1 < ctx->nranks, ctx->p2p_halo_seq, ctx->skip_flag);
   CK(cudaGetLastError());
   return 0;
 }

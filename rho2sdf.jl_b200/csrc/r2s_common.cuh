@@ -105,6 +105,7 @@ struct r2s_ctx {
   bool has_grid = false;
   GridDev g;
   i64 k0 = 0, k1 = 0;                       // slab of coarse planes handled by this context
+  const float *skip_flag = nullptr;          // device flag: while set and non-zero, the peer-memory exchange kernels return at once (CG iterations launched ahead of the convergence check)
   LocalGroup *lg = nullptr;                  // set when this context is one slab of an in-process group (threads instead of processes, no NCCL)
   void *comm = nullptr; int rank = 0, nranks = 1; i64 collectives = 0; std::vector<int> slab_k0;
   // peer-memory fast path for the latency-critical exchanges (scalar all-reduces, CG halo planes): every rank maps every

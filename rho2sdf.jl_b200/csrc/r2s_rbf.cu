@@ -43,6 +43,22 @@ __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__re
 // ------------------------------------------------------------------------------------------------ 81-point stencil
 // weights by squared offset m = di^2+dj^2+dk^2 <= 6
 struct StencilW { float w[8]; };
+// The CTA that finishes LAST adds up the per-CTA partial sums (fixed order: 256 strided sums, then slot 0..255 sequentially -- the same
+// order whatever CTA happens to be last, so the result is deterministic) and stores the total: no separate reduction launch.
+// Call with all 256 threads of the CTA after thread 0 has written partial[this CTA].
+__device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks, unsigned *ticket, double *dst) {
+  __shared__ bool s_last; __shared__ double s_sum[256];
+  const int tid = threadIdx.x;
+  if (tid == 0) { __threadfence(); s_last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1u; }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double a = 0; for (int i = tid; i < nblocks; i += 256) a += __ldcg(&partial[i]);
+  s_sum[tid] = a; __syncthreads();
+  if (tid == 0) { double t = 0; for (int i = 0; i < 256; i++) t += s_sum[i]; *dst = t; *ticket = 0; __threadfence(); }
+  __syncthreads();
+  return true;
+}
 // ---- plane marching (2.5-D blocking) with TMA-staged planes, two outputs per thread ------------------------------------------------
 // A CTA owns a 32 x 16 column of the grid and marches along z over zc output planes.  Each input plane tile (40 x 20 floats with its
 // x-y halo) is brought into shared memory by ONE bulk tensor copy (cp.async.bulk.tensor.3d, TMA) issued by one thread NST - 1 planes
@@ -85,8 +101,9 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 template <bool BETA>
 __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nx, int ny, int nz, int px,
                                                        int kz0, int kz1, int zc, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
-                                                       double *__restrict__ partial, StencilW W) {
+                                                       double *__restrict__ partial, StencilW W, unsigned *__restrict__ ticket, double *__restrict__ dot_out) {
   constexpr int TX = S3_TX, TY = S3_TY, NT = TX * TY, NARR = BETA ? 2 : 1;
+  if (BETA && scal[5] != 0.0f) return;      // CG has converged: the iterations launched ahead of the host's check are no-ops
   __shared__ __align__(128) unsigned char stage[S3_NST * NARR * S3_SLOT];
   __shared__ __align__(16) float comb[BETA ? 2 : 1][BETA ? NT : 2];      // combined plane r + beta * u (double buffered), CG form only
   __shared__ __align__(8) unsigned long long full[S3_NST];
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
     double a = 0; for (int i = 0; i < 8; i++) a += red[i];
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
+  if (ticket) cta_sum_last(partial, (int)(gridDim.x * gridDim.y * gridDim.z), ticket, dot_out);
 }
 // tensor map of a coarse Float32 field (nx x ny x nz values, row pitch px floats) with the 40 x 20 x 1 box of the stencil tiles
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -207,23 +225,30 @@ static int stencil_tensor_map(r2s_ctx *ctx, CUtensorMap *map, const float *base,
   if (rc != CUDA_SUCCESS) { char b[96]; snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc); FAIL(b); }
   return 0;
 }
-// CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, uc, rr}
+// CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, converged flag, iterations}
 __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restrict__ dst) {
   __shared__ double sh[256];
   double a = 0; for (int i = threadIdx.x; i < n; i += 256) a += part[i];
   sh[threadIdx.x] = a; __syncthreads();
   if (threadIdx.x == 0) { double s = 0; for (int i = 0; i < 256; i++) s += sh[i]; *dst = s; }
 }
-__global__ void k_cg_alpha(float *scal, const double *uc) {     // alpha = residual^2 / dot(u, c)
-  float res = scal[2]; scal[1] = res * res / (float)(*uc);
-}
 // elementwise over [0, n) (owned planes plus halo); the residual norm is summed over the owned part [o_lo, o_hi) only.
 // Grid-stride with a fixed grid (CG_BLOCKS CTAs): few, fat CTAs keep the loads in flight and leave only CG_BLOCKS partial sums.
+// alpha = residual^2 / dot(u, c) is formed by every thread from the (all-reduced) dot product; the last CTA adds up the partial sums of
+// |r|^2 and, on a single rank (finalize), closes the iteration: residual, beta, iteration count, convergence flag.
 #define CG_BLOCKS (148 * 8)
-__global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, const float *__restrict__ scal, const float *__restrict__ u, const float *__restrict__ c,
-                                                   float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial) {
+__device__ __forceinline__ void cg_close_iteration(float *scal, double rr) {      // prev = residual; residual = norm(r); beta for the next iteration (IterativeSolvers CGIterable)
+  const float prev = scal[2], res = (float)sqrt(rr);
+  scal[3] = prev; scal[2] = res; scal[0] = res * res / (prev * prev);
+  scal[6] += 1.0f;
+  if (res <= scal[4]) scal[5] = 1.0f;
+}
+__global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, float *__restrict__ scal, const double *__restrict__ uc, const float *__restrict__ u,
+                                                   const float *__restrict__ c, float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial, unsigned *__restrict__ ticket,
+                                                   double *__restrict__ rr_out, int finalize) {
   __shared__ double red[8];
-  const float alpha = scal[1]; double rr = 0.0;
+  if (scal[5] != 0.0f) return;
+  const float res0 = scal[2], alpha = res0 * res0 / (float)(*uc); double rr = 0.0;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += 4 * stride) {       // 4 independent elements per trip: 16 loads in flight
     float xv[4], uv[4], rv[4], cv[4];
@@ -239,14 +264,16 @@ __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, co
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
   __syncthreads();
   if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i]; partial[blockIdx.x] = a; }
+  if (cta_sum_last(partial, (int)gridDim.x, ticket, rr_out) && finalize && threadIdx.x == 0) { scal[1] = alpha; cg_close_iteration(scal, *rr_out); }
 }
-__global__ void k_cg_residual(float *scal, const double *rr) {  // prev = residual; residual = norm(r); beta for the next iteration
-  float prev = scal[2], res = (float)sqrt(*rr);
-  scal[3] = prev; scal[2] = res; scal[0] = res * res / (prev * prev);
+__global__ void k_cg_residual(float *scal, const double *rr) {      // several ranks: the same closing step after the all-reduce of |r|^2
+  if (scal[5] != 0.0f) return;
+  cg_close_iteration(scal, *rr);
 }
 __global__ void k_cg_init(float *scal, const double *rr) {
   float res = (float)sqrt(*rr);
   scal[2] = res; scal[3] = 1.0f; scal[4] = sqrtf(FLT_EPSILON) * res; scal[0] = res * res / (1.0f * 1.0f); scal[1] = 0.0f;
+  scal[6] = 0.0f; scal[5] = (res <= scal[4]) ? 1.0f : 0.0f;
 }
 __global__ void __launch_bounds__(256) k_dot_self(i64 n, const float *__restrict__ a, double *__restrict__ partial) {
   __shared__ double red[8];
@@ -841,7 +868,7 @@ __global__ void __launch_bounds__(F2_X *F2_Y *F2_ZT) k_fine_eval2(int nx, int ny
 // u_new = r + beta * u_old on the halo planes of a slab (the fused stencil kernel writes u_new on the owned planes only)
 __global__ void k_unew_halo(i64 n1, i64 off2, i64 n2, const float *__restrict__ scal, const float *__restrict__ r, const float *__restrict__ u, float *__restrict__ unew) {
   i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (v >= n1 + n2) return;
+  if (v >= n1 + n2 || scal[5] != 0.0f) return;
   i64 i = v < n1 ? v : off2 + (v - n1);
   unew[i] = r[i] + scal[0] * u[i];
 }
@@ -946,42 +973,51 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     k_cg_init<<<1, 1, 0, st>>>(scal, dsc); LAUNCH_CHECK();
     float hs[8];
     if (r2s_readback(ctx, hs, scal, sizeof(hs))) return 1;
-    float residual = hs[2], tol = hs[4];
     float *u_old = u, *u_new = u + n;      // ping-pong halves of the u buffer
     if (r2s_p2p_map_c(ctx, c, sizeof(float) * (size_t)n)) return 1;
     const i64 nh_lo = (i64)(k0 - e0) * pl, nh_hi = (i64)(e1 - k1) * pl;      // halo sizes below / above
-    while (iters < n && !(residual <= tol)) {
-      const bool probe = iters == 3;      // one iteration is split by events for the report (cg_probe)
-      if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
-      // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)
-      k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W);
-      LAUNCH_CHECK();
-      if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
-      k_sum_to<<<1, 256, 0, st>>>(part, nsb, dsc + 1); LAUNCH_CHECK();
-      if (probe) CK(cudaEventRecord(ctx->ev_probe[1], st));
-      if (ctx->p2p) {                                // peer memory: my boundary planes of c go straight into the neighbours' halos
-        if (r2s_p2p_halo_put_c(ctx, c, pl, k0, k1, nz, 2)) return 1;
-        if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
-        if (r2s_p2p_halo_wait(ctx)) return 1;
-      } else {
-        if (r2s_group_start(ctx)) return 1;          // one NCCL launch: scalar all-reduce + halo planes of c
-        if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
-        if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
-        if (r2s_group_end(ctx)) return 1;
+    unsigned *tick = (unsigned *)((char *)ctx->f_scal.p + 80);               // tickets of the two fused reductions
+    // The convergence test lives on the device (scal[5]); the host launches CG_CHUNK iterations at a time and then reads the flag and the
+    // iteration count back.  Iterations launched after convergence return at their first instruction (and the peer-memory exchanges skip
+    // themselves through ctx->skip_flag), so the result is that of IterativeSolvers' loop: while iters < maxiter && residual > tol.
+    constexpr int CG_CHUNK = 4;
+    ctx->skip_flag = scal + 5;
+    int launched = 0; bool probed = false;
+    const int single = ctx->nranks == 1 ? 1 : 0;
+    while (hs[5] == 0.0f && launched < n) {
+      for (int q = 0; q < CG_CHUNK; q++, launched++) {
+        const bool probe = launched == 3;      // one iteration is split by events for the report (cg_probe)
+        if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
+        // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)  (partial sums added up by the last CTA)
+        k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W, tick, dsc + 1);
+        LAUNCH_CHECK();
+        if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
+        if (probe) CK(cudaEventRecord(ctx->ev_probe[1], st));
+        if (ctx->p2p) {                                // peer memory: my boundary planes of c go straight into the neighbours' halos
+          if (r2s_p2p_halo_put_c(ctx, c, pl, k0, k1, nz, 2)) return 1;
+          if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
+          if (r2s_p2p_halo_wait(ctx)) return 1;
+        } else {
+          if (r2s_group_start(ctx)) return 1;          // one NCCL launch: scalar all-reduce + halo planes of c
+          if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
+          if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
+          if (r2s_group_end(ctx)) return 1;
+        }
+        if (probe) CK(cudaEventRecord(ctx->ev_probe[2], st));
+        k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, dsc + 1, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part, tick + 1, dsc + 2, single); LAUNCH_CHECK();
+        if (probe) CK(cudaEventRecord(ctx->ev_probe[3], st));
+        if (!single) {
+          if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
+          k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
+        }
+        if (probe) CK(cudaEventRecord(ctx->ev_probe[4], st));
+        { float *t = u_old; u_old = u_new; u_new = t; upar ^= 1; }
       }
-      if (probe) CK(cudaEventRecord(ctx->ev_probe[2], st));
-      k_cg_alpha<<<1, 1, 0, st>>>(scal, dsc + 1); LAUNCH_CHECK();
-      k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part); LAUNCH_CHECK();
-      k_sum_to<<<1, 256, 0, st>>>(part, nub, dsc + 2); LAUNCH_CHECK();
-      if (probe) CK(cudaEventRecord(ctx->ev_probe[3], st));
-      if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
-      if (probe) CK(cudaEventRecord(ctx->ev_probe[4], st));
-      k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
-      if (r2s_readback(ctx, hs, scal, sizeof(hs))) return 1;
-      residual = hs[2]; iters++;
-      if (probe) for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1]));
-      { float *t = u_old; u_old = u_new; u_new = t; upar ^= 1; }
+      if (r2s_readback(ctx, hs, scal, sizeof(hs))) { ctx->skip_flag = nullptr; return 1; }
+      if (!probed && launched > 3) { probed = true; for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1])); }
     }
+    ctx->skip_flag = nullptr;
+    iters = (int)hs[6];
     wgt = x;
     if (r2s_halo_exchange_f32(ctx, x, pl, k0, k1, nz, 2, 3)) return 1;      // the fine evaluation reaches 3 planes up
   }
@@ -992,7 +1028,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   {
     CUtensorMap tm_w;
     if (stencil_tensor_map(ctx, &tm_w, wgt, nx, ny, nz, px)) return 1;
-    k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W);
+    k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W, nullptr, nullptr);
   }
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1

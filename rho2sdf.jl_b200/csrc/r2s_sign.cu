@@ -288,28 +288,25 @@ __global__ void k_lat_pt(GridDev g, const double *__restrict__ xs, int o0, int o
   pt[g.pc_off[d] + i] = (a0 << 2) | cnt;
 }
 #define CSWAP(a, b) do { const unsigned _lo = min(key[a], key[b]), _hi = max(key[a], key[b]); key[a] = _lo; key[b] = _hi; } while (0)
-__global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz1, const int *__restrict__ pt, const double *__restrict__ xs, int o0, int o1, int o2,
+__global__ void __launch_bounds__(128) k_sign_lattice(GridDev g, int kz0, int kz1, const int *__restrict__ pt, const double *__restrict__ xs, int o0, int o1, int o2,
                                                       int m0, int m1, const unsigned *__restrict__ info, const int *__restrict__ IEN, const double *__restrict__ rn,
                                                       double rho_t, const double *__restrict__ dist, double *__restrict__ signs, double *__restrict__ sdf) {
-  const i64 pl = (i64)g.np[0] * g.np[1], nv = pl * (kz1 - kz0);
-  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (t >= nv) return;
-  const int i = (int)(t % g.np[0]), j = (int)((t / g.np[0]) % g.np[1]), k = kz0 + (int)(t / pl);
+  // one thread per grid point; block = 128 consecutive points of one grid row (no 64-bit index arithmetic)
+  const i64 pl = (i64)g.np[0] * g.np[1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = kz0 + blockIdx.z;
+  if (i >= g.np[0]) return;
   const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
   const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
   double sign = -1.0;
   if (n0 * n1 * n2 != 0) {
-    unsigned key[8]; bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
+    // first look at the density classes only: most points need nothing else
+    bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
-      key[q] = 0xffffffffu;
       if (ii < n0 && jj < n1 && kk < n2) {
         const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
-        if (w != 0xffffffffu) {
-          key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q; hotany = hotany || (w >> 31); nc++;
-          const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2;
-        }
+        if (w != 0xffffffffu) { hotany = hotany || (w >> 31); nc++; const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2; }
       }
     }
     // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
@@ -319,6 +316,16 @@ __global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz
     if (nc > 0 && nvoid == nc) sign = -1.0;
     else if (nc > 0 && nsolid == nc) sign = 1.0;
     else if (nc > 0 && hotany) {      // skip rule (SignDetection.jl:36): some candidate has a nodal density >= rho_t
+      unsigned key[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+        key[q] = 0xffffffffu;
+        if (ii < n0 && jj < n1 && kk < n2) {
+          const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
+          if (w != 0xffffffffu) key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q;
+        }
+      }
       if (nc > 1) {              // ascending element index = the reference's candidate order
         CSWAP(0, 1); CSWAP(2, 3); CSWAP(4, 5); CSWAP(6, 7); CSWAP(0, 2); CSWAP(1, 3); CSWAP(4, 6); CSWAP(5, 7); CSWAP(1, 2); CSWAP(5, 6);
         CSWAP(0, 4); CSWAP(1, 5); CSWAP(2, 6); CSWAP(3, 7); CSWAP(2, 4); CSWAP(3, 5); CSWAP(1, 2); CSWAP(3, 4); CSWAP(5, 6);
@@ -385,8 +392,8 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
     const int *lo = ctx->lat_off, *nd = ctx->lat_nd;
     k_lat_info<<<cdiv(nel, 256), 256, 0, st>>>(nel, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->lat_cell.as<int>(), ctx->ezr.as<double2>(), zlo, zhi, ctx->lat_info.as<unsigned>()); LAUNCH_CHECK();
     k_lat_pt<<<cdiv(npt, 256), 256, 0, st>>>(g, ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0], nd[1], nd[2], ctx->lat_pt.as<int>()); LAUNCH_CHECK();
-    const i64 nv = (i64)g.np[0] * g.np[1] * (kz1 - kz0);
-    k_sign_lattice<<<cdiv(nv, 256), 256, 0, st>>>(g, kz0, kz1, ctx->lat_pt.as<int>(), ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0] - 1, nd[1] - 1, ctx->lat_info.as<unsigned>(),
+    const dim3 sg((unsigned)cdiv(g.np[0], 128), (unsigned)g.np[1], (unsigned)(kz1 - kz0));
+    k_sign_lattice<<<sg, 128, 0, st>>>(g, kz0, kz1, ctx->lat_pt.as<int>(), ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0] - 1, nd[1] - 1, ctx->lat_info.as<unsigned>(),
                                                   ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf); LAUNCH_CHECK();
     return 0;
   }
