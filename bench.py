@@ -29,8 +29,10 @@ import numpy as np  # noqa: E402
 METRIC = "sdf_voxels_per_sec"
 UNIT = "voxels/s"
 # algorithmic work per unit (restated in DESIGN.md "Rooflines")
-FLOP_PER_PAIR = 2100.0          # FP64 flop per (element, grid point) projection
-B_PER_VOXEL_CG_ITER = 28.0      # Float32 CG: stencil read p + write Ap (8 B) + x, r, p updates (20 B)
+FLOP_PER_PAIR_SURVEY = 2100.0   # SURVEY 8(d) estimate: FP64 flop per (element, grid point) projection (about 6 SQP evaluations of 350 flop)
+B_PER_VOXEL_MATVEC = 16.0       # CG mat-vec: read r, u_old; write u_new, c (Float32)
+B_PER_VOXEL_UPDATE = 24.0       # CG update: read x, u, r, c; write x, r
+B_PER_VOXEL_CG_ITER = B_PER_VOXEL_MATVEC + B_PER_VOXEL_UPDATE
 B_PER_FINE_VOXEL = 4.5          # fine evaluation: 4 B write + 1/8 * 4 B weight read
 FMA_PER_FINE_VOXEL = 79.75      # mean of the 8 polyphase tap counts (81 + 3*70 + 3*80 + 88) / 8
 B_PER_VOXEL_SIGN = 8.0
@@ -362,38 +364,42 @@ def run_gpu(args):
                                                                          "ms_threshold", "ms_fine", "ms_volume", "ms_total")}
         rep = reps[-1]
         ngp_local = n_sdf_local
+        # k_project_list: EXECUTED FP64 flop per solved pair, measured with ncu on this workload (tools/extract_counts.py -> profiles/project_list_counts.json;
+        # thread-level dfma x 2 + dadd + dmul with the predicate on).  Pruned pairs are never projected, so they carry no work.
+        counts = None
+        cp = os.path.join(ROOT, "profiles", "project_list_counts.json")
+        if os.path.exists(cp):
+            try:
+                counts = json.load(open(cp))
+            except Exception:
+                counts = None
+        solved = int(rep.n_pairs - rep.n_pairs_pruned)
+        ms_solve = float(np.mean([r.ms_solve for r in reps]))
+        ms_scan = float(np.mean([r.ms_scan for r in reps]))
+        box_variant = ms_solve > 0
+        fpp = counts["fp64_flop_per_solved_pair"] if (counts and box_variant and "fp64_flop_per_solved_pair" in counts) else None
+        ngp_pad = int((grid.N[0] + 1 + 3) // 4 * 4) * int(grid.N[1] + 1) * (k1 - k0)      # CG fields carry a row pitch that is a multiple of 4 floats
+        mv_ms, up_ms = float(rep.cg_probe[0]), float(rep.cg_probe[2])
         stages = {
-            "project_hex8": {"bound": "fp64", "ms": d["ms_project"], "achieved": FLOP_PER_PAIR * rep.n_pairs / (d["ms_project"] * 1e-3) / 1e12 if d["ms_project"] > 0 else None,
-                             "peak": fp64.value, "unit": "TFLOP/s"},
-            "cg_stencil81": {"bound": "hbm", "ms": d["ms_cg"], "achieved": B_PER_VOXEL_CG_ITER * ngp_local * rep.cg_iters / (d["ms_cg"] * 1e-3) / 1e9 if d["ms_cg"] > 0 else None,
-                             "peak": hbm, "unit": "GB/s"},
-            "fine_eval": {"bound": "hbm", "ms": d["ms_fine"], "achieved": B_PER_FINE_VOXEL * n_fine_local / (d["ms_fine"] * 1e-3) / 1e9 if d["ms_fine"] > 0 else None,
+            "project_list": {"bound": "fp64", "ms": ms_solve, "achieved": (fpp * solved / (ms_solve * 1e-3) / 1e12) if (fpp and ms_solve > 0) else None, "peak": fp64.value, "unit": "TFLOP/s",
+                             "pairs_solved": solved, "pairs_pruned": int(rep.n_pairs_pruned), "flop_per_solved_pair_measured": fpp,
+                             "survey_estimate_tflops": FLOP_PER_PAIR_SURVEY * rep.n_pairs / (d["ms_project"] * 1e-3) / 1e12 if d["ms_project"] > 0 else None},
+            "pair_scan": {"bound": "latency", "ms": ms_scan},
+            "cg_matvec_tma": {"bound": "hbm", "ms": mv_ms, "achieved": B_PER_VOXEL_MATVEC * ngp_pad / (mv_ms * 1e-3) / 1e9 if mv_ms > 0 else None, "peak": hbm, "unit": "GB/s"},
+            "cg_update": {"bound": "hbm", "ms": up_ms, "achieved": B_PER_VOXEL_UPDATE * ngp_pad / (up_ms * 1e-3) / 1e9 if up_ms > 0 else None, "peak": hbm, "unit": "GB/s"},
+            "cg_total": {"bound": "hbm", "ms": d["ms_cg"], "achieved": B_PER_VOXEL_CG_ITER * ngp_pad * rep.cg_iters / (d["ms_cg"] * 1e-3) / 1e9 if d["ms_cg"] > 0 else None, "peak": hbm, "unit": "GB/s"},
+            "fine_eval": {"bound": "fp32 issue", "ms": d["ms_fine"], "achieved": B_PER_FINE_VOXEL * n_fine_local / (d["ms_fine"] * 1e-3) / 1e9 if d["ms_fine"] > 0 else None,
                           "peak": hbm, "unit": "GB/s", "fp32_tflops": 2 * FMA_PER_FINE_VOXEL * n_fine_local / (d["ms_fine"] * 1e-3) / 1e12 if d["ms_fine"] > 0 else None,
                           "fp32_peak": fp32.value},
-            "sign": {"bound": "hbm", "ms": d["ms_sign"], "achieved": B_PER_VOXEL_SIGN * ngp_local / (d["ms_sign"] * 1e-3) / 1e9 if d["ms_sign"] > 0 else None, "peak": hbm, "unit": "GB/s"},
+            "sign": {"bound": "hbm", "ms": d["ms_sign"], "achieved": 2 * B_PER_VOXEL_SIGN * ngp_local / (d["ms_sign"] * 1e-3) / 1e9 if d["ms_sign"] > 0 else None, "peak": hbm, "unit": "GB/s"},
             "cc": {"bound": "hbm", "ms": d["ms_cc"], "achieved": B_PER_VOXEL_CC * ngp_local / (d["ms_cc"] * 1e-3) / 1e9 if d["ms_cc"] > 0 else None, "peak": hbm, "unit": "GB/s"},
         }
-        for s in stages.values():
-            s["frac"] = (s["achieved"] / s["peak"]) if s["achieved"] and s["peak"] else None
-        dom = stages["project_hex8"]
-        # DRAM bytes per launch from the committed ncu --set full capture -- only quoted when it was taken on the kernel variant that
-        # ran here (the capture of round 1 is the general trilinear variant; the HexBox variant has none yet)
-        traffic, traffic_note = None, None
-        try:
-            box_variant = rep_box_elements(mesh) > 0 and os.environ.get("R2S_PROJ_BOX", "1") != "0"
-        except Exception as exc:                                   # a statistic only: never let it take the bench line down
-            box_variant, traffic_note = False, "box-element count unavailable: %s" % exc
-        tp = os.path.join(ROOT, "profiles", "project_hex8_traffic.json")
-        if os.path.exists(tp):
-            try:
-                prof = json.load(open(tp))
-                if prof.get("variant", "general") == ("box" if box_variant else "general"):
-                    traffic = prof.get("dram_bytes_per_launch")
-                else:
-                    traffic_note = "no ncu --set full capture of the %s variant yet (profiles/project_hex8_traffic.json is the %s one: %.3g B per launch)" % (
-                        "HexBox" if box_variant else "general", prof.get("variant", "general"), prof.get("dram_bytes_per_launch", float("nan")))
-            except Exception:
-                traffic = None
+        for s_ in stages.values():
+            s_["frac"] = (s_["achieved"] / s_["peak"]) if s_.get("achieved") and s_.get("peak") else None
+        dom = stages["project_list"]
+        traffic = counts["dram_bytes_per_step"] if (counts and box_variant) else None
+        traffic_note = ("measured DRAM bytes of the two k_project_list launches of one step (ncu --set full, %s); algorithmic: 8 B list entry + 16 B atomicMin per solved pair + 208 B record per "
+                        "crossing element = %.2f GB" % (counts.get("source", "?"), (24.0 * solved + 208.0 * rep.n_crossing) / 1e9)) if traffic else "no ncu capture of the kernel that ran (profiles/project_list_counts.json missing)"
         line = {
             "metric": METRIC, "value": nfine / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -401,12 +407,14 @@ def run_gpu(args):
             "e2e": {"value": nfine / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(rho_n.nbytes) * world,
                     "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4), "api": "r2s_pipeline_slab (pinned host buffers)"},
             "gpu_launches": int(sum(r.launches for r in reps)),
-            "roofline": {"kernel": "k_project_hex8", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
-                         "variant": "HexBox (axis-aligned box elements)" if box_variant else "general trilinear",
-                         "peak_source": "FP64 FMA chain micro-kernel measured in this run (r2s_measure_fma_peak); HBM peak %s" % hbm_src,
-                         "algorithmic": "%.0f FP64 flop per (element, point) pair x %d pairs per launch" % (FLOP_PER_PAIR, rep.n_pairs)},
+            "roofline": {"kernel": "k_project_list (two launches per step: pairs inside the element box, then the pruned rest)", "bound": "fp64", "achieved": dom["achieved"], "peak": dom["peak"],
+                         "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
+                         "peak_source": "FP64 FMA chain micro-kernel measured in this run (r2s_measure_fma_peak; MEASURED_PEAKS.json has no FP64 figure); HBM peak %s" % hbm_src,
+                         "algorithmic": "%s executed FP64 flop per solved pair (ncu: dfma x 2 + dadd + dmul, profiles/project_list_counts.json) x %d pairs solved of %d candidates (%d pruned by their lower bound) / %.2f ms of k_project_list (CUDA events around the two launches)"
+                                        % ("%.0f" % fpp if fpp else "n/a", solved, rep.n_pairs, rep.n_pairs_pruned, ms_solve),
+                         "ncu": {"lanes_per_warp_instruction": [round(l["lanes_per_warp_inst"], 2) for l in counts["launches"]], "fp64_pipe_pct": [round(l["fp64_pipe_pct"], 1) for l in counts["launches"]]} if counts else None},
             "stages_ms": d, "kernels": stages, "cg_iteration_ms": dict(zip(("matvec", "exchange1", "update", "exchange2"), [round(float(v), 4) for v in rep.cg_probe])),
-            "report": {"pairs": int(rep.n_pairs), "newton_iters": int(rep.n_newton_iters), "not_converged": int(rep.n_not_converged), "cg_iters": int(rep.cg_iters),
+            "report": {"pairs": int(rep.n_pairs), "pairs_pruned": int(rep.n_pairs_pruned), "ms_solve": ms_solve, "ms_scan": ms_scan, "newton_iters": int(rep.n_newton_iters), "not_converged": int(rep.n_not_converged), "cg_iters": int(rep.cg_iters),
                        "bisections": int(rep.bisections), "flipped": int(rep.n_flipped), "th": float(rep.th), "volume": float(rep.volume),
                        "target_volume": float(p.target_volume), "solid": int(rep.n_solid), "crossing": int(rep.n_crossing)},
             "clocks": clocks,

@@ -50,6 +50,7 @@ typedef struct r2s_report {
   int64_t collectives;          /* NCCL collectives / grouped halo exchanges issued by the last call       */
   float cg_probe[4];            /* one CG iteration split: mat-vec, exchange 1 (dot + halo), update, exchange 2 (ms) */
   int64_t n_pairs_pruned;       /* (element, point) pairs never projected: their lower bound was not below the point's minimum */
+  float ms_solve, ms_scan;      /* pair-list projection: the two k_project_list launches / record building + the two k_pair_scan launches (ms) */
 } r2s_report;
 
 /* ---- context -------------------------------------------------------------------------------------------- */

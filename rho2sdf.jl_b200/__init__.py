@@ -54,7 +54,7 @@ class Report(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_solid", "n_crossing", "n_active", "n_pairs", "n_not_converged", "n_newton_iters", "n_flipped")] + \
                [("cg_iters", C.c_int32), ("bisections", C.c_int32), ("th", C.c_float), ("volume", C.c_float)] + \
                [(n, C.c_float) for n in ("ms_bin", "ms_project", "ms_assemble", "ms_sign", "ms_cc", "ms_rbf_prep", "ms_cg", "ms_lsf",
-                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64), ("collectives", C.c_int64), ("cg_probe", C.c_float * 4), ("n_pairs_pruned", C.c_int64)]
+                                         "ms_threshold", "ms_fine", "ms_volume", "ms_total")] + [("launches", C.c_int64), ("collectives", C.c_int64), ("cg_probe", C.c_float * 4), ("n_pairs_pruned", C.c_int64), ("ms_solve", C.c_float), ("ms_scan", C.c_float)]
 
     def asdict(self):
         return {n: (list(getattr(self, n)) if n == "cg_probe" else getattr(self, n)) for n, _ in self._fields_}

@@ -21,7 +21,7 @@ int r2s_create(r2s_ctx **out, int device, void *stream) {
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; } ctx->own_stream = true; }
   for (int i = 0; i < 16; i++) cudaEventCreate(&ctx->ev[i]);
-  for (int i = 0; i < 5; i++) cudaEventCreate(&ctx->ev_probe[i]);
+  for (int i = 0; i < 5; i++) { cudaEventCreate(&ctx->ev_probe[i]); cudaEventCreate(&ctx->ev_k[i]); }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 64; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
@@ -44,7 +44,7 @@ void r2s_destroy(r2s_ctx *ctx) {
                    &ctx->f_scal, &ctx->cutlist, &ctx->slablist, &ctx->v_part, &ctx->vlist[0], &ctx->vlist[1], &ctx->vent[0], &ctx->vent[1], &ctx->vrec, &ctx->lat_xs, &ctx->lat_cell, &ctx->lat_map, &ctx->lat_info, &ctx->lat_pt};
   for (DevBuf *b : all) b->release();
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev_probe[i]);
+  for (int i = 0; i < 5; i++) { cudaEventDestroy(ctx->ev_probe[i]); cudaEventDestroy(ctx->ev_k[i]); }
   for (int i = 0; i < 64; i++) cudaEventDestroy(ctx->ev_copy[i]);
   for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_done[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -83,7 +83,7 @@ struct r2s_ctx {
   std::string err;
   r2s_report rep;
   i64 launches = 0;
-  cudaEvent_t ev[16]; cudaEvent_t ev_probe[5];
+  cudaEvent_t ev[16]; cudaEvent_t ev_probe[5]; cudaEvent_t ev_k[5];      // ev_k: per-kernel timing of the pair-list projection (report: ms_solve / ms_scan)
   // overlap of the result download with compute (r2s_pipeline_slab): copies run on copy_stream behind events of the main stream
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[64]; int n_ev_copy = 0;
   double *async_sdf_host = nullptr; float *async_fine_host = nullptr;

@@ -809,6 +809,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(cudaEventRecord(ctx->ev[1], st));
   // Without xp, dist[] starts at BIG and receives the minima of the face-free tiles by atomicMin; k_assemble then replays only the tiles
   // with boundary-face elements.  With xp everything goes through the pair buffer (the closest point of a voxel is tie-order dependent).
+  bool timed_list = false;
   if (!want_xp) {
     i64 v0 = (i64)kz0 * g.np[0] * g.np[1], nv = (i64)(kz1 - kz0) * g.np[0] * g.np[1];
     k_fill_f64<<<cdiv(nv, 256), 256, 0, st>>>(nv, ctx->dist.as<double>() + v0, R2S_BIG); LAUNCH_CHECK();
@@ -831,14 +832,20 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
         CK(ctx->plist.reserve(sizeof(u64) * (size_t)(npairs + 1)));
         u64 *pc = ctx->counters.as<u64>() + NCTR;      // 4 words behind the statistics slots: [0],[1] pass A, [2],[3] pass B
         BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
+        CK(cudaEventRecord(ctx->ev_k[0], st));
         k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box); LAUNCH_CHECK();
         const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * 5 * 4;
         k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc, ctx->counters.as<u64>()); LAUNCH_CHECK();
+        CK(cudaEventRecord(ctx->ev_k[1], st));
         k_project_list<<<pgrid, 128, 0, st>>>(pl, pc, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
+        CK(cudaEventRecord(ctx->ev_k[2], st));
         if (prune) {
           k_pair_scan<1><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc + 2, ctx->counters.as<u64>()); LAUNCH_CHECK();
+          CK(cudaEventRecord(ctx->ev_k[3], st));
           k_project_list<<<pgrid, 128, 0, st>>>(pl, pc + 2, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
-        }
+        } else CK(cudaEventRecord(ctx->ev_k[3], st));
+        CK(cudaEventRecord(ctx->ev_k[4], st));
+        timed_list = true;
       }
     } else {
       if (want_xp) k_project_tet4<true><<<nb, 128, 0, st>>>(nitems, nact, ctx->act_rec.as<ActRec>(), choff, ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), ctx->counters.as<u64>());
@@ -867,6 +874,12 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
   ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
   ctx->rep.n_pairs_pruned = (i64)hc[4];
+  ctx->rep.ms_solve = ctx->rep.ms_scan = 0.0f;
+  if (timed_list) {      // the read-back above synchronised the stream: the events are complete
+    float t[4];
+    for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&t[q], ctx->ev_k[q], ctx->ev_k[q + 1]));
+    ctx->rep.ms_scan = t[0] + t[2]; ctx->rep.ms_solve = t[1] + t[3];
+  }
   CK(cudaEventElapsedTime(&ctx->rep.ms_bin, ctx->ev[0], ctx->ev[1]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_project, ctx->ev[1], ctx->ev[2]));
   CK(cudaEventElapsedTime(&ctx->rep.ms_assemble, ctx->ev[2], ctx->ev[3]));

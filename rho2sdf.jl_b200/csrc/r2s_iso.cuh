@@ -114,16 +114,6 @@ struct HexBox {
     double hg[3];         // off-diagonal terms of Hess g, pairs (0,1),(1,2),(2,0)
   };
 };
-// HexBoxS: the box element in SCALED form for one grid point x (MODE bit 2 of the kernels): with xs_d = (x_d - c_d) / h_d the objective
-// is f = sum h_d^2 (xi_d - xs_d)^2, so c, h and x (9 doubles per lane) are replaced by xs (3): 11 element constants + 3 per point
-// instead of 17 + 3.  Fewer live registers for a kernel whose speed is set by occupancy; the evaluation avoids the cancellation of
-// large coordinates in X(xi) - x.  Same mathematics as HexBox, rounding differs in the last bits.
-struct HexBoxS {
-  double R[8];
-  double hh[3];           // 2 h_d^2
-  double xs[3];           // local coordinates of the grid point (may lie outside [-1,1])
-  typedef HexBox::EvalT EvalT;
-};
 // true when the geometry coefficients A[0..2] describe a box in canonical orientation
 __device__ __forceinline__ bool is_box(const double A[4][8]) {
   bool ok = true;
@@ -178,30 +168,10 @@ __device__ __forceinline__ void eval_full(const HexBox &B, const double x[3], do
   E_.hg[0] = fma(B.R[7], xi[2], B.R[4]); E_.hg[1] = fma(B.R[7], xi[0], B.R[5]); E_.hg[2] = fma(B.R[7], xi[1], B.R[6]);
 }
 __device__ __forceinline__ double hdiag(const HexBox::EvalT &E, int i) { return E.hh[i]; }
-// HexBoxS overloads (x is carried by the element as xs; the x argument is ignored)
-__device__ __forceinline__ void make_box_scaled(const double A[4][8], const double x[3], HexBoxS &B) {
-#pragma unroll
-  for (int k = 0; k < 8; k++) B.R[k] = A[3][k];
-#pragma unroll
-  for (int d = 0; d < 3; d++) { B.hh[d] = 2.0 * (A[d][d + 1] * A[d][d + 1]); B.xs[d] = (x[d] - A[d][0]) / A[d][d + 1]; }
-}
-__device__ __forceinline__ void eval_g(const HexBoxS &B, double rho_t, const double xi[3], double &g, double a[3]) { eval_g_R(B.R, rho_t, xi, g, a); }
-__device__ __forceinline__ double eval_f(const HexBoxS &B, const double *, const double xi[3]) {
-  ISO_COUNT(2);
-  const double F0 = xi[0] - B.xs[0], F1 = xi[1] - B.xs[1], F2 = xi[2] - B.xs[2];
-  return 0.5 * fma(B.hh[2] * F2, F2, fma(B.hh[1] * F1, F1, (B.hh[0] * F0) * F0));
-}
-__device__ __forceinline__ void eval_full(const HexBoxS &B, const double *, double rho_t, const double xi[3], HexBox::EvalT &E_) {
-  ISO_COUNT(0); ISO_TRACE(3);
-#pragma unroll
-  for (int d = 0; d < 3; d++) { E_.F[d] = xi[d] - B.xs[d]; E_.c[d] = B.hh[d] * E_.F[d]; E_.hh[d] = B.hh[d]; }
-  E_.f = 0.5 * fma(E_.c[2], E_.F[2], fma(E_.c[1], E_.F[1], E_.c[0] * E_.F[0]));
-  eval_g_R(B.R, rho_t, xi, E_.g, E_.a);
-  E_.hg[0] = fma(B.R[7], xi[2], B.R[4]); E_.hg[1] = fma(B.R[7], xi[0], B.R[5]); E_.hg[2] = fma(B.R[7], xi[1], B.R[6]);
-}
-__device__ __forceinline__ const double *rho_coeffs(const HexBoxS &B) { return B.R; }
-
-// FAST variant of the solver (template flag, off by default): restore() leaves without the confirming evaluation once the step
+// Solver variants (template parameter MODE).  The kernels run MODE 3 = FAST restoration + one tangent-step code path; MODE 0 (every
+// step confirmed by an evaluation, one template instance per tangent-step case) and MODE 1 (FAST only) are instantiated by the host
+// build (tests/host/iso_host.cpp), where MODE 3 is checked against them and against the oracle pair by pair.
+// FAST: restore() leaves without the confirming evaluation once the step
 // just taken is so short that the remainder of the trilinear field is below tolg:
 //   g(xi + D) - g(xi) - a.D = R4 D0 D1 + R5 D1 D2 + R6 D2 D0 + R7 (xi0 D1 D2 + xi1 D2 D0 + xi2 D0 D1 + D0 D1 D2),
 // so |g_new| <= (|R4| + |R5| + |R6| + 4 |R7|) |D|^2 for |xi|, |D| <= 1 when D is the full Newton step (no variable clamped).

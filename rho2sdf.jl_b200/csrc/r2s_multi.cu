@@ -145,6 +145,7 @@ int r2s_multi_pipeline(r2s_multi *m, const r2s_params *p, const double *rho_n, d
       a.n_newton_iters += b.n_newton_iters; a.n_pairs_pruned += b.n_pairs_pruned; a.launches += b.launches; a.collectives += b.collectives;
       float *fa = &a.ms_bin; const float *fb = &b.ms_bin;
       for (int q = 0; q < 12; q++) fa[q] = std::max(fa[q], fb[q]);      // ms_bin .. ms_total are contiguous floats
+      a.ms_solve = std::max(a.ms_solve, b.ms_solve); a.ms_scan = std::max(a.ms_scan, b.ms_scan);
     }
     *rep = a;
   }

@@ -25,8 +25,8 @@ mutable struct R2SReport
   cg_iters::Int32; bisections::Int32; th::Cfloat; volume::Cfloat
   ms_bin::Cfloat; ms_project::Cfloat; ms_assemble::Cfloat; ms_sign::Cfloat; ms_cc::Cfloat; ms_rbf_prep::Cfloat; ms_cg::Cfloat; ms_lsf::Cfloat
   ms_threshold::Cfloat; ms_fine::Cfloat; ms_volume::Cfloat; ms_total::Cfloat
-  launches::Int64; collectives::Int64; cg_probe::NTuple{4,Cfloat}; n_pairs_pruned::Int64
-  R2SReport() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0, (0f0, 0f0, 0f0, 0f0), 0)
+  launches::Int64; collectives::Int64; cg_probe::NTuple{4,Cfloat}; n_pairs_pruned::Int64; ms_solve::Cfloat; ms_scan::Cfloat
+  R2SReport() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0, (0f0, 0f0, 0f0, 0f0), 0, 0f0, 0f0)
 end
 
 mutable struct Context

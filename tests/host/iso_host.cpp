@@ -64,15 +64,14 @@ int iso_host_is_box(const double *Xe, const double *re) { double A[4][8]; coeffi
 // batch over n points of ONE element; its[n] receives the phase-2 iteration count (the quantity a warp waits on).
 // variant 0: general trilinear, 1: HexBox, 2: HexBox FAST, 3: HexBox FAST with phase 1 computed once for the element (the table
 // path of the kernels), 4: general trilinear with phase 1 once per element, 5: as 3 with the single-path tangent step (MODE 3),
-// 6: scaled box form HexBoxS with MODE 3 and element phase 1 (what MODE 7 of the kernels runs), 7: HexBoxS with the exact solver,
 // 8: general trilinear with MODE 3 and element phase 1
 int iso_host_project_many(const double *Xe, const double *re, long n, const double *x, double rho_t, int variant, double *dist, int *its) {
   double A[4][8]; coefficients(Xe, re, A);
   const double gs = gscale(re, rho_t);
   iso::HexTri T{(const double(*)[8])A}; iso::HexBox B;
-  if ((variant >= 1 && variant <= 3) || (variant >= 5 && variant <= 7)) { if (!iso::is_box(A)) return -2; iso::make_box(A, B); }
+  if ((variant >= 1 && variant <= 3) || variant == 5) { if (!iso::is_box(A)) return -2; iso::make_box(A, B); }
   iso::ProjState S0; bool ok0 = false;
-  if (variant == 3 || variant == 5 || variant == 6) ok0 = iso::proj_init_element<iso::HexBox, 1>(B, rho_t, gs, S0);
+  if (variant == 3 || variant == 5) ok0 = iso::proj_init_element<iso::HexBox, 1>(B, rho_t, gs, S0);
   if (variant == 4) ok0 = iso::proj_init_element<iso::HexTri, 0>(T, rho_t, gs, S0);
   if (variant == 8) ok0 = iso::proj_init_element<iso::HexTri, 1>(T, rho_t, gs, S0);
   int bad = 0;
@@ -84,13 +83,6 @@ int iso_host_project_many(const double *Xe, const double *re, long n, const doub
     else if (variant == 2) { ok = iso::project_hex8<iso::HexBox, 1>(B, re, sg, edges, xq, rho_t, gs, xi, nit); iso::eval_pos(B, xi, p); }
     else if (variant == 3) { ok = iso::project_hex8_from<iso::HexBox, 1>(B, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(B, xi, p); }
     else if (variant == 5) { ok = iso::project_hex8_from<iso::HexBox, 3>(B, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(B, xi, p); }
-    else if (variant == 6 || variant == 7) {
-      iso::HexBoxS Bs; iso::make_box_scaled((const double(*)[8])A, xq, Bs);
-      if (variant == 6) ok = iso::project_hex8_from<iso::HexBoxS, 3>(Bs, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit);
-      else ok = iso::project_hex8<iso::HexBoxS, 0>(Bs, re, sg, edges, xq, rho_t, gs, xi, nit);
-      dist[q] = sqrt(iso::eval_f(Bs, xq, xi)); its[q] = nit; bad += ok ? 0 : 1; ISO_TRACE(0);
-      continue;
-    }
     else if (variant == 8) { ok = iso::project_hex8_from<iso::HexTri, 3>(T, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(T, xi, p); }
     else { ok = iso::project_hex8_from<iso::HexTri, 0>(T, re, sg, edges, xq, rho_t, gs, S0.xi, ok0, xi, nit); iso::eval_pos(T, xi, p); }
     const double d0 = xq[0] - p[0], d1 = xq[1] - p[1], d2 = xq[2] - p[2];
