@@ -122,7 +122,7 @@ struct r2s_ctx {
   // connected components
   DevBuf cc_label, cc_size, cc_scal, cc_bits, cc_bits_all, cc_gsz, cc_seen;
   // smoothing
-  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2], vent[2], vrec;
+  DevBuf f_s, f_w, f_r, f_u, f_c, f_lsf, f_fine, f_part, f_scal, cutlist, slablist, vlist[2], vent[2], vrec, bis_state;
   int smooth_last = 1;
   bool have_sdf = false, have_fine = false;      // ctx->sdf / ctx->f_fine hold a result of the CURRENT grid (cleared by r2s_set_grid / r2s_set_mesh)
 

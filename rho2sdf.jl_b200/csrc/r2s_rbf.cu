@@ -552,10 +552,41 @@ __global__ void __launch_bounds__(256) k_vol_rows(int nx, int ny, int px, int kc
 // bracket halves, almost every cell freezes: the 40 bisections cost about a dozen full quadratures instead of 40.  The total is an
 // exact integer sum, so the result is bit-identical to re-evaluating every cut cell at every step (R2S_VOL_CACHE=0 does that).
 struct VRec { float c[8]; float part, th_e, margin; int pad; };
+// State of the bisection on the DEVICE (steps >= 4): the bracket update is a one-thread kernel, so the host enqueues all remaining steps
+// without waiting for any of them and reads the result once.  A step whose threshold repeats the previous one (lo and hi adjacent floats)
+// and every step after the stopping rule has fired are skipped by all kernels of the step (skip / skipf).
+struct BisState {
+  float lo, hi, th, th_prev; int nb, have_prev, done, skip; float skipf; int cur; double v, eps, target; float ev, jac; unsigned long long n_eval;
+};
+__global__ void k_bis_begin(BisState *S, u64 *acc) {
+  if (S->done) { S->skip = 1; S->skipf = 1.0f; return; }
+  const float th = (S->lo + S->hi) / 2;
+  S->th = th;
+  const int skip = (S->have_prev && th == S->th_prev) ? 1 : 0;      // the volume of an identical threshold is not recomputed
+  S->skip = skip; S->skipf = skip ? 1.0f : 0.0f;
+  if (!skip) { acc[0] = 0; acc[1] = 0; acc[2] = 0; acc[4 + (1 - S->cur)] = 0; }
+}
+__global__ void k_bis_end(BisState *S, const u64 *acc, const u64 *red) {      // LS_Threshold's loop body after the volume (RBFs4Smoothing.jl:286-296)
+  if (S->done) return;
+  if (!S->skip) {
+    S->v = (double)red[0] * (double)S->ev + ((double)red[2] / 137438953472.0 /* 2^37 */) * (double)S->jac;
+    S->cur = 1 - S->cur; S->n_eval += acc[1];
+  }
+  const float cur = (float)S->v;
+  S->eps = fabs(S->target - (double)cur);
+  if ((double)cur > S->target) S->lo = S->th; else S->hi = S->th;
+  S->nb++; S->have_prev = 1; S->th_prev = S->th;
+  if (!(S->nb < 40 && S->eps > 1.0e-4)) S->done = 1;
+}
 // one thread per active cell: retire / keep (compaction into `out`), classify at th from (mn, mx), use the cached quadrature of the cell's
 // record or queue the cell for k_vl_eval.  acc[6] = records handed out so far.
-__global__ void __launch_bounds__(256) k_vl_step(const VAct *__restrict__ in, const u64 *__restrict__ n_in_ptr, VAct *__restrict__ out, u64 *__restrict__ n_out_ptr, i64 out_cap, float lo,
-                                                 float hi, float th, int use_cache, u64 *__restrict__ acc, const VRec *__restrict__ recs, int2 *__restrict__ evlist, i64 ev_cap) {
+__global__ void __launch_bounds__(256) k_vl_step(const BisState *__restrict__ S, VAct *l0, VAct *l1, i64 out_cap, int use_cache, u64 *__restrict__ acc, const VRec *__restrict__ recs,
+                                                 int2 *__restrict__ evlist, i64 ev_cap) {
+  if (S->skip) return;
+  const int icur = S->cur;
+  const VAct *__restrict__ in = icur ? l1 : l0; VAct *__restrict__ out = icur ? l0 : l1;
+  const u64 *n_in_ptr = acc + 4 + icur; u64 *n_out_ptr = acc + 4 + (1 - icur);
+  const float lo = S->lo, hi = S->hi, th = S->th;
   __shared__ VAct s_keep[8][WS_CAP];
   __shared__ int2 s_ev[8][WS_CAP];
   const i64 n_in = (i64)*n_in_ptr;
@@ -598,8 +629,10 @@ __global__ void __launch_bounds__(256) k_vl_step(const VAct *__restrict__ in, co
 }
 // quadrature of the queued cells at th (same point values, same order of the Float32 sum as k_vol_cut) + their new cache entries; a cell
 // that is cut for the first time gathers its corner values into its record
-__global__ void __launch_bounds__(128) k_vl_eval(VRec *__restrict__ recs, const int2 *__restrict__ evlist, int nx, int ny, int px, const float *__restrict__ sdf, float th, GaussF G,
-                                                 u64 *__restrict__ acc) {
+__global__ void __launch_bounds__(128) k_vl_eval(const BisState *__restrict__ S, VRec *__restrict__ recs, const int2 *__restrict__ evlist, int nx, int ny, int px, const float *__restrict__ sdf,
+                                                 GaussF G, u64 *__restrict__ acc) {
+  if (S->skip) return;
+  const float th = S->th;
   const int nev = (int)acc[1];
   const int lane = threadIdx.x & 31, nthr = gridDim.x * blockDim.x;
   u64 local = 0;
@@ -653,7 +686,8 @@ __global__ void __launch_bounds__(128) k_vl_eval(VRec *__restrict__ recs, const 
   if (lane == 0 && local) atomicAdd(&acc[2], local);
 }
 // acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
-__global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red) {
+__global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red, const BisState *S) {
+  if (S && S->skip) return;
   red[0] = acc[0] + acc[3]; red[1] = acc[1] > (u64)cutcap ? 1 : 0; red[2] = acc[2]; red[3] = 0;
 }
 // state of one LS_Threshold search (see k_vol_step)
@@ -676,26 +710,6 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
   static const GaussF G9 = gauss9f();
   const i64 n_all = (i64)(vb.nx - 1) * (vb.ny - 1) * (i64)(vb.kc1 - vb.kc0);
   vb.step++;
-  if (vb.step >= 4) {      // active-list steps: 16-byte entries, records with cached quadratures for the cells that get cut (see k_vl_step)
-    const int in = vb.cur, out = 1 - vb.cur;
-    CK(ctx->vent[out].reserve(sizeof(VAct) * (size_t)(vb.n_cur + 1)));
-    CK(ctx->vlist[1].reserve(sizeof(int2) * (size_t)(vb.n_cur + 1)));      // queue of cells to evaluate
-    u64 *nin = vb.acc + 4 + in, *nout = vb.acc + 4 + out;
-    CK(cudaMemsetAsync(vb.acc, 0, sizeof(u64) * 3, st));
-    CK(cudaMemsetAsync(nout, 0, sizeof(u64), st));
-    const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 8);
-    k_vl_step<<<grid, 256, 0, st>>>(ctx->vent[in].as<VAct>(), nin, ctx->vent[out].as<VAct>(), nout, vb.n_cur + 1, lo, hi, th, ctx->knobs.vol_cache, vb.acc, ctx->vrec.as<VRec>(),
-                                    ctx->vlist[1].as<int2>(), vb.n_cur + 1); LAUNCH_CHECK();
-    k_vl_eval<<<148 * 16, 128, 0, st>>>(ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.nx, vb.ny, vb.px, vb.sdf, th, G9, vb.acc); LAUNCH_CHECK();
-    u64 *red = vb.acc + 8, hall[12];
-    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, 0x7fffffff, red); LAUNCH_CHECK();
-    if (r2s_allreduce(ctx, red, 4, 1)) return 1;
-    if (r2s_readback(ctx, hall, vb.acc, sizeof(hall))) return 1;
-    vb.cur = out; vb.n_cur = (i64)hall[4 + out]; vb.n_eval += (i64)hall[1];
-    const float ev = vb.edge * vb.edge * vb.edge, jac = ev / 8.0f;
-    *vol = (double)hall[8] * (double)ev + ((double)hall[10] / 137438953472.0 /* 2^37 */) * (double)jac;
-    return 0;
-  }
   const bool emit = vb.step == 3;      // steps 1-3 classify the whole grid (k_vol_rows); step 3 also emits the active list (into list 0)
   if (emit) CK(ctx->vent[0].reserve(sizeof(VAct) * (size_t)(n_all + 1)));
   u64 h[6];
@@ -713,7 +727,7 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
     k_vol_cut<<<148 * 16, 128, 0, st>>>(vb.nx, vb.ny, vb.px, vb.sdf, th, 0.0f, ctx->cutlist.as<int>(), cutcap, G9, vb.acc); LAUNCH_CHECK();
     // cross-rank sum of (full cells, overflow flag, cut sum); integers, so the total does not depend on the slab count
     u64 *red = vb.acc + 8, hr[4];
-    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, cutcap, red); LAUNCH_CHECK();
+    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, cutcap, red, nullptr); LAUNCH_CHECK();
     if (r2s_allreduce(ctx, red, 4, 1)) return 1;
     {      // acc[0..5] and red[0..3] are contiguous (red = acc + 8): one read-back of 12 words
       u64 hall[12];
@@ -735,6 +749,35 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
     return 0;
   }
   FAIL("LS_Threshold: cut-cell list overflow");
+}
+// Steps 4 .. 40 on the device: 16-byte active entries, records with cached quadratures for the cells that get cut (k_vl_step / k_vl_eval), the
+// bracket update in k_bis_end.  Everything is enqueued at once; the host reads the final state back.  h = state after step 3.
+static int vol_bisect_finish(r2s_ctx *ctx, VolBisect &vb, float &lo, float &hi, float &th, double &v, double &eps, int &nb, float th_prev, double target) {
+  cudaStream_t st = ctx->stream;
+  static const GaussF G9 = gauss9f();
+  CK(ctx->vent[1].reserve(sizeof(VAct) * (size_t)(vb.n_cur + 1)));
+  CK(ctx->vlist[1].reserve(sizeof(int2) * (size_t)(vb.n_cur + 1)));      // queue of cells to evaluate
+  CK(ctx->bis_state.reserve(256));
+  BisState h; memset(&h, 0, sizeof(h));
+  h.lo = lo; h.hi = hi; h.th = th; h.th_prev = th_prev; h.nb = nb; h.have_prev = 1; h.done = 0; h.cur = 0; h.v = v; h.eps = eps; h.target = target;
+  h.ev = vb.edge * vb.edge * vb.edge; h.jac = h.ev / 8.0f;
+  BisState *S = ctx->bis_state.as<BisState>();
+  CK(cudaMemcpyAsync(S, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 8);
+  u64 *red = vb.acc + 8;
+  ctx->skip_flag = &S->skipf;      // the peer-memory all-reduce of a skipped step skips itself (same flag value on every rank)
+  for (int step = nb; step < 40; step++) {
+    k_bis_begin<<<1, 1, 0, st>>>(S, vb.acc); LAUNCH_CHECK();
+    k_vl_step<<<grid, 256, 0, st>>>(S, ctx->vent[0].as<VAct>(), ctx->vent[1].as<VAct>(), vb.n_cur + 1, ctx->knobs.vol_cache, vb.acc, ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.n_cur + 1); LAUNCH_CHECK();
+    k_vl_eval<<<148 * 16, 128, 0, st>>>(S, ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.nx, vb.ny, vb.px, vb.sdf, G9, vb.acc); LAUNCH_CHECK();
+    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, 0x7fffffff, red, S); LAUNCH_CHECK();
+    if (r2s_allreduce(ctx, red, 4, 1)) { ctx->skip_flag = nullptr; return 1; }
+    k_bis_end<<<1, 1, 0, st>>>(S, vb.acc, red); LAUNCH_CHECK();
+  }
+  ctx->skip_flag = nullptr;
+  if (r2s_readback(ctx, &h, S, sizeof(h))) return 1;
+  lo = h.lo; hi = h.hi; th = h.th; v = h.v; eps = h.eps; nb = h.nb; vb.n_eval += (i64)h.n_eval;
+  return 0;
 }
 int r2s_dev_volume_from_sdf(r2s_ctx *ctx, const float *sdf_dev, i64 nx, i64 ny, i64 nz, float edge, float iso, int order, double *vol) {
   if (order < 1 || order > 32) FAIL("calculate_volume_from_sdf: detailed_quad_order must be between 1 and 32");
@@ -1064,6 +1107,8 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
     eps = fabs(target - (double)cur);
     if ((double)cur > target) lo = th; else hi = th;
     nb++;
+    // three whole-grid steps driven from the host (they size the lists); the rest of the search runs on the device without host round trips
+    if (vb.step == 3 && nb < 40 && eps > 1.0e-4) { if (vol_bisect_finish(ctx, vb, lo, hi, th, v, eps, nb, th_prev, target)) return 1; break; }
   }
   ctx->rep.bisections = nb;
   float tho = -th;
