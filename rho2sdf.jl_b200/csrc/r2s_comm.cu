@@ -258,17 +258,11 @@ int r2s_halo_exchange_f32(r2s_ctx *ctx, float *a, i64 plane_elems, int k0, int k
 // (system scope) and stores s; then thread p spins on the local slot[s&1][p] until it carries s; thread 0 combines the R
 // contributions IN RANK ORDER (deterministic, identical on every rank).  Two parities make it safe for a fast rank to start
 // call s+1 while a slow one still combines call s (call s+2 cannot start before everybody finished call s).  The CG halo
-// planes of c are written straight into the neighbours' c arrays (also IPC-mapped) followed by a flag; the consumer waits for
-// both neighbours' flags in a one-warp kernel before its update kernel starts.  Spins are bounded: a timeout raises an error
+// planes of c are written straight into the neighbours' c arrays (also IPC-mapped) BY THE MAT-VEC KERNEL ITSELF, whose last CTA also
+// all-reduces the dot product through the mailbox and raises the halo flags; the update kernel waits for both neighbours' flags in
+// its prologue (r2s_p2p.cuh, r2s_rbf.cu: fused compute + exchange, no separate communication launch inside a CG iteration).  Spins are bounded: a timeout raises an error
 // flag instead of hanging the GPU.  R2S_P2P=0 falls back to NCCL for everything.
-#define P2P_SLOT_WORDS 8
-#define P2P_MAX_SPIN (1u << 26)      // bounded waits (tens of seconds): a dead peer raises the error flag instead of hanging the GPU
-struct P2PBox {
-  unsigned long long slot[2][64][P2P_SLOT_WORDS];
-  unsigned long long halo_flag[2][2];      // [parity][0 = from lower neighbour, 1 = from upper neighbour]
-  unsigned long long error;
-  unsigned long long halo_count[2];        // CTA completion counters of the put kernel
-};
+#include "r2s_p2p.cuh"
 __global__ void k_p2p_allreduce(P2PBox *mine, P2PBox *const *peers, int rank, int R, unsigned seq, unsigned long long *vals, int n, int kind, const float *skip) {
   if (skip && *skip != 0.0f) return;      // every rank sees the same flag (it is computed from all-reduced values): all skip or none
   const int p = threadIdx.x, par = seq & 1;
@@ -472,57 +466,21 @@ int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes) {
   (void)bytes;
   return 0;
 }
-// copies [n floats at src_off] of my array into the same offsets of the neighbour's array, then the last CTA raises the flag
-__global__ void __launch_bounds__(256) k_p2p_halo_put(const float *__restrict__ mine, float *lower, float *upper, i64 off_lo, i64 n_lo, i64 off_hi, i64 n_hi,
-                                                      P2PBox *box_lower, P2PBox *box_upper, P2PBox *box_mine, unsigned seq, const float *skip) {
-  if (skip && *skip != 0.0f) return;
-  const i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n_lo + n_hi; i += stride) {
-    if (i < n_lo) { if (lower) lower[off_lo + i] = mine[off_lo + i]; }
-    else if (upper) upper[off_hi + (i - n_lo)] = mine[off_hi + (i - n_lo)];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int par = seq & 1;
-    unsigned long long done = atomicAdd(&box_mine->halo_count[par], 1ull) + 1;
-    if (done == gridDim.x) {      // all CTAs have fenced their stores
-      box_mine->halo_count[par] = 0;
-      __threadfence_system();
-      if (box_lower) ((volatile unsigned long long *)box_lower->halo_flag[par])[1] = seq;      // I am the lower neighbour's UPPER neighbour
-      if (box_upper) ((volatile unsigned long long *)box_upper->halo_flag[par])[0] = seq;
-    }
-  }
-}
-__global__ void k_p2p_halo_wait(P2PBox *mine, int has_lower, int has_upper, unsigned seq, const float *skip) {
-  if (skip && *skip != 0.0f) return;
-  const int par = seq & 1;
-  if (threadIdx.x < 2) {
-    const bool need = threadIdx.x == 0 ? has_lower : has_upper;
-    volatile unsigned long long *f = &mine->halo_flag[par][threadIdx.x];
-    unsigned spin = 0;
-    while (need && *f != (unsigned long long)seq) { if (++spin > P2P_MAX_SPIN) { mine->error = 1; break; } }
-  }
-  __threadfence_system();
-}
-int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, int nz, int H) {
-  const int r = ctx->rank;
-  const unsigned seq = ++ctx->p2p_halo_seq;
-  const bool lo = r > 0, hi = r + 1 < ctx->nranks;
-  const i64 n_lo = lo ? (i64)std::min(H, k1 - k0) * plane_elems : 0, n_hi = hi ? (i64)std::min(H, k1 - k0) * plane_elems : 0;
-  const i64 off_lo = (i64)k0 * plane_elems, off_hi = (i64)(k1 - std::min(H, k1 - k0)) * plane_elems;
-  (void)nz;
-  P2PBox *mine = (P2PBox *)ctx->p2p_box;
-  k_p2p_halo_put<<<148, 256, 0, ctx->stream>>>(c, lo ? (float *)ctx->p2p_c_peer[0] : nullptr, hi ? (float *)ctx->p2p_c_peer[1] : nullptr, off_lo, n_lo, off_hi, n_hi,
-                                               lo ? (P2PBox *)ctx->p2p_peer_box[r - 1] : nullptr, hi ? (P2PBox *)ctx->p2p_peer_box[r + 1] : nullptr, mine, seq, ctx->skip_flag);
-  CK(cudaGetLastError());
-  ctx->p2p_ops++;
-  return 0;
-}
-int r2s_p2p_halo_wait(r2s_ctx *ctx) {
-  const int r = ctx->rank;
-  k_p2p_halo_wait<<<1, 32, 0, ctx->stream>>>((P2PBox *)ctx->p2p_box, r > 0, r + 1 < ctx->nranks, ctx->p2p_halo_seq, ctx->skip_flag);
-  CK(cudaGetLastError());
+// parameters of the fused CG kernels for one iteration (r2s_rbf.cu): consumes two all-reduce sequence numbers and one halo sequence number
+int r2s_p2p_fuse_params(r2s_ctx *ctx, P2PFuse *fs, P2PFuse *fu, i64 plane_elems, int k0, int k1, int H) {
+  P2PFuse f; memset(&f, 0, sizeof(f));
+  if (!ctx->p2p) { *fs = f; *fu = f; return 0; }
+  const int r = ctx->rank; const bool lo = r > 0, hi = r + 1 < ctx->nranks; const int h = std::min(H, k1 - k0);
+  f.enabled = 1; f.rank = r; f.R = ctx->nranks;
+  f.mine = (P2PBox *)ctx->p2p_box; f.peers = (P2PBox *const *)ctx->p2p_peer_box_dev;
+  f.box_lower = lo ? (P2PBox *)ctx->p2p_peer_box[r - 1] : nullptr; f.box_upper = hi ? (P2PBox *)ctx->p2p_peer_box[r + 1] : nullptr;
+  f.c_lower = lo ? (float *)ctx->p2p_c_peer[0] : nullptr; f.c_upper = hi ? (float *)ctx->p2p_c_peer[1] : nullptr;
+  f.lo0 = lo ? (i64)k0 * plane_elems : 0; f.lo1 = lo ? (i64)(k0 + h) * plane_elems : 0;
+  f.hi0 = hi ? (i64)(k1 - h) * plane_elems : 0; f.hi1 = hi ? (i64)k1 * plane_elems : 0;
+  f.seq_halo = ++ctx->p2p_halo_seq;
+  f.seq_ar = ++ctx->p2p_seq; *fs = f;
+  f.seq_ar = ++ctx->p2p_seq; *fu = f;
+  ctx->p2p_ops += 3;
   return 0;
 }
 // error flag of the mailbox (bounded spins): checked by the pipeline after its final synchronisation

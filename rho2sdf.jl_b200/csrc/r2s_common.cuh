@@ -184,8 +184,8 @@ int r2s_mesh_build_lattice(r2s_ctx *ctx);                                  // r2
 int r2s_allreduce(r2s_ctx *ctx, void *buf, size_t count, int kind /*0 f64 sum, 1 u64 sum, 2 u32 max, 3 u32 min, 4 u64 max*/);
 int r2s_p2p_prepare_c(r2s_ctx *ctx, size_t have_bytes, size_t need_bytes);                  // collective; before c may be re-allocated
 int r2s_p2p_map_c(r2s_ctx *ctx, float *c, size_t bytes);                                     // (re)map the neighbours' CG vector c
-int r2s_p2p_halo_put_c(r2s_ctx *ctx, float *c, i64 plane_elems, int k0, int k1, int nz, int H);   // my boundary planes -> neighbours' halos
-int r2s_p2p_halo_wait(r2s_ctx *ctx);
+struct P2PFuse;
+int r2s_p2p_fuse_params(r2s_ctx *ctx, P2PFuse *stencil, P2PFuse *update, i64 plane_elems, int k0, int k1, int H);      // r2s_p2p.cuh
 int r2s_p2p_check(r2s_ctx *ctx);
 int r2s_group_start(r2s_ctx *ctx);
 int r2s_group_end(r2s_ctx *ctx);

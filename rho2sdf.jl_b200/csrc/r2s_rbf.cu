@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include "r2s_common.cuh"
 #include "r2s_tables.cuh"
+#include "r2s_p2p.cuh"
 
 // ------------------------------------------------------------------------------------------------ process_vector (:15-22)
 __global__ void __launch_bounds__(256) k_to_f32(i64 n, i64 v0, int nx, int px, const double *__restrict__ sdf, float *__restrict__ s, unsigned *__restrict__ maxbits) {
@@ -46,16 +47,24 @@ struct StencilW { float w[8]; };
 // The CTA that finishes LAST adds up the per-CTA partial sums (fixed order: 256 strided sums, then slot 0..255 sequentially -- the same
 // order whatever CTA happens to be last, so the result is deterministic) and stores the total: no separate reduction launch.
 // Call with all 256 threads of the CTA after thread 0 has written partial[this CTA].
-__device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks, unsigned *ticket, double *dst) {
+// F.enabled (several GPUs, peer-memory transport): the CTAs have also stored halo values into the neighbours' arrays, so the fence before
+// the ticket is system-wide, and the last CTA all-reduces the total over the ranks through the mailbox itself (p2p_allreduce_cta).
+__device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks, unsigned *ticket, double *dst, const P2PFuse &F) {
   __shared__ bool s_last; __shared__ double s_sum[256];
   const int tid = threadIdx.x;
+  if (F.enabled) { __threadfence_system(); __syncthreads(); }
   if (tid == 0) { __threadfence(); s_last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1u; }
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
   double a = 0; for (int i = tid; i < nblocks; i += 256) a += __ldcg(&partial[i]);
   s_sum[tid] = a; __syncthreads();
-  if (tid == 0) { double t = 0; for (int i = 0; i < 256; i++) t += s_sum[i]; *dst = t; *ticket = 0; __threadfence(); }
+  __shared__ double s_tot;
+  if (tid == 0) { double t = 0; for (int i = 0; i < 256; i++) t += s_sum[i]; s_tot = t; *ticket = 0; }
+  __syncthreads();
+  double t = s_tot;                                          // every thread holds the local total: thread p sends it to rank p
+  if (F.enabled) t = p2p_allreduce_cta(F, F.seq_ar, t);
+  if (tid == 0) { *dst = t; __threadfence(); }
   __syncthreads();
   return true;
 }
@@ -101,7 +110,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 template <bool BETA>
 __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nx, int ny, int nz, int px,
                                                        int kz0, int kz1, int zc, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
-                                                       double *__restrict__ partial, StencilW W, unsigned *__restrict__ ticket, double *__restrict__ dot_out) {
+                                                       double *__restrict__ partial, StencilW W, unsigned *__restrict__ ticket, double *__restrict__ dot_out, const P2PFuse F) {
   constexpr int TX = S3_TX, TY = S3_TY, NT = TX * TY, NARR = BETA ? 2 : 1;
   if (BETA && scal[5] != 0.0f) return;      // CG has converged: the iterations launched ahead of the host's check are no-ops
   __shared__ __align__(128) unsigned char stage[S3_NST * NARR * S3_SLOT];
@@ -193,6 +202,10 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
       const i64 gi = (i64)zo * pl + (i64)gy * px + gx;
       if (in0) { out[gi] = a0; dsum += (double)ca0 * (double)a0; }
       if (in1) { out[gi + 1] = b0; dsum += (double)cb0 * (double)b0; }
+      if (BETA && F.enabled) {      // fused halo exchange: my boundary planes of c go straight into the neighbours' arrays over NVLink
+        if (gi >= F.lo0 && gi < F.lo1) { if (in0) F.c_lower[gi] = a0; if (in1) F.c_lower[gi + 1] = b0; }
+        if (gi >= F.hi0 && gi < F.hi1) { if (in0) F.c_upper[gi] = a0; if (in1) F.c_upper[gi + 1] = b0; }
+      }
     }
     a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f; b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0.f;
     ca0 = ca1; ca1 = ctra; cb0 = cb1; cb1 = ctrb;
@@ -205,7 +218,8 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
     double a = 0; for (int i = 0; i < 8; i++) a += red[i];
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
-  if (ticket) cta_sum_last(partial, (int)(gridDim.x * gridDim.y * gridDim.z), ticket, dot_out);
+  if (ticket && cta_sum_last(partial, (int)(gridDim.x * gridDim.y * gridDim.z), ticket, dot_out, F) && F.enabled && tid == 0)
+    p2p_raise_halo_flags(F);      // every CTA fenced its remote stores before its ticket: the neighbours may read their halos now
 }
 // tensor map of a coarse Float32 field (nx x ny x nz values, row pitch px floats) with the 40 x 20 x 1 box of the stencil tiles
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -245,9 +259,13 @@ __device__ __forceinline__ void cg_close_iteration(float *scal, double rr) {    
 }
 __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, float *__restrict__ scal, const double *__restrict__ uc, const float *__restrict__ u,
                                                    const float *__restrict__ c, float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial, unsigned *__restrict__ ticket,
-                                                   double *__restrict__ rr_out, int finalize) {
+                                                   double *__restrict__ rr_out, int finalize, const P2PFuse F) {
   __shared__ double red[8];
   if (scal[5] != 0.0f) return;
+  if (F.enabled) {      // the halo planes of c are written by the neighbours' mat-vec kernels: wait for their flags of this iteration
+    if (threadIdx.x == 0) p2p_wait_halo_flags(F);
+    __syncthreads();
+  }
   const float res0 = scal[2], alpha = res0 * res0 / (float)(*uc); double rr = 0.0;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x; v < n; v += 4 * stride) {       // 4 independent elements per trip: 16 loads in flight
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, fl
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rr;
   __syncthreads();
   if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i]; partial[blockIdx.x] = a; }
-  if (cta_sum_last(partial, (int)gridDim.x, ticket, rr_out) && finalize && threadIdx.x == 0) { scal[1] = alpha; cg_close_iteration(scal, *rr_out); }
+  if (cta_sum_last(partial, (int)gridDim.x, ticket, rr_out, F) && finalize && threadIdx.x == 0) { scal[1] = alpha; cg_close_iteration(scal, *rr_out); }
 }
 __global__ void k_cg_residual(float *scal, const double *rr) {      // several ranks: the same closing step after the all-reduce of |r|^2
   if (scal[5] != 0.0f) return;
@@ -1032,24 +1050,26 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
         const bool probe = launched == 3;      // one iteration is split by events for the report (cg_probe)
         if (probe) CK(cudaEventRecord(ctx->ev_probe[0], st));
         // u_new = r + beta*u_old ; c = K u_new ; uc = dot(u_new, c)  (partial sums added up by the last CTA)
-        k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W, tick, dsc + 1);
+        // Peer-memory transport: the two kernels of an iteration do their exchanges themselves -- the mat-vec stores its boundary planes of
+        // c into the neighbours' arrays while it computes, its last CTA all-reduces the dot product through the mailbox and raises the
+        // halo flags; the update waits for the neighbours' flags, its last CTA all-reduces |r|^2 and closes the iteration.
+        P2PFuse fs, fu;
+        if (r2s_p2p_fuse_params(ctx, &fs, &fu, pl, k0, k1, 2)) return 1;
+        k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W, tick, dsc + 1, fs);
         LAUNCH_CHECK();
         if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
         if (probe) CK(cudaEventRecord(ctx->ev_probe[1], st));
-        if (ctx->p2p) {                                // peer memory: my boundary planes of c go straight into the neighbours' halos
-          if (r2s_p2p_halo_put_c(ctx, c, pl, k0, k1, nz, 2)) return 1;
-          if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
-          if (r2s_p2p_halo_wait(ctx)) return 1;
-        } else {
-          if (r2s_group_start(ctx)) return 1;          // one NCCL launch: scalar all-reduce + halo planes of c
+        if (!fs.enabled && !single) {
+          if (r2s_group_start(ctx)) return 1;          // NCCL / event transport: scalar all-reduce + halo planes of c
           if (r2s_allreduce(ctx, dsc + 1, 1, 0)) return 1;
           if (r2s_halo_exchange_f32(ctx, c, pl, k0, k1, nz, 2, 2)) return 1;
           if (r2s_group_end(ctx)) return 1;
         }
         if (probe) CK(cudaEventRecord(ctx->ev_probe[2], st));
-        k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, dsc + 1, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part, tick + 1, dsc + 2, single); LAUNCH_CHECK();
+        const int closes = (single || fs.enabled) ? 1 : 0;      // the update's last CTA closes the iteration unless |r|^2 still needs a separate all-reduce
+        k_cg_update<<<nub, 256, 0, st>>>(next, o_lo - x_lo, o_lo - x_lo + nown, scal, dsc + 1, u_new + x_lo, c + x_lo, x + x_lo, r + x_lo, part, tick + 1, dsc + 2, closes, fu); LAUNCH_CHECK();
         if (probe) CK(cudaEventRecord(ctx->ev_probe[3], st));
-        if (!single) {
+        if (!closes) {
           if (r2s_allreduce(ctx, dsc + 2, 1, 0)) return 1;
           k_cg_residual<<<1, 1, 0, st>>>(scal, dsc + 2); LAUNCH_CHECK();
         }
@@ -1071,7 +1091,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   {
     CUtensorMap tm_w;
     if (stencil_tensor_map(ctx, &tm_w, wgt, nx, ny, nz, px)) return 1;
-    k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W, nullptr, nullptr);
+    { P2PFuse f0; memset(&f0, 0, sizeof(f0)); k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W, nullptr, nullptr, f0); }
   }
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
