@@ -116,7 +116,7 @@ struct r2s_ctx {
   std::vector<double> h_pc[3];
 
   // distance / sign work buffers
-  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters, box_rec, plist;
+  DevBuf cls, act_flag, act_idx, act_rec, cnt_a, cnt_b, keys, keys_alt, tile_ptr, tile_faces, face_tiles, fc_list, tri_cnt, tri_rec, pairbuf, pairxp, cubtmp, counters, box_rec, plist;
   DevBuf dist, xp, sdf, signs;
   DevBuf s_rng, s_el, s_cnt, s_keys, s_keys_alt, s_tile_ptr;
   // connected components
@@ -198,3 +198,30 @@ extern "C" int r2s_export_pvti(r2s_ctx *ctx, const char *path, const char *label
 LocalGroup *r2s_local_group_create(r2s_ctx **ctxs, int n, std::string *err);
 void r2s_local_group_destroy(LocalGroup *g);
 void r2s_local_group_abort(LocalGroup *g);      // a rank failed: wake everybody waiting at a host barrier
+
+#ifdef __CUDACC__
+// ---- warp-private staging of list entries in shared memory ------------------------------------------------------------------------
+// Every device-built list (pairs, cut cells, active cells, cells to evaluate, hard sign points) is appended to through ONE global counter.  Same-address atomics
+// retire at about one per clock, so a claim per 32-lane round makes a kernel atomic-bound (measured: k_vol_rows, k_vl_step, k_pair_scan).
+// Each warp therefore collects its entries in a shared-memory buffer and claims slots for ~100 entries at a time.  n is warp-uniform.
+#define WS_CAP 128
+template <typename T>
+__device__ __forceinline__ void ws_flush(T *buf, int &n, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
+  if (n == 0) return;
+  u64 base = 0;
+  if (lane == 0) base = atomicAdd(gcount, (u64)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < n; i += 32) if ((i64)(base + i) < cap) gout[base + i] = buf[i];
+  __syncwarp();
+  n = 0;
+}
+template <typename T>
+__device__ __forceinline__ void ws_push(T *buf, int &n, bool pred, const T &val, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (!m) return;
+  if (pred) buf[n + __popc(m & ((1u << lane) - 1))] = val;
+  n += __popc(m);
+  __syncwarp();
+  if (n > WS_CAP - 32) ws_flush(buf, n, gout, gcount, cap, lane);
+}
+#endif

@@ -265,6 +265,9 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 // one warp per active element; lanes stride over its candidate points.  plist entry: bit 63 = goes to the pair buffer, bits 24..62 =
 // active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
 #define PL_LI_BITS 24
+#ifndef R2S_PL_MINB
+#define R2S_PL_MINB 5      // resident CTAs per SM the projection kernel is compiled for (96 registers; A/B: tools/gpu_ab_minb.sh)
+#endif
 template <int PASS>
 __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
                                                    int prune, u64 *__restrict__ plist, u64 *__restrict__ cnt, u64 *__restrict__ stats) {
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__res
   }
 }
 // grid-stride over the list: consecutive lanes take consecutive entries (mostly the same element: broadcast loads of its record)
-__global__ void __launch_bounds__(128, 5) k_project_list(const u64 *__restrict__ plist, const u64 *__restrict__ cnt, const BoxRec *__restrict__ box, const int *__restrict__ IEN,
+__global__ void __launch_bounds__(128, R2S_PL_MINB) k_project_list(const u64 *__restrict__ plist, const u64 *__restrict__ cnt, const BoxRec *__restrict__ box, const int *__restrict__ IEN,
                                                          const double *__restrict__ rn, GridDev g, double rho_t, double *__restrict__ pairbuf, double *__restrict__ dist,
                                                          u64 *__restrict__ counters) {
   const u64 n = cnt[0];
@@ -488,6 +491,7 @@ struct TriRec {
   int ps[3], pe[3];      // candidate grid-point range per axis [ps, pe)
   double Xt[3][3];       // vertices (x1, x2, centroid)
   double n[3];           // unit normal
+  double lo[3], hi[3];   // bounding box of the three vertices (lower bound of every candidate distance, k_assemble)
 };
 __global__ void k_tri_count(i64 nact, const ActRec *__restrict__ rec, int nsn, int *__restrict__ cnt) {
   i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -496,13 +500,14 @@ __global__ void k_tri_count(i64 nact, const ActRec *__restrict__ rec, int nsn, i
 }
 template <int NEN>
 __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__restrict__ toff, const int *__restrict__ IEN, const double *__restrict__ X, GridDev g,
-                              double delta, TriRec *__restrict__ tri) {
+                              double delta, TriRec *__restrict__ tri, int *__restrict__ fc_list, u64 *__restrict__ fc_count) {
   constexpr int NSN = NEN == 8 ? 4 : 3, NES = NEN == 8 ? 6 : 4;
   i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (a >= nact) return;
   ActRec r = rec[a];
   rec[a].tri_off = toff[a];
   if (!r.fmask) return;
+  if (r.cls == 2) fc_list[atomicAdd(fc_count, 1ull)] = (int)a;      // crossing element with boundary faces: work list of k_faces_crossing (a few 10^4 entries)
   double Xe[3][NEN];
   for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
   int o = toff[a];
@@ -517,6 +522,7 @@ __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__r
       bool ok = true;
       for (int d = 0; d < 3; d++) {
         double lo = fmin(T.Xt[0][d], fmin(T.Xt[1][d], T.Xt[2][d])), hi = fmax(T.Xt[0][d], fmax(T.Xt[1][d], T.Xt[2][d])); int I0 = 0, I1 = -1;
+        T.lo[d] = lo; T.hi[d] = hi;
         ok = ok && ex::cell_range_axis(lo, hi, delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
         if (ok) { T.ps[d] = g.cstart[g.cs_off[d] + I0]; T.pe[d] = g.cstart[g.cs_off[d] + I1 + 1]; } else { T.ps[d] = 0; T.pe[d] = 0; }
       }
@@ -531,42 +537,6 @@ __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__r
     }
   }
 }
-// process_boundary_faces! for one grid point (point index pi[3], coordinate x): walks the element's triangle records
-template <bool WANT_XP, int NEN>
-__device__ inline void boundary_faces_point(const ActRec &r, const TriRec *__restrict__ tri, const int *__restrict__ IEN, const double *__restrict__ X,
-                                            const double *__restrict__ rn, double rho_t, const int pi[3], const double x[3], VoxState &s) {
-  constexpr int NSN = NEN == 8 ? 4 : 3;
-  const int ntri = __popc((unsigned)r.fmask) * NSN;
-  bool loaded = false;
-  double Xe[3][NEN], re[NEN];
-  for (int t = 0; t < ntri; t++) {
-    const TriRec &T = tri[r.tri_off + t];
-    if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
-    if (r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113)
-      for (int a = 0; a < NEN; a++) { i64 n = IEN[NEN * (i64)r.el + a]; re[a] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * n + d]; }
-      loaded = true;
-    }
-    double Xt[3][3], Et[3][3], n[3];
-    for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; n[d] = T.n[d]; }
-    if (r.cls == 1) {
-      // Solid element: every candidate of this triangle (face, edge or vertex projection) only replaces the running value if it is
-      // strictly smaller, and each of them is at least the distance from x to the triangle's bounding box.  If that bound is not
-      // below the running value the triangle cannot change anything (exact; the margin covers the rounding of the candidates).
-      double lb2 = 0.0;
-#pragma unroll
-      for (int d = 0; d < 3; d++) {
-        const double lo = fmin(Xt[0][d], fmin(Xt[1][d], Xt[2][d])), hi = fmax(Xt[0][d], fmax(Xt[1][d], Xt[2][d]));
-        const double e = fmax(fmax(lo - x[d], x[d] - hi), 0.0);
-        lb2 = fma(e, e, lb2);
-      }
-      const double cur = fabs(s.c) * (1.0 + 1e-12);
-      if (lb2 * (1.0 - 1e-12) > cur * cur) continue;
-    }
-    for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
-    triangle_point<WANT_XP, NEN>(Xe, re, rho_t, r.cls == 1, Xt, Et, n, x, s);
-  }
-}
-
 // Boundary faces of CROSSING elements (process_boundary_faces!(..., false), :584).  For a crossing element every candidate of
 // process_triangle_projection! is accepted or rejected by the rho-test alone (IsProjectedOnFullSegment, :78-119) -- never by
 // the running minimum -- and accepted candidates only ever lower the minimum.  So the element's face contribution to a grid
@@ -575,13 +545,13 @@ __device__ inline void boundary_faces_point(const ActRec &r, const TriRec *__res
 // boundary faces, lanes over the element's candidate points; the order-dependent replay (k_assemble) is then left with the
 // faces of SOLID elements only, which need no inverse map.
 template <int NEN>
-__global__ void __launch_bounds__(128) k_faces_crossing(i64 nact, const ActRec *__restrict__ rec, const TriRec *__restrict__ tri, const int *__restrict__ IEN,
-                                                        const double *__restrict__ X, const double *__restrict__ rn, GridDev g, double rho_t, double *__restrict__ pairbuf) {
+__global__ void __launch_bounds__(128) k_faces_crossing(const int *__restrict__ fc_list, const u64 *__restrict__ fc_count, const ActRec *__restrict__ rec, const TriRec *__restrict__ tri,
+                                                        const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn, GridDev g, double rho_t,
+                                                        double *__restrict__ pairbuf) {
   constexpr int NSN = NEN == 8 ? 4 : 3;
-  const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
-  if (a >= nact) return;
-  const ActRec r = rec[a];
-  if (r.cls != 2 || !r.fmask) return;
+  const int lane = threadIdx.x & 31; const i64 nlist = (i64)*fc_count;
+  for (i64 w = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; w < nlist; w += ((i64)gridDim.x * blockDim.x) >> 5) {
+  const ActRec r = rec[fc_list[w]];
   double Xe[3][NEN], re[NEN];
   for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; re[q] = rn[n]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
   ex::AffineInv pre; pre.affine = 0;
@@ -611,21 +581,37 @@ __global__ void __launch_bounds__(128) k_faces_crossing(i64 nact, const ActRec *
       if (!(cur >= 0.0 && cur <= s.c)) pairbuf[idx] = s.c;
     }
   }
+  }
 }
 
 // One CTA per tile, one thread per grid point; the tile's element list is culled per warp (footprint 8x4x1 points) into
-// shared memory in list order, then every lane replays ITS candidates in ascending element order.
+// shared memory in list order, then the warp replays the culled records in ascending element order.
 #define ACULL_CAP 96
-// FACES = false: tiles whose list holds no element with boundary faces (the vast majority) run a light variant with a
-// small register footprint; FACES = true handles the others.  Both walk all tiles and skip those of the other kind.
+// FACES = false: tiles whose list holds no element with boundary faces (the vast majority; only needed when xp is wanted or for
+// TET4) -- one CTA per tile, tiles of the other kind exit.  FACES = true: the tiles with boundary-face elements, taken from the
+// compacted list k_face_tile_list wrote (a few per cent of all tiles), grid-stride.
+__global__ void k_face_tile_list(int ntiles, const unsigned char *__restrict__ tile_faces, int *__restrict__ list, u64 *__restrict__ count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool f = t < ntiles && tile_faces[t] != 0;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (!m) return;
+  u64 base = 0;
+  if (lane == 0) base = atomicAdd(count, (u64)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (f) list[base + __popc(m & ((1u << lane) - 1))] = t;
+}
 template <bool WANT_XP, int NEN, bool FACES>
-__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
+__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ face_list, const u64 *__restrict__ nface,
+                                                       const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
                                                        const ActRec *__restrict__ rec, const TriRec *__restrict__ tri, const int *__restrict__ IEN, const double *__restrict__ X,
                                                        const double *__restrict__ rn, double rho_t, double delta, const double *__restrict__ pairbuf,
                                                        const double *__restrict__ pairxp, double *__restrict__ dist, double *__restrict__ xpo) {
   __shared__ ActRec srec[TILE_VOX / 32][ACULL_CAP];
-  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if ((tile_faces[t] != 0) != FACES) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nlist = FACES ? (int)*nface : (int)gridDim.x;
+  for (int it = blockIdx.x; it < nlist; it += gridDim.x) {
+  const int t = FACES ? face_list[it] : it;
+  if (!FACES && tile_faces[t] != 0) return;
   const int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
   const int li = threadIdx.x % TILE_X, lj = (threadIdx.x / TILE_X) % TILE_Y, lk = threadIdx.x / (TILE_X * TILE_Y);
   const int pi[3] = {tx * TILE_X + li, ty * TILE_Y + lj, tz * TILE_Z + lk};
@@ -649,70 +635,47 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       n += __popc(m); p += 32;
     }
     __syncwarp();
-    // which culled records contain THIS lane's point: one uniform sweep (broadcast reads)
-    unsigned mk0 = 0, mk1 = 0, mk2 = 0;
+    // Replay, warp-uniform: all lanes walk the culled records in list order (= ascending element index) and, inside a record, its
+    // boundary triangles in order, then take the record's pair-buffer entry -- for every grid point exactly the reference's
+    // sequence restricted to the records / triangles whose candidate range holds the point.  Records and triangles are the
+    // same for the whole warp (broadcast loads, no per-lane cursor); only the rare triangle_point call diverges.
+    constexpr int NSN = NEN == 8 ? 4 : 3;
     for (int q = 0; q < n; q++) {
       const ActRec &r = srec[warp][q];
-      if (valid && pi[0] >= r.ps[0] && pi[0] < r.pe[0] && pi[1] >= r.ps[1] && pi[1] < r.pe[1] && pi[2] >= r.ps[2] && pi[2] < r.pe[2]) {
-        if (q < 32) mk0 |= 1u << q; else if (q < 64) mk1 |= 1u << (q - 32); else mk2 |= 1u << (q - 64);
-      }
-    }
-    // Every lane walks ITS records in list order (= ascending element index) and, inside a record, its boundary triangles in
-    // order, then takes the record's pair-buffer entry -- exactly the reference's sequence for that grid point.  The lanes do
-    // not wait for each other's records: in each round every lane brings its own next triangle to triangle_point, so the
-    // expensive part runs with (nearly) full warps instead of only the lanes that happen to share the current element.
-    constexpr int NSN = NEN == 8 ? 4 : 3;
-    int w = 0, pos = -1, t = 0, ntri = 0; unsigned cur = mk0; bool more = valid;
-    ActRec r; r.cls = 0; r.tri_off = 0; r.pair_off = 0; r.fmask = 0; r.el = 0;
-    double Xe[3][NEN], re[NEN]; bool loaded = false;
-    while (true) {
-      int ti = -1;                                   // index of this lane's next triangle (work item of this round)
-      while (more && ti < 0) {
-        if (t < ntri) {
-          const TriRec &T = tri[r.tri_off + t]; const int tcur = t; t++;
-          if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
+      const bool mine = valid && pi[0] >= r.ps[0] && pi[0] < r.pe[0] && pi[1] >= r.ps[1] && pi[1] < r.pe[1] && pi[2] >= r.ps[2] && pi[2] < r.pe[2];
+      const int ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
+      if (ntri && __any_sync(0xffffffffu, mine)) {
+        double Xe[3][NEN], re[NEN]; bool loaded = false;
+        for (int t = 0; t < ntri; t++) {
+          const TriRec &T = tri[r.tri_off + t];
+          bool go = mine && pi[0] >= T.ps[0] && pi[0] < T.pe[0] && pi[1] >= T.ps[1] && pi[1] < T.pe[1] && pi[2] >= T.ps[2] && pi[2] < T.pe[2];
           if (r.cls == 1) {
             // solid element: no candidate of this triangle can be below the distance to its bounding box; if that is not
             // below the running value the triangle changes nothing (exact; the margin covers the rounding of the candidates)
             double lb2 = 0.0;
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-              const double lo = fmin(T.Xt[0][d], fmin(T.Xt[1][d], T.Xt[2][d])), hi = fmax(T.Xt[0][d], fmax(T.Xt[1][d], T.Xt[2][d]));
-              const double e = fmax(fmax(lo - x[d], x[d] - hi), 0.0);
-              lb2 = fma(e, e, lb2);
-            }
+            for (int d = 0; d < 3; d++) { const double e = fmax(fmax(T.lo[d] - x[d], x[d] - T.hi[d]), 0.0); lb2 = fma(e, e, lb2); }
             const double cv = fabs(s.c) * (1.0 + 1e-12);
-            if (lb2 * (1.0 - 1e-12) > cv * cv) continue;
+            if (lb2 * (1.0 - 1e-12) > cv * cv) go = false;
           }
-          ti = tcur;
-        } else {
-          if (pos >= 0 && r.cls == 2) {              // the record's faces are done: now its iso distance (:617-621)
-            i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
-            double dt = pairbuf[idx];
-            if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
-              s.c = dt;
-              if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
-            }
+          if (!go) continue;
+          if (WANT_XP && r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113), replayed here only when xp is wanted
+            for (int a = 0; a < NEN; a++) { i64 nd = IEN[NEN * (i64)r.el + a]; re[a] = rn[nd]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * nd + d]; }
+            loaded = true;
           }
-          while (w < 3 && cur == 0) { w++; cur = (w == 1) ? mk1 : (w == 2 ? mk2 : 0u); }
-          if (w >= 3) { more = false; pos = -1; break; }
-          const int bq = __ffs(cur) - 1; cur &= cur - 1; pos = w * 32 + bq;
-          r = srec[warp][pos];
-          t = 0; loaded = false;
-          ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
+          double Xt[3][3], Et[3][3], nn[3];
+          for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; nn[d] = T.n[d]; }
+          for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+          triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
         }
       }
-      if (!__any_sync(0xffffffffu, ti >= 0)) break;
-      if (ti >= 0) {
-        const TriRec &T = tri[r.tri_off + ti];
-        if (WANT_XP && r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113), replayed here only when xp is wanted
-          for (int a = 0; a < NEN; a++) { i64 nd = IEN[NEN * (i64)r.el + a]; re[a] = rn[nd]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * nd + d]; }
-          loaded = true;
+      if (mine && r.cls == 2) {                        // the record's faces are done: now its iso distance (:617-621)
+        i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
+        double dt = pairbuf[idx];
+        if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
+          s.c = dt;
+          if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
         }
-        double Xt[3][3], Et[3][3], nn[3];
-        for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; nn[d] = T.n[d]; }
-        for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
-        triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
       }
     }
     __syncwarp();
@@ -721,6 +684,8 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
     i64 v = ((i64)pi[2] * g.np[1] + pi[1]) * g.np[0] + pi[0];
     dist[v] = fabs(s.c);
     if (WANT_XP) { xpo[3 * v] = s.xp[0]; xpo[3 * v + 1] = s.xp[1]; xpo[3 * v + 2] = s.xp[2]; }
+  }
+  __syncwarp();
   }
 }
 
@@ -795,8 +760,10 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     // boundary-face triangle table
     int *toff32 = ctx->tri_cnt.as<int>() + (nact + 1);
     CK(ctx->tri_rec.reserve(sizeof(TriRec) * (size_t)(ntri + 1)));
-    if (nen == 8) k_tri_records<8><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
-    else k_tri_records<4><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>());
+    CK(ctx->fc_list.reserve(sizeof(int) * (size_t)(nact + 16)));
+    u64 *fc_count = ctx->counters.as<u64>() + NCTR + 5;
+    if (nen == 8) k_tri_records<8><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>(), ctx->fc_list.as<int>(), fc_count);
+    else k_tri_records<4><<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), toff32, ctx->IEN32.as<int>(), ctx->X.as<double>(), g, delta, ctx->tri_rec.as<TriRec>(), ctx->fc_list.as<int>(), fc_count);
     LAUNCH_CHECK();
   }
   // tile_ptr[t+1] currently holds the count of tile t (tile_ptr[0] = 0): inclusive scan in place == exclusive offsets
@@ -854,13 +821,20 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
     }
   }
   if (!want_xp && nact > 0 && npairs > 0) {
-    if (nen == 8) k_faces_crossing<8><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
-    else k_faces_crossing<4><<<cdiv(nact * 32, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
+    const u64 *fc_count = ctx->counters.as<u64>() + NCTR + 5;
+    const unsigned fcg = (unsigned)std::min<i64>(cdiv(nact * 32, 128), 148 * 32);
+    if (nen == 8) k_faces_crossing<8><<<fcg, 128, 0, st>>>(ctx->fc_list.as<int>(), fc_count, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
+    else k_faces_crossing<4><<<fcg, 128, 0, st>>>(ctx->fc_list.as<int>(), fc_count, ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>());
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   {
-#define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->tile_ptr.as<int>(), sorted, \
+    // the tiles that hold boundary-face elements, as a list (order irrelevant: tiles are independent)
+    u64 *nface = ctx->counters.as<u64>() + NCTR + 4;
+    CK(ctx->face_tiles.reserve(sizeof(int) * ((size_t)g.ntiles + 16)));
+    k_face_tile_list<<<cdiv(g.ntiles, 256), 256, 0, st>>>((int)g.ntiles, ctx->tile_faces.as<unsigned char>(), ctx->face_tiles.as<int>(), nface); LAUNCH_CHECK();
+    const unsigned fgrid = (unsigned)std::min<i64>(g.ntiles, (i64)148 * 64);
+#define ASM(XP, NEN, F) k_assemble<XP, NEN, F><<<(F) ? fgrid : (unsigned)g.ntiles, TILE_VOX, 0, st>>>(g, kz0, kz1, ctx->tile_faces.as<unsigned char>(), ctx->face_tiles.as<int>(), nface, ctx->tile_ptr.as<int>(), sorted, \
         ctx->act_rec.as<ActRec>(), ctx->tri_rec.as<TriRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), rho_t, delta, ctx->pairbuf.as<double>(), ctx->pairxp.as<double>(), \
         ctx->dist.as<double>(), ctx->xp.as<double>()); LAUNCH_CHECK()
     if (nen == 8) { if (want_xp) { ASM(true, 8, false); ASM(true, 8, true); } else { ASM(false, 8, true); } }      // without xp the face-free tiles are final already

@@ -489,30 +489,6 @@ static int volume_dev(r2s_ctx *ctx, const float *sdf, int nx, int ny, int nz, in
   }
   FAIL("calculate_volume_from_sdf: cut-cell list overflow");
 }
-// ---- warp-private staging of list entries in shared memory ------------------------------------------------------------------------
-// Every list of this file (cut cells, active cells, cells to evaluate) is appended to through ONE global counter.  Same-address atomics
-// retire at about one per clock, so a claim per 32-lane round makes a kernel atomic-bound (measured: k_vol_rows, k_vl_step, k_pair_scan).
-// Each warp therefore collects its entries in a shared-memory buffer and claims slots for ~100 entries at a time.  n is warp-uniform.
-#define WS_CAP 128
-template <typename T>
-__device__ __forceinline__ void ws_flush(T *buf, int &n, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
-  if (n == 0) return;
-  u64 base = 0;
-  if (lane == 0) base = atomicAdd(gcount, (u64)n);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (int i = lane; i < n; i += 32) if ((i64)(base + i) < cap) gout[base + i] = buf[i];
-  __syncwarp();
-  n = 0;
-}
-template <typename T>
-__device__ __forceinline__ void ws_push(T *buf, int &n, bool pred, const T &val, T *__restrict__ gout, u64 *__restrict__ gcount, i64 cap, int lane) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (!m) return;
-  if (pred) buf[n + __popc(m & ((1u << lane) - 1))] = val;
-  n += __popc(m);
-  __syncwarp();
-  if (n > WS_CAP - 32) ws_flush(buf, n, gout, gcount, cap, lane);
-}
 // active cell of the threshold search: id, min / max of its corner values, index of its quadrature record (-1: none yet)
 struct VAct { int id; float mn, mx; int rec; };
 // Whole-grid classification (bisection steps 1-3 and the final fine-grid volume): a warp owns cell ROWS; per 31-cell segment every lane

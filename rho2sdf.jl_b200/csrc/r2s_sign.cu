@@ -287,90 +287,118 @@ __global__ void k_lat_pt(GridDev g, const double *__restrict__ xs, int o0, int o
   else { a0 = l - 1; cnt = (l >= 1 && l <= n - 1) ? 1 : 0; }
   pt[g.pc_off[d] + i] = (a0 << 2) | cnt;
 }
+// Two kernels.  k_sign_lattice looks at the density classes of the candidates only -- enough for nine points out of ten -- and lists
+// the others (packed i | j << 21 | k << 42; per-warp staging, r2s_common.cuh); k_sign_lattice_hard replays the reference's rule for the
+// listed points, one lane each, so its FP64 work runs in full warps instead of the few lanes per warp that sit next to the surface.
+__global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz1, const int *__restrict__ pt, int m0, int m1, const unsigned *__restrict__ info,
+                                                      const double *__restrict__ dist, double *__restrict__ signs, double *__restrict__ sdf,
+                                                      u64 *__restrict__ hard, u64 *__restrict__ nhard, i64 cap) {
+  __shared__ u64 s_hard[8][WS_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; int nh = 0;
+  const int segs = (g.np[0] + 31) >> 5;
+  const i64 pl = (i64)g.np[0] * g.np[1], nchunk = (i64)segs * g.np[1] * (kz1 - kz0);
+  for (i64 c = (i64)blockIdx.x * 8 + warp; c < nchunk; c += (i64)gridDim.x * 8) {
+    const int seg = (int)(c % segs); const i64 row = c / segs;
+    const int j = (int)(row % g.np[1]), k = kz0 + (int)(row / g.np[1]), i = seg * 32 + lane;
+    const bool in = i < g.np[0];
+    bool later = false; double sign = -1.0;
+    if (in) {
+      const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
+      const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
+      if (n0 * n1 * n2 != 0) {
+        bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+          if (ii < n0 && jj < n1 && kk < n2) {
+            const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
+            if (w != 0xffffffffu) { hotany = hotany || (w >> 31); nc++; const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2; }
+          }
+        }
+        // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
+        // density class 2 (rho < rho_t wherever max|xi| < 1.01) no candidate can set the sign; if ALL are of class 1 (rho >= rho_t there)
+        // the first candidate -- accepted whatever its max|xi|, because max_local starts at 10 -- sets it.  Only points next to an element
+        // that may cross rho_t replay the rule (about 7 % of the elements of a SIMP field); skip rule (SignDetection.jl:36): and only if
+        // some candidate has a nodal density >= rho_t.
+        if (nc > 0 && nvoid == nc) sign = -1.0;
+        else if (nc > 0 && nsolid == nc) sign = 1.0;
+        else if (nc > 0 && hotany) later = true;
+      }
+      if (!later) {
+        const i64 v = (i64)k * pl + (i64)j * g.np[0] + i;
+        if (signs) signs[v] = sign;
+        if (sdf) sdf[v] = dist[v] * sign;
+      }
+    }
+    ws_push<u64>(s_hard[warp], nh, later, (u64)i | ((u64)j << 21) | ((u64)k << 42), hard, nhard, cap, lane);
+  }
+  ws_flush<u64>(s_hard[warp], nh, hard, nhard, cap, lane);
+}
 #define CSWAP(a, b) do { const unsigned _lo = min(key[a], key[b]), _hi = max(key[a], key[b]); key[a] = _lo; key[b] = _hi; } while (0)
-__global__ void __launch_bounds__(128) k_sign_lattice(GridDev g, int kz0, int kz1, const int *__restrict__ pt, const double *__restrict__ xs, int o0, int o1, int o2,
-                                                      int m0, int m1, const unsigned *__restrict__ info, const int *__restrict__ IEN, const double *__restrict__ rn,
-                                                      double rho_t, const double *__restrict__ dist, double *__restrict__ signs, double *__restrict__ sdf) {
-  // one thread per grid point; block = 128 consecutive points of one grid row (no 64-bit index arithmetic)
-  const i64 pl = (i64)g.np[0] * g.np[1];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = kz0 + blockIdx.z;
-  if (i >= g.np[0]) return;
-  const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
-  const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
-  double sign = -1.0;
-  if (n0 * n1 * n2 != 0) {
-    // first look at the density classes only: most points need nothing else
-    bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
+__global__ void __launch_bounds__(128) k_sign_lattice_hard(GridDev g, const u64 *__restrict__ hard, const u64 *__restrict__ nhard, const int *__restrict__ pt,
+                                                           const double *__restrict__ xs, int o0, int o1, int o2, int m0, int m1, const unsigned *__restrict__ info,
+                                                           const int *__restrict__ IEN, const double *__restrict__ rn, double rho_t, const double *__restrict__ dist,
+                                                           double *__restrict__ signs, double *__restrict__ sdf) {
+  const i64 pl = (i64)g.np[0] * g.np[1], n = (i64)*nhard;
+  for (i64 h = blockIdx.x * (i64)blockDim.x + threadIdx.x; h < n; h += (i64)gridDim.x * blockDim.x) {
+    const u64 w64 = hard[h];
+    const int i = (int)(w64 & 0x1fffffu), j = (int)((w64 >> 21) & 0x1fffffu), k = (int)(w64 >> 42);
+    const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
+    const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
+    double sign = -1.0;
+    unsigned key[8]; int nc = 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
+      key[q] = 0xffffffffu;
       if (ii < n0 && jj < n1 && kk < n2) {
         const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
-        if (w != 0xffffffffu) { hotany = hotany || (w >> 31); nc++; const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2; }
+        if (w != 0xffffffffu) { key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q; nc++; }
       }
     }
-    // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
-    // density class 2 (rho < rho_t wherever max|xi| < 1.01) no candidate can set the sign; if ALL are of class 1 (rho >= rho_t there)
-    // the first candidate -- accepted whatever its max|xi|, because max_local starts at 10 -- sets it.  Only points next to an element
-    // that may cross rho_t replay the rule (about 7 % of the elements of a SIMP field).
-    if (nc > 0 && nvoid == nc) sign = -1.0;
-    else if (nc > 0 && nsolid == nc) sign = 1.0;
-    else if (nc > 0 && hotany) {      // skip rule (SignDetection.jl:36): some candidate has a nodal density >= rho_t
-      unsigned key[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
-        key[q] = 0xffffffffu;
-        if (ii < n0 && jj < n1 && kk < n2) {
-          const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
-          if (w != 0xffffffffu) key[q] = ((w & 0x0fffffffu) << 3) | (unsigned)q;
-        }
-      }
-      if (nc > 1) {              // ascending element index = the reference's candidate order
-        CSWAP(0, 1); CSWAP(2, 3); CSWAP(4, 5); CSWAP(6, 7); CSWAP(0, 2); CSWAP(1, 3); CSWAP(4, 6); CSWAP(5, 7); CSWAP(1, 2); CSWAP(5, 6);
-        CSWAP(0, 4); CSWAP(1, 5); CSWAP(2, 6); CSWAP(3, 7); CSWAP(2, 4); CSWAP(3, 5); CSWAP(1, 2); CSWAP(3, 4); CSWAP(5, 6);
-      } else {
-#pragma unroll
-        for (int q = 1; q < 8; q++) if (key[q] != 0xffffffffu) { key[0] = key[q]; }
-      }
-      const double x[3] = {g.pc[g.pc_off[0] + i], g.pc[g.pc_off[1] + j], g.pc[g.pc_off[2] + k]};
-      double max_local = 10.0;
+    // ascending element index = the reference's candidate order (missing candidates sort to the end)
+    CSWAP(0, 1); CSWAP(2, 3); CSWAP(4, 5); CSWAP(6, 7); CSWAP(0, 2); CSWAP(1, 3); CSWAP(4, 6); CSWAP(5, 7); CSWAP(1, 2); CSWAP(5, 6);
+    CSWAP(0, 4); CSWAP(1, 5); CSWAP(2, 6); CSWAP(3, 7); CSWAP(2, 4); CSWAP(3, 5); CSWAP(1, 2); CSWAP(3, 4); CSWAP(5, 6);
+    const double x[3] = {g.pc[g.pc_off[0] + i], g.pc[g.pc_off[1] + j], g.pc[g.pc_off[2] + k]};
+    double max_local = 10.0;
 #pragma unroll 1
-      for (int q = 0; q < nc; q++) {
-        const unsigned kq = key[q]; const int e = (int)(kq >> 3), loc = (int)(kq & 7u);
-        const int a[3] = {c0 + (loc & 1), c1 + ((loc >> 1) & 1), c2 + (loc >> 2)};
-        const double l0 = xs[o0 + a[0]], h0 = xs[o0 + a[0] + 1], l1 = xs[o1 + a[1]], h1 = xs[o1 + a[1] + 1], l2 = xs[o2 + a[2]], h2 = xs[o2 + a[2] + 1];
-        const double hx = ex::mul(0.5, ex::sub(h0, l0)), hy = ex::mul(0.5, ex::sub(h1, l1)), hz = ex::mul(0.5, ex::sub(h2, l2));
-        const double cof0 = ex::mul(hy, hz), cof1 = ex::mul(hx, hz), cof2 = ex::mul(hx, hy), det = ex::mul(hx, cof0);
-        double xi[3];
-        if (!(fabs(det) > 0.0)) xi[0] = xi[1] = xi[2] = 10.0;
-        else {
-          const double d0 = ex::dvd(ex::mul(cof0, ex::sub(ex::mul(0.5, ex::add(l0, h0)), x[0])), det);
-          const double d1 = ex::dvd(ex::mul(cof1, ex::sub(ex::mul(0.5, ex::add(l1, h1)), x[1])), det);
-          const double d2 = ex::dvd(ex::mul(cof2, ex::sub(ex::mul(0.5, ex::add(l2, h2)), x[2])), det);
-          xi[0] = ex::sub(0.0, d0); xi[1] = ex::sub(0.0, d1); xi[2] = ex::sub(0.0, d2);
-          if (!(ex::max3abs(d0, d1, d2) < 1.0e3) || !(ex::max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) xi[0] = xi[1] = xi[2] = 10.0;
-        }
-        const double mn = ex::max3abs(xi[0], xi[1], xi[2]);
-        if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
-          const unsigned cls = (info[((i64)a[2] * m1 + a[1]) * m0 + a[0]] >> 29) & 3u;
-          if (cls == 1) sign = 1.0;
-          else if (cls == 0) {
-            double N[8], re[8];
+    for (int q = 0; q < nc; q++) {
+      unsigned kq = key[0];
 #pragma unroll
-            for (int b = 0; b < 8; b++) re[b] = rn[IEN[8 * (i64)e + b]];
-            ex::hex8_shape(xi, N);
-            if (ex::dot8(N, re) >= rho_t) sign = 1.0;
-          }
-          if (mn < 0.95) break;                                    // :51-59
-          max_local = mn;
+      for (int b = 1; b < 8; b++) if (q == b) kq = key[b];      // register select instead of a local-memory array
+      const int e = (int)(kq >> 3), loc = (int)(kq & 7u);
+      const int a[3] = {c0 + (loc & 1), c1 + ((loc >> 1) & 1), c2 + (loc >> 2)};
+      const double l0 = xs[o0 + a[0]], h0 = xs[o0 + a[0] + 1], l1 = xs[o1 + a[1]], h1 = xs[o1 + a[1] + 1], l2 = xs[o2 + a[2]], h2 = xs[o2 + a[2] + 1];
+      const double hx = ex::mul(0.5, ex::sub(h0, l0)), hy = ex::mul(0.5, ex::sub(h1, l1)), hz = ex::mul(0.5, ex::sub(h2, l2));
+      const double cof0 = ex::mul(hy, hz), cof1 = ex::mul(hx, hz), cof2 = ex::mul(hx, hy), det = ex::mul(hx, cof0);
+      double xi[3];
+      if (!(fabs(det) > 0.0)) xi[0] = xi[1] = xi[2] = 10.0;
+      else {
+        const double d0 = ex::dvd(ex::mul(cof0, ex::sub(ex::mul(0.5, ex::add(l0, h0)), x[0])), det);
+        const double d1 = ex::dvd(ex::mul(cof1, ex::sub(ex::mul(0.5, ex::add(l1, h1)), x[1])), det);
+        const double d2 = ex::dvd(ex::mul(cof2, ex::sub(ex::mul(0.5, ex::add(l2, h2)), x[2])), det);
+        xi[0] = ex::sub(0.0, d0); xi[1] = ex::sub(0.0, d1); xi[2] = ex::sub(0.0, d2);
+        if (!(ex::max3abs(d0, d1, d2) < 1.0e3) || !(ex::max3abs(xi[0], xi[1], xi[2]) < 1.0e3)) xi[0] = xi[1] = xi[2] = 10.0;
+      }
+      const double mn = ex::max3abs(xi[0], xi[1], xi[2]);
+      if (mn < 1.01 && max_local > mn) {                         // SignDetection.jl:48
+        const unsigned cls = (info[((i64)a[2] * m1 + a[1]) * m0 + a[0]] >> 29) & 3u;
+        if (cls == 1) sign = 1.0;
+        else if (cls == 0) {
+          double N[8], re[8];
+#pragma unroll
+          for (int b = 0; b < 8; b++) re[b] = rn[IEN[8 * (i64)e + b]];
+          ex::hex8_shape(xi, N);
+          if (ex::dot8(N, re) >= rho_t) sign = 1.0;
         }
+        if (mn < 0.95) break;                                    // :51-59
+        max_local = mn;
       }
     }
+    const i64 v = (i64)k * pl + (i64)j * g.np[0] + i;
+    if (signs) signs[v] = sign;
+    if (sdf) sdf[v] = dist[v] * sign;
   }
-  const i64 v = (i64)k * pl + (i64)j * g.np[0] + i;
-  if (signs) signs[v] = sign;
-  if (sdf) sdf[v] = dist[v] * sign;
 }
 #undef CSWAP
 
@@ -392,9 +420,16 @@ int r2s_dev_sign(r2s_ctx *ctx, double rho_t, bool write_signs, bool write_sdf) {
     const int *lo = ctx->lat_off, *nd = ctx->lat_nd;
     k_lat_info<<<cdiv(nel, 256), 256, 0, st>>>(nel, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->lat_cell.as<int>(), ctx->ezr.as<double2>(), zlo, zhi, ctx->lat_info.as<unsigned>()); LAUNCH_CHECK();
     k_lat_pt<<<cdiv(npt, 256), 256, 0, st>>>(g, ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0], nd[1], nd[2], ctx->lat_pt.as<int>()); LAUNCH_CHECK();
-    const dim3 sg((unsigned)cdiv(g.np[0], 128), (unsigned)g.np[1], (unsigned)(kz1 - kz0));
-    k_sign_lattice<<<sg, 128, 0, st>>>(g, kz0, kz1, ctx->lat_pt.as<int>(), ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0] - 1, nd[1] - 1, ctx->lat_info.as<unsigned>(),
-                                                  ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf); LAUNCH_CHECK();
+    // hard-point list: the pair list of the projection is free by now and large enough in all but degenerate cases
+    const i64 cap = (i64)g.np[0] * g.np[1] * (kz1 - kz0);
+    CK(ctx->plist.reserve(sizeof(u64) * (size_t)(cap + 16)));
+    CK(ctx->counters.reserve(sizeof(u64) * 16));
+    u64 *nhard = ctx->counters.as<u64>();
+    CK(cudaMemsetAsync(nhard, 0, sizeof(u64), st));
+    k_sign_lattice<<<148 * 8, 256, 0, st>>>(g, kz0, kz1, ctx->lat_pt.as<int>(), nd[0] - 1, nd[1] - 1, ctx->lat_info.as<unsigned>(), ctx->dist.as<double>(), signs, sdf,
+                                            ctx->plist.as<u64>(), nhard, cap); LAUNCH_CHECK();
+    k_sign_lattice_hard<<<148 * 16, 128, 0, st>>>(g, ctx->plist.as<u64>(), nhard, ctx->lat_pt.as<int>(), ctx->lat_xs.as<double>(), lo[0], lo[1], lo[2], nd[0] - 1, nd[1] - 1,
+                                                  ctx->lat_info.as<unsigned>(), ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), rho_t, ctx->dist.as<double>(), signs, sdf); LAUNCH_CHECK();
     return 0;
   }
   CK(ctx->s_rng.reserve(sizeof(SRange) * (size_t)nel));

@@ -4,7 +4,7 @@
 # usage: tools/gpu_prof_r2.sh TAG [kernel-group ...]   groups: proj scan asm sign cg upd vol fine   (default: all)
 mkdir -p gpurun_out
 TAG=${1:-r2a}; shift
-GROUPS_=${@:-proj scan asm sign cg upd vol fine}
+GROUPS_=${@:-proj asm sign cg upd vol}
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain256.log 2>&1 || { echo plain failed; tail gpurun_out/plain256.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_${TAG}_n256.csv $CMD > gpurun_out/ncu_l.log 2>&1; echo "ncu launches rc=$?"
@@ -18,9 +18,9 @@ for g in $GROUPS_; do
     scan) cap scan "k_pair_scan|k_box_records" 3 3 ;;
     asm)  cap asm "k_assemble|k_faces_crossing" 2 2 ;;
     sign) cap sign "k_sign_lattice|k_lat_info" 2 2 ;;
-    cg)   cap cg "k_stencil81" 24 1 ;;
+    cg)   cap cg "k_stencil81_tma" 24 1 ;;
     upd)  cap upd "k_cg_update" 23 1 ;;
-    vol)  cap vol "k_vol_cut|k_vol_rows|k_vol_step" 120 4 ;;
+    vol)  cap vol "k_vol_cut|k_vol_rows|k_vl_step|k_vl_eval" 90 4 ;;
     fine) cap fine "k_fine_eval2" 1 1 ;;
   esac
 done
