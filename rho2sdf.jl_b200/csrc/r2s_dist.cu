@@ -265,8 +265,11 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 // one warp per active element; lanes stride over its candidate points.  plist entry: bit 63 = goes to the pair buffer, bits 24..62 =
 // active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
 #define PL_LI_BITS 24
+#ifndef R2S_ASM_UNIFORM
+#define R2S_ASM_UNIFORM 0
+#endif
 #ifndef R2S_PL_MINB
-#define R2S_PL_MINB 5      // resident CTAs per SM the projection kernel is compiled for (96 registers; A/B: tools/gpu_ab_minb.sh)
+#define R2S_PL_MINB 4      // resident CTAs per SM the projection kernel is compiled for: 4 = 128 registers (solve 36.1 ms), 5 = 96 registers with spills (37.5), 3 = 167 registers (42.3); tools/gpu_ab_libs.sh
 #endif
 template <int PASS>
 __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
@@ -601,15 +604,23 @@ __global__ void k_face_tile_list(int ntiles, const unsigned char *__restrict__ t
   if (f) list[base + __popc(m & ((1u << lane) - 1))] = t;
 }
 template <bool WANT_XP, int NEN, bool FACES>
-__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ face_list, const u64 *__restrict__ nface,
+__global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int kz1, const unsigned char *__restrict__ tile_faces, const int *__restrict__ face_list, u64 *__restrict__ nface,
                                                        const int *__restrict__ tile_ptr, const u64 *__restrict__ keys,
                                                        const ActRec *__restrict__ rec, const TriRec *__restrict__ tri, const int *__restrict__ IEN, const double *__restrict__ X,
                                                        const double *__restrict__ rn, double rho_t, double delta, const double *__restrict__ pairbuf,
                                                        const double *__restrict__ pairxp, double *__restrict__ dist, double *__restrict__ xpo) {
   __shared__ ActRec srec[TILE_VOX / 32][ACULL_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nlist = FACES ? (int)*nface : (int)gridDim.x;
-  for (int it = blockIdx.x; it < nlist; it += gridDim.x) {
+  __shared__ int s_next;
+  const int nlist = FACES ? (int)nface[0] : (int)gridDim.x;
+  for (int it = blockIdx.x;;) {
+  if (FACES) {        // tiles differ a lot in work (edges and corners of the domain): fetch them dynamically
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = (int)atomicAdd((u64 *)&nface[1], 1ull);
+    __syncthreads();
+    it = s_next;
+  }
+  if (it >= nlist) return;
   const int t = FACES ? face_list[it] : it;
   if (!FACES && tile_faces[t] != 0) return;
   const int tx = t % g.nt[0], ty = (t / g.nt[0]) % g.nt[1], tz = t / (g.nt[0] * g.nt[1]);
@@ -635,6 +646,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       n += __popc(m); p += 32;
     }
     __syncwarp();
+#if R2S_ASM_UNIFORM
     // Replay, warp-uniform: all lanes walk the culled records in list order (= ascending element index) and, inside a record, its
     // boundary triangles in order, then take the record's pair-buffer entry -- for every grid point exactly the reference's
     // sequence restricted to the records / triangles whose candidate range holds the point.  Records and triangles are the
@@ -678,6 +690,73 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
         }
       }
     }
+#else
+    // which culled records contain THIS lane's point: one uniform sweep (broadcast reads)
+    unsigned mk0 = 0, mk1 = 0, mk2 = 0;
+    for (int q = 0; q < n; q++) {
+      const ActRec &r = srec[warp][q];
+      if (valid && pi[0] >= r.ps[0] && pi[0] < r.pe[0] && pi[1] >= r.ps[1] && pi[1] < r.pe[1] && pi[2] >= r.ps[2] && pi[2] < r.pe[2]) {
+        if (q < 32) mk0 |= 1u << q; else if (q < 64) mk1 |= 1u << (q - 32); else mk2 |= 1u << (q - 64);
+      }
+    }
+    // Every lane walks ITS records in list order (= ascending element index) and, inside a record, its boundary triangles in
+    // order, then takes the record's pair-buffer entry -- exactly the reference's sequence for that grid point.  The lanes do
+    // not wait for each other's records: in each round every lane brings its own next triangle to triangle_point, so the
+    // expensive part runs with (nearly) full warps instead of only the lanes that happen to share the current element.
+    constexpr int NSN = NEN == 8 ? 4 : 3;
+    int w = 0, pos = -1, t = 0, ntri = 0; unsigned cur = mk0; bool more = valid;
+    ActRec r; r.cls = 0; r.tri_off = 0; r.pair_off = 0; r.fmask = 0; r.el = 0;
+    double Xe[3][NEN], re[NEN]; bool loaded = false;
+    while (true) {
+      int ti = -1;                                   // index of this lane's next triangle (work item of this round)
+      while (more && ti < 0) {
+        if (t < ntri) {
+          const TriRec &T = tri[r.tri_off + t]; const int tcur = t; t++;
+          if (pi[0] < T.ps[0] || pi[0] >= T.pe[0] || pi[1] < T.ps[1] || pi[1] >= T.pe[1] || pi[2] < T.ps[2] || pi[2] >= T.pe[2]) continue;
+          if (r.cls == 1) {
+            // solid element: no candidate of this triangle can be below the distance to its bounding box; if that is not
+            // below the running value the triangle changes nothing (exact; the margin covers the rounding of the candidates)
+            double lb2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+              const double e = fmax(fmax(T.lo[d] - x[d], x[d] - T.hi[d]), 0.0);
+              lb2 = fma(e, e, lb2);
+            }
+            const double cv = fabs(s.c) * (1.0 + 1e-12);
+            if (lb2 * (1.0 - 1e-12) > cv * cv) continue;
+          }
+          ti = tcur;
+        } else {
+          if (pos >= 0 && r.cls == 2) {              // the record's faces are done: now its iso distance (:617-621)
+            i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
+            double dt = pairbuf[idx];
+            if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
+              s.c = dt;
+              if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
+            }
+          }
+          while (w < 3 && cur == 0) { w++; cur = (w == 1) ? mk1 : (w == 2 ? mk2 : 0u); }
+          if (w >= 3) { more = false; pos = -1; break; }
+          const int bq = __ffs(cur) - 1; cur &= cur - 1; pos = w * 32 + bq;
+          r = srec[warp][pos];
+          t = 0; loaded = false;
+          ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
+        }
+      }
+      if (!__any_sync(0xffffffffu, ti >= 0)) break;
+      if (ti >= 0) {
+        const TriRec &T = tri[r.tri_off + ti];
+        if (WANT_XP && r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113), replayed here only when xp is wanted
+          for (int a = 0; a < NEN; a++) { i64 nd = IEN[NEN * (i64)r.el + a]; re[a] = rn[nd]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * nd + d]; }
+          loaded = true;
+        }
+        double Xt[3][3], Et[3][3], nn[3];
+        for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; nn[d] = T.n[d]; }
+        for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
+        triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
+      }
+    }
+#endif
     __syncwarp();
   }
   if (valid) {
@@ -686,6 +765,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
     if (WANT_XP) { xpo[3 * v] = s.xp[0]; xpo[3 * v + 1] = s.xp[1]; xpo[3 * v + 2] = s.xp[2]; }
   }
   __syncwarp();
+  if (!FACES) return;
   }
 }
 
@@ -801,7 +881,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
         BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
         CK(cudaEventRecord(ctx->ev_k[0], st));
         k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box); LAUNCH_CHECK();
-        const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * 5 * 4;
+        const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * R2S_PL_MINB * 4;
         k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc, ctx->counters.as<u64>()); LAUNCH_CHECK();
         CK(cudaEventRecord(ctx->ev_k[1], st));
         k_project_list<<<pgrid, 128, 0, st>>>(pl, pc, box, ctx->IEN32.as<int>(), ctx->rho_n.as<double>(), g, rho_t, ctx->pairbuf.as<double>(), ctx->dist.as<double>(), ctx->counters.as<u64>()); LAUNCH_CHECK();
@@ -830,7 +910,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   CK(cudaEventRecord(ctx->ev[2], st));
   {
     // the tiles that hold boundary-face elements, as a list (order irrelevant: tiles are independent)
-    u64 *nface = ctx->counters.as<u64>() + NCTR + 4;
+    u64 *nface = ctx->counters.as<u64>() + NCTR + 6;      // [0] list length, [1] next tile to fetch
     CK(ctx->face_tiles.reserve(sizeof(int) * ((size_t)g.ntiles + 16)));
     k_face_tile_list<<<cdiv(g.ntiles, 256), 256, 0, st>>>((int)g.ntiles, ctx->tile_faces.as<unsigned char>(), ctx->face_tiles.as<int>(), nface); LAUNCH_CHECK();
     const unsigned fgrid = (unsigned)std::min<i64>(g.ntiles, (i64)148 * 64);
