@@ -265,9 +265,6 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 // one warp per active element; lanes stride over its candidate points.  plist entry: bit 63 = goes to the pair buffer, bits 24..62 =
 // active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
 #define PL_LI_BITS 24
-#ifndef R2S_ASM_UNIFORM
-#define R2S_ASM_UNIFORM 0
-#endif
 #ifndef R2S_PL_MINB
 #define R2S_PL_MINB 4      // resident CTAs per SM the projection kernel is compiled for: 4 = 128 registers (solve 36.1 ms), 5 = 96 registers with spills (37.5), 3 = 167 registers (42.3); tools/gpu_ab_libs.sh
 #endif
@@ -588,7 +585,8 @@ __global__ void __launch_bounds__(128) k_faces_crossing(const int *__restrict__ 
 }
 
 // One CTA per tile, one thread per grid point; the tile's element list is culled per warp (footprint 8x4x1 points) into
-// shared memory in list order, then the warp replays the culled records in ascending element order.
+// shared memory in list order, then every lane replays ITS candidates in ascending element order (a warp-uniform walk over the
+// culled records was measured: 13.5 vs 8.4 ms -- the per-lane cursors keep 32 different triangles in flight per round).
 #define ACULL_CAP 96
 // FACES = false: tiles whose list holds no element with boundary faces (the vast majority; only needed when xp is wanted or for
 // TET4) -- one CTA per tile, tiles of the other kind exit.  FACES = true: the tiles with boundary-face elements, taken from the
@@ -646,51 +644,6 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
       n += __popc(m); p += 32;
     }
     __syncwarp();
-#if R2S_ASM_UNIFORM
-    // Replay, warp-uniform: all lanes walk the culled records in list order (= ascending element index) and, inside a record, its
-    // boundary triangles in order, then take the record's pair-buffer entry -- for every grid point exactly the reference's
-    // sequence restricted to the records / triangles whose candidate range holds the point.  Records and triangles are the
-    // same for the whole warp (broadcast loads, no per-lane cursor); only the rare triangle_point call diverges.
-    constexpr int NSN = NEN == 8 ? 4 : 3;
-    for (int q = 0; q < n; q++) {
-      const ActRec &r = srec[warp][q];
-      const bool mine = valid && pi[0] >= r.ps[0] && pi[0] < r.pe[0] && pi[1] >= r.ps[1] && pi[1] < r.pe[1] && pi[2] >= r.ps[2] && pi[2] < r.pe[2];
-      const int ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
-      if (ntri && __any_sync(0xffffffffu, mine)) {
-        double Xe[3][NEN], re[NEN]; bool loaded = false;
-        for (int t = 0; t < ntri; t++) {
-          const TriRec &T = tri[r.tri_off + t];
-          bool go = mine && pi[0] >= T.ps[0] && pi[0] < T.pe[0] && pi[1] >= T.ps[1] && pi[1] < T.pe[1] && pi[2] >= T.ps[2] && pi[2] < T.pe[2];
-          if (r.cls == 1) {
-            // solid element: no candidate of this triangle can be below the distance to its bounding box; if that is not
-            // below the running value the triangle changes nothing (exact; the margin covers the rounding of the candidates)
-            double lb2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < 3; d++) { const double e = fmax(fmax(T.lo[d] - x[d], x[d] - T.hi[d]), 0.0); lb2 = fma(e, e, lb2); }
-            const double cv = fabs(s.c) * (1.0 + 1e-12);
-            if (lb2 * (1.0 - 1e-12) > cv * cv) go = false;
-          }
-          if (!go) continue;
-          if (WANT_XP && r.cls != 1 && !loaded) {      // the element itself is only needed for the rho-test of crossing elements (:92-113), replayed here only when xp is wanted
-            for (int a = 0; a < NEN; a++) { i64 nd = IEN[NEN * (i64)r.el + a]; re[a] = rn[nd]; for (int d = 0; d < 3; d++) Xe[d][a] = X[3 * nd + d]; }
-            loaded = true;
-          }
-          double Xt[3][3], Et[3][3], nn[3];
-          for (int d = 0; d < 3; d++) { Xt[0][d] = T.Xt[0][d]; Xt[1][d] = T.Xt[1][d]; Xt[2][d] = T.Xt[2][d]; nn[d] = T.n[d]; }
-          for (int d = 0; d < 3; d++) { Et[0][d] = ex::sub(Xt[1][d], Xt[0][d]); Et[1][d] = ex::sub(Xt[2][d], Xt[1][d]); Et[2][d] = ex::sub(Xt[0][d], Xt[2][d]); }
-          triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
-        }
-      }
-      if (mine && r.cls == 2) {                        // the record's faces are done: now its iso distance (:617-621)
-        i64 idx = r.pair_off + ((i64)(pi[2] - r.ps[2]) * (r.pe[1] - r.ps[1]) + (pi[1] - r.ps[1])) * (r.pe[0] - r.ps[0]) + (pi[0] - r.ps[0]);
-        double dt = pairbuf[idx];
-        if (dt >= 0.0 && fabs(dt) < fabs(s.c)) {
-          s.c = dt;
-          if (WANT_XP) { s.xp[0] = pairxp[3 * idx]; s.xp[1] = pairxp[3 * idx + 1]; s.xp[2] = pairxp[3 * idx + 2]; }
-        }
-      }
-    }
-#else
     // which culled records contain THIS lane's point: one uniform sweep (broadcast reads)
     unsigned mk0 = 0, mk1 = 0, mk2 = 0;
     for (int q = 0; q < n; q++) {
@@ -756,7 +709,6 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
         triangle_point<WANT_XP, NEN>(Xe, re, rho_t, WANT_XP ? r.cls == 1 : true, Xt, Et, nn, x, s);
       }
     }
-#endif
     __syncwarp();
   }
   if (valid) {

@@ -256,6 +256,7 @@ __device__ __forceinline__ void cg_close_iteration(float *scal, double rr) {    
   scal[3] = prev; scal[2] = res; scal[0] = res * res / (prev * prev);
   scal[6] += 1.0f;
   if (res <= scal[4]) scal[5] = 1.0f;
+  else if (!(res < INFINITY)) scal[5] = 2.0f;      // NaN / Inf residual (bad input or a failed exchange): stop instead of iterating to maxiter = n
 }
 __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, float *__restrict__ scal, const double *__restrict__ uc, const float *__restrict__ u,
                                                    const float *__restrict__ c, float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial, unsigned *__restrict__ ticket,
@@ -1056,6 +1057,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       if (!probed && launched > 3) { probed = true; for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1])); }
     }
     ctx->skip_flag = nullptr;
+    if (hs[5] == 2.0f) FAIL("RBFs_smoothing: the CG residual is not finite (non-finite SDF input, or a peer-memory exchange failed)");
     iters = (int)hs[6];
     wgt = x;
     if (r2s_halo_exchange_f32(ctx, x, pl, k0, k1, nz, 2, 3)) return 1;      // the fine evaluation reaches 3 planes up

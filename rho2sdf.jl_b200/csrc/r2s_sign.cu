@@ -295,42 +295,54 @@ __global__ void __launch_bounds__(256) k_sign_lattice(GridDev g, int kz0, int kz
                                                       u64 *__restrict__ hard, u64 *__restrict__ nhard, i64 cap) {
   __shared__ u64 s_hard[8][WS_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; int nh = 0;
-  const int segs = (g.np[0] + 31) >> 5;
-  const i64 pl = (i64)g.np[0] * g.np[1], nchunk = (i64)segs * g.np[1] * (kz1 - kz0);
-  for (i64 c = (i64)blockIdx.x * 8 + warp; c < nchunk; c += (i64)gridDim.x * 8) {
-    const int seg = (int)(c % segs); const i64 row = c / segs;
-    const int j = (int)(row % g.np[1]), k = kz0 + (int)(row / g.np[1]), i = seg * 32 + lane;
-    const bool in = i < g.np[0];
-    bool later = false; double sign = -1.0;
-    if (in) {
-      const int p0 = pt[g.pc_off[0] + i], p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
-      const int c0 = p0 >> 2, c1 = p1 >> 2, c2 = p2 >> 2, n0 = p0 & 3, n1 = p1 & 3, n2 = p2 & 3;
-      if (n0 * n1 * n2 != 0) {
-        bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
+  const i64 pl = (i64)g.np[0] * g.np[1];
+  const int nrow = g.np[1] * (kz1 - kz0);
+  // a warp owns grid ROWS (j, k): the candidate cells' row offsets are the same for the whole row, only the x cell differs per lane
+  for (int row = blockIdx.x * 8 + warp; row < nrow; row += gridDim.x * 8) {
+    const int j = row % g.np[1], k = kz0 + row / g.np[1];
+    const int p1 = pt[g.pc_off[1] + j], p2 = pt[g.pc_off[2] + k];
+    const int c1 = p1 >> 2, c2 = p2 >> 2, n1 = p1 & 3, n2 = p2 & 3;
+    const i64 vrow = (i64)k * pl + (i64)j * g.np[0];
+    const unsigned *__restrict__ rb[4];      // (jj, kk) candidate rows; a missing one repeats the first (its loads are predicated off)
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int ii = q & 1, jj = (q >> 1) & 1, kk = q >> 2;
-          if (ii < n0 && jj < n1 && kk < n2) {
-            const unsigned w = info[((i64)(c2 + kk) * m1 + (c1 + jj)) * m0 + (c0 + ii)];
-            if (w != 0xffffffffu) { hotany = hotany || (w >> 31); nc++; const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2; }
+    for (int q = 0; q < 4; q++) rb[q] = info + ((i64)(c2 + (q >> 1)) * m1 + (c1 + (q & 1))) * m0;
+    for (int i0 = 0; i0 < g.np[0]; i0 += 32) {
+      const int i = i0 + lane;
+      const bool in = i < g.np[0];
+      bool later = false; double sign = -1.0;
+      if (in) {
+        const int p0 = pt[g.pc_off[0] + i];
+        const int c0 = p0 >> 2, n0 = p0 & 3;
+        if (n0 * n1 * n2 != 0) {
+          bool hotany = false; int nc = 0, nsolid = 0, nvoid = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if ((q & 1) < n1 && (q >> 1) < n2) {      // warp-uniform
+#pragma unroll
+              for (int ii = 0; ii < 2; ii++) {
+                if (ii < n0) {
+                  const unsigned w = rb[q][c0 + ii];
+                  if (w != 0xffffffffu) { hotany = hotany || (w >> 31); nc++; const unsigned cls = (w >> 29) & 3u; nsolid += cls == 1; nvoid += cls == 2; }
+                }
+              }
+            }
           }
+          // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
+          // density class 2 (rho < rho_t wherever max|xi| < 1.01) no candidate can set the sign; if ALL are of class 1 (rho >= rho_t there)
+          // the first candidate -- accepted whatever its max|xi|, because max_local starts at 10 -- sets it.  Only points next to an element
+          // that may cross rho_t replay the rule (about 7 % of the elements of a SIMP field); skip rule (SignDetection.jl:36): and only if
+          // some candidate has a nodal density >= rho_t.
+          if (nc > 0 && nvoid == nc) sign = -1.0;
+          else if (nc > 0 && nsolid == nc) sign = 1.0;
+          else if (nc > 0 && hotany) later = true;
         }
-        // Every candidate holds the point in its closed AABB, so max|xi| <= 1 + O(eps) < 1.01 for each of them.  If ALL candidates are of
-        // density class 2 (rho < rho_t wherever max|xi| < 1.01) no candidate can set the sign; if ALL are of class 1 (rho >= rho_t there)
-        // the first candidate -- accepted whatever its max|xi|, because max_local starts at 10 -- sets it.  Only points next to an element
-        // that may cross rho_t replay the rule (about 7 % of the elements of a SIMP field); skip rule (SignDetection.jl:36): and only if
-        // some candidate has a nodal density >= rho_t.
-        if (nc > 0 && nvoid == nc) sign = -1.0;
-        else if (nc > 0 && nsolid == nc) sign = 1.0;
-        else if (nc > 0 && hotany) later = true;
+        if (!later) {
+          if (signs) signs[vrow + i] = sign;
+          if (sdf) sdf[vrow + i] = dist[vrow + i] * sign;
+        }
       }
-      if (!later) {
-        const i64 v = (i64)k * pl + (i64)j * g.np[0] + i;
-        if (signs) signs[v] = sign;
-        if (sdf) sdf[v] = dist[v] * sign;
-      }
+      ws_push<u64>(s_hard[warp], nh, later, (u64)i | ((u64)j << 21) | ((u64)k << 42), hard, nhard, cap, lane);
     }
-    ws_push<u64>(s_hard[warp], nh, later, (u64)i | ((u64)j << 21) | ((u64)k << 42), hard, nhard, cap, lane);
   }
   ws_flush<u64>(s_hard[warp], nh, hard, nhard, cap, lane);
 }

@@ -274,6 +274,9 @@ def test_empty_and_degenerate_inputs(r2s):
         r2s.remove_sdf_artifacts(np.zeros(5), grid, mesh=mesh)                    # SdfArtifactRemoval.jl:142
     with pytest.raises(r2s.R2SError):
         r2s.RBFs_smoothing(mesh, np.full(grid.ngp, -1e10), grid, True, 1)         # no finite value (RBFs4Smoothing.jl:17)
+    withnan = np.linspace(-1.0, 1.0, grid.ngp); withnan[grid.ngp // 2] = np.nan
+    with pytest.raises(r2s.R2SError, match="not finite"):
+        r2s.RBFs_smoothing(mesh, withnan, grid, True, 1)                          # CG stops on a NaN residual instead of running to maxiter = n
     mesh.ctx.close()
     bad = IEN.copy(); bad[0, 0] = 99
     with pytest.raises(r2s.R2SError):
