@@ -198,7 +198,7 @@ struct BoxRec {
   int ftile, pad_;           // 1 = some tile overlapped by the candidate range holds boundary-face elements (its pairs may go to the pair buffer)
 };
 __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const int *__restrict__ IEN, const double *__restrict__ X, const double *__restrict__ rn,
-                              const unsigned char *__restrict__ ebox, double rho_t, GridDev g, const unsigned char *__restrict__ tile_faces, BoxRec *__restrict__ box) {
+                              const unsigned char *__restrict__ ebox, double rho_t, GridDev g, const unsigned char *__restrict__ tile_faces, BoxRec *__restrict__ box, u64 *__restrict__ too_big) {
   const i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (a >= nact) return;
   const ActRec r = rec[a];
@@ -227,6 +227,7 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 #pragma unroll
   for (int d = 0; d < 3; d++) { B.c[d] = H.c[d]; B.h[d] = H.h[d]; B.xi0[d] = S0.xi[d]; B.ps[d] = r.ps[d]; }
   B.nx = r.pe[0] - r.ps[0]; B.ny = r.pe[1] - r.ps[1]; B.vol = B.nx * B.ny * (r.pe[2] - r.ps[2]);
+  if ((i64)B.nx * B.ny * (r.pe[2] - r.ps[2]) >= (1ll << 24)) { B.vol = 0; atomicAdd(too_big, 1ull); }      // a pair-list entry holds 24 bits of local point index (PL_LI_BITS)
   B.ftile = 0; B.pad_ = 0;
   if (B.vol > 0)
     for (int tz = r.ps[2] / TILE_Z; tz <= (r.pe[2] - 1) / TILE_Z; tz++)
@@ -290,14 +291,19 @@ __global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__res
   const double sl = 1e-9 * (ehi[0] - elo[0] + ehi[1] - elo[1] + ehi[2] - elo[2]);
   constexpr int RB = 7;      // rounds handled as one batch: all loads of a batch are issued before the first decision (32 * 7 >= 6^3 points)
   int npruned = 0;
+  // local point index li = lane, lane + 32, ... -> (ci, cj, ck), advanced by 32 per round without divisions (runtime divisors cost ~25
+  // instructions each and were 40 % of this kernel's instructions)
+  int ci = lane % nx, cj = (lane / nx) % ny, ck = lane / (nx * ny);
+  const int r32 = 32 % nx, q32 = 32 / nx, jq = q32 % ny, kq = q32 / ny;
   for (int base0 = 0; base0 < vol; base0 += 32 * RB) {
     double lb2[RB], cur[RB]; int flags[RB];      // flags: bit 0 valid candidate of this pass, bit 1 to_buf, bit 2 needs the bound test
 #pragma unroll
     for (int r = 0; r < RB; r++) {
       const int li = base0 + r * 32 + lane;
       flags[r] = 0; lb2[r] = 0.0; cur[r] = R2S_BIG;
+      const int i = ci, j = cj, k = ck;
+      { ci += r32; const int c = ci >= nx ? 1 : 0; ci -= c ? nx : 0; cj += jq + c; ck += kq; if (cj >= ny) { cj -= ny; ck++; } }
       if (li < vol) {
-        const int i = li % nx, j = (li / nx) % ny, k = li / (nx * ny);
         const int pi0 = ps0 + i, pi1 = ps1 + j, pi2 = ps2 + k;
         const double x0 = fma(g.cell, (double)pi0, g.amin[0]), x1 = fma(g.cell, (double)pi1, g.amin[1]), x2 = fma(g.cell, (double)pi2, g.amin[2]);
         const bool to_buf = ftile && tile_faces[((i64)(pi2 / TILE_Z) * g.nt[1] + pi1 / TILE_Y) * g.nt[0] + pi0 / TILE_X] != 0;
@@ -492,6 +498,7 @@ struct TriRec {
   double Xt[3][3];       // vertices (x1, x2, centroid)
   double n[3];           // unit normal
   double lo[3], hi[3];   // bounding box of the three vertices (lower bound of every candidate distance, k_assemble)
+  double rlo[3], rhi[3]; // in the FIRST triangle of an element: bounding box of all its boundary triangles (record-level bound)
 };
 __global__ void k_tri_count(i64 nact, const ActRec *__restrict__ rec, int nsn, int *__restrict__ cnt) {
   i64 a = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -511,6 +518,7 @@ __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__r
   double Xe[3][NEN];
   for (int q = 0; q < NEN; q++) { i64 n = IEN[NEN * (i64)r.el + q]; for (int d = 0; d < 3; d++) Xe[d][q] = X[3 * n + d]; }
   int o = toff[a];
+  double rlo[3] = {1e300, 1e300, 1e300}, rhi[3] = {-1e300, -1e300, -1e300};
   for (int sg = 0; sg < NES; sg++) {
     if (!((r.fmask >> sg) & 1)) continue;
     double Xs[NSN][3], Xc[3];
@@ -522,7 +530,7 @@ __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__r
       bool ok = true;
       for (int d = 0; d < 3; d++) {
         double lo = fmin(T.Xt[0][d], fmin(T.Xt[1][d], T.Xt[2][d])), hi = fmax(T.Xt[0][d], fmax(T.Xt[1][d], T.Xt[2][d])); int I0 = 0, I1 = -1;
-        T.lo[d] = lo; T.hi[d] = hi;
+        T.lo[d] = lo; T.hi[d] = hi; rlo[d] = fmin(rlo[d], lo); rhi[d] = fmax(rhi[d], hi); T.rlo[d] = 0.0; T.rhi[d] = 0.0;
         ok = ok && ex::cell_range_axis(lo, hi, delta, g.amin[d], g.amax[d], g.N[d], I0, I1);
         if (ok) { T.ps[d] = g.cstart[g.cs_off[d] + I0]; T.pe[d] = g.cstart[g.cs_off[d] + I1 + 1]; } else { T.ps[d] = 0; T.pe[d] = 0; }
       }
@@ -536,6 +544,7 @@ __global__ void k_tri_records(i64 nact, ActRec *__restrict__ rec, const int *__r
       tri[o++] = T;
     }
   }
+  for (int d = 0; d < 3; d++) { tri[toff[a]].rlo[d] = rlo[d]; tri[toff[a]].rhi[d] = rhi[d]; }
 }
 // Boundary faces of CROSSING elements (process_boundary_faces!(..., false), :584).  For a crossing element every candidate of
 // process_triangle_projection! is accepted or rejected by the rho-test alone (IsProjectedOnFullSegment, :78-119) -- never by
@@ -694,6 +703,16 @@ __global__ void __launch_bounds__(TILE_VOX) k_assemble(GridDev g, int kz0, int k
           r = srec[warp][pos];
           t = 0; loaded = false;
           ntri = (FACES && r.fmask && (WANT_XP || r.cls == 1)) ? __popc((unsigned)r.fmask) * NSN : 0;      // crossing faces are folded into the pair buffer unless xp is wanted
+          if (ntri && r.cls == 1) {
+            // solid element: if even the box around all its boundary triangles is not closer than the running value, none of them can
+            // change it (same bound and margin as per triangle below) -- skip the record without touching its triangles
+            const TriRec &T0 = tri[r.tri_off];
+            double lb2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) { const double e = fmax(fmax(T0.rlo[d] - x[d], x[d] - T0.rhi[d]), 0.0); lb2 = fma(e, e, lb2); }
+            const double cv = fabs(s.c) * (1.0 + 1e-12);
+            if (lb2 * (1.0 - 1e-12) > cv * cv) ntri = 0;
+          }
         }
       }
       if (!__any_sync(0xffffffffu, ti >= 0)) break;
@@ -832,7 +851,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
         u64 *pc = ctx->counters.as<u64>() + NCTR;      // 4 words behind the statistics slots: [0],[1] pass A, [2],[3] pass B
         BoxRec *box = ctx->box_rec.as<BoxRec>(); u64 *pl = ctx->plist.as<u64>();
         CK(cudaEventRecord(ctx->ev_k[0], st));
-        k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box); LAUNCH_CHECK();
+        k_box_records<<<cdiv(nact, 128), 128, 0, st>>>(nact, ctx->act_rec.as<ActRec>(), ctx->IEN32.as<int>(), ctx->X.as<double>(), ctx->rho_n.as<double>(), ctx->ebox.as<unsigned char>(), rho_t, g, ctx->tile_faces.as<unsigned char>(), box, ctx->counters.as<u64>() + NCTR + 4); LAUNCH_CHECK();
         const int prune = ctx->knobs.proj_prune ? 1 : 0, pgrid = 148 * R2S_PL_MINB * 4;
         k_pair_scan<0><<<cdiv(nact * 32, 256), 256, 0, st>>>(nact, box, g, ctx->tile_faces.as<unsigned char>(), ctx->dist.as<double>(), prune, pl, pc, ctx->counters.as<u64>()); LAUNCH_CHECK();
         CK(cudaEventRecord(ctx->ev_k[1], st));
@@ -880,6 +899,7 @@ int r2s_dev_eval_distances(r2s_ctx *ctx, double rho_t, double delta_factor, bool
   ctx->rep.n_solid = (i64)hc[0]; ctx->rep.n_crossing = (i64)hc[1]; ctx->rep.n_active = nact; ctx->rep.n_pairs = npairs;
   ctx->rep.n_newton_iters = (i64)hc[2]; ctx->rep.n_not_converged = (i64)hc[3];
   ctx->rep.n_pairs_pruned = (i64)hc[4];
+  if (hall[NCTR + 4] != 0) FAIL("evalDistances: the grid is so much finer than the mesh that one element's candidate range exceeds 2^24 grid points");
   ctx->rep.ms_solve = ctx->rep.ms_scan = 0.0f;
   if (timed_list) {      // the read-back above synchronised the stream: the events are complete
     float t[4];

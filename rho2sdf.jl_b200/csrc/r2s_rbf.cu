@@ -553,7 +553,7 @@ struct VRec { float c[8]; float part, th_e, margin; int pad; };
 struct BisState {
   float lo, hi, th, th_prev; int nb, have_prev, done, skip; float skipf; int cur; double v, eps, target; float ev, jac; unsigned long long n_eval;
 };
-__global__ void k_bis_begin(BisState *S, u64 *acc) {
+__device__ __forceinline__ void bis_begin(BisState *S, u64 *acc) {
   if (S->done) { S->skip = 1; S->skipf = 1.0f; return; }
   const float th = (S->lo + S->hi) / 2;
   S->th = th;
@@ -561,7 +561,7 @@ __global__ void k_bis_begin(BisState *S, u64 *acc) {
   S->skip = skip; S->skipf = skip ? 1.0f : 0.0f;
   if (!skip) { acc[0] = 0; acc[1] = 0; acc[2] = 0; acc[4 + (1 - S->cur)] = 0; }
 }
-__global__ void k_bis_end(BisState *S, const u64 *acc, const u64 *red) {      // LS_Threshold's loop body after the volume (RBFs4Smoothing.jl:286-296)
+__device__ __forceinline__ void bis_end(BisState *S, const u64 *acc, const u64 *red) {      // LS_Threshold's loop body after the volume (RBFs4Smoothing.jl:286-296)
   if (S->done) return;
   if (!S->skip) {
     S->v = (double)red[0] * (double)S->ev + ((double)red[2] / 137438953472.0 /* 2^37 */) * (double)S->jac;
@@ -681,9 +681,16 @@ __global__ void __launch_bounds__(128) k_vl_eval(const BisState *__restrict__ S,
   if (lane == 0 && local) atomicAdd(&acc[2], local);
 }
 // acc -> red for the cross-rank sum: [0] full + permanently full, [1] 1 if this rank's cut list overflowed, [2] cut sum
-__global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red, const BisState *S) {
+__device__ __forceinline__ void vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red, const BisState *S) {
   if (S && S->skip) return;
   red[0] = acc[0] + acc[3]; red[1] = acc[1] > (u64)cutcap ? 1 : 0; red[2] = acc[2]; red[3] = 0;
+}
+__global__ void k_vol_pack(const u64 *__restrict__ acc, int cutcap, u64 *__restrict__ red, const BisState *S) { vol_pack(acc, cutcap, red, S); }
+// the one-thread kernels between two bisection steps, fused: what = 1 begin, 2 end, 4 pack (pack -> [all-reduce] -> end -> begin of the next step)
+__global__ void k_bis_turn(BisState *S, u64 *acc, u64 *red, int what) {
+  if (what & 4) vol_pack(acc, 0x7fffffff, red, S);
+  if (what & 2) bis_end(S, acc, red);
+  if (what & 1) bis_begin(S, acc);
 }
 // state of one LS_Threshold search (see k_vol_step)
 struct VolBisect {
@@ -746,7 +753,7 @@ static int vol_bisect_step(r2s_ctx *ctx, VolBisect &vb, float lo, float hi, floa
   FAIL("LS_Threshold: cut-cell list overflow");
 }
 // Steps 4 .. 40 on the device: 16-byte active entries, records with cached quadratures for the cells that get cut (k_vl_step / k_vl_eval), the
-// bracket update in k_bis_end.  Everything is enqueued at once; the host reads the final state back.  h = state after step 3.
+// bracket update in k_bis_turn.  Everything is enqueued at once; the host reads the final state back.  h = state after step 3.
 static int vol_bisect_finish(r2s_ctx *ctx, VolBisect &vb, float &lo, float &hi, float &th, double &v, double &eps, int &nb, float th_prev, double target) {
   cudaStream_t st = ctx->stream;
   static const GaussF G9 = gauss9f();
@@ -761,13 +768,18 @@ static int vol_bisect_finish(r2s_ctx *ctx, VolBisect &vb, float &lo, float &hi, 
   const int grid = (int)std::min<i64>(std::max<i64>(cdiv(vb.n_cur, 256), 1), 148 * 8);
   u64 *red = vb.acc + 8;
   ctx->skip_flag = &S->skipf;      // the peer-memory all-reduce of a skipped step skips itself (same flag value on every rank)
+  const bool single = ctx->nranks == 1;
+  k_bis_turn<<<1, 1, 0, st>>>(S, vb.acc, red, 1); LAUNCH_CHECK();
   for (int step = nb; step < 40; step++) {
-    k_bis_begin<<<1, 1, 0, st>>>(S, vb.acc); LAUNCH_CHECK();
+    const int next = step + 1 < 40 ? 1 : 0;
     k_vl_step<<<grid, 256, 0, st>>>(S, ctx->vent[0].as<VAct>(), ctx->vent[1].as<VAct>(), vb.n_cur + 1, ctx->knobs.vol_cache, vb.acc, ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.n_cur + 1); LAUNCH_CHECK();
     k_vl_eval<<<148 * 16, 128, 0, st>>>(S, ctx->vrec.as<VRec>(), ctx->vlist[1].as<int2>(), vb.nx, vb.ny, vb.px, vb.sdf, G9, vb.acc); LAUNCH_CHECK();
-    k_vol_pack<<<1, 1, 0, st>>>(vb.acc, 0x7fffffff, red, S); LAUNCH_CHECK();
-    if (r2s_allreduce(ctx, red, 4, 1)) { ctx->skip_flag = nullptr; return 1; }
-    k_bis_end<<<1, 1, 0, st>>>(S, vb.acc, red); LAUNCH_CHECK();
+    if (single) { k_bis_turn<<<1, 1, 0, st>>>(S, vb.acc, red, 4 | 2 | next); LAUNCH_CHECK(); }
+    else {
+      k_bis_turn<<<1, 1, 0, st>>>(S, vb.acc, red, 4); LAUNCH_CHECK();
+      if (r2s_allreduce(ctx, red, 4, 1)) { ctx->skip_flag = nullptr; return 1; }
+      k_bis_turn<<<1, 1, 0, st>>>(S, vb.acc, red, 2 | next); LAUNCH_CHECK();
+    }
   }
   ctx->skip_flag = nullptr;
   if (r2s_readback(ctx, &h, S, sizeof(h))) return 1;
