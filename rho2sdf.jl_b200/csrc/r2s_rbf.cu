@@ -46,7 +46,7 @@ __global__ void k_replace_far(i64 n, float *__restrict__ s, const unsigned *__re
 struct StencilW { float w[8]; };
 // The CTA that finishes LAST adds up the per-CTA partial sums (fixed order: 256 strided sums, then slot 0..255 sequentially -- the same
 // order whatever CTA happens to be last, so the result is deterministic) and stores the total: no separate reduction launch.
-// Call with all 256 threads of the CTA after thread 0 has written partial[this CTA].
+// Call with all threads of the CTA after thread 0 has written partial[this CTA].
 // F.enabled (several GPUs, peer-memory transport): the CTAs have also stored halo values into the neighbours' arrays, so the fence before
 // the ticket is system-wide, and the last CTA all-reduces the total over the ranks through the mailbox itself (p2p_allreduce_cta).
 __device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks, unsigned *ticket, double *dst, const P2PFuse &F) {
@@ -57,8 +57,11 @@ __device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks,
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  double a = 0; for (int i = tid; i < nblocks; i += 256) a += __ldcg(&partial[i]);
-  s_sum[tid] = a; __syncthreads();
+  for (int v = tid; v < 256; v += (int)blockDim.x) {      // 256 strided sums whatever the block size
+    double a = 0; for (int i = v; i < nblocks; i += 256) a += __ldcg(&partial[i]);
+    s_sum[v] = a;
+  }
+  __syncthreads();
   __shared__ double s_tot;
   if (tid == 0) { double t = 0; for (int i = 0; i < 256; i++) t += s_sum[i]; s_tot = t; *ticket = 0; }
   __syncthreads();
@@ -93,36 +96,49 @@ __device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks,
 #define S3_SLOT 3200       // stage stride in shared memory (= tile bytes, a multiple of 128: destinations are 128-byte aligned)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// bar / dst are shared-window addresses (smem_u32), taken once per kernel: the generic -> shared conversion per use was 5 % of the stencil kernel's instructions
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(c0),
-               "r"(c1), "r"(c2), "r"(smem_u32(bar))
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(bar)
                : "memory");
 }
-template <bool BETA>
-__global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nx, int ny, int nz, int px,
-                                                       int kz0, int kz1, int zc, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
-                                                       double *__restrict__ partial, StencilW W, unsigned *__restrict__ ticket, double *__restrict__ dot_out, const P2PFuse F) {
-  constexpr int TX = S3_TX, TY = S3_TY, NT = TX * TY, NARR = BETA ? 2 : 1;
+// packed FP32 FMA (FFMA2 on sm_100a): IEEE fma per half, i.e. the same bits as two scalar FMAs, in ONE issue slot.  tools/probes/ffma2_probe.cu:
+// the same flop rate as FFMA (72.9 vs 71.7 TFLOP/s) -- it helps kernels that are bound by instruction issue (k_fine_eval2: 6.97 -> 5.73 ms),
+// not the stencil (LDS / barrier bound: no change measured)
+#ifndef R2S_F32X2
+#define R2S_F32X2 1
+#endif
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long xa = *reinterpret_cast<unsigned long long *>(&a), xb = *reinterpret_cast<unsigned long long *>(&b), xc = *reinterpret_cast<unsigned long long *>(&c), r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(xa), "l"(xb), "l"(xc));
+  return *reinterpret_cast<float2 *>(&r);
+}
+#ifndef R2S_ST_NO
+#define R2S_ST_NO 4        // x-adjacent outputs per thread of the stencil kernel (2 or 4): 4 = 128 threads per CTA, 40 B of shared-memory loads per output instead of 60
+#endif
+template <bool BETA, int NO>
+__global__ void __launch_bounds__(16 * S3_X / NO) k_stencil81_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nx, int ny, int nz, int px,
+                                                                   int kz0, int kz1, int zc, float *__restrict__ unew, const float *__restrict__ scal, float *__restrict__ out,
+                                                                   double *__restrict__ partial, StencilW W, unsigned *__restrict__ ticket, double *__restrict__ dot_out, const P2PFuse F) {
+  static_assert(NO == 2 || NO == 4, "outputs per thread");
+  constexpr int TX = S3_TX, TY = S3_TY, NT = TX * TY, NARR = BETA ? 2 : 1, NTHR = 16 * S3_X / NO, NV = NO + 4;
   if (BETA && scal[5] != 0.0f) return;      // CG has converged: the iterations launched ahead of the host's check are no-ops
   __shared__ __align__(128) unsigned char stage[S3_NST * NARR * S3_SLOT];
-  __shared__ __align__(16) float comb[BETA ? 2 : 1][BETA ? NT : 2];      // combined plane r + beta * u (double buffered), CG form only
+  __shared__ __align__(16) float comb[BETA ? 2 : 1][BETA ? NT : 4];      // combined plane r + beta * u (double buffered), CG form only
   __shared__ __align__(8) unsigned long long full[S3_NST];
   __shared__ double red[8];
-  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int tid = threadIdx.x, tx = tid % (S3_X / NO), ty = tid / (S3_X / NO);
   const int bx = blockIdx.x * S3_X, by = blockIdx.y * S3_Y;
   const int zc0 = kz0 + blockIdx.z * zc, zc1 = min(zc0 + zc, kz1);      // zc output planes per CTA (chosen by the host so that the chunks are even)
   const int np = zc1 - zc0 + 4;                                           // input planes zc0 - 2 .. zc1 + 1
-  const int gx = bx + 2 * tx, gy = by + ty;
-  const bool in0 = gx < nx && gy < ny, in1 = gx + 1 < nx && gy < ny;
+  const int gx = bx + NO * tx, gy = by + ty;
+  bool in[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) in[o] = gx + o < nx && gy < ny;
   float beta = 0.0f;
   if (BETA) beta = scal[0];
   if (tid == 0) {
@@ -131,91 +147,122 @@ __global__ void __launch_bounds__(256) k_stencil81_tma(const __grid_constant__ C
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const unsigned stage_a = smem_u32(stage), full_a = smem_u32(full);
   auto issue = [&](int p) {      // thread 0: plane p of this CTA's march into stage p % NST
     const int st = p % S3_NST;
-    mbar_expect_tx(&full[st], S3_TILE_BYTES * NARR);
-    tma_load_3d(stage + (st * NARR) * S3_SLOT, &mapA, bx - S3_HX, by - 2, zc0 - 2 + p, &full[st]);
-    if (BETA) tma_load_3d(stage + (st * NARR + 1) * S3_SLOT, &mapB, bx - S3_HX, by - 2, zc0 - 2 + p, &full[st]);
+    mbar_expect_tx(full_a + 8 * st, S3_TILE_BYTES * NARR);
+    tma_load_3d(stage_a + (st * NARR) * S3_SLOT, &mapA, bx - S3_HX, by - 2, zc0 - 2 + p, full_a + 8 * st);
+    if (BETA) tma_load_3d(stage_a + (st * NARR + 1) * S3_SLOT, &mapB, bx - S3_HX, by - 2, zc0 - 2 + p, full_a + 8 * st);
   };
   if (tid == 0) for (int p = 0; p < S3_NST - 1 && p < np; p++) issue(p);
-  // elements of the tile this thread combines per plane (CG form): interior ones are also written back to u_new
-  constexpr int NE = (NT + 255) / 256;
-  int e_ok[NE]; i64 e_off[NE];
-  if (BETA) {
+  // CG form: the threads combine the tile float4 by float4 (16-byte shared loads / stores); a float4 of the tile interior is also written
+  // back to u_new with one 16-byte store (x is a multiple of 4, the row pitch too; values beyond nx are the TMA's zero fill and land in
+  // the zero pad columns)
+  static_assert(NT % 4 == 0 && S3_TX % 4 == 0 && S3_HX % 4 == 0, "float4 combine");
+  constexpr int NC = (NT / 4 + NTHR - 1) / NTHR;
+  bool c_act[NC], c_int[NC]; i64 c_off[NC];
 #pragma unroll
-    for (int q = 0; q < NE; q++) {
-      const int t = tid + q * 256, ly = t / TX, lx = t % TX, x = bx + lx - S3_HX, y = by + ly - 2;
-      e_ok[q] = (t < NT ? 1 : 0) | ((t < NT && lx >= S3_HX && lx < TX - S3_HX && ly >= 2 && ly < TY - 2 && x < nx && y < ny) ? 2 : 0);
-      e_off[q] = (i64)y * px + x;
+  for (int q = 0; q < NC; q++) {
+    c_act[q] = false; c_int[q] = false; c_off[q] = 0;
+    if (BETA) {
+      const int t4 = tid + q * NTHR, t = 4 * t4, ly = t / TX, lx = t % TX, x = bx + lx - S3_HX, y = by + ly - 2;
+      c_act[q] = t4 < NT / 4;
+      c_int[q] = c_act[q] && lx >= S3_HX && lx < TX - S3_HX && ly >= 2 && ly < TY - 2 && x < nx && y < ny;
+      c_off[q] = (i64)y * px + x;
     }
   }
   const i64 pl = (i64)px * ny;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f;
-  float ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f;
+  float acc[5][NO], ctr0[NO], ctr1[NO];      // acc[q][o]: output plane (current input plane - 2 + q) of column o; ctr: centre values (= u) of the two planes before
+#pragma unroll
+  for (int o = 0; o < NO; o++) { ctr0[o] = ctr1[o] = 0.f; for (int q = 0; q < 5; q++) acc[q][o] = 0.f; }
   double dsum = 0.0;
   for (int p = 0; p < np; p++) {
     const int st = p % S3_NST, zin = zc0 - 2 + p;
     // the stage that plane p + NST - 1 goes into was read during iteration p - 1; everybody has passed that iteration's barrier
     if (tid == 0 && p + S3_NST - 1 < np) issue(p + S3_NST - 1);
-    mbar_wait(&full[st], (unsigned)((p / S3_NST) & 1));
+    mbar_wait(full_a + 8 * st, (unsigned)((p / S3_NST) & 1));
     const float *tile;
     if (BETA) {
       const float *tr = reinterpret_cast<const float *>(stage + (st * NARR) * S3_SLOT), *tu = reinterpret_cast<const float *>(stage + (st * NARR + 1) * S3_SLOT);
       float *cb = comb[p & 1];
 #pragma unroll
-      for (int q = 0; q < NE; q++)
-        if (e_ok[q] & 1) {
-          const int t = tid + q * 256;
-          const float v = tr[t] + beta * tu[t];
-          cb[t] = v;
-          if ((e_ok[q] & 2) && zin >= zc0 && zin < zc1) unew[(i64)zin * pl + e_off[q]] = v;
+      for (int q = 0; q < NC; q++)
+        if (c_act[q]) {
+          const int t4 = tid + q * NTHR;
+          const float4 a = reinterpret_cast<const float4 *>(tr)[t4], b = reinterpret_cast<const float4 *>(tu)[t4];
+          float4 v; v.x = a.x + beta * b.x; v.y = a.y + beta * b.y; v.z = a.z + beta * b.z; v.w = a.w + beta * b.w;
+          reinterpret_cast<float4 *>(cb)[t4] = v;
+          if (c_int[q] && zin >= zc0 && zin < zc1) *reinterpret_cast<float4 *>(unew + (i64)zin * pl + c_off[q]) = v;
         }
       __syncthreads();      // comb[p & 1] complete; also: every thread is done with the raw stage of plane p and with comb[(p + 1) & 1] of plane p - 1
       tile = cb;
     } else {
       tile = reinterpret_cast<const float *>(stage + st * S3_SLOT);
     }
-    float ctra = 0.f, ctrb = 0.f;
-    float s9a = 0.f, s9b = 0.f, s12a = 0.f, s12b = 0.f;
+    float ctr[NO], s9[NO], s12[NO];
+#pragma unroll
+    for (int o = 0; o < NO; o++) { ctr[o] = 0.f; s9[o] = 0.f; s12[o] = 0.f; }
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++) {
-      const float2 *row = reinterpret_cast<const float2 *>(tile + (ty + 2 + dj) * TX + 2 * tx + (S3_HX - 2));
-      const float2 p0 = row[0], p1 = row[1], p2 = row[2];
-      const float v[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};       // x0-2 .. x0+3
-      if (dj == 0) { ctra = v[2]; ctrb = v[3]; }
+      const float *rowp = tile + (ty + 2 + dj) * TX + NO * tx + (S3_HX - 2);      // x0 - 2 .. x0 + NO + 1
+      float v[NV];
+      if (NO == 2) {
+        const float2 *row = reinterpret_cast<const float2 *>(rowp);
+        const float2 p0 = row[0], p1 = row[1], p2 = row[2];
+        v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y;
+      } else {       // 8 + 16 + 8 bytes: the middle four values are 16-byte aligned
+        const float2 p0 = *reinterpret_cast<const float2 *>(rowp), p2 = *reinterpret_cast<const float2 *>(rowp + 6); const float4 p1 = *reinterpret_cast<const float4 *>(rowp + 2);
+        v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p1.z; v[5] = p1.w; v[NV - 2] = p2.x; v[NV - 1] = p2.y;
+      }
+      if (dj == 0) {
+#pragma unroll
+        for (int o = 0; o < NO; o++) ctr[o] = v[2 + o];
+      }
 #pragma unroll
       for (int di = -2; di <= 2; di++) {
         const int m2 = di * di + dj * dj;
         if (m2 > 6) continue;
-        const float va = v[di + 2], vb = v[di + 3];
-        if (m2 <= 2) { s9a = fmaf(W.w[m2], va, s9a); s9b = fmaf(W.w[m2], vb, s9b); }
-        else { s12a = fmaf(W.w[m2], va, s12a); s12b = fmaf(W.w[m2], vb, s12b); }
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+          if (m2 <= 2) s9[o] = fmaf(W.w[m2], v[di + 2 + o], s9[o]); else s12[o] = fmaf(W.w[m2], v[di + 2 + o], s12[o]);
+        }
       }
     }
     {
-      const float e1 = W.w[1], e4 = W.w[4], s21a = s9a + s12a, s21b = s9b + s12b;
-      a2 += s21a; a1 = fmaf(e1, s21a, a1); a3 = fmaf(e1, s21a, a3); a0 = fmaf(e4, s9a, a0); a4 = fmaf(e4, s9a, a4);
-      b2 += s21b; b1 = fmaf(e1, s21b, b1); b3 = fmaf(e1, s21b, b3); b0 = fmaf(e4, s9b, b0); b4 = fmaf(e4, s9b, b4);
+      const float e1 = W.w[1], e4 = W.w[4];
+#pragma unroll
+      for (int o = 0; o < NO; o++) {
+        const float s21 = s9[o] + s12[o];
+        acc[2][o] += s21; acc[1][o] = fmaf(e1, s21, acc[1][o]); acc[3][o] = fmaf(e1, s21, acc[3][o]); acc[0][o] = fmaf(e4, s9[o], acc[0][o]); acc[4][o] = fmaf(e4, s9[o], acc[4][o]);
+      }
     }
     const int zo = zin - 2;
     if (zo >= zc0) {
       const i64 gi = (i64)zo * pl + (i64)gy * px + gx;
-      if (in0) { out[gi] = a0; dsum += (double)ca0 * (double)a0; }
-      if (in1) { out[gi + 1] = b0; dsum += (double)cb0 * (double)b0; }
+      if (NO == 4 && in[NO - 1]) *reinterpret_cast<float4 *>(out + gi) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][NO - 1]);      // gx and the row pitch are multiples of 4
+#pragma unroll
+      for (int o = 0; o < NO; o++)
+        if (in[o]) { if (!(NO == 4 && in[NO - 1])) out[gi + o] = acc[0][o]; dsum += (double)ctr0[o] * (double)acc[0][o]; }
       if (BETA && F.enabled) {      // fused halo exchange: my boundary planes of c go straight into the neighbours' arrays over NVLink
-        if (gi >= F.lo0 && gi < F.lo1) { if (in0) F.c_lower[gi] = a0; if (in1) F.c_lower[gi + 1] = b0; }
-        if (gi >= F.hi0 && gi < F.hi1) { if (in0) F.c_upper[gi] = a0; if (in1) F.c_upper[gi + 1] = b0; }
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+          if (gi >= F.lo0 && gi < F.lo1 && in[o]) F.c_lower[gi + o] = acc[0][o];
+          if (gi >= F.hi0 && gi < F.hi1 && in[o]) F.c_upper[gi + o] = acc[0][o];
+        }
       }
     }
-    a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f; b0 = b1; b1 = b2; b2 = b3; b3 = b4; b4 = 0.f;
-    ca0 = ca1; ca1 = ctra; cb0 = cb1; cb1 = ctrb;
+#pragma unroll
+    for (int o = 0; o < NO; o++) {
+      acc[0][o] = acc[1][o]; acc[1][o] = acc[2][o]; acc[2][o] = acc[3][o]; acc[3][o] = acc[4][o]; acc[4][o] = 0.f;
+      ctr0[o] = ctr1[o]; ctr1[o] = ctr[o];
+    }
     if (!BETA) __syncthreads();      // the stage of plane p may be overwritten by the load issued at the top of the next iteration
   }
   for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
   if ((tid & 31) == 0) red[tid >> 5] = dsum;
   __syncthreads();
   if (tid == 0) {
-    double a = 0; for (int i = 0; i < 8; i++) a += red[i];
+    double a = 0; for (int i = 0; i < NTHR / 32; i++) a += red[i];
     partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
   }
   if (ticket && cta_sum_last(partial, (int)(gridDim.x * gridDim.y * gridDim.z), ticket, dot_out, F) && F.enabled && tid == 0)
@@ -834,7 +881,7 @@ __global__ void __launch_bounds__(FN_X *FN_Y *FN_Z) k_fine_eval(int nx, int ny, 
 // constant-bank operand; taps that are outside the largest supported radius (|d|^2 > 8) are pruned at compile time.
 // Per 6-value x-row loaded from shared memory up to 48 FMAs are issued (FMA-bound, not LDS-bound).  Accumulation order per
 // output is dk, dj, di ascending -- the same as k_fine_eval<2> -- so both kernels give bit-identical results.
-__constant__ float c_w2[2][2][6][6][2][6];          // [pz][py][dk+2][dj+2][px][di+2]
+__constant__ float c_w2[2][2][6][6][6][2];          // [pz][py][dk+2][dj+2][di+2][px]: the two x-phases of a tap are adjacent (one 8-byte constant operand of FFMA2)
 #define F2_X 32
 #define F2_Y 4
 #define F2_Z 8            // coarse cells per block along z (2 per thread)
@@ -847,8 +894,15 @@ template <int PZ, int PY, int DK, int DJ>
 __device__ __forceinline__ void f2_row(const float row[6], float &acc0, float &acc1) {
 #pragma unroll
   for (int di = -2; di <= 3; di++) {
-    if (f2_tap_possible(0, PY, PZ, di, DJ, DK)) acc0 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][0][di + 2], row[di + 2], acc0);
-    if (f2_tap_possible(1, PY, PZ, di, DJ, DK)) acc1 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][1][di + 2], row[di + 2], acc1);
+#if R2S_F32X2
+    if (f2_tap_possible(0, PY, PZ, di, DJ, DK) && f2_tap_possible(1, PY, PZ, di, DJ, DK)) {      // both x-phases take this value: one packed FMA (same bits as two scalar ones)
+      const float2 t = ffma2(make_float2(c_w2[PZ][PY][DK + 2][DJ + 2][di + 2][0], c_w2[PZ][PY][DK + 2][DJ + 2][di + 2][1]), make_float2(row[di + 2], row[di + 2]), make_float2(acc0, acc1));
+      acc0 = t.x; acc1 = t.y;
+      continue;
+    }
+#endif
+    if (f2_tap_possible(0, PY, PZ, di, DJ, DK)) acc0 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][di + 2][0], row[di + 2], acc0);
+    if (f2_tap_possible(1, PY, PZ, di, DJ, DK)) acc1 = fmaf(c_w2[PZ][PY][DK + 2][DJ + 2][di + 2][1], row[di + 2], acc1);
   }
 }
 template <int DK, int DJ>
@@ -945,12 +999,12 @@ static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
     T.n[ph] = n;
   }
   if (sm == 2) {      // dense per-phase weight table of k_fine_eval2 (same inclusion test, zero = excluded)
-    static float W2[2][2][6][6][2][6];
+    static float W2[2][2][6][6][6][2];
     for (int pz = 0; pz < 2; pz++) for (int py = 0; py < 2; py++) for (int dk = -2; dk <= 3; dk++) for (int dj = -2; dj <= 3; dj++)
       for (int px = 0; px < 2; px++) for (int di = -2; di <= 3; di++) {
         double ox = di - 0.5 * px, oy = dj - 0.5 * py, oz = dk - 0.5 * pz, m = ox * ox + oy * oy + oz * oz;
         float dist = (float)(sqrt(m) * cell);
-        W2[pz][py][dk + 2][dj + 2][px][di + 2] = (dist <= maxd) ? (float)exp(-m) : 0.0f;
+        W2[pz][py][dk + 2][dj + 2][di + 2][px] = (dist <= maxd) ? (float)exp(-m) : 0.0f;
       }
     CK(cudaMemcpyToSymbolAsync(c_w2, W2, sizeof(W2), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -996,7 +1050,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   // mat-vec kernel: plane marching, two outputs per thread, factorised weights; even z-chunks of about 64 planes (a 65-plane slab is one chunk, not 64 + 1)
   const int nchunk = std::max(1, (k1 - k0 + 32) / 64), zc = cdiv(k1 - k0, nchunk);
   dim3 sgrid(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc));
-  const int sthreads = 256;
+  const int sthreads = 16 * S3_X / R2S_ST_NO;
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
   double *part = ctx->f_part.as<double>();
@@ -1044,7 +1098,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
         // halo flags; the update waits for the neighbours' flags, its last CTA all-reduces |r|^2 and closes the iteration.
         P2PFuse fs, fu;
         if (r2s_p2p_fuse_params(ctx, &fs, &fu, pl, k0, k1, 2)) return 1;
-        k_stencil81_tma<true><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W, tick, dsc + 1, fs);
+        k_stencil81_tma<true, R2S_ST_NO><<<sgrid, sthreads, 0, st>>>(tm_r, tm_u[upar], nx, ny, nz, px, k0, k1, zc, u_new, scal, c, part, W, tick, dsc + 1, fs);
         LAUNCH_CHECK();
         if (nh_lo + nh_hi > 0) { k_unew_halo<<<cdiv(nh_lo + nh_hi, 256), 256, 0, st>>>(nh_lo, (i64)(k1 - e0) * pl, nh_hi, scal, r + x_lo, u_old + x_lo, u_new + x_lo); LAUNCH_CHECK(); }
         if (probe) CK(cudaEventRecord(ctx->ev_probe[1], st));
@@ -1081,7 +1135,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   {
     CUtensorMap tm_w;
     if (stencil_tensor_map(ctx, &tm_w, wgt, nx, ny, nz, px)) return 1;
-    { P2PFuse f0; memset(&f0, 0, sizeof(f0)); k_stencil81_tma<false><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W, nullptr, nullptr, f0); }
+    { P2PFuse f0; memset(&f0, 0, sizeof(f0)); k_stencil81_tma<false, R2S_ST_NO><<<sgrid, sthreads, 0, st>>>(tm_w, tm_w, nx, ny, nz, px, k0, k1, zc, nullptr, nullptr, lsf, part, W, nullptr, nullptr, f0); }
   }
   LAUNCH_CHECK();
   if (r2s_halo_exchange_f32(ctx, lsf, pl, k0, k1, nz, 0, 1)) return 1;      // cells of my top plane need plane k1
