@@ -314,10 +314,10 @@ def run_gpu(args):
         barrier()
         wall_e2e = (time.perf_counter() - w0) * 1e3
         ms_e2e = max(f0.elapsed_time(f1), 0.0)
-        # ---- optional: the same K steps through the pipelined host-buffer calls (two buffer sets; the downloads of step k drain
-        # while step k+1 computes).  Opt-in until it has been validated on a GPU (tests: R2S_TEST_OPTIN=1).
+        # ---- extra: the same K steps through the pipelined host-buffer calls (two buffer sets; the downloads of step k drain
+        # while step k+1 computes): the throughput of a batch of density fields.  Reported as "e2e_pipelined" beside the per-call "e2e".
         ms_pipe = None
-        if args.pipelined_e2e:
+        if args.pipelined_e2e and not args.no_pipelined_e2e and world == 1:      # (single GPU only: the multi-rank runs keep to the per-call API)
             h_sdf2 = torch.empty(n_sdf_local, dtype=torch.float64).pin_memory()
             h_fine2 = torch.empty(n_fine_local, dtype=torch.float32).pin_memory()
             bufs = [(h_sdf, h_fine), (h_sdf2, h_fine2)]
@@ -447,7 +447,8 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="elements per axis of the synthetic HEX8 SIMP field")
     ap.add_argument("--cpu-n", type=int, default=96, help="replica size for the CPU oracle leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipelined-e2e", action="store_true", help="also time the pipelined host-buffer calls (r2s_pipeline_slab_begin/_wait); opt-in")
+    ap.add_argument("--pipelined-e2e", action="store_true", default=True, help="also time the pipelined host-buffer calls (r2s_pipeline_slab_begin/_wait) -> e2e_pipelined (default)")
+    ap.add_argument("--no-pipelined-e2e", action="store_true", help="skip the pipelined host-buffer leg")
     ap.add_argument("--no-balance", action="store_true", help="keep equal plane counts per slab (no cost-based re-cut during warm-up)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -266,11 +266,14 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 // one warp per active element; lanes stride over its candidate points.  plist entry: bit 63 = goes to the pair buffer, bits 24..62 =
 // active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
 #define PL_LI_BITS 24
+#ifndef R2S_SCAN_MINB
+#define R2S_SCAN_MINB 2
+#endif
 #ifndef R2S_PL_MINB
 #define R2S_PL_MINB 4      // resident CTAs per SM the projection kernel is compiled for: 4 = 128 registers (solve 36.1 ms), 5 = 96 registers with spills (37.5), 3 = 167 registers (42.3); tools/gpu_ab_libs.sh
 #endif
 template <int PASS>
-__global__ void __launch_bounds__(256) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
+__global__ void __launch_bounds__(256, R2S_SCAN_MINB) k_pair_scan(i64 nact, const BoxRec *__restrict__ box, GridDev g, const unsigned char *__restrict__ tile_faces, const double *__restrict__ dist,
                                                    int prune, u64 *__restrict__ plist, u64 *__restrict__ cnt, u64 *__restrict__ stats) {
   const i64 a = (blockIdx.x * (i64)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
   if (a >= nact) return;

@@ -91,7 +91,9 @@ __device__ __forceinline__ bool cta_sum_last(const double *partial, int nblocks,
                            // a box starting at bx - 2 raises "illegal instruction" on B200 (tools/probes/tma_probe.cu), bx - 4 is fine
 #define S3_TX (S3_X + 2 * S3_HX)   // 40 x 20 tile; 40 floats = 160 B per row (a multiple of 16 B, as the TMA box requires)
 #define S3_TY (S3_Y + 4)
+#ifndef S3_NST
 #define S3_NST 4           // TMA stages: loads run 3 planes ahead of the compute
+#endif
 #define S3_TILE_BYTES (S3_TX * S3_TY * 4)
 #define S3_SLOT 3200       // stage stride in shared memory (= tile bytes, a multiple of 128: destinations are 128-byte aligned)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -135,10 +137,14 @@ __global__ void __launch_bounds__(16 * S3_X / NO) k_stencil81_tma(const __grid_c
   const int bx = blockIdx.x * S3_X, by = blockIdx.y * S3_Y;
   const int zc0 = kz0 + blockIdx.z * zc, zc1 = min(zc0 + zc, kz1);      // zc output planes per CTA (chosen by the host so that the chunks are even)
   const int np = zc1 - zc0 + 4;                                           // input planes zc0 - 2 .. zc1 + 1
-  const int gx = bx + NO * tx, gy = by + ty;
+  // NO == 4: the CTA's outputs are the columns [bx - 2, bx + 30), so that the eight values a thread needs per row (x0 - 2 .. x0 + 5) are two
+  // ALIGNED 16-byte shared-memory loads (tile column 4 tx .. 4 tx + 7) -- the kernel is bound by shared-memory wavefronts (ncu: l1tex 87 %),
+  // and an unaligned 8 + 16 + 8 byte split costs 12 wavefronts per warp and row instead of 8.  The grid has cdiv(nx + 2, 32) columns.
+  constexpr int XS = NO == 4 ? 2 : 0;
+  const int gx = bx - XS + NO * tx, gy = by + ty;
   bool in[NO];
 #pragma unroll
-  for (int o = 0; o < NO; o++) in[o] = gx + o < nx && gy < ny;
+  for (int o = 0; o < NO; o++) in[o] = gx + o >= 0 && gx + o < nx && gy < ny;
   float beta = 0.0f;
   if (BETA) beta = scal[0];
   if (tid == 0) {
@@ -204,15 +210,15 @@ __global__ void __launch_bounds__(16 * S3_X / NO) k_stencil81_tma(const __grid_c
     for (int o = 0; o < NO; o++) { ctr[o] = 0.f; s9[o] = 0.f; s12[o] = 0.f; }
 #pragma unroll
     for (int dj = -2; dj <= 2; dj++) {
-      const float *rowp = tile + (ty + 2 + dj) * TX + NO * tx + (S3_HX - 2);      // x0 - 2 .. x0 + NO + 1
+      const float *rowp = tile + (ty + 2 + dj) * TX + NO * tx + (S3_HX - 2 - XS);      // x0 - 2 .. x0 + NO + 1
       float v[NV];
       if (NO == 2) {
         const float2 *row = reinterpret_cast<const float2 *>(rowp);
         const float2 p0 = row[0], p1 = row[1], p2 = row[2];
         v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y;
-      } else {       // 8 + 16 + 8 bytes: the middle four values are 16-byte aligned
-        const float2 p0 = *reinterpret_cast<const float2 *>(rowp), p2 = *reinterpret_cast<const float2 *>(rowp + 6); const float4 p1 = *reinterpret_cast<const float4 *>(rowp + 2);
-        v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p1.z; v[5] = p1.w; v[NV - 2] = p2.x; v[NV - 1] = p2.y;
+      } else {
+        const float4 p0 = *reinterpret_cast<const float4 *>(rowp), p1 = *reinterpret_cast<const float4 *>(rowp + 4);
+        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[NV - 4] = p1.x; v[NV - 3] = p1.y; v[NV - 2] = p1.z; v[NV - 1] = p1.w;
       }
       if (dj == 0) {
 #pragma unroll
@@ -239,10 +245,11 @@ __global__ void __launch_bounds__(16 * S3_X / NO) k_stencil81_tma(const __grid_c
     const int zo = zin - 2;
     if (zo >= zc0) {
       const i64 gi = (i64)zo * pl + (i64)gy * px + gx;
-      if (NO == 4 && in[NO - 1]) *reinterpret_cast<float4 *>(out + gi) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][NO - 1]);      // gx and the row pitch are multiples of 4
+      const bool vec = NO == 4 && in[0] && in[NO - 1];      // gx is even and the row pitch a multiple of 4: 8-byte stores
+      if (vec) { *reinterpret_cast<float2 *>(out + gi) = make_float2(acc[0][0], acc[0][1]); *reinterpret_cast<float2 *>(out + gi + 2) = make_float2(acc[0][2], acc[0][NO - 1]); }
 #pragma unroll
       for (int o = 0; o < NO; o++)
-        if (in[o]) { if (!(NO == 4 && in[NO - 1])) out[gi + o] = acc[0][o]; dsum += (double)ctr0[o] * (double)acc[0][o]; }
+        if (in[o]) { if (!vec) out[gi + o] = acc[0][o]; dsum += (double)ctr0[o] * (double)acc[0][o]; }
       if (BETA && F.enabled) {      // fused halo exchange: my boundary planes of c go straight into the neighbours' arrays over NVLink
 #pragma unroll
         for (int o = 0; o < NO; o++) {
@@ -1049,7 +1056,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
   CK(cudaEventRecord(ctx->ev[5], st));
   // mat-vec kernel: plane marching, two outputs per thread, factorised weights; even z-chunks of about 64 planes (a 65-plane slab is one chunk, not 64 + 1)
   const int nchunk = std::max(1, (k1 - k0 + 32) / 64), zc = cdiv(k1 - k0, nchunk);
-  dim3 sgrid(cdiv(nx, S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc));
+  dim3 sgrid(cdiv(nx + (R2S_ST_NO == 4 ? 2 : 0), S3_X), cdiv(ny, S3_Y), cdiv(k1 - k0, zc));
   const int sthreads = 16 * S3_X / R2S_ST_NO;
   int nsb = (int)(sgrid.x * sgrid.y * sgrid.z), nub = (int)std::min<i64>(cdiv(next, 256), CG_BLOCKS);
   CK(ctx->f_part.reserve(sizeof(double) * (size_t)(nsb > nub ? nsb : nub)));
