@@ -267,7 +267,7 @@ __global__ void k_box_records(i64 nact, const ActRec *__restrict__ rec, const in
 // active-element index, bits 0..23 = local point index.  cnt[0] = list length, cnt[1] = pairs pruned (statistics).
 #define PL_LI_BITS 24
 #ifndef R2S_SCAN_MINB
-#define R2S_SCAN_MINB 2
+#define R2S_SCAN_MINB 4      // pair scan: 64 registers (a few spills), 4 CTAs of 256 threads per SM: project 43.8 -> 42.7 ms against the unconstrained 94-register build
 #endif
 #ifndef R2S_PL_MINB
 #define R2S_PL_MINB 4      // resident CTAs per SM the projection kernel is compiled for: 4 = 128 registers (solve 36.1 ms), 5 = 96 registers with spills (37.5), 3 = 167 registers (42.3); tools/gpu_ab_libs.sh
