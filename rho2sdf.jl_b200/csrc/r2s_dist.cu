@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128, WANT_XP ? (BOX ? 4 : 2) : 4) k_project_he
 //                  with boundary-face elements (those go to the pair buffer un-pruned: k_assemble replays them in element order)
 //   k_pair_scan<1> pass B, after pass A has been projected: the other pairs, kept only if their bound is below dist[] so far
 //   k_project_list one LANE per listed pair (dense warps whatever was pruned), result by atomicMin / into the pair buffer.
-struct BoxRec {
+struct __align__(16) BoxRec {      // 16-byte aligned: the projection kernel reads its doubles two at a time
   double R[8];               // monomial coefficients of rho
   double c[3], h[3];         // X_d = c_d + h_d xi_d in element-local coordinates (node 0 at the origin)
   double org[3];             // node 0

@@ -30,13 +30,6 @@ static int *iso_trace = nullptr; static long iso_trace_n = 0, iso_trace_cap = 0;
 #endif
 
 namespace iso {
-// a / b, bit for bit, with a shortcut for a == 0 (finite non-zero b): nvcc's FP64 division takes its out-of-line slow path whenever the
-// numerator or the quotient is zero or tiny, and exact zeros are common here (a coordinate sitting on its bound, a vanishing residual).
-// ncu, k_project_list: the slow path was 11.7 % of all executed instructions at 7.5 of 32 lanes.
-__host__ __device__ __forceinline__ double zdiv(double a, double b) {
-  if (a == 0.0 && b != 0.0 && fabs(b) < INFINITY) return copysign(0.0, a) * copysign(1.0, b);      // +-0 with the sign of the quotient (a NaN / Inf / zero b takes the division)
-  return a / b;
-}
 
 struct Eval {
   double f, g, F[3], c[3], a[3];
@@ -200,7 +193,7 @@ __device__ __forceinline__ bool restore(const EL &A, double rho_t, double xi[3],
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) den = fma(a[i], a[i], den);
     if (!(den > 0.0)) return false;
-    double s = zdiv(g, den);
+    double s = g / den;
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) {
@@ -223,7 +216,7 @@ __device__ __forceinline__ void tangent2(const Eval &E, double lam, double d[3])
   double kgn = zi * fma(E.Hgn[I][I], zi, E.Hgn[I][J] * zj) + zj * fma(E.Hgn[I][J], zi, E.Hgn[J][J] * zj);
   if (!(kap > 1e-8 * kgn)) kap = kgn;
   if (!(kap > 0.0)) return;
-  double t = zdiv(-fma(zi, E.c[I], zj * E.c[J]), kap);
+  double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
   d[I] = t * zi; d[J] = t * zj;
 }
 // tangent step, all three free; null-space basis built around component K (largest |a_K|), U=(K+1)%3, V=(K+2)%3
@@ -248,7 +241,7 @@ __device__ __forceinline__ void tangent3(const Eval &E, double lam, double d[3])
   double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
   if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
   if (!(det > 0.0 && m11 > 0.0)) return;
-  double y1 = zdiv(m22 * r1 - m12 * r2, det), y2 = zdiv(m11 * r2 - m12 * r1, det);
+  double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
 #pragma unroll
   for (int i = 0; i < 3; i++) d[i] = fma(y1, z1[i], y2 * z2[i]);
 }
@@ -265,7 +258,7 @@ __device__ __forceinline__ void tangent2(const HexBox::EvalT &E, double lam, dou
   double kgn = zi * (hii * zi) + zj * (hjj * zj);
   if (!(kap > 1e-8 * kgn)) kap = kgn;
   if (!(kap > 0.0)) return;
-  double t = zdiv(-fma(zi, E.c[I], zj * E.c[J]), kap);
+  double t = -fma(zi, E.c[I], zj * E.c[J]) / kap;
   d[I] = t * zi; d[J] = t * zj;
 }
 template <int K>
@@ -282,7 +275,7 @@ __device__ __forceinline__ void tangent3(const HexBox::EvalT &E, double lam, dou
   double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
   if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
   if (!(det > 0.0 && m11 > 0.0)) return;
-  const double y1 = zdiv(m22 * r1 - m12 * r2, det), y2 = zdiv(m11 * r2 - m12 * r1, det);
+  const double y1 = (m22 * r1 - m12 * r2) / det, y2 = (m11 * r2 - m12 * r1) / det;
   d[U] = y1 * aK; d[V] = y2 * aK; d[K] = -fma(y1, aU, y2 * aV);
 }
 // MODE bit 1: ONE code path for every tangent-step case.  The three tangent3<K> and the three tangent2<I,J> variants
@@ -338,7 +331,9 @@ __device__ __forceinline__ void tangent_step_rot(const EV &E, const int fix[3], 
   double det = m11 * m22 - m12 * m12, detg = g11 * g22 - g12 * g12;
   if (!(m11 > 1e-8 * g11 && det > 1e-8 * detg)) { m11 = g11; m12 = g12; m22 = g22; det = detg; }
   if (!(det > 0.0 && m11 > 0.0)) return;
-  const double y1 = zdiv(m22 * r1 - m12 * r2, det), y2 = zdiv(m11 * r2 - m12 * r1, det);
+  // Two free variables: m12 = 0, m22 = 1, r2 = 0, so y2 = (+0) / det = +0 exactly -- and a zero numerator sends nvcc's FP64 division
+  // down its out-of-line slow path (ncu, k_project_list: 11.7 % of all executed instructions at 7.5 of 32 lanes came from there).
+  const double y1 = (m22 * r1 - m12 * r2) / det, y2 = with3 ? (m11 * r2 - m12 * r1) / det : 0.0;
   const double dU = y1 * aK, dV = y2 * aK, dK = -fma(y1, aU, y2 * aV);
   // rotate back: component i receives dK / dU / dV according to its role
 #pragma unroll
@@ -421,7 +416,7 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
 #pragma unroll
       for (int i = 0; i < 3; i++) if (!fix[i]) { num = fma(E.a[i], E.c[i], num); den = fma(E.a[i], E.a[i], den); }
       ISO_COUNT(5);
-      if (den > atol2) { lam = zdiv(-num, den); ISO_COUNT(3); tangent_step<typename EL::EvalT, MODE>(E, fix, lam, d); }
+      if (den > atol2) { lam = -num / den; ISO_COUNT(3); tangent_step<typename EL::EvalT, MODE>(E, fix, lam, d); }
       else {
         ISO_TRACE(17);
         double llo = -INFINITY, lhi = INFINITY, akk = 0.0, ckk = 0.0; bool anyk = false;
@@ -436,7 +431,7 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
         d[0] = d[1] = d[2] = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; i++) if (!fix[i]) {
-          double h = hdiag(E, i); if (h > 0.0) d[i] = zdiv(-E.c[i], h);    // Hess g has a zero diagonal
+          double h = hdiag(E, i); if (h > 0.0) d[i] = -E.c[i] / h;    // Hess g has a zero diagonal
         }
       }
       bool refix = false;
@@ -463,8 +458,8 @@ __device__ __forceinline__ int proj_iter(const EL &A, const double x[3], double 
 #pragma unroll
     for (int i = 0; i < 3; i++) if (!fix[i]) {
       // ties between blocking bounds (within 1e-12) go to the lower index, so that round-off cannot choose the face
-      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = zdiv(1.0 - xi[i], d[i]); if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
-      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = zdiv(-1.0 - xi[i], d[i]); if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
+      if (d[i] > 0 && xi[i] + d[i] > 1.0) { double t = (1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
+      if (d[i] < 0 && xi[i] + d[i] < -1.0) { double t = (-1.0 - xi[i]) / d[i]; if (t < amax * (1.0 - 1e-12)) { amax = t; blk = i; } }
     }
     double slope = fma(E.c[2], d[2], fma(E.c[1], d[1], E.c[0] * d[0]));
     if (!(slope < 0.0)) { S.force = true; S.it++; return 0; }      // no descent left on this face: go to the multiplier test
