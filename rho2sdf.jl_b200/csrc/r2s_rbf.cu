@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(16 * S3_X / NO) k_stencil81_tma(const __grid_c
         if (in[o]) { if (!vec) out[gi + o] = acc[0][o]; dsum += (double)ctr0[o] * (double)acc[0][o]; }
       if (BETA && F.enabled) {      // fused halo exchange: my boundary planes of c go straight into the neighbours' arrays over NVLink
 #pragma unroll
-        for (int o = 0; o < NO; o++) {
-          if (gi >= F.lo0 && gi < F.lo1 && in[o]) F.c_lower[gi + o] = acc[0][o];
-          if (gi >= F.hi0 && gi < F.hi1 && in[o]) F.c_upper[gi + o] = acc[0][o];
+        for (int o = 0; o < NO; o++) {      // per OUTPUT: gi itself may lie two columns left of the row (gx = -2 in the first CTA column)
+          if (gi + o >= F.lo0 && gi + o < F.lo1 && in[o]) F.c_lower[gi + o] = acc[0][o];
+          if (gi + o >= F.hi0 && gi + o < F.hi1 && in[o]) F.c_upper[gi + o] = acc[0][o];
         }
       }
     }

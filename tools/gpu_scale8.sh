@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29741 tests/slab_parity_ranks.py 48 > gpurun_out/slab_parity_8.log 2>&1; echo "slab parity (8 ranks) rc=$?"
 grep -E "FAIL|OK|Error" gpurun_out/slab_parity_8.log | head -8
-for n in 8 4; do
+for n in ${SCALE_NS:-8 4}; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2975$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
   echo "N=$n rc=$?"
   python - gpurun_out/scale_$n.json <<'PY'
