@@ -275,7 +275,8 @@ __global__ void k_p2p_allreduce(P2PBox *mine, P2PBox *const *peers, int rank, in
   if (p < R) {
     volatile unsigned long long *src = mine->slot[par][p];
     unsigned spin = 0;
-    while (src[P2P_SLOT_WORDS - 1] != (unsigned long long)seq) { if (++spin > P2P_MAX_SPIN) { mine->error = 1; break; } }
+    const unsigned lim = mine->error ? 1024u : P2P_MAX_SPIN;      // after a first time-out the later waits give up quickly
+    while (src[P2P_SLOT_WORDS - 1] != (unsigned long long)seq) { if (++spin > lim) { mine->error = 1; break; } }
   }
   __threadfence_system();
   __syncthreads();
@@ -488,6 +489,6 @@ int r2s_p2p_check(r2s_ctx *ctx) {
   if (!ctx->p2p) return 0;
   unsigned long long e = 0;
   if (r2s_readback(ctx, &e, &((P2PBox *)ctx->p2p_box)->error, sizeof(e))) return 1;
-  if (e) FAIL("peer-memory exchange timed out (a rank did not arrive); set R2S_P2P=0 to use NCCL only");
+  if (e) FAIL("peer-memory exchange timed out (a rank did not arrive; the communicator is unusable afterwards); set R2S_P2P=0 to use NCCL only");
   return 0;
 }

@@ -33,7 +33,8 @@ __device__ __forceinline__ double p2p_allreduce_cta(const P2PFuse &F, unsigned s
     dst[P2P_SLOT_WORDS - 1] = (unsigned long long)seq;
     volatile unsigned long long *src = F.mine->slot[par][p];
     unsigned spin = 0;
-    while (src[P2P_SLOT_WORDS - 1] != (unsigned long long)seq) { if (++spin > P2P_MAX_SPIN) { F.mine->error = 1; break; } }
+    const unsigned lim = F.mine->error ? 1024u : P2P_MAX_SPIN;      // after a first time-out the later waits give up quickly: the call is failing anyway
+    while (src[P2P_SLOT_WORDS - 1] != (unsigned long long)seq) { if (++spin > lim) { F.mine->error = 1; break; } }
   }
   __threadfence_system();
   __syncthreads();
@@ -60,7 +61,8 @@ __device__ __forceinline__ void p2p_wait_halo_flags(const P2PFuse &F) {
     if (!(side == 0 ? F.box_lower : F.box_upper)) continue;
     volatile unsigned long long *f = &F.mine->halo_flag[par][side];
     unsigned spin = 0;
-    while (*f != (unsigned long long)F.seq_halo) { if (++spin > P2P_MAX_SPIN) { F.mine->error = 1; break; } }
+    const unsigned lim = F.mine->error ? 1024u : P2P_MAX_SPIN;
+    while (*f != (unsigned long long)F.seq_halo) { if (++spin > lim) { F.mine->error = 1; break; } }
   }
   __threadfence_system();
 }

@@ -293,7 +293,7 @@ static int stencil_tensor_map(r2s_ctx *ctx, CUtensorMap *map, const float *base,
   if (rc != CUDA_SUCCESS) { char b[96]; snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc); FAIL(b); }
   return 0;
 }
-// CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, converged flag, iterations}
+// CG scalar bookkeeping (IterativeSolvers.cg, CGIterable): scal = {beta, alpha, residual, prev_residual, tol, converged flag, iterations, initial residual}
 __global__ void k_sum_to(const double *__restrict__ part, int n, double *__restrict__ dst) {
   __shared__ double sh[256];
   double a = 0; for (int i = threadIdx.x; i < n; i += 256) a += part[i];
@@ -310,7 +310,7 @@ __device__ __forceinline__ void cg_close_iteration(float *scal, double rr) {    
   scal[3] = prev; scal[2] = res; scal[0] = res * res / (prev * prev);
   scal[6] += 1.0f;
   if (res <= scal[4]) scal[5] = 1.0f;
-  else if (!(res < INFINITY)) scal[5] = 2.0f;      // NaN / Inf residual (bad input or a failed exchange): stop instead of iterating to maxiter = n
+  else if (!(res < 1.0e8f * scal[7])) scal[5] = 2.0f;      // NaN / Inf residual, or one that has grown by 10^8 (bad input or a failed exchange -- CG on an SPD system does not do that): stop instead of iterating to maxiter = n
 }
 __global__ void __launch_bounds__(256) k_cg_update(i64 n, i64 o_lo, i64 o_hi, float *__restrict__ scal, const double *__restrict__ uc, const float *__restrict__ u,
                                                    const float *__restrict__ c, float *__restrict__ x, float *__restrict__ r, double *__restrict__ partial, unsigned *__restrict__ ticket,
@@ -346,7 +346,7 @@ __global__ void k_cg_residual(float *scal, const double *rr) {      // several r
 __global__ void k_cg_init(float *scal, const double *rr) {
   float res = (float)sqrt(*rr);
   scal[2] = res; scal[3] = 1.0f; scal[4] = sqrtf(FLT_EPSILON) * res; scal[0] = res * res / (1.0f * 1.0f); scal[1] = 0.0f;
-  scal[6] = 0.0f; scal[5] = (res <= scal[4]) ? 1.0f : 0.0f;
+  scal[6] = 0.0f; scal[5] = (res <= scal[4]) ? 1.0f : 0.0f; scal[7] = res;      // [7]: the initial residual (divergence guard)
 }
 __global__ void __launch_bounds__(256) k_dot_self(i64 n, const float *__restrict__ a, double *__restrict__ partial) {
   __shared__ double red[8];
@@ -1130,7 +1130,7 @@ int r2s_dev_rbf(r2s_ctx *ctx, int is_interp, int smooth, double rbf_cut, double 
       if (!probed && launched > 3) { probed = true; for (int q = 0; q < 4; q++) CK(cudaEventElapsedTime(&ctx->rep.cg_probe[q], ctx->ev_probe[q], ctx->ev_probe[q + 1])); }
     }
     ctx->skip_flag = nullptr;
-    if (hs[5] == 2.0f) FAIL("RBFs_smoothing: the CG residual is not finite (non-finite SDF input, or a peer-memory exchange failed)");
+    if (hs[5] == 2.0f) FAIL("RBFs_smoothing: the CG residual is not finite or diverges (non-finite SDF input, or a peer-memory exchange failed)");
     iters = (int)hs[6];
     wgt = x;
     if (r2s_halo_exchange_f32(ctx, x, pl, k0, k1, nz, 2, 3)) return 1;      // the fine evaluation reaches 3 planes up
