@@ -228,28 +228,56 @@ def run_gpu(args):
     n = args.n
     with torch.cuda.stream(stream):
         X, IEN, rho = workload(n)
-        mesh = r2s.Mesh(X, IEN, rho, element_type=r2s.HEX8, device=local, stream=stream.cuda_stream)      # untimed: the reference builds Mesh before its timer
         grid = r2s.Grid(X.min(0), X.max(0), 2 * n, 3)
-        rho_n = r2s.DenseInNodes(mesh, rho)
-        mesh._use_grid(grid)
-        c = mesh.ctx
         nz = int(grid.N[2]) + 1
-        k0, k1 = 0, nz
+
+        def build():      # untimed: the reference builds Mesh before its timer
+            mesh = r2s.Mesh(X, IEN, rho, element_type=r2s.HEX8, device=local, stream=stream.cuda_stream)
+            rho_n = r2s.DenseInNodes(mesh, rho)
+            mesh._use_grid(grid)
+            c = mesh.ctx
+            c.check(c.lib.r2s_upload_nodal_densities(c.h, rho_n.ctypes.data_as(C.c_void_p)))
+            k0, k1 = 0, nz
+            if world > 1:
+                k0, k1 = r2s.slab_partition(nz, world)[rank]
+                r2s.init_slab_comm(c, rank, world, k0, k1)
+            return mesh, rho_n, c, k0, k1
+        mesh, rho_n, c, k0, k1 = build()
         p = r2s.Params(); c.lib.r2s_default_params(C.byref(p))
         p.rho_t, p.smooth, p.rbf_interp, p.remove_artifacts = 0.5, 2, 1, 1
         p.target_volume, p.final_volume = mesh.V_frac * mesh.V_domain, 1
-        c.check(c.lib.r2s_upload_nodal_densities(c.h, rho_n.ctypes.data_as(C.c_void_p)))
         n_balance = 0
+        transport = None
         if world > 1:
-            parts = r2s.slab_partition(nz, world)
-            k0, k1 = parts[rank]
-            r2s.init_slab_comm(c, rank, world, k0, k1)
-            # load balancing during warm-up: the planes next to the mesh boundary carry the boundary-face work, so equal plane
-            # counts are not equal work.  Measure the collective-free stages per rank, re-cut the slabs by cumulative cost.
-            n_balance = 0 if args.no_balance else min(2, max(0, args.warmup - 1))
-            for _ in range(n_balance):
+            # One untimed call first.  If the peer-memory transport fails on this box (an error on any rank: time-out, diverging CG), every
+            # rank abandons its context and continues on a fresh one with NCCL only (R2S_P2P=0); the line says which transport was measured.
+            transport = "nccl" if os.environ.get("R2S_P2P", "1") == "0" else "peer-memory + nccl"
+            ok, err = 1.0, ""
+            try:
                 rep = r2s.Report()
                 c.check(c.lib.r2s_pipeline_resident(c.h, C.byref(p), C.byref(rep)))
+            except r2s.R2SError as e:
+                ok, err = 0.0, str(e)
+            flag = torch.tensor([ok], dtype=torch.float64, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() < 0.5:
+                if transport == "nccl":
+                    raise SystemExit("bench.py: the multi-GPU pipeline failed on the NCCL transport: %s" % err)
+                print("rank %d: peer-memory transport failed (%s); continuing with R2S_P2P=0" % (rank, err or "another rank failed"), file=sys.stderr, flush=True)
+                os.environ["R2S_P2P"] = "0"
+                failed = (mesh, c)      # kept alive on purpose: tearing a failed communicator down is not worth the risk inside a benchmark
+                mesh, rho_n, c, k0, k1 = build()
+                transport = "nccl (peer-memory transport failed: %s)" % (err or "on another rank")[:160]
+            # load balancing during warm-up: the planes next to the mesh boundary carry the boundary-face work, so equal plane
+            # counts are not equal work.  Measure the collective-free stages per rank, re-cut the slabs by cumulative cost.  The transport
+            # check above is the first of these warm-up calls.
+            n_balance = 0 if args.no_balance else min(2, max(0, args.warmup - 1))
+            parts = r2s.slab_partition(nz, world)
+            first = rep if flag.item() >= 0.5 else None
+            for it in range(n_balance):
+                if it > 0 or first is None:
+                    rep = r2s.Report()
+                    c.check(c.lib.r2s_pipeline_resident(c.h, C.byref(p), C.byref(rep)))
                 free = rep.ms_bin + rep.ms_project + rep.ms_assemble + rep.ms_sign
                 rbf = rep.ms_rbf_prep + rep.ms_cg + rep.ms_lsf + rep.ms_threshold + rep.ms_fine + rep.ms_volume
                 mine = torch.tensor([free, rbf, float(k0), float(k1)], dtype=torch.float64, device="cuda")
@@ -263,6 +291,8 @@ def run_gpu(args):
                 parts = r2s.slab_partition(nz, world, plane_cost=cost)
                 k0, k1 = parts[rank]
                 c.check(c.lib.r2s_set_slab(c.h, k0, k1))
+            if n_balance == 0 and first is not None:
+                n_balance = 1      # the check itself was a warm-up call
         nfine = fine_voxels(grid, 2)
         fdims = [int(v) * 2 + 1 for v in grid.N]
         # slab-local output sizes (planes this rank returns to the host in the e2e leg)
@@ -406,7 +436,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": nfine / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(base_config(n), parallelism="zslab%d" % world, slab_planes=[int(b - a) for a, b in parts] if world > 1 else [nz], l2_policy="inputs larger than L2 (working set %.1f GB per step)" % ((rep.n_pairs * 8 + grid.ngp * 40 + nfine * 4) / 1e9)),
+            "config": dict(base_config(n), parallelism="zslab%d" % world, slab_planes=[int(b - a) for a, b in parts] if world > 1 else [nz], **({"transport": transport} if transport else {}), l2_policy="inputs larger than L2 (working set %.1f GB per step)" % ((rep.n_pairs * 8 + grid.ngp * 40 + nfine * 4) / 1e9)),
             "e2e": {"value": nfine / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(rho_n.nbytes) * world,
                     "d2h_bytes_per_step": int(grid.ngp * 8 + nfine * 4), "api": "r2s_pipeline_slab (pinned host buffers)"},
             "gpu_launches": int(sum(r.launches for r in reps)),
