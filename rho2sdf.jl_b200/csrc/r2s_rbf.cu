@@ -983,10 +983,6 @@ __global__ void k_unew_halo(i64 n1, i64 off2, i64 n2, const float *__restrict__ 
   i64 i = v < n1 ? v : off2 + (v - n1);
   unew[i] = r[i] + scal[0] * u[i];
 }
-__global__ void k_add_scalar(i64 n, float *__restrict__ a, float s) {
-  i64 v = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (v < n) a[v] = a[v] + s;
-}
 
 static int upload_taps(r2s_ctx *ctx, int sm, double rbf_cut, double cell) {
   TapTable T; static float W[8][96];
